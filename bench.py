@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of uammd_b200 (contract in the task statement).
+
+Workload (BASELINE.json configs[1]): PairForces<LJ, CellList> + VerletNVE molecular dynamics, N = 1e6
+particles, rho = 0.8, rc = 2.5 sigma, fp32, one B200. A "step" is one VerletNVE::forwardTime():
+cell-list rebuild + LJ forces + velocity-Verlet update. Metric: MD steps/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles N]
+
+Timing protocol: W untimed warm-up steps, then exactly K steps, each bracketed by CUDA events on the
+launching stream with a 256 MiB L2-evicting write before every step (the working set, ~90 MB, would
+otherwise sit in the 126 MB L2); ms_per_step = sum(step times)/K, max over ranks. `value_back_to_back`
+reports the same K steps enqueued back to back (how an application runs them).
+
+Multi GPU (N > 1, launched by torchrun): path 1 has no multi-GPU decomposition yet -> "replicas only":
+each rank integrates its own 1e6-particle system (weak scaling), value = sum over ranks of steps/s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RHO, RC, DT, TEMP = 0.8, 2.5, 0.005, 1.0
+ALG_BYTES_PAIR = 52          # per particle: R sortPos 16 + R groupIndex 4 + RMW force 32
+ALG_BYTES_STEP = 216         # per particle and step: build 36 + traverse 52 + integrate 112 + zero 16
+FLOP_PER_CANDIDATE = 25
+FP32_PEAK_TFLOPS = 74.4      # 148 SM x 128 lanes x 2 x 1.965 GHz
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def workload(N):
+    from uammd_b200 import synthetic as syn
+    Lb = syn.lj_box_length(N, RHO)
+    return Lb, syn.fcc_lattice(N, Lb), syn.maxwell_velocities(N, TEMP, seed=7)
+
+
+def run_reference(args):
+    """Reference arm: the UNMODIFIED reference (PairForces<Potential::LJ, CellList> + VerletNVE) compiled from
+    /root/reference by oracle/Makefile into oracle/_ref/ref_lj. UAMMD has no CPU implementation - its only
+    implementation of this path is CUDA - so this arm runs on the same B200, same workload, same protocol."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_lj")
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_lj was not built (no reference tree at build time)"}))
+        return 0
+    N = args.particles
+    Lb, pos, vel = workload(N)
+    with tempfile.TemporaryDirectory() as td:
+        pos.tofile(os.path.join(td, "pos.bin"))
+        vel.tofile(os.path.join(td, "vel.bin"))
+        cmd = [exe, "md", str(N), str(Lb), str(Lb), str(Lb), str(RC), "1", "1", str(DT), str(args.warmup + args.equil),
+               str(args.steps), "1", "1", os.path.join(td, "pos.bin"), os.path.join(td, "vel.bin"), "-"]
+        t0 = time.time()
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=3000).stdout
+        wall = time.time() - t0
+    summ = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    s = [x for x in summ if x.get("mode") == "md_summary"][0]
+    ms = s["ms_per_step_mean"]
+    val = 1000.0 / ms
+    line = {
+        "impl": "reference", "metric": "MD steps/s @1e6 LJ particles", "value": val, "unit": "steps/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
+                   "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
+                   "device": "B200 GPU: the reference's only implementation of this path is CUDA (unmodified, sm_100a build)"},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": 1, "kind": "reference",
+                         "sample": f"{args.steps} steps of the full workload; 1 host thread driving the reference's CUDA kernels"},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline(N, nsteps=3):
+    """The oracle's OpenMP restatement of the same MD step on the host cores (bounded sample)."""
+    from oracle import oracle as orc
+    from uammd_b200 import synthetic as syn
+    Lb, pos, vel = workload(N)
+    md = orc.MDOracle((Lb,) * 3, RC, syn.lj_params(), DT, pos, vel)
+    md.step(1)
+    t0 = time.time()
+    md.step(nsteps)
+    dt = time.time() - t0
+    return {"value": nsteps / dt, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{nsteps} steps of the N={N} workload (OpenMP, all host cores) after 1 warm-up step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--particles", type=int, default=1_000_000)
+    ap.add_argument("--equil", type=int, default=300, help="untimed equilibration steps (melts the FCC start)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fcm", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import uammd_b200
+    from uammd_b200.md import Box, LJ, LJMD, PairForces
+
+    uammd_b200.lib()  # no CPU fallback: raises if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N = args.particles
+    Lb, pos, vel = workload(N)
+    pot = LJ()
+    pot.setPotParameters(0, 0, cutOff=RC, sigma=1.0, epsilon=1.0)
+    box = Box(Lb)
+    md = LJMD(box, pot, DT)
+    p = torch.from_numpy(pos).to(dev)
+    v = torch.from_numpy(vel).to(dev)
+    f = torch.zeros(N, 4, device=dev)
+    scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = uammd_b200.lib()
+
+    md.run(p, v, f, args.equil + args.warmup)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, L2 evicted before each, CUDA events on the launching stream ----
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = lib.ub200_launch_count()
+    barrier()
+    with ClockSampler(local) as clk:
+        for a, b in evs:
+            scrub.fill_(1)
+            a.record()
+            md.run(p, v, f, 1)
+            b.record()
+        barrier()
+    launches = lib.ub200_launch_count() - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in evs]
+    ms_per_step = float(np.sum(ms_steps) / args.steps)
+
+    # same K steps back to back (L2 warm, launch overheads overlapped)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    md.run(p, v, f, args.steps)
+    e1.record()
+    barrier()
+    ms_b2b = e0.elapsed_time(e1) / args.steps
+
+    # ---- roofline of the dominant kernel (LJ cell traversal), timed alone on its stream ----
+    pf = PairForces(pot, box)
+    pf.nl.update(p, box, RC)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    for a, b in kev:
+        scrub.fill_(2)
+        a.record()
+        pf.sumWithCurrentList(force=f)
+        b.record()
+    torch.cuda.synchronize()
+    t_pair_ms = float(np.median([a.elapsed_time(b) for a, b in kev]))
+    pf.nl.update(p, box, RC)
+    md.prepared = False  # f was accumulated into by the roofline probe: recompute before any further stepping
+    peak, peak_src = measured_peaks()
+    ncells = int(np.prod(pf.nl.cellDim))
+    cand = 27.0 * N / ncells
+    pair_gbs = ALG_BYTES_PAIR * N / (t_pair_ms * 1e-3) / 1e9
+    pair_tflops = cand * FLOP_PER_CANDIDATE * N / (t_pair_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "ljCellTraversal", "bound": "hbm", "achieved": pair_gbs, "peak": peak, "unit": "GB/s",
+        "frac": pair_gbs / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": t_pair_ms,
+        "algorithmic_bytes_per_launch": ALG_BYTES_PAIR * N,
+        "note": "the pair kernel is FP32-ALU/shared-memory bound, not HBM bound (SURVEY 8(d)); see fp32 and pipeline",
+        "fp32": {"achieved_tflops": pair_tflops, "peak_tflops": FP32_PEAK_TFLOPS, "frac": pair_tflops / FP32_PEAK_TFLOPS,
+                 "candidates_per_particle": cand, "flop_per_candidate": FLOP_PER_CANDIDATE},
+        "pipeline": {"bytes_per_step": ALG_BYTES_STEP * N, "achieved": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9,
+                     "unit": "GB/s", "frac": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- e2e: the public host-buffer entry point, state round trip over PCIe every step ----
+    hp, hv, hf = p.cpu().pin_memory(), v.cpu().pin_memory(), torch.zeros(N, 4).pin_memory()
+    md2 = LJMD(box, pot, DT)
+    for _ in range(3):
+        md2.runHost(hp, hv, hf, 1)
+    n_e2e = max(10, min(args.steps, 50))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        md2.runHost(hp, hv, hf, 1)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    # device-resident state through the same public API, one scalar (kinetic energy) read back per step
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        md.run(p, v, f, 1)
+        ke = float((v * v).sum()) * 0.5
+    e2e_res_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+
+    # ---- aggregate over ranks ----
+    t = torch.tensor([ms_per_step, ms_b2b, e2e_ms, e2e_res_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step, ms_b2b, e2e_ms, e2e_res_ms = (float(x) for x in t.cpu())
+    if rank == 0:
+        line = {
+            "metric": "MD steps/s @1e6 LJ particles", "value": world * 1000.0 / ms_per_step, "unit": "steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
+                       "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no path-1 decomposition yet)"},
+            "value_back_to_back": world * 1000.0 / ms_b2b,
+            "clocks": clk.summary(),
+            "e2e": {"value": world * 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": N * 28,
+                    "d2h_bytes_per_step": N * 44,
+                    "what": "ub200_md_lj_nve_run_host_f32: pinned host pos+vel uploaded, forces recomputed, 1 step, pos+vel+force downloaded, every step"},
+            "e2e_resident": {"value": world * 1000.0 / e2e_res_ms, "unit": "steps/s", "d2h_bytes_per_step": 4,
+                             "what": "same API with device-resident state, kinetic energy read back every step", "last_ke": ke},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(N)
+        if not args.no_fcm and world == 1:
+            try:
+                from uammd_b200 import fcm_bench
+                line["fcm"] = fcm_bench.run(dev, peak)
+            except ImportError:
+                pass
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,128 @@
+/* uammd_b200 - C ABI of the B200-native (sm_100a) engine for UAMMD's two data-parallel hot paths.
+ *
+ * UAMMD has no FFI: its extension points are C++ template concepts and virtual classes compiled into
+ * the user's translation unit. The drop-in therefore has two layers: the C++14 glue
+ * headers in include/uammd_b200/ (classes satisfying UAMMD's Interactor / NeighbourList / BDHI-Method
+ * concepts) and this C ABI, which is everything those glue classes call. Each entry point cites the
+ * reference interface it replaces (file:line relative to the reference's src/).
+ *
+ * Conventions
+ *  - all pointers named d_* are DEVICE pointers owned by the caller (UAMMD's ParticleData), layouts are
+ *    the reference's: pos real4 {x,y,z,type}, force real4 {fx,fy,fz,_}, vel real3, energy/virial real.
+ *  - every call is asynchronous on the given CUDA stream (passed as void* == cudaStream_t); no hidden
+ *    device synchronisation; device scratch is owned by the handle and only (re)allocated when N or the
+ *    cell grid grows.
+ *  - return value: 0 = ok, <0 = error (UB200_ERR_*); ub200_error_string() describes it. No exceptions
+ *    cross the boundary; the glue converts codes into the reference's exceptions.
+ *  - precision: the reference fixes `real` per translation unit (-DDOUBLE_PRECISION, global/defines.h:9-11)
+ *    so symbols come in _f32 / _f64 flavours.
+ */
+#ifndef UAMMD_B200_H
+#define UAMMD_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB200_OK 0
+#define UB200_ERR_INVALID_ARGUMENT (-1)
+#define UB200_ERR_CUDA (-2)
+#define UB200_ERR_ALLOC (-3)
+#define UB200_ERR_GRID_TOO_LARGE (-4)
+#define UB200_ERR_NOT_BUILT (-5)
+#define UB200_ERR_UNSUPPORTED (-6)
+
+const char *ub200_error_string(int code);
+/* last cudaError_t seen by the calling thread inside the library (0 if none) */
+int ub200_last_cuda_error(void);
+/* library version / build info: "uammd_b200 <ver> sm_100a" */
+const char *ub200_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path 1a: cell list.  Replaces CellList::update / CellListBase::update
+ * (Interactor/NeighbourList/CellList.cuh:145-163, CellList/CellListBase.cuh:124-140) and the
+ * ParticleSorter Morton sort beneath it (utils/ParticleSorter.cuh:156-164,243-274).
+ * Output arrays are bit-identical to the reference's CellListData (CellListBase.cuh:145-160):
+ * sortPos, groupIndex (stable Morton order), cellStart (+VALID_CELL epoch bias), cellEnd.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_celllist ub200_celllist;
+
+typedef struct {
+  const uint32_t *d_cellStart; /* [ncells] first sorted index + VALID_CELL; < VALID_CELL means empty */
+  const int *d_cellEnd;        /* [ncells] last sorted index + 1 (only meaningful for non-empty cells) */
+  const void *d_sortPos;       /* real4[N] positions in sorted order */
+  const int *d_groupIndex;     /* int[N] sorted slot -> particle (group) index */
+  uint32_t VALID_CELL;
+  int cellDim[3];
+  int numberParticles;
+  /* engine-native view (dense, no epoch trick): bins in Morton-code space */
+  const uint32_t *d_binStart;  /* [nbins+1] exclusive prefix of particles per Morton code */
+  int nbins;
+} ub200_celllist_view;
+
+int ub200_celllist_create(ub200_celllist **out);
+int ub200_celllist_destroy(ub200_celllist *cl);
+
+/* cellDim as CellList::createUpdateGrid computes it (CellList.cuh:100-126): int(L/rc), <=3 -> 1 */
+int ub200_neighbour_celldim_f32(const float L[3], float rc, int cellDim[3]);
+
+/* d_pos: real4[*]; d_groupIdx: optional int[N] indirection (ParticleGroup::getIndexIterator,
+ * ParticleData/ParticleGroup.cuh:304-327) or NULL for identity. periodic[d]==0 marks a non periodic
+ * dimension (Box::setPeriodicity utils/Box.cuh:32-39). */
+int ub200_celllist_build_f32(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx, int N,
+                             const float L[3], const int periodic[3], const int cellDim[3], void *stream);
+int ub200_celllist_view_get(ub200_celllist *cl, ub200_celllist_view *view);
+/* reads back (synchronising the stream) the NaN / out-of-box flag of the last build
+ * (CellList_ns::fillCellList errorFlag, CellListBase.cuh:68-95,258-265). 0 = clean. */
+int ub200_celllist_error_flag(ub200_celllist *cl, void *stream, int *flag);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path 1b: pair traversal with the LJ transverser. Replaces CellList::transverseList
+ * (CellList.cuh:165-182 -> NeighbourList/common.cuh:10-34) specialised for
+ * Potential::Radial<LJFunctor>::Transverser (Potential/RadialPotential.cuh:107-127, Potential.cuh:25-83).
+ * params: host array [ntypes*ntypes] of {cutOff2, sigma2, epsilonDivSigma2, shift}
+ * (LJFunctor::PairParameters, Potential.cuh:31-35). Outputs ACCUMULATE (+=) like Transverser::set; any
+ * of d_force / d_energy / d_virial may be NULL (Interactor::Computables, Interactor/Interactor.cuh:94-103).
+ * d_globalIdx: optional group->global index map used for the output scatter (NULL = identity).
+ * ------------------------------------------------------------------------------------------------ */
+int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, float *d_energy,
+                     float *d_virial, const int *d_globalIdx, void *stream);
+
+/* DPD transverser (Potential/DPD.cuh:92-159). d_vel: real3[*] indexed by GLOBAL index like getInfo(pi).
+ * sigma = sqrt(2 T)/sqrt(dt) as DPD_impl computes it (:66,:84-92); seed/step are the Saru seeds (:129).
+ * idStride = N used in ij = min + N*max (int32 arithmetic, wraps like the reference). */
+int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
+                      uint32_t seed, uint32_t step, int idStride, void *d_force, const int *d_globalIdx,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path 1c: velocity Verlet. Replaces VerletNVE_ns::integrateGPU<1|2> (Integrator/VerletNVE.cu:64-85)
+ * and VerletNVE::resetForces (:152-158). d_mass may be NULL (defaultMass used). step==1 also drifts.
+ * ------------------------------------------------------------------------------------------------ */
+int ub200_nve_half_step_f32(void *d_pos, void *d_vel, const void *d_force, const float *d_mass,
+                            float defaultMass, const int *d_groupIdx, int N, float dt, int is2D, int step,
+                            void *stream);
+
+/* Fused engine for a whole VerletNVE::forwardTime with one PairForces<LJ,CellList> interactor
+ * (Integrator/VerletNVE.cu:174-188): kick+drift, cell list rebuild, LJ forces (written, not accumulated),
+ * second kick. d_force must hold F(t) on entry (see ub200_md_lj_nve_prepare_f32). nsteps steps are
+ * enqueued back to back on the stream. */
+typedef struct ub200_md ub200_md;
+int ub200_md_create(ub200_md **out);
+int ub200_md_destroy(ub200_md *md);
+int ub200_md_lj_nve_prepare_f32(ub200_md *md, void *d_pos, void *d_force, int N, const float L[3], float rc,
+                                const float *params, int ntypes, void *stream);
+int ub200_md_lj_nve_run_f32(ub200_md *md, void *d_pos, void *d_vel, void *d_force, int N, const float L[3],
+                            float rc, const float *params, int ntypes, float dt, int nsteps, void *stream);
+/* same through HOST buffers (pinned or pageable): H2D pos+vel, prepare, nsteps, D2H pos+vel+force; synchronises. */
+int ub200_md_lj_nve_run_host_f32(ub200_md *md, float *h_pos4, float *h_vel3, float *h_force4, int N,
+                                 const float L[3], float rc, const float *params, int ntypes, float dt,
+                                 int nsteps, void *stream);
+ub200_celllist *ub200_md_celllist(ub200_md *md);
+/* number of kernel launches the library enqueued since process start (bench.py's gpu_launches) */
+unsigned long long ub200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,258 @@
+"""TEST INFRASTRUCTURE - ctypes binding of the C restatement oracle (oracle/_build/liboracle.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module. Nothing under uammd_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+KERNEL_PESKIN3, KERNEL_PESKIN4, KERNEL_GAUSSIAN = 0, 1, 2
+
+
+class GridF(C.Structure):
+    _fields_ = [("L", C.c_float * 3), ("minusInvL", C.c_float * 3), ("cellDim", C.c_int * 3),
+                ("cellSize", C.c_float * 3), ("invCellSize", C.c_float * 3)]
+
+
+class GridD(C.Structure):
+    _fields_ = [("L", C.c_double * 3), ("minusInvL", C.c_double * 3), ("cellDim", C.c_int * 3),
+                ("cellSize", C.c_double * 3), ("invCellSize", C.c_double * 3)]
+
+
+class IBMKernel(C.Structure):
+    _fields_ = [("kind", C.c_int), ("support", C.c_int), ("h", C.c_double), ("prefactor", C.c_double),
+                ("tau", C.c_double), ("rmax", C.c_double)]
+
+
+def build():
+    """Compile the C oracle (gcc). Safe to call repeatedly."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_morton_hash.restype = C.c_uint32
+        _lib.orc_ibm_phi.restype = C.c_double
+        _lib.orc_ibm_phi.argtypes = [C.POINTER(IBMKernel), C.c_double]
+        _lib.orc_md_scratch_new.restype = C.c_void_p
+        _lib.orc_md_scratch_new.argtypes = [C.c_int, C.c_int]
+        _lib.orc_md_scratch_free.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def make_grid_f(L, cellDim, periodic=(1, 1, 1)):
+    g = GridF()
+    lib().orc_grid_init_f(C.byref(g), (C.c_float * 3)(*L), (C.c_int * 3)(*[int(p) for p in periodic]),
+                          (C.c_int * 3)(*cellDim))
+    return g
+
+
+def make_grid_d(L, cellDim, periodic=(1, 1, 1)):
+    g = GridD()
+    lib().orc_grid_init_d(C.byref(g), (C.c_double * 3)(*L), (C.c_int * 3)(*[int(p) for p in periodic]),
+                          (C.c_int * 3)(*cellDim))
+    return g
+
+
+def neighbour_celldim(L, rc):
+    cd = (C.c_int * 3)()
+    lib().orc_neighbour_celldim_f((C.c_float * 3)(*L), C.c_float(rc), cd)
+    return tuple(cd)
+
+
+def get_cells(grid, pos4):
+    pos4 = np.ascontiguousarray(pos4, dtype=np.float32)
+    out = np.zeros((pos4.shape[0], 3), dtype=np.int32)
+    c = (C.c_int * 3)()
+    l = lib()
+    for i in range(pos4.shape[0]):
+        l.orc_get_cell_f(C.byref(grid), _p(pos4[i]), c)
+        out[i] = c[:]
+    return out
+
+
+def celllist_build(grid, pos4):
+    pos4 = np.ascontiguousarray(pos4, dtype=np.float32)
+    N = pos4.shape[0]
+    ncells = grid.cellDim[0] * grid.cellDim[1] * grid.cellDim[2]
+    sortPos = np.empty((N, 4), np.float32)
+    index = np.empty(N, np.int32)
+    cs = np.empty(ncells, np.int32)
+    ce = np.empty(ncells, np.int32)
+    err = lib().orc_celllist_build_f(C.byref(grid), _p(pos4), N, _p(sortPos), _p(index), _p(cs), _p(ce))
+    return dict(sortPos=sortPos, index=index, cellStart=cs, cellEnd=ce, error=err)
+
+
+def lj_f32(grid, cl, params, ntypes, N, energy=False, virial=False):
+    force = np.zeros((N, 4), np.float32)
+    e = np.zeros(N, np.float32) if energy else None
+    v = np.zeros(N, np.float32) if virial else None
+    params = np.ascontiguousarray(params, np.float32)
+    lib().orc_lj_f32(C.byref(grid), _p(cl["sortPos"]), _p(cl["index"]), _p(cl["cellStart"]), _p(cl["cellEnd"]),
+                     N, _p(params), ntypes, _p(force), _p(e), _p(v))
+    return force, e, v
+
+
+def lj_f64(grid, cl, params, ntypes, N):
+    force = np.zeros((N, 3), np.float64)
+    e = np.zeros(N, np.float64)
+    v = np.zeros(N, np.float64)
+    a = np.zeros(N, np.float64)
+    params = np.ascontiguousarray(params, np.float32)
+    lib().orc_lj_f64(C.byref(grid), _p(cl["sortPos"]), _p(cl["index"]), _p(cl["cellStart"]), _p(cl["cellEnd"]),
+                     N, _p(params), ntypes, _p(force), _p(e), _p(v), _p(a))
+    return force, e, v, a
+
+
+def dpd_f32(grid, cl, vel3, A, gamma, sigma, rcut, seed, step, N):
+    force = np.zeros((N, 4), np.float32)
+    force64 = np.zeros((N, 3), np.float64)
+    vel3 = np.ascontiguousarray(vel3, np.float32)
+    lib().orc_dpd_f32(C.byref(grid), _p(cl["sortPos"]), _p(cl["index"]), _p(cl["cellStart"]), _p(cl["cellEnd"]),
+                      N, _p(vel3), C.c_float(A), C.c_float(gamma), C.c_float(sigma), C.c_float(rcut),
+                      C.c_uint32(seed), C.c_uint32(step), 0, _p(force), _p(force64))
+    return force, force64
+
+
+def saru3_u32(s1, s2, s3, n):
+    out = np.zeros(n, np.uint32)
+    lib().orc_saru3_u32(C.c_uint32(s1), C.c_uint32(s2), C.c_uint32(s3), n, _p(out))
+    return out
+
+
+def saru3_gf(s1, s2, s3, mean, std):
+    out = (C.c_float * 2)()
+    lib().orc_saru3_gf(C.c_uint32(s1), C.c_uint32(s2), C.c_uint32(s3), C.c_float(mean), C.c_float(std), out)
+    return out[0], out[1]
+
+
+def nve_half(pos4, vel3, force4, dt, mass, step):
+    lib().orc_nve_half_f32(_p(pos4), _p(vel3), _p(force4), pos4.shape[0], C.c_float(dt), C.c_float(mass), step)
+
+
+class MDOracle:
+    """CPU (OpenMP) VerletNVE + PairForces<LJ,CellList>; used as correctness oracle and cpu_baseline."""
+
+    def __init__(self, L, rc, params, dt, pos4, vel3):
+        self.L = (C.c_float * 3)(*L)
+        self.rc, self.dt = float(rc), float(dt)
+        self.params = np.ascontiguousarray(params, np.float32)
+        self.pos = np.ascontiguousarray(pos4, np.float32).copy()
+        self.vel = np.ascontiguousarray(vel3, np.float32).copy()
+        self.N = self.pos.shape[0]
+        cd = neighbour_celldim(L, rc)
+        self.grid = make_grid_f(L, cd)
+        self.ncells = cd[0] * cd[1] * cd[2]
+        self.scratch = lib().orc_md_scratch_new(self.N, self.ncells)
+        self.force = np.zeros((self.N, 4), np.float32)
+        cl = celllist_build(self.grid, self.pos)
+        self.force, _, _ = lj_f32(self.grid, cl, self.params, 1, self.N)
+
+    def step(self, n=1):
+        for _ in range(n):
+            rc = lib().orc_md_step_f32(self.L, C.c_float(self.rc), _p(self.params), C.c_float(self.dt), self.N,
+                                       _p(self.pos), _p(self.vel), _p(self.force), C.c_void_p(self.scratch))
+            if rc:
+                raise RuntimeError(f"oracle md step failed: {rc}")
+
+    def __del__(self):
+        try:
+            lib().orc_md_scratch_free(C.c_void_p(self.scratch))
+        except Exception:
+            pass
+
+
+# ---------------- path 2 ----------------
+def peskin3(h):
+    return IBMKernel(KERNEL_PESKIN3, 3, h, 0.0, 0.0, 0.0)
+
+
+def peskin4(h):
+    return IBMKernel(KERNEL_PESKIN4, 4, h, 0.0, 0.0, 0.0)
+
+
+def gaussian_fcm(h, tolerance):
+    """FCM_ns::Kernels::Gaussian constructor (Integrator/BDHI/FCM/FCM_kernels.cuh:22-46)."""
+    amin, amax = 0.55, 1.65
+    x = -np.log10(3 * tolerance) / 10.0
+    ups = min(amin + x * (amax - amin), amax)
+    width = h * ups
+    pref = (2.0 * np.pi * width * width) ** -0.5
+    tau = -0.5 / (width * width)
+    dr = 0.5 * h
+    r = dr
+    while pref * np.exp(tau * r * r) > tolerance:
+        r += dr
+    support = max(3, int(2 * r / h + 0.5))
+    k = IBMKernel(KERNEL_GAUSSIAN, support, h, pref, tau, support * h)
+    k_a = h * ups * np.sqrt(np.pi)
+    return k, k_a
+
+
+def ibm_spread(grid, kern, pos4, val3, nxPad):
+    pos4 = np.ascontiguousarray(pos4, np.float64)
+    val3 = np.ascontiguousarray(val3, np.float64)
+    n = grid.cellDim
+    out = np.zeros((n[2], n[1], nxPad, 3), np.float64)
+    lib().orc_ibm_spread_d(C.byref(grid), C.byref(kern), _p(pos4), _p(val3), pos4.shape[0], nxPad, _p(out))
+    return out
+
+
+def ibm_gather(grid, kern, pos4, grid3, nxPad):
+    pos4 = np.ascontiguousarray(pos4, np.float64)
+    grid3 = np.ascontiguousarray(grid3, np.float64)
+    out = np.zeros((pos4.shape[0], 3), np.float64)
+    lib().orc_ibm_gather_d(C.byref(grid), C.byref(kern), _p(pos4), pos4.shape[0], nxPad, _p(grid3), _p(out))
+    return out
+
+
+def fcm_force2vel(grid, viscosity, ghat):
+    """ghat: complex128 [nz, ny, nx/2+1, 3]; returns the scaled copy."""
+    g = np.ascontiguousarray(ghat, np.complex128).copy()
+    lib().orc_fcm_force2vel_d(C.byref(grid), C.c_double(viscosity), _p(g))
+    return g
+
+
+def dft3_r2c(grid3, nx):
+    nz, ny, nxPad, _ = grid3.shape
+    out = np.zeros((nz, ny, nx // 2 + 1, 3), np.complex128)
+    g = np.ascontiguousarray(grid3, np.float64)
+    lib().orc_dft3_r2c_d(nx, ny, nz, nxPad, _p(g), _p(out))
+    return out
+
+
+def dft3_c2r(ghat, nx, nxPad):
+    nz, ny, _, _ = ghat.shape
+    out = np.zeros((nz, ny, nxPad, 3), np.float64)
+    g = np.ascontiguousarray(ghat, np.complex128)
+    lib().orc_dft3_c2r_d(nx, ny, nz, nxPad, _p(g), _p(out))
+    return out
+
+
+def fcm_mdot(L, cells, kern, viscosity, pos4, force3):
+    """Full deterministic FCM pipeline FCM_impl::computeHydrodynamicDisplacements (T=0)
+    (Integrator/BDHI/FCM/FCM_impl.cuh:652-693) with numpy.fft standing in for cuFFT."""
+    g = make_grid_d(L, cells)
+    nx, ny, nz = cells
+    nxPad = 2 * (nx // 2 + 1)
+    sp = ibm_spread(g, kern, pos4, force3, nxPad)
+    ghat = np.fft.rfftn(sp[:, :, :nx, :], axes=(0, 1, 2))
+    ghat = fcm_force2vel(g, viscosity, ghat)
+    vel = np.zeros((nz, ny, nxPad, 3))
+    vel[:, :, :nx, :] = np.fft.irfftn(ghat, s=(nz, ny, nx), axes=(0, 1, 2)) * (nx * ny * nz)
+    return ibm_gather(g, kern, pos4, vel, nxPad)

@@ -1,0 +1,271 @@
+/* TEST INFRASTRUCTURE - NOT PART OF THE PRODUCT PATH (see oracle.h).
+ * CPU restatement of path 2 in double precision: IBM window functions, spreading, interpolation, the FCM
+ * Fourier-space Stokes operator and a naive separable DFT for small grids (large grids are transformed
+ * with numpy.fft inside tests/). Citations are file:line relative to /root/reference/src.
+ */
+#include "oracle.h"
+#include "oracle_saru.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---------- window functions ---------- */
+/* IBM_kernels::Peskin::threePoint::phi misc/IBM_kernels.cuh:118-137 */
+static double peskin3(double rr, double invh) {
+  const double r = fabs(rr) * invh;
+  if (r < 0.5) return invh * (1.0 / 3.0) * (1.0 + sqrt(1.0 + (-3.0) * r * r));
+  if (r < 1.5) {
+    const double omr = 1.0 - r;
+    return invh * (1.0 / 6.0) * (5.0 - 3.0 * r - sqrt(1.0 + (-3.0) * omr * omr));
+  }
+  return 0.0;
+}
+/* IBM_kernels::Peskin::fourPoint::phi misc/IBM_kernels.cuh:140-157 */
+static double peskin4(double rr, double invh) {
+  const double r = fabs(rr) * invh;
+  if (r < 1.0) return invh * 0.125 * (3.0 - 2.0 * r + sqrt(1.0 + 4.0 * r * (1.0 - r)));
+  if (r < 2.0) return invh * 0.125 * (5.0 - 2.0 * r - sqrt(-7.0 + 12.0 * r - 4.0 * r * r));
+  return 0.0;
+}
+/* FCM_ns::Kernels::Gaussian::phi Integrator/BDHI/FCM/FCM_kernels.cuh:54-56 over IBM_kernels::Gaussian
+   misc/IBM_kernels.cuh:28-40 */
+double orc_ibm_phi(const orc_ibm_kernel *k, double r) {
+  switch (k->kind) {
+  case ORC_KERNEL_PESKIN3: return peskin3(r, 1.0 / k->h);
+  case ORC_KERNEL_PESKIN4: return peskin4(r, 1.0 / k->h);
+  default: return r >= k->rmax ? 0.0 : k->prefactor * exp(k->tau * r * r);
+  }
+}
+
+static inline double pbc1(double r, double L, double minusInvL) {
+  if (minusInvL == 0.0) return r;
+  return r + floor(r * minusInvL + 0.5) * L;
+}
+/* Grid::distanceToCellCenter utils/Grid.cuh:124-131 (one coordinate) */
+static inline double dist_to_center(const orc_grid_d *g, int d, double p, int cell) {
+  return pbc1(p + g->L[d] * 0.5 - g->cellSize[d] * ((double)cell + 0.5), g->L[d], g->minusInvL[d]);
+}
+/* Grid::pbc_cell_coord utils/Grid.cuh:90-106 */
+static inline int pbc_cell(const orc_grid_d *g, int d, int c) {
+  const int nc = g->minusInvL[d] != 0.0 ? g->cellDim[d] : 0;
+  if (c <= -1) c += nc;
+  else if (c >= nc) c -= nc;
+  return c;
+}
+
+/* per particle stencil: IBM_ns::detail::computeSupportShift misc/IBM.cu:11-31 and fillSharedWeights :33-66 */
+typedef struct {
+  int cell[3];
+  int P[3];
+  double w[3][32];
+} stencil;
+
+static void make_stencil(const orc_grid_d *g, const orc_ibm_kernel *k, const double *p, stencil *s) {
+  orc_get_cell_d(g, p, s->cell);
+  const int sup = k->support;
+  for (int d = 0; d < 3; d++) {
+    int P = sup / 2;
+    const double dl = fabs(dist_to_center(g, d, p[d], s->cell[d] - P));
+    if (g->cellSize[d] > 0 && dl > sup * g->cellSize[d] / 2.0) P -= 1;
+    s->P[d] = P;
+    for (int i = 0; i < sup; i++) {
+      const int cj = pbc_cell(g, d, s->cell[d] + i - P);
+      s->w[d][i] = 0.0;
+      if (cj >= 0) s->w[d][i] = orc_ibm_phi(k, dist_to_center(g, d, p[d], cj));
+    }
+  }
+}
+
+/* IBM_ns::particles2GridD misc/IBM.cu:83-147 with DefaultWeightCompute misc/IBM.cuh:88-97
+   (value*phiX*phiY*phiZ) and LinearIndex3D(nxPad, ny, nz) :65-78 */
+void orc_ibm_spread_d(const orc_grid_d *g, const orc_ibm_kernel *k, const double *pos4, const double *val3,
+                      int N, int nxPad, double *grid3) {
+  const int sup = k->support;
+  for (int n = 0; n < N; n++) {
+    stencil s;
+    make_stencil(g, k, pos4 + 4 * (size_t)n, &s);
+    for (int kk = 0; kk < sup; kk++)
+      for (int jj = 0; jj < sup; jj++)
+        for (int ii = 0; ii < sup; ii++) {
+          const int cx = pbc_cell(g, 0, s.cell[0] + ii - s.P[0]);
+          const int cy = pbc_cell(g, 1, s.cell[1] + jj - s.P[1]);
+          const int cz = pbc_cell(g, 2, s.cell[2] + kk - s.P[2]);
+          if (cx < 0 || cy < 0 || cz < 0) continue;
+          if (cx >= g->cellDim[0] || cy >= g->cellDim[1] || cz >= g->cellDim[2]) continue;
+          const size_t c = (size_t)cx + (size_t)nxPad * ((size_t)cy + (size_t)g->cellDim[1] * cz);
+          for (int d = 0; d < 3; d++) grid3[3 * c + d] += val3[3 * (size_t)n + d] * s.w[0][ii] * s.w[1][jj] * s.w[2][kk];
+        }
+  }
+}
+
+/* IBM_ns::grid2ParticlesDTPP misc/IBM.cu:168-235; quadrature weight = cell volume (IBM.cuh:80-86) */
+void orc_ibm_gather_d(const orc_grid_d *g, const orc_ibm_kernel *k, const double *pos4, int N, int nxPad,
+                      const double *grid3, double *out3) {
+  const int sup = k->support;
+  double dV = g->cellSize[0] * g->cellSize[1];
+  if (g->cellDim[2] > 1) dV *= g->cellSize[2];
+#pragma omp parallel for schedule(static)
+  for (int n = 0; n < N; n++) {
+    stencil s;
+    make_stencil(g, k, pos4 + 4 * (size_t)n, &s);
+    double acc[3] = {0, 0, 0};
+    for (int kk = 0; kk < sup; kk++)
+      for (int jj = 0; jj < sup; jj++)
+        for (int ii = 0; ii < sup; ii++) {
+          const int cx = pbc_cell(g, 0, s.cell[0] + ii - s.P[0]);
+          const int cy = pbc_cell(g, 1, s.cell[1] + jj - s.P[1]);
+          const int cz = pbc_cell(g, 2, s.cell[2] + kk - s.P[2]);
+          if (cx < 0 || cy < 0 || cz < 0) continue;
+          if (cx >= g->cellDim[0] || cy >= g->cellDim[1] || cz >= g->cellDim[2]) continue;
+          const size_t c = (size_t)cx + (size_t)nxPad * ((size_t)cy + (size_t)g->cellDim[1] * cz);
+          for (int d = 0; d < 3; d++) acc[d] += dV * (grid3[3 * c + d] * s.w[0][ii] * s.w[1][jj] * s.w[2][kk]);
+        }
+    for (int d = 0; d < 3; d++) out3[3 * (size_t)n + d] += acc[d];
+  }
+}
+
+/* ---------- Fourier space ---------- */
+/* fcm_detail::indexToWaveNumber Integrator/BDHI/FCM/utils.cuh:27-35 */
+static inline int fold(int i, int n) { return i - n * (i >= (n / 2 + 1)); }
+
+/* fcm_detail::forceFourier2Vel Integrator/BDHI/FCM/FCM_impl.cuh:375-397 with getGradientFourier utils.cuh:41-51
+   and projectFourier :70-100. ghat: [(nx/2+1)*ny*nz][3 components][re,im] */
+void orc_fcm_force2vel_d(const orc_grid_d *g, double viscosity, double *ghat) {
+  const int nx = g->cellDim[0], ny = g->cellDim[1], nz = g->cellDim[2];
+  const int nkx = nx / 2 + 1;
+  const double norm = (double)(nx * ny * nz);
+  for (int iz = 0; iz < nz; iz++)
+    for (int iy = 0; iy < ny; iy++)
+      for (int ix = 0; ix < nkx; ix++) {
+        const size_t id = (size_t)ix + (size_t)nkx * ((size_t)iy + (size_t)ny * iz);
+        double *v = ghat + 6 * id;
+        if (id == 0) { memset(v, 0, 6 * sizeof(double)); continue; }
+        const int ik[3] = {fold(ix, nx), fold(iy, ny), fold(iz, nz)};
+        const int nk[3] = {nx, ny, nz};
+        double k[3], dk[3], k2 = 0;
+        for (int d = 0; d < 3; d++) {
+          k[d] = (2.0 * M_PI / g->L[d]) * ik[d];
+          dk[d] = (ik[d] == nk[d] - ik[d]) ? 0.0 : k[d];
+          k2 += k[d] * k[d];
+        }
+        const double B = 1.0 / (viscosity * k2), invk2 = 1.0 / k2;
+        for (int c = 0; c < 2; c++) { /* re, im */
+          const double f[3] = {v[0 + c], v[2 + c], v[4 + c]};
+          const double fdk = f[0] * (dk[0] * invk2) + f[1] * (dk[1] * invk2) + f[2] * (dk[2] * invk2);
+          for (int d = 0; d < 3; d++) v[2 * d + c] = (f[d] - dk[d] * fdk) * (B / norm);
+        }
+      }
+}
+
+/* naive separable DFT (small grids): forward sign -, unnormalised, like cufftExecD2Z with the
+   batched-3 interleaved plan of FCM_impl.cuh:179-234 */
+void orc_dft3_r2c_d(int nx, int ny, int nz, int nxPad, const double *grid3, double *ghat) {
+  const int nkx = nx / 2 + 1;
+  const size_t ntot = (size_t)nx * ny * nz;
+  double *a = (double *)calloc(ntot * 2, sizeof(double));
+  double *b = (double *)calloc(ntot * 2, sizeof(double));
+  for (int comp = 0; comp < 3; comp++) {
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int kx = 0; kx < nx; kx++) {
+          double re = 0, im = 0;
+          for (int x = 0; x < nx; x++) {
+            const double v = grid3[3 * ((size_t)x + (size_t)nxPad * (y + (size_t)ny * z)) + comp];
+            const double ang = -2.0 * M_PI * (double)((long)kx * x % nx) / nx;
+            re += v * cos(ang); im += v * sin(ang);
+          }
+          const size_t o = 2 * ((size_t)kx + (size_t)nx * (y + (size_t)ny * z));
+          a[o] = re; a[o + 1] = im;
+        }
+    for (int z = 0; z < nz; z++)
+      for (int ky = 0; ky < ny; ky++)
+        for (int kx = 0; kx < nx; kx++) {
+          double re = 0, im = 0;
+          for (int y = 0; y < ny; y++) {
+            const size_t i = 2 * ((size_t)kx + (size_t)nx * (y + (size_t)ny * z));
+            const double ang = -2.0 * M_PI * (double)((long)ky * y % ny) / ny;
+            const double c = cos(ang), s = sin(ang);
+            re += a[i] * c - a[i + 1] * s; im += a[i] * s + a[i + 1] * c;
+          }
+          const size_t o = 2 * ((size_t)kx + (size_t)nx * (ky + (size_t)ny * z));
+          b[o] = re; b[o + 1] = im;
+        }
+    for (int kz = 0; kz < nz; kz++)
+      for (int ky = 0; ky < ny; ky++)
+        for (int kx = 0; kx < nkx; kx++) {
+          double re = 0, im = 0;
+          for (int z = 0; z < nz; z++) {
+            const size_t i = 2 * ((size_t)kx + (size_t)nx * (ky + (size_t)ny * z));
+            const double ang = -2.0 * M_PI * (double)((long)kz * z % nz) / nz;
+            const double c = cos(ang), s = sin(ang);
+            re += b[i] * c - b[i + 1] * s; im += b[i] * s + b[i + 1] * c;
+          }
+          const size_t o = 6 * ((size_t)kx + (size_t)nkx * (ky + (size_t)ny * kz)) + 2 * comp;
+          ghat[o] = re; ghat[o + 1] = im;
+        }
+  }
+  free(a); free(b);
+}
+
+void orc_dft3_c2r_d(int nx, int ny, int nz, int nxPad, const double *ghat, double *grid3) {
+  const int nkx = nx / 2 + 1;
+  const size_t ntot = (size_t)nx * ny * nz;
+  double *a = (double *)calloc(ntot * 2, sizeof(double));
+  double *b = (double *)calloc(ntot * 2, sizeof(double));
+  for (int comp = 0; comp < 3; comp++) {
+    /* rebuild the full spectrum from the stored half, like a C2R transform implicitly does
+       (cuFFT ignores the imaginary parts that Hermitian symmetry forces to zero; here the stored half is
+       simply mirrored, which agrees whenever the input IS Hermitian) */
+    for (int kz = 0; kz < nz; kz++)
+      for (int ky = 0; ky < ny; ky++)
+        for (int kx = 0; kx < nx; kx++) {
+          const size_t o = 2 * ((size_t)kx + (size_t)nx * (ky + (size_t)ny * kz));
+          if (kx < nkx) {
+            const size_t i = 6 * ((size_t)kx + (size_t)nkx * (ky + (size_t)ny * kz)) + 2 * comp;
+            a[o] = ghat[i]; a[o + 1] = ghat[i + 1];
+          } else {
+            const int cx = nx - kx, cy = (ny - ky) % ny, cz = (nz - kz) % nz;
+            const size_t i = 6 * ((size_t)cx + (size_t)nkx * (cy + (size_t)ny * cz)) + 2 * comp;
+            a[o] = ghat[i]; a[o + 1] = -ghat[i + 1];
+          }
+        }
+    for (int z = 0; z < nz; z++)
+      for (int ky = 0; ky < ny; ky++)
+        for (int kx = 0; kx < nx; kx++) {
+          double re = 0, im = 0;
+          for (int kz = 0; kz < nz; kz++) {
+            const size_t i = 2 * ((size_t)kx + (size_t)nx * (ky + (size_t)ny * kz));
+            const double ang = 2.0 * M_PI * (double)((long)kz * z % nz) / nz;
+            const double c = cos(ang), s = sin(ang);
+            re += a[i] * c - a[i + 1] * s; im += a[i] * s + a[i + 1] * c;
+          }
+          const size_t o = 2 * ((size_t)kx + (size_t)nx * (ky + (size_t)ny * z));
+          b[o] = re; b[o + 1] = im;
+        }
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int kx = 0; kx < nx; kx++) {
+          double re = 0, im = 0;
+          for (int ky = 0; ky < ny; ky++) {
+            const size_t i = 2 * ((size_t)kx + (size_t)nx * (ky + (size_t)ny * z));
+            const double ang = 2.0 * M_PI * (double)((long)ky * y % ny) / ny;
+            const double c = cos(ang), s = sin(ang);
+            re += b[i] * c - b[i + 1] * s; im += b[i] * s + b[i + 1] * c;
+          }
+          const size_t o = 2 * ((size_t)kx + (size_t)nx * (y + (size_t)ny * z));
+          a[o] = re; a[o + 1] = im;
+        }
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+          double re = 0;
+          for (int kx = 0; kx < nx; kx++) {
+            const size_t i = 2 * ((size_t)kx + (size_t)nx * (y + (size_t)ny * z));
+            const double ang = 2.0 * M_PI * (double)((long)kx * x % nx) / nx;
+            re += a[i] * cos(ang) - a[i + 1] * sin(ang);
+          }
+          grid3[3 * ((size_t)x + (size_t)nxPad * (y + (size_t)ny * z)) + comp] = re;
+        }
+  }
+  free(a); free(b);
+}

@@ -1,0 +1,78 @@
+"""GPU: parity against the UNMODIFIED reference compiled from /root/reference (oracle/_ref/ref_lj, built in the
+build container by oracle/Makefile; the binary travels with the snapshot, the reference tree does not).
+Cell-list arrays must be bit-exact; forces are compared through the fp64 oracle with the same tolerance as
+tests/test_lj_gpu.py, and the reference's own distance from the fp64 truth is checked to be of the same size."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from uammd_b200 import synthetic as syn
+from uammd_b200.md import Box, CellList, LJ, PairForces
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LJ = os.path.join(ROOT, "oracle", "_ref", "ref_lj")
+
+
+def _run_ref(tmp_path, pos, L, rc=2.5):
+    if not os.path.exists(REF_LJ):
+        pytest.skip("oracle/_ref/ref_lj not built (needs the reference tree at build time)")
+    pf = tmp_path / "pos.bin"
+    pos.tofile(pf)
+    out = str(tmp_path / "ref")
+    subprocess.run([REF_LJ, "forces", str(pos.shape[0]), str(L[0]), str(L[1]), str(L[2]), str(rc), "1", "1", "0",
+                    str(pf), out], check=True, capture_output=True, timeout=600)
+    N = pos.shape[0]
+    return {
+        "celldim": np.fromfile(out + ".celldim.bin", np.int32),
+        "sortPos": np.fromfile(out + ".sortpos.bin", np.float32).reshape(N, 4),
+        "index": np.fromfile(out + ".index.bin", np.int32),
+        "cellStart": np.fromfile(out + ".cellstart.bin", np.int32),
+        "cellEnd": np.fromfile(out + ".cellend.bin", np.int32),
+        "force": np.fromfile(out + ".force.bin", np.float32).reshape(N, 4),
+        "energy": np.fromfile(out + ".energy.bin", np.float32),
+        "virial": np.fromfile(out + ".virial.bin", np.float32),
+    }
+
+
+@pytest.mark.parametrize("N,kind", [(20000, "uniform"), (1_000_000, "uniform"), (1_000_000, "fcc")])
+def test_reference_parity(orc, cuda, tmp_path, N, kind):
+    Lb = syn.lj_box_length(N)
+    pos = syn.uniform_cloud(N, Lb, seed=2024) if kind == "uniform" else syn.fcc_lattice(N, Lb)
+    if kind == "fcc":  # thermal jitter so that forces are non trivial
+        pos[:, :3] += np.random.default_rng(5).normal(0, 0.05, (N, 3)).astype(np.float32)
+    L = (Lb,) * 3
+    ref = _run_ref(tmp_path, pos, L)
+    pot = LJ(); pot.setPotParameters(0, 0, cutOff=2.5)
+    pf = PairForces(pot, Box(L))
+    dpos = torch.from_numpy(pos).to(cuda)
+    force = torch.zeros(N, 4, device=cuda); e = torch.zeros(N, device=cuda); v = torch.zeros(N, device=cuda)
+    pf.sum(dpos, force=force, energy=e, virial=v)
+    torch.cuda.synchronize()
+    d = pf.nl.getCellList()
+    # --- integer/byte parity: bit-exact ---
+    assert tuple(ref["celldim"][:3]) == tuple(d["cellDim"])
+    assert np.array_equal(d["groupIndex"].cpu().numpy(), ref["index"])
+    assert np.array_equal(d["sortPos"].cpu().numpy().view(np.uint32), ref["sortPos"].view(np.uint32))
+    cs, ce = pf.nl.normalizedCells()
+    assert np.array_equal(cs, ref["cellStart"]) and np.array_equal(ce, ref["cellEnd"])
+    # --- oracle pinned by the reference: restated cell list == reference cell list ---
+    g = orc.make_grid_f(L, orc.neighbour_celldim(L, 2.5))
+    ocl = orc.celllist_build(g, pos)
+    assert np.array_equal(ocl["index"], ref["index"]) and np.array_equal(ocl["cellStart"], ref["cellStart"])
+    # --- forces: both implementations vs fp64 truth ---
+    f64, e64, v64, a = orc.lj_f64(g, ocl, pot.table(), 1, N)
+    a = np.maximum(a, 1e-30)
+    err_ref = (np.abs(ref["force"][:, :3] - f64).max(axis=1) / a).max()
+    err_new = (np.abs(force.cpu().numpy()[:, :3] - f64).max(axis=1) / a).max()
+    direct = (np.abs(force.cpu().numpy()[:, :3] - ref["force"][:, :3]).max(axis=1) / a).max()
+    print(f"[parity N={N} {kind}] reference vs fp64 {err_ref:.3e}; new vs fp64 {err_new:.3e}; new vs reference {direct:.3e}")
+    assert err_new < 2e-4 and err_ref < 2e-4 and direct < 2e-4
+    # the restated fp32 oracle in reference order should be (nearly) the reference's bits
+    f32, _, _ = orc.lj_f32(g, ocl, pot.table(), 1, N)
+    assert (np.abs(f32[:, :3] - ref["force"][:, :3]).max(axis=1) / a).max() < 2e-5
+    assert np.allclose(e.cpu().numpy(), ref["energy"], rtol=2e-4, atol=2e-4 * np.abs(ref["energy"]).max())
+    assert np.allclose(v.cpu().numpy(), ref["virial"], rtol=2e-4, atol=2e-4 * np.abs(ref["virial"]).max())

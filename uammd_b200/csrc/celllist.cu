@@ -1,0 +1,333 @@
+// Cell list build for sm_100a: warp-aggregated counting sort over Morton-code bins.
+//
+// Replaces the reference chain assignHash -> cub::DeviceRadixSort::SortPairs -> permutation gather ->
+// fillCellList (utils/ParticleSorter.cuh:102-111,243-274,179-187; CellList/CellListBase.cuh:68-95) by
+//   1. binParticles   : cell of each particle (reference-exact fp32 arithmetic), Morton code, slot in the
+//                       bin from a warp-aggregated atomicAdd                       R 16 B  W 8 B / particle
+//   2. scan (3 tiny kernels over the 2^maxbit Morton codes)                         ~4 B / code
+//   3. scatterToBins  : unstable[binStart[code]+slot] = i                           R 8 B   W 4 B
+//   4. orderAndGather : restores the STABLE order inside each bin (rank = #smaller indices in the bin,
+//                       bins hold ~N/ncells entries and sit in L1), writes groupIndex, gathers sortPos and
+//                       emits cellStart/cellEnd in the reference layout            R 12+16 B W 20 B
+// The result is bit-identical to the reference's stable radix sort by Morton hash.
+#include "common.cuh"
+
+namespace ub200 {
+
+thread_local int g_lastCudaError = 0;
+unsigned long long g_launchCount = 0;
+
+__global__ void __launch_bounds__(256)
+binParticles(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, GridF g,
+             uint32_t *__restrict__ binCount, uint2 *__restrict__ codeSlot, int *__restrict__ errorFlag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float4 p = ldg4(pos + (groupIdx ? groupIdx[i] : i));
+  int cx = cellCoord(p.x, g.Lx, g.mx, g.hLx, g.ix, g.nx);
+  int cy = cellCoord(p.y, g.Ly, g.my, g.hLy, g.iy, g.ny);
+  int cz = cellCoord(p.z, g.Lz, g.mz, g.hLz, g.iz, g.nz);
+  if ((unsigned)cx >= (unsigned)g.nx || (unsigned)cy >= (unsigned)g.ny || (unsigned)cz >= (unsigned)g.nz) {
+    // outside a non periodic box (the reference raises errorFlag in fillCellList): flag and clamp
+    *errorFlag = 1;
+    cx = min(max(cx, 0), g.nx - 1);
+    cy = min(max(cy, 0), g.ny - 1);
+    cz = min(max(cz, 0), g.nz - 1);
+  }
+  const uint32_t code = mortonCode(cx, cy, cz);
+  // warp-aggregated increment: one atomic per distinct bin per warp
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, code);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(binCount + code, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  codeSlot[i] = make_uint2(code, base + rank);
+}
+
+// ---- exclusive scan over the bins: block sums -> top scan -> apply ----
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems; // 4096
+
+__device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread across the block; returns the exclusive prefix, total in *total
+template <int THREADS> __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t *total) {
+  __shared__ uint32_t warpSums[THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t inc = warpInclusiveScan(v, lane);
+  if (lane == 31) warpSums[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = lane < THREADS / 32 ? warpSums[lane] : 0;
+    s = warpInclusiveScan(s, lane);
+    if (lane < THREADS / 32) warpSums[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t warpOff = w ? warpSums[w - 1] : 0;
+  *total = warpSums[THREADS / 32 - 1];
+  return warpOff + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scanTileSums(const uint32_t *__restrict__ in, int M,
+                                                             uint32_t *__restrict__ tileSums) {
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  uint32_t s = 0;
+  if (base + kScanItems <= M) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(in + base);
+    const uint4 b = *reinterpret_cast<const uint4 *>(in + base + 4);
+    s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  } else {
+    for (int k = 0; k < kScanItems; k++)
+      if (base + k < M) s += in[base + k];
+  }
+  uint32_t total;
+  blockExclusiveScan<kScanThreads>(s, &total);
+  if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to 4096 tile sums in place
+__global__ void __launch_bounds__(1024) scanTop(uint32_t *__restrict__ tileSums, int ntiles) {
+  uint32_t v[4];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int idx = threadIdx.x * 4 + k;
+    v[k] = idx < ntiles ? tileSums[idx] : 0;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = blockExclusiveScan<1024>(s, &total);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int idx = threadIdx.x * 4 + k;
+    if (idx < ntiles) tileSums[idx] = ex;
+    ex += v[k];
+  }
+}
+
+// out[i] = exclusive prefix; out[M] = grand total. Also re-zeroes `in` for the next build.
+__global__ void __launch_bounds__(kScanThreads) scanApply(uint32_t *__restrict__ in, int M,
+                                                          const uint32_t *__restrict__ tileOffsets,
+                                                          uint32_t *__restrict__ out) {
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    v[k] = (base + k < M) ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = blockExclusiveScan<kScanThreads>(s, &total) + tileOffsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    if (base + k < M) {
+      out[base + k] = ex;
+      in[base + k] = 0;
+    }
+    ex += v[k];
+  }
+  if (base <= M - 1 && M - 1 < base + kScanItems) out[M] = ex; // thread owning the last item: ex == grand total
+}
+
+__global__ void __launch_bounds__(256)
+scatterToBins(const uint2 *__restrict__ codeSlot, const uint32_t *__restrict__ binStart, int N,
+              int *__restrict__ unstable) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint2 cs = codeSlot[i];
+  unstable[binStart[cs.x] + cs.y] = i;
+}
+
+__global__ void __launch_bounds__(256)
+orderAndGather(const int *__restrict__ unstable, const uint2 *__restrict__ codeSlot,
+               const uint32_t *__restrict__ binStart, const float4 *__restrict__ pos,
+               const int *__restrict__ groupIdx, int N, GridF g, uint32_t validCell,
+               float4 *__restrict__ sortPos, int *__restrict__ groupIndex, uint32_t *__restrict__ cellStart,
+               int *__restrict__ cellEnd) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const int i = unstable[k];
+  const uint32_t code = codeSlot[i].x;
+  const int s = (int)binStart[code], e = (int)binStart[code + 1];
+  int rank = 0;
+  for (int j = s; j < e; j++) rank += (__ldg(unstable + j) < i);
+  const int dst = s + rank;
+  groupIndex[dst] = i;
+  sortPos[dst] = ldg4(pos + (groupIdx ? groupIdx[i] : i));
+  if (rank == 0) {
+    const int cx = compactBits10(code), cy = compactBits10(code >> 1), cz = compactBits10(code >> 2);
+    const int lin = cx + g.nx * (cy + g.ny * cz);
+    cellStart[lin] = (uint32_t)s + validCell;
+    cellEnd[lin] = e;
+  }
+}
+
+static int highestBit(uint32_t v) { // position of MSB + 1 (0 for v == 0)
+  int b = 0;
+  while (v) { b++; v >>= 1; }
+  return b;
+}
+
+} // namespace ub200
+
+using namespace ub200;
+
+extern "C" {
+
+int ub200_celllist_create(ub200_celllist **out) {
+  if (!out) return UB200_ERR_INVALID_ARGUMENT;
+  *out = new (std::nothrow) ub200_celllist();
+  return *out ? UB200_OK : UB200_ERR_ALLOC;
+}
+
+int ub200_celllist_destroy(ub200_celllist *cl) {
+  if (!cl) return UB200_OK;
+  DevBuf *bufs[] = {&cl->sortPos, &cl->groupIndex, &cl->cellStart, &cl->cellEnd, &cl->binCount,
+                    &cl->binStart, &cl->blockSums, &cl->codeSlot, &cl->unstable, &cl->errorFlag};
+  for (DevBuf *b : bufs) b->release();
+  delete cl;
+  return UB200_OK;
+}
+
+int ub200_neighbour_celldim_f32(const float L[3], float rc, int cellDim[3]) {
+  if (!L || !cellDim || !(rc > 0)) return UB200_ERR_INVALID_ARGUMENT;
+  for (int d = 0; d < 3; d++) {
+    int c = (int)(L[d] / rc); // Grid(Box, real3 minCellSize): make_int3(boxSize/minCellSize), utils/Grid.cuh:31-33
+    if (c <= 3) c = 1;        // CellList.cuh:117-122
+    cellDim[d] = c;
+  }
+  return UB200_OK;
+}
+
+int ub200_celllist_build_f32(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx, int N,
+                             const float L[3], const int periodic[3], const int cellDim[3], void *stream) {
+  if (!cl || !d_pos || N <= 0 || !L || !periodic || !cellDim) return UB200_ERR_INVALID_ARGUMENT;
+  for (int d = 0; d < 3; d++)
+    if (cellDim[d] < 1 || cellDim[d] > 1024) return UB200_ERR_INVALID_ARGUMENT; // 10 bit Morton fields
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridF g = makeGridF(L, periodic, cellDim);
+  const int ncells = g.nx * g.ny * g.nz;
+  // ParticleSorter::updateOrderByCellHash: maxHash = hash(cellDim-1), sort bits [0, 32-clz(maxHash))
+  const uint32_t maxHash = mortonCode(g.nx - 1, g.ny - 1, g.nz - 1);
+  const int maxbit = highestBit(maxHash);
+  if (maxbit > 24) return UB200_ERR_GRID_TOO_LARGE;
+  const int nbins = 1 << maxbit;
+  const int ntiles = (nbins + kScanTile - 1) / kScanTile;
+  if (ntiles > 4096) return UB200_ERR_GRID_TOO_LARGE;
+
+  int rc;
+  if ((rc = cl->sortPos.reserve(sizeof(float4) * (size_t)N))) return rc;
+  if ((rc = cl->groupIndex.reserve(sizeof(int) * (size_t)N))) return rc;
+  if ((rc = cl->codeSlot.reserve(sizeof(uint2) * (size_t)N))) return rc;
+  if ((rc = cl->unstable.reserve(sizeof(int) * (size_t)N))) return rc;
+  if ((rc = cl->blockSums.reserve(sizeof(uint32_t) * 4096))) return rc;
+  if (!cl->errorFlag.p) {
+    if ((rc = cl->errorFlag.reserve(sizeof(int)))) return rc;
+    UB200_CUDA(cudaMemsetAsync(cl->errorFlag.p, 0, sizeof(int), st));
+  }
+  if (cl->nbins != nbins || !cl->binCount.p) {
+    if ((rc = cl->binCount.reserve(sizeof(uint32_t) * (size_t)nbins))) return rc;
+    if ((rc = cl->binStart.reserve(sizeof(uint32_t) * ((size_t)nbins + 1)))) return rc;
+    // binCount is re-zeroed by scanApply at every build; zero it once here
+    UB200_CUDA(cudaMemsetAsync(cl->binCount.p, 0, sizeof(uint32_t) * (size_t)nbins, st));
+  }
+  // CellListBase::tryToResizeCellListToCurrentGrid (CellListBase.cuh:186-200): cellStart zero-filled on resize
+  bool resized = false;
+  if (cl->cellStartCells != (size_t)ncells) {
+    if ((rc = cl->cellStart.reserve(sizeof(uint32_t) * (size_t)ncells))) return rc;
+    if ((rc = cl->cellEnd.reserve(sizeof(int) * (size_t)ncells))) return rc;
+    UB200_CUDA(cudaMemsetAsync(cl->cellStart.p, 0, sizeof(uint32_t) * (size_t)ncells, st));
+    cl->cellStartCells = (size_t)ncells;
+    resized = true;
+  }
+  (void)resized;
+  // CellListBase::updateCurrentValidCell (CellListBase.cuh:210-230)
+  if (N != cl->lastN) cl->validCounter = -1;
+  const unsigned long long nextMax = (unsigned long long)N * (unsigned long long)(cl->validCounter + 2);
+  if (cl->validCounter < 0 || nextMax >= 0xFFFFFFFFull - 1ull) {
+    cl->validCell = (uint32_t)N;
+    cl->validCounter = 1;
+    UB200_CUDA(cudaMemsetAsync(cl->cellStart.p, 0, sizeof(uint32_t) * (size_t)ncells, st));
+  } else {
+    cl->validCounter++;
+    cl->validCell = (uint32_t)N * (uint32_t)cl->validCounter;
+  }
+  cl->lastN = N;
+  cl->grid = g;
+  cl->N = N;
+  cl->ncells = ncells;
+  cl->nbins = nbins;
+  for (int d = 0; d < 3; d++) cl->cellDim[d] = cellDim[d];
+
+  const int nb = (N + 255) / 256;
+  binParticles<<<nb, 256, 0, st>>>((const float4 *)d_pos, d_groupIdx, N, g, cl->binCount.as<uint32_t>(),
+                                   cl->codeSlot.as<uint2>(), cl->errorFlag.as<int>());
+  UB200_LAUNCHED();
+  scanTileSums<<<ntiles, kScanThreads, 0, st>>>(cl->binCount.as<uint32_t>(), nbins, cl->blockSums.as<uint32_t>());
+  UB200_LAUNCHED();
+  scanTop<<<1, 1024, 0, st>>>(cl->blockSums.as<uint32_t>(), ntiles);
+  UB200_LAUNCHED();
+  scanApply<<<ntiles, kScanThreads, 0, st>>>(cl->binCount.as<uint32_t>(), nbins, cl->blockSums.as<uint32_t>(),
+                                             cl->binStart.as<uint32_t>());
+  UB200_LAUNCHED();
+  scatterToBins<<<nb, 256, 0, st>>>(cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(), N, cl->unstable.as<int>());
+  UB200_LAUNCHED();
+  orderAndGather<<<nb, 256, 0, st>>>(cl->unstable.as<int>(), cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(),
+                                     (const float4 *)d_pos, d_groupIdx, N, g, cl->validCell,
+                                     cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
+                                     cl->cellStart.as<uint32_t>(), cl->cellEnd.as<int>());
+  UB200_LAUNCHED();
+  cl->built = 1;
+  return UB200_OK;
+}
+
+int ub200_celllist_view_get(ub200_celllist *cl, ub200_celllist_view *v) {
+  if (!cl || !v) return UB200_ERR_INVALID_ARGUMENT;
+  if (!cl->built) return UB200_ERR_NOT_BUILT;
+  v->d_cellStart = cl->cellStart.as<uint32_t>();
+  v->d_cellEnd = cl->cellEnd.as<int>();
+  v->d_sortPos = cl->sortPos.p;
+  v->d_groupIndex = cl->groupIndex.as<int>();
+  v->VALID_CELL = cl->validCell;
+  for (int d = 0; d < 3; d++) v->cellDim[d] = cl->cellDim[d];
+  v->numberParticles = cl->N;
+  v->d_binStart = cl->binStart.as<uint32_t>();
+  v->nbins = cl->nbins;
+  return UB200_OK;
+}
+
+int ub200_celllist_error_flag(ub200_celllist *cl, void *stream, int *flag) {
+  if (!cl || !flag) return UB200_ERR_INVALID_ARGUMENT;
+  if (!cl->built) return UB200_ERR_NOT_BUILT;
+  UB200_CUDA(cudaMemcpyAsync(flag, cl->errorFlag.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  UB200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return UB200_OK;
+}
+
+const char *ub200_error_string(int code) {
+  switch (code) {
+  case UB200_OK: return "ok";
+  case UB200_ERR_INVALID_ARGUMENT: return "invalid argument";
+  case UB200_ERR_CUDA: return "CUDA runtime error (see ub200_last_cuda_error)";
+  case UB200_ERR_ALLOC: return "device allocation failed";
+  case UB200_ERR_GRID_TOO_LARGE: return "cell grid too large for the Morton bin table";
+  case UB200_ERR_NOT_BUILT: return "cell list has not been built";
+  case UB200_ERR_UNSUPPORTED: return "unsupported configuration";
+  default: return "unknown error";
+  }
+}
+int ub200_last_cuda_error(void) { return g_lastCudaError; }
+const char *ub200_version(void) { return "uammd_b200 0.1 sm_100a"; }
+unsigned long long ub200_launch_count(void) { return g_launchCount; }
+}

@@ -1,0 +1,147 @@
+// uammd_b200 internal helpers shared by all kernels (sm_100a only).
+#pragma once
+#include "../../include/uammd_b200.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <new>
+#include <cmath>
+
+namespace ub200 {
+
+extern thread_local int g_lastCudaError;
+extern unsigned long long g_launchCount;
+
+inline int cudaFail(cudaError_t e) {
+  g_lastCudaError = (int)e;
+  return UB200_ERR_CUDA;
+}
+#define UB200_CUDA(call)                                                                                     \
+  do {                                                                                                       \
+    cudaError_t e__ = (call);                                                                                \
+    if (e__ != cudaSuccess) return ::ub200::cudaFail(e__);                                                   \
+  } while (0)
+// count + check a kernel launch (no sync)
+#define UB200_LAUNCHED()                                                                                     \
+  do {                                                                                                       \
+    ::ub200::g_launchCount++;                                                                                \
+    cudaError_t e__ = cudaPeekAtLastError();                                                                 \
+    if (e__ != cudaSuccess) return ::ub200::cudaFail(e__);                                                   \
+  } while (0)
+
+constexpr int kNumSMs = 148; // B200
+
+// Device buffer that only ever grows (scratch owned by a handle; no allocation on the steady-state path).
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return UB200_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      g_lastCudaError = (int)e;
+      return UB200_ERR_ALLOC;
+    }
+    cap = want;
+    return UB200_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Box + Grid in the reference's single precision arithmetic (utils/Box.cuh:16-36, utils/Grid.cuh:21-48).
+// All derived quantities are computed on the host in fp32 exactly like the reference constructors do.
+struct GridF {
+  float Lx, Ly, Lz;
+  float mx, my, mz; // minusInvBoxSize, 0 when the dimension is not periodic
+  float hLx, hLy, hLz; // 0.5*L (exact)
+  float ix, iy, iz; // invCellSize
+  int nx, ny, nz;
+};
+
+inline GridF makeGridF(const float L[3], const int periodic[3], const int cellDim[3]) {
+  GridF g;
+  float m[3], inv[3];
+  int n[3];
+  for (int d = 0; d < 3; d++) {
+    m[d] = -1.0f / L[d];
+    if (L[d] == 0.0f || isinf(L[d]) || !periodic[d]) m[d] = 0.0f;
+    n[d] = cellDim[d];
+    if (d == 2 && n[d] == 0) n[d] = 1;
+    const float cs = L[d] / (float)n[d];
+    inv[d] = 1.0f / cs;
+  }
+  if (L[2] == 0.0f) inv[2] = 0.0f;
+  g.Lx = L[0]; g.Ly = L[1]; g.Lz = L[2];
+  g.mx = m[0]; g.my = m[1]; g.mz = m[2];
+  g.hLx = 0.5f * L[0]; g.hLy = 0.5f * L[1]; g.hLz = 0.5f * L[2];
+  g.ix = inv[0]; g.iy = inv[1]; g.iz = inv[2];
+  g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+  return g;
+}
+
+// Box::apply_pbc for one coordinate (utils/Box.cuh:51-58). The reference is compiled with nvcc's default
+// -fmad=true, which contracts r*minusInvL+0.5 and r+offset*L into FMAs; we spell the FMAs out so that the
+// cell of a particle is decided by the same roundings.
+__device__ __forceinline__ float foldCoord(float r, float L, float minusInvL) {
+  const float offset = floorf(__fmaf_rn(r, minusInvL, 0.5f));
+  return (minusInvL != 0.0f) ? __fmaf_rn(offset, L, r) : r;
+}
+// Grid::getCell for one coordinate (utils/Grid.cuh:49-71): trunc((fold(r) + 0.5 L) * invCellSize), n -> 0.
+__device__ __forceinline__ int cellCoord(float r, float L, float minusInvL, float halfL, float invCell, int n) {
+  const float rf = foldCoord(r, L, minusInvL);
+  int c = __float2int_rz(__fmul_rn(__fadd_rn(rf, halfL), invCell));
+  return (c == n) ? 0 : c;
+}
+
+// Sorter::MortonHash (utils/ParticleSorter.cuh:51-76): 10 bits per dimension, x in the lowest bit.
+__host__ __device__ __forceinline__ uint32_t spreadBits10(uint32_t v) {
+  uint32_t x = v & 0x3ffu;
+  x = (x | (x << 16)) & 0x30000ffu;
+  x = (x | (x << 8)) & 0x300f00fu;
+  x = (x | (x << 4)) & 0x30c30c3u;
+  x = (x | (x << 2)) & 0x9249249u;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t mortonCode(int cx, int cy, int cz) {
+  return spreadBits10((uint32_t)cx) | (spreadBits10((uint32_t)cy) << 1) | (spreadBits10((uint32_t)cz) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t compactBits10(uint32_t x) {
+  x &= 0x9249249u;
+  x = (x | (x >> 2)) & 0x30c30c3u;
+  x = (x | (x >> 4)) & 0x300f00fu;
+  x = (x | (x >> 8)) & 0x30000ffu;
+  x = (x | (x >> 16)) & 0x3ffu;
+  return x;
+}
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+} // namespace ub200
+
+// Opaque handle behind ub200_celllist
+struct ub200_celllist {
+  ub200::GridF grid;
+  int N = 0;
+  int ncells = 0;
+  int nbins = 0;       // 2^maxbit Morton codes
+  int built = 0;
+  uint32_t validCell = 0; // VALID_CELL epoch (CellListBase.cuh:210-230)
+  int validCounter = -1;
+  int lastN = -1;
+  int cellDim[3] = {0, 0, 0};
+  ub200::DevBuf sortPos, groupIndex, cellStart, cellEnd; // reference-layout outputs
+  ub200::DevBuf binCount, binStart, blockSums;           // Morton-code space histogram + scan
+  ub200::DevBuf codeSlot;                                // per particle {code, slot}
+  ub200::DevBuf unstable;                                // scatter target before the stable fix-up
+  ub200::DevBuf errorFlag;
+  size_t cellStartCells = 0;
+};

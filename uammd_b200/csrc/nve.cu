@@ -1,0 +1,168 @@
+// Velocity Verlet (NVE) half steps and the fused LJ molecular dynamics engine, sm_100a.
+// Replaces VerletNVE_ns::integrateGPU<step> / VerletNVE::forwardTime (Integrator/VerletNVE.cu:64-85,174-188).
+#include "common.cuh"
+
+namespace ub200 {
+
+int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
+          const int *globalIdx, bool accumulate, DevBuf *tableBuf, cudaStream_t st);
+
+// v += (F/m) dt/2 ; step 1 also x += v dt. Same operation order as the reference (force/m is (1/m)*force,
+// utils/vector.cuh:191-193; the trailing multiply-adds are contracted by nvcc there, spelled out here).
+template <int STEP>
+__global__ void __launch_bounds__(256)
+nveHalfStep(float4 *__restrict__ pos, float *__restrict__ vel, const float4 *__restrict__ force,
+            const float *__restrict__ mass, float defaultMass, const int *__restrict__ groupIdx, int N, float dt,
+            int is2D) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  const int i = groupIdx ? groupIdx[id] : id;
+  const float invm = 1.0f / (mass ? mass[i] : defaultMass);
+  const float4 f = force[i];
+  float vx = vel[3 * (size_t)i + 0], vy = vel[3 * (size_t)i + 1], vz = vel[3 * (size_t)i + 2];
+  vx = __fmaf_rn(__fmul_rn(__fmul_rn(invm, f.x), dt), 0.5f, vx);
+  vy = __fmaf_rn(__fmul_rn(__fmul_rn(invm, f.y), dt), 0.5f, vy);
+  vz = __fmaf_rn(__fmul_rn(__fmul_rn(invm, f.z), dt), 0.5f, vz);
+  if (is2D) vz = 0.0f;
+  vel[3 * (size_t)i + 0] = vx;
+  vel[3 * (size_t)i + 1] = vy;
+  vel[3 * (size_t)i + 2] = vz;
+  if (STEP == 1) {
+    float4 p = pos[i];
+    p.x = __fmaf_rn(vx, dt, p.x);
+    p.y = __fmaf_rn(vy, dt, p.y);
+    p.z = __fmaf_rn(vz, dt, p.z);
+    pos[i] = p;
+  }
+}
+
+// second kick of step n fused with the first kick + drift of step n+1 (same roundings as two separate passes)
+__global__ void __launch_bounds__(256)
+nveKickKickDrift(float4 *__restrict__ pos, float *__restrict__ vel, const float4 *__restrict__ force, int N,
+                 float dt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float4 f = force[i];
+  float vx = vel[3 * (size_t)i + 0], vy = vel[3 * (size_t)i + 1], vz = vel[3 * (size_t)i + 2];
+  const float hx = __fmul_rn(f.x, dt), hy = __fmul_rn(f.y, dt), hz = __fmul_rn(f.z, dt);
+  vx = __fmaf_rn(hx, 0.5f, vx); vy = __fmaf_rn(hy, 0.5f, vy); vz = __fmaf_rn(hz, 0.5f, vz);
+  vx = __fmaf_rn(hx, 0.5f, vx); vy = __fmaf_rn(hy, 0.5f, vy); vz = __fmaf_rn(hz, 0.5f, vz);
+  vel[3 * (size_t)i + 0] = vx;
+  vel[3 * (size_t)i + 1] = vy;
+  vel[3 * (size_t)i + 2] = vz;
+  float4 p = pos[i];
+  p.x = __fmaf_rn(vx, dt, p.x);
+  p.y = __fmaf_rn(vy, dt, p.y);
+  p.z = __fmaf_rn(vz, dt, p.z);
+  pos[i] = p;
+}
+
+} // namespace ub200
+
+using namespace ub200;
+
+struct ub200_md {
+  ub200_celllist *cl = nullptr;
+  DevBuf ljTable;
+  DevBuf dpos, dvel, dforce; // device state for the host-buffer entry point
+};
+
+extern "C" {
+
+int ub200_nve_half_step_f32(void *d_pos, void *d_vel, const void *d_force, const float *d_mass, float defaultMass,
+                            const int *d_groupIdx, int N, float dt, int is2D, int step, void *stream) {
+  if (!d_pos || !d_vel || !d_force || N <= 0 || (step != 1 && step != 2)) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (N + 255) / 256;
+  if (step == 1)
+    nveHalfStep<1><<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, d_mass, defaultMass,
+                                       d_groupIdx, N, dt, is2D);
+  else
+    nveHalfStep<2><<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, d_mass, defaultMass,
+                                       d_groupIdx, N, dt, is2D);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
+int ub200_md_create(ub200_md **out) {
+  if (!out) return UB200_ERR_INVALID_ARGUMENT;
+  ub200_md *md = new (std::nothrow) ub200_md();
+  if (!md) return UB200_ERR_ALLOC;
+  int rc = ub200_celllist_create(&md->cl);
+  if (rc) { delete md; return rc; }
+  *out = md;
+  return UB200_OK;
+}
+
+int ub200_md_destroy(ub200_md *md) {
+  if (!md) return UB200_OK;
+  ub200_celllist_destroy(md->cl);
+  md->ljTable.release(); md->dpos.release(); md->dvel.release(); md->dforce.release();
+  delete md;
+  return UB200_OK;
+}
+
+ub200_celllist *ub200_md_celllist(ub200_md *md) { return md ? md->cl : nullptr; }
+
+static int mdForces(ub200_md *md, void *d_pos, void *d_force, int N, const float L[3], float rc, const float *params,
+                    int ntypes, cudaStream_t st) {
+  const int periodic[3] = {1, 1, 1};
+  int cellDim[3];
+  int e = ub200_neighbour_celldim_f32(L, rc, cellDim);
+  if (e) return e;
+  if ((e = ub200_celllist_build_f32(md->cl, d_pos, nullptr, N, L, periodic, cellDim, st))) return e;
+  // sole interactor: forces are written, not accumulated (replaces resetForces + sum)
+  return ljSum(md->cl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, false, &md->ljTable, st);
+}
+
+int ub200_md_lj_nve_prepare_f32(ub200_md *md, void *d_pos, void *d_force, int N, const float L[3], float rc,
+                                const float *params, int ntypes, void *stream) {
+  if (!md || !d_pos || !d_force || N <= 0 || !L || !params) return UB200_ERR_INVALID_ARGUMENT;
+  return mdForces(md, d_pos, d_force, N, L, rc, params, ntypes, (cudaStream_t)stream);
+}
+
+int ub200_md_lj_nve_run_f32(ub200_md *md, void *d_pos, void *d_vel, void *d_force, int N, const float L[3], float rc,
+                            const float *params, int ntypes, float dt, int nsteps, void *stream) {
+  if (!md || !d_pos || !d_vel || !d_force || N <= 0 || !L || !params || nsteps < 0) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (N + 255) / 256;
+  for (int s = 0; s < nsteps; s++) {
+    int e;
+    if (s == 0) {
+      nveHalfStep<1><<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, nullptr, 1.0f,
+                                         nullptr, N, dt, 0);
+      UB200_LAUNCHED();
+    }
+    if ((e = mdForces(md, d_pos, d_force, N, L, rc, params, ntypes, st))) return e;
+    if (s == nsteps - 1) {
+      nveHalfStep<2><<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, nullptr, 1.0f,
+                                         nullptr, N, dt, 0);
+    } else {
+      nveKickKickDrift<<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, N, dt);
+    }
+    UB200_LAUNCHED();
+  }
+  return UB200_OK;
+}
+
+int ub200_md_lj_nve_run_host_f32(ub200_md *md, float *h_pos4, float *h_vel3, float *h_force4, int N, const float L[3],
+                                 float rc, const float *params, int ntypes, float dt, int nsteps, void *stream) {
+  if (!md || !h_pos4 || !h_vel3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  int e;
+  if ((e = md->dpos.reserve(sizeof(float4) * (size_t)N))) return e;
+  if ((e = md->dvel.reserve(sizeof(float) * 3 * (size_t)N))) return e;
+  if ((e = md->dforce.reserve(sizeof(float4) * (size_t)N))) return e;
+  UB200_CUDA(cudaMemcpyAsync(md->dpos.p, h_pos4, sizeof(float4) * (size_t)N, cudaMemcpyHostToDevice, st));
+  UB200_CUDA(cudaMemcpyAsync(md->dvel.p, h_vel3, sizeof(float) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
+  if ((e = ub200_md_lj_nve_prepare_f32(md, md->dpos.p, md->dforce.p, N, L, rc, params, ntypes, stream))) return e;
+  if ((e = ub200_md_lj_nve_run_f32(md, md->dpos.p, md->dvel.p, md->dforce.p, N, L, rc, params, ntypes, dt, nsteps, stream)))
+    return e;
+  UB200_CUDA(cudaMemcpyAsync(h_pos4, md->dpos.p, sizeof(float4) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  UB200_CUDA(cudaMemcpyAsync(h_vel3, md->dvel.p, sizeof(float) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
+  if (h_force4)
+    UB200_CUDA(cudaMemcpyAsync(h_force4, md->dforce.p, sizeof(float4) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  UB200_CUDA(cudaStreamSynchronize(st));
+  return UB200_OK;
+}
+}

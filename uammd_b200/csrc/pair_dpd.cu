@@ -1,0 +1,232 @@
+// Dissipative particle dynamics pair forces over the cell list, sm_100a.
+// Replaces transverseWithNeighbourContainer (Interactor/NeighbourList/common.cuh:10-34) driving
+// DPD_impl::ForceTransverser (Interactor/Potential/DPD.cuh:92-159). The reference evaluates getInfo(j)
+// = {vel[global j], global j} for every CANDIDATE through the unsorted global index (81 scattered 12-byte
+// loads per particle at rho=3); here velocities and ids are staged once per neighbour cell next to the
+// positions and read conflict-free from shared memory.
+//
+// Saru PRNG (Afshar et al., Comput. Phys. Commun. 184 (2013) 1119; third_party/saruprng.cuh:257-280 seeding,
+// :196-213,:339-351 stepping/output, :115-128 Box-Muller) is restated below; its constants are the algorithm.
+#include "pair_common.cuh"
+#include <cfloat>
+
+namespace ub200 {
+
+struct Saru {
+  uint32_t lcg, weyl;
+  __device__ __forceinline__ Saru(uint32_t s1, uint32_t s2, uint32_t s3) {
+    s3 ^= (s1 << 7) ^ (s2 >> 6);
+    s2 += (s1 >> 4) ^ (s3 >> 15);
+    s1 ^= (s2 << 9) + (s3 << 8);
+    s3 ^= 0xA5366B4Du * ((s2 >> 11) ^ (s1 << 1));
+    s2 += 0x72BE1579u * ((s1 << 4) ^ (s3 >> 16));
+    s1 ^= 0x3F38A6EDu * ((s3 >> 5) ^ (uint32_t)(((int32_t)s2) >> 22));
+    s2 += s1 * s3;
+    s1 += s3 ^ (s2 >> 2);
+    s2 ^= (uint32_t)(((int32_t)s2) >> 17);
+    lcg = 0x79dedea3u * (s1 ^ (uint32_t)(((int32_t)s1) >> 14));
+    weyl = (lcg + s2) ^ (uint32_t)(((int32_t)lcg) >> 8);
+    lcg = lcg + (weyl * (weyl ^ 0xdddf97f5u));
+    weyl = 0xABCB96F7u + (weyl >> 1);
+  }
+  __device__ __forceinline__ uint32_t u32() {
+    lcg = 0x4beb5d59u * lcg + 0x2600e1f7u;
+    weyl = weyl + 0x8009d14bu + ((uint32_t)(((int32_t)weyl) >> 31) & 0xda879addu);
+    const uint32_t v = (lcg ^ (lcg >> 26)) + weyl;
+    return (v ^ (v >> 20)) * 0x6957f5a7u;
+  }
+  __device__ __forceinline__ float f() { return ((int32_t)(u32() >> 1)) * (1.0f / 2147483648.0f); }
+  // first component of the Box-Muller pair gf(mean=0, std)
+  __device__ __forceinline__ float gaussX(float std) {
+    float u0;
+    do { u0 = f(); } while (u0 <= FLT_MIN);
+    const float u1 = f();
+    const float r = sqrtf(-2.0f * logf(u0));
+    const float theta = 6.283185307179586f * u1;
+    return (r * sinf(theta)) * std;
+  }
+};
+
+struct DPDPar {
+  float A, gamma, sigmaSqrtGamma, invrcut;
+  uint32_t seed, step;
+  int idStride;
+};
+
+__device__ __forceinline__ void dpdPair(float rx, float ry, float rz, float vx, float vy, float vz, int idi, int idj,
+                                        const DPDPar &p, float &fx, float &fy, float &fz) {
+  // rij = ri - rj, vij = vi - vj (DPD.cuh:123-124)
+  const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx));
+  const float rmod = __fsqrt_rn(r2);
+  if (rmod == 0.0f) return;
+  const float invrmod = __frcp_rn(rmod);
+  if (invrmod <= p.invrcut) return;
+  int i = idi, j = idj;
+  if (i > j) { const int t = i; i = j; j = t; }
+  const uint32_t ij = (uint32_t)i + (uint32_t)p.idStride * (uint32_t)j; // int32 wrap of i + N*j (DPD.cuh:128)
+  Saru rng(ij, p.seed, p.step);
+  const float wr = __fmaf_rn(-rmod, p.invrcut, 1.0f);
+  const float Fc = p.A * wr * invrmod;
+  const float wd = wr * wr;
+  const float rv = __fmaf_rn(rz, vz, __fmaf_rn(ry, vy, rx * vx));
+  const float Fd = -p.gamma * wd * invrmod * invrmod * rv;
+  const float Fr = rng.gaussX(p.sigmaSqrtGamma * wr * invrmod);
+  const float ft = Fc + Fd + Fr;
+  fx = __fmaf_rn(ft, rx, fx);
+  fy = __fmaf_rn(ft, ry, fy);
+  fz = __fmaf_rn(ft, rz, fz);
+}
+
+constexpr int kDpdCap = 768; // staged candidates (pos + vel/id): 24 KB
+
+template <bool PAIRMIC>
+__global__ void __launch_bounds__(kPairThreads)
+dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
+                 const uint32_t *__restrict__ binStart, GridF g, int ncells, const float *__restrict__ vel, DPDPar par,
+                 float4 *__restrict__ force, const int *__restrict__ globalIdx) {
+  __shared__ float4 cand[kDpdCap];
+  __shared__ float4 candVel[kDpdCap]; // vx, vy, vz, id (bits)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+    const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
+    const NeighbourCells nc = describeNeighbours(g, cx, cy, cz, binStart, lane);
+    const int hStart = __shfl_sync(0xffffffffu, nc.start, nc.centre);
+    const int hCount = __shfl_sync(0xffffffffu, nc.count, nc.centre);
+    if (hCount == 0) continue;
+    const int hOff = __shfl_sync(0xffffffffu, nc.off, nc.centre);
+    const bool staged = nc.total <= kDpdCap;
+    if (staged) {
+      for (int c = warp; c < 27; c += kPairWarps) {
+        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+        if (cnt == 0) continue;
+        const int st = __shfl_sync(0xffffffffu, nc.start, c);
+        const int off = __shfl_sync(0xffffffffu, nc.off, c);
+        const float sx = __shfl_sync(0xffffffffu, nc.sx, c);
+        const float sy = __shfl_sync(0xffffffffu, nc.sy, c);
+        const float sz = __shfl_sync(0xffffffffu, nc.sz, c);
+        for (int t = lane; t < cnt; t += 32) {
+          float4 p = ldg4(sortPos + st + t);
+          if (!PAIRMIC) {
+            p.x = foldCoord(p.x, g.Lx, g.mx) + sx;
+            p.y = foldCoord(p.y, g.Ly, g.my) + sy;
+            p.z = foldCoord(p.z, g.Lz, g.mz) + sz;
+          }
+          const int gi = groupIndex[st + t];
+          const int id = globalIdx ? globalIdx[gi] : gi;
+          cand[off + t] = p;
+          candVel[off + t] = make_float4(__ldg(vel + 3 * (size_t)id), __ldg(vel + 3 * (size_t)id + 1),
+                                         __ldg(vel + 3 * (size_t)id + 2), __int_as_float(id));
+        }
+      }
+    }
+    __syncthreads();
+    for (int h = warp; h < hCount; h += kPairWarps) {
+      float4 pi, vi;
+      if (staged) {
+        pi = cand[hOff + h];
+        vi = candVel[hOff + h];
+      } else {
+        pi = ldg4(sortPos + hStart + h);
+        if (!PAIRMIC) {
+          pi.x = foldCoord(pi.x, g.Lx, g.mx);
+          pi.y = foldCoord(pi.y, g.Ly, g.my);
+          pi.z = foldCoord(pi.z, g.Lz, g.mz);
+        }
+        const int gi = groupIndex[hStart + h];
+        const int id = globalIdx ? globalIdx[gi] : gi;
+        vi = make_float4(vel[3 * (size_t)id], vel[3 * (size_t)id + 1], vel[3 * (size_t)id + 2], __int_as_float(id));
+      }
+      const int idi = __float_as_int(vi.w);
+      float fx = 0.f, fy = 0.f, fz = 0.f;
+      if (staged) {
+        for (int t = lane; t < nc.total; t += 32) {
+          const float4 pj = cand[t];
+          const float4 vj = candVel[t];
+          float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+          if (PAIRMIC) {
+            rx = foldCoord(rx, g.Lx, g.mx);
+            ry = foldCoord(ry, g.Ly, g.my);
+            rz = foldCoord(rz, g.Lz, g.mz);
+          }
+          dpdPair(rx, ry, rz, vi.x - vj.x, vi.y - vj.y, vi.z - vj.z, idi, __float_as_int(vj.w), par, fx, fy, fz);
+        }
+      } else {
+        for (int c = 0; c < 27; c++) {
+          const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+          if (cnt == 0) continue;
+          const int st = __shfl_sync(0xffffffffu, nc.start, c);
+          const float sx = __shfl_sync(0xffffffffu, nc.sx, c);
+          const float sy = __shfl_sync(0xffffffffu, nc.sy, c);
+          const float sz = __shfl_sync(0xffffffffu, nc.sz, c);
+          for (int t = lane; t < cnt; t += 32) {
+            const float4 pj = ldg4(sortPos + st + t);
+            const int gj = groupIndex[st + t];
+            const int idj = globalIdx ? globalIdx[gj] : gj;
+            float rx, ry, rz;
+            if (PAIRMIC) {
+              rx = foldCoord(pi.x - pj.x, g.Lx, g.mx);
+              ry = foldCoord(pi.y - pj.y, g.Ly, g.my);
+              rz = foldCoord(pi.z - pj.z, g.Lz, g.mz);
+            } else {
+              rx = pi.x - (foldCoord(pj.x, g.Lx, g.mx) + sx);
+              ry = pi.y - (foldCoord(pj.y, g.Ly, g.my) + sy);
+              rz = pi.z - (foldCoord(pj.z, g.Lz, g.mz) + sz);
+            }
+            dpdPair(rx, ry, rz, vi.x - vel[3 * (size_t)idj], vi.y - vel[3 * (size_t)idj + 1],
+                    vi.z - vel[3 * (size_t)idj + 2], idi, idj, par, fx, fy, fz);
+          }
+        }
+      }
+      fx = warpSum(fx);
+      fy = warpSum(fy);
+      fz = warpSum(fz);
+      if (lane == 0) {
+        // ForceTransverser::set: force[pi] += make_real4(total) (make_real4(real3) zero-fills w)
+        float4 f = force[idi];
+        f.x += fx; f.y += fy; f.z += fz;
+        force[idi] = f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+} // namespace ub200
+
+using namespace ub200;
+
+extern "C" int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
+                                 uint32_t seed, uint32_t step, int idStride, void *d_force, const int *d_globalIdx,
+                                 void *stream) {
+  if (!cl || !d_vel || !d_force || !(rcut > 0)) return UB200_ERR_INVALID_ARGUMENT;
+  if (!cl->built) return UB200_ERR_NOT_BUILT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridF &g = cl->grid;
+  const bool pairMic = (g.mx != 0.0f && g.nx < 4) || (g.my != 0.0f && g.ny < 4) || (g.mz != 0.0f && g.nz < 4);
+  DPDPar par;
+  par.A = A;
+  par.gamma = gamma;
+  par.sigmaSqrtGamma = sigma * sqrtf(gamma); // sigma*sqrt(g), evaluated per pair in the reference (DPD.cuh:148)
+  par.invrcut = (float)(1.0 / (double)rcut); // invrcut(1.0/rcut) (DPD.cuh:110)
+  par.seed = seed;
+  par.step = step;
+  par.idStride = idStride;
+  static int bps[2] = {0, 0};
+  if (!bps[pairMic]) {
+    if (pairMic) UB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], dpdCellTraversal<true>, kPairThreads, 0));
+    else UB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], dpdCellTraversal<false>, kPairThreads, 0));
+    if (bps[pairMic] < 1) bps[pairMic] = 1;
+  }
+  int grid = kNumSMs * bps[pairMic];
+  if (grid > cl->ncells) grid = cl->ncells;
+  if (pairMic)
+    dpdCellTraversal<true><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
+                                                          cl->binStart.as<uint32_t>(), g, cl->ncells,
+                                                          (const float *)d_vel, par, (float4 *)d_force, d_globalIdx);
+  else
+    dpdCellTraversal<false><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
+                                                           cl->binStart.as<uint32_t>(), g, cl->ncells,
+                                                           (const float *)d_vel, par, (float4 *)d_force, d_globalIdx);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}

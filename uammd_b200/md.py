@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's operator interface for path 1 (short-range pair forces).
+
+Same names, argument meaning and error behaviour as the reference classes they stand in for:
+  Box                  utils/Box.cuh:15-98
+  LJ                   Interactor/Potential/Potential.cuh:25-86 (Potential::LJ = Radial<LJFunctor>)
+  CellList             Interactor/NeighbourList/CellList.cuh:66-208 (+ CellListBase::CellListData)
+  PairForces           Interactor/PairForces.cuh:23-68, PairForces.cu:43-78 (Interactor::sum)
+  VerletNVE            Integrator/VerletNVE.cu:174-188 (Integrator::forwardTime)
+Everything computes through the C ABI (include/uammd_b200.h); torch only owns device memory/streams.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import UB200Error, check, f3, i3
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+_cudart = None
+
+
+def _memcpy_d2d(dst_ptr, src_ptr, nbytes):
+    global _cudart
+    if _cudart is None:
+        _cudart = C.CDLL("libcudart.so.12")
+        _cudart.cudaMemcpy.restype = C.c_int
+        _cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    err = _cudart.cudaMemcpy(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nbytes, 3)
+    if err != 0:
+        raise UB200Error(f"cudaMemcpy D2D failed with cudaError {err}")
+
+
+def _device_copy(ptr, shape, dtype, device):
+    out = torch.empty(shape, dtype=dtype, device=device)
+    if out.numel():
+        torch.cuda.current_stream().synchronize()
+        _memcpy_d2d(out.data_ptr(), ptr, out.numel() * out.element_size())
+    return out
+
+
+class Box:
+    """utils/Box.cuh: box sizes and per-dimension periodicity."""
+
+    def __init__(self, L):
+        if np.isscalar(L):
+            L = (L, L, L)
+        self.boxSize = tuple(float(np.float32(x)) for x in L)
+        self.periodic = [not (x == 0.0 or math.isinf(x)) for x in self.boxSize]
+
+    def setPeriodicity(self, x, y, z):
+        self.periodic = [p and bool(f) for p, f in zip(self.periodic, (x, y, z))]
+
+    def __eq__(self, other):
+        return isinstance(other, Box) and self.boxSize == other.boxSize and self.periodic == other.periodic
+
+
+class LJ:
+    """Potential::LJ. setPotParameters(ti, tj, cutOff=, sigma=, epsilon=, shift=) like
+    Radial::setPotParameters (RadialPotential.cuh:75-81); the table rows are LJFunctor::PairParameters
+    {cutOff2, sigma2, epsilonDivSigma2, shift} computed as processPairParameters does (Potential.cuh:67-82)."""
+
+    def __init__(self):
+        self._pairs = {}
+        self.ntypes = 0
+
+    def setPotParameters(self, ti, tj, cutOff, sigma=1.0, epsilon=1.0, shift=False):
+        f = np.float32
+        cutOff, sigma, epsilon = f(cutOff), f(sigma), f(epsilon)
+        cutOff2 = f(cutOff * cutOff)
+        sigma2 = f(sigma * sigma)
+        eds2 = f(epsilon / sigma2)
+        sh = f(0.0)
+        if shift:
+            ic2 = f(sigma2 / cutOff2)
+            ic6 = f(f(ic2 * ic2) * ic2)
+            sh = f(f(f(epsilon * f(4.0)) * ic6) * f(ic6 - f(1.0)))
+        row = (cutOff2, sigma2, eds2, sh, cutOff)
+        self._pairs[(ti, tj)] = row
+        self._pairs[(tj, ti)] = row
+        self.ntypes = max(self.ntypes, ti + 1, tj + 1)
+
+    def getCutOff(self):
+        if not self._pairs:
+            raise UB200Error("LJ: no pair parameters set")
+        return float(max(r[4] for r in self._pairs.values()))
+
+    def table(self):
+        n = self.ntypes
+        t = np.zeros((n, n, 4), dtype=np.float32)
+        for (a, b), r in self._pairs.items():
+            t[a, b] = r[:4]
+        return np.ascontiguousarray(t.reshape(-1))
+
+
+class CellList:
+    """NeighbourList concept: update(pos, box, cutOff) rebuilds the list on every call (the reference's
+    force_next_update is never cleared), getCellList() exposes CellListData."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(_lib.lib().ub200_celllist_create(C.byref(self._h)))
+        self.N = 0
+        self.device = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().ub200_celllist_destroy(self._h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def gridFor(box, cutOff):
+        cd = i3((0, 0, 0))
+        check(_lib.lib().ub200_neighbour_celldim_f32(f3(box.boxSize), float(cutOff), cd))
+        return tuple(cd)
+
+    def update(self, pos, box, cutOff, stream=None, cellDim=None, groupIndex=None):
+        if pos.dtype != torch.float32 or pos.dim() != 2 or pos.shape[1] != 4 or not pos.is_cuda:
+            raise UB200Error("CellList.update: pos must be a CUDA float32 [N,4] tensor (real4)")
+        if not pos.is_contiguous():
+            raise UB200Error("CellList.update: pos must be contiguous")
+        N = pos.shape[0] if groupIndex is None else groupIndex.shape[0]
+        cd = cellDim if cellDim is not None else self.gridFor(box, cutOff)
+        check(_lib.lib().ub200_celllist_build_f32(self._h, _ptr(pos), _ptr(groupIndex), N, f3(box.boxSize),
+                                                  i3([int(p) for p in box.periodic]), i3(cd), _stream_ptr(stream)))
+        self.N, self.device, self.cellDim = N, pos.device, tuple(cd)
+
+    def view(self):
+        v = _lib.CellListView()
+        check(_lib.lib().ub200_celllist_view_get(self._h, C.byref(v)))
+        return v
+
+    def errorFlag(self):
+        flag = C.c_int(0)
+        check(_lib.lib().ub200_celllist_error_flag(self._h, _stream_ptr(), C.byref(flag)))
+        return flag.value
+
+    def getCellList(self):
+        """Copies of the CellListData arrays (CellListBase.cuh:145-160) as torch tensors."""
+        v = self.view()
+        ncells = v.cellDim[0] * v.cellDim[1] * v.cellDim[2]
+        dev = self.device
+        return {
+            "cellStart": _device_copy(v.d_cellStart, (ncells,), torch.int32, dev),  # uint32 bit pattern
+            "cellEnd": _device_copy(v.d_cellEnd, (ncells,), torch.int32, dev),
+            "sortPos": _device_copy(v.d_sortPos, (v.numberParticles, 4), torch.float32, dev),
+            "groupIndex": _device_copy(v.d_groupIndex, (v.numberParticles,), torch.int32, dev),
+            "VALID_CELL": int(v.VALID_CELL),
+            "cellDim": tuple(v.cellDim),
+            "binStart": _device_copy(v.d_binStart, (v.nbins + 1,), torch.int32, dev),
+        }
+
+    def normalizedCells(self):
+        """cellStart/cellEnd with the VALID_CELL epoch removed: -1 for empty cells (parity helper)."""
+        d = self.getCellList()
+        cs = d["cellStart"].cpu().numpy().view(np.uint32).astype(np.int64)
+        ce = d["cellEnd"].cpu().numpy().astype(np.int64)
+        empty = cs < d["VALID_CELL"]
+        cs = np.where(empty, -1, cs - d["VALID_CELL"])
+        ce = np.where(empty, -1, ce)
+        return cs, ce
+
+
+class PairForces:
+    """Interactor: sum(pos, force=, energy=, virial=) accumulates (+=) like Transverser::set."""
+
+    def __init__(self, potential, box, nl=None):
+        self.pot, self.box = potential, box
+        self.nl = nl if nl is not None else CellList()
+
+    def updateBox(self, box):
+        self.box = box
+
+    def sum(self, pos, force=None, energy=None, virial=None, stream=None, globalIndex=None):
+        rcut = self.pot.getCutOff()
+        L = self.box.boxSize
+        if all(l <= 3 * rcut for l in L):
+            # PairForces.cu:49-53 switches to NBody here; that O(N^2) fallback is out of scope
+            raise UB200Error("PairForces: box <= 3*rcut in every dimension needs the NBody fallback (out of scope)")
+        self.nl.update(pos, self.box, rcut, stream)
+        self.sumWithCurrentList(force, energy, virial, stream, globalIndex)
+
+    def sumWithCurrentList(self, force=None, energy=None, virial=None, stream=None, globalIndex=None):
+        tab = self.pot.table()
+        check(_lib.lib().ub200_lj_sum_f32(self.nl._h, tab.ctypes.data_as(C.POINTER(C.c_float)), self.pot.ntypes,
+                                          _ptr(force), _ptr(energy), _ptr(virial), _ptr(globalIndex),
+                                          _stream_ptr(stream)))
+
+
+class DPD:
+    """Potential::DPD parameters (Interactor/Potential/DPD.cuh:51-92). sigma = sqrt(2 T)/sqrt(dt)."""
+
+    def __init__(self, cutOff=1.0, dt=0.01, gamma=1.0, temperature=1.0, A=1.0, seed=0):
+        self.rcut, self.dt, self.gamma, self.temperature, self.A = cutOff, dt, gamma, temperature, A
+        self.seed, self.step = int(seed) & 0xFFFFFFFF, 0
+        self._updateSigma()
+
+    def _updateSigma(self):
+        self.sigma = float(np.float32(np.sqrt(2.0 * self.temperature) / np.sqrt(self.dt)))
+
+    def getCutOff(self):
+        return self.rcut
+
+    def updateTemperature(self, T):
+        self.temperature = T
+        self._updateSigma()
+
+    def updateTimeStep(self, dt):
+        self.dt = dt
+        self._updateSigma()
+
+
+class PairForcesDPD:
+    """PairForces<Potential::DPD> through a getTransverser adaptor (the stock Potential::DPD only exposes the
+    pre-v2 getForceTransverser and is silently skipped by PairForces). step is incremented before
+    every force evaluation like DPD_impl::getForceTransverser (DPD.cuh:161-170)."""
+
+    def __init__(self, potential, box, nl=None):
+        self.pot, self.box = potential, box
+        self.nl = nl if nl is not None else CellList()
+
+    def sum(self, pos, vel, force, stream=None, globalIndex=None):
+        self.nl.update(pos, self.box, self.pot.getCutOff(), stream)
+        self.pot.step += 1
+        p = self.pot
+        check(_lib.lib().ub200_dpd_sum_f32(self.nl._h, _ptr(vel), p.A, p.gamma, p.sigma, p.rcut, p.seed,
+                                           p.step & 0xFFFFFFFF, pos.shape[0], _ptr(force), _ptr(globalIndex),
+                                           _stream_ptr(stream)))
+
+
+class VerletNVE:
+    """Integrator: forwardTime() = kick+drift, reset forces, sum interactors, kick (VerletNVE.cu:174-188)."""
+
+    def __init__(self, pos, vel, dt, mass=1.0, is2D=False):
+        self.pos, self.vel, self.dt, self.mass, self.is2D = pos, vel, float(dt), float(mass), bool(is2D)
+        self.force = torch.zeros_like(pos)
+        self.interactors = []
+        self.steps = 0
+
+    def addInteractor(self, it):
+        self.interactors.append(it)
+
+    def _half(self, step):
+        N = self.pos.shape[0]
+        check(_lib.lib().ub200_nve_half_step_f32(_ptr(self.pos), _ptr(self.vel), _ptr(self.force), C.c_void_p(0),
+                                                 self.mass, C.c_void_p(0), N, self.dt, int(self.is2D), step,
+                                                 _stream_ptr()))
+
+    def _sumForces(self):
+        self.force.zero_()
+        for it in self.interactors:
+            it.sum(self.pos, force=self.force)
+
+    def forwardTime(self):
+        self.steps += 1
+        if self.steps == 1:
+            self._sumForces()
+        self._half(1)
+        self._sumForces()
+        self._half(2)
+
+
+class LJMD:
+    """Fused engine for VerletNVE + PairForces<LJ, CellList> (ub200_md_* in include/uammd_b200.h)."""
+
+    def __init__(self, box, potential, dt):
+        self.box, self.pot, self.dt = box, potential, float(dt)
+        self._h = C.c_void_p()
+        check(_lib.lib().ub200_md_create(C.byref(self._h)))
+        self._tab = potential.table()
+        self._tabp = self._tab.ctypes.data_as(C.POINTER(C.c_float))
+        self.prepared = False
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().ub200_md_destroy(self._h)
+        except Exception:
+            pass
+
+    def prepare(self, pos, force, stream=None):
+        check(_lib.lib().ub200_md_lj_nve_prepare_f32(self._h, _ptr(pos), _ptr(force), pos.shape[0],
+                                                     f3(self.box.boxSize), self.pot.getCutOff(), self._tabp,
+                                                     self.pot.ntypes, _stream_ptr(stream)))
+        self.prepared = True
+
+    def run(self, pos, vel, force, nsteps, stream=None):
+        if not self.prepared:
+            self.prepare(pos, force, stream)
+        check(_lib.lib().ub200_md_lj_nve_run_f32(self._h, _ptr(pos), _ptr(vel), _ptr(force), pos.shape[0],
+                                                 f3(self.box.boxSize), self.pot.getCutOff(), self._tabp,
+                                                 self.pot.ntypes, self.dt, int(nsteps), _stream_ptr(stream)))
+
+    def runHost(self, h_pos, h_vel, h_force, nsteps, stream=None):
+        """Host (pinned) buffers in/out: H2D, prepare, nsteps, D2H, synchronise."""
+        check(_lib.lib().ub200_md_lj_nve_run_host_f32(self._h, _ptr(h_pos), _ptr(h_vel), _ptr(h_force),
+                                                      h_pos.shape[0], f3(self.box.boxSize), self.pot.getCutOff(),
+                                                      self._tabp, self.pot.ntypes, self.dt, int(nsteps),
+                                                      _stream_ptr(stream)))
