@@ -54,10 +54,12 @@ int orc_celllist_build_f(const orc_grid_f *g, const float *pos4, int N, float *s
 void orc_lj_f32(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
                 const int *cellEnd, int N, const float *params4, int ntypes, float *force4, float *energy,
                 float *virial);
-/* same pair set, all arithmetic in fp64 from the fp32 inputs ("truth"); abssum = sum_j |f_ij| per particle */
+/* same pair set, all arithmetic in fp64 from the fp32 inputs ("truth"); abssum = sum_j |f_ij| per particle,
+   sens = sum_j |d f_ij / d r_ij| (how far a perturbation of the separations moves the force),
+   edge = sum of |f_ij| over pairs with |r2 - rc2| <= band (pairs that fp32 rounding can move across the cut-off) */
 void orc_lj_f64(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
                 const int *cellEnd, int N, const float *params4, int ntypes, double *force3, double *energy,
-                double *virial, double *abssum);
+                double *virial, double *abssum, double *sens, double band, double *edge);
 
 /* DPD pair forces (Interactor/Potential/DPD.cuh:121-158) */
 void orc_dpd_f32(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,

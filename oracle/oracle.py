@@ -108,15 +108,44 @@ def lj_f32(grid, cl, params, ntypes, N, energy=False, virial=False):
     return force, e, v
 
 
+def _sep_uncertainty(L, rc):
+    """fp32 uncertainty of a pair separation: see LJScale."""
+    return 2.0 ** -23 * (float(np.max(L)) + 8.0 * rc)
+
+
 def lj_f64(grid, cl, params, ntypes, N):
     force = np.zeros((N, 3), np.float64)
     e = np.zeros(N, np.float64)
     v = np.zeros(N, np.float64)
     a = np.zeros(N, np.float64)
+    s = np.zeros(N, np.float64)
+    g = np.zeros(N, np.float64)
     params = np.ascontiguousarray(params, np.float32)
+    rcmax = float(np.sqrt(params.reshape(-1, 4)[:, 0].max()))
+    band = 2.0 * rcmax * 2.0 * _sep_uncertainty(tuple(grid.L), rcmax)  # |d r2| = 2 r |dr|, both particles
     lib().orc_lj_f64(C.byref(grid), _p(cl["sortPos"]), _p(cl["index"]), _p(cl["cellStart"]), _p(cl["cellEnd"]),
-                     N, _p(params), ntypes, _p(force), _p(e), _p(v), _p(a))
-    return force, e, v, a
+                     N, _p(params), ntypes, _p(force), _p(e), _p(v), _p(a), _p(s), C.c_double(band), _p(g))
+    return force, e, v, LJScale(a, s, g)
+
+
+class LJScale:
+    """Per particle error scales from the fp64 pass: abssum = sum_j |f_ij|, sens = sum_j |df_ij/dr|.
+
+    force_tol(L, rc): the fp32 error model used by the parity tests. A separation is known to
+    ~2^-23 * max(|x|) <= 2^-23 * L (positions are fp32 numbers of box scale and pairs across the periodic
+    boundary pick up one more rounding of that size), r2 and the force polynomial add a few relative
+    roundings (8 * 2^-23 * rc in separation terms), and the sum itself 2e-6 relative to sum |f_ij|.
+    The unshifted LJ force is discontinuous at the cut-off (|f(rc)| ~ 0.04 eps/sigma): edge = sum of |f_ij|
+    over the pairs whose r2 lies within that separation uncertainty of rc2, which either side may count."""
+
+    def __init__(self, abssum, sens, edge=0.0):
+        self.abssum, self.sens, self.edge = abssum, sens, edge
+
+    def force_tol(self, L, rc):
+        return _sep_uncertainty(L, rc) * self.sens + 2e-6 * self.abssum + 1.01 * self.edge + 1e-30
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.abssum, dtype=dtype)
 
 
 def dpd_f32(grid, cl, vel3, A, gamma, sigma, rcut, seed, step, N):

@@ -240,14 +240,14 @@ void orc_lj_f32(const orc_grid_f *g, const float *sortPos4, const int *index, co
 
 void orc_lj_f64(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
                 const int *cellEnd, int N, const float *params4, int ntypes, double *force3, double *energy,
-                double *virial, double *abssum) {
+                double *virial, double *abssum, double *sens, double band, double *edge) {
 #pragma omp parallel for schedule(dynamic, 256)
   for (int id = 0; id < N; id++) {
     const float *pi = sortPos4 + 4 * (size_t)id;
     int celli[3], cells[27];
     orc_get_cell_f(g, pi, celli);
     const int ncl = neighbour_cells(g, celli, cells);
-    double F[3] = {0, 0, 0}, E = 0, V = 0, A = 0;
+    double F[3] = {0, 0, 0}, E = 0, V = 0, A = 0, S = 0, G = 0;
     for (int c = 0; c < ncl; c++) {
       const int cs = cellStart[cells[c]];
       if (cs < 0) continue;
@@ -263,11 +263,16 @@ void orc_lj_f64(const orc_grid_f *g, const float *sortPos4, const int *index, co
         }
         if (r2 == 0.0) continue;
         const float *p = params4 + 4 * ((int)pi[3] * ntypes + (int)pj[3]);
-        if (r2 >= (double)p[0]) continue;
         const double invr2 = (double)p[1] / r2, invr6 = invr2 * invr2 * invr2;
         const double fm = (double)p[2] * (-48.0 * invr6 + 24.0) * invr6 * invr2;
+        /* the unshifted force jumps by |f(rc)| at the cut-off: a pair within the fp32 uncertainty band of rc
+           may legitimately be counted on either side */
+        if (fabs(r2 - (double)p[0]) <= band) G += fabs(fm) * sqrt(r2);
+        if (r2 >= (double)p[0]) continue;
         for (int d = 0; d < 3; d++) F[d] += fm * r12[d];
         A += fabs(fm) * sqrt(r2);
+        /* |d|F|/dr| = 24 eps/sigma^2 * |7 u^4 - 26 u^7| (u = sigma^2/r^2): sensitivity of the pair force to r */
+        S += 24.0 * (double)p[2] * fabs(7.0 * invr6 * invr2 - 26.0 * invr6 * invr6 * invr2);
         E += 0.5 * ((double)p[2] * (double)p[1] * 4.0 * invr6 * (invr6 - 1.0) - (double)p[3]);
         V += fm * r2;
       }
@@ -277,6 +282,8 @@ void orc_lj_f64(const orc_grid_f *g, const float *sortPos4, const int *index, co
     if (energy) energy[ori] += E;
     if (virial) virial[ori] += V;
     if (abssum) abssum[ori] += A;
+    if (sens) sens[ori] += S;
+    if (edge) edge[ori] += G;
   }
 }
 

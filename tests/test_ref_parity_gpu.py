@@ -64,15 +64,16 @@ def test_reference_parity(orc, cuda, tmp_path, N, kind):
     ocl = orc.celllist_build(g, pos)
     assert np.array_equal(ocl["index"], ref["index"]) and np.array_equal(ocl["cellStart"], ref["cellStart"])
     # --- forces: both implementations vs fp64 truth ---
-    f64, e64, v64, a = orc.lj_f64(g, ocl, pot.table(), 1, N)
-    a = np.maximum(a, 1e-30)
-    err_ref = (np.abs(ref["force"][:, :3] - f64).max(axis=1) / a).max()
-    err_new = (np.abs(force.cpu().numpy()[:, :3] - f64).max(axis=1) / a).max()
-    direct = (np.abs(force.cpu().numpy()[:, :3] - ref["force"][:, :3]).max(axis=1) / a).max()
-    print(f"[parity N={N} {kind}] reference vs fp64 {err_ref:.3e}; new vs fp64 {err_new:.3e}; new vs reference {direct:.3e}")
-    assert err_new < 2e-4 and err_ref < 2e-4 and direct < 2e-4
+    f64, e64, v64, sc = orc.lj_f64(g, ocl, pot.table(), 1, N)
+    tol = sc.force_tol(L, 2.5)   # the fp32 error model of tests/test_lj_gpu.py
+    err_ref = (np.abs(ref["force"][:, :3] - f64).max(axis=1) / tol).max()
+    err_new = (np.abs(force.cpu().numpy()[:, :3] - f64).max(axis=1) / tol).max()
+    direct = (np.abs(force.cpu().numpy()[:, :3] - ref["force"][:, :3]).max(axis=1) / tol).max()
+    print(f"[parity N={N} {kind}] in units of the fp32 tolerance: reference vs fp64 {err_ref:.3f}; "
+          f"new vs fp64 {err_new:.3f}; new vs reference {direct:.3f}")
+    assert err_new < 1.0 and err_ref < 1.0 and direct < 2.0
     # the restated fp32 oracle in reference order should be (nearly) the reference's bits
     f32, _, _ = orc.lj_f32(g, ocl, pot.table(), 1, N)
-    assert (np.abs(f32[:, :3] - ref["force"][:, :3]).max(axis=1) / a).max() < 2e-5
+    assert (np.abs(f32[:, :3] - ref["force"][:, :3]).max(axis=1) / tol).max() < 0.5
     assert np.allclose(e.cpu().numpy(), ref["energy"], rtol=2e-4, atol=2e-4 * np.abs(ref["energy"]).max())
     assert np.allclose(v.cpu().numpy(), ref["virial"], rtol=2e-4, atol=2e-4 * np.abs(ref["virial"]).max())

@@ -64,12 +64,13 @@ struct GridF {
   float mx, my, mz; // minusInvBoxSize, 0 when the dimension is not periodic
   float hLx, hLy, hLz; // 0.5*L (exact)
   float ix, iy, iz; // invCellSize
+  float csx, csy, csz; // cellSize
   int nx, ny, nz;
 };
 
 inline GridF makeGridF(const float L[3], const int periodic[3], const int cellDim[3]) {
   GridF g;
-  float m[3], inv[3];
+  float m[3], inv[3], csz[3];
   int n[3];
   for (int d = 0; d < 3; d++) {
     m[d] = -1.0f / L[d];
@@ -78,12 +79,14 @@ inline GridF makeGridF(const float L[3], const int periodic[3], const int cellDi
     if (d == 2 && n[d] == 0) n[d] = 1;
     const float cs = L[d] / (float)n[d];
     inv[d] = 1.0f / cs;
+    csz[d] = cs;
   }
   if (L[2] == 0.0f) inv[2] = 0.0f;
   g.Lx = L[0]; g.Ly = L[1]; g.Lz = L[2];
   g.mx = m[0]; g.my = m[1]; g.mz = m[2];
   g.hLx = 0.5f * L[0]; g.hLy = 0.5f * L[1]; g.hLz = 0.5f * L[2];
   g.ix = inv[0]; g.iy = inv[1]; g.iz = inv[2];
+  g.csx = csz[0]; g.csy = csz[1]; g.csz = csz[2];
   g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
   return g;
 }
@@ -121,6 +124,15 @@ __host__ __device__ __forceinline__ uint32_t compactBits10(uint32_t x) {
   x = (x | (x >> 8)) & 0x30000ffu;
   x = (x | (x >> 16)) & 0x3ffu;
   return x;
+}
+
+// Periodic image of coordinate r closest to the reference point c (valid whenever the true separation is
+// below L/2, i.e. for neighbour-cell candidates on grids with >= 4 cells per periodic dimension). Unlike
+// "fold into the box, then add the image shift of the cell", this is robust for particles whose stored
+// coordinate sits outside the geometric bounds of their cell (x == +L/2 is assigned to cell 0 by Grid::getCell).
+__device__ __forceinline__ float imageNear(float r, float c, float L, float minusInvL) {
+  const float off = floorf(__fmaf_rn(r - c, minusInvL, 0.5f));
+  return __fmaf_rn(off, L, r);
 }
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }

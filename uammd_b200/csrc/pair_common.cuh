@@ -10,7 +10,6 @@ constexpr int kCandCap = 1024; // staged candidates per home cell (16 KB); dense
 
 struct NeighbourCells {
   int start, count, off; // per lane (= neighbour cell slot): first sorted index, population, exclusive prefix
-  float sx, sy, sz;      // periodic image shift of that cell
   int total, centre;     // warp uniform
 };
 
@@ -22,7 +21,7 @@ __device__ __forceinline__ NeighbourCells describeNeighbours(const GridF &g, int
   const int npx = g.nx > 1 ? 3 : 1, npy = g.ny > 1 ? 3 : 1, npz = g.nz > 1 ? 3 : 1;
   const int ncell = npx * npy * npz;
   nc.centre = (npx > 1) + npx * (npy > 1) + npx * npy * (npz > 1);
-  nc.start = 0; nc.count = 0; nc.sx = nc.sy = nc.sz = 0.0f;
+  nc.start = 0; nc.count = 0;
   if (lane < ncell) {
     int jx = cx + (npx > 1 ? lane % 3 - 1 : 0);
     int jy = cy + (npy > 1 ? (lane / npx) % 3 - 1 : 0);
@@ -30,12 +29,12 @@ __device__ __forceinline__ NeighbourCells describeNeighbours(const GridF &g, int
     bool valid = true;
     // Grid::pbc_cell (utils/Grid.cuh:81-106): single wrap in periodic dims; non periodic dims keep the raw
     // coordinate, whose out-of-range cells can hold nothing within the cut-off -> skipped here.
-    if (jx < 0) { if (g.mx != 0.0f) { jx += g.nx; nc.sx = -g.Lx; } else valid = false; }
-    else if (jx >= g.nx) { if (g.mx != 0.0f) { jx -= g.nx; nc.sx = g.Lx; } else valid = false; }
-    if (jy < 0) { if (g.my != 0.0f) { jy += g.ny; nc.sy = -g.Ly; } else valid = false; }
-    else if (jy >= g.ny) { if (g.my != 0.0f) { jy -= g.ny; nc.sy = g.Ly; } else valid = false; }
-    if (jz < 0) { if (g.mz != 0.0f) { jz += g.nz; nc.sz = -g.Lz; } else valid = false; }
-    else if (jz >= g.nz) { if (g.mz != 0.0f) { jz -= g.nz; nc.sz = g.Lz; } else valid = false; }
+    if (jx < 0) { if (g.mx != 0.0f) jx += g.nx; else valid = false; }
+    else if (jx >= g.nx) { if (g.mx != 0.0f) jx -= g.nx; else valid = false; }
+    if (jy < 0) { if (g.my != 0.0f) jy += g.ny; else valid = false; }
+    else if (jy >= g.ny) { if (g.my != 0.0f) jy -= g.ny; else valid = false; }
+    if (jz < 0) { if (g.mz != 0.0f) jz += g.nz; else valid = false; }
+    else if (jz >= g.nz) { if (g.mz != 0.0f) jz -= g.nz; else valid = false; }
     if (valid) {
       const uint32_t code = mortonCode(jx, jy, jz);
       const uint32_t s = __ldg(binStart + code), e = __ldg(binStart + code + 1);
@@ -52,6 +51,18 @@ __device__ __forceinline__ NeighbourCells describeNeighbours(const GridF &g, int
   nc.off = inc - nc.count;
   nc.total = __shfl_sync(0xffffffffu, inc, 31);
   return nc;
+}
+
+// centre of cell (cx,cy,cz) in box coordinates
+__device__ __forceinline__ float3 cellCentre(const GridF &g, int cx, int cy, int cz) {
+  return make_float3(__fmaf_rn((float)cx + 0.5f, g.csx, -g.hLx), __fmaf_rn((float)cy + 0.5f, g.csy, -g.hLy),
+                     __fmaf_rn((float)cz + 0.5f, g.csz, -g.hLz));
+}
+// bring p to the periodic image nearest the home cell centre c
+__device__ __forceinline__ void toHomeImage(float4 &p, const GridF &g, const float3 &c) {
+  p.x = imageNear(p.x, c.x, g.Lx, g.mx);
+  p.y = imageNear(p.y, c.y, g.Ly, g.my);
+  p.z = imageNear(p.z, c.z, g.Lz, g.mz);
 }
 
 __device__ __forceinline__ float warpSum(float v) {

@@ -95,22 +95,16 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
     if (hCount == 0) continue;
     const int hOff = __shfl_sync(0xffffffffu, nc.off, nc.centre);
     const bool staged = nc.total <= kDpdCap;
+    const float3 hc = cellCentre(g, cx, cy, cz);
     if (staged) {
       for (int c = warp; c < 27; c += kPairWarps) {
         const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
         if (cnt == 0) continue;
         const int st = __shfl_sync(0xffffffffu, nc.start, c);
         const int off = __shfl_sync(0xffffffffu, nc.off, c);
-        const float sx = __shfl_sync(0xffffffffu, nc.sx, c);
-        const float sy = __shfl_sync(0xffffffffu, nc.sy, c);
-        const float sz = __shfl_sync(0xffffffffu, nc.sz, c);
         for (int t = lane; t < cnt; t += 32) {
           float4 p = ldg4(sortPos + st + t);
-          if (!PAIRMIC) {
-            p.x = foldCoord(p.x, g.Lx, g.mx) + sx;
-            p.y = foldCoord(p.y, g.Ly, g.my) + sy;
-            p.z = foldCoord(p.z, g.Lz, g.mz) + sz;
-          }
+          if (!PAIRMIC) toHomeImage(p, g, hc);
           const int gi = groupIndex[st + t];
           const int id = globalIdx ? globalIdx[gi] : gi;
           cand[off + t] = p;
@@ -127,11 +121,7 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
         vi = candVel[hOff + h];
       } else {
         pi = ldg4(sortPos + hStart + h);
-        if (!PAIRMIC) {
-          pi.x = foldCoord(pi.x, g.Lx, g.mx);
-          pi.y = foldCoord(pi.y, g.Ly, g.my);
-          pi.z = foldCoord(pi.z, g.Lz, g.mz);
-        }
+        if (!PAIRMIC) toHomeImage(pi, g, hc);
         const int gi = groupIndex[hStart + h];
         const int id = globalIdx ? globalIdx[gi] : gi;
         vi = make_float4(vel[3 * (size_t)id], vel[3 * (size_t)id + 1], vel[3 * (size_t)id + 2], __int_as_float(id));
@@ -155,11 +145,8 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
           const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
           if (cnt == 0) continue;
           const int st = __shfl_sync(0xffffffffu, nc.start, c);
-          const float sx = __shfl_sync(0xffffffffu, nc.sx, c);
-          const float sy = __shfl_sync(0xffffffffu, nc.sy, c);
-          const float sz = __shfl_sync(0xffffffffu, nc.sz, c);
           for (int t = lane; t < cnt; t += 32) {
-            const float4 pj = ldg4(sortPos + st + t);
+            float4 pj = ldg4(sortPos + st + t);
             const int gj = groupIndex[st + t];
             const int idj = globalIdx ? globalIdx[gj] : gj;
             float rx, ry, rz;
@@ -168,9 +155,10 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
               ry = foldCoord(pi.y - pj.y, g.Ly, g.my);
               rz = foldCoord(pi.z - pj.z, g.Lz, g.mz);
             } else {
-              rx = pi.x - (foldCoord(pj.x, g.Lx, g.mx) + sx);
-              ry = pi.y - (foldCoord(pj.y, g.Ly, g.my) + sy);
-              rz = pi.z - (foldCoord(pj.z, g.Lz, g.mz) + sz);
+              toHomeImage(pj, g, hc);
+              rx = pi.x - pj.x;
+              ry = pi.y - pj.y;
+              rz = pi.z - pj.z;
             }
             dpdPair(rx, ry, rz, vi.x - vel[3 * (size_t)idj], vi.y - vel[3 * (size_t)idj + 1],
                     vi.z - vel[3 * (size_t)idj + 2], idi, idj, par, fx, fy, fz);

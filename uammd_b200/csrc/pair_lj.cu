@@ -4,11 +4,12 @@
 // + CellList_ns::NeighbourIterator (CellList/NeighbourContainer.cuh:95-138) + Radial<LJFunctor>::Transverser
 // (Potential/RadialPotential.cuh:107-127, Potential/Potential.cuh:37-65).
 //
-// Design (B200): persistent CTAs walk the home cells. For each home cell the particles of its (up to) 27
-// neighbour cells are staged ONCE into shared memory, already folded into the primary box and displaced by
-// the periodic image shift of their cell, so the inner loop needs no per-pair minimum-image arithmetic.
-// Each warp then owns one home particle at a time: its 32 lanes stride over the staged candidates
-// (conflict-free LDS.128), accumulate privately and finish with a shuffle reduction. The reference instead
+// Design (B200): persistent warps walk the home cells, one WARP per cell (no block barriers). For each home
+// cell the particles of its (up to) 27 neighbour cells are staged ONCE into the warp's slice of shared memory,
+// already folded into the primary box and displaced by the periodic image shift of their cell, so the inner
+// loop needs no per-pair minimum-image arithmetic. The warp then takes the home particles two at a time: its
+// 32 lanes stride over the staged candidates (one conflict-free LDS.128 feeds two pair evaluations), the LJ
+// body is branch free, and a half-warp split butterfly reduces both particles at once. The reference instead
 // runs one thread per particle through a divergent 27-cell iterator with ~340 dependent global loads.
 #include "pair_common.cuh"
 
@@ -22,87 +23,137 @@ struct Acc {
   float fx, fy, fz, e, v;
 };
 
+// One LJ pair, branch free. r2 is a non negative float, so its bit pattern orders like an unsigned integer:
+// (bits(r2) - 1) < (bits(rc2) - 1) <=> 0 < r2 < rc2 (r2 == 0 wraps to 0xffffffff) - two integer-pipe
+// instructions instead of two FSETPs. Out-of-range pairs get r2 = +inf, hence 1/r2 = 0 and a zero force.
+// The reciprocal is MUFU.RCP (1 ulp); with u = sigma2/r2: |F|/r = epsDivSigma2 (24 - 48 u^3) u^4.
 template <bool ENERGY, bool VIRIAL>
-__device__ __forceinline__ void ljPair(float dx, float dy, float dz, const LJPar &p, Acc &a) {
+__device__ __forceinline__ void ljPair(float dx, float dy, float dz, const LJPar &p, uint32_t rc2bitsm1, Acc &a) {
   const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-  if (r2 < p.cutOff2 && r2 != 0.0f) {
-    const float invr2 = __fdividef(p.sigma2, r2);
-    const float invr6 = invr2 * invr2 * invr2;
-    const float fm = p.epsDivSigma2 * __fmaf_rn(-48.0f, invr6, 24.0f) * invr6 * invr2;
-    a.fx = __fmaf_rn(fm, dx, a.fx);
-    a.fy = __fmaf_rn(fm, dy, a.fy);
-    a.fz = __fmaf_rn(fm, dz, a.fz);
-    if (ENERGY) a.e += 0.5f * (p.epsDivSigma2 * p.sigma2 * 4.0f * invr6 * (invr6 - 1.0f) - p.shift);
-    if (VIRIAL) a.v = __fmaf_rn(fm, r2, a.v);
-  }
+  const bool in = (__float_as_uint(r2) - 1u) < rc2bitsm1;
+  const float r2s = in ? r2 : __int_as_float(0x7f800000);
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r2s));
+  const float u = p.sigma2 * inv;
+  const float u2 = u * u;
+  const float u3 = u2 * u;
+  const float fm = (p.epsDivSigma2 * __fmaf_rn(-48.0f, u3, 24.0f)) * (u2 * u2);
+  a.fx = __fmaf_rn(fm, dx, a.fx);
+  a.fy = __fmaf_rn(fm, dy, a.fy);
+  a.fz = __fmaf_rn(fm, dz, a.fz);
+  if (ENERGY) a.e += in ? 0.5f * (p.epsDivSigma2 * p.sigma2 * 4.0f * u3 * (u3 - 1.0f) - p.shift) : 0.0f;
+  if (VIRIAL) a.v += in ? fm * r2 : 0.0f;
 }
 
-// PAIRMIC: per-pair minimum image exactly like Radial::Transverser::compute (box.apply_pbc(rj-ri)); needed
-// when a periodic dimension has fewer than 4 cells (a collapsed dimension still wraps). Otherwise the cell
-// image shift staged with the candidates is the minimum image.
+// Sum the 2x3 force components (and optionally energy/virial) of two home particles over the warp.
+// First exchange across lane halves so that each half carries one particle, then a 4 level butterfly.
+__device__ __forceinline__ void reducePair(Acc &a0, Acc &a1, int lane, bool ev) {
+  const bool hi = lane & 16;
+  // lanes 0-15 keep particle 0, lanes 16-31 keep particle 1
+  float sx = hi ? a0.fx : a1.fx, sy = hi ? a0.fy : a1.fy, sz = hi ? a0.fz : a1.fz;
+  float kx = hi ? a1.fx : a0.fx, ky = hi ? a1.fy : a0.fy, kz = hi ? a1.fz : a0.fz;
+  kx += __shfl_xor_sync(0xffffffffu, sx, 16);
+  ky += __shfl_xor_sync(0xffffffffu, sy, 16);
+  kz += __shfl_xor_sync(0xffffffffu, sz, 16);
+  float se = 0.f, sv = 0.f, ke = 0.f, kv = 0.f;
+  if (ev) {
+    se = hi ? a0.e : a1.e; sv = hi ? a0.v : a1.v;
+    ke = hi ? a1.e : a0.e; kv = hi ? a1.v : a0.v;
+    ke += __shfl_xor_sync(0xffffffffu, se, 16);
+    kv += __shfl_xor_sync(0xffffffffu, sv, 16);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    kx += __shfl_xor_sync(0xffffffffu, kx, o);
+    ky += __shfl_xor_sync(0xffffffffu, ky, o);
+    kz += __shfl_xor_sync(0xffffffffu, kz, o);
+    if (ev) {
+      ke += __shfl_xor_sync(0xffffffffu, ke, o);
+      kv += __shfl_xor_sync(0xffffffffu, kv, o);
+    }
+  }
+  // result for particle 0 in lane 0, particle 1 in lane 16 (stored in a0)
+  a0.fx = kx; a0.fy = ky; a0.fz = kz; a0.e = ke; a0.v = kv;
+}
+
+constexpr int kWarpCap = 416; // staged candidates per warp (6.5 KB, 8 CTAs/SM); denser neighbourhoods take the direct path
+
+// One WARP per home cell (no block level barriers). PAIRMIC: per-pair minimum image exactly like
+// Radial::Transverser::compute (box.apply_pbc(rj-ri)); needed when a periodic dimension has fewer than 4 cells
+// (a collapsed dimension still wraps). Otherwise the cell image shift staged with the candidates is the
+// minimum image.
 template <bool ENERGY, bool VIRIAL, bool MULTITYPE, bool PAIRMIC, bool ACCUMULATE>
-__global__ void __launch_bounds__(kPairThreads)
+__global__ void __launch_bounds__(kPairThreads, 8)
 ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
                 const uint32_t *__restrict__ binStart, GridF g, int ncells, LJPar par0,
                 const LJPar *__restrict__ parTable, int ntypes, float4 *__restrict__ force,
                 float *__restrict__ energy, float *__restrict__ virial, const int *__restrict__ globalIdx) {
-  __shared__ float4 cand[kCandCap];
+  __shared__ float4 candAll[kPairWarps][kWarpCap];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+  float4 *cand = candAll[warp];
+  const int warpsTotal = gridDim.x * kPairWarps;
+  const uint32_t rc2bitsm1 = __float_as_uint(par0.cutOff2) - 1u;
+  for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
     const NeighbourCells nc = describeNeighbours(g, cx, cy, cz, binStart, lane);
     const int hStart = __shfl_sync(0xffffffffu, nc.start, nc.centre);
     const int hCount = __shfl_sync(0xffffffffu, nc.count, nc.centre);
-    if (hCount == 0) continue; // CTA uniform
+    if (hCount == 0) continue; // warp uniform
     const int hOff = __shfl_sync(0xffffffffu, nc.off, nc.centre);
-    const bool staged = nc.total <= kCandCap;
+    const bool staged = nc.total <= kWarpCap;
+    const float3 hc = cellCentre(g, cx, cy, cz);
+    __syncwarp();
     if (staged) {
-      for (int c = warp; c < 27; c += kPairWarps) {
+      // two neighbour cells per pass, 16 lanes each
+      const int half = lane >> 4, l16 = lane & 15;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 27; c0 += 2) {
+        const int c = c0 + half;
         const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
-        if (cnt == 0) continue;
         const int st = __shfl_sync(0xffffffffu, nc.start, c);
         const int off = __shfl_sync(0xffffffffu, nc.off, c);
-        const float sx = __shfl_sync(0xffffffffu, nc.sx, c);
-        const float sy = __shfl_sync(0xffffffffu, nc.sy, c);
-        const float sz = __shfl_sync(0xffffffffu, nc.sz, c);
-        for (int t = lane; t < cnt; t += 32) {
+        for (int t = l16; t < cnt; t += 16) {
           float4 p = ldg4(sortPos + st + t);
-          if (!PAIRMIC) {
-            p.x = foldCoord(p.x, g.Lx, g.mx) + sx;
-            p.y = foldCoord(p.y, g.Ly, g.my) + sy;
-            p.z = foldCoord(p.z, g.Lz, g.mz) + sz;
-          }
+          if (!PAIRMIC) toHomeImage(p, g, hc);
           cand[off + t] = p;
         }
       }
     }
-    __syncthreads();
-    for (int h = warp; h < hCount; h += kPairWarps) {
-      float4 pi;
-      if (staged) pi = cand[hOff + h];
-      else {
-        pi = ldg4(sortPos + hStart + h);
+    __syncwarp();
+    for (int h = 0; h < hCount; h += 2) {
+      const bool two = h + 1 < hCount;
+      float4 pi0, pi1;
+      if (staged) {
+        pi0 = cand[hOff + h];
+        pi1 = cand[hOff + h + (two ? 1 : 0)];
+      } else {
+        pi0 = ldg4(sortPos + hStart + h);
+        pi1 = ldg4(sortPos + hStart + h + (two ? 1 : 0));
         if (!PAIRMIC) {
-          pi.x = foldCoord(pi.x, g.Lx, g.mx);
-          pi.y = foldCoord(pi.y, g.Ly, g.my);
-          pi.z = foldCoord(pi.z, g.Lz, g.mz);
+          toHomeImage(pi0, g, hc);
+          toHomeImage(pi1, g, hc);
         }
       }
-      Acc a = {0.f, 0.f, 0.f, 0.f, 0.f};
-      LJPar p = par0;
-      const int ti = MULTITYPE ? (int)pi.w * ntypes : 0;
+      Acc a0 = {0.f, 0.f, 0.f, 0.f, 0.f}, a1 = {0.f, 0.f, 0.f, 0.f, 0.f};
+      LJPar p0 = par0, p1 = par0;
+      uint32_t rcb0 = rc2bitsm1, rcb1 = rc2bitsm1;
+      const int t0 = MULTITYPE ? (int)pi0.w * ntypes : 0, t1 = MULTITYPE ? (int)pi1.w * ntypes : 0;
       if (staged) {
 #pragma unroll 2
         for (int t = lane; t < nc.total; t += 32) {
           const float4 pj = cand[t];
-          float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+          float dx0 = pj.x - pi0.x, dy0 = pj.y - pi0.y, dz0 = pj.z - pi0.z;
+          float dx1 = pj.x - pi1.x, dy1 = pj.y - pi1.y, dz1 = pj.z - pi1.z;
           if (PAIRMIC) {
-            dx = foldCoord(dx, g.Lx, g.mx);
-            dy = foldCoord(dy, g.Ly, g.my);
-            dz = foldCoord(dz, g.Lz, g.mz);
+            dx0 = foldCoord(dx0, g.Lx, g.mx); dy0 = foldCoord(dy0, g.Ly, g.my); dz0 = foldCoord(dz0, g.Lz, g.mz);
+            dx1 = foldCoord(dx1, g.Lx, g.mx); dy1 = foldCoord(dy1, g.Ly, g.my); dz1 = foldCoord(dz1, g.Lz, g.mz);
           }
-          if (MULTITYPE) p = parTable[ti + (int)pj.w];
-          ljPair<ENERGY, VIRIAL>(dx, dy, dz, p, a);
+          if (MULTITYPE) {
+            p0 = parTable[t0 + (int)pj.w]; rcb0 = __float_as_uint(p0.cutOff2) - 1u;
+            p1 = parTable[t1 + (int)pj.w]; rcb1 = __float_as_uint(p1.cutOff2) - 1u;
+          }
+          ljPair<ENERGY, VIRIAL>(dx0, dy0, dz0, p0, rcb0, a0);
+          ljPair<ENERGY, VIRIAL>(dx1, dy1, dz1, p1, rcb1, a1);
         }
       } else {
         // dense neighbourhood: walk the neighbour cells straight from global memory
@@ -110,48 +161,41 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
           const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
           if (cnt == 0) continue;
           const int st = __shfl_sync(0xffffffffu, nc.start, c);
-          const float sx = __shfl_sync(0xffffffffu, nc.sx, c);
-          const float sy = __shfl_sync(0xffffffffu, nc.sy, c);
-          const float sz = __shfl_sync(0xffffffffu, nc.sz, c);
           for (int t = lane; t < cnt; t += 32) {
-            const float4 pj = ldg4(sortPos + st + t);
-            float dx, dy, dz;
+            float4 pj = ldg4(sortPos + st + t);
+            if (!PAIRMIC) toHomeImage(pj, g, hc);
+            float dx0 = pj.x - pi0.x, dy0 = pj.y - pi0.y, dz0 = pj.z - pi0.z;
+            float dx1 = pj.x - pi1.x, dy1 = pj.y - pi1.y, dz1 = pj.z - pi1.z;
             if (PAIRMIC) {
-              dx = foldCoord(pj.x - pi.x, g.Lx, g.mx);
-              dy = foldCoord(pj.y - pi.y, g.Ly, g.my);
-              dz = foldCoord(pj.z - pi.z, g.Lz, g.mz);
-            } else {
-              dx = (foldCoord(pj.x, g.Lx, g.mx) + sx) - pi.x;
-              dy = (foldCoord(pj.y, g.Ly, g.my) + sy) - pi.y;
-              dz = (foldCoord(pj.z, g.Lz, g.mz) + sz) - pi.z;
+              dx0 = foldCoord(dx0, g.Lx, g.mx); dy0 = foldCoord(dy0, g.Ly, g.my); dz0 = foldCoord(dz0, g.Lz, g.mz);
+              dx1 = foldCoord(dx1, g.Lx, g.mx); dy1 = foldCoord(dy1, g.Ly, g.my); dz1 = foldCoord(dz1, g.Lz, g.mz);
             }
-            if (MULTITYPE) p = parTable[ti + (int)pj.w];
-            ljPair<ENERGY, VIRIAL>(dx, dy, dz, p, a);
+            if (MULTITYPE) {
+              p0 = parTable[t0 + (int)pj.w]; rcb0 = __float_as_uint(p0.cutOff2) - 1u;
+              p1 = parTable[t1 + (int)pj.w]; rcb1 = __float_as_uint(p1.cutOff2) - 1u;
+            }
+            ljPair<ENERGY, VIRIAL>(dx0, dy0, dz0, p0, rcb0, a0);
+            ljPair<ENERGY, VIRIAL>(dx1, dy1, dz1, p1, rcb1, a1);
           }
         }
       }
-      a.fx = warpSum(a.fx);
-      a.fy = warpSum(a.fy);
-      a.fz = warpSum(a.fz);
-      if (ENERGY) a.e = warpSum(a.e);
-      if (VIRIAL) a.v = warpSum(a.v);
-      if (lane == 0) {
-        const int gi = groupIndex[hStart + h];
+      reducePair(a0, a1, lane, ENERGY || VIRIAL);
+      if ((lane == 0) || (lane == 16 && two)) {
+        const int gi = groupIndex[hStart + h + (lane >> 4)];
         const int ori = globalIdx ? globalIdx[gi] : gi;
         if (force) {
           if (ACCUMULATE) {
             float4 f = force[ori];
-            f.x += a.fx; f.y += a.fy; f.z += a.fz;
+            f.x += a0.fx; f.y += a0.fy; f.z += a0.fz;
             force[ori] = f;
           } else {
-            force[ori] = make_float4(a.fx, a.fy, a.fz, 0.0f);
+            force[ori] = make_float4(a0.fx, a0.fy, a0.fz, 0.0f);
           }
         }
-        if (ENERGY) energy[ori] += a.e;
-        if (VIRIAL) virial[ori] += a.v;
+        if (ENERGY) energy[ori] += a0.e;
+        if (VIRIAL) virial[ori] += a0.v;
       }
     }
-    __syncthreads();
   }
 }
 
