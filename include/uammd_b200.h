@@ -119,6 +119,57 @@ int ub200_md_lj_nve_run_host_f32(ub200_md *md, float *h_pos4, float *h_vel3, flo
                                  const float L[3], float rc, const float *params, int ntypes, float dt,
                                  int nsteps, void *stream);
 ub200_celllist *ub200_md_celllist(ub200_md *md);
+/* ------------------------------------------------------------------------------------------------
+ * Path 2: FFT-based hydrodynamics. Precision is chosen at create time (precisionBytes = 4 | 8, the
+ * reference's global `real`); positions/forces are real4, per-particle outputs real3, grids real3 AoS
+ * [nz][ny][nxPad][3] with nxPad = 2(nx/2+1) which the FFT turns IN PLACE into complex3 AoS
+ * [nz][ny][nx/2+1][3] - the reference's cufftMakePlanMany(batch 3, stride 3) layout
+ * (Integrator/BDHI/FCM/FCM_impl.cuh:186-211).
+ * ------------------------------------------------------------------------------------------------ */
+#define UB200_KERNEL_PESKIN3 0  /* IBM_kernels::Peskin::threePoint  misc/IBM_kernels.cuh:118-137 */
+#define UB200_KERNEL_PESKIN4 1  /* IBM_kernels::Peskin::fourPoint   misc/IBM_kernels.cuh:140-157 */
+#define UB200_KERNEL_GAUSSIAN 2 /* FCM_ns::Kernels::Gaussian        Integrator/BDHI/FCM/FCM_kernels.cuh:22-58 */
+typedef struct {
+  int kind;
+  int support;  /* points per dimension (Kernel::support / getMaxSupport) */
+  double h;     /* Peskin: grid spacing */
+  double prefactor, tau, rmax; /* Gaussian: prefactor*exp(tau r^2) for r < rmax */
+} ub200_ibm_kernel;
+
+/* 3-D real FFT, hand written (no cuFFT). Replaces the cuFFT plans + cufftExecR2C/D2Z/C2R/Z2D calls
+ * (FCM_impl.cuh:179-234,293-304,544-557; PSE/FarField.cuh:555-603). Unnormalised; direction -1 = forward
+ * (real -> complex), +1 = inverse. Sizes with prime factors 2, 3, 5, 7. */
+typedef struct ub200_fft3d ub200_fft3d;
+int ub200_fft3d_create(ub200_fft3d **out, int precisionBytes, int nx, int ny, int nz);
+int ub200_fft3d_destroy(ub200_fft3d *plan);
+int ub200_fft3d_exec(ub200_fft3d *plan, void *d_grid, int direction, void *stream);
+
+/* Immersed boundary spreading / interpolation. Replaces IBM<Kernel>::spread / gather (misc/IBM.cuh:117-184,
+ * kernels misc/IBM.cu:83-147,168-235). spread ADDS into d_grid3 and gather ADDS into d_out3 like the
+ * reference; spread_overwrite writes every node of the grid (no prior zero fill needed) and is what the
+ * FCM/PSE pipelines use. d_val: real3 (valStride 3) or real4 (valStride 4) per particle. */
+typedef struct ub200_ibm ub200_ibm;
+int ub200_ibm_create(ub200_ibm **out, int precisionBytes, const double L[3], const int periodic[3], const int cells[3],
+                     const ub200_ibm_kernel *kernel, int nxPad);
+int ub200_ibm_destroy(ub200_ibm *ibm);
+int ub200_ibm_spread(ub200_ibm *ibm, const void *d_pos, const void *d_val, int valStride, int N, void *d_grid3,
+                     void *stream);
+int ub200_ibm_spread_overwrite(ub200_ibm *ibm, const void *d_pos, const void *d_val, int valStride, int N,
+                               void *d_grid3, void *stream);
+int ub200_ibm_gather(ub200_ibm *ibm, const void *d_pos, int N, const void *d_grid3, void *d_out3, void *stream);
+
+/* Force Coupling Method. Replaces FCM_impl<Kernel,KernelTorque>::computeHydrodynamicDisplacements without
+ * torques (Integrator/BDHI/FCM/FCM_impl.cuh:652-693) and hence BDHI::FCM::computeMF (BDHI_FCM.cuh:131-142):
+ * d_out3[i] = (M F)_i + prefactor*sqrt(2 T)*(M^1/2 dW)_i. d_force may be NULL (noise only). The Brownian
+ * noise follows fourierBrownianNoise (FCM_impl.cuh:437-542): Saru(node id, seed, call counter). */
+typedef struct ub200_fcm ub200_fcm;
+int ub200_fcm_create(ub200_fcm **out, int precisionBytes, const double L[3], const int cells[3],
+                     const ub200_ibm_kernel *kernel, double viscosity, uint32_t seed);
+int ub200_fcm_destroy(ub200_fcm *fcm);
+int ub200_fcm_mdot(ub200_fcm *fcm, const void *d_pos, const void *d_force, int N, double temperature,
+                   double prefactor, void *d_out3, void *stream);
+int ub200_fcm_grid_info(ub200_fcm *fcm, int cells[3], int *nxPad, void **d_grid);
+
 /* number of kernel launches the library enqueued since process start (bench.py's gpu_launches) */
 unsigned long long ub200_launch_count(void);
 

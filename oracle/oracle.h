@@ -98,6 +98,9 @@ void orc_ibm_gather_d(const orc_grid_d *g, const orc_ibm_kernel *k, const double
                       const double *grid3, double *out3);
 /* FCM spectral step FCM_impl.cuh:375-397 on complex3 AoS [(nx/2+1)*ny*nz][3][2] */
 void orc_fcm_force2vel_d(const orc_grid_d *g, double viscosity, double *ghat);
+/* FCM Brownian noise added to the Fourier grid, FCM_impl.cuh:437-542 */
+void orc_fcm_add_noise_d(const orc_grid_d *g, double viscosity, double noisePrefactor, uint32_t seed1, uint32_t seed2,
+                         double *ghat);
 /* naive-but-exact separable 3D real-to-complex / complex-to-real DFT (unnormalised, cuFFT sign convention)
    on the interleaved-3 layout. For small grids only (O(n^4)). */
 void orc_dft3_r2c_d(int nx, int ny, int nz, int nxPad, const double *grid3, double *ghat);

@@ -257,6 +257,13 @@ def fcm_force2vel(grid, viscosity, ghat):
     return g
 
 
+def fcm_add_noise(grid, viscosity, noisePrefactor, seed1, seed2, ghat):
+    g = np.ascontiguousarray(ghat, np.complex128).copy()
+    lib().orc_fcm_add_noise_d(C.byref(grid), C.c_double(viscosity), C.c_double(noisePrefactor), C.c_uint32(seed1),
+                              C.c_uint32(seed2), _p(g))
+    return g
+
+
 def dft3_r2c(grid3, nx):
     nz, ny, nxPad, _ = grid3.shape
     out = np.zeros((nz, ny, nx // 2 + 1, 3), np.complex128)
@@ -273,15 +280,23 @@ def dft3_c2r(ghat, nx, nxPad):
     return out
 
 
-def fcm_mdot(L, cells, kern, viscosity, pos4, force3):
-    """Full deterministic FCM pipeline FCM_impl::computeHydrodynamicDisplacements (T=0)
-    (Integrator/BDHI/FCM/FCM_impl.cuh:652-693) with numpy.fft standing in for cuFFT."""
+def fcm_mdot(L, cells, kern, viscosity, pos4, force3, temperature=0.0, prefactor=0.0, seed=0, seed2=1):
+    """FCM pipeline FCM_impl::computeHydrodynamicDisplacements (Integrator/BDHI/FCM/FCM_impl.cuh:652-693)
+    with numpy.fft standing in for cuFFT. force3 may be None (noise only); seed2 = number of noisy calls so far."""
     g = make_grid_d(L, cells)
     nx, ny, nz = cells
     nxPad = 2 * (nx // 2 + 1)
-    sp = ibm_spread(g, kern, pos4, force3, nxPad)
-    ghat = np.fft.rfftn(sp[:, :, :nx, :], axes=(0, 1, 2))
-    ghat = fcm_force2vel(g, viscosity, ghat)
+    if force3 is not None:
+        sp = ibm_spread(g, kern, pos4, force3, nxPad)
+        ghat = np.fft.rfftn(sp[:, :, :nx, :], axes=(0, 1, 2))
+        ghat = fcm_force2vel(g, viscosity, ghat)
+    else:
+        ghat = np.zeros((nz, ny, nx // 2 + 1, 3), np.complex128)
+    if temperature > 0:
+        dV = g.cellSize[0] * g.cellSize[1] * g.cellSize[2]
+        noisePrefactor = prefactor * np.sqrt((1.0 / (float(nx) * ny * nz)) * 2 * temperature / dV)
+        ghat = fcm_add_noise(g, viscosity, noisePrefactor, seed, seed2, ghat)
+
     vel = np.zeros((nz, ny, nxPad, 3))
     vel[:, :, :nx, :] = np.fft.irfftn(ghat, s=(nz, ny, nx), axes=(0, 1, 2)) * (nx * ny * nz)
     return ibm_gather(g, kern, pos4, vel, nxPad)

@@ -269,3 +269,68 @@ void orc_dft3_c2r_d(int nx, int ny, int nz, int nxPad, const double *ghat, doubl
   }
   free(a); free(b);
 }
+
+/* ---------- Brownian noise in Fourier space ---------- */
+/* fcm_detail::isNyquistWaveNumber Integrator/BDHI/FCM/utils.cuh:132-168 */
+static int is_nyquist(const int c[3], const int n[3]) {
+  const int xq = (c[0] == n[0] - c[0]) && (n[0] % 2 == 0);
+  const int yq = (c[1] == n[1] - c[1]) && (n[1] % 2 == 0);
+  const int zq = (c[2] == n[2] - c[2]) && (n[2] % 2 == 0);
+  return (xq && c[1] == 0 && c[2] == 0) || (xq && yq && c[2] == 0) || (c[0] == 0 && yq && c[2] == 0) ||
+         (xq && c[1] == 0 && zq) || (c[0] == 0 && c[1] == 0 && zq) || (c[0] == 0 && yq && zq) || (xq && yq && zq);
+}
+
+static void noise_term(const orc_grid_d *g, double viscosity, const int cell[3], const double nz[6], int conj,
+                       double *dst) {
+  const int n[3] = {g->cellDim[0], g->cellDim[1], g->cellDim[2]};
+  double k[3], dk[3], k2 = 0;
+  for (int d = 0; d < 3; d++) {
+    const int ik = fold(cell[d], n[d]);
+    k[d] = (2.0 * M_PI / g->L[d]) * ik;
+    dk[d] = (ik == n[d] - ik) ? 0.0 : k[d];
+    k2 += k[d] * k[d];
+  }
+  const double Bsq = sqrt(1.0 / (k2 * viscosity)), invk2 = 1.0 / k2;
+  for (int c = 0; c < 2; c++) {
+    const double sgn = (c == 1 && conj) ? -1.0 : 1.0;
+    const double f[3] = {sgn * nz[0 + c] * Bsq, sgn * nz[2 + c] * Bsq, sgn * nz[4 + c] * Bsq};
+    const double fdk = f[0] * (dk[0] * invk2) + f[1] * (dk[1] * invk2) + f[2] * (dk[2] * invk2);
+    for (int d = 0; d < 3; d++) dst[2 * d + c] += f[d] - dk[d] * fdk;
+  }
+}
+
+/* fcm_detail::fourierBrownianNoise Integrator/BDHI/FCM/FCM_impl.cuh:437-512, executed node by node in index order
+   (the reference kernel's two non-atomic "+=" per node race on the kx = nx/2 plane; this is the race-free sum).
+   noisePrefactor = prefactor*sqrt(2T/(dV Nxyz)) as computed by addBrownianNoise :514-542. */
+void orc_fcm_add_noise_d(const orc_grid_d *g, double viscosity, double noisePrefactor, uint32_t seed1, uint32_t seed2,
+                         double *ghat) {
+  const int n[3] = {g->cellDim[0], g->cellDim[1], g->cellDim[2]};
+  const int nkx = n[0] / 2 + 1;
+  for (int iz = 0; iz < n[2]; iz++)
+    for (int iy = 0; iy < n[1]; iy++)
+      for (int ix = 0; ix < nkx; ix++) {
+        const uint32_t id = (uint32_t)ix + (uint32_t)nkx * ((uint32_t)iy + (uint32_t)n[1] * iz);
+        const int cell[3] = {ix, iy, iz};
+        if (id == 0 || (ix == 0 && iy == 0 && 2 * iz >= n[2] + 1) || (ix == 0 && 2 * iy >= n[1] + 1)) continue;
+        /* generateNoise (FCM/utils.cuh:115-130): Saru(id, seed1, seed2), three float Box-Muller pairs */
+        orc_saru rng = orc_saru_seed3(id, seed1, seed2);
+        const float sc = (float)(0.707106781186547 * noisePrefactor);
+        double nzv[6];
+        for (int c = 0; c < 3; c++) {
+          float pr[2];
+          orc_saru_gf(&rng, 0.0f, sc, pr);
+          nzv[2 * c] = pr[0];
+          nzv[2 * c + 1] = pr[1];
+        }
+        const int nyq = is_nyquist(cell, n);
+        if (nyq)
+          for (int c = 0; c < 3; c++) { nzv[2 * c] *= 1.41421356237310; nzv[2 * c + 1] = 0.0; }
+        noise_term(g, viscosity, cell, nzv, 0, ghat + 6 * (size_t)id);
+        if (nyq) continue;
+        if (ix == n[0] - ix || ix == 0) {
+          const int cc[3] = {ix, (iy > 0) * (n[1] - iy), (iz > 0) * (n[2] - iz)};
+          const size_t idc = (size_t)cc[0] + (size_t)nkx * ((size_t)cc[1] + (size_t)n[1] * cc[2]);
+          noise_term(g, viscosity, cc, nzv, 1, ghat + 6 * idc);
+        }
+      }
+}

@@ -173,6 +173,26 @@ orderAndGather(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
   }
 }
 
+// Exclusive prefix sum of counts[0..M) into out[0..M], out[M] = total; counts are zeroed again on the way.
+// tileSums: scratch of >= 4096 uint32. Three tiny launches, no host synchronisation.
+int exclusiveScanAndClear(uint32_t *counts, int M, uint32_t *out, uint32_t *tileSums, cudaStream_t st) {
+  const int ntiles = (M + kScanTile - 1) / kScanTile;
+  if (ntiles > 4096) return UB200_ERR_GRID_TOO_LARGE;
+  scanTileSums<<<ntiles, kScanThreads, 0, st>>>(counts, M, tileSums);
+  UB200_LAUNCHED();
+  scanTop<<<1, 1024, 0, st>>>(tileSums, ntiles);
+  UB200_LAUNCHED();
+  scanApply<<<ntiles, kScanThreads, 0, st>>>(counts, M, tileSums, out);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
+int scatterToBinsLaunch(const uint2 *codeSlot, const uint32_t *binStart, int N, int *unstable, cudaStream_t st) {
+  scatterToBins<<<(N + 255) / 256, 256, 0, st>>>(codeSlot, binStart, N, unstable);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
 static int highestBit(uint32_t v) { // position of MSB + 1 (0 for v == 0)
   int b = 0;
   while (v) { b++; v >>= 1; }
@@ -274,13 +294,9 @@ int ub200_celllist_build_f32(ub200_celllist *cl, const void *d_pos, const int *d
   binParticles<<<nb, 256, 0, st>>>((const float4 *)d_pos, d_groupIdx, N, g, cl->binCount.as<uint32_t>(),
                                    cl->codeSlot.as<uint2>(), cl->errorFlag.as<int>());
   UB200_LAUNCHED();
-  scanTileSums<<<ntiles, kScanThreads, 0, st>>>(cl->binCount.as<uint32_t>(), nbins, cl->blockSums.as<uint32_t>());
-  UB200_LAUNCHED();
-  scanTop<<<1, 1024, 0, st>>>(cl->blockSums.as<uint32_t>(), ntiles);
-  UB200_LAUNCHED();
-  scanApply<<<ntiles, kScanThreads, 0, st>>>(cl->binCount.as<uint32_t>(), nbins, cl->blockSums.as<uint32_t>(),
-                                             cl->binStart.as<uint32_t>());
-  UB200_LAUNCHED();
+  if ((rc = exclusiveScanAndClear(cl->binCount.as<uint32_t>(), nbins, cl->binStart.as<uint32_t>(),
+                                  cl->blockSums.as<uint32_t>(), st)))
+    return rc;
   scatterToBins<<<nb, 256, 0, st>>>(cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(), N, cl->unstable.as<int>());
   UB200_LAUNCHED();
   orderAndGather<<<nb, 256, 0, st>>>(cl->unstable.as<int>(), cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(),

@@ -137,6 +137,10 @@ __device__ __forceinline__ float imageNear(float r, float c, float L, float minu
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
+// defined in celllist.cu
+int exclusiveScanAndClear(uint32_t *counts, int M, uint32_t *out, uint32_t *tileSums, cudaStream_t st);
+int scatterToBinsLaunch(const uint2 *codeSlot, const uint32_t *binStart, int N, int *unstable, cudaStream_t st);
+
 } // namespace ub200
 
 // Opaque handle behind ub200_celllist

@@ -1,0 +1,424 @@
+// Force Coupling Method pipeline (BDHI::FCM), IBM spread/gather and the 3-D FFT behind the C ABI, sm_100a.
+//
+// Replaces FCM_impl::computeHydrodynamicDisplacements (Integrator/BDHI/FCM/FCM_impl.cuh:652-693):
+//   reference: fill grid 0 -> spread (atomics) -> alloc+fill Fourier grid -> cuFFT R2C -> forceFourier2Vel
+//              -> fourierBrownianNoise -> alloc+fill real grid -> cuFFT C2R -> fill out 0 -> gather -> copy
+//   here     : bin+order+stencil records -> node-centric spread (writes every node once) -> FFT x, y ->
+//              fused [FFT z, Stokes projector, Brownian noise, inverse FFT z] -> inverse FFT y, x -> gather.
+// One grid buffer, transformed in place; no memsets, no atomics (small supports), no per-step allocation.
+#include "fft3d.cuh"
+#include "ibm.cuh"
+#include "saru.cuh"
+
+namespace ub200 {
+
+// ---- spectral operator of FCM: forceFourier2Vel (FCM_impl.cuh:375-397) + fourierBrownianNoise (:437-512) ----
+template <class T> struct FcmSpectralOp {
+  using C = typename Vec2<T>::type;
+  int nx, ny, nz, nkx;
+  T kfx, kfy, kfz;  // 2 pi / L
+  T vis;
+  T invNorm;        // 1 / (nx ny nz)
+  int deterministic; // apply B * projector to the incoming spectrum (forces were spread)
+  int noise;
+  T noisePrefactor;
+  uint32_t seed1, seed2;
+
+  __device__ __forceinline__ static int fold(int i, int n) { return i - n * (i >= (n / 2 + 1)); }
+
+  __device__ __forceinline__ bool generates(int ix, int iy, int iz) const {
+    if (ix == 0 && iy == 0 && iz == 0) return false;
+    if (ix == 0 && iy == 0 && 2 * iz >= nz + 1) return false;
+    if (ix == 0 && 2 * iy >= ny + 1) return false;
+    return true;
+  }
+  // fcm_detail::isNyquistWaveNumber (FCM/utils.cuh:132-168)
+  __device__ __forceinline__ bool nyquist(int ix, int iy, int iz) const {
+    const bool nxq = (ix == nx - ix) && (nx % 2 == 0);
+    const bool nyq = (iy == ny - iy) && (ny % 2 == 0);
+    const bool nzq = (iz == nz - iz) && (nz % 2 == 0);
+    return (nxq && iy == 0 && iz == 0) || (nxq && nyq && iz == 0) || (ix == 0 && nyq && iz == 0) ||
+           (nxq && iy == 0 && nzq) || (ix == 0 && iy == 0 && nzq) || (ix == 0 && nyq && nzq) || (nxq && nyq && nzq);
+  }
+  // fcm_detail::generateNoise (FCM/utils.cuh:115-130): three float Box-Muller pairs from Saru(id, seed1, seed2)
+  __device__ __forceinline__ void drawNoise(uint32_t id, C &a, C &b, C &c) const {
+    Saru rng(id, seed1, seed2);
+    const float sc = (float)(T(0.707106781186547) * noisePrefactor);
+    float2 g = rng.gauss2(sc); a = mk2<T>((T)g.x, (T)g.y);
+    g = rng.gauss2(sc); b = mk2<T>((T)g.x, (T)g.y);
+    g = rng.gauss2(sc); c = mk2<T>((T)g.x, (T)g.y);
+  }
+
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, C &vx, C &vy, C &vz) const {
+    if (ix == 0 && iy == 0 && iz == 0) { vx = vy = vz = mk2<T>(T(0), T(0)); return; }
+    const int fx = fold(ix, nx), fy = fold(iy, ny), fz = fold(iz, nz);
+    const T kx = kfx * fx, ky = kfy * fy, kz = kfz * fz;
+    const T k2 = kx * kx + ky * ky + kz * kz;
+    // getGradientFourier (FCM/utils.cuh:41-51): unpaired (Nyquist) components of the gradient are zeroed
+    const T dx = (fx == nx - fx) ? T(0) : kx, dy = (fy == ny - fy) ? T(0) : ky, dz = (fz == nz - fz) ? T(0) : kz;
+    const T invk2 = T(1.0) / k2;
+    const T B = T(1.0) / (vis * k2);
+    auto project = [&](T f0, T f1, T f2, T &o0, T &o1, T &o2) { // projectFourier (FCM/utils.cuh:70-76)
+      const T s = f0 * (dx * invk2) + f1 * (dy * invk2) + f2 * (dz * invk2);
+      o0 = f0 - dx * s; o1 = f1 - dy * s; o2 = f2 - dz * s;
+    };
+    C ox = mk2<T>(T(0), T(0)), oy = ox, oz = ox;
+    if (deterministic) {
+      const T sc = B * invNorm;
+      T a0, a1, a2, b0, b1, b2;
+      project(vx.x, vy.x, vz.x, a0, a1, a2);
+      project(vx.y, vy.y, vz.y, b0, b1, b2);
+      ox = mk2<T>(a0 * sc, b0 * sc); oy = mk2<T>(a1 * sc, b1 * sc); oz = mk2<T>(a2 * sc, b2 * sc);
+    }
+    if (noise) {
+      const T Bsq = sqrt(B);
+      if (generates(ix, iy, iz)) {
+        C n0, n1, n2;
+        drawNoise((uint32_t)(ix + nkx * (iy + ny * iz)), n0, n1, n2);
+        if (nyquist(ix, iy, iz)) {
+          const T q = T(1.41421356237310);
+          n0.x *= q; n0.y = T(0); n1.x *= q; n1.y = T(0); n2.x *= q; n2.y = T(0);
+        }
+        T a0, a1, a2, b0, b1, b2;
+        project(n0.x * Bsq, n1.x * Bsq, n2.x * Bsq, a0, a1, a2);
+        project(n0.y * Bsq, n1.y * Bsq, n2.y * Bsq, b0, b1, b2);
+        ox.x += a0; ox.y += b0; oy.x += a1; oy.y += b1; oz.x += a2; oz.y += b2;
+      }
+      // contribution written by the conjugate partner (stored twice only on the kx = 0 and kx = nx/2 planes)
+      if (ix == 0 || ix == nx - ix) {
+        const int cy = (iy > 0) * (ny - iy), cz = (iz > 0) * (nz - iz);
+        if (!(cy == iy && cz == iz) && generates(ix, cy, cz) && !nyquist(ix, cy, cz)) {
+          C n0, n1, n2;
+          drawNoise((uint32_t)(ix + nkx * (cy + ny * cz)), n0, n1, n2);
+          T a0, a1, a2, b0, b1, b2;
+          project(n0.x * Bsq, n1.x * Bsq, n2.x * Bsq, a0, a1, a2);
+          project(-(n0.y * Bsq), -(n1.y * Bsq), -(n2.y * Bsq), b0, b1, b2);
+          ox.x += a0; ox.y += b0; oy.x += a1; oy.y += b1; oz.x += a2; oz.y += b2;
+        }
+      }
+    }
+    vx = ox; vy = oy; vz = oz;
+  }
+};
+
+template <class T> struct Real4;
+template <> struct Real4<float> { using type = float4; };
+template <> struct Real4<double> { using type = double4; };
+
+template <class T> struct IbmState {
+  GridT<T> grid;
+  IbmKernel<T> kern;
+  int nxPad = 0;
+  bool nodeCentric = false;
+  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, recs;
+  int recsValidFor = -1;
+
+  int init(const double L[3], const int periodic[3], const int cells[3], const ub200_ibm_kernel &k, int nxPad_) {
+    grid = makeGridT<T>(L, periodic, cells);
+    kern.kind = k.kind;
+    kern.support = k.support;
+    kern.invh = (T)(1.0 / k.h);
+    kern.prefactor = (T)k.prefactor;
+    kern.tau = (T)k.tau;
+    kern.rmax = (T)k.rmax;
+    nxPad = nxPad_;
+    if (k.support < 1 || k.support > kMaxSupport) return UB200_ERR_INVALID_ARGUMENT;
+    const long long ncells = (long long)grid.n[0] * grid.n[1] * grid.n[2];
+    nodeCentric = k.support <= kSmallSupport && ncells <= 4096LL * 4096LL;
+    for (int d = 0; d < 3; d++)
+      if (grid.m[d] != T(0) && grid.n[d] < k.support + 1) nodeCentric = false; // support would overlap itself
+    if (grid.n[2] == 1) nodeCentric = false; // 2-D grids take the generic path
+    return UB200_OK;
+  }
+  void release() {
+    DevBuf *b[] = {&binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &recs};
+    for (auto *x : b) x->release();
+  }
+
+  // bin, order and build the stencil records (positions + optional values)
+  int prepare(const void *pos, const void *val, int valStride, int N, cudaStream_t st) {
+    using T4 = typename Real4<T>::type;
+    const int ncells = grid.n[0] * grid.n[1] * grid.n[2];
+    int rc;
+    if (!binCount.p || binCount.cap < sizeof(uint32_t) * (size_t)ncells) {
+      if ((rc = binCount.reserve(sizeof(uint32_t) * (size_t)ncells))) return rc;
+      if ((rc = binStart.reserve(sizeof(uint32_t) * ((size_t)ncells + 1)))) return rc;
+      if ((rc = tileSums.reserve(sizeof(uint32_t) * 4096))) return rc;
+      UB200_CUDA(cudaMemsetAsync(binCount.p, 0, binCount.cap, st));
+    }
+    if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N))) return rc;
+    if ((rc = unstable.reserve(sizeof(int) * (size_t)N))) return rc;
+    if ((rc = sortedIndex.reserve(sizeof(int) * (size_t)N))) return rc;
+    if ((rc = recs.reserve(sizeof(StencilRec<T>) * (size_t)N))) return rc;
+    const int nb = (N + 255) / 256;
+    ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
+    UB200_LAUNCHED();
+    if ((rc = exclusiveScanAndClear(binCount.as<uint32_t>(), ncells, binStart.as<uint32_t>(), tileSums.as<uint32_t>(), st)))
+      return rc;
+    if ((rc = scatterToBinsLaunch(codeSlot.as<uint2>(), binStart.as<uint32_t>(), N, unstable.as<int>(), st))) return rc;
+    ibmOrderAndStencil<T4, T><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(),
+                                                  (const T4 *)pos, (const T *)val, valStride, N, grid, kern,
+                                                  sortedIndex.as<int>(), recs.as<StencilRec<T>>());
+    UB200_LAUNCHED();
+    recsValidFor = N;
+    return UB200_OK;
+  }
+
+  // grid3 is completely overwritten on the node-centric path; the generic path accumulates into it
+  int spread(const void *pos, const void *val, int valStride, int N, T *grid3, bool gridIsZero, cudaStream_t st) {
+    using T4 = typename Real4<T>::type;
+    if (nodeCentric) {
+      int rc = prepare(pos, val, valStride, N, st);
+      if (rc) return rc;
+      dim3 grd((nxPad + 127) / 128, grid.n[1], grid.n[2]);
+      ibmSpreadNodes<T><<<grd, 128, 0, st>>>(recs.as<StencilRec<T>>(), binStart.as<uint32_t>(), grid, kern.support, nxPad,
+                                             grid3);
+      UB200_LAUNCHED();
+      return UB200_OK;
+    }
+    if (!gridIsZero)
+      UB200_CUDA(cudaMemsetAsync(grid3, 0, sizeof(T) * 3 * (size_t)nxPad * grid.n[1] * grid.n[2], st));
+    ibmWarpPerParticle<T4, T, true, false><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)val, valStride, N,
+                                                                         grid, kern, nxPad, grid3, nullptr);
+    UB200_LAUNCHED();
+    recsValidFor = -1;
+    return UB200_OK;
+  }
+
+  // reuseRecords: positions are the ones of the preceding spread on this state
+  int gather(const void *pos, int N, const T *grid3, T *out3, bool accumulate, bool reuseRecords, cudaStream_t st) {
+    using T4 = typename Real4<T>::type;
+    if (nodeCentric) {
+      if (!(reuseRecords && recsValidFor == N)) {
+        int rc = prepare(pos, nullptr, 0, N, st);
+        if (rc) return rc;
+      }
+      const int nb = (N + 127) / 128;
+      if (accumulate)
+        ibmGatherSorted<T, true><<<nb, 128, 0, st>>>(recs.as<StencilRec<T>>(), sortedIndex.as<int>(), N, grid,
+                                                     kern.support, nxPad, grid3, out3);
+      else
+        ibmGatherSorted<T, false><<<nb, 128, 0, st>>>(recs.as<StencilRec<T>>(), sortedIndex.as<int>(), N, grid,
+                                                      kern.support, nxPad, grid3, out3);
+      UB200_LAUNCHED();
+      return UB200_OK;
+    }
+    if (accumulate)
+      ibmWarpPerParticle<T4, T, false, true><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)nullptr, 0, N, grid,
+                                                                         kern, nxPad, const_cast<T *>(grid3), out3);
+    else
+      ibmWarpPerParticle<T4, T, false, false><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)nullptr, 0, N,
+                                                                          grid, kern, nxPad, const_cast<T *>(grid3), out3);
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+};
+
+template <class T> struct FcmState {
+  Fft3dPlan<T> plan;
+  IbmState<T> ibm;
+  DevBuf grid;
+  double viscosity = 1;
+  double L[3];
+  uint32_t seed = 0, seed2 = 0;
+
+  int init(const double L_[3], const int cells[3], const ub200_ibm_kernel &k, double vis, uint32_t seed_) {
+    int rc = plan.init(cells[0], cells[1], cells[2]);
+    if (rc) return rc;
+    const int periodic[3] = {1, 1, 1};
+    if ((rc = ibm.init(L_, periodic, cells, k, plan.nxPad))) return rc;
+    if ((rc = grid.reserve(plan.gridBytes()))) return rc;
+    for (int d = 0; d < 3; d++) L[d] = L_[d];
+    viscosity = vis;
+    seed = seed_;
+    return UB200_OK;
+  }
+  void release() { plan.release(); ibm.release(); grid.release(); }
+
+  FcmSpectralOp<T> makeOp(bool deterministic, double temperature, double prefactor) {
+    FcmSpectralOp<T> op;
+    op.nx = plan.nx; op.ny = plan.ny; op.nz = plan.nz; op.nkx = plan.nkx;
+    op.kfx = (T)(T(2.0) * T(M_PI) / (T)L[0]);
+    op.kfy = (T)(T(2.0) * T(M_PI) / (T)L[1]);
+    op.kfz = (T)(T(2.0) * T(M_PI) / (T)L[2]);
+    op.vis = (T)viscosity;
+    op.invNorm = T(1.0) / T((double)plan.nx * plan.ny * plan.nz);
+    op.deterministic = deterministic;
+    op.noise = temperature > 0.0;
+    op.noisePrefactor = T(0);
+    op.seed1 = seed;
+    op.seed2 = seed2;
+    if (op.noise) {
+      // addBrownianNoise (FCM_impl.cuh:514-542): prefactor * sqrt(2 T / (dV * Nxyz)); seed2 counts the calls
+      seed2++;
+      op.seed2 = seed2;
+      const T dV = ibm.grid.cellVolume;
+      const T fourierNormalization = (T)(1.0 / ((double)plan.nx * plan.ny * plan.nz));
+      op.noisePrefactor = (T)prefactor * (T)sqrt((double)(fourierNormalization * 2 * (T)temperature / dV));
+    }
+    return op;
+  }
+
+  int mdot(const void *pos, const void *force, int N, double temperature, double prefactor, void *out3,
+           cudaStream_t st) {
+    int rc;
+    T *g = grid.as<T>();
+    const bool det = force != nullptr;
+    if (det) {
+      if ((rc = ibm.spread(pos, force, 4, N, g, false, st))) return rc;
+      if ((rc = launchPassX<T, true>(plan, g, st))) return rc;
+      if ((rc = launchPassY<T, -1>(plan, g, st))) return rc;
+    } else {
+      UB200_CUDA(cudaMemsetAsync(g, 0, plan.gridBytes(), st));
+    }
+    FcmSpectralOp<T> op = makeOp(det, temperature, prefactor);
+    if ((rc = launchPassZ<T, 0, FcmSpectralOp<T>>(plan, g, st, op))) return rc;
+    if ((rc = launchPassY<T, +1>(plan, g, st))) return rc;
+    if ((rc = launchPassX<T, false>(plan, g, st))) return rc;
+    return ibm.gather(pos, N, g, (T *)out3, false, det, st);
+  }
+};
+
+} // namespace ub200
+
+using namespace ub200;
+
+struct ub200_fcm {
+  int precision;
+  FcmState<float> f;
+  FcmState<double> d;
+};
+struct ub200_ibm {
+  int precision;
+  IbmState<float> f;
+  IbmState<double> d;
+};
+struct ub200_fft3d {
+  int precision;
+  Fft3dPlan<float> f;
+  Fft3dPlan<double> d;
+};
+
+extern "C" {
+
+int ub200_fcm_create(ub200_fcm **out, int precisionBytes, const double L[3], const int cells[3],
+                     const ub200_ibm_kernel *kernel, double viscosity, uint32_t seed) {
+  if (!out || !L || !cells || !kernel || (precisionBytes != 4 && precisionBytes != 8)) return UB200_ERR_INVALID_ARGUMENT;
+  ub200_fcm *h = new (std::nothrow) ub200_fcm();
+  if (!h) return UB200_ERR_ALLOC;
+  h->precision = precisionBytes;
+  int rc = precisionBytes == 4 ? h->f.init(L, cells, *kernel, viscosity, seed) : h->d.init(L, cells, *kernel, viscosity, seed);
+  if (rc) { h->f.release(); h->d.release(); delete h; return rc; }
+  *out = h;
+  return UB200_OK;
+}
+int ub200_fcm_destroy(ub200_fcm *h) {
+  if (!h) return UB200_OK;
+  h->f.release(); h->d.release();
+  delete h;
+  return UB200_OK;
+}
+int ub200_fcm_mdot(ub200_fcm *h, const void *d_pos, const void *d_force, int N, double temperature, double prefactor,
+                   void *d_out3, void *stream) {
+  if (!h || !d_pos || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? h->f.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream)
+                           : h->d.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream);
+}
+int ub200_fcm_grid_info(ub200_fcm *h, int cells[3], int *nxPad, void **d_grid) {
+  if (!h) return UB200_ERR_INVALID_ARGUMENT;
+  const bool f = h->precision == 4;
+  if (cells) { cells[0] = f ? h->f.plan.nx : h->d.plan.nx; cells[1] = f ? h->f.plan.ny : h->d.plan.ny; cells[2] = f ? h->f.plan.nz : h->d.plan.nz; }
+  if (nxPad) *nxPad = f ? h->f.plan.nxPad : h->d.plan.nxPad;
+  if (d_grid) *d_grid = f ? h->f.grid.p : h->d.grid.p;
+  return UB200_OK;
+}
+
+int ub200_ibm_create(ub200_ibm **out, int precisionBytes, const double L[3], const int periodic[3], const int cells[3],
+                     const ub200_ibm_kernel *kernel, int nxPad) {
+  if (!out || !L || !cells || !periodic || !kernel || (precisionBytes != 4 && precisionBytes != 8) || nxPad < cells[0])
+    return UB200_ERR_INVALID_ARGUMENT;
+  ub200_ibm *h = new (std::nothrow) ub200_ibm();
+  if (!h) return UB200_ERR_ALLOC;
+  h->precision = precisionBytes;
+  int rc = precisionBytes == 4 ? h->f.init(L, periodic, cells, *kernel, nxPad) : h->d.init(L, periodic, cells, *kernel, nxPad);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return UB200_OK;
+}
+int ub200_ibm_destroy(ub200_ibm *h) {
+  if (!h) return UB200_OK;
+  h->f.release(); h->d.release();
+  delete h;
+  return UB200_OK;
+}
+int ub200_ibm_spread(ub200_ibm *h, const void *d_pos, const void *d_val, int valStride, int N, void *d_grid3,
+                     void *stream) {
+  if (!h || !d_pos || !d_val || !d_grid3 || N <= 0 || valStride < 3) return UB200_ERR_INVALID_ARGUMENT;
+  // IBM::spread ADDS into the caller's grid (atomicAdd, misc/IBM.cu:145). The node-centric path writes every node, so
+  // it goes through a scratch-free trick only when the caller's grid is known to be zero; keep the reference
+  // semantics here: generic accumulate path unless the grid was declared empty via ub200_ibm_spread_overwrite.
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->precision == 4) {
+    const bool nc = h->f.nodeCentric; h->f.nodeCentric = false;
+    int rc = h->f.spread(d_pos, d_val, valStride, N, (float *)d_grid3, true, st);
+    h->f.nodeCentric = nc;
+    return rc;
+  }
+  const bool nc = h->d.nodeCentric; h->d.nodeCentric = false;
+  int rc = h->d.spread(d_pos, d_val, valStride, N, (double *)d_grid3, true, st);
+  h->d.nodeCentric = nc;
+  return rc;
+}
+int ub200_ibm_spread_overwrite(ub200_ibm *h, const void *d_pos, const void *d_val, int valStride, int N, void *d_grid3,
+                               void *stream) {
+  if (!h || !d_pos || !d_val || !d_grid3 || N <= 0 || valStride < 3) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? h->f.spread(d_pos, d_val, valStride, N, (float *)d_grid3, false, (cudaStream_t)stream)
+                           : h->d.spread(d_pos, d_val, valStride, N, (double *)d_grid3, false, (cudaStream_t)stream);
+}
+int ub200_ibm_gather(ub200_ibm *h, const void *d_pos, int N, const void *d_grid3, void *d_out3, void *stream) {
+  if (!h || !d_pos || !d_grid3 || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  // IBM::gather accumulates into the output (particleQuantity[id] += total, misc/IBM.cu:231-233)
+  return h->precision == 4 ? h->f.gather(d_pos, N, (const float *)d_grid3, (float *)d_out3, true, false, (cudaStream_t)stream)
+                           : h->d.gather(d_pos, N, (const double *)d_grid3, (double *)d_out3, true, false, (cudaStream_t)stream);
+}
+
+int ub200_fft3d_create(ub200_fft3d **out, int precisionBytes, int nx, int ny, int nz) {
+  if (!out || (precisionBytes != 4 && precisionBytes != 8)) return UB200_ERR_INVALID_ARGUMENT;
+  ub200_fft3d *h = new (std::nothrow) ub200_fft3d();
+  if (!h) return UB200_ERR_ALLOC;
+  h->precision = precisionBytes;
+  int rc = precisionBytes == 4 ? h->f.init(nx, ny, nz) : h->d.init(nx, ny, nz);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return UB200_OK;
+}
+int ub200_fft3d_destroy(ub200_fft3d *h) {
+  if (!h) return UB200_OK;
+  h->f.release(); h->d.release();
+  delete h;
+  return UB200_OK;
+}
+int ub200_fft3d_exec(ub200_fft3d *h, void *d_grid, int direction, void *stream) {
+  if (!h || !d_grid || (direction != -1 && direction != 1)) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (h->precision == 4) {
+    if (direction < 0) {
+      if ((rc = launchPassX<float, true>(h->f, d_grid, st))) return rc;
+      if ((rc = launchPassY<float, -1>(h->f, d_grid, st))) return rc;
+      return launchPassZ<float, -1>(h->f, d_grid, st);
+    }
+    if ((rc = launchPassZ<float, +1>(h->f, d_grid, st))) return rc;
+    if ((rc = launchPassY<float, +1>(h->f, d_grid, st))) return rc;
+    return launchPassX<float, false>(h->f, d_grid, st);
+  }
+  if (direction < 0) {
+    if ((rc = launchPassX<double, true>(h->d, d_grid, st))) return rc;
+    if ((rc = launchPassY<double, -1>(h->d, d_grid, st))) return rc;
+    return launchPassZ<double, -1>(h->d, d_grid, st);
+  }
+  if ((rc = launchPassZ<double, +1>(h->d, d_grid, st))) return rc;
+  if ((rc = launchPassY<double, +1>(h->d, d_grid, st))) return rc;
+  return launchPassX<double, false>(h->d, d_grid, st);
+}
+}

@@ -1,0 +1,227 @@
+// 3-D FFT plan + pass kernels (see fft.cuh for the design). Header so that the FCM / PSE pipelines can
+// instantiate the fused z pass with their own spectral operators.
+#pragma once
+#include "fft.cuh"
+#include <vector>
+
+namespace ub200 {
+
+constexpr int kFftThreads = 256;
+
+template <class T> struct Fft3dPlan {
+  using C = typename Vec2<T>::type;
+  int nx = 0, ny = 0, nz = 0, nkx = 0, nxPad = 0;
+  FftAxis ax, ay, az;
+  DevBuf twx, twy, twz;
+  int linesPerCta = 0; // X pass: real lines per CTA (even)
+  int tileY = 0, tileZ = 0; // Y/Z pass: kx per tile
+  size_t smemX = 0, smemY = 0, smemZ = 0;
+
+  static size_t smemBudget() { return 96 * 1024; }
+
+  int init(int nx_, int ny_, int nz_) {
+    nx = nx_; ny = ny_; nz = nz_;
+    nkx = nx / 2 + 1;
+    nxPad = 2 * nkx;
+    if (nx < 2 || ny < 1 || nz < 1) return UB200_ERR_INVALID_ARGUMENT;
+    if (!factorize(nx, ax) || !factorize(ny, ay) || !factorize(nz, az)) return UB200_ERR_UNSUPPORTED;
+    int rc;
+    if ((rc = upload(twx, nx)) || (rc = upload(twy, ny)) || (rc = upload(twz, nz))) return rc;
+    // X: pairs of lines, 3 components -> (lines/2)*3 complex transforms of length nx, two buffers
+    auto fit = [&](int n, int perUnit, int maxUnits) {
+      int units = maxUnits;
+      while (units > 1 && 2 * (size_t)units * perUnit * (n + 1) * sizeof(C) > smemBudget()) units--;
+      return units;
+    };
+    const int pairs = fit(nx, 3, 4);
+    linesPerCta = 2 * pairs;
+    smemX = 2 * (size_t)pairs * 3 * (nx + 1) * sizeof(C);
+    tileY = fit(ny, 3, 4);
+    smemY = 2 * (size_t)tileY * 3 * (ny + 1) * sizeof(C);
+    tileZ = fit(nz, 3, 4);
+    smemZ = 2 * (size_t)tileZ * 3 * (nz + 1) * sizeof(C);
+    if (smemX > 200 * 1024 || smemY > 200 * 1024 || smemZ > 200 * 1024) return UB200_ERR_UNSUPPORTED;
+    return UB200_OK;
+  }
+  void release() { twx.release(); twy.release(); twz.release(); }
+  size_t gridBytes() const { return (size_t)nz * ny * nkx * 3 * sizeof(C); }
+
+private:
+  static int upload(DevBuf &buf, int n) {
+    std::vector<C> h(n);
+    for (int j = 0; j < n; j++) {
+      const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+      h[j].x = (T)cosl(a);
+      h[j].y = (T)sinl(a);
+    }
+    int rc = buf.reserve(sizeof(C) * (size_t)n);
+    if (rc) return rc;
+    UB200_CUDA(cudaMemcpy(buf.p, h.data(), sizeof(C) * (size_t)n, cudaMemcpyHostToDevice));
+    return UB200_OK;
+  }
+};
+
+// ---------------- X pass: real <-> complex along the contiguous axis, in place ----------------
+template <class T, bool FORWARD>
+__global__ void __launch_bounds__(kFftThreads)
+fftPassX(T *__restrict__ grid, int nx, int nkx, int nlines, int linesPerCta, FftAxis ax,
+         const typename Vec2<T>::type *__restrict__ tw) {
+  using C = typename Vec2<T>::type;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int fstride = nx + 1;
+  const int pairs = linesPerCta / 2;
+  const int nf = pairs * 3;
+  C *buf0 = reinterpret_cast<C *>(smemRaw);
+  C *buf1 = buf0 + (size_t)nf * fstride;
+  const int line0 = blockIdx.x * linesPerCta;
+  const int nl = min(linesPerCta, nlines - line0);
+  const size_t lineReals = (size_t)2 * nkx * 3; // reals per line (padded) == 2 * complex per line
+  T *base = grid + (size_t)line0 * lineReals;
+  C *cbase = reinterpret_cast<C *>(base);
+  if (FORWARD) {
+    // load real lines: line l, sample x, component c -> transform (l/2)*3+c, real (l even) or imaginary part
+    for (int idx = threadIdx.x; idx < linesPerCta * nx * 3; idx += blockDim.x) {
+      const int l = idx / (nx * 3), rem = idx - l * nx * 3;
+      const int x = rem / 3, c = rem - 3 * x;
+      const T v = l < nl ? base[(size_t)l * lineReals + rem] : T(0);
+      T *dst = reinterpret_cast<T *>(buf0 + ((l >> 1) * 3 + c) * fstride + x);
+      dst[l & 1] = v;
+    }
+    __syncthreads();
+    C *res = fftInShared<T, -1>(buf0, buf1, ax, fstride, nf, tw);
+    // untangle the two real transforms and store the Hermitian halves
+    for (int idx = threadIdx.x; idx < pairs * nkx * 3; idx += blockDim.x) {
+      const int p = idx / (nkx * 3), rem = idx - p * nkx * 3;
+      const int k = rem / 3, c = rem - 3 * k;
+      const C zk = res[(p * 3 + c) * fstride + k];
+      const C zn = res[(p * 3 + c) * fstride + (k == 0 ? 0 : nx - k)];
+      const C A = mk2<T>(T(0.5) * (zk.x + zn.x), T(0.5) * (zk.y - zn.y));
+      const C B = mk2<T>(T(0.5) * (zk.y + zn.y), T(0.5) * (zn.x - zk.x));
+      if (2 * p < nl) cbase[(size_t)(2 * p) * nkx * 3 + rem] = A;
+      if (2 * p + 1 < nl) cbase[(size_t)(2 * p + 1) * nkx * 3 + rem] = B;
+    }
+  } else {
+    // build Z_k = A_k + i B_k for all k from the stored halves (Hermitian symmetry for k > nx/2); like a C2R
+    // transform, the imaginary parts of the self-conjugate modes (k = 0, and k = nx/2 for even nx) are ignored
+    for (int idx = threadIdx.x; idx < pairs * nx * 3; idx += blockDim.x) {
+      const int p = idx / (nx * 3), rem = idx - p * nx * 3;
+      const int k = rem / 3, c = rem - 3 * k;
+      const int ks = k < nkx ? k : nx - k;
+      C A = mk2<T>(T(0), T(0)), B = A;
+      if (2 * p < nl) A = cbase[(size_t)(2 * p) * nkx * 3 + ks * 3 + c];
+      if (2 * p + 1 < nl) B = cbase[(size_t)(2 * p + 1) * nkx * 3 + ks * 3 + c];
+      if (k >= nkx) { A.y = -A.y; B.y = -B.y; }
+      if (k == 0 || 2 * k == nx) { A.y = T(0); B.y = T(0); }
+      buf0[(p * 3 + c) * fstride + k] = mk2<T>(A.x - B.y, A.y + B.x);
+    }
+    __syncthreads();
+    C *res = fftInShared<T, +1>(buf0, buf1, ax, fstride, nf, tw);
+    for (int idx = threadIdx.x; idx < linesPerCta * nx * 3; idx += blockDim.x) {
+      const int l = idx / (nx * 3), rem = idx - l * nx * 3;
+      const int x = rem / 3, c = rem - 3 * x;
+      if (l < nl) {
+        const T *src = reinterpret_cast<const T *>(res + ((l >> 1) * 3 + c) * fstride + x);
+        base[(size_t)l * lineReals + rem] = src[l & 1];
+      }
+    }
+  }
+}
+
+// ---------------- Y / Z pass: complex transforms along a strided axis, in place ----------------
+// A tile is `tile` consecutive kx (x 3 components) times the whole axis of length n. elemStride = distance
+// (in complex3 nodes) between consecutive points of the axis; tiles are enumerated by (tx, other) where
+// `other` runs over the remaining axis with stride otherStride.
+struct NoSpectralOp {
+  template <class C> __device__ __forceinline__ void operator()(int, int, int, C &, C &, C &) const {}
+};
+
+// MODE: -1 forward, +1 inverse, 0 fused (forward, op, inverse)
+template <class T, int MODE, bool AXIS_IS_Z, class Op>
+__global__ void __launch_bounds__(kFftThreads)
+fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int n, int nkx, int nOther, int tile, size_t elemStride,
+               size_t otherStride, FftAxis ax, const typename Vec2<T>::type *__restrict__ tw, Op op) {
+  using C = typename Vec2<T>::type;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int fstride = n + 1;
+  const int ntx = (nkx + tile - 1) / tile;
+  const int tx = blockIdx.x % ntx, other = blockIdx.x / ntx;
+  const int kx0 = tx * tile;
+  const int w = min(tile, nkx - kx0) * 3; // complex numbers per axis point in this tile
+  const int nf = tile * 3;
+  C *buf0 = reinterpret_cast<C *>(smemRaw);
+  C *buf1 = buf0 + (size_t)nf * fstride;
+  C *base = grid + ((size_t)other * otherStride + kx0) * 3;
+  for (int idx = threadIdx.x; idx < n * nf; idx += blockDim.x) {
+    const int i = idx / nf, f = idx - i * nf;
+    buf0[f * fstride + i] = f < w ? base[(size_t)i * elemStride * 3 + f] : mk2<T>(T(0), T(0));
+  }
+  __syncthreads();
+  C *res;
+  if (MODE <= 0) res = fftInShared<T, -1>(buf0, buf1, ax, fstride, nf, tw);
+  else res = fftInShared<T, +1>(buf0, buf1, ax, fstride, nf, tw);
+  if (MODE == 0) {
+    // spectral operator on the three components of every Fourier node of the tile
+    for (int idx = threadIdx.x; idx < n * tile; idx += blockDim.x) {
+      const int i = idx / tile, t = idx - i * tile;
+      if (kx0 + t < nkx) {
+        C *v = res + (t * 3) * fstride + i;
+        C vx = v[0], vy = v[fstride], vz = v[2 * fstride];
+        if (AXIS_IS_Z) op(kx0 + t, other, i, vx, vy, vz);
+        else op(kx0 + t, i, other, vx, vy, vz);
+        v[0] = vx; v[fstride] = vy; v[2 * fstride] = vz;
+      }
+    }
+    __syncthreads();
+    C *other1 = res == buf0 ? buf1 : buf0;
+    res = fftInShared<T, +1>(res, other1, ax, fstride, nf, tw);
+  }
+  for (int idx = threadIdx.x; idx < n * nf; idx += blockDim.x) {
+    const int i = idx / nf, f = idx - i * nf;
+    if (f < w) base[(size_t)i * elemStride * 3 + f] = res[f * fstride + i];
+  }
+}
+
+template <class T> int fftEnsureSmem(const void *kern, size_t bytes) {
+  if (bytes > 48 * 1024) UB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return UB200_OK;
+}
+
+template <class T, bool FORWARD> int launchPassX(const Fft3dPlan<T> &p, void *grid, cudaStream_t st) {
+  auto kern = fftPassX<T, FORWARD>;
+  int rc = fftEnsureSmem<T>((const void *)kern, p.smemX);
+  if (rc) return rc;
+  const int nlines = p.ny * p.nz;
+  const int nb = (nlines + p.linesPerCta - 1) / p.linesPerCta;
+  kern<<<nb, kFftThreads, p.smemX, st>>>((T *)grid, p.nx, p.nkx, nlines, p.linesPerCta, p.ax,
+                                         p.twx.template as<typename Vec2<T>::type>());
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
+template <class T, int MODE, class Op = NoSpectralOp>
+int launchPassY(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()) {
+  auto kern = fftPassStrided<T, MODE, false, Op>;
+  int rc = fftEnsureSmem<T>((const void *)kern, p.smemY);
+  if (rc) return rc;
+  const int ntx = (p.nkx + p.tileY - 1) / p.tileY;
+  kern<<<ntx * p.nz, kFftThreads, p.smemY, st>>>((typename Vec2<T>::type *)grid, p.ny, p.nkx, p.nz, p.tileY,
+                                                 (size_t)p.nkx, (size_t)p.nkx * p.ny, p.ay,
+                                                 p.twy.template as<typename Vec2<T>::type>(), op);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
+template <class T, int MODE, class Op = NoSpectralOp>
+int launchPassZ(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()) {
+  auto kern = fftPassStrided<T, MODE, true, Op>;
+  int rc = fftEnsureSmem<T>((const void *)kern, p.smemZ);
+  if (rc) return rc;
+  const int ntx = (p.nkx + p.tileZ - 1) / p.tileZ;
+  kern<<<ntx * p.ny, kFftThreads, p.smemZ, st>>>((typename Vec2<T>::type *)grid, p.nz, p.nkx, p.ny, p.tileZ,
+                                                 (size_t)p.nkx * p.ny, (size_t)p.nkx, p.az,
+                                                 p.twz.template as<typename Vec2<T>::type>(), op);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
+} // namespace ub200

@@ -1,0 +1,320 @@
+"""Host-side mirror of the reference's operator interface for path 2 (FFT-based hydrodynamics).
+
+  kernels: Peskin3 / Peskin4 / Gaussian        Integrator/BDHI/FCM/FCM_kernels.cuh:22-58,159-196
+  FFT3D                                         cuFFT plans of FCM_impl.cuh:179-234
+  IBM                                           misc/IBM.cuh:99-203  (spread / gather)
+  FCM_impl                                      Integrator/BDHI/FCM/FCM_impl.cuh:36-129,652-693
+  FCM (BDHI Method) + EulerMaruyama             BDHI_FCM.cuh:85-153, BDHI_EulerMaruyama.cu:82-166
+Everything computes through the C ABI (include/uammd_b200.h); torch only owns device memory/streams.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import UB200Error, check, d3, i3
+from .md import _ptr, _stream_ptr
+
+
+class IBMKernelStruct(C.Structure):
+    _fields_ = [("kind", C.c_int), ("support", C.c_int), ("h", C.c_double), ("prefactor", C.c_double),
+                ("tau", C.c_double), ("rmax", C.c_double)]
+
+
+def _declare():
+    lib = _lib.lib()
+    if getattr(lib, "_fcm_declared", False):
+        return lib
+    vp, i, d, u32 = C.c_void_p, C.c_int, C.c_double, C.c_uint32
+    D3, I3 = C.c_double * 3, C.c_int * 3
+    K = C.POINTER(IBMKernelStruct)
+    sig = {
+        "ub200_fft3d_create": (i, [C.POINTER(vp), i, i, i, i]),
+        "ub200_fft3d_destroy": (i, [vp]),
+        "ub200_fft3d_exec": (i, [vp, vp, i, vp]),
+        "ub200_ibm_create": (i, [C.POINTER(vp), i, D3, I3, I3, K, i]),
+        "ub200_ibm_destroy": (i, [vp]),
+        "ub200_ibm_spread": (i, [vp, vp, vp, i, i, vp, vp]),
+        "ub200_ibm_spread_overwrite": (i, [vp, vp, vp, i, i, vp, vp]),
+        "ub200_ibm_gather": (i, [vp, vp, i, vp, vp, vp]),
+        "ub200_fcm_create": (i, [C.POINTER(vp), i, D3, I3, K, d, u32]),
+        "ub200_fcm_destroy": (i, [vp]),
+        "ub200_fcm_mdot": (i, [vp, vp, vp, i, d, d, vp, vp]),
+        "ub200_fcm_grid_info": (i, [vp, I3, C.POINTER(i), C.POINTER(vp)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib._fcm_declared = True
+    return lib
+
+
+# ---------------- spreading kernels (host-side parameter resolution, like the reference constructors) ----
+class Peskin3:
+    """FCM_ns::Kernels::Peskin::threePoint (FCM_kernels.cuh:159-176): support 3, hydrodynamic radius = h."""
+    support = 3
+
+    def __init__(self, h, tolerance=None):
+        self.h = float(h)
+
+    @staticmethod
+    def adviseGridSize(hydrodynamicRadius, tolerance=None):
+        return hydrodynamicRadius
+
+    def fixHydrodynamicRadius(self, hydrodynamicRadius, h):
+        return h
+
+    def struct(self):
+        return IBMKernelStruct(0, 3, self.h, 0.0, 0.0, 0.0)
+
+
+class Peskin4:
+    """FCM_ns::Kernels::Peskin::fourPoint (FCM_kernels.cuh:178-196): support 4, a = 1.31 h."""
+    support = 4
+    fac = 1.31
+
+    def __init__(self, h, tolerance=None):
+        self.h = float(h)
+
+    @staticmethod
+    def adviseGridSize(hydrodynamicRadius, tolerance=None):
+        return hydrodynamicRadius / Peskin4.fac
+
+    def fixHydrodynamicRadius(self, hydrodynamicRadius, h):
+        return h * Peskin4.fac
+
+    def struct(self):
+        return IBMKernelStruct(1, 4, self.h, 0.0, 0.0, 0.0)
+
+
+class Gaussian:
+    """FCM_ns::Kernels::Gaussian (FCM_kernels.cuh:22-58): width = h * upsampling(tolerance); the support is
+    found by marching r in steps of h/2 until phi(r) <= tolerance."""
+
+    @staticmethod
+    def computeUpsampling(tolerance):
+        amin, amax = 0.55, 1.65
+        x = -math.log10(3 * tolerance) / 10.0
+        return min(amin + x * (amax - amin), amax)
+
+    def __init__(self, h, tolerance):
+        self.h = float(h)
+        ups = self.computeUpsampling(tolerance)
+        width = h * ups
+        self.prefactor = (2.0 * math.pi * width * width) ** -0.5
+        self.tau = -0.5 / (width * width)
+        dr = 0.5 * h
+        r = dr
+        while self.prefactor * math.exp(self.tau * r * r) > tolerance:
+            r += dr
+        self.support = max(3, int(2 * r / h + 0.5))
+        self.rmax = self.support * h
+        self.a = h * ups * math.sqrt(math.pi)
+
+    @staticmethod
+    def adviseGridSize(hydrodynamicRadius, tolerance):
+        return hydrodynamicRadius / (math.sqrt(math.pi) * Gaussian.computeUpsampling(tolerance))
+
+    def fixHydrodynamicRadius(self, hydrodynamicRadius, h):
+        return self.a
+
+    def struct(self):
+        return IBMKernelStruct(2, self.support, self.h, self.prefactor, self.tau, self.rmax)
+
+
+def _prec(dtype):
+    if dtype == torch.float64:
+        return 8
+    if dtype == torch.float32:
+        return 4
+    raise UB200Error("precision must be torch.float32 or torch.float64")
+
+
+class FFT3D:
+    """In-place batched-3 real FFT on the padded real3 grid [nz, ny, 2(nx/2+1), 3]."""
+
+    def __init__(self, nx, ny, nz, dtype=torch.float64):
+        self.lib = _declare()
+        self.n = (nx, ny, nz)
+        self.dtype = dtype
+        self._h = C.c_void_p()
+        check(self.lib.ub200_fft3d_create(C.byref(self._h), _prec(dtype), nx, ny, nz))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib.ub200_fft3d_destroy(self._h)
+        except Exception:
+            pass
+
+    def _check(self, grid):
+        nx, ny, nz = self.n
+        if tuple(grid.shape) != (nz, ny, 2 * (nx // 2 + 1), 3) or grid.dtype != self.dtype or not grid.is_contiguous():
+            raise UB200Error("FFT3D: grid must be a contiguous [nz, ny, 2(nx/2+1), 3] tensor of the plan precision")
+
+    def forward(self, grid, stream=None):
+        """real3 -> complex3 in place; returns a complex view [nz, ny, nx/2+1, 3]."""
+        self._check(grid)
+        check(self.lib.ub200_fft3d_exec(self._h, _ptr(grid), -1, _stream_ptr(stream)))
+        nx, ny, nz = self.n
+        return torch.view_as_complex(grid.view(nz, ny, nx // 2 + 1, 3, 2))
+
+    def inverse(self, grid, stream=None):
+        self._check(grid)
+        check(self.lib.ub200_fft3d_exec(self._h, _ptr(grid), 1, _stream_ptr(stream)))
+        return grid
+
+
+class IBM:
+    """IBM<Kernel>(kernel, grid, LinearIndex3D(nxPad, ny, nz)): spread / gather accumulate like the reference."""
+
+    def __init__(self, kernel, L, cells, nxPad=None, periodic=(1, 1, 1), dtype=torch.float64):
+        self.lib = _declare()
+        self.kernel, self.cells, self.dtype = kernel, tuple(int(c) for c in cells), dtype
+        self.nxPad = int(nxPad) if nxPad is not None else self.cells[0]
+        L = (L, L, L) if np.isscalar(L) else L
+        self._h = C.c_void_p()
+        ks = kernel.struct()
+        check(self.lib.ub200_ibm_create(C.byref(self._h), _prec(dtype), d3(L), i3([int(p) for p in periodic]),
+                                        i3(self.cells), C.byref(ks), self.nxPad))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib.ub200_ibm_destroy(self._h)
+        except Exception:
+            pass
+
+    def newGrid(self, device):
+        nx, ny, nz = self.cells
+        return torch.zeros(nz, ny, self.nxPad, 3, dtype=self.dtype, device=device)
+
+    def spread(self, pos, values, grid, stream=None, overwrite=False):
+        fn = self.lib.ub200_ibm_spread_overwrite if overwrite else self.lib.ub200_ibm_spread
+        check(fn(self._h, _ptr(pos), _ptr(values), values.shape[1], pos.shape[0], _ptr(grid), _stream_ptr(stream)))
+
+    def gather(self, pos, grid, out, stream=None):
+        check(self.lib.ub200_ibm_gather(self._h, _ptr(pos), pos.shape[0], _ptr(grid), _ptr(out), _stream_ptr(stream)))
+
+
+def hasimotoSelfMobility(hydrodynamicRadius, viscosity, L):
+    """FCM_impl::getSelfMobility (FCM_impl.cuh:102-119): periodic correction to O(a^6)."""
+    a = hydrodynamicRadius / L
+    a3 = a ** 3
+    c = 2.83729747948061947666591710460773907
+    b = 0.19457
+    a6pref = 16.0 * math.pi ** 2 / 45.0 + 630.0 * b * b
+    return 1.0 / (6.0 * math.pi * viscosity * hydrodynamicRadius) * (1.0 - c * a + (4.0 / 3.0) * math.pi * a3 - a6pref * a3 * a3)
+
+
+class FCM_impl:
+    """FCM_impl<Kernel, KernelTorque> without torques. Parameters mirror FCM_impl::Parameters."""
+
+    def __init__(self, box, cells, kernel, viscosity, hydrodynamicRadius=None, seed=0, dtype=torch.float64):
+        self.lib = _declare()
+        L = (box, box, box) if np.isscalar(box) else tuple(box)
+        if L[0] <= 0:
+            raise UB200Error("FCM_impl requires a valid box")
+        if cells[0] <= 0:
+            raise UB200Error("FCM_impl requires a valid grid dimension")
+        if kernel is None:
+            raise UB200Error("FCM_impl requires instances of the spreading kernels")
+        self.L, self.cells, self.kernel, self.viscosity, self.dtype = L, tuple(int(c) for c in cells), kernel, viscosity, dtype
+        h = min(L[d] / cells[d] for d in range(3))
+        self.hydrodynamicRadius = hydrodynamicRadius if hydrodynamicRadius is not None else kernel.fixHydrodynamicRadius(0, h)
+        if seed == 0:
+            seed = int(np.random.SeedSequence().entropy & 0xFFFFFFFF) or 1
+        self.seed = seed & 0xFFFFFFFF
+        self._h = C.c_void_p()
+        ks = kernel.struct()
+        check(self.lib.ub200_fcm_create(C.byref(self._h), _prec(dtype), d3(L), i3(self.cells), C.byref(ks),
+                                        float(viscosity), self.seed))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib.ub200_fcm_destroy(self._h)
+        except Exception:
+            pass
+
+    def getHydrodynamicRadius(self):
+        return self.hydrodynamicRadius
+
+    def getSelfMobility(self):
+        return hasimotoSelfMobility(self.hydrodynamicRadius, self.viscosity, self.L[0])
+
+    def computeHydrodynamicDisplacements(self, pos, force, N=None, temperature=0.0, prefactor=0.0, out=None, stream=None):
+        """pos, force: real4 [N,4]; returns real3 [N,3] linear displacements (torques are not supported)."""
+        N = pos.shape[0] if N is None else N
+        if out is None:
+            out = torch.empty(N, 3, dtype=self.dtype, device=pos.device)
+        check(self.lib.ub200_fcm_mdot(self._h, _ptr(pos), _ptr(force), N, float(temperature), float(prefactor),
+                                      _ptr(out), _stream_ptr(stream)))
+        return out
+
+    def velocityGrid(self):
+        """Copy of the internal grid buffer (real-space velocities after the last call)."""
+        cells, nxPad, ptr = i3((0, 0, 0)), C.c_int(0), C.c_void_p()
+        check(self.lib.ub200_fcm_grid_info(self._h, cells, C.byref(nxPad), C.byref(ptr)))
+        from .md import _device_copy
+        return _device_copy(ptr.value, (cells[2], cells[1], nxPad.value, 3), self.dtype, torch.device("cuda"))
+
+
+class FCM:
+    """BDHI Method (BDHI_FCM.cuh:85-153): computeMF = computeHydrodynamicDisplacements(T, prefactor = 1/sqrt(dt));
+    computeBdW is a no-op (noise is already in MF)."""
+
+    def __init__(self, box, cells, kernel, viscosity, temperature, dt, seed=0, dtype=torch.float64):
+        self.impl = FCM_impl(box, cells, kernel, viscosity, seed=seed, dtype=dtype)
+        self.temperature, self.dt = temperature, dt
+
+    def computeMF(self, pos, force, MF, stream=None):
+        return self.impl.computeHydrodynamicDisplacements(pos, force, temperature=self.temperature,
+                                                          prefactor=1.0 / math.sqrt(self.dt), out=MF, stream=stream)
+
+    def computeBdW(self, BdW, stream=None):
+        return None
+
+    def getHydrodynamicRadius(self):
+        return self.impl.getHydrodynamicRadius()
+
+    def getSelfMobility(self):
+        return self.impl.getSelfMobility()
+
+
+class EulerMaruyama:
+    """BDHI::EulerMaruyama<Method>::forwardTime (BDHI_EulerMaruyama.cu:125-166) with external forces supplied by a
+    callable force(pos) -> real4 tensor (the interactors); positions updated as x += MF dt (noise lives in MF for
+    FCM, integrateGPUD :82-113 with BdW = nullptr semantics)."""
+
+    def __init__(self, method, pos, dt, forceFn=None):
+        self.method, self.pos, self.dt, self.forceFn = method, pos, float(dt), forceFn
+        self.MF = torch.zeros(pos.shape[0], 3, dtype=pos.dtype, device=pos.device)
+        self.force = torch.zeros_like(pos)
+        self.steps = 0
+
+    def forwardTime(self):
+        self.steps += 1
+        if self.forceFn is not None:
+            self.force = self.forceFn(self.pos)
+        self.method.computeMF(self.pos, self.force, self.MF)
+        self.pos[:, :3] += self.MF * self.dt
+
+
+def smoke(dev):
+    """Tiny FCM invocation checked against the oracle (called by __graft_entry__.smoke)."""
+    from oracle import oracle as orc
+    from . import synthetic as syn
+    N, n, L = 2000, 32, 32.0
+    pos = syn.uniform_cloud(N, L, seed=11).astype(np.float64)
+    force = np.zeros((N, 4))
+    force[:, :3] = syn.gaussian_forces(N, seed=12)
+    fcm = FCM_impl(L, (n, n, n), Peskin3(L / n), viscosity=1.0, seed=1)
+    out = fcm.computeHydrodynamicDisplacements(torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev))
+    torch.cuda.synchronize()
+    ref = orc.fcm_mdot((L, L, L), (n, n, n), orc.peskin3(L / n), 1.0, pos, force[:, :3])
+    err = np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref)
+    assert err < 1e-11, f"FCM mdot rel-L2 error {err}"
+    return f"path2 FCM N={N} {n}^3 rel-L2 {err:.1e}"
