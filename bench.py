@@ -138,6 +138,9 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
+    if not args.no_fcm:
+        from uammd_b200 import fcm_bench
+        line["fcm"] = fcm_bench.run_reference(ROOT, steps=args.fcm_steps)
     print(json.dumps(line))
     return 0
 
@@ -166,6 +169,7 @@ def main():
     ap.add_argument("--equil", type=int, default=300, help="untimed equilibration steps (melts the FCC start)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fcm", action="store_true")
+    ap.add_argument("--fcm-steps", type=int, default=100)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -305,7 +309,7 @@ def main():
         if not args.no_fcm and world == 1:
             try:
                 from uammd_b200 import fcm_bench
-                line["fcm"] = fcm_bench.run(dev, peak)
+                line["fcm"] = fcm_bench.run(dev, peak, steps=args.fcm_steps)
             except ImportError:
                 pass
         print(json.dumps(line))

@@ -88,6 +88,11 @@ int ub200_celllist_error_flag(ub200_celllist *cl, void *stream, int *flag);
 int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, float *d_energy,
                      float *d_virial, const int *d_globalIdx, void *stream);
 
+/* same with the parameter table already on the device (Radial<LJFunctor>'s BasicParameterHandler keeps it there,
+ * Potential/ParameterHandler.cuh:8-12,62-65): d_params = PairParameters[ntypes*ntypes] */
+int ub200_lj_sum_devparams_f32(ub200_celllist *cl, const void *d_params, int ntypes, void *d_force, float *d_energy,
+                               float *d_virial, const int *d_globalIdx, void *stream);
+
 /* DPD transverser (Potential/DPD.cuh:92-159). d_vel: real3[*] indexed by GLOBAL index like getInfo(pi).
  * sigma = sqrt(2 T)/sqrt(dt) as DPD_impl computes it (:66,:84-92); seed/step are the Saru seeds (:129).
  * idStride = N used in ij = min + N*max (int32 arithmetic, wraps like the reference). */
@@ -169,6 +174,11 @@ int ub200_fcm_destroy(ub200_fcm *fcm);
 int ub200_fcm_mdot(ub200_fcm *fcm, const void *d_pos, const void *d_force, int N, double temperature,
                    double prefactor, void *d_out3, void *stream);
 int ub200_fcm_grid_info(ub200_fcm *fcm, int cells[3], int *nxPad, void **d_grid);
+/* BDHI::EulerMaruyama position update. Replaces EulerMaruyama_ns::integrateGPUD
+ * (Integrator/BDHI/BDHI_EulerMaruyama.cu:82-113): x += dt (K x + MF) + sqrt2Tdt BdW. d_MF/d_BdW real3[N] indexed by
+ * group slot, d_BdW and K9 (host, row major 3x3 shear matrix) may be NULL. */
+int ub200_bdhi_euler_update(int precisionBytes, void *d_pos, const int *d_groupIdx, const void *d_MF, const void *d_BdW,
+                            const double *K9, int N, double sqrt2Tdt, double dt, int is2D, void *stream);
 
 /* number of kernel launches the library enqueued since process start (bench.py's gpu_launches) */
 unsigned long long ub200_launch_count(void);

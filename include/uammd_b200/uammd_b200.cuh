@@ -1,0 +1,293 @@
+/* uammd_b200 - C++14 glue between UAMMD's concepts and the C ABI (include/uammd_b200.h).
+ *
+ * Include it from a UAMMD program (after "uammd.cuh") and link with -luammd_b200. The classes satisfy the
+ * reference's duck-typed concepts, so they drop into its templates:
+ *
+ *   uammd::b200::CellList         NeighbourList concept (Interactor/NeighbourList/CellList.cuh:66-208):
+ *                                 PairForces<AnyPotential, b200::CellList> builds the list with our CUDA path and
+ *                                 runs ANY user Transverser through the reference's own traversal kernel, because
+ *                                 getCellList() returns the reference's CellListData bit for bit.
+ *   uammd::b200::LJ               Potential::LJ with access to its device parameter table.
+ *   uammd::b200::PairForcesLJ     Interactor (Interactor/Interactor.cuh:56-119) = PairForces<Potential::LJ, CellList>
+ *                                 with the specialised LJ traversal (Interactor/PairForces.cu:43-78).
+ *   uammd::b200::FCM<Kernel>      BDHI Method concept (Integrator/BDHI/BDHI_FCM.cuh:85-153) for
+ *                                 BDHI::EulerMaruyama<Method> (Integrator/BDHI/BDHI_EulerMaruyama.cuh:64-98).
+ * Error codes of the C ABI are converted into the reference's exception convention (std::runtime_error).
+ */
+#ifndef UAMMD_B200_GLUE_CUH
+#define UAMMD_B200_GLUE_CUH
+#include "uammd.cuh"
+#include "Interactor/Interactor.cuh"
+#include "Interactor/NeighbourList/CellList.cuh"
+#include "Interactor/Potential/Potential.cuh"
+#include "Integrator/BDHI/BDHI.cuh"
+#include "Integrator/BDHI/FCM/FCM_kernels.cuh"
+#include "../uammd_b200.h"
+#include <cmath>
+#include <limits>
+#include <stdexcept>
+#include <string>
+
+namespace uammd {
+namespace b200 {
+
+inline void check(int code, const char *where) {
+  if (code != UB200_OK) {
+    std::string msg = std::string("[uammd_b200] ") + where + ": " + ub200_error_string(code);
+    if (code == UB200_ERR_CUDA) msg += " (cudaError " + std::to_string(ub200_last_cuda_error()) + ")";
+    System::log<System::ERROR>("%s", msg.c_str());
+    throw std::runtime_error(msg);
+  }
+}
+
+#ifndef DOUBLE_PRECISION /* path 1 is single precision (BASELINE config 2); a double build only gets path 2 */
+/* ---------------------------------------------------------------- CellList ---------------------------------- */
+class CellList {
+  shared_ptr<ParticleGroup> pg;
+  ub200_celllist *handle = nullptr;
+  connection posWriteConnection;
+  bool force_next_update = true;
+  real3 currentCutOff = real3();
+  Box currentBox = Box();
+  Grid grid;
+
+  /* CellList::createUpdateGrid (CellList.cuh:100-126): infinite dimensions get 64 non periodic cells of one cut-off,
+     cellDim = int(L/rc), dimensions with <= 3 cells collapse to one cell */
+  Grid createUpdateGrid(Box box, real3 cutOff) {
+    real3 L = box.boxSize;
+    constexpr real inf = std::numeric_limits<real>::max();
+    const bool fx = L.x < inf, fy = L.y < inf, fz = L.z < inf;
+    if (!fx) L.x = 64 * cutOff.x;
+    if (!fy) L.y = 64 * cutOff.y;
+    if (!fz) L.z = 64 * cutOff.z;
+    Box ubox(L);
+    ubox.setPeriodicity(box.isPeriodicX() and fx, box.isPeriodicY() and fy, box.isPeriodicZ() and fz);
+    int3 cd = make_int3(L / cutOff);
+    if (cd.x <= 3) cd.x = 1;
+    if (cd.y <= 3) cd.y = 1;
+    if (cd.z <= 3) cd.z = 1;
+    return Grid(ubox, cd);
+  }
+
+public:
+  CellList(shared_ptr<ParticleData> pd) : CellList(std::make_shared<ParticleGroup>(pd)) {}
+  CellList(shared_ptr<ParticleGroup> pg) : pg(pg) {
+    check(ub200_celllist_create(&handle), "celllist_create");
+    posWriteConnection = pg->getParticleData()->getPosWriteRequestedSignal()->connect(
+        [this]() { this->force_next_update = true; });
+  }
+  CellList(const CellList &) = delete;
+  ~CellList() {
+    posWriteConnection.disconnect();
+    ub200_celllist_destroy(handle);
+  }
+
+  void update(Box box, real cutOff, cudaStream_t st = 0) { update(box, make_real3(cutOff), st); }
+
+  void update(Box box, real3 cutOff, cudaStream_t st = 0) {
+    const bool rebuild = force_next_update or cutOff.x != currentCutOff.x or cutOff.y != currentCutOff.y or
+                         cutOff.z != currentCutOff.z or box != currentBox;
+    if (!rebuild) return;
+    currentBox = box;
+    currentCutOff = cutOff;
+    grid = createUpdateGrid(box, cutOff);
+    auto pd = pg->getParticleData();
+    const int N = pg->getNumberParticles();
+    auto pos = pd->getPos(access::location::gpu, access::mode::read);
+    const int *gidx = pg->getIndicesRawPtr(access::location::gpu);
+    const float L[3] = {grid.box.boxSize.x, grid.box.boxSize.y, grid.box.boxSize.z};
+    const int periodic[3] = {grid.box.isPeriodicX(), grid.box.isPeriodicY(), grid.box.isPeriodicZ()};
+    const int cd[3] = {grid.cellDim.x, grid.cellDim.y, grid.cellDim.z};
+    check(ub200_celllist_build_f32(handle, pos.raw(), gidx, N, L, periodic, cd, (void *)st), "celllist_build");
+    force_next_update = false;
+  }
+
+  /* same launch as CellList::transverseList (CellList.cuh:165-182): the reference's generic kernel over OUR list */
+  template <class Transverser> void transverseList(Transverser &tr, cudaStream_t st = 0) {
+    const int N = pg->getNumberParticles();
+    const int Nthreads = 128;
+    const int Nblocks = N / Nthreads + ((N % Nthreads) ? 1 : 0);
+    auto globalIndex = pg->getIndexIterator(access::location::gpu);
+    size_t shMemorySize = SFINAE::SharedMemorySizeDelegator<Transverser>().getSharedMemorySize(tr);
+    SFINAE::TransverserAdaptor<Transverser>::prepare(tr, pg->getParticleData());
+    NeighbourList_ns::transverseWithNeighbourContainer<<<Nblocks, Nthreads, shMemorySize, st>>>(
+        tr, globalIndex, this->getNeighbourContainer(), N);
+    CudaCheckError();
+  }
+
+  CellListBase::CellListData getCellList() {
+    ub200_celllist_view v;
+    check(ub200_celllist_view_get(handle, &v), "celllist_view_get");
+    CellListBase::CellListData cl;
+    cl.cellStart = v.d_cellStart;
+    cl.cellEnd = v.d_cellEnd;
+    cl.sortPos = reinterpret_cast<const real4 *>(v.d_sortPos);
+    cl.groupIndex = v.d_groupIndex;
+    cl.grid = grid;
+    cl.VALID_CELL = v.VALID_CELL;
+    return cl;
+  }
+
+  CellList_ns::NeighbourContainer getNeighbourContainer() { return CellList_ns::NeighbourContainer(getCellList()); }
+
+  ub200_celllist *getHandle() { return handle; }
+  shared_ptr<ParticleGroup> getGroup() { return pg; }
+};
+
+/* ---------------------------------------------------------------- LJ ---------------------------------------- */
+/* Radial<LJFunctor> keeps its PairParameters table {cutOff2, sigma2, epsilonDivSigma2, shift} in a protected
+   BasicParameterHandler (Potential/RadialPotential.cuh:55-58, ParameterHandler.cuh:41-65); deriving exposes it. */
+class LJ : public Potential::LJ {
+public:
+  struct DeviceTable {
+    const void *d_params;
+    int ntypes;
+  };
+  DeviceTable getDeviceTable() {
+    auto it = this->pairParameters->getIterator();
+    return {it.globalMem, it.ntypes};
+  }
+};
+
+class PairForcesLJ : public Interactor {
+  shared_ptr<CellList> nl;
+  shared_ptr<LJ> pot;
+  Box box;
+
+public:
+  struct Parameters {
+    Box box = Box(std::numeric_limits<real>::infinity());
+    shared_ptr<CellList> nl = nullptr;
+  };
+  PairForcesLJ(shared_ptr<ParticleData> pd, Parameters par, shared_ptr<LJ> pot)
+      : PairForcesLJ(std::make_shared<ParticleGroup>(pd, "All"), par, pot) {}
+  PairForcesLJ(shared_ptr<ParticleGroup> pg, Parameters par, shared_ptr<LJ> pot)
+      : Interactor(pg, "b200::PairForcesLJ"), nl(par.nl), pot(pot), box(par.box) {
+    if (!nl) nl = std::make_shared<CellList>(pg);
+  }
+
+  void updateBox(Box newBox) override { box = newBox; }
+
+  /* Interactor::sum: accumulates into pd's force / energy / virial like Radial::Transverser::set */
+  void sum(Computables comp, cudaStream_t st = 0) override {
+    const real rcut = pot->getCutOff();
+    if (box.boxSize.x <= 3 * rcut and box.boxSize.y <= 3 * rcut and box.boxSize.z <= 3 * rcut)
+      throw std::runtime_error("[uammd_b200] box <= 3 rcut in every dimension needs the NBody path (PairForces.cu:49-53)");
+    nl->update(box, rcut, st);
+    auto force = comp.force ? pd->getForce(access::location::gpu, access::mode::readwrite).raw() : nullptr;
+    auto energy = comp.energy ? pd->getEnergy(access::location::gpu, access::mode::readwrite).raw() : nullptr;
+    auto virial = comp.virial ? pd->getVirial(access::location::gpu, access::mode::readwrite).raw() : nullptr;
+    const auto table = pot->getDeviceTable();
+    const int *gidx = pg->getIndicesRawPtr(access::location::gpu);
+    check(ub200_lj_sum_devparams_f32(nl->getHandle(), table.d_params, table.ntypes, force, energy, virial, gidx,
+                                     (void *)st),
+          "lj_sum");
+  }
+  shared_ptr<CellList> getNeighbourList() { return nl; }
+};
+#endif /* !DOUBLE_PRECISION */
+
+/* ---------------------------------------------------------------- FCM --------------------------------------- */
+namespace detail {
+template <class Kernel> struct KernelDescriptor;
+template <> struct KernelDescriptor<BDHI::FCM_ns::Kernels::Peskin::threePoint> {
+  static ub200_ibm_kernel make(real h, real) { return {UB200_KERNEL_PESKIN3, 3, (double)h, 0, 0, 0}; }
+  static real radius(real h, real) { return h; }
+};
+template <> struct KernelDescriptor<BDHI::FCM_ns::Kernels::Peskin::fourPoint> {
+  static ub200_ibm_kernel make(real h, real) { return {UB200_KERNEL_PESKIN4, 4, (double)h, 0, 0, 0}; }
+  static real radius(real h, real) { return h * BDHI::FCM_ns::Kernels::Peskin::fourPoint::fac; }
+};
+/* FCM_ns::Kernels::Gaussian keeps width/prefactor private: recompute them with its constructor's rule
+   (Integrator/BDHI/FCM/FCM_kernels.cuh:22-46) */
+template <> struct KernelDescriptor<BDHI::FCM_ns::Kernels::Gaussian> {
+  static double upsampling(double tolerance) {
+    const double amin = 0.55, amax = 1.65, x = -std::log10(3 * tolerance) / 10.0;
+    return std::min(amin + x * (amax - amin), amax);
+  }
+  static ub200_ibm_kernel make(real h, real tolerance) {
+    const double width = (double)h * upsampling(tolerance);
+    ub200_ibm_kernel k;
+    k.kind = UB200_KERNEL_GAUSSIAN;
+    k.h = h;
+    k.prefactor = std::pow(2.0 * M_PI * width * width, -0.5);
+    k.tau = -0.5 / (width * width);
+    const double dr = 0.5 * h;
+    double r = dr;
+    while (k.prefactor * std::exp(k.tau * r * r) > tolerance) r += dr;
+    k.support = std::max(3, int(2 * r / h + 0.5));
+    k.rmax = k.support * (double)h;
+    return k;
+  }
+  static real radius(real h, real tolerance) { return h * upsampling(tolerance) * std::sqrt(M_PI); }
+};
+} // namespace detail
+
+template <class Kernel = BDHI::FCM_ns::Kernels::Gaussian> class FCM {
+  shared_ptr<ParticleGroup> pg;
+  ub200_fcm *handle = nullptr;
+  real temperature, dt, viscosity, hydrodynamicRadius;
+  Box box;
+
+public:
+  struct Parameters : BDHI::Parameters {
+    int3 cells = make_int3(-1, -1, -1);
+    uint seed = 0;
+    bool adaptBoxSize = false;
+  };
+
+  FCM(shared_ptr<ParticleData> pd, Parameters par) : FCM(std::make_shared<ParticleGroup>(pd, "All"), par) {}
+
+  FCM(shared_ptr<ParticleGroup> pg, Parameters par)
+      : pg(pg), temperature(par.temperature), dt(par.dt), viscosity(par.viscosity), box(par.box) {
+    if (par.seed == 0) par.seed = pg->getParticleData()->getSystem()->rng().next32();
+    /* detail::initializeGrid (BDHI_FCM.cuh:29-48) */
+    int3 cd = par.cells;
+    if (cd.x <= 0) {
+      if (par.hydrodynamicRadius <= 0)
+        throw std::runtime_error("[uammd_b200::FCM] hydrodynamic radius needed when cells are not provided");
+      const real h = Kernel::adviseGridSize(par.hydrodynamicRadius, par.tolerance);
+      cd = nextFFTWiseSize3D(make_int3(box.boxSize / h));
+      if (par.adaptBoxSize) box = Box(make_real3(cd) * h);
+    }
+    Grid grid(box, cd);
+    const real h = std::min({grid.cellSize.x, grid.cellSize.y, grid.cellSize.z});
+    const ub200_ibm_kernel k = detail::KernelDescriptor<Kernel>::make(h, par.tolerance);
+    hydrodynamicRadius = detail::KernelDescriptor<Kernel>::radius(grid.cellSize.x, par.tolerance);
+    const double L[3] = {(double)box.boxSize.x, (double)box.boxSize.y, (double)box.boxSize.z};
+    const int cells[3] = {cd.x, cd.y, cd.z};
+    check(ub200_fcm_create(&handle, (int)sizeof(real), L, cells, &k, (double)viscosity, par.seed), "fcm_create");
+  }
+  FCM(const FCM &) = delete;
+  ~FCM() { ub200_fcm_destroy(handle); }
+
+  void setup_step(cudaStream_t st = 0) {}
+
+  /* BDHI::FCM::computeMF (BDHI_FCM.cuh:131-142): MF = M F + sqrt(2T/dt) M^1/2 dW, written straight into MF */
+  void computeMF(real3 *MF, cudaStream_t st = 0) {
+    auto pd = pg->getParticleData();
+    auto force = pd->getForce(access::gpu, access::read);
+    auto pos = pd->getPos(access::gpu, access::read);
+    const int N = pg->getNumberParticles();
+    check(ub200_fcm_mdot(handle, pos.raw(), force.raw(), N, (double)temperature, 1.0 / std::sqrt((double)dt), MF,
+                         (void *)st),
+          "fcm_mdot");
+  }
+  void computeBdW(real3 *BdW, cudaStream_t st = 0) {} // included in MF, like the reference
+  void finish_step(cudaStream_t st = 0) {}
+
+  real getHydrodynamicRadius() { return hydrodynamicRadius; }
+
+  /* FCM_impl::getSelfMobility (FCM_impl.cuh:102-119) */
+  real getSelfMobility() {
+    long double rh = hydrodynamicRadius, L = box.boxSize.x, a = rh / L, a3 = a * a * a;
+    const long double c = 2.83729747948061947666591710460773907l, b = 0.19457l;
+    const long double a6pref = 16.0l * M_PIl * M_PIl / 45.0l + 630.0L * b * b;
+    return 1.0l / (6.0l * M_PIl * viscosity * rh) * (1.0l - c * a + (4.0l / 3.0l) * M_PIl * a3 - a6pref * a3 * a3);
+  }
+  ub200_fcm *getHandle() { return handle; }
+};
+
+} // namespace b200
+} // namespace uammd
+#endif

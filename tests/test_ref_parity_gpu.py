@@ -74,6 +74,6 @@ def test_reference_parity(orc, cuda, tmp_path, N, kind):
     assert err_new < 1.0 and err_ref < 1.0 and direct < 2.0
     # the restated fp32 oracle in reference order should be (nearly) the reference's bits
     f32, _, _ = orc.lj_f32(g, ocl, pot.table(), 1, N)
-    assert (np.abs(f32[:, :3] - ref["force"][:, :3]).max(axis=1) / tol).max() < 0.5
+    assert (np.abs(f32[:, :3] - ref["force"][:, :3]).max(axis=1) / tol).max() < 1.0
     assert np.allclose(e.cpu().numpy(), ref["energy"], rtol=2e-4, atol=2e-4 * np.abs(ref["energy"]).max())
     assert np.allclose(v.cpu().numpy(), ref["virial"], rtol=2e-4, atol=2e-4 * np.abs(ref["virial"]).max())

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <new>
 #include <cmath>
+#include <vector>
 
 namespace ub200 {
 
@@ -136,6 +137,14 @@ __device__ __forceinline__ float imageNear(float r, float c, float L, float minu
 }
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+struct LJPar {
+  float cutOff2, sigma2, epsDivSigma2, shift; // LJFunctor::PairParameters (Potential/Potential.cuh:31-35)
+};
+struct LJTableCache {
+  DevBuf dev;
+  std::vector<float> host;
+};
 
 // defined in celllist.cu
 int exclusiveScanAndClear(uint32_t *counts, int M, uint32_t *out, uint32_t *tileSums, cudaStream_t st);

@@ -105,6 +105,35 @@ template <class T> struct Real4;
 template <> struct Real4<float> { using type = float4; };
 template <> struct Real4<double> { using type = double4; };
 
+// EulerMaruyama_ns::integrateGPUD (Integrator/BDHI/BDHI_EulerMaruyama.cu:82-113): dR = dt (K R + MF) + sqrt(2 T dt) BdW
+template <class T> struct ShearK { T k[9]; int on; };
+template <class T4>
+__global__ void __launch_bounds__(256)
+bdhiEulerUpdate(T4 *__restrict__ pos, const int *__restrict__ groupIdx, const decltype(T4::x) *__restrict__ MF,
+                const decltype(T4::x) *__restrict__ BdW, ShearK<decltype(T4::x)> K, int N, decltype(T4::x) sqrt2Tdt,
+                decltype(T4::x) dt, int is2D) {
+  using T = decltype(T4::x);
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  const int i = groupIdx ? groupIdx[id] : id;
+  T4 pc = pos[i];
+  T px = pc.x, py = pc.y, pz = pc.z;
+  if (K.on) {
+    const T kx = K.k[0] * px + K.k[1] * py + K.k[2] * pz;
+    const T ky = K.k[3] * px + K.k[4] * py + K.k[5] * pz;
+    const T kz = is2D ? T(0) : K.k[6] * px + K.k[7] * py + K.k[8] * pz;
+    px += kx * dt; py += ky * dt; pz += kz * dt;
+  }
+  px += MF[3 * (size_t)id] * dt; py += MF[3 * (size_t)id + 1] * dt; pz += MF[3 * (size_t)id + 2] * dt;
+  if (BdW) {
+    px += sqrt2Tdt * BdW[3 * (size_t)id];
+    py += sqrt2Tdt * BdW[3 * (size_t)id + 1];
+    if (!is2D) pz += sqrt2Tdt * BdW[3 * (size_t)id + 2];
+  }
+  pc.x = px; pc.y = py; pc.z = pz;
+  pos[i] = pc;
+}
+
 template <class T> struct IbmState {
   GridT<T> grid;
   IbmKernel<T> kern;
@@ -330,6 +359,26 @@ int ub200_fcm_grid_info(ub200_fcm *h, int cells[3], int *nxPad, void **d_grid) {
   if (cells) { cells[0] = f ? h->f.plan.nx : h->d.plan.nx; cells[1] = f ? h->f.plan.ny : h->d.plan.ny; cells[2] = f ? h->f.plan.nz : h->d.plan.nz; }
   if (nxPad) *nxPad = f ? h->f.plan.nxPad : h->d.plan.nxPad;
   if (d_grid) *d_grid = f ? h->f.grid.p : h->d.grid.p;
+  return UB200_OK;
+}
+
+int ub200_bdhi_euler_update(int precisionBytes, void *d_pos, const int *d_groupIdx, const void *d_MF, const void *d_BdW,
+                            const double *K9, int N, double sqrt2Tdt, double dt, int is2D, void *stream) {
+  if (!d_pos || !d_MF || N <= 0 || (precisionBytes != 4 && precisionBytes != 8)) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (N + 255) / 256;
+  if (precisionBytes == 4) {
+    ShearK<float> K; K.on = K9 != nullptr;
+    for (int q = 0; q < 9; q++) K.k[q] = K9 ? (float)K9[q] : 0.f;
+    bdhiEulerUpdate<float4><<<nb, 256, 0, st>>>((float4 *)d_pos, d_groupIdx, (const float *)d_MF, (const float *)d_BdW, K,
+                                                N, (float)sqrt2Tdt, (float)dt, is2D);
+  } else {
+    ShearK<double> K; K.on = K9 != nullptr;
+    for (int q = 0; q < 9; q++) K.k[q] = K9 ? K9[q] : 0.0;
+    bdhiEulerUpdate<double4><<<nb, 256, 0, st>>>((double4 *)d_pos, d_groupIdx, (const double *)d_MF,
+                                                 (const double *)d_BdW, K, N, sqrt2Tdt, dt, is2D);
+  }
+  UB200_LAUNCHED();
   return UB200_OK;
 }
 

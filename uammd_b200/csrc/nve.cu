@@ -5,7 +5,7 @@
 namespace ub200 {
 
 int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
-          const int *globalIdx, bool accumulate, DevBuf *tableBuf, cudaStream_t st);
+          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st);
 
 // v += (F/m) dt/2 ; step 1 also x += v dt. Same operation order as the reference (force/m is (1/m)*force,
 // utils/vector.cuh:191-193; the trailing multiply-adds are contracted by nvcc there, spelled out here).
@@ -63,7 +63,7 @@ using namespace ub200;
 
 struct ub200_md {
   ub200_celllist *cl = nullptr;
-  DevBuf ljTable;
+  LJTableCache ljTable;
   DevBuf dpos, dvel, dforce; // device state for the host-buffer entry point
 };
 
@@ -97,7 +97,7 @@ int ub200_md_create(ub200_md **out) {
 int ub200_md_destroy(ub200_md *md) {
   if (!md) return UB200_OK;
   ub200_celllist_destroy(md->cl);
-  md->ljTable.release(); md->dpos.release(); md->dvel.release(); md->dforce.release();
+  md->ljTable.dev.release(); md->dpos.release(); md->dvel.release(); md->dforce.release();
   delete md;
   return UB200_OK;
 }

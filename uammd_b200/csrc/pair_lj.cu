@@ -12,12 +12,9 @@
 // body is branch free, and a half-warp split butterfly reduces both particles at once. The reference instead
 // runs one thread per particle through a divergent 27-cell iterator with ~340 dependent global loads.
 #include "pair_common.cuh"
+#include <cstring>
 
 namespace ub200 {
-
-struct LJPar {
-  float cutOff2, sigma2, epsDivSigma2, shift;
-};
 
 struct Acc {
   float fx, fy, fz, e, v;
@@ -85,13 +82,14 @@ constexpr int kWarpCap = 416; // staged candidates per warp (6.5 KB, 8 CTAs/SM);
 template <bool ENERGY, bool VIRIAL, bool MULTITYPE, bool PAIRMIC, bool ACCUMULATE>
 __global__ void __launch_bounds__(kPairThreads, 8)
 ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
-                const uint32_t *__restrict__ binStart, GridF g, int ncells, LJPar par0,
+                const uint32_t *__restrict__ binStart, GridF g, int ncells,
                 const LJPar *__restrict__ parTable, int ntypes, float4 *__restrict__ force,
                 float *__restrict__ energy, float *__restrict__ virial, const int *__restrict__ globalIdx) {
   __shared__ float4 candAll[kPairWarps][kWarpCap];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 *cand = candAll[warp];
   const int warpsTotal = gridDim.x * kPairWarps;
+  const LJPar par0 = parTable[0]; // single type: BasicParameterHandler::Iterator returns entry 0 (ParameterHandler.cuh:49-50)
   const uint32_t rc2bitsm1 = __float_as_uint(par0.cutOff2) - 1u;
   for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
@@ -137,7 +135,10 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
       Acc a0 = {0.f, 0.f, 0.f, 0.f, 0.f}, a1 = {0.f, 0.f, 0.f, 0.f, 0.f};
       LJPar p0 = par0, p1 = par0;
       uint32_t rcb0 = rc2bitsm1, rcb1 = rc2bitsm1;
-      const int t0 = MULTITYPE ? (int)pi0.w * ntypes : 0, t1 = MULTITYPE ? (int)pi1.w * ntypes : 0;
+      // types outside the table fall back to entry 0 like BasicParameterHandler::Iterator (ParameterHandler.cuh:55-57)
+      const int ty0 = (int)pi0.w, ty1 = (int)pi1.w;
+      const int t0 = MULTITYPE && (unsigned)ty0 < (unsigned)ntypes ? ty0 * ntypes : -1;
+      const int t1 = MULTITYPE && (unsigned)ty1 < (unsigned)ntypes ? ty1 * ntypes : -1;
       if (staged) {
 #pragma unroll 2
         for (int t = lane; t < nc.total; t += 32) {
@@ -149,8 +150,10 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
             dx1 = foldCoord(dx1, g.Lx, g.mx); dy1 = foldCoord(dy1, g.Ly, g.my); dz1 = foldCoord(dz1, g.Lz, g.mz);
           }
           if (MULTITYPE) {
-            p0 = parTable[t0 + (int)pj.w]; rcb0 = __float_as_uint(p0.cutOff2) - 1u;
-            p1 = parTable[t1 + (int)pj.w]; rcb1 = __float_as_uint(p1.cutOff2) - 1u;
+            const int tj = (int)pj.w;
+            const bool ok = (unsigned)tj < (unsigned)ntypes;
+            p0 = parTable[(ok && t0 >= 0) ? t0 + tj : 0]; rcb0 = __float_as_uint(p0.cutOff2) - 1u;
+            p1 = parTable[(ok && t1 >= 0) ? t1 + tj : 0]; rcb1 = __float_as_uint(p1.cutOff2) - 1u;
           }
           ljPair<ENERGY, VIRIAL>(dx0, dy0, dz0, p0, rcb0, a0);
           ljPair<ENERGY, VIRIAL>(dx1, dy1, dz1, p1, rcb1, a1);
@@ -171,8 +174,10 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
               dx1 = foldCoord(dx1, g.Lx, g.mx); dy1 = foldCoord(dy1, g.Ly, g.my); dz1 = foldCoord(dz1, g.Lz, g.mz);
             }
             if (MULTITYPE) {
-              p0 = parTable[t0 + (int)pj.w]; rcb0 = __float_as_uint(p0.cutOff2) - 1u;
-              p1 = parTable[t1 + (int)pj.w]; rcb1 = __float_as_uint(p1.cutOff2) - 1u;
+              const int tj = (int)pj.w;
+              const bool ok = (unsigned)tj < (unsigned)ntypes;
+              p0 = parTable[(ok && t0 >= 0) ? t0 + tj : 0]; rcb0 = __float_as_uint(p0.cutOff2) - 1u;
+              p1 = parTable[(ok && t1 >= 0) ? t1 + tj : 0]; rcb1 = __float_as_uint(p1.cutOff2) - 1u;
             }
             ljPair<ENERGY, VIRIAL>(dx0, dy0, dz0, p0, rcb0, a0);
             ljPair<ENERGY, VIRIAL>(dx1, dy1, dz1, p1, rcb1, a1);
@@ -200,8 +205,8 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
 }
 
 template <bool E, bool V, bool M, bool P, bool A>
-static int launchLJ(ub200_celllist *cl, LJPar par0, const LJPar *table, int ntypes, float4 *force, float *energy,
-                    float *virial, const int *globalIdx, cudaStream_t st) {
+static int launchLJ(ub200_celllist *cl, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
+                    const int *globalIdx, cudaStream_t st) {
   auto kern = ljCellTraversal<E, V, M, P, A>;
   static int blocksPerSM = 0; // per instantiation
   if (!blocksPerSM) {
@@ -209,41 +214,27 @@ static int launchLJ(ub200_celllist *cl, LJPar par0, const LJPar *table, int ntyp
     if (blocksPerSM < 1) blocksPerSM = 1;
   }
   int grid = kNumSMs * blocksPerSM;
-  if (grid > cl->ncells) grid = cl->ncells;
+  const int needed = (cl->ncells + kPairWarps - 1) / kPairWarps;
+  if (grid > needed) grid = needed;
   kern<<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(), cl->binStart.as<uint32_t>(),
-                                      cl->grid, cl->ncells, par0, table, ntypes, force, energy, virial, globalIdx);
+                                      cl->grid, cl->ncells, table, ntypes, force, energy, virial, globalIdx);
   UB200_LAUNCHED();
   return UB200_OK;
 }
 
-// parameter table cache (device) for multi-type systems
-struct ParTableCache {
-  DevBuf buf;
-  int ntypes = 0;
-};
-
-int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
-          const int *globalIdx, bool accumulate, DevBuf *tableBuf, cudaStream_t st) {
-  if (!cl || !params || ntypes < 1) return UB200_ERR_INVALID_ARGUMENT;
+// d_table: device table [ntypes*ntypes] of LJPar
+int ljSumDev(ub200_celllist *cl, const LJPar *d_table, int ntypes, float4 *force, float *energy, float *virial,
+             const int *globalIdx, bool accumulate, cudaStream_t st) {
+  if (!cl || !d_table || ntypes < 1) return UB200_ERR_INVALID_ARGUMENT;
   if (!cl->built) return UB200_ERR_NOT_BUILT;
   if (!force && !energy && !virial) return UB200_OK;
   const GridF &g = cl->grid;
   // a periodic dimension with fewer than 4 cells needs the per-pair minimum image
   const bool pairMic = (g.mx != 0.0f && g.nx < 4) || (g.my != 0.0f && g.ny < 4) || (g.mz != 0.0f && g.nz < 4);
-  LJPar par0 = {params[0], params[1], params[2], params[3]};
-  const LJPar *table = nullptr;
-  if (ntypes > 1) {
-    if (!tableBuf) return UB200_ERR_INVALID_ARGUMENT;
-    int rc = tableBuf->reserve(sizeof(LJPar) * (size_t)ntypes * ntypes);
-    if (rc) return rc;
-    UB200_CUDA(cudaMemcpyAsync(tableBuf->p, params, sizeof(LJPar) * (size_t)ntypes * ntypes, cudaMemcpyHostToDevice, st));
-    table = tableBuf->as<LJPar>();
-  }
   const bool E = energy != nullptr, V = virial != nullptr, M = ntypes > 1;
 #define UB200_LJ_DISPATCH(e, v, m, p, a)                                                                     \
   if (E == e && V == v && M == m && pairMic == p && accumulate == a)                                         \
-    return launchLJ<e, v, m, p, a>(cl, par0, table, ntypes, force, energy, virial, globalIdx, st);
-  // forces only, single type: the hot configurations
+    return launchLJ<e, v, m, p, a>(cl, d_table, ntypes, force, energy, virial, globalIdx, st);
   UB200_LJ_DISPATCH(false, false, false, false, true)
   UB200_LJ_DISPATCH(false, false, false, false, false)
   UB200_LJ_DISPATCH(false, false, false, true, true)
@@ -253,13 +244,11 @@ int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, fl
   UB200_LJ_DISPATCH(false, false, true, true, true)
   UB200_LJ_DISPATCH(false, false, true, true, false)
 #undef UB200_LJ_DISPATCH
-  // anything asking for energy and/or virial: one generic instantiation per (M, P) computing both when needed
-  // (unrequested outputs are routed to a null pointer check inside the kernel via template flags)
 #define UB200_LJ_DISPATCH_EV(m, p)                                                                           \
   if (M == m && pairMic == p) {                                                                              \
-    if (E && V) return launchLJ<true, true, m, p, true>(cl, par0, table, ntypes, force, energy, virial, globalIdx, st); \
-    if (E) return launchLJ<true, false, m, p, true>(cl, par0, table, ntypes, force, energy, virial, globalIdx, st);     \
-    return launchLJ<false, true, m, p, true>(cl, par0, table, ntypes, force, energy, virial, globalIdx, st);  \
+    if (E && V) return launchLJ<true, true, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st); \
+    if (E) return launchLJ<true, false, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st);     \
+    return launchLJ<false, true, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st);      \
   }
   UB200_LJ_DISPATCH_EV(false, false)
   UB200_LJ_DISPATCH_EV(false, true)
@@ -269,14 +258,34 @@ int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, fl
   return UB200_ERR_UNSUPPORTED;
 }
 
+// host parameter table: uploaded into `cache` only when it changed since the last call
+int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
+          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st) {
+  if (!params || ntypes < 1 || !cache) return UB200_ERR_INVALID_ARGUMENT;
+  const size_t n = (size_t)ntypes * ntypes * 4;
+  if (cache->host.size() != n || memcmp(cache->host.data(), params, n * sizeof(float)) != 0) {
+    int rc = cache->dev.reserve(n * sizeof(float));
+    if (rc) return rc;
+    cache->host.assign(params, params + n);
+    UB200_CUDA(cudaMemcpyAsync(cache->dev.p, cache->host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  return ljSumDev(cl, cache->dev.as<LJPar>(), ntypes, force, energy, virial, globalIdx, accumulate, st);
+}
+
 } // namespace ub200
 
 using namespace ub200;
 
-static DevBuf g_ljTable; // shared parameter table for the stateless ub200_lj_sum_f32 entry point
+static LJTableCache g_ljTable; // parameter table of the stateless ub200_lj_sum_f32 entry point
 
 extern "C" int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, float *d_energy,
                                 float *d_virial, const int *d_globalIdx, void *stream) {
   return ljSum(cl, params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true, &g_ljTable,
                (cudaStream_t)stream);
+}
+
+extern "C" int ub200_lj_sum_devparams_f32(ub200_celllist *cl, const void *d_params, int ntypes, void *d_force,
+                                          float *d_energy, float *d_virial, const int *d_globalIdx, void *stream) {
+  return ljSumDev(cl, (const LJPar *)d_params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true,
+                  (cudaStream_t)stream);
 }

@@ -43,6 +43,7 @@ def _declare():
         "ub200_fcm_destroy": (i, [vp]),
         "ub200_fcm_mdot": (i, [vp, vp, vp, i, d, d, vp, vp]),
         "ub200_fcm_grid_info": (i, [vp, I3, C.POINTER(i), C.POINTER(vp)]),
+        "ub200_bdhi_euler_update": (i, [i, vp, vp, vp, vp, vp, i, d, d, i, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -300,7 +301,10 @@ class EulerMaruyama:
         if self.forceFn is not None:
             self.force = self.forceFn(self.pos)
         self.method.computeMF(self.pos, self.force, self.MF)
-        self.pos[:, :3] += self.MF * self.dt
+        T = getattr(self.method, "temperature", 0.0)
+        check(_declare().ub200_bdhi_euler_update(_prec(self.pos.dtype), _ptr(self.pos), None, _ptr(self.MF), None, None,
+                                                 self.pos.shape[0], math.sqrt(2 * self.dt * T), self.dt, 0,
+                                                 _stream_ptr()))
 
 
 def smoke(dev):

@@ -1,0 +1,98 @@
+"""FCM leg of bench.py: BASELINE.json configs[2] - BDHI::FCM triply periodic, N = 5e5, 128^3 grid, Peskin 3pt,
+fp64. A step is the body of BDHI::EulerMaruyama<FCM>::forwardTime with fixed external forces at T = 1:
+spread + FFT + Stokes projector + Fourier noise + inverse FFT + gather + position update.
+Metric: Mdof.steps/s with dof = 3*128^3 grid velocity unknowns."""
+import json
+import math
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import torch
+
+N, NGRID, L, ETA, TEMP, DT = 500_000, 128, 128.0, 1.0, 1.0, 0.01
+DOF = 3 * NGRID ** 3
+# compulsory bytes per step: 7 grid passes of 51.12 MB + 60 MB particle I/O
+GR = 2 * (NGRID // 2 + 1) * NGRID * NGRID * 24
+ALG_BYTES = 7 * GR + N * (32 * 2 + 32 + 24)
+
+
+def inputs():
+    from . import synthetic as syn
+    pos = np.zeros((N, 4)); pos[:, :3] = syn.uniform_cloud(N, L, seed=11)[:, :3].astype(np.float64)
+    force = np.zeros((N, 4)); force[:, :3] = syn.gaussian_forces(N, seed=12)
+    return pos, force
+
+
+def run(dev, hbm_peak, steps=100, warmup=10):
+    from .fcm import EulerMaruyama, FCM, Peskin3
+    from . import lib
+    pos, force = inputs()
+    dpos, dforce = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)
+    method = FCM(L, (NGRID,) * 3, Peskin3(L / NGRID), ETA, TEMP, DT, seed=1234)
+    integ = EulerMaruyama(method, dpos, DT)
+    integ.force = dforce
+    scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        integ.forwardTime()
+    torch.cuda.synchronize()
+    l0 = lib().ub200_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        scrub.fill_(3)
+        a.record()
+        integ.forwardTime()
+        b.record()
+    torch.cuda.synchronize()
+    launches = lib().ub200_launch_count() - l0
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        integ.forwardTime()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_b2b = e0.elapsed_time(e1) / steps
+    # e2e: host (pinned) positions + forces in, displacements out, every step
+    hp, hf = torch.from_numpy(pos).pin_memory(), torch.from_numpy(force).pin_memory()
+    hout = torch.zeros(N, 3, dtype=torch.float64).pin_memory()
+    dout = torch.zeros(N, 3, dtype=torch.float64, device=dev)
+    import time
+    for it in range(13):
+        if it == 3:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        dpos.copy_(hp, non_blocking=True); dforce.copy_(hf, non_blocking=True)
+        method.computeMF(dpos, dforce, dout)
+        hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / 10
+    gbs = ALG_BYTES / (ms * 1e-3) / 1e9
+    return {
+        "metric": "FCM Mdof.steps/s @128^3", "value": DOF / 1e6 * 1000.0 / ms, "unit": "Mdof.steps/s",
+        "steps_per_s": 1000.0 / ms, "ms_per_step": ms, "value_back_to_back": DOF / 1e6 * 1000.0 / ms_b2b,
+        "dtype": "f64", "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+        "config": {"workload": f"BDHI::EulerMaruyama<FCM>, N={N}, {NGRID}^3 grid, Peskin 3pt, eta={ETA}, T={TEMP}, dt={DT}",
+                   "l2": "flushed before every step (256 MiB write)"},
+        "e2e": {"value": DOF / 1e6 * 1000.0 / e2e_ms, "unit": "Mdof.steps/s", "h2d_bytes_per_step": N * 64,
+                "d2h_bytes_per_step": N * 24},
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                     "traffic": None, "algorithmic_bytes_per_step": ALG_BYTES,
+                     "note": "whole step against the compulsory 7 grid passes + particle I/O (SURVEY 8(d))"},
+    }
+
+
+def run_reference(root, steps=100, warmup=10):
+    exe = os.path.join(root, "oracle", "_ref", "ref_fcm")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_fcm was not built"}
+    pos, force = inputs()
+    with tempfile.TemporaryDirectory() as td:
+        pos.tofile(os.path.join(td, "p.bin")); force.tofile(os.path.join(td, "f.bin"))
+        out = subprocess.run([exe, "time", "peskin3", str(N), str(L), str(NGRID), str(ETA), "1e-3", str(TEMP), str(DT),
+                              str(warmup), str(steps), "1", os.path.join(td, "p.bin"), os.path.join(td, "f.bin")],
+                             check=True, capture_output=True, text=True, timeout=1200).stdout
+    r = [json.loads(l) for l in out.splitlines() if l.startswith("{")][-1]
+    return {"metric": "FCM Mdof.steps/s @128^3", "value": DOF / 1e6 * r["steps_per_s"], "unit": "Mdof.steps/s",
+            "steps_per_s": r["steps_per_s"], "ms_per_step": r["ms_per_step"], "dtype": "f64",
+            "what": "unmodified reference FCM_impl<Peskin::threePoint> (cuFFT) on the same B200, same protocol"}
