@@ -72,9 +72,11 @@ __device__ __forceinline__ void stockhamStage(const typename Vec2<T>::type *__re
   using C = typename Vec2<T>::type;
   const int nb = n / R;            // butterflies per transform
   const int twStep = n / (Ns * R); // twiddle index stride
+  // exact small-integer division through a float reciprocal: (w + 0.5)/nb stays >= 0.5/nb away from integers
+  const float invNb = 1.0f / (float)nb, invNs = 1.0f / (float)Ns;
   for (int w = threadIdx.x; w < nf * nb; w += blockDim.x) {
-    const int f = w / nb, j = w - f * nb;
-    const int k = j % Ns;
+    const int f = __float2int_rz(((float)w + 0.5f) * invNb), j = w - f * nb;
+    const int k = j - Ns * __float2int_rz(((float)j + 0.5f) * invNs);
     const C *src = a + f * fstride;
     C *dst = b + f * fstride + (j - k) * R + k;
     auto twid = [&](int idx) {

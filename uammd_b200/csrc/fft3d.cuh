@@ -17,7 +17,7 @@ template <class T> struct Fft3dPlan {
   int tileY = 0, tileZ = 0; // Y/Z pass: kx per tile
   size_t smemX = 0, smemY = 0, smemZ = 0;
 
-  static size_t smemBudget() { return 96 * 1024; }
+  static size_t smemBudget() { return 75 * 1024; } // 3 CTAs per SM
 
   int init(int nx_, int ny_, int nz_) {
     nx = nx_; ny = ny_; nz = nz_;
@@ -28,18 +28,19 @@ template <class T> struct Fft3dPlan {
     int rc;
     if ((rc = upload(twx, nx)) || (rc = upload(twy, ny)) || (rc = upload(twz, nz))) return rc;
     // X: pairs of lines, 3 components -> (lines/2)*3 complex transforms of length nx, two buffers
-    auto fit = [&](int n, int perUnit, int maxUnits) {
+    auto fit = [&](int n, int perUnit, int maxUnits, int nbuf = 3) {
       int units = maxUnits;
-      while (units > 1 && 2 * (size_t)units * perUnit * (n + 1) * sizeof(C) > smemBudget()) units--;
+      while (units > 1 && nbuf * (size_t)units * perUnit * (n + 1) * sizeof(C) > smemBudget()) units--;
       return units;
     };
-    const int pairs = fit(nx, 3, 4);
+    const int pairs = fit(nx, 3, 4, 2);
     linesPerCta = 2 * pairs;
     smemX = 2 * (size_t)pairs * 3 * (nx + 1) * sizeof(C);
-    tileY = fit(ny, 3, 4);
-    smemY = 2 * (size_t)tileY * 3 * (ny + 1) * sizeof(C);
-    tileZ = fit(nz, 3, 4);
-    smemZ = 2 * (size_t)tileZ * 3 * (nz + 1) * sizeof(C);
+    auto pow2 = [](int v) { return v >= 4 ? 4 : (v >= 2 ? 2 : 1); };
+    tileY = pow2(fit(ny, 3, 4));
+    smemY = 3 * (size_t)tileY * 3 * (ny + 1) * sizeof(C);
+    tileZ = pow2(fit(nz, 3, 4));
+    smemZ = 3 * (size_t)tileZ * 3 * (nz + 1) * sizeof(C);
     if (smemX > 200 * 1024 || smemY > 200 * 1024 || smemZ > 200 * 1024) return UB200_ERR_UNSUPPORTED;
     return UB200_OK;
   }
@@ -80,18 +81,18 @@ fftPassX(T *__restrict__ grid, int nx, int nkx, int nlines, int linesPerCta, Fft
   C *cbase = reinterpret_cast<C *>(base);
   if (FORWARD) {
     // load real lines: line l, sample x, component c -> transform (l/2)*3+c, real (l even) or imaginary part
-    for (int idx = threadIdx.x; idx < linesPerCta * nx * 3; idx += blockDim.x) {
-      const int l = idx / (nx * 3), rem = idx - l * nx * 3;
-      const int x = rem / 3, c = rem - 3 * x;
-      const T v = l < nl ? base[(size_t)l * lineReals + rem] : T(0);
-      T *dst = reinterpret_cast<T *>(buf0 + ((l >> 1) * 3 + c) * fstride + x);
-      dst[l & 1] = v;
-    }
+    for (int l = 0; l < linesPerCta; l++)
+      for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
+        const int x = rem / 3, c = rem - 3 * x;
+        const T v = l < nl ? base[(size_t)l * lineReals + rem] : T(0);
+        T *dst = reinterpret_cast<T *>(buf0 + ((l >> 1) * 3 + c) * fstride + x);
+        dst[l & 1] = v;
+      }
     __syncthreads();
     C *res = fftInShared<T, -1>(buf0, buf1, ax, fstride, nf, tw);
     // untangle the two real transforms and store the Hermitian halves
-    for (int idx = threadIdx.x; idx < pairs * nkx * 3; idx += blockDim.x) {
-      const int p = idx / (nkx * 3), rem = idx - p * nkx * 3;
+    for (int p = 0; p < pairs; p++)
+    for (int rem = threadIdx.x; rem < nkx * 3; rem += blockDim.x) {
       const int k = rem / 3, c = rem - 3 * k;
       const C zk = res[(p * 3 + c) * fstride + k];
       const C zn = res[(p * 3 + c) * fstride + (k == 0 ? 0 : nx - k)];
@@ -103,8 +104,8 @@ fftPassX(T *__restrict__ grid, int nx, int nkx, int nlines, int linesPerCta, Fft
   } else {
     // build Z_k = A_k + i B_k for all k from the stored halves (Hermitian symmetry for k > nx/2); like a C2R
     // transform, the imaginary parts of the self-conjugate modes (k = 0, and k = nx/2 for even nx) are ignored
-    for (int idx = threadIdx.x; idx < pairs * nx * 3; idx += blockDim.x) {
-      const int p = idx / (nx * 3), rem = idx - p * nx * 3;
+    for (int p = 0; p < pairs; p++)
+    for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
       const int k = rem / 3, c = rem - 3 * k;
       const int ks = k < nkx ? k : nx - k;
       C A = mk2<T>(T(0), T(0)), B = A;
@@ -116,14 +117,12 @@ fftPassX(T *__restrict__ grid, int nx, int nkx, int nlines, int linesPerCta, Fft
     }
     __syncthreads();
     C *res = fftInShared<T, +1>(buf0, buf1, ax, fstride, nf, tw);
-    for (int idx = threadIdx.x; idx < linesPerCta * nx * 3; idx += blockDim.x) {
-      const int l = idx / (nx * 3), rem = idx - l * nx * 3;
-      const int x = rem / 3, c = rem - 3 * x;
-      if (l < nl) {
+    for (int l = 0; l < nl; l++)
+      for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
+        const int x = rem / 3, c = rem - 3 * x;
         const T *src = reinterpret_cast<const T *>(res + ((l >> 1) * 3 + c) * fstride + x);
         base[(size_t)l * lineReals + rem] = src[l & 1];
       }
-    }
   }
 }
 
@@ -135,7 +134,19 @@ struct NoSpectralOp {
   template <class C> __device__ __forceinline__ void operator()(int, int, int, C &, C &, C &) const {}
 };
 
-// MODE: -1 forward, +1 inverse, 0 fused (forward, op, inverse)
+// 16- or 8-byte asynchronous global->shared copy (LDGSTS): no registers, completion through commit groups
+template <class C> __device__ __forceinline__ void cpAsync(C *smemDst, const C *gmemSrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// MODE: -1 forward, +1 inverse, 0 fused (forward, op, inverse).
+// Persistent CTAs walk the tiles; three shared buffers rotate as {current, ping-pong scratch, prefetch}: the
+// cp.async loads of the NEXT tile are in flight while the current tile is transformed and stored, so HBM/L2
+// latency is hidden even at 3 CTAs per SM.
 template <class T, int MODE, bool AXIS_IS_Z, class Op>
 __global__ void __launch_bounds__(kFftThreads)
 fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int n, int nkx, int nOther, int tile, size_t elemStride,
@@ -144,46 +155,86 @@ fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int n, int nkx, int nO
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int fstride = n + 1;
   const int ntx = (nkx + tile - 1) / tile;
-  const int tx = blockIdx.x % ntx, other = blockIdx.x / ntx;
-  const int kx0 = tx * tile;
-  const int w = min(tile, nkx - kx0) * 3; // complex numbers per axis point in this tile
+  const int ntiles = ntx * nOther;
   const int nf = tile * 3;
-  C *buf0 = reinterpret_cast<C *>(smemRaw);
-  C *buf1 = buf0 + (size_t)nf * fstride;
-  C *base = grid + ((size_t)other * otherStride + kx0) * 3;
-  for (int idx = threadIdx.x; idx < n * nf; idx += blockDim.x) {
-    const int i = idx / nf, f = idx - i * nf;
-    buf0[f * fstride + i] = f < w ? base[(size_t)i * elemStride * 3 + f] : mk2<T>(T(0), T(0));
-  }
-  __syncthreads();
-  C *res;
-  if (MODE <= 0) res = fftInShared<T, -1>(buf0, buf1, ax, fstride, nf, tw);
-  else res = fftInShared<T, +1>(buf0, buf1, ax, fstride, nf, tw);
-  if (MODE == 0) {
-    // spectral operator on the three components of every Fourier node of the tile
-    for (int idx = threadIdx.x; idx < n * tile; idx += blockDim.x) {
-      const int i = idx / tile, t = idx - i * tile;
-      if (kx0 + t < nkx) {
-        C *v = res + (t * 3) * fstride + i;
-        C vx = v[0], vy = v[fstride], vz = v[2 * fstride];
-        if (AXIS_IS_Z) op(kx0 + t, other, i, vx, vy, vz);
-        else op(kx0 + t, i, other, vx, vy, vz);
-        v[0] = vx; v[fstride] = vy; v[2 * fstride] = vz;
-      }
+  C *const bufBase = reinterpret_cast<C *>(smemRaw);
+  const int bufStride = nf * fstride;
+#define bufs(k) (bufBase + (k) * bufStride)
+  // threads in groups of gsz = 2^glog >= nf: lane f of a group moves complex number f of axis point i
+  const int glog = nf <= 4 ? 2 : (nf <= 8 ? 3 : 4), gsz = 1 << glog;
+  const int gf = threadIdx.x & (gsz - 1), gi = threadIdx.x >> glog, gstep = blockDim.x >> glog;
+  const int tlog = tile == 4 ? 2 : (tile == 2 ? 1 : 0); // tile is 1, 2 or 4
+
+  auto issueLoad = [&](int t, C *dst) {
+    const int tx = t % ntx, other = t / ntx;
+    const int kx0 = tx * tile;
+    const int w = min(tile, nkx - kx0) * 3;
+    const C *base = grid + ((size_t)other * otherStride + kx0) * 3;
+    if (gf < nf) {
+      if (gf < w) for (int i = gi; i < n; i += gstep) cpAsync(dst + gf * fstride + i, base + (size_t)i * elemStride * 3 + gf);
+      else for (int i = gi; i < n; i += gstep) dst[gf * fstride + i] = mk2<T>(T(0), T(0));
     }
+    cpAsyncCommit();
+  };
+
+  int t = blockIdx.x, cur = 0;
+  if (t < ntiles) issueLoad(t, bufs(0));
+  for (; t < ntiles; t += gridDim.x) {
+    const int nxt = t + gridDim.x;
+    const int scratch = cur == 2 ? 0 : cur + 1, pre = scratch == 2 ? 0 : scratch + 1;
+    if (nxt < ntiles) { issueLoad(nxt, bufs(pre)); cpAsyncWait<1>(); } else { cpAsyncWait<0>(); }
     __syncthreads();
-    C *other1 = res == buf0 ? buf1 : buf0;
-    res = fftInShared<T, +1>(res, other1, ax, fstride, nf, tw);
+    const int tx = t % ntx, other = t / ntx;
+    const int kx0 = tx * tile;
+    const int w = min(tile, nkx - kx0) * 3;
+    C *base = grid + ((size_t)other * otherStride + kx0) * 3;
+    C *res;
+    if (MODE <= 0) res = fftInShared<T, -1>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
+    else res = fftInShared<T, +1>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
+    if (MODE == 0) {
+      // spectral operator on the three components of every Fourier node of the tile
+      for (int idx = threadIdx.x; idx < n * tile; idx += blockDim.x) {
+        const int i = idx >> tlog, tt = idx & (tile - 1);
+        if (kx0 + tt < nkx) {
+          C *v = res + (tt * 3) * fstride + i;
+          C vx = v[0], vy = v[fstride], vz = v[2 * fstride];
+          if (AXIS_IS_Z) op(kx0 + tt, other, i, vx, vy, vz);
+          else op(kx0 + tt, i, other, vx, vy, vz);
+          v[0] = vx; v[fstride] = vy; v[2 * fstride] = vz;
+        }
+      }
+      __syncthreads();
+      C *other1 = res == bufs(cur) ? bufs(scratch) : bufs(cur);
+      res = fftInShared<T, +1>(res, other1, ax, fstride, nf, tw);
+    }
+    if (gf < w)
+      for (int i = gi; i < n; i += gstep) base[(size_t)i * elemStride * 3 + gf] = res[gf * fstride + i];
+    __syncthreads(); // result consumed: current + scratch may be overwritten by the next iterations
+    cur = pre;
   }
-  for (int idx = threadIdx.x; idx < n * nf; idx += blockDim.x) {
-    const int i = idx / nf, f = idx - i * nf;
-    if (f < w) base[(size_t)i * elemStride * 3 + f] = res[f * fstride + i];
-  }
+#undef bufs
 }
 
 template <class T> int fftEnsureSmem(const void *kern, size_t bytes) {
   if (bytes > 48 * 1024) UB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return UB200_OK;
+}
+
+// one CTA wave that fills the GPU (occupancy is a property of (kernel, smem); cached per kernel pointer)
+inline int persistentGrid(const void *kern, size_t smem, int ntiles) {
+  static const void *cachedKern[16];
+  static size_t cachedSmem[16];
+  static int cachedBlocks[16];
+  static int ncached = 0;
+  int perSM = 0;
+  for (int i = 0; i < ncached; i++)
+    if (cachedKern[i] == kern && cachedSmem[i] == smem) perSM = cachedBlocks[i];
+  if (!perSM) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kFftThreads, smem) != cudaSuccess || perSM < 1) perSM = 1;
+    if (ncached < 16) { cachedKern[ncached] = kern; cachedSmem[ncached] = smem; cachedBlocks[ncached++] = perSM; }
+  }
+  const int g = kNumSMs * perSM;
+  return g < ntiles ? g : ntiles;
 }
 
 template <class T, bool FORWARD> int launchPassX(const Fft3dPlan<T> &p, void *grid, cudaStream_t st) {
@@ -204,7 +255,7 @@ int launchPassY(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()
   int rc = fftEnsureSmem<T>((const void *)kern, p.smemY);
   if (rc) return rc;
   const int ntx = (p.nkx + p.tileY - 1) / p.tileY;
-  kern<<<ntx * p.nz, kFftThreads, p.smemY, st>>>((typename Vec2<T>::type *)grid, p.ny, p.nkx, p.nz, p.tileY,
+  kern<<<persistentGrid((const void *)kern, p.smemY, ntx * p.nz), kFftThreads, p.smemY, st>>>((typename Vec2<T>::type *)grid, p.ny, p.nkx, p.nz, p.tileY,
                                                  (size_t)p.nkx, (size_t)p.nkx * p.ny, p.ay,
                                                  p.twy.template as<typename Vec2<T>::type>(), op);
   UB200_LAUNCHED();
@@ -217,7 +268,7 @@ int launchPassZ(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()
   int rc = fftEnsureSmem<T>((const void *)kern, p.smemZ);
   if (rc) return rc;
   const int ntx = (p.nkx + p.tileZ - 1) / p.tileZ;
-  kern<<<ntx * p.ny, kFftThreads, p.smemZ, st>>>((typename Vec2<T>::type *)grid, p.nz, p.nkx, p.ny, p.tileZ,
+  kern<<<persistentGrid((const void *)kern, p.smemZ, ntx * p.ny), kFftThreads, p.smemZ, st>>>((typename Vec2<T>::type *)grid, p.nz, p.nkx, p.ny, p.tileZ,
                                                  (size_t)p.nkx * p.ny, (size_t)p.nkx, p.az,
                                                  p.twz.template as<typename Vec2<T>::type>(), op);
   UB200_LAUNCHED();

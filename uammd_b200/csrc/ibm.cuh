@@ -6,10 +6,10 @@
 // value*phiX*phiY*phiZ (DefaultWeightCompute, IBM.cuh:88-97) and quadrature weight = cell volume (:80-86).
 //
 // Small supports (Peskin 3/4 point): spreading is turned into an atomic-free, write-once NODE gather:
-//   binByCell -> stable order -> per-particle stencil records (support origin + 1-D weights + value) ->
-//   one thread per grid node sums the records of the particles whose support covers it and writes the node
-//   exactly once (no memset, no atomics, deterministic). The reference launches one 32-thread block per
-//   particle issuing 3*support^3 scalar atomics into a zero-filled grid.
+//   binByCell -> stable order + cell-sorted copies of position/value -> one CTA per 16x8x4 brick of grid nodes
+//   stages the particles of the brick's halo region in shared memory with their 1-D weights and every node is
+//   summed and written exactly once (no memset, no atomics, deterministic). The reference launches one
+//   32-thread block per particle issuing 3*support^3 scalar atomics into a zero-filled grid.
 // Large supports (Gaussian, up to 32 points per dimension): one warp per particle, weights in shared memory,
 //   atomics for spreading / shuffle reduction for interpolation.
 #pragma once
@@ -103,14 +103,8 @@ __device__ __forceinline__ T supportWeight(const GridT<T> &g, const IbmKernel<T>
   return cj >= 0 ? ibmPhi(k, distToCentre(g, d, r, cj)) : T(0);
 }
 
-// ---------------- small supports: sorted records + node-centric spread ----------------
+// ---------------- small supports: cell-sorted particles + brick-tiled node-centric spread ----------------
 constexpr int kSmallSupport = 4;
-template <class T> struct StencilRec {
-  int ox, oy, oz, pad; // support origin (unwrapped)
-  T w[3 * kSmallSupport];
-  T v[3];
-  T pad2;
-};
 
 template <class T4>
 __global__ void __launch_bounds__(256)
@@ -136,13 +130,16 @@ ibmBinByCell(const T4 *__restrict__ pos, int N, GridT<decltype(T4::x)> g, uint32
   codeSlot[i] = make_uint2(code, base + rank);
 }
 
-// stable order inside each cell + stencil record of the particle in its sorted slot
-template <class T4, class V>
+// stable order inside each cell; cell-sorted copies of the spread value, of the support origin and of the 3*S
+// one-dimensional weights (window evaluations happen once per particle, here)
+template <class T4, int S>
 __global__ void __launch_bounds__(256)
-ibmOrderAndStencil(const int *__restrict__ unstable, const uint2 *__restrict__ codeSlot,
-                   const uint32_t *__restrict__ binStart, const T4 *__restrict__ pos, const V *__restrict__ val,
-                   int valStride, int N, GridT<decltype(T4::x)> g, IbmKernel<decltype(T4::x)> k,
-                   int *__restrict__ sortedIndex, StencilRec<decltype(T4::x)> *__restrict__ recs) {
+ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeSlot,
+               const uint32_t *__restrict__ binStart, const T4 *__restrict__ pos,
+               const decltype(T4::x) *__restrict__ val, int valStride, int N, GridT<decltype(T4::x)> g,
+               IbmKernel<decltype(T4::x)> k, int *__restrict__ sortedIndex, T4 *__restrict__ sortedPos,
+               decltype(T4::x) *__restrict__ sortedVal, int4 *__restrict__ sortedOrigin,
+               decltype(T4::x) *__restrict__ sortedW) {
   using T = decltype(T4::x);
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= N) return;
@@ -153,119 +150,240 @@ ibmOrderAndStencil(const int *__restrict__ unstable, const uint2 *__restrict__ c
   for (int j = s; j < e; j++) rank += (__ldg(unstable + j) < i);
   const int dst = s + rank;
   sortedIndex[dst] = i;
-  const T4 p = pos[i];
-  StencilRec<T> r;
+  T4 p = pos[i];
+  T v0 = T(0), v1 = T(0), v2 = T(0);
+  if (val) {
+    const T *vp = val + (size_t)i * valStride;
+    v0 = vp[0]; v1 = vp[1]; v2 = vp[2];
+  }
   const T pr[3] = {p.x, p.y, p.z};
   int o[3];
+  T *wout = sortedW + (size_t)dst * (3 * S);
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    const int c = cellOfT(g, d, pr[d]);
-    o[d] = supportOrigin(g, k, d, pr[d], c);
+    const int cell = cellOfT(g, d, pr[d]);
+    o[d] = supportOrigin(g, k, d, pr[d], cell);
 #pragma unroll
-    for (int q = 0; q < kSmallSupport; q++)
-      r.w[d * kSmallSupport + q] = q < k.support ? supportWeight(g, k, d, pr[d], o[d], q) : T(0);
+    for (int i = 0; i < S; i++) wout[d * S + i] = supportWeight(g, k, d, pr[d], o[d], i);
   }
-  r.ox = o[0]; r.oy = o[1]; r.oz = o[2]; r.pad = 0;
-  if (val) {
-    const T *vp = reinterpret_cast<const T *>(val) + (size_t)i * valStride;
-    r.v[0] = vp[0]; r.v[1] = vp[1]; r.v[2] = vp[2];
-  } else {
-    r.v[0] = r.v[1] = r.v[2] = T(0);
-  }
-  r.pad2 = T(0);
-  recs[dst] = r;
+  sortedOrigin[dst] = make_int4(o[0], o[1], o[2], 0);
+  p.w = v0; // {x, y, z, v.x} in one record, {v.y, v.z} next to it
+  sortedPos[dst] = p;
+  sortedVal[2 * (size_t)dst] = v1;
+  sortedVal[2 * (size_t)dst + 1] = v2;
 }
 
-// One thread per grid node (x fastest, padded pitch): sums the particles whose support covers the node.
-// Particle cells that can reach node X in one dimension: X - S + 1 + Pmin .. X + Pmax with Pmax = S/2 and
-// Pmin = S/2 - (S even) (computeSupportShift only ever lowers P by one, and only for even supports).
-template <class T>
-__global__ void __launch_bounds__(128)
-ibmSpreadNodes(const StencilRec<T> *__restrict__ recs, const uint32_t *__restrict__ binStart, GridT<T> g, int support,
-               int nxPad, T *__restrict__ grid3) {
-  const int X = blockIdx.x * blockDim.x + threadIdx.x;
-  const int Y = blockIdx.y, Z = blockIdx.z;
-  if (X >= nxPad) return;
-  T ax = T(0), ay = T(0), az = T(0);
-  if (X < g.n[0]) {
-    const int S = support;
-    const int lo = -(S - 1) + (S / 2 - ((S & 1) ? 0 : 1)), hi = S / 2; // particle cell offsets relative to the node
-    for (int dz = lo; dz <= hi; dz++) {
-      int cz = Z + dz;
-      if (cz < 0 || cz >= g.n[2]) {
-        if (g.m[2] == T(0)) continue;
-        cz += cz < 0 ? g.n[2] : -g.n[2];
+// Brick of kBrickX x kBrickY x kBrickZ grid nodes per CTA; every THREAD owns one short x-row of kBrickX nodes
+// and keeps their 3*kBrickX accumulators in registers, so there are no atomics at all. The particles of the
+// brick's halo region (cells that can reach a node of the brick) are staged in shared memory once (origin
+// relative to the brick, 3*S precomputed weights, value); a thread then walks the particles of the (S or S+1)^2
+// region rows around its own row - contiguous in staged order for fixed z - and adds the contributions that
+// land on its nodes. The brick is written out once: no zero fill of the grid, deterministic summation order.
+// Particle cells reaching node X in one dimension: X + lo .. X + hi with hi = S/2, lo = -(S-1) + S/2 - (S even)
+// (computeSupportShift lowers P by at most one).
+constexpr int kBrickX = 4, kBrickY = 16, kBrickZ = 16, kBrickThreads = kBrickY * kBrickZ;
+template <class T, int S> struct BrickGeom {
+  static constexpr int hi = S / 2, lo = -(S - 1) + S / 2 - ((S & 1) ? 0 : 1);
+  static constexpr int W = hi - lo; // extra region cells per dimension
+  static constexpr int RX = kBrickX + W, RY = kBrickY + W, RZ = kBrickZ + W;
+  static constexpr int ncells = RX * RY * RZ, nrows = RY * RZ;
+  static constexpr int cap = 512;                 // staged particles per pass
+  static constexpr int REC = 3 * S + 3;           // weights + value per particle (T)
+  static constexpr size_t smemBytes = (size_t)cap * (REC * sizeof(T) + sizeof(int)) + (size_t)(2 * ncells + 1) * sizeof(int) + 64;
+};
+
+template <class T4, int S>
+__global__ void __launch_bounds__(kBrickThreads)
+ibmSpreadBricks(const T4 *__restrict__ sortedPos, const decltype(T4::x) *__restrict__ sortedVal,
+                const int4 *__restrict__ sortedOrigin, const decltype(T4::x) *__restrict__ sortedW,
+                const uint32_t *__restrict__ binStart, GridT<decltype(T4::x)> g, int nxPad,
+                decltype(T4::x) *__restrict__ grid3) {
+  using T = decltype(T4::x);
+  using G = BrickGeom<T, S>;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T *recs = reinterpret_cast<T *>(smemRaw);                        // [cap][REC]
+  int *org = reinterpret_cast<int *>(recs + (size_t)G::cap * G::REC); // [cap] packed origin relative to the brick
+  int *cellOff = org + G::cap;                                     // [ncells+1] staged-order prefix of region cells
+  int *cellGStart = cellOff + G::ncells + 1;                       // [ncells] first sorted slot of each region cell
+  __shared__ int warpTot[kBrickThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid % kBrickY, tz = tid / kBrickY;
+  const int bx0 = blockIdx.x * kBrickX, by0 = blockIdx.y * kBrickY, bz0 = blockIdx.z * kBrickZ;
+
+  // ---- region cell populations -> exclusive prefix (block scan); thread t owns cells [t*per, (t+1)*per) ----
+  constexpr int per = (G::ncells + kBrickThreads - 1) / kBrickThreads;
+  int cnt[per];
+  int mine = 0;
+#pragma unroll
+  for (int q = 0; q < per; q++) {
+    const int c = tid * per + q;
+    cnt[q] = 0;
+    if (c < G::ncells) {
+      int gs = 0;
+      const int rx = c % G::RX, ry = (c / G::RX) % G::RY, rz = c / (G::RX * G::RY);
+      int cx = bx0 + G::lo + rx, cy = by0 + G::lo + ry, cz = bz0 + G::lo + rz;
+      bool ok = true;
+      // unwrapped -> actual cell (periodic image) or nothing (non periodic / beyond one wrap)
+      if (cx < 0 || cx >= g.n[0]) { if (g.m[0] != T(0)) cx += cx < 0 ? g.n[0] : -g.n[0]; else ok = false; }
+      if (cy < 0 || cy >= g.n[1]) { if (g.m[1] != T(0)) cy += cy < 0 ? g.n[1] : -g.n[1]; else ok = false; }
+      if (cz < 0 || cz >= g.n[2]) { if (g.m[2] != T(0)) cz += cz < 0 ? g.n[2] : -g.n[2]; else ok = false; }
+      ok = ok && cx >= 0 && cx < g.n[0] && cy >= 0 && cy < g.n[1] && cz >= 0 && cz < g.n[2];
+      if (ok) {
+        const uint32_t cell = (uint32_t)cx + (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)cz);
+        const uint32_t s0 = __ldg(binStart + cell), s1 = __ldg(binStart + cell + 1);
+        gs = (int)s0;
+        cnt[q] = (int)(s1 - s0);
       }
-      for (int dy = lo; dy <= hi; dy++) {
-        int cy = Y + dy;
-        if (cy < 0 || cy >= g.n[1]) {
-          if (g.m[1] == T(0)) continue;
-          cy += cy < 0 ? g.n[1] : -g.n[1];
-        }
-        const uint32_t row = (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)cz);
-        // particle cells X+lo .. X+hi of this row; a periodic wrap splits the range in two segments
-        // (the host guarantees n >= support + 1 in periodic dimensions, so the segments never overlap)
-        const int a = X + lo, b = X + hi;
-        int segLo[2], segHi[2], nseg = 1;
-        if (g.m[0] == T(0)) { segLo[0] = max(a, 0); segHi[0] = min(b, g.n[0] - 1); }
-        else if (a < 0) { segLo[0] = a + g.n[0]; segHi[0] = g.n[0] - 1; segLo[1] = 0; segHi[1] = b; nseg = 2; }
-        else if (b >= g.n[0]) { segLo[0] = a; segHi[0] = g.n[0] - 1; segLo[1] = 0; segHi[1] = b - g.n[0]; nseg = 2; }
-        else { segLo[0] = a; segHi[0] = b; }
-        for (int seg = 0; seg < nseg; seg++) {
-          const int x0 = segLo[seg], x1 = segHi[seg];
-          if (x0 > x1) continue;
-          const int pb = (int)__ldg(binStart + row + x0), pe = (int)__ldg(binStart + row + x1 + 1);
-          for (int q = pb; q < pe; q++) {
-            const StencilRec<T> *r = recs + q;
-            int ix = X - r->ox, iy = Y - r->oy, iz = Z - r->oz;
-            // periodic images of the node relative to the (unwrapped) support origin
-            if (g.m[0] != T(0)) { if (ix < 0) ix += g.n[0]; else if (ix >= g.n[0]) ix -= g.n[0]; }
-            if (g.m[1] != T(0)) { if (iy < 0) iy += g.n[1]; else if (iy >= g.n[1]) iy -= g.n[1]; }
-            if (g.m[2] != T(0)) { if (iz < 0) iz += g.n[2]; else if (iz >= g.n[2]) iz -= g.n[2]; }
-            if ((unsigned)ix < (unsigned)S && (unsigned)iy < (unsigned)S && (unsigned)iz < (unsigned)S) {
-              const T wx = r->w[ix], wy = r->w[kSmallSupport + iy], wz = r->w[2 * kSmallSupport + iz];
-              ax += r->v[0] * wx * wy * wz;
-              ay += r->v[1] * wx * wy * wz;
-              az += r->v[2] * wx * wy * wz;
-            }
+      cellGStart[c] = gs;
+    }
+    mine += cnt[q];
+  }
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warpTot[warp] = inc;
+  __syncthreads();
+  int warpOff = 0, total = 0;
+#pragma unroll
+  for (int q = 0; q < kBrickThreads / 32; q++) {
+    if (q < warp) warpOff += warpTot[q];
+    total += warpTot[q];
+  }
+  int run = warpOff + inc - mine;
+#pragma unroll
+  for (int q = 0; q < per; q++) {
+    const int c = tid * per + q;
+    if (c < G::ncells) cellOff[c] = run;
+    run += cnt[q];
+  }
+  if (tid == 0) cellOff[G::ncells] = total;
+  __syncthreads();
+
+  T acc[kBrickX][3];
+#pragma unroll
+  for (int q = 0; q < kBrickX; q++) acc[q][0] = acc[q][1] = acc[q][2] = T(0);
+
+  for (int chunk0 = 0; chunk0 < total; chunk0 += G::cap) {
+    // ---- stage: one thread per staged particle; its region row by binary search, its cell by a short walk ----
+    const int nstage = min(G::cap, total - chunk0);
+    for (int slot = tid; slot < nstage; slot += kBrickThreads) {
+      const int t = chunk0 + slot;
+      int loc = 0, hic = G::ncells; // largest c with cellOff[c] <= t (cellOff[ncells] = total > t)
+      while (hic - loc > 1) {
+        const int mid = (loc + hic) >> 1;
+        if (cellOff[mid] <= t) loc = mid; else hic = mid;
+      }
+      const int c = loc;
+      const int src = cellGStart[c] + (t - cellOff[c]);
+      const int rx = c % G::RX, ry = (c / G::RX) % G::RY, rz = c / (G::RX * G::RY);
+      const int rc[3] = {rx, ry, rz};
+      const int b0[3] = {bx0, by0, bz0};
+      const int4 og = sortedOrigin[src];
+      const int oabs[3] = {og.x, og.y, og.z};
+      int packed = 0;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        // actual cell from the region coordinate; support shift P = cell - origin; origin relative to the brick
+        // from the (unwrapped) region coordinate, valid for any periodic image
+        int cell = b0[d] + G::lo + rc[d];
+        if (cell < 0) cell += g.n[d]; else if (cell >= g.n[d]) cell -= g.n[d];
+        const int rel = G::lo + rc[d] - (cell - oabs[d]);
+        packed |= ((rel + 64) & 0xff) << (8 * d);
+      }
+      org[slot] = packed;
+      const T *wsrc = sortedW + (size_t)src * (3 * S);
+#pragma unroll
+      for (int q = 0; q < 3 * S; q++) recs[q * G::cap + slot] = wsrc[q]; // field-major: lanes hit distinct banks
+      recs[(3 * S) * G::cap + slot] = sortedPos[src].w;
+      recs[(3 * S + 1) * G::cap + slot] = sortedVal[2 * (size_t)src];
+      recs[(3 * S + 2) * G::cap + slot] = sortedVal[2 * (size_t)src + 1];
+    }
+    __syncthreads();
+    // ---- my row of nodes: for each dz the region rows ty .. ty+W are contiguous in staged order ----
+    for (int dz = 0; dz <= G::W; dz++) {
+      const int r0 = ty + G::RY * (tz + dz);
+      int b = cellOff[r0 * G::RX] - chunk0, e = cellOff[(r0 + G::W + 1) * G::RX] - chunk0;
+      b = max(b, 0); e = min(e, G::cap);
+      for (int s = b; s < e; s++) {
+        const int pk = org[s];
+        const int iy = ty - (((pk >> 8) & 0xff) - 64), iz = tz - (((pk >> 16) & 0xff) - 64);
+        if ((unsigned)iy >= (unsigned)S || (unsigned)iz >= (unsigned)S) continue;
+        const T *rec = recs + s;
+        const T wyz = rec[(S + iy) * G::cap] * rec[(2 * S + iz) * G::cap];
+        const T v0 = rec[(3 * S) * G::cap], v1 = rec[(3 * S + 1) * G::cap], v2 = rec[(3 * S + 2) * G::cap];
+        const int relx = (pk & 0xff) - 64;
+#pragma unroll
+        for (int lx = 0; lx < kBrickX; lx++) {
+          const int ix = lx - relx;
+          if ((unsigned)ix < (unsigned)S) {
+            const T wgt = rec[ix * G::cap] * wyz;
+            acc[lx][0] += v0 * wgt;
+            acc[lx][1] += v1 * wgt;
+            acc[lx][2] += v2 * wgt;
           }
         }
       }
     }
+    __syncthreads();
   }
-  T *out = grid3 + 3 * ((size_t)X + (size_t)nxPad * ((size_t)Y + (size_t)g.n[1] * Z));
-  out[0] = ax; out[1] = ay; out[2] = az;
+  const int Y = by0 + ty, Z = bz0 + tz;
+  if (Y < g.n[1] && Z < g.n[2]) {
+#pragma unroll
+    for (int lx = 0; lx < kBrickX; lx++) {
+      const int X = bx0 + lx;
+      if (X < nxPad) {
+        T *out = grid3 + 3 * ((size_t)X + (size_t)nxPad * ((size_t)Y + (size_t)g.n[1] * Z));
+        const bool real = X < g.n[0];
+        out[0] = real ? acc[lx][0] : T(0);
+        out[1] = real ? acc[lx][1] : T(0);
+        out[2] = real ? acc[lx][2] : T(0);
+      }
+    }
+  }
 }
 
-// Interpolation with the sorted stencil records: one thread per particle slot, S^3 nodes.
-template <class T, bool ACCUMULATE>
+// Interpolation: one thread per particle slot (cell-sorted, so neighbouring threads read neighbouring nodes),
+// support origin and weights precomputed by ibmOrderSorted, S^3 node loads fully unrolled.
+template <class T, int S, bool ACCUMULATE>
 __global__ void __launch_bounds__(128)
-ibmGatherSorted(const StencilRec<T> *__restrict__ recs, const int *__restrict__ sortedIndex, int N, GridT<T> g,
-                int support, int nxPad, const T *__restrict__ grid3, T *__restrict__ out3) {
+ibmGatherSorted(const int4 *__restrict__ sortedOrigin, const T *__restrict__ sortedW,
+                const int *__restrict__ sortedIndex, int N, GridT<T> g, int nxPad, const T *__restrict__ grid3,
+                T *__restrict__ out3) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= N) return;
-  const StencilRec<T> r = recs[slot];
+  const int4 og = sortedOrigin[slot];
+  const int o[3] = {og.x, og.y, og.z};
+  T w[3][S];
+  int cidx[3][S];
+  const T *wsrc = sortedW + (size_t)slot * (3 * S);
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      const int cj = wrapCell(g, d, o[d] + i);
+      cidx[d][i] = (cj >= 0 && cj < g.n[d]) ? cj : -1;
+      w[d][i] = wsrc[d * S + i];
+    }
   T ax = T(0), ay = T(0), az = T(0);
-  for (int kk = 0; kk < support; kk++) {
-    const int cz = wrapCell(g, 2, r.oz + kk);
-    if (cz < 0 || cz >= g.n[2]) continue;
-    for (int jj = 0; jj < support; jj++) {
-      const int cy = wrapCell(g, 1, r.oy + jj);
-      if (cy < 0 || cy >= g.n[1]) continue;
-      for (int ii = 0; ii < support; ii++) {
-        const int cx = wrapCell(g, 0, r.ox + ii);
-        if (cx < 0 || cx >= g.n[0]) continue;
-        const T *gp = grid3 + 3 * ((size_t)cx + (size_t)nxPad * ((size_t)cy + (size_t)g.n[1] * cz));
-        const T wx = r.w[ii], wy = r.w[kSmallSupport + jj], wz = r.w[2 * kSmallSupport + kk];
+#pragma unroll
+  for (int kk = 0; kk < S; kk++)
+#pragma unroll
+    for (int jj = 0; jj < S; jj++)
+#pragma unroll
+      for (int ii = 0; ii < S; ii++) {
+        if (cidx[0][ii] < 0 || cidx[1][jj] < 0 || cidx[2][kk] < 0) continue;
+        const T *gp = grid3 + 3 * ((size_t)cidx[0][ii] + (size_t)nxPad * ((size_t)cidx[1][jj] + (size_t)g.n[1] * cidx[2][kk]));
+        const T wx = w[0][ii], wy = w[1][jj], wz = w[2][kk];
         ax += g.cellVolume * (__ldg(gp) * wx * wy * wz);
         ay += g.cellVolume * (__ldg(gp + 1) * wx * wy * wz);
         az += g.cellVolume * (__ldg(gp + 2) * wx * wy * wz);
       }
-    }
-  }
-  T *o = out3 + 3 * (size_t)sortedIndex[slot];
-  if (ACCUMULATE) { o[0] += ax; o[1] += ay; o[2] += az; }
-  else { o[0] = ax; o[1] = ay; o[2] = az; }
+  T *op = out3 + 3 * (size_t)sortedIndex[slot];
+  if (ACCUMULATE) { op[0] += ax; op[1] += ay; op[2] += az; }
+  else { op[0] = ax; op[1] = ay; op[2] = az; }
 }
 
 // ---------------- any support: one warp per particle ----------------
