@@ -12,8 +12,9 @@ launching stream with a 256 MiB L2-evicting write before every step (the working
 otherwise sit in the 126 MB L2); ms_per_step = sum(step times)/K, max over ranks. `value_back_to_back`
 reports the same K steps enqueued back to back (how an application runs them).
 
-Multi GPU (N > 1, launched by torchrun): path 1 has no multi-GPU decomposition yet -> "replicas only":
-each rank integrates its own 1e6-particle system (weak scaling), value = sum over ranks of steps/s.
+Multi GPU (N > 1, launched by torchrun): ONE 1e6-particle system over all ranks (strong scaling) by particle
+decomposition: block-owned particles, NCCL all-gather of the position blocks every step, forces only for the
+owned block (uammd_b200/multigpu.py). value = steps/s of that single system.
 """
 import argparse
 import json
@@ -194,6 +195,8 @@ def main():
     pot = LJ()
     pot.setPotParameters(0, 0, cutOff=RC, sigma=1.0, epsilon=1.0)
     box = Box(Lb)
+    if world > 1:
+        return main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box)
     md = LJMD(box, pot, DT)
     p = torch.from_numpy(pos).to(dev)
     v = torch.from_numpy(vel).to(dev)
@@ -315,6 +318,84 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
+    """N > 1: strong scaling of the single 1e6-particle system (uammd_b200.multigpu.DistributedLJMD)."""
+    import torch
+    import torch.distributed as dist
+    import uammd_b200
+    from uammd_b200.multigpu import DistributedLJMD
+    lib = uammd_b200.lib()
+    md = DistributedLJMD(box, pot, DT, N, engine="cuda")
+    lo, hi = md.dec.lo, md.dec.hi
+    p = torch.from_numpy(pos).to(dev)
+    f = torch.zeros(N, 4, device=dev)
+    vb = torch.from_numpy(vel[lo:hi].copy()).to(dev)
+    scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    md.run(p, vb, f, args.equil + args.warmup)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = lib.ub200_launch_count()
+    barrier()
+    with ClockSampler(local) as clk:
+        for a, b in evs:
+            scrub.fill_(1)
+            a.record()
+            md.run(p, vb, f, 1)
+            b.record()
+        barrier()
+    launches = lib.ub200_launch_count() - launches0
+    ms_per_step = float(np.sum([a.elapsed_time(b) for a, b in evs]) / args.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    md.run(p, vb, f, args.steps)
+    e1.record()
+    barrier()
+    ms_b2b = e0.elapsed_time(e1) / args.steps
+    # e2e: every rank round-trips ITS block (pos + vel) through pinned host memory every step
+    hp, hv = p[lo:hi].cpu().pin_memory(), vb.cpu().pin_memory()
+    n_e2e = max(10, min(args.steps, 50))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        p[lo:hi].copy_(hp, non_blocking=True); vb.copy_(hv, non_blocking=True)
+        md.prepared = False
+        md._gather(p)
+        md.run(p, vb, f, 1)
+        hp.copy_(p[lo:hi], non_blocking=True); hv.copy_(vb, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    t = torch.tensor([ms_per_step, ms_b2b, e2e_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step, ms_b2b, e2e_ms = (float(x) for x in t.cpu())
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        line = {
+            "metric": "MD steps/s @1e6 LJ particles", "value": 1000.0 / ms_per_step, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
+                       "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
+                       "parallelism": f"particle decomposition over {world} GPUs: block-owned particles, NCCL all-gather of positions "
+                                      f"({N * 16} B) every step, forces for the owned block only"},
+            "value_back_to_back": 1000.0 / ms_b2b, "clocks": clk.summary(),
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": (hi - lo) * 28 * world,
+                    "d2h_bytes_per_step": (hi - lo) * 28 * world,
+                    "what": "each rank uploads its pinned pos+vel block, positions are all-gathered, forces recomputed, 1 step, block downloaded"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9 / world / peak, "traffic": None,
+                         "note": "whole-step pipeline bytes per GPU (216 B/particle/step over all ranks); see the N=1 line for the pair kernel"},
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
     return 0
 
 

@@ -93,6 +93,12 @@ int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int ntypes, void *
 int ub200_lj_sum_devparams_f32(ub200_celllist *cl, const void *d_params, int ntypes, void *d_force, float *d_energy,
                                float *d_virial, const int *d_globalIdx, void *stream);
 
+/* Multi-GPU particle decomposition: forces only for the home particles whose (group) index lies in
+ * [ownerLo, ownerHi); every rank holds all positions and the full cell list (the reference is single-GPU: new
+ * functionality). accumulate = 0 writes (x,y,z,0), 1 adds. */
+int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, int ownerLo,
+                           int ownerHi, int accumulate, void *stream);
+
 /* DPD transverser (Potential/DPD.cuh:92-159). d_vel: real3[*] indexed by GLOBAL index like getInfo(pi).
  * sigma = sqrt(2 T)/sqrt(dt) as DPD_impl computes it (:66,:84-92); seed/step are the Saru seeds (:129).
  * idStride = N used in ij = min + N*max (int32 arithmetic, wraps like the reference). */
@@ -107,6 +113,10 @@ int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A, float gamm
 int ub200_nve_half_step_f32(void *d_pos, void *d_vel, const void *d_force, const float *d_mass,
                             float defaultMass, const int *d_groupIdx, int N, float dt, int is2D, int step,
                             void *stream);
+
+/* second kick of step n fused with kick + drift of step n+1 (unit mass, all particles [0,N)): same roundings as
+ * ub200_nve_half_step_f32(step=2) followed by (step=1) */
+int ub200_nve_kick_kick_drift_f32(void *d_pos, void *d_vel, const void *d_force, int N, float dt, void *stream);
 
 /* Fused engine for a whole VerletNVE::forwardTime with one PairForces<LJ,CellList> interactor
  * (Integrator/VerletNVE.cu:174-188): kick+drift, cell list rebuild, LJ forces (written, not accumulated),

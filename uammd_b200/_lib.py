@@ -51,7 +51,9 @@ def _declare(lib):
         "ub200_celllist_error_flag": (i, [vp, vp, C.POINTER(i)]),
         "ub200_lj_sum_f32": (i, [vp, fp, i, vp, vp, vp, vp, vp]),
         "ub200_lj_sum_devparams_f32": (i, [vp, vp, i, vp, vp, vp, vp, vp]),
+        "ub200_lj_sum_owned_f32": (i, [vp, fp, i, vp, i, i, i, vp]),
         "ub200_nve_half_step_f32": (i, [vp, vp, vp, vp, f, vp, i, f, i, i, vp]),
+        "ub200_nve_kick_kick_drift_f32": (i, [vp, vp, vp, i, f, vp]),
         "ub200_md_create": (i, [C.POINTER(vp)]),
         "ub200_md_destroy": (i, [vp]),
         "ub200_md_celllist": (vp, [vp]),

@@ -5,7 +5,7 @@
 namespace ub200 {
 
 int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
-          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st);
+          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st, int ownerLo, int ownerHi);
 
 // v += (F/m) dt/2 ; step 1 also x += v dt. Same operation order as the reference (force/m is (1/m)*force,
 // utils/vector.cuh:191-193; the trailing multiply-adds are contracted by nvcc there, spelled out here).
@@ -84,6 +84,14 @@ int ub200_nve_half_step_f32(void *d_pos, void *d_vel, const void *d_force, const
   return UB200_OK;
 }
 
+int ub200_nve_kick_kick_drift_f32(void *d_pos, void *d_vel, const void *d_force, int N, float dt, void *stream) {
+  if (!d_pos || !d_vel || !d_force || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  nveKickKickDrift<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float4 *)d_pos, (float *)d_vel,
+                                                                    (const float4 *)d_force, N, dt);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
 int ub200_md_create(ub200_md **out) {
   if (!out) return UB200_ERR_INVALID_ARGUMENT;
   ub200_md *md = new (std::nothrow) ub200_md();
@@ -112,7 +120,7 @@ static int mdForces(ub200_md *md, void *d_pos, void *d_force, int N, const float
   if (e) return e;
   if ((e = ub200_celllist_build_f32(md->cl, d_pos, nullptr, N, L, periodic, cellDim, st))) return e;
   // sole interactor: forces are written, not accumulated (replaces resetForces + sum)
-  return ljSum(md->cl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, false, &md->ljTable, st);
+  return ljSum(md->cl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, false, &md->ljTable, st, 0, 0x7fffffff);
 }
 
 int ub200_md_lj_nve_prepare_f32(ub200_md *md, void *d_pos, void *d_force, int N, const float L[3], float rc,

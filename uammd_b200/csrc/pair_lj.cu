@@ -79,12 +79,15 @@ constexpr int kWarpCap = 416; // staged candidates per warp (6.5 KB, 8 CTAs/SM);
 // Radial::Transverser::compute (box.apply_pbc(rj-ri)); needed when a periodic dimension has fewer than 4 cells
 // (a collapsed dimension still wraps). Otherwise the cell image shift staged with the candidates is the
 // minimum image.
+// ownerLo/ownerHi: only home particles whose group index lies in [ownerLo, ownerHi) are computed and written
+// (multi-GPU particle decomposition: every rank holds all positions and the full list, and computes its block).
 template <bool ENERGY, bool VIRIAL, bool MULTITYPE, bool PAIRMIC, bool ACCUMULATE>
 __global__ void __launch_bounds__(kPairThreads, 8)
 ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
                 const uint32_t *__restrict__ binStart, GridF g, int ncells,
                 const LJPar *__restrict__ parTable, int ntypes, float4 *__restrict__ force,
-                float *__restrict__ energy, float *__restrict__ virial, const int *__restrict__ globalIdx) {
+                float *__restrict__ energy, float *__restrict__ virial, const int *__restrict__ globalIdx,
+                int ownerLo, int ownerHi) {
   __shared__ float4 candAll[kPairWarps][kWarpCap];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 *cand = candAll[warp];
@@ -97,6 +100,14 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
     const int hStart = __shfl_sync(0xffffffffu, nc.start, nc.centre);
     const int hCount = __shfl_sync(0xffffffffu, nc.count, nc.centre);
     if (hCount == 0) continue; // warp uniform
+    if (ownerLo > 0 || ownerHi < 0x7fffffff) { // any owned home particle in this cell?
+      bool mineAny = false;
+      for (int h = lane; h < hCount; h += 32) {
+        const int gi = groupIndex[hStart + h];
+        mineAny |= (gi >= ownerLo && gi < ownerHi);
+      }
+      if (!__any_sync(0xffffffffu, mineAny)) continue;
+    }
     const int hOff = __shfl_sync(0xffffffffu, nc.off, nc.centre);
     const bool staged = nc.total <= kWarpCap;
     const float3 hc = cellCentre(g, cx, cy, cz);
@@ -120,6 +131,9 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
     __syncwarp();
     for (int h = 0; h < hCount; h += 2) {
       const bool two = h + 1 < hCount;
+      const int gi0 = groupIndex[hStart + h], gi1 = groupIndex[hStart + h + (two ? 1 : 0)];
+      const bool own0 = gi0 >= ownerLo && gi0 < ownerHi, own1 = two && gi1 >= ownerLo && gi1 < ownerHi;
+      if (!own0 && !own1) continue;
       float4 pi0, pi1;
       if (staged) {
         pi0 = cand[hOff + h];
@@ -185,8 +199,8 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
         }
       }
       reducePair(a0, a1, lane, ENERGY || VIRIAL);
-      if ((lane == 0) || (lane == 16 && two)) {
-        const int gi = groupIndex[hStart + h + (lane >> 4)];
+      if ((lane == 0 && own0) || (lane == 16 && own1)) {
+        const int gi = lane ? gi1 : gi0;
         const int ori = globalIdx ? globalIdx[gi] : gi;
         if (force) {
           if (ACCUMULATE) {
@@ -206,7 +220,7 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
 
 template <bool E, bool V, bool M, bool P, bool A>
 static int launchLJ(ub200_celllist *cl, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
-                    const int *globalIdx, cudaStream_t st) {
+                    const int *globalIdx, cudaStream_t st, int ownerLo, int ownerHi) {
   auto kern = ljCellTraversal<E, V, M, P, A>;
   static int blocksPerSM = 0; // per instantiation
   if (!blocksPerSM) {
@@ -217,14 +231,15 @@ static int launchLJ(ub200_celllist *cl, const LJPar *table, int ntypes, float4 *
   const int needed = (cl->ncells + kPairWarps - 1) / kPairWarps;
   if (grid > needed) grid = needed;
   kern<<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(), cl->binStart.as<uint32_t>(),
-                                      cl->grid, cl->ncells, table, ntypes, force, energy, virial, globalIdx);
+                                      cl->grid, cl->ncells, table, ntypes, force, energy, virial, globalIdx, ownerLo,
+                                      ownerHi);
   UB200_LAUNCHED();
   return UB200_OK;
 }
 
 // d_table: device table [ntypes*ntypes] of LJPar
 int ljSumDev(ub200_celllist *cl, const LJPar *d_table, int ntypes, float4 *force, float *energy, float *virial,
-             const int *globalIdx, bool accumulate, cudaStream_t st) {
+             const int *globalIdx, bool accumulate, cudaStream_t st, int ownerLo = 0, int ownerHi = 0x7fffffff) {
   if (!cl || !d_table || ntypes < 1) return UB200_ERR_INVALID_ARGUMENT;
   if (!cl->built) return UB200_ERR_NOT_BUILT;
   if (!force && !energy && !virial) return UB200_OK;
@@ -234,7 +249,7 @@ int ljSumDev(ub200_celllist *cl, const LJPar *d_table, int ntypes, float4 *force
   const bool E = energy != nullptr, V = virial != nullptr, M = ntypes > 1;
 #define UB200_LJ_DISPATCH(e, v, m, p, a)                                                                     \
   if (E == e && V == v && M == m && pairMic == p && accumulate == a)                                         \
-    return launchLJ<e, v, m, p, a>(cl, d_table, ntypes, force, energy, virial, globalIdx, st);
+    return launchLJ<e, v, m, p, a>(cl, d_table, ntypes, force, energy, virial, globalIdx, st, ownerLo, ownerHi);
   UB200_LJ_DISPATCH(false, false, false, false, true)
   UB200_LJ_DISPATCH(false, false, false, false, false)
   UB200_LJ_DISPATCH(false, false, false, true, true)
@@ -246,9 +261,9 @@ int ljSumDev(ub200_celllist *cl, const LJPar *d_table, int ntypes, float4 *force
 #undef UB200_LJ_DISPATCH
 #define UB200_LJ_DISPATCH_EV(m, p)                                                                           \
   if (M == m && pairMic == p) {                                                                              \
-    if (E && V) return launchLJ<true, true, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st); \
-    if (E) return launchLJ<true, false, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st);     \
-    return launchLJ<false, true, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st);      \
+    if (E && V) return launchLJ<true, true, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st, ownerLo, ownerHi); \
+    if (E) return launchLJ<true, false, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st, ownerLo, ownerHi);     \
+    return launchLJ<false, true, m, p, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st, ownerLo, ownerHi);      \
   }
   UB200_LJ_DISPATCH_EV(false, false)
   UB200_LJ_DISPATCH_EV(false, true)
@@ -260,7 +275,7 @@ int ljSumDev(ub200_celllist *cl, const LJPar *d_table, int ntypes, float4 *force
 
 // host parameter table: uploaded into `cache` only when it changed since the last call
 int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
-          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st) {
+          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st, int ownerLo, int ownerHi) {
   if (!params || ntypes < 1 || !cache) return UB200_ERR_INVALID_ARGUMENT;
   const size_t n = (size_t)ntypes * ntypes * 4;
   if (cache->host.size() != n || memcmp(cache->host.data(), params, n * sizeof(float)) != 0) {
@@ -269,7 +284,7 @@ int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, fl
     cache->host.assign(params, params + n);
     UB200_CUDA(cudaMemcpyAsync(cache->dev.p, cache->host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
   }
-  return ljSumDev(cl, cache->dev.as<LJPar>(), ntypes, force, energy, virial, globalIdx, accumulate, st);
+  return ljSumDev(cl, cache->dev.as<LJPar>(), ntypes, force, energy, virial, globalIdx, accumulate, st, ownerLo, ownerHi);
 }
 
 } // namespace ub200
@@ -281,7 +296,14 @@ static LJTableCache g_ljTable; // parameter table of the stateless ub200_lj_sum_
 extern "C" int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, float *d_energy,
                                 float *d_virial, const int *d_globalIdx, void *stream) {
   return ljSum(cl, params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true, &g_ljTable,
-               (cudaStream_t)stream);
+               (cudaStream_t)stream, 0, 0x7fffffff);
+}
+
+extern "C" int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, int ownerLo,
+                                      int ownerHi, int accumulate, void *stream) {
+  if (ownerLo < 0 || ownerHi < ownerLo) return UB200_ERR_INVALID_ARGUMENT;
+  return ljSum(cl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, accumulate != 0, &g_ljTable,
+               (cudaStream_t)stream, ownerLo, ownerHi);
 }
 
 extern "C" int ub200_lj_sum_devparams_f32(ub200_celllist *cl, const void *d_params, int ntypes, void *d_force,
