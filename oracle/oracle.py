@@ -144,6 +144,16 @@ class LJScale:
     def force_tol(self, L, rc):
         return _sep_uncertainty(L, rc) * self.sens + 2e-6 * self.abssum + 1.01 * self.edge + 1e-30
 
+    def energy_tol(self, L, rc, escale):
+        """|dE_i| <= 1/2 sum_j |dE_ij/dr| dsep = dsep/2 * abssum; a pair inside the cut-off band adds or drops
+        |e(rc)|/2 ~ 0.21 |f(rc)|; summation roundings relative to the largest per-particle energy."""
+        return 0.5 * _sep_uncertainty(L, rc) * self.abssum + 0.25 * self.edge + 4e-6 * escale + 1e-30
+
+    def virial_tol(self, L, rc, vscale):
+        """V_ij = f_ij . r_ij: |dV| <= rc |df| + |f| dsep."""
+        return rc * (_sep_uncertainty(L, rc) * self.sens + 1.01 * self.edge) + _sep_uncertainty(L, rc) * self.abssum \
+            + 4e-6 * vscale + 1e-30
+
     def __array__(self, dtype=None, copy=None):
         return np.asarray(self.abssum, dtype=dtype)
 
