@@ -190,6 +190,19 @@ int ub200_fcm_grid_info(ub200_fcm *fcm, int cells[3], int *nxPad, void **d_grid)
 int ub200_bdhi_euler_update(int precisionBytes, void *d_pos, const int *d_groupIdx, const void *d_MF, const void *d_BdW,
                             const double *K9, int N, double sqrt2Tdt, double dt, int is2D, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * BASELINE config 0: BD::EulerMaruyama (ideal or with interactor forces). Replaces EulerMaruyama_ns::integrateGPU
+ * (Integrator/BrownianDynamics.cu:117-145, launched by EulerMaruyama::updatePositions :158-173):
+ *   M = selfMobility * (radius ? 1/radius[i] : 1);  R += dt (K R + M F);  R += (gf(0,B).x, gf(0,B).y, gf'(0,B).x),
+ *   B = sqrt(2 T M dt), gf from Saru(i, stepNum, seed) with i the particle (global) index.
+ * d_force: real4[*] or NULL (ideal particles); K9: host row-major shear matrix or NULL; d_radius: real[*] or NULL.
+ * The caller increments stepNum before every call like EulerMaruyama::forwardTime does (:148-155); seed is the
+ * integrator's Saru seed (BaseBrownianIntegrator ctor :14-16). Results are bit-identical to the reference's.
+ * ------------------------------------------------------------------------------------------------ */
+int ub200_bd_euler_maruyama_step(int precisionBytes, void *d_pos, const int *d_groupIdx, const void *d_force,
+                                 const double *K9, double selfMobility, const void *d_radius, double dt, int is2D,
+                                 double temperature, int N, uint32_t stepNum, uint32_t seed, void *stream);
+
 /* number of kernel launches the library enqueued since process start (bench.py's gpu_launches) */
 unsigned long long ub200_launch_count(void);
 

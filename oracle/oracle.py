@@ -310,3 +310,11 @@ def fcm_mdot(L, cells, kern, viscosity, pos4, force3, temperature=0.0, prefactor
     vel = np.zeros((nz, ny, nxPad, 3))
     vel[:, :, :nx, :] = np.fft.irfftn(ghat, s=(nz, ny, nx), axes=(0, 1, 2)) * (nx * ny * nz)
     return ibm_gather(g, kern, pos4, vel, nxPad)
+
+
+def bd_euler_maruyama_f64(pos4, force4, selfMobility, dt, temperature, step, seed, K9=None, radius=None, is2D=False):
+    """In place BD::EulerMaruyama update (BrownianDynamics.cu:117-145), fp64."""
+    assert pos4.dtype == np.float64 and pos4.flags.c_contiguous
+    k = np.ascontiguousarray(K9, np.float64) if K9 is not None else None
+    lib().orc_bd_euler_maruyama_f64(_p(pos4), _p(force4), _p(k), C.c_double(selfMobility), _p(radius), C.c_double(dt),
+                                    int(is2D), C.c_double(temperature), pos4.shape[0], C.c_uint32(step), C.c_uint32(seed))

@@ -406,3 +406,36 @@ int orc_md_step_f32(const float L[3], float rc, const float *params4, float dt, 
   orc_nve_half_f32(pos4, vel3, force4, N, dt, 1.0f, 2);
   return 0;
 }
+
+/* ---------- BD::EulerMaruyama (BASELINE config 0) ---------- */
+/* EulerMaruyama_ns::integrateGPU Integrator/BrownianDynamics.cu:117-145, double precision build:
+ * M = selfMobility (/radius[i]); R += dt (K R + M F); Saru(i, step, seed): B = sqrt(2 T M dt),
+ * dW = (gf(0,B).x, gf(0,B).y, gf'(0,B).x) with gf the FLOAT Box-Muller (saruprng.cuh:115-128). fma() spells out
+ * the contractions nvcc applies to the reference kernel. The host libm logf/sinf/cosf differ from the device's in
+ * the last ulp, so against the GPU this oracle agrees to ~1e-6 of the noise amplitude; bit parity is pinned by the
+ * compiled reference (oracle/_ref/ref_bd). */
+void orc_bd_euler_maruyama_f64(double *pos4, const double *force4, const double *K9, double selfMobility,
+                               const double *radius, double dt, int is2D, double temperature, int N, uint32_t step,
+                               uint32_t seed) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < N; i++) {
+    double R[3] = {pos4[4 * (size_t)i], pos4[4 * (size_t)i + 1], pos4[4 * (size_t)i + 2]};
+    double F[3] = {0, 0, 0}, KR[3] = {0, 0, 0};
+    if (force4) for (int d = 0; d < 3; d++) F[d] = force4[4 * (size_t)i + d];
+    if (K9) for (int d = 0; d < 3; d++) KR[d] = fma(K9[3 * d + 2], R[2], fma(K9[3 * d + 1], R[1], K9[3 * d] * R[0]));
+    const double M = selfMobility * (radius ? 1.0 / radius[i] : 1.0);
+    double out[3];
+    for (int d = 0; d < 3; d++) out[d] = fma(dt, fma(M, F[d], KR[d]), R[d]);
+    if (temperature > 0) {
+      orc_saru r = orc_saru_seed3((uint32_t)i, step, seed);
+      const float B = (float)sqrt(2.0 * temperature * M * dt);
+      float g0[2], g1[2];
+      orc_saru_gf(&r, 0.0f, B, g0);
+      orc_saru_gf(&r, 0.0f, B, g1);
+      out[0] += (double)g0[0]; out[1] += (double)g0[1]; out[2] += (double)g1[0];
+    }
+    pos4[4 * (size_t)i] = out[0];
+    pos4[4 * (size_t)i + 1] = out[1];
+    if (!is2D) pos4[4 * (size_t)i + 2] = out[2];
+  }
+}

@@ -133,6 +133,94 @@ __device__ __forceinline__ void stockhamStage(const typename Vec2<T>::type *__re
   }
 }
 
+// ---- compile-time specialised stages (power-of-two axes) ----
+// Same Stockham indexing as stockhamStage, but N, the radix and Ns are template constants: every division is a
+// shift/mask, the butterflies are fully unrolled, and an odd log2(N) is absorbed by ONE leading radix-8 stage
+// (Ns = 1, so it needs no twiddles): 128 = 8*4*4 is three trips through shared memory instead of four.
+template <int DIR, class C> __device__ __forceinline__ void radix4(C &v0, C &v1, C &v2, C &v3) {
+  const C s02 = cadd(v0, v2), d02 = csub(v0, v2), s13 = cadd(v1, v3), d13 = mulI<DIR>(csub(v1, v3));
+  v0 = cadd(s02, s13); v1 = cadd(d02, d13); v2 = csub(s02, s13); v3 = csub(d02, d13);
+}
+// multiply by exp(DIR * i * pi / 4) and exp(DIR * 3 i pi / 4)
+template <int DIR, class T, class C> __device__ __forceinline__ C mulW8(C a) {
+  const T h = T(0.70710678118654752440084436210485);
+  return DIR < 0 ? mk2<T>(h * (a.x + a.y), h * (a.y - a.x)) : mk2<T>(h * (a.x - a.y), h * (a.x + a.y));
+}
+template <int DIR, class T, class C> __device__ __forceinline__ C mulW8c(C a) {
+  const T h = T(0.70710678118654752440084436210485);
+  return DIR < 0 ? mk2<T>(h * (a.y - a.x), -h * (a.x + a.y)) : mk2<T>(-h * (a.x + a.y), h * (a.x - a.y));
+}
+
+constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
+constexpr bool fftFixedSupported(int n) { return n >= 8 && n <= 2048 && (n & (n - 1)) == 0; }
+
+template <class T, int DIR, int N, int R, int Ns>
+__device__ __forceinline__ void stockhamStageFixed(const typename Vec2<T>::type *__restrict__ a,
+                                                   typename Vec2<T>::type *__restrict__ b, int fstride, int nf,
+                                                   const typename Vec2<T>::type *__restrict__ tw) {
+  using C = typename Vec2<T>::type;
+  constexpr int nb = N / R, lnb = ilog2c(nb);
+  constexpr int twStep = N / (Ns * R);
+  auto twid = [&](int idx) {
+    C t = __ldg(tw + idx);
+    if (DIR > 0) t.y = -t.y;
+    return t;
+  };
+  // work item w -> (transform f FASTEST, butterfly j): consecutive lanes touch consecutive transforms, i.e. shared
+  // memory addresses fstride (odd) complex numbers apart -> distinct banks. With j fastest the Ns = 1 stage would
+  // write R elements apart (8 * 16 B = every lane of a quarter warp in the same bank: measured 47 % replays).
+  const int total = nf << lnb;
+  const float invNf = 1.0f / (float)nf;
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    const int j = __float2int_rz(((float)w + 0.5f) * invNf), f = w - j * nf;
+    const int k = j & (Ns - 1);
+    const C *src = a + f * fstride + j;
+    C *dst = b + f * fstride + (j - k) * R + k;
+    if (R == 4) {
+      C v0 = src[0], v1 = src[nb], v2 = src[2 * nb], v3 = src[3 * nb];
+      if (Ns > 1) {
+        const int t1 = k * twStep;
+        v1 = cmul(v1, twid(t1)); v2 = cmul(v2, twid(2 * t1)); v3 = cmul(v3, twid(3 * t1));
+      }
+      radix4<DIR>(v0, v1, v2, v3);
+      dst[0] = v0; dst[Ns] = v1; dst[2 * Ns] = v2; dst[3 * Ns] = v3;
+    } else if (R == 8) {
+      C v0 = src[0], v1 = src[nb], v2 = src[2 * nb], v3 = src[3 * nb];
+      C v4 = src[4 * nb], v5 = src[5 * nb], v6 = src[6 * nb], v7 = src[7 * nb];
+      if (Ns > 1) {
+        const int t1 = k * twStep;
+        v1 = cmul(v1, twid(t1)); v2 = cmul(v2, twid(2 * t1)); v3 = cmul(v3, twid(3 * t1)); v4 = cmul(v4, twid(4 * t1));
+        v5 = cmul(v5, twid(5 * t1)); v6 = cmul(v6, twid(6 * t1)); v7 = cmul(v7, twid(7 * t1));
+      }
+      radix4<DIR>(v0, v2, v4, v6); // even half: E0..E3 in v0, v2, v4, v6
+      radix4<DIR>(v1, v3, v5, v7); // odd half:  O0..O3 in v1, v3, v5, v7
+      const C o1 = mulW8<DIR, T>(v3), o2 = mulI<DIR>(v5), o3 = mulW8c<DIR, T>(v7);
+      dst[0] = cadd(v0, v1); dst[4 * Ns] = csub(v0, v1);
+      dst[Ns] = cadd(v2, o1); dst[5 * Ns] = csub(v2, o1);
+      dst[2 * Ns] = cadd(v4, o2); dst[6 * Ns] = csub(v4, o2);
+      dst[3 * Ns] = cadd(v6, o3); dst[7 * Ns] = csub(v6, o3);
+    } else { // R == 2
+      C v0 = src[0], v1 = src[nb];
+      if (Ns > 1) v1 = cmul(v1, twid(k * twStep));
+      dst[0] = cadd(v0, v1); dst[Ns] = csub(v0, v1);
+    }
+  }
+}
+
+template <class T, int DIR, int N, int Ns>
+__device__ __forceinline__ typename Vec2<T>::type *fftFixedFrom(typename Vec2<T>::type *a, typename Vec2<T>::type *b,
+                                                                int fstride, int nf,
+                                                                const typename Vec2<T>::type *__restrict__ tw) {
+  if constexpr (Ns >= N) {
+    return a;
+  } else {
+    constexpr int R = (Ns == 1 && (ilog2c(N) & 1)) ? 8 : 4;
+    stockhamStageFixed<T, DIR, N, R, Ns>(a, b, fstride, nf, tw);
+    __syncthreads();
+    return fftFixedFrom<T, DIR, N, Ns * R>(b, a, fstride, nf, tw);
+  }
+}
+
 // All stages of `nf` transforms; data starts in buf0, returns the buffer that holds the result.
 // Block-wide barriers inside: every thread of the CTA must call it.
 template <class T, int DIR>
@@ -151,6 +239,15 @@ __device__ __forceinline__ typename Vec2<T>::type *fftInShared(typename Vec2<T>:
     C *t = a; a = b; b = t;
   }
   return a;
+}
+
+// NFIX > 0: axis length known at compile time (power of two) -> specialised stages; 0 -> generic
+template <class T, int DIR, int NFIX>
+__device__ __forceinline__ typename Vec2<T>::type *fftShared(typename Vec2<T>::type *buf0, typename Vec2<T>::type *buf1,
+                                                             const FftAxis &ax, int fstride, int nf,
+                                                             const typename Vec2<T>::type *__restrict__ tw) {
+  if constexpr (NFIX > 0) return fftFixedFrom<T, DIR, NFIX, 1>(buf0, buf1, fstride, nf, tw);
+  else return fftInShared<T, DIR>(buf0, buf1, ax, fstride, nf, tw);
 }
 
 } // namespace ub200

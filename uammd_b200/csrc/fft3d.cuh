@@ -63,11 +63,12 @@ private:
 };
 
 // ---------------- X pass: real <-> complex along the contiguous axis, in place ----------------
-template <class T, bool FORWARD>
+template <class T, bool FORWARD, int NFIX>
 __global__ void __launch_bounds__(kFftThreads)
-fftPassX(T *__restrict__ grid, int nx, int nkx, int nlines, int linesPerCta, FftAxis ax,
+fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int linesPerCta, FftAxis ax,
          const typename Vec2<T>::type *__restrict__ tw) {
   using C = typename Vec2<T>::type;
+  const int nx = NFIX > 0 ? NFIX : nxRuntime, nkx = NFIX > 0 ? NFIX / 2 + 1 : nkxRuntime;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int fstride = nx + 1;
   const int pairs = linesPerCta / 2;
@@ -89,7 +90,7 @@ fftPassX(T *__restrict__ grid, int nx, int nkx, int nlines, int linesPerCta, Fft
         dst[l & 1] = v;
       }
     __syncthreads();
-    C *res = fftInShared<T, -1>(buf0, buf1, ax, fstride, nf, tw);
+    C *res = fftShared<T, -1, NFIX>(buf0, buf1, ax, fstride, nf, tw);
     // untangle the two real transforms and store the Hermitian halves
     for (int p = 0; p < pairs; p++)
     for (int rem = threadIdx.x; rem < nkx * 3; rem += blockDim.x) {
@@ -116,7 +117,7 @@ fftPassX(T *__restrict__ grid, int nx, int nkx, int nlines, int linesPerCta, Fft
       buf0[(p * 3 + c) * fstride + k] = mk2<T>(A.x - B.y, A.y + B.x);
     }
     __syncthreads();
-    C *res = fftInShared<T, +1>(buf0, buf1, ax, fstride, nf, tw);
+    C *res = fftShared<T, +1, NFIX>(buf0, buf1, ax, fstride, nf, tw);
     for (int l = 0; l < nl; l++)
       for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
         const int x = rem / 3, c = rem - 3 * x;
@@ -147,11 +148,12 @@ template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("c
 // Persistent CTAs walk the tiles; three shared buffers rotate as {current, ping-pong scratch, prefetch}: the
 // cp.async loads of the NEXT tile are in flight while the current tile is transformed and stored, so HBM/L2
 // latency is hidden even at 3 CTAs per SM.
-template <class T, int MODE, bool AXIS_IS_Z, class Op>
+template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX>
 __global__ void __launch_bounds__(kFftThreads)
-fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int n, int nkx, int nOther, int tile, size_t elemStride,
+fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int nRuntime, int nkx, int nOther, int tile, size_t elemStride,
                size_t otherStride, FftAxis ax, const typename Vec2<T>::type *__restrict__ tw, Op op) {
   using C = typename Vec2<T>::type;
+  const int n = NFIX > 0 ? NFIX : nRuntime;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int fstride = n + 1;
   const int ntx = (nkx + tile - 1) / tile;
@@ -189,8 +191,8 @@ fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int n, int nkx, int nO
     const int w = min(tile, nkx - kx0) * 3;
     C *base = grid + ((size_t)other * otherStride + kx0) * 3;
     C *res;
-    if (MODE <= 0) res = fftInShared<T, -1>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
-    else res = fftInShared<T, +1>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
+    if (MODE <= 0) res = fftShared<T, -1, NFIX>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
+    else res = fftShared<T, +1, NFIX>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
     if (MODE == 0) {
       // spectral operator on the three components of every Fourier node of the tile
       for (int idx = threadIdx.x; idx < n * tile; idx += blockDim.x) {
@@ -205,7 +207,7 @@ fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int n, int nkx, int nO
       }
       __syncthreads();
       C *other1 = res == bufs(cur) ? bufs(scratch) : bufs(cur);
-      res = fftInShared<T, +1>(res, other1, ax, fstride, nf, tw);
+      res = fftShared<T, +1, NFIX>(res, other1, ax, fstride, nf, tw);
     }
     if (gf < w)
       for (int i = gi; i < n; i += gstep) base[(size_t)i * elemStride * 3 + gf] = res[gf * fstride + i];
@@ -220,59 +222,88 @@ template <class T> int fftEnsureSmem(const void *kern, size_t bytes) {
   return UB200_OK;
 }
 
-// one CTA wave that fills the GPU (occupancy is a property of (kernel, smem); cached per kernel pointer)
-inline int persistentGrid(const void *kern, size_t smem, int ntiles) {
-  static const void *cachedKern[16];
-  static size_t cachedSmem[16];
-  static int cachedBlocks[16];
+// one CTA wave that fills the GPU (occupancy is a property of (kernel, smem, threads); cached per kernel pointer)
+inline int persistentGrid(const void *kern, size_t smem, int ntiles, int threads) {
+  static const void *cachedKern[64];
+  static size_t cachedSmem[64];
+  static int cachedBlocks[64];
   static int ncached = 0;
   int perSM = 0;
   for (int i = 0; i < ncached; i++)
     if (cachedKern[i] == kern && cachedSmem[i] == smem) perSM = cachedBlocks[i];
   if (!perSM) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kFftThreads, smem) != cudaSuccess || perSM < 1) perSM = 1;
-    if (ncached < 16) { cachedKern[ncached] = kern; cachedSmem[ncached] = smem; cachedBlocks[ncached++] = perSM; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem) != cudaSuccess || perSM < 1) perSM = 1;
+    if (ncached < 64) { cachedKern[ncached] = kern; cachedSmem[ncached] = smem; cachedBlocks[ncached++] = perSM; }
   }
   const int g = kNumSMs * perSM;
   return g < ntiles ? g : ntiles;
 }
 
-template <class T, bool FORWARD> int launchPassX(const Fft3dPlan<T> &p, void *grid, cudaStream_t st) {
-  auto kern = fftPassX<T, FORWARD>;
+// CTA size: the specialised stages split 12 transforms * n/R butterflies evenly over 192 threads
+template <int NFIX> constexpr int fftThreads() { return NFIX > 0 ? 192 : kFftThreads; }
+
+// axis lengths with compile-time specialised kernels (anything else takes the generic mixed-radix path)
+#define UB200_FFT_DISPATCH(n, CALL)                                                                         \
+  switch (n) {                                                                                              \
+  case 32: { constexpr int NFIX = 32; CALL; } break;                                                        \
+  case 64: { constexpr int NFIX = 64; CALL; } break;                                                        \
+  case 128: { constexpr int NFIX = 128; CALL; } break;                                                      \
+  case 256: { constexpr int NFIX = 256; CALL; } break;                                                      \
+  case 512: { constexpr int NFIX = 512; CALL; } break;                                                      \
+  default: { constexpr int NFIX = 0; CALL; } break;                                                         \
+  }
+
+template <class T, bool FORWARD, int NFIX> int launchPassXFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st) {
+  auto kern = fftPassX<T, FORWARD, NFIX>;
   int rc = fftEnsureSmem<T>((const void *)kern, p.smemX);
   if (rc) return rc;
   const int nlines = p.ny * p.nz;
   const int nb = (nlines + p.linesPerCta - 1) / p.linesPerCta;
-  kern<<<nb, kFftThreads, p.smemX, st>>>((T *)grid, p.nx, p.nkx, nlines, p.linesPerCta, p.ax,
-                                         p.twx.template as<typename Vec2<T>::type>());
+  kern<<<nb, fftThreads<NFIX>(), p.smemX, st>>>((T *)grid, p.nx, p.nkx, nlines, p.linesPerCta, p.ax,
+                                                p.twx.template as<typename Vec2<T>::type>());
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+template <class T, bool FORWARD> int launchPassX(const Fft3dPlan<T> &p, void *grid, cudaStream_t st) {
+  int rc = UB200_OK;
+  UB200_FFT_DISPATCH(p.nx, (rc = launchPassXFixed<T, FORWARD, NFIX>(p, grid, st)));
+  return rc;
+}
+
+template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX>
+int launchPassStridedFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op) {
+  using C = typename Vec2<T>::type;
+  auto kern = fftPassStrided<T, MODE, AXIS_IS_Z, Op, NFIX>;
+  const size_t smem = AXIS_IS_Z ? p.smemZ : p.smemY;
+  int rc = fftEnsureSmem<T>((const void *)kern, smem);
+  if (rc) return rc;
+  const int tile = AXIS_IS_Z ? p.tileZ : p.tileY;
+  const int ntx = (p.nkx + tile - 1) / tile;
+  const int nOther = AXIS_IS_Z ? p.ny : p.nz;
+  const int threads = fftThreads<NFIX>();
+  const int nblocks = persistentGrid((const void *)kern, smem, ntx * nOther, threads);
+  if (AXIS_IS_Z)
+    kern<<<nblocks, threads, smem, st>>>((C *)grid, p.nz, p.nkx, p.ny, tile, (size_t)p.nkx * p.ny, (size_t)p.nkx, p.az,
+                                         p.twz.template as<C>(), op);
+  else
+    kern<<<nblocks, threads, smem, st>>>((C *)grid, p.ny, p.nkx, p.nz, tile, (size_t)p.nkx, (size_t)p.nkx * p.ny, p.ay,
+                                         p.twy.template as<C>(), op);
   UB200_LAUNCHED();
   return UB200_OK;
 }
 
 template <class T, int MODE, class Op = NoSpectralOp>
 int launchPassY(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()) {
-  auto kern = fftPassStrided<T, MODE, false, Op>;
-  int rc = fftEnsureSmem<T>((const void *)kern, p.smemY);
-  if (rc) return rc;
-  const int ntx = (p.nkx + p.tileY - 1) / p.tileY;
-  kern<<<persistentGrid((const void *)kern, p.smemY, ntx * p.nz), kFftThreads, p.smemY, st>>>((typename Vec2<T>::type *)grid, p.ny, p.nkx, p.nz, p.tileY,
-                                                 (size_t)p.nkx, (size_t)p.nkx * p.ny, p.ay,
-                                                 p.twy.template as<typename Vec2<T>::type>(), op);
-  UB200_LAUNCHED();
-  return UB200_OK;
+  int rc = UB200_OK;
+  UB200_FFT_DISPATCH(p.ny, (rc = launchPassStridedFixed<T, MODE, false, Op, NFIX>(p, grid, st, op)));
+  return rc;
 }
 
 template <class T, int MODE, class Op = NoSpectralOp>
 int launchPassZ(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()) {
-  auto kern = fftPassStrided<T, MODE, true, Op>;
-  int rc = fftEnsureSmem<T>((const void *)kern, p.smemZ);
-  if (rc) return rc;
-  const int ntx = (p.nkx + p.tileZ - 1) / p.tileZ;
-  kern<<<persistentGrid((const void *)kern, p.smemZ, ntx * p.ny), kFftThreads, p.smemZ, st>>>((typename Vec2<T>::type *)grid, p.nz, p.nkx, p.ny, p.tileZ,
-                                                 (size_t)p.nkx * p.ny, (size_t)p.nkx, p.az,
-                                                 p.twz.template as<typename Vec2<T>::type>(), op);
-  UB200_LAUNCHED();
-  return UB200_OK;
+  int rc = UB200_OK;
+  UB200_FFT_DISPATCH(p.nz, (rc = launchPassStridedFixed<T, MODE, true, Op, NFIX>(p, grid, st, op)));
+  return rc;
 }
 
 } // namespace ub200

@@ -53,3 +53,36 @@ def lj_params(sigma=1.0, epsilon=1.0, rc=2.5, shift=False):
         i6 = f(f(i2 * i2) * i2)
         sh = f(f(f(f(epsilon) * f(4)) * i6) * f(i6 - f(1)))
     return np.array([c2, s2, f(f(epsilon) / s2), sh], dtype=np.float32)
+
+
+class Xorshift128plus:
+    """The reference's host generator (utils/utils.h:38-115), restated: used to reproduce the README example's
+    initial positions (sys->rng().uniform3) and the Saru seed an integrator draws at construction (next32)."""
+    M64 = (1 << 64) - 1
+
+    def __init__(self, s0=None):
+        if s0 is None:
+            self.s = [12679825035178159220, 15438657923749336752]
+        else:
+            self.setSeed(s0)
+
+    def setSeed(self, s0):
+        self.s = [s0 & self.M64, ((s0 + 15438657923749336752) & self.M64) % self.M64]
+
+    def next(self):
+        x, y = self.s
+        self.s[0] = y
+        x ^= (x << 23) & self.M64
+        x ^= x >> 17
+        x ^= y ^ (y >> 26)
+        self.s[1] = x
+        return (x + y) & self.M64
+
+    def next32(self):
+        return self.next() % 0xFFFFFFFF
+
+    def uniform(self, lo, hi):
+        return lo + (self.next() / float(self.M64)) * (hi - lo)
+
+    def uniform3(self, lo, hi):
+        return (self.uniform(lo, hi), self.uniform(lo, hi), self.uniform(lo, hi))
