@@ -153,7 +153,7 @@ typedef struct {
 
 /* 3-D real FFT, hand written (no cuFFT). Replaces the cuFFT plans + cufftExecR2C/D2Z/C2R/Z2D calls
  * (FCM_impl.cuh:179-234,293-304,544-557; PSE/FarField.cuh:555-603). Unnormalised; direction -1 = forward
- * (real -> complex), +1 = inverse. Sizes with prime factors 2, 3, 5, 7. */
+ * (real -> complex), +1 = inverse. Sizes with prime factors 2, 3, 5, 7, 11. */
 typedef struct ub200_fft3d ub200_fft3d;
 int ub200_fft3d_create(ub200_fft3d **out, int precisionBytes, int nx, int ny, int nz);
 int ub200_fft3d_destroy(ub200_fft3d *plan);
@@ -189,6 +189,43 @@ int ub200_fcm_grid_info(ub200_fcm *fcm, int cells[3], int *nxPad, void **d_grid)
  * group slot, d_BdW and K9 (host, row major 3x3 shear matrix) may be NULL. */
 int ub200_bdhi_euler_update(int precisionBytes, void *d_pos, const int *d_groupIdx, const void *d_MF, const void *d_BdW,
                             const double *K9, int N, double sqrt2Tdt, double dt, int is2D, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Positively Split Ewald RPY hydrodynamics. Replaces BDHI::PSE (Integrator/BDHI/BDHI_PSE.cuh:82-176) =
+ * pse_ns::FarField (PSE/FarField.cuh:317-553) + pse_ns::NearField (PSE/NearField.cuh:29-282) + the Lanczos
+ * square root (misc/LanczosAlgorithm/LanczosAlgorithm.cu:27-250). ub200_pse_create resolves every derived
+ * parameter exactly like the reference constructors: near-field cut-off and F/G table (NearField.cuh:65-102),
+ * far-field grid through nextFFTWiseSize3D (FarField.cuh:646-654, utils/Grid.cuh:142-213), Gaussian support
+ * and eta (FarField.cuh:605-644). seedNear / seedFar are the two sys->rng().next32() draws the reference
+ * makes at construction (near first: initialization.cu:57-59); seed2 arguments are the per-call draws
+ * (FarField.cuh:478, NearField.cuh:274).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_pse ub200_pse;
+typedef struct {
+  double L[3];
+  double viscosity, hydrodynamicRadius, tolerance, psi, shearStrain; /* pse_ns::Parameters (PSE/utils.cuh:17-24) */
+  int cellsOverride[3]; /* {0,0,0}: grid chosen like the reference; otherwise forced (tests on small grids) */
+} ub200_pse_params;
+typedef struct {
+  int cells[3], support, nTable, lastLanczosIterations;
+  double eta, rcut;
+  const void *d_table; /* real2[nTable]: F, G divided by 6 pi eta a */
+  void *d_grid;
+} ub200_pse_info_t;
+int ub200_pse_create(ub200_pse **out, int precisionBytes, const ub200_pse_params *par, uint32_t seedNear, uint32_t seedFar);
+int ub200_pse_destroy(ub200_pse *pse);
+int ub200_pse_info(ub200_pse *pse, ub200_pse_info_t *info);
+int ub200_pse_set_shear_strain(ub200_pse *pse, double strain); /* PSE::setShearStrain BDHI_PSE.cuh:160-165 */
+/* FarField::computeHydrodynamicDisplacements (FarField.cuh:535-553): d_MF3 += Mw F + prefactor sqrt(2T) Mw^1/2 dW.
+ * d_force (real4) may be NULL (noise only). */
+int ub200_pse_far_mdot(ub200_pse *pse, const void *d_pos, const void *d_force, int N, double temperature, double prefactor,
+                       uint32_t seed2, void *d_MF3, void *stream);
+/* NearField::Mdot (NearField.cuh:243-252): rebuilds the cell list, d_Mv3 += Mr v. d_v: real4 (vStride 4) or real3 (3). */
+int ub200_pse_near_mdot(ub200_pse *pse, const void *d_pos, const void *d_v, int vStride, int N, void *d_Mv3, void *stream);
+/* NearField::computeStochasticDisplacements (NearField.cuh:254-282): d_BdW3 = prefactor sqrt(2T) Mr^1/2 dW (overwritten,
+ * like the reference's gemv with beta = 0). Host-synchronous (Lanczos convergence checks) like the reference. */
+int ub200_pse_near_noise(ub200_pse *pse, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
+                         void *d_BdW3, int *iterations, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BASELINE config 0: BD::EulerMaruyama (ideal or with interactor forces). Replaces EulerMaruyama_ns::integrateGPU

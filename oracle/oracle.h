@@ -106,6 +106,18 @@ void orc_fcm_add_noise_d(const orc_grid_d *g, double viscosity, double noisePref
 void orc_dft3_r2c_d(int nx, int ny, int nz, int nxPad, const double *grid3, double *ghat);
 void orc_dft3_c2r_d(int nx, int ny, int nz, int nxPad, const double *ghat, double *grid3);
 
+/* ---------------- BDHI::PSE (fp64) ---------------- */
+double orc_pse_greens_d(const double k[3], double shear, double rh, double viscosity, double split, double eta, double ntot);
+void orc_pse_force2vel_d(const orc_grid_d *g, double shear, double rh, double viscosity, double split, double eta,
+                         double *ghat);
+void orc_pse_add_noise_d(const orc_grid_d *g, double shear, double rh, double viscosity, double split, double eta,
+                         double noisePrefactor, uint32_t seed1, uint32_t seed2, double *ghat);
+void orc_rpy_near_fg(double r, double rh, double psi, double rcut, double out[2]);
+void orc_pse_near_table_d(int nPoints, double rh, double psi, double normalization, double rcut, double *table2);
+void orc_pse_near_mdot_d(int N, const double *pos4, const double *v, int vStride, const double L[3], double shear,
+                         double rh, double psi, double normalization, double rcut, const double *table2, int nPoints,
+                         int useTable, double *out3);
+
 #ifdef __cplusplus
 }
 #endif

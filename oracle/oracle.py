@@ -318,3 +318,106 @@ def bd_euler_maruyama_f64(pos4, force4, selfMobility, dt, temperature, step, see
     k = np.ascontiguousarray(K9, np.float64) if K9 is not None else None
     lib().orc_bd_euler_maruyama_f64(_p(pos4), _p(force4), _p(k), C.c_double(selfMobility), _p(radius), C.c_double(dt),
                                     int(is2D), C.c_double(temperature), pos4.shape[0], C.c_uint32(step), C.c_uint32(seed))
+
+
+# ---------------- BDHI::PSE ----------------
+def next_fft_wise_size(n):
+    """nextFFTWiseSize3D (utils/Grid.cuh:142-213), one dimension."""
+    best = None
+    for m in range(4):
+        for l in range(5):
+            for k in range(6):
+                base = 11 ** m * 7 ** l * 5 ** k
+                p3 = 1
+                while base * p3 <= (1 << 40):
+                    p2 = 2
+                    while base * p3 * p2 < n:
+                        p2 *= 2
+                    v = base * p3 * p2
+                    if best is None or v < best:
+                        best = v
+                    p3 *= 3
+    return best
+
+
+def pse_params(L, viscosity, rh, tolerance, psi, cells=None):
+    """Derived PSE parameters in double precision: NearField::initializeDeterministicPart (PSE/NearField.cuh:65-102),
+    FarField::initializeGrid / initializeKernel (PSE/FarField.cuh:605-654)."""
+    import math
+    L = (L, L, L) if np.isscalar(L) else tuple(L)
+    rcut = math.sqrt(-math.log(tolerance)) / psi
+    nTable = int(min(1 << 22, max(1 << 14, int(rcut / (rh * tolerance) + 0.5))))
+    kcut = 2 * psi * math.sqrt(-math.log(tolerance))
+    hgrid = 2 * math.pi / kcut
+    if cells is None:
+        cells = tuple(next_fft_wise_size(int(2 * L[d] / hgrid) + 1) for d in range(3))
+    Cc, m = 0.976, 1.0
+    while math.erfc(m / math.sqrt(2)) > 0.1 * tolerance:
+        m += 0.01
+    while True:
+        support = int((m / Cc) ** 2 / math.pi + 0.5) + 1
+        if support % 2 == 1:
+            break
+        m += tolerance
+    P = support // 2
+    if support > min(cells):
+        support = min(cells)
+        if support % 2 == 0:
+            support -= 1
+        P = support // 2
+        m = Cc * math.sqrt(math.pi * support)
+    h = min(L[d] / cells[d] for d in range(3))
+    w = (2 * P + 1) * h / 2.0
+    eta = (2.0 * psi * w / m) ** 2
+    width = math.sqrt(eta) / (2.0 * psi)
+    kern = IBMKernel(KERNEL_GAUSSIAN, 2 * P + 1, h, (1.0 / (width ** 3 * (2.0 * math.pi) ** 1.5)) ** (1.0 / 3.0),
+                     -0.5 / (width * width), float("inf"))
+    return dict(L=L, cells=tuple(cells), support=2 * P + 1, eta=eta, rcut=rcut, nTable=nTable, kernel=kern,
+                normalization=6 * math.pi * rh * viscosity)
+
+
+def pse_far_mdot(par, viscosity, rh, psi, pos4, force3, shear=0.0, temperature=0.0, prefactor=0.0, seed=0, seed2=0):
+    """FarField::computeHydrodynamicDisplacements (PSE/FarField.cuh:535-553) with numpy.fft standing in for cuFFT."""
+    L, cells, kern = par["L"], par["cells"], par["kernel"]
+    g = make_grid_d(L, cells)
+    nx, ny, nz = cells
+    nxPad = 2 * (nx // 2 + 1)
+    if force3 is not None:
+        sp = ibm_spread(g, kern, pos4, force3, nxPad)
+        ghat = np.ascontiguousarray(np.fft.rfftn(sp[:, :, :nx, :], axes=(0, 1, 2)))
+        lib().orc_pse_force2vel_d(C.byref(g), C.c_double(shear), C.c_double(rh), C.c_double(viscosity), C.c_double(psi),
+                                  C.c_double(par["eta"]), _p(ghat))
+    else:
+        ghat = np.zeros((nz, ny, nx // 2 + 1, 3), np.complex128)
+    if temperature > 0:
+        dV = g.cellSize[0] * g.cellSize[1] * g.cellSize[2]
+        lib().orc_pse_add_noise_d(C.byref(g), C.c_double(shear), C.c_double(rh), C.c_double(viscosity), C.c_double(psi),
+                                  C.c_double(par["eta"]), C.c_double(prefactor * np.sqrt(2 * temperature / dV)),
+                                  C.c_uint32(seed), C.c_uint32(seed2), _p(ghat))
+    vel = np.zeros((nz, ny, nxPad, 3))
+    vel[:, :, :nx, :] = np.fft.irfftn(ghat, s=(nz, ny, nx), axes=(0, 1, 2)) * (nx * ny * nz)
+    return ibm_gather(g, kern, pos4, vel, nxPad)
+
+
+def rpy_near_fg(r, rh, psi, rcut):
+    out = (C.c_double * 2)()
+    lib().orc_rpy_near_fg(C.c_double(r), C.c_double(rh), C.c_double(psi), C.c_double(rcut), out)
+    return out[0], out[1]
+
+
+def pse_near_table(par, rh, psi):
+    t = np.zeros((par["nTable"], 2))
+    lib().orc_pse_near_table_d(par["nTable"], C.c_double(rh), C.c_double(psi), C.c_double(par["normalization"]),
+                               C.c_double(par["rcut"]), _p(t))
+    return t
+
+
+def pse_near_mdot(par, rh, psi, pos4, v, shear=0.0, table=None):
+    """Direct O(N^2) near-field mat-vec (NearField.cuh:131-182); table=None evaluates F, G in closed form."""
+    pos4 = np.ascontiguousarray(pos4, np.float64)
+    v = np.ascontiguousarray(v, np.float64)
+    out = np.zeros((pos4.shape[0], 3))
+    lib().orc_pse_near_mdot_d(pos4.shape[0], _p(pos4), _p(v), v.shape[1], (C.c_double * 3)(*par["L"]), C.c_double(shear),
+                              C.c_double(rh), C.c_double(psi), C.c_double(par["normalization"]), C.c_double(par["rcut"]),
+                              _p(table), par["nTable"], 1 if table is not None else 0, _p(out))
+    return out

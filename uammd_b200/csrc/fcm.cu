@@ -7,7 +7,7 @@
 //              fused [FFT z, Stokes projector, Brownian noise, inverse FFT z] -> inverse FFT y, x -> gather.
 // One grid buffer, transformed in place; no memsets, no atomics (small supports), no per-step allocation.
 #include "fft3d.cuh"
-#include "ibm.cuh"
+#include "ibm_state.cuh"
 #include "saru.cuh"
 
 namespace ub200 {
@@ -101,10 +101,6 @@ template <class T> struct FcmSpectralOp {
   }
 };
 
-template <class T> struct Real4;
-template <> struct Real4<float> { using type = float4; };
-template <> struct Real4<double> { using type = double4; };
-
 // EulerMaruyama_ns::integrateGPUD (Integrator/BDHI/BDHI_EulerMaruyama.cu:82-113): dR = dt (K R + MF) + sqrt(2 T dt) BdW
 template <class T> struct ShearK { T k[9]; int on; };
 template <class T4>
@@ -133,135 +129,6 @@ bdhiEulerUpdate(T4 *__restrict__ pos, const int *__restrict__ groupIdx, const de
   pc.x = px; pc.y = py; pc.z = pz;
   pos[i] = pc;
 }
-
-template <class T> struct IbmState {
-  GridT<T> grid;
-  IbmKernel<T> kern;
-  int nxPad = 0;
-  bool nodeCentric = false;
-  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedPos, sortedVal, sortedOrigin, sortedW;
-  int sortedValidFor = -1;
-
-  int init(const double L[3], const int periodic[3], const int cells[3], const ub200_ibm_kernel &k, int nxPad_) {
-    grid = makeGridT<T>(L, periodic, cells);
-    kern.kind = k.kind;
-    kern.support = k.support;
-    kern.invh = (T)(1.0 / k.h);
-    kern.prefactor = (T)k.prefactor;
-    kern.tau = (T)k.tau;
-    kern.rmax = (T)k.rmax;
-    nxPad = nxPad_;
-    if (k.support < 1 || k.support > kMaxSupport) return UB200_ERR_INVALID_ARGUMENT;
-    const long long ncells = (long long)grid.n[0] * grid.n[1] * grid.n[2];
-    nodeCentric = (k.support == 3 || k.support == 4) && ncells <= 4096LL * 4096LL;
-    for (int d = 0; d < 3; d++)
-      if (grid.m[d] != T(0) && grid.n[d] < k.support + 1) nodeCentric = false; // support would overlap itself
-    if (grid.n[2] == 1) nodeCentric = false; // 2-D grids take the generic path
-    return UB200_OK;
-  }
-  void release() {
-    DevBuf *b[] = {&binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedPos, &sortedVal, &sortedOrigin, &sortedW};
-    for (auto *x : b) x->release();
-  }
-
-  // bin, order and build the stencil records (positions + optional values)
-  int prepare(const void *pos, const void *val, int valStride, int N, cudaStream_t st) {
-    using T4 = typename Real4<T>::type;
-    const int ncells = grid.n[0] * grid.n[1] * grid.n[2];
-    int rc;
-    if (!binCount.p || binCount.cap < sizeof(uint32_t) * (size_t)ncells) {
-      if ((rc = binCount.reserve(sizeof(uint32_t) * (size_t)ncells))) return rc;
-      if ((rc = binStart.reserve(sizeof(uint32_t) * ((size_t)ncells + 1)))) return rc;
-      if ((rc = tileSums.reserve(sizeof(uint32_t) * 4096))) return rc;
-      UB200_CUDA(cudaMemsetAsync(binCount.p, 0, binCount.cap, st));
-    }
-    if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N))) return rc;
-    if ((rc = unstable.reserve(sizeof(int) * (size_t)N))) return rc;
-    if ((rc = sortedIndex.reserve(sizeof(int) * (size_t)N))) return rc;
-    if ((rc = sortedPos.reserve(sizeof(T4) * (size_t)N))) return rc;
-    if ((rc = sortedVal.reserve(sizeof(T) * 2 * (size_t)N))) return rc;
-    if ((rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N))) return rc;
-    if ((rc = sortedW.reserve(sizeof(T) * 3 * kSmallSupport * (size_t)N))) return rc;
-    const int nb = (N + 255) / 256;
-    ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
-    UB200_LAUNCHED();
-    if ((rc = exclusiveScanAndClear(binCount.as<uint32_t>(), ncells, binStart.as<uint32_t>(), tileSums.as<uint32_t>(), st)))
-      return rc;
-    if ((rc = scatterToBinsLaunch(codeSlot.as<uint2>(), binStart.as<uint32_t>(), N, unstable.as<int>(), st))) return rc;
-    if (kern.support == 3)
-      ibmOrderSorted<T4, 3><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(),
-                                                (const T4 *)pos, (const T *)val, valStride, N, grid, kern,
-                                                sortedIndex.as<int>(), sortedPos.as<T4>(), sortedVal.as<T>(),
-                                                sortedOrigin.as<int4>(), sortedW.as<T>());
-    else
-      ibmOrderSorted<T4, 4><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(),
-                                                (const T4 *)pos, (const T *)val, valStride, N, grid, kern,
-                                                sortedIndex.as<int>(), sortedPos.as<T4>(), sortedVal.as<T>(),
-                                                sortedOrigin.as<int4>(), sortedW.as<T>());
-    UB200_LAUNCHED();
-    sortedValidFor = N;
-    return UB200_OK;
-  }
-
-  // grid3 is completely overwritten on the node-centric path; the generic path accumulates into it
-  int spread(const void *pos, const void *val, int valStride, int N, T *grid3, bool gridIsZero, cudaStream_t st) {
-    using T4 = typename Real4<T>::type;
-    if (nodeCentric) {
-      int rc = prepare(pos, val, valStride, N, st);
-      if (rc) return rc;
-      dim3 grd((nxPad + kBrickX - 1) / kBrickX, (grid.n[1] + kBrickY - 1) / kBrickY, (grid.n[2] + kBrickZ - 1) / kBrickZ);
-      if (kern.support == 3) {
-        auto kfn = ibmSpreadBricks<T4, 3>;
-        const size_t sm = BrickGeom<T, 3>::smemBytes;
-        UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(),
-                                            binStart.as<uint32_t>(), grid, nxPad, grid3);
-      } else {
-        auto kfn = ibmSpreadBricks<T4, 4>;
-        const size_t sm = BrickGeom<T, 4>::smemBytes;
-        UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(),
-                                            binStart.as<uint32_t>(), grid, nxPad, grid3);
-      }
-      UB200_LAUNCHED();
-      return UB200_OK;
-    }
-    if (!gridIsZero)
-      UB200_CUDA(cudaMemsetAsync(grid3, 0, sizeof(T) * 3 * (size_t)nxPad * grid.n[1] * grid.n[2], st));
-    ibmWarpPerParticle<T4, T, true, false><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)val, valStride, N,
-                                                                         grid, kern, nxPad, grid3, nullptr);
-    UB200_LAUNCHED();
-    sortedValidFor = -1;
-    return UB200_OK;
-  }
-
-  // reuseRecords: positions are the ones of the preceding spread on this state
-  int gather(const void *pos, int N, const T *grid3, T *out3, bool accumulate, bool reuseRecords, cudaStream_t st) {
-    using T4 = typename Real4<T>::type;
-    if (nodeCentric) {
-      if (!(reuseRecords && sortedValidFor == N)) {
-        int rc = prepare(pos, nullptr, 0, N, st);
-        if (rc) return rc;
-      }
-      const int nb = (N + 127) / 128;
-#define UB200_GATHER(SS, ACC)                                                                                 \
-  ibmGatherSorted<T, SS, ACC><<<nb, 128, 0, st>>>(sortedOrigin.as<int4>(), sortedW.as<T>(), sortedIndex.as<int>(), N, grid, nxPad, grid3, out3)
-      if (kern.support == 3) { if (accumulate) UB200_GATHER(3, true); else UB200_GATHER(3, false); }
-      else { if (accumulate) UB200_GATHER(4, true); else UB200_GATHER(4, false); }
-#undef UB200_GATHER
-      UB200_LAUNCHED();
-      return UB200_OK;
-    }
-    if (accumulate)
-      ibmWarpPerParticle<T4, T, false, true><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)nullptr, 0, N, grid,
-                                                                         kern, nxPad, const_cast<T *>(grid3), out3);
-    else
-      ibmWarpPerParticle<T4, T, false, false><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)nullptr, 0, N,
-                                                                          grid, kern, nxPad, const_cast<T *>(grid3), out3);
-    UB200_LAUNCHED();
-    return UB200_OK;
-  }
-};
 
 template <class T> struct FcmState {
   Fft3dPlan<T> plan;

@@ -51,13 +51,13 @@ struct FftAxis {
   int radix[kMaxStages];
 };
 
-// n = prod radix; prefer 4, then 2, 3, 5, 7. Returns false when n has other prime factors.
+// n = prod radix; prefer 4, then 2, 3, 5, 7, 11. Returns false when n has other prime factors.
 inline bool factorize(int n, FftAxis &ax) {
   ax.n = n;
   ax.nstages = 0;
   int m = n;
   while (m % 4 == 0 && ax.nstages < kMaxStages) { ax.radix[ax.nstages++] = 4; m /= 4; }
-  const int primes[4] = {2, 3, 5, 7};
+  const int primes[5] = {2, 3, 5, 7, 11}; // nextFFTWiseSize3D (utils/Grid.cuh:142-213) emits 2^a 3^b 5^c 7^d 11^e
   for (int p : primes)
     while (m % p == 0 && ax.nstages < kMaxStages) { ax.radix[ax.nstages++] = p; m /= p; }
   return m == 1;
@@ -117,8 +117,8 @@ __device__ __forceinline__ void stockhamStage(const typename Vec2<T>::type *__re
       dst[0] = cadd(v0, t);
       dst[Ns] = cadd(m1, d);
       dst[2 * Ns] = csub(m1, d);
-    } else { // generic small radix (5, 7): direct DFT with roots taken from the twiddle table
-      C v[7];
+    } else { // generic small radix (5, 7, 11): direct DFT with roots taken from the twiddle table
+      C v[11];
       for (int p = 0; p < R; p++) {
         v[p] = src[j + p * nb];
         if (Ns > 1 && p > 0) v[p] = cmul(v[p], twid(p * k * twStep));

@@ -1,0 +1,826 @@
+// Positively Split Ewald RPY hydrodynamics (BDHI::PSE) behind the C ABI, sm_100a.
+//
+// Far field  (PSE/FarField.cuh:535-553): Gaussian spread -> FFT x, y -> fused [FFT z, Hasimoto-split RPY Green's
+//            function x projector, Brownian noise, inverse FFT z] -> inverse FFT y, x -> gather (accumulating into MF).
+//            Same kernels as FCM; only the spectral operator (greensFunction :85-119, fourierBrownianNoise :235-308)
+//            and the window (pse_ns::Kernel :25-41, support 2P+1) differ. One grid buffer, in place, no per-call
+//            allocation (the reference re-allocates both grids and the cuFFT work area from its pool every call).
+// Near field (PSE/NearField.cuh:120-196,243-282): RPY mat-vec over our cell list with the tabulated F(r), G(r)
+//            (RPY_PSE.cuh:45-128, TabulatedFunction.cuh:63-158), warp per home cell with the candidates staged in
+//            shared memory (positions AND the vector v), sheared minimum image exactly as the reference computes it.
+// Near-field noise (NearField.cuh:254-282): Lanczos sqrt(M) z (misc/LanczosAlgorithm/LanczosAlgorithm.cu) with our
+//            own reduction kernels and a host QL eigen-solver for the small tridiagonal matrix (no cuBLAS / LAPACKE).
+#include "fft3d.cuh"
+#include "ibm_state.cuh"
+#include "pair_common.cuh"
+#include "saru.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace ub200 {
+
+// ------------------------------------------------------------------------------------------------------------
+// Far field spectral operator
+// ------------------------------------------------------------------------------------------------------------
+template <class T> struct PseSpectralOp {
+  using C = typename Vec2<T>::type;
+  int nx, ny, nz, nkx;
+  T kfx, kfy, kfz; // 2 pi / L (waveNumberToWaveVector, PSE/utils.cuh:41-44)
+  T shear, rh, vis, split, eta, nTot;
+  int deterministic, noise;
+  T noisePrefactor;
+  uint32_t seed1, seed2;
+
+  __device__ __forceinline__ static int fold(int i, int n) { return i - n * (i >= (n / 2 + 1)); }
+  __device__ __forceinline__ bool generates(int ix, int iy, int iz) const {
+    if (ix == 0 && iy == 0 && iz == 0) return false;
+    if (ix == 0 && iy == 0 && 2 * iz >= nz + 1) return false;
+    if (ix == 0 && 2 * iy >= ny + 1) return false;
+    return true;
+  }
+  __device__ __forceinline__ bool nyquist(int ix, int iy, int iz) const { // FarField.cuh:183-219
+    const bool nxq = (ix == nx - ix) && (nx % 2 == 0);
+    const bool nyq = (iy == ny - iy) && (ny % 2 == 0);
+    const bool nzq = (iz == nz - iz) && (nz % 2 == 0);
+    return (nxq && iy == 0 && iz == 0) || (nxq && nyq && iz == 0) || (ix == 0 && nyq && iz == 0) ||
+           (nxq && iy == 0 && nzq) || (ix == 0 && iy == 0 && nzq) || (ix == 0 && nyq && nzq) || (nxq && nyq && nzq);
+  }
+  __device__ __forceinline__ void drawNoise(uint32_t id, C &a, C &b, C &c) const { // generateNoise :161-177
+    Saru rng(id, seed1, seed2);
+    const float sc = (float)(T(0.707106781186547) * noisePrefactor);
+    float2 g = rng.gauss2(sc); a = mk2<T>((T)g.x, (T)g.y);
+    g = rng.gauss2(sc); b = mk2<T>((T)g.x, (T)g.y);
+    g = rng.gauss2(sc); c = mk2<T>((T)g.x, (T)g.y);
+  }
+  // greensFunction (FarField.cuh:85-119); (kx, ky, kz) is the unsheared (NUFFT) wave vector, kyE the sheared ky
+  __device__ __forceinline__ T greens(T kx, T ky, T kz, T kyE) const {
+    const T kN2 = kx * kx + ky * ky + kz * kz;
+    if (kN2 == T(0)) return T(0);
+    const T kE2 = kx * kx + kyE * kyE + kz * kz;
+    const T kmod = sqrt(kE2);
+    const T invk2 = T(1.0) / kE2;
+    const T sink = sin(kmod * rh);
+    const T kEw = kE2 / (T(4.0) * split * split);
+    const T kNu = kN2 / (T(4.0) * split * split);
+    const T tau = eta * kNu - kEw;
+    const T hashimoto = (T(1.0) + kEw) * exp(tau) / kE2;
+    T B = sink * sink * invk2 * hashimoto / (vis * rh * rh);
+    B /= nTot;
+    return B;
+  }
+
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, C &vx, C &vy, C &vz) const {
+    if (ix == 0 && iy == 0 && iz == 0) { vx = vy = vz = mk2<T>(T(0), T(0)); return; }
+    const T kx = kfx * (T)fold(ix, nx), ky = kfy * (T)fold(iy, ny), kz = kfz * (T)fold(iz, nz);
+    const T kyE = ky - shear * kx; // shearWaveVector (PSE/utils.cuh:36-39)
+    const T B = greens(kx, ky, kz, kyE);
+    const T invk2 = T(1.0) / (kx * kx + kyE * kyE + kz * kz);
+    auto project = [&](T f0, T f1, T f2, T &o0, T &o1, T &o2) { // projectFourier (FarField.cuh:53-73)
+      const T kf = (kx * f0 + kyE * f1 + kz * f2) * invk2;
+      o0 = f0 - kx * kf; o1 = f1 - kyE * kf; o2 = f2 - kz * kf;
+    };
+    C ox = mk2<T>(T(0), T(0)), oy = ox, oz = ox;
+    if (deterministic) {
+      T a0, a1, a2, b0, b1, b2;
+      project(B * vx.x, B * vy.x, B * vz.x, a0, a1, a2);
+      project(B * vx.y, B * vy.y, B * vz.y, b0, b1, b2);
+      ox = mk2<T>(a0, b0); oy = mk2<T>(a1, b1); oz = mk2<T>(a2, b2);
+    }
+    if (noise) {
+      const T Bsq = sqrt(B);
+      if (generates(ix, iy, iz)) {
+        C n0, n1, n2;
+        drawNoise((uint32_t)(ix + nkx * (iy + ny * iz)), n0, n1, n2);
+        if (nyquist(ix, iy, iz)) {
+          const T q = T(1.41421356237310);
+          n0.x *= q; n0.y = T(0); n1.x *= q; n1.y = T(0); n2.x *= q; n2.y = T(0);
+        }
+        T a0, a1, a2, b0, b1, b2;
+        project(n0.x, n1.x, n2.x, a0, a1, a2);
+        project(n0.y, n1.y, n2.y, b0, b1, b2);
+        ox.x += Bsq * a0; ox.y += Bsq * b0; oy.x += Bsq * a1; oy.y += Bsq * b1; oz.x += Bsq * a2; oz.y += Bsq * b2;
+      }
+      // what the conjugate partner adds here (stored twice only on the kx = 0 and kx = nx/2 planes); the
+      // reference does this with a second non-atomic "+=" from another thread, this is the race-free sum
+      if (ix == 0 || ix == nx - ix) {
+        const int cy = (iy > 0) * (ny - iy), cz = (iz > 0) * (nz - iz);
+        if (!(cy == iy && cz == iz) && generates(ix, cy, cz) && !nyquist(ix, cy, cz)) {
+          C n0, n1, n2;
+          drawNoise((uint32_t)(ix + nkx * (cy + ny * cz)), n0, n1, n2);
+          T a0, a1, a2, b0, b1, b2;
+          project(n0.x, n1.x, n2.x, a0, a1, a2);
+          project(-n0.y, -n1.y, -n2.y, b0, b1, b2);
+          ox.x += Bsq * a0; ox.y += Bsq * b0; oy.x += Bsq * a1; oy.y += Bsq * b1; oz.x += Bsq * a2; oz.y += Bsq * b2;
+        }
+      }
+    }
+    vx = ox; vy = oy; vz = oz;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Near field
+// ------------------------------------------------------------------------------------------------------------
+template <class T> struct TableView { // TabulatedFunction<real2, LinearInterpolation> (misc/TabulatedFunction.cuh:78-158)
+  const typename Vec2<T>::type *table;
+  int Ntable;
+  T rmin, rmax, interval, dr;
+};
+
+template <class T> __device__ __forceinline__ typename Vec2<T>::type tableGet(const TableView<T> &tb, T rs) {
+  using C = typename Vec2<T>::type;
+  const T r = (rs - tb.rmin) * tb.interval;
+  if (rs >= tb.rmax) return mk2<T>(T(0), T(0));
+  if (r <= T(0)) return __ldg(tb.table);
+  const int i = (int)(r * tb.Ntable);
+  const T r0 = i * tb.dr;
+  const C v0 = __ldg(tb.table + i), v1 = __ldg(tb.table + i + 1);
+  const T t = (r - r0) * (T)tb.Ntable;
+  return mk2<T>(fma(t, v1.x, fma(-t, v0.x, v0.x)), fma(t, v1.y, fma(-t, v0.y, v0.y)));
+}
+
+template <class T> struct NearGeom {
+  T Lx, Ly, Lz, shear, rcut2;
+};
+
+// RPYNearTransverser::compute (NearField.cuh:131-182)
+template <class T>
+__device__ __forceinline__ void rpyPair(const NearGeom<T> &q, const TableView<T> &tb, T pix, T piy, T piz, T pjx, T pjy,
+                                        T pjz, T vjx, T vjy, T vjz, T &ax, T &ay, T &az) {
+  T rx = pjx - pix, ry = pjy - piy, rz = pjz - piz;
+  rx += q.shear * ry;
+  const T s1 = round(ry / q.Ly);
+  rx -= q.shear * q.Ly * s1;
+  ry -= q.Ly * s1;
+  rz -= q.Lz * round(rz / q.Lz);
+  rx -= q.Lx * round(rx / q.Lx);
+  const T r2 = rx * rx + ry * ry + rz * rz;
+  if (r2 >= q.rcut2) return;
+  const auto fg = tableGet(tb, sqrt(r2));
+  const T f = fg.x, g = fg.y;
+  if (r2 == T(0)) { ax += f * vjx; ay += f * vjy; az += f * vjz; return; }
+  const T invr2 = T(1.0) / r2;
+  const T gmfv = (g - f) * (rx * vjx + ry * vjy + rz * vjz) * invr2;
+  ax += f * vjx + gmfv * rx;
+  ay += f * vjy + gmfv * ry;
+  az += f * vjz + gmfv * rz;
+}
+
+// sorted copies: position (xyz) and the vector v (xyz) of the particle in sorted slot k
+template <class T4, class T>
+__global__ void __launch_bounds__(256)
+pseGatherSorted(const int *__restrict__ groupIndex, const T4 *__restrict__ pos, const T *__restrict__ v, int vStride, int N,
+                T *__restrict__ sortedPos3, T *__restrict__ sortedV3) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const int i = groupIndex[k];
+  if (sortedPos3) {
+    const T4 p = pos[i];
+    sortedPos3[3 * (size_t)k] = p.x; sortedPos3[3 * (size_t)k + 1] = p.y; sortedPos3[3 * (size_t)k + 2] = p.z;
+  }
+  if (sortedV3) {
+    const T *vp = v + (size_t)i * vStride;
+    sortedV3[3 * (size_t)k] = vp[0]; sortedV3[3 * (size_t)k + 1] = vp[1]; sortedV3[3 * (size_t)k + 2] = vp[2];
+  }
+}
+
+__global__ void __launch_bounds__(256) pseToFloat4(const double4 *__restrict__ in, float4 *__restrict__ out, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double4 p = in[i];
+  out[i] = make_float4((float)p.x, (float)p.y, (float)p.z, 0.f);
+}
+
+constexpr int kNearCap = 224; // staged candidates per warp
+
+// One warp per home cell: the (up to) 27 neighbour cells are staged once per cell (position + v, 6 reals per
+// candidate), then every home particle is served by the 32 lanes striding over the staged candidates and a
+// butterfly reduction. Replaces transverseWithNeighbourContainer (NeighbourList/common.cuh:10-34) for the
+// RPYNearTransverser. ACCUMULATE: Mv[i] += (Transverser::set, NearField.cuh:184-186); otherwise Mv[i] = (the
+// Dotctor's fill + traverse, :212-218, in one pass).
+template <class T, bool ACCUMULATE>
+__global__ void __launch_bounds__(kPairThreads)
+rpyNearTraversal(const T *__restrict__ sortedPos3, const T *__restrict__ sortedV3, const int *__restrict__ groupIndex,
+                 const uint32_t *__restrict__ binStart, GridF g, int ncells, TableView<T> tb, NearGeom<T> q,
+                 T *__restrict__ Mv3) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *cand = reinterpret_cast<T *>(smemRaw) + (size_t)warp * kNearCap * 6;
+  const int warpsTotal = gridDim.x * kPairWarps;
+  for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
+    const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
+    const NeighbourCells nc = describeNeighbours(g, cx, cy, cz, binStart, lane);
+    const int hStart = __shfl_sync(0xffffffffu, nc.start, nc.centre);
+    const int hCount = __shfl_sync(0xffffffffu, nc.count, nc.centre);
+    if (hCount == 0) continue;
+    const bool staged = nc.total <= kNearCap;
+    __syncwarp();
+    if (staged) {
+      for (int c = 0; c < 27; c++) {
+        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+        if (cnt == 0) continue;
+        const int st = __shfl_sync(0xffffffffu, nc.start, c);
+        const int off = __shfl_sync(0xffffffffu, nc.off, c);
+        for (int t = lane; t < 3 * cnt; t += 32) {
+          cand[(size_t)off * 6 + t] = sortedPos3[3 * (size_t)st + t];           // [off*6 .. off*6+3cnt): positions
+          cand[(size_t)off * 6 + 3 * cnt + t] = sortedV3[3 * (size_t)st + t];   // then the v of the same cell
+        }
+      }
+    }
+    __syncwarp();
+    for (int h = 0; h < hCount; h++) {
+      const T pix = sortedPos3[3 * (size_t)(hStart + h)], piy = sortedPos3[3 * (size_t)(hStart + h) + 1],
+              piz = sortedPos3[3 * (size_t)(hStart + h) + 2];
+      T ax = T(0), ay = T(0), az = T(0);
+      for (int c = 0; c < 27; c++) {
+        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+        if (cnt == 0) continue;
+        const int st = __shfl_sync(0xffffffffu, nc.start, c);
+        const int off = __shfl_sync(0xffffffffu, nc.off, c);
+        for (int t = lane; t < cnt; t += 32) {
+          T pjx, pjy, pjz, vjx, vjy, vjz;
+          if (staged) {
+            const T *pp = cand + (size_t)off * 6 + 3 * t, *vp = cand + (size_t)off * 6 + 3 * cnt + 3 * t;
+            pjx = pp[0]; pjy = pp[1]; pjz = pp[2]; vjx = vp[0]; vjy = vp[1]; vjz = vp[2];
+          } else {
+            const T *pp = sortedPos3 + 3 * (size_t)(st + t), *vp = sortedV3 + 3 * (size_t)(st + t);
+            pjx = pp[0]; pjy = pp[1]; pjz = pp[2]; vjx = vp[0]; vjy = vp[1]; vjz = vp[2];
+          }
+          rpyPair(q, tb, pix, piy, piz, pjx, pjy, pjz, vjx, vjy, vjz, ax, ay, az);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+      }
+      if (lane == 0) {
+        T *out = Mv3 + 3 * (size_t)groupIndex[hStart + h];
+        if (ACCUMULATE) { out[0] += ax; out[1] += ay; out[2] += az; }
+        else { out[0] = ax; out[1] = ay; out[2] = az; }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Lanczos helpers (vectors of n reals on the device, scalars through a small pinned-free host read)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kRedBlocks = 592, kRedThreads = 256;
+
+template <class T>
+__global__ void __launch_bounds__(kRedThreads) redDotPartial(const T *__restrict__ a, const T *__restrict__ b, size_t n,
+                                                             double *__restrict__ partial) {
+  __shared__ double sh[kRedThreads / 32];
+  double acc = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc += (double)a[i] * (double)b[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < kRedThreads / 32; w++) s += sh[w];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(kRedThreads) redFinal(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+  __shared__ double sh[kRedThreads / 32];
+  double acc = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < kRedThreads / 32; w++) s += sh[w];
+    *out = s;
+  }
+}
+// y = alpha x + beta y (beta == 0: y is not read)
+template <class T>
+__global__ void __launch_bounds__(256) vecAxpby(T alpha, const T *__restrict__ x, T beta, T *__restrict__ y, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = beta == T(0) ? alpha * x[i] : alpha * x[i] + beta * y[i];
+}
+// out = scale * V[:, 0:m] c   (V column major, leading dimension n)
+template <class T>
+__global__ void __launch_bounds__(256) vecGemv(const T *__restrict__ V, size_t n, int m, const T *__restrict__ c, T scale,
+                                               T *__restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T acc = T(0);
+  for (int j = 0; j < m; j++) acc += V[i + n * (size_t)j] * __ldg(c + j);
+  out[i] = scale * acc;
+}
+// SaruTransform (NearField.cuh:222-232)
+template <class T>
+__global__ void __launch_bounds__(256) pseNearNoise(T *__restrict__ z3, int N, T variance, uint32_t seed1, uint32_t seed2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  Saru rng((uint32_t)i, seed1, seed2);
+  const float2 a = rng.gauss2(1.0f), b = rng.gauss2(1.0f);
+  z3[3 * (size_t)i] = (T)a.x * variance; z3[3 * (size_t)i + 1] = (T)a.y * variance; z3[3 * (size_t)i + 2] = (T)b.x * variance;
+}
+
+// eigen-decomposition of a symmetric tridiagonal matrix (implicit QL, double precision): d[n] diagonal ->
+// eigenvalues, e[n-1] sub-diagonal, Z (column major n x n) -> eigenvectors. Stands in for LAPACKE_steqr('I').
+inline bool tridiagEigen(int n, std::vector<double> &d, std::vector<double> e, std::vector<double> &Z) {
+  Z.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) Z[(size_t)i * n + i] = 1.0;
+  e.resize(n, 0.0);
+  for (int l = 0; l < n; l++) {
+    int iter = 0, m;
+    do {
+      for (m = l; m < n - 1; m++) {
+        const double dd = fabs(d[m]) + fabs(d[m + 1]);
+        if (fabs(e[m]) <= 2.3e-16 * dd) break;
+      }
+      if (m != l) {
+        if (iter++ == 200) return false;
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + (g >= 0 ? fabs(r) : -fabs(r)));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = m - 1; i >= l; i--) {
+          double f = s * e[i], b = c * e[i];
+          r = hypot(f, g);
+          e[i + 1] = r;
+          if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+          s = f / r; c = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * b;
+          p = s * r;
+          d[i + 1] = g + p;
+          g = c * r - b;
+          for (int k = 0; k < n; k++) { // rotate eigenvector columns i and i+1
+            f = Z[(size_t)(i + 1) * n + k];
+            Z[(size_t)(i + 1) * n + k] = s * Z[(size_t)i * n + k] + c * f;
+            Z[(size_t)i * n + k] = c * Z[(size_t)i * n + k] - s * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p; e[l] = g; e[m] = 0.0;
+      }
+    } while (m != l);
+  }
+  return true;
+}
+
+struct GrowBuf { // device buffer that keeps its contents when it grows
+  void *p = nullptr;
+  size_t cap = 0;
+  int grow(size_t bytes, cudaStream_t st) {
+    if (bytes <= cap) return UB200_OK;
+    size_t want = std::max(bytes, 2 * cap);
+    void *np = nullptr;
+    if (cudaMalloc(&np, want) != cudaSuccess) return UB200_ERR_ALLOC;
+    if (p) {
+      cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+      cudaStreamSynchronize(st);
+      cudaFree(p);
+    }
+    p = np; cap = want;
+    return UB200_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// nextFFTWiseSize3D (utils/Grid.cuh:142-213), one dimension: smallest 2^i 3^j 5^k 7^l 11^m >= n with i >= 1,
+// k <= 5, l <= 4, m <= 3 (the reference's "forbidden sizes" loop has no effect: its `continue` only leaves the inner loop)
+inline int nextFFTWiseSize(int n) {
+  long long best = -1;
+  for (long long p11 = 1, m = 0; m <= 3; m++, p11 *= 11)
+    for (long long p7 = 1, l = 0; l <= 4; l++, p7 *= 7)
+      for (long long p5 = 1, k = 0; k <= 5; k++, p5 *= 5)
+        for (long long p3 = 1; p3 * p5 * p7 * p11 <= (1LL << 40); p3 *= 3)
+          for (long long p2 = 2; p2 * p3 * p5 * p7 * p11 <= (1LL << 40); p2 *= 2) {
+            const long long v = p2 * p3 * p5 * p7 * p11;
+            if (v >= n && (best < 0 || v < best)) best = v;
+            if (v >= n) break;
+          }
+  return best >= (1LL << 31) ? -1 : (int)best;
+}
+
+// RPYPSE_near::FandG (PSE/RPY_PSE.cuh:45-128): host, double precision
+inline void rpyNearFG(double r, double rh, double psi, double rcut, double &F, double &G) {
+  if (r >= rcut) { F = G = 0; return; }
+  if (r <= 0.0) {
+    const double pi = M_PI;
+    F = (1.0 / (4 * sqrt(pi) * psi * rh)) * (1 - exp(-4 * rh * rh * psi * psi) + 4 * sqrt(pi) * rh * psi * erfc(2 * rh * psi));
+    G = 0;
+    return;
+  }
+  const double r2 = r * r, a2mr = 2 * rh - r, a2pr = 2 * rh + r, rh2 = rh * rh, rh4 = rh2 * rh2, psi2 = psi * psi,
+               psi3 = psi2 * psi, psi4 = psi2 * psi2, r3 = r2 * r, r4 = r3 * r, sp = sqrt(M_PI);
+  double f0, f1, f2, f3, f4, f5, f6, f7, g0, g1, g2, g3, g4, g5, g6, g7;
+  if (r > 2 * rh) {
+    f0 = (64.0 * rh4 * psi4 + 96.0 * rh2 * r2 * psi4 - 128.0 * rh * r3 * psi4 + 36.0 * r4 * psi4 - 3.0) / (128.0 * rh * r3 * psi4);
+    f4 = (3.0 - 4.0 * psi4 * a2mr * a2mr * (4.0 * rh2 + 4.0 * rh * r + 9.0 * r2)) / (256.0 * rh * r3 * psi4);
+    f5 = 0;
+    g0 = (-64.0 * rh4 * psi4 + 96.0 * rh2 * r2 * psi4 - 64.0 * rh * r3 * psi4 + 12.0 * r4 * psi4 + 3.0) / (64.0 * rh * r3 * psi4);
+    g4 = (4.0 * psi4 * a2mr * a2mr * a2mr * (2.0 * rh + 3.0 * r) - 3.0) / (128.0 * rh * r3 * psi4);
+    g5 = 0;
+  } else {
+    f0 = (-16.0 * rh4 - 24.0 * rh2 * r2 + 32.0 * rh * r3 - 9.0 * r4) / (32.0 * rh * r3);
+    f4 = 0;
+    f5 = (4.0 * psi4 * a2mr * a2mr * (4.0 * rh2 + 4.0 * rh * r + 9.0 * r2) - 3.0) / (256.0 * rh * r3 * psi4);
+    g0 = a2mr * a2mr * a2mr * (2.0 * rh + 3.0 * r) / (16.0 * rh * r3);
+    g4 = 0;
+    g5 = (3.0 - 4.0 * psi4 * a2mr * a2mr * a2mr * (2.0 * rh + 3.0 * r)) / (128.0 * rh * r3 * psi4);
+  }
+  f1 = (-2.0 * psi2 * a2pr * (4.0 * rh2 - 4.0 * rh * r + 9.0 * r2) + 2.0 * rh - 3.0 * r) / (128.0 * rh * r3 * psi3 * sp);
+  f2 = (2.0 * psi2 * a2mr * (4.0 * rh2 + 4.0 * rh * r + 9.0 * r2) - 2.0 * rh - 3.0 * r) / (128.0 * rh * r3 * psi3 * sp);
+  f3 = 3.0 * (6.0 * r2 * psi2 + 1.0) / (64.0 * sp * rh * r2 * psi3);
+  f6 = (4.0 * psi4 * a2pr * a2pr * (4.0 * rh2 - 4.0 * rh * r + 9.0 * r2) - 3.0) / (256.0 * rh * r3 * psi4);
+  f7 = 3.0 * (1.0 - 12.0 * r4 * psi4) / (128.0 * rh * r3 * psi4);
+  g1 = (2.0 * psi2 * a2pr * a2pr * (2.0 * rh - 3.0 * r) - 2.0 * rh + 3.0 * r) / (64.0 * sp * rh * r3 * psi3);
+  g2 = (-2.0 * psi2 * a2mr * a2mr * (2.0 * rh + 3.0 * r) + 2.0 * rh + 3.0 * r) / (64.0 * sp * rh * r3 * psi3);
+  g3 = (3.0 * (2.0 * r2 * psi2 - 1.0)) / (32.0 * sp * rh * r2 * psi3);
+  g6 = (3.0 - 4.0 * psi4 * (2.0 * rh - 3.0 * r) * a2pr * a2pr * a2pr) / (128.0 * rh * r3 * psi4);
+  g7 = -3.0 * (4.0 * r4 * psi4 + 1.0) / (64.0 * rh * r3 * psi4);
+  auto comb = [&](double c0, double c1, double c2, double c3, double c4, double c5, double c6, double c7) {
+    return c0 + c1 * exp(-psi2 * a2pr * a2pr) + c2 * exp(-a2mr * a2mr * psi2) + c3 * exp(-psi2 * r2) + c4 * erfc(a2mr * psi) +
+           c5 * erfc(-a2mr * psi) + c6 * erfc(a2pr * psi) + c7 * erfc(r * psi);
+  };
+  F = comb(f0, f1, f2, f3, f4, f5, f6, f7);
+  G = comb(g0, g1, g2, g3, g4, g5, g6, g7);
+}
+
+template <class T> struct PseState {
+  using C = typename Vec2<T>::type;
+  using T4 = typename Real4<T>::type;
+  // parameters (stored in `real` like the reference's members)
+  T Lb[3];
+  T viscosity, rh, psi, tolerance, shear;
+  uint32_t seedNear = 0, seedFar = 0;
+  // far field
+  Fft3dPlan<T> plan;
+  IbmState<T> ibm;
+  DevBuf grid;
+  T eta = 0;
+  int support = 0;
+  // near field
+  T rcut = 0;
+  DevBuf table;
+  int nTable = 0;
+  ub200_celllist *cl = nullptr;
+  DevBuf posF, sortedPos, sortedV;
+  int nearN = -1;
+  // Lanczos
+  GrowBuf V;
+  DevBuf w, oldBz, z, partial, scalar, coeff;
+  int checkConvergenceSteps = 3, iterationHardLimit = 200, lastRunRequiredSteps = 0;
+
+  int init(const ub200_pse_params &par, uint32_t seedNear_, uint32_t seedFar_) {
+    for (int d = 0; d < 3; d++) Lb[d] = (T)par.L[d];
+    viscosity = (T)par.viscosity; rh = (T)par.hydrodynamicRadius; psi = (T)par.psi; tolerance = (T)par.tolerance;
+    shear = (T)par.shearStrain;
+    seedNear = seedNear_; seedFar = seedFar_;
+    if (Lb[0] <= 0 || Lb[1] <= 0 || Lb[2] <= 0 || par.tolerance <= 0 || par.tolerance > 0.1 || par.psi <= 0) return UB200_ERR_INVALID_ARGUMENT;
+    int rc;
+    // ---- near field: NearField::initializeDeterministicPart (NearField.cuh:65-102) ----
+    const double split = psi;
+    rcut = (T)(sqrt(-log((double)tolerance)) / split);
+    if (0.5 * Lb[0] < rcut) return UB200_ERR_INVALID_ARGUMENT; // "Cut off is too large, try increasing psi"
+    const double a = rh;
+    const T textureTolerance = (T)(a * tolerance);
+    const unsigned maximumTextureElements = 1u << 22;
+    unsigned nPointsTable = (unsigned)std::min((double)(rcut / textureTolerance + 0.5), 4e9);
+    nPointsTable = std::min(maximumTextureElements, std::max(1u << 14, nPointsTable));
+    nTable = (int)nPointsTable;
+    {
+      // RPYPSE_near(rh, psi, 6 pi a vis, rcut) takes `real` arguments; TabulatedFunction(table, N = nPointsTable, 0, rcut)
+      const double rhd = (double)(T)a, psid = (double)(T)split, norm = (double)(T)(6 * M_PI * a * viscosity), rcd = (double)rcut;
+      const int Ntable = nTable - 1;
+      std::vector<C> h((size_t)Ntable + 2);
+      for (int i = 0; i <= Ntable; i++) {
+        const double x = (i / (double)Ntable) * ((double)rcut - 0.0) + 0.0;
+        double F, G;
+        rpyNearFG(x, rhd, psid, rcd, F, G);
+        h[i] = mk2<T>((T)(F / norm), (T)(G / norm));
+      }
+      h[Ntable + 1] = mk2<T>(T(0), T(0));
+      if ((rc = table.reserve(sizeof(C) * h.size()))) return rc;
+      UB200_CUDA(cudaMemcpy(table.p, h.data(), sizeof(C) * h.size(), cudaMemcpyHostToDevice));
+    }
+    if ((rc = ub200_celllist_create(&cl))) return rc;
+    // ---- far field: FarField::initializeGrid / initializeKernel (FarField.cuh:605-654) ----
+    const T kcut = T(2) * psi * (T)sqrt(-log(tolerance));
+    const double hgrid = 2 * M_PI / kcut;
+    int cells[3];
+    for (int d = 0; d < 3; d++) {
+      cells[d] = (int)(T(2) * Lb[d] / (T)hgrid) + 1;
+      cells[d] = nextFFTWiseSize(cells[d]);
+      if (cells[d] < 0) return UB200_ERR_GRID_TOO_LARGE;
+    }
+    if (par.cellsOverride[0] > 0) for (int d = 0; d < 3; d++) cells[d] = par.cellsOverride[d];
+    const double C0 = 0.976;
+    double m = 1;
+    while (erfc(m / sqrt(2)) > 0.1 * tolerance) m += 0.01;
+    int sup;
+    while ((sup = int(pow(m / C0, 2) / M_PI + 0.5) + 1) % 2 == 0) m += tolerance;
+    int P = sup / 2;
+    const int minCellDim = std::min({cells[0], cells[1], cells[2]});
+    if (sup > minCellDim) {
+      sup = minCellDim;
+      if (sup % 2 == 0) sup--;
+      P = sup / 2;
+      m = C0 * sqrt(M_PI * sup);
+    }
+    const double pw = 2 * P + 1;
+    const T cs[3] = {Lb[0] / (T)cells[0], Lb[1] / (T)cells[1], Lb[2] / (T)cells[2]};
+    const double h = std::min({cs[0], cs[1], cs[2]});
+    const double wgauss = pw * h / 2.0;
+    eta = (T)pow(2.0 * psi * wgauss / m, 2);
+    support = 2 * P + 1;
+    if (support > kMaxSupport) return UB200_ERR_UNSUPPORTED;
+    // pse_ns::Kernel(P, width = sqrt(eta)/(2 psi)) (FarField.cuh:25-41), members stored as real
+    const T width = (T)(sqrt(eta) / (2.0 * psi));
+    ub200_ibm_kernel k;
+    k.kind = UB200_KERNEL_GAUSSIAN;
+    k.support = support;
+    k.h = h;
+    k.prefactor = (double)(T)cbrt(1.0 / (width * width * width * pow(2.0 * M_PI, 1.5)));
+    k.tau = (double)(T)(-0.5 / (width * width));
+    k.rmax = INFINITY; // the PSE window has no cut-off inside its support
+    if ((rc = plan.init(cells[0], cells[1], cells[2]))) return rc;
+    const int periodic[3] = {1, 1, 1};
+    const double Ld[3] = {par.L[0], par.L[1], par.L[2]};
+    if ((rc = ibm.init(Ld, periodic, cells, k, plan.nxPad))) return rc;
+    ibm.nodeCentric = false;
+    if ((rc = grid.reserve(plan.gridBytes()))) return rc;
+    return UB200_OK;
+  }
+  void release() {
+    plan.release(); ibm.release(); grid.release(); table.release(); posF.release(); sortedPos.release(); sortedV.release();
+    V.release(); w.release(); oldBz.release(); z.release(); partial.release(); scalar.release(); coeff.release();
+    if (cl) ub200_celllist_destroy(cl);
+    cl = nullptr;
+  }
+
+  // ---------------- far field ----------------
+  int farMdot(const void *pos, const void *force, int N, double temperature, double prefactor, uint32_t seed2, void *MF3,
+              cudaStream_t st) {
+    int rc;
+    T *g = grid.as<T>();
+    const bool det = force != nullptr;
+    if (!det && !(temperature > 0)) return UB200_OK; // nothing to add
+    if (det) {
+      if ((rc = ibm.spread(pos, force, 4, N, g, false, st))) return rc;
+      if ((rc = launchPassX<T, true>(plan, g, st))) return rc;
+      if ((rc = launchPassY<T, -1>(plan, g, st))) return rc;
+    } else {
+      UB200_CUDA(cudaMemsetAsync(g, 0, plan.gridBytes(), st));
+    }
+    PseSpectralOp<T> op;
+    op.nx = plan.nx; op.ny = plan.ny; op.nz = plan.nz; op.nkx = plan.nkx;
+    op.kfx = T(2.0) * T(M_PI) / Lb[0]; op.kfy = T(2.0) * T(M_PI) / Lb[1]; op.kfz = T(2.0) * T(M_PI) / Lb[2];
+    op.shear = shear; op.rh = rh; op.vis = viscosity; op.split = psi; op.eta = eta;
+    op.nTot = (T)(plan.nx * plan.ny * plan.nz);
+    op.deterministic = det;
+    op.noise = temperature > 0;
+    op.seed1 = seedFar; op.seed2 = seed2;
+    // addBrownianNoise (FarField.cuh:467-492): prefactor * sqrt(2 T / dV)
+    op.noisePrefactor = op.noise ? (T)prefactor * (T)sqrt(2 * (T)temperature / ibm.grid.cellVolume) : T(0);
+    if ((rc = launchPassZ<T, 0, PseSpectralOp<T>>(plan, g, st, op))) return rc;
+    if ((rc = launchPassY<T, +1>(plan, g, st))) return rc;
+    if ((rc = launchPassX<T, false>(plan, g, st))) return rc;
+    return ibm.gather(pos, N, g, (T *)MF3, true, false, st); // IBM::gather accumulates (misc/IBM.cu:231-233)
+  }
+
+  // ---------------- near field ----------------
+  // NearField::updateNeighbourList (NearField.cuh:236-241) + sorted copy of the positions
+  int nearPrepare(const void *pos, int N, cudaStream_t st) {
+    int rc;
+    const double gs = shear;
+    const T safety = (T)(1 + 0.5 * gs * gs + 0.5 * sqrt(gs * gs * (gs * gs + 4.0))); // cutOffShearedSafetyFactor :24-27
+    const float Lf[3] = {(float)Lb[0], (float)Lb[1], (float)Lb[2]};
+    int cd[3];
+    if ((rc = ub200_neighbour_celldim_f32(Lf, (float)(rcut * safety), cd))) return rc;
+    const int periodic[3] = {1, 1, 1};
+    const void *posf = pos;
+    if (sizeof(T) == 8) {
+      if ((rc = posF.reserve(sizeof(float4) * (size_t)N))) return rc;
+      pseToFloat4<<<(N + 255) / 256, 256, 0, st>>>((const double4 *)pos, posF.as<float4>(), N);
+      UB200_LAUNCHED();
+      posf = posF.p;
+    }
+    if ((rc = ub200_celllist_build_f32(cl, posf, nullptr, N, Lf, periodic, cd, st))) return rc;
+    if ((rc = sortedPos.reserve(sizeof(T) * 3 * (size_t)N))) return rc;
+    if ((rc = sortedV.reserve(sizeof(T) * 3 * (size_t)N))) return rc;
+    pseGatherSorted<T4, T><<<(N + 255) / 256, 256, 0, st>>>(cl->groupIndex.as<int>(), (const T4 *)pos, (const T *)nullptr, 0, N,
+                                                           sortedPos.as<T>(), (T *)nullptr);
+    UB200_LAUNCHED();
+    nearN = N;
+    return UB200_OK;
+  }
+  // Mv (+)= M_near v with the list of the last nearPrepare
+  int nearDot(const T *v, int vStride, int N, T *Mv3, bool accumulate, cudaStream_t st) {
+    if (nearN != N) return UB200_ERR_NOT_BUILT;
+    pseGatherSorted<T4, T><<<(N + 255) / 256, 256, 0, st>>>(cl->groupIndex.as<int>(), (const T4 *)nullptr, v, vStride, N,
+                                                           (T *)nullptr, sortedV.as<T>());
+    UB200_LAUNCHED();
+    TableView<T> tb;
+    tb.table = table.as<C>(); tb.Ntable = nTable - 1; tb.rmin = T(0); tb.rmax = rcut;
+    tb.interval = (T)(1.0 / (rcut - T(0))); tb.dr = (T)(1.0 / (T)(nTable - 1));
+    NearGeom<T> q;
+    q.Lx = Lb[0]; q.Ly = Lb[1]; q.Lz = Lb[2]; q.shear = shear; q.rcut2 = rcut * rcut;
+    const size_t smem = (size_t)kPairWarps * kNearCap * 6 * sizeof(T);
+    const int needed = (cl->ncells + kPairWarps - 1) / kPairWarps;
+    const int gridSize = std::min(needed, kNumSMs * 4);
+    if (accumulate)
+      rpyNearTraversal<T, true><<<gridSize, kPairThreads, smem, st>>>(sortedPos.as<T>(), sortedV.as<T>(), cl->groupIndex.as<int>(),
+                                                                     cl->binStart.as<uint32_t>(), cl->grid, cl->ncells, tb, q, Mv3);
+    else
+      rpyNearTraversal<T, false><<<gridSize, kPairThreads, smem, st>>>(sortedPos.as<T>(), sortedV.as<T>(), cl->groupIndex.as<int>(),
+                                                                      cl->binStart.as<uint32_t>(), cl->grid, cl->ncells, tb, q, Mv3);
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+
+  // ---------------- Lanczos ----------------
+  int dotHost(const T *a, const T *b, size_t n, double *out, cudaStream_t st) {
+    redDotPartial<T><<<kRedBlocks, kRedThreads, 0, st>>>(a, b, n, partial.as<double>());
+    UB200_LAUNCHED();
+    redFinal<<<1, kRedThreads, 0, st>>>(partial.as<double>(), kRedBlocks, scalar.as<double>());
+    UB200_LAUNCHED();
+    UB200_CUDA(cudaMemcpyAsync(out, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    UB200_CUDA(cudaStreamSynchronize(st));
+    return UB200_OK;
+  }
+  int axpby(T alpha, const T *x, T beta, T *y, size_t n, cudaStream_t st) {
+    vecAxpby<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(alpha, x, beta, y, n);
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+
+  // lanczos::Solver::run (LanczosAlgorithm.cu:202-228) with KrylovSubspace (:27-173); matrix = near-field mobility
+  int lanczosSqrt(const T *zin, T *Bz, int N, double tol, int *iterations, cudaStream_t st) {
+    const size_t n = 3 * (size_t)N;
+    int rc;
+    if ((rc = w.reserve(sizeof(T) * n)) || (rc = oldBz.reserve(sizeof(T) * n)) || (rc = partial.reserve(sizeof(double) * kRedBlocks)) ||
+        (rc = scalar.reserve(sizeof(double))) || (rc = coeff.reserve(sizeof(T) * (iterationHardLimit + 2))))
+      return rc;
+    UB200_CUDA(cudaMemsetAsync(oldBz.p, 0, sizeof(T) * n, st));
+    std::vector<double> hdiag, hsup;
+    double nz2;
+    if ((rc = dotHost(zin, zin, n, &nz2, st))) return rc;
+    const T normz = (T)sqrt(nz2);
+    if ((rc = V.grow(sizeof(T) * n * 8, st))) return rc;
+    if ((rc = axpby((T)(1.0 / normz), zin, T(0), (T *)V.p, n, st))) return rc;
+    const int checkSteps = std::min(checkConvergenceSteps, iterationHardLimit - 2);
+    for (int i = 0; i < iterationHardLimit; i++) {
+      if ((rc = V.grow(sizeof(T) * n * (size_t)(i + 2), st))) return rc;
+      T *Vm = (T *)V.p, *dw = w.as<T>();
+      if ((rc = nearDot(Vm + n * i, 3, N, dw, false, st))) return rc;                    // w = M v_i
+      if (i > 0 && (rc = axpby((T)(-hsup[i - 1]), Vm + n * (i - 1), T(1), dw, n, st))) return rc;
+      double hd;
+      if ((rc = dotHost(dw, Vm + n * i, n, &hd, st))) return rc;
+      hdiag.push_back((double)(T)hd);
+      if ((rc = axpby((T)(-hdiag[i]), Vm + n * i, T(1), dw, n, st))) return rc;
+      double hs2;
+      if ((rc = dotHost(dw, dw, n, &hs2, st))) return rc;
+      double hs = (double)(T)sqrt(hs2);
+      const T tolw = (T)(1e-3 * hdiag[i] / normz);
+      if (hs < tolw) hs = 0.0;
+      hsup.push_back(hs);
+      if (hs > 0.0) {
+        if ((rc = axpby((T)(1.0 / hs), dw, T(0), Vm + n * (i + 1), n, st))) return rc;
+      } else { // w = e1
+        UB200_CUDA(cudaMemsetAsync(Vm + n * (i + 1), 0, sizeof(T) * n, st));
+        const T one = T(1);
+        UB200_CUDA(cudaMemcpyAsync(Vm + n * (i + 1), &one, sizeof(T), cudaMemcpyHostToDevice, st));
+      }
+      if (i >= checkSteps) {
+        // Bz = ||z|| V_m H^1/2 e1 (computeCurrentResultEstimation :163-172, computeSquareRoot :63-80)
+        const int m = i + 1;
+        std::vector<double> d(hdiag.begin(), hdiag.begin() + m), e(hsup.begin(), hsup.begin() + m), Z;
+        if (!tridiagEigen(m, d, e, Z)) return UB200_ERR_UNSUPPORTED;
+        std::vector<double> tmp(m);
+        for (int j = 0; j < m; j++) tmp[j] = sqrt(std::max(d[j], 0.0)) * Z[(size_t)j * m];
+        std::vector<T> c(m);
+        for (int r = 0; r < m; r++) {
+          double s = 0;
+          for (int j = 0; j < m; j++) s += Z[(size_t)j * m + r] * tmp[j];
+          c[r] = (T)s;
+        }
+        UB200_CUDA(cudaMemcpyAsync(coeff.p, c.data(), sizeof(T) * m, cudaMemcpyHostToDevice, st));
+        UB200_CUDA(cudaStreamSynchronize(st)); // c is a local
+        vecGemv<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Vm, n, m, coeff.as<T>(), normz, Bz);
+        UB200_LAUNCHED();
+        if (i > 0) { // computeError (:231-250): ||Bz_i - Bz_{i-1}|| / ||Bz_{i-1}||
+          double prev2, yy2;
+          if ((rc = dotHost(oldBz.as<T>(), oldBz.as<T>(), n, &prev2, st))) return rc;
+          if ((rc = axpby(T(-1), Bz, T(1), oldBz.as<T>(), n, st))) return rc;
+          if ((rc = dotHost(oldBz.as<T>(), oldBz.as<T>(), n, &yy2, st))) return rc;
+          const double err = fabs(sqrt(yy2) / sqrt(prev2));
+          if (std::isnan(err)) return UB200_ERR_UNSUPPORTED;
+          if (err <= tol) {
+            lastRunRequiredSteps = i;
+            if (i - 2 > checkConvergenceSteps) checkConvergenceSteps += 1;
+            else checkConvergenceSteps = std::max(1, checkConvergenceSteps - 2);
+            if (iterations) *iterations = i;
+            return UB200_OK;
+          }
+        }
+        UB200_CUDA(cudaMemcpyAsync(oldBz.p, Bz, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    return UB200_ERR_UNSUPPORTED; // "[Lanczos] Could not converge"
+  }
+
+  // NearField::computeStochasticDisplacements (NearField.cuh:254-282): BdW = prefactor sqrt(2 T) M_near^1/2 dW
+  int nearNoise(const void *pos, int N, double temperature, double prefactor, uint32_t seed2, void *BdW3, int *iterations,
+                cudaStream_t st) {
+    if (iterations) *iterations = 0;
+    if (temperature == 0.0) return UB200_OK;
+    int rc;
+    if ((rc = nearPrepare(pos, N, st))) return rc;
+    if ((rc = z.reserve(sizeof(T) * 3 * (size_t)N))) return rc;
+    const T noisePrefactor = (T)prefactor * (T)sqrt(2 * (T)temperature);
+    pseNearNoise<T><<<(N + 255) / 256, 256, 0, st>>>(z.as<T>(), N, noisePrefactor, seedNear, seed2);
+    UB200_LAUNCHED();
+    return lanczosSqrt(z.as<T>(), (T *)BdW3, N, (double)tolerance, iterations, st);
+  }
+};
+
+} // namespace ub200
+
+using namespace ub200;
+
+struct ub200_pse {
+  int precision;
+  PseState<float> f;
+  PseState<double> d;
+};
+
+#define PSE_DISPATCH(h, call) ((h)->precision == 4 ? (h)->f.call : (h)->d.call)
+
+extern "C" {
+
+int ub200_pse_create(ub200_pse **out, int precisionBytes, const ub200_pse_params *par, uint32_t seedNear, uint32_t seedFar) {
+  if (!out || !par || (precisionBytes != 4 && precisionBytes != 8)) return UB200_ERR_INVALID_ARGUMENT;
+  ub200_pse *h = new (std::nothrow) ub200_pse();
+  if (!h) return UB200_ERR_ALLOC;
+  h->precision = precisionBytes;
+  const int rc = precisionBytes == 4 ? h->f.init(*par, seedNear, seedFar) : h->d.init(*par, seedNear, seedFar);
+  if (rc) { h->f.release(); h->d.release(); delete h; return rc; }
+  *out = h;
+  return UB200_OK;
+}
+int ub200_pse_destroy(ub200_pse *h) {
+  if (!h) return UB200_OK;
+  h->f.release(); h->d.release();
+  delete h;
+  return UB200_OK;
+}
+int ub200_pse_info(ub200_pse *h, ub200_pse_info_t *info) {
+  if (!h || !info) return UB200_ERR_INVALID_ARGUMENT;
+  const bool f = h->precision == 4;
+  info->cells[0] = f ? h->f.plan.nx : h->d.plan.nx;
+  info->cells[1] = f ? h->f.plan.ny : h->d.plan.ny;
+  info->cells[2] = f ? h->f.plan.nz : h->d.plan.nz;
+  info->support = f ? h->f.support : h->d.support;
+  info->eta = f ? (double)h->f.eta : h->d.eta;
+  info->rcut = f ? (double)h->f.rcut : h->d.rcut;
+  info->nTable = f ? h->f.nTable : h->d.nTable;
+  info->lastLanczosIterations = f ? h->f.lastRunRequiredSteps : h->d.lastRunRequiredSteps;
+  info->d_table = f ? h->f.table.p : h->d.table.p;
+  info->d_grid = f ? h->f.grid.p : h->d.grid.p;
+  return UB200_OK;
+}
+int ub200_pse_set_shear_strain(ub200_pse *h, double strain) {
+  if (!h) return UB200_ERR_INVALID_ARGUMENT;
+  h->f.shear = (float)strain; h->d.shear = strain;
+  return UB200_OK;
+}
+int ub200_pse_far_mdot(ub200_pse *h, const void *d_pos, const void *d_force, int N, double temperature, double prefactor,
+                       uint32_t seed2, void *d_MF3, void *stream) {
+  if (!h || !d_pos || !d_MF3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return PSE_DISPATCH(h, farMdot(d_pos, d_force, N, temperature, prefactor, seed2, d_MF3, (cudaStream_t)stream));
+}
+int ub200_pse_near_mdot(ub200_pse *h, const void *d_pos, const void *d_v, int vStride, int N, void *d_Mv3, void *stream) {
+  if (!h || !d_pos || !d_Mv3 || N <= 0 || (vStride != 3 && vStride != 4)) return UB200_ERR_INVALID_ARGUMENT;
+  if (!d_v) return UB200_OK; // NearField::Mdot skips when there are no forces
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (h->precision == 4) {
+    if ((rc = h->f.nearPrepare(d_pos, N, st))) return rc;
+    return h->f.nearDot((const float *)d_v, vStride, N, (float *)d_Mv3, true, st);
+  }
+  if ((rc = h->d.nearPrepare(d_pos, N, st))) return rc;
+  return h->d.nearDot((const double *)d_v, vStride, N, (double *)d_Mv3, true, st);
+}
+int ub200_pse_near_noise(ub200_pse *h, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
+                         void *d_BdW3, int *iterations, void *stream) {
+  if (!h || !d_pos || !d_BdW3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return PSE_DISPATCH(h, nearNoise(d_pos, N, temperature, prefactor, seed2, d_BdW3, iterations, (cudaStream_t)stream));
+}
+}
