@@ -100,18 +100,26 @@ def test_fluctuation_dissipation(cuda):
     assert np.abs(dx2 / ntest - want).max() < max(1e-2, 4 * want * math.sqrt(2.0 / ntest))
 
 
-@pytest.mark.parametrize("shear", [0.0, 0.2])
-def test_parity_vs_reference_fp64(cuda, tmp_path, shear):
-    N, L, vis, a, tol, psi, T, dt, sysseed = 20000, 64.0, 1.3, 1.1, 1e-6, 0.6, 0.7, 0.01, 4242
+@pytest.mark.parametrize("shear,T", [(0.0, 0.0), (0.2, 0.0), (0.0, 0.7), (0.2, 0.7)])
+def test_parity_vs_reference_fp64(cuda, tmp_path, shear, T):
+    N, L, vis, a, tol, psi, dt, sysseed = 20000, 64.0, 1.3, 1.1, 1e-6, 0.6, 0.01, 4242
     pos, force = _cloud(N, L, 31)
     rfar, rnear, rbdw, info = _run_ref(tmp_path, "ref_pse", N, L, vis, a, tol, psi, shear, T, dt, sysseed, pos, force)
     far, near, bdw, m = _ours(cuda, L, vis, a, tol, psi, shear, T, dt, sysseed, pos, force)
     assert abs(m.getSelfMobility() - info["M0"]) < 1e-15
-    print(f"[pse fp64 shear={shear}] far {_rel(far, rfar):.2e} near {_rel(near, rnear):.2e} bdw {_rel(bdw, rbdw):.2e} "
+    print(f"[pse fp64 shear={shear} T={T}] far {_rel(far, rfar):.2e} near {_rel(near, rnear):.2e} "
           f"lanczos iterations {m.info().lastLanczosIterations}")
-    assert _rel(far, rfar) < 1e-10      # includes the far-field noise: same Saru streams, same float Box-Muller
     assert _rel(near, rnear) < 1e-12
-    assert _rel(bdw, rbdw) < 20 * tol   # two Lanczos runs stopped by the same criterion at tolerance tol
+    if T == 0:
+        assert _rel(far, rfar) < 1e-11
+        assert np.all(bdw == 0) and np.all(rbdw == 0)
+    else:
+        # Far-field noise: same Saru streams and float Box-Muller, but the reference adds the conjugate partner's
+        # contribution on the kx = 0 / nx/2 planes with a second NON-ATOMIC "+=" from another thread (FarField.cuh:283,
+        # :305): a benign-looking race that drops a few updates per call. We compute the race-free sum.
+        assert _rel(far, rfar) < 1e-7
+        print(f"[pse fp64 shear={shear} T={T}] bdw {_rel(bdw, rbdw):.2e}")
+        assert _rel(bdw, rbdw) < 20 * tol   # two Lanczos runs stopped by the same criterion at tolerance tol
 
 
 def test_parity_vs_reference_fp32_config3_shape(cuda, tmp_path):
