@@ -191,6 +191,29 @@ int ub200_bdhi_euler_update(int precisionBytes, void *d_pos, const int *d_groupI
                             const double *K9, int N, double sqrt2Tdt, double dt, int is2D, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU FCM (new functionality: the reference is single-GPU). One process per GPU of one
+ * NVSwitch box; the grid is decomposed in z slabs, the 3-D FFT transposes through peer-mapped NVLink stores
+ * fused into the y / z passes (no NCCL on the data path), halo planes of the interpolation are read through
+ * peer-mapped pointers. Same semantics as ub200_fcm_mdot, every rank passes the same (replicated) positions
+ * and forces and receives the full result; the result is bit-identical to the single-GPU one.
+ * Set-up: create on every rank, exchange the ub200_fcm_dist_ipc_size()-byte blobs of ub200_fcm_dist_ipc_export
+ * between the ranks (any transport; rank order), hand all of them to ub200_fcm_dist_ipc_import.
+ * cells[1] and cells[2] must be divisible by world (<= 8); Peskin 3/4-point kernels.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_fcm_dist ub200_fcm_dist;
+int ub200_fcm_dist_create(ub200_fcm_dist **out, int precisionBytes, const double L[3], const int cells[3],
+                          const ub200_ibm_kernel *kernel, double viscosity, uint32_t seed, int rank, int world,
+                          int maxParticles);
+int ub200_fcm_dist_destroy(ub200_fcm_dist *fcm);
+int ub200_fcm_dist_ipc_size(void);
+int ub200_fcm_dist_ipc_export(ub200_fcm_dist *fcm, void *blob);
+int ub200_fcm_dist_ipc_import(ub200_fcm_dist *fcm, const void *blobsOfAllRanks);
+int ub200_fcm_dist_mdot(ub200_fcm_dist *fcm, const void *d_pos, const void *d_force, int N, double temperature,
+                        double prefactor, void *d_out3, void *stream);
+/* synchronises the stream; *flag != 0 when a peer barrier timed out (a rank died) */
+int ub200_fcm_dist_error_flag(ub200_fcm_dist *fcm, void *stream, int *flag);
+
+/* ------------------------------------------------------------------------------------------------
  * Positively Split Ewald RPY hydrodynamics. Replaces BDHI::PSE (Integrator/BDHI/BDHI_PSE.cuh:82-176) =
  * pse_ns::FarField (PSE/FarField.cuh:317-553) + pse_ns::NearField (PSE/NearField.cuh:29-282) + the Lanczos
  * square root (misc/LanczosAlgorithm/LanczosAlgorithm.cu:27-250). ub200_pse_create resolves every derived

@@ -59,3 +59,31 @@ def test_two_ranks_reproduce_single_process_trajectory(tmp_path, orc):
     ref.step(steps + 2)
     assert np.array_equal(got[:4 * N].view(np.uint32), ref.pos.ravel().view(np.uint32))
     assert np.array_equal(got[4 * N:].view(np.uint32), ref.vel.ravel().view(np.uint32))
+
+
+def _blob_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from uammd_b200.multigpu import exchange_blobs
+    blob = bytes([rank * 16 + k for k in range(8)]) + bytes(56)   # 64 bytes like a cudaIpcMemHandle_t
+    allb = exchange_blobs(blob)
+    if rank == 1:
+        open(out, "wb").write(allb)
+    dist.destroy_process_group()
+
+
+def test_slab_ranges_and_blob_exchange(tmp_path):
+    sys.path.insert(0, ROOT)
+    from uammd_b200.multigpu import slab_ranges
+    assert slab_ranges(128, 8) == [(16 * r, 16 * r + 16) for r in range(8)]
+    assert slab_ranges(64, 2) == [(0, 32), (32, 64)]
+    try:
+        slab_ranges(130, 8)
+        assert False
+    except ValueError:
+        pass
+    out = str(tmp_path / "blobs.bin")
+    mp.spawn(_blob_worker, args=(2, 29519, out), nprocs=2, join=True)
+    b = open(out, "rb").read()
+    assert len(b) == 128 and b[:8] == bytes(range(8)) and b[64:72] == bytes(range(16, 24))

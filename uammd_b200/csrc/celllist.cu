@@ -146,6 +146,7 @@ scatterToBins(const uint2 *__restrict__ codeSlot, const uint32_t *__restrict__ b
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const uint2 cs = codeSlot[i];
+  if (cs.x == 0xffffffffu) return; // particle outside the caller's window (slab-decomposed IBM)
   unstable[binStart[cs.x] + cs.y] = i;
 }
 

@@ -1,0 +1,300 @@
+// Slab-decomposed Force Coupling Method over the GPUs of one NVSwitch box (one process per GPU), sm_100a.
+//
+// The reference is single-GPU; the oracle of this path is the single-GPU result on the same input,
+// which it reproduces bit for bit (same kernels, same per-node summation order, same noise stream keyed on the
+// GLOBAL Fourier index).
+//
+// Rank r owns the z planes [r nzl, (r+1) nzl) of the grid (buffer S) and the particles whose cell lies in them;
+// positions / forces are replicated (every rank receives the same arrays), so spreading needs no communication:
+// a rank bins the particles of its planes plus one support of halo cells and writes its planes once.
+//   bin (window) + scan + scatter + order   local
+//   spread bricks -> S                       local, atomic-free
+//   FFT x, FFT y                             local lines; the y pass STORES its output into the owners' transposed
+//                                            buffers T over NVLink (the all-to-all is the pass's store, no NCCL, no pack)
+//   --- barrier ---
+//   fused [FFT z, Stokes, noise, iFFT z]     on T = [nz][nyl][nkx] (ky rows of this rank); stores go straight back
+//                                            into the owners' S
+//   --- barrier ---
+//   iFFT y, iFFT x                           local
+//   --- barrier ---
+//   gather                                   owned particles; support planes of the neighbouring slabs are read
+//                                            through peer-mapped pointers; each result row is pushed to every rank
+//   --- barrier ---
+// Buffers S, T, the result and the barrier flags of a rank live in ONE cudaMalloc allocation exported to the peers
+// through CUDA IPC (ub200_fcm_dist_ipc_export / _import; the caller moves the 64-byte handles, e.g. with
+// torch.distributed.all_gather_object). Barriers are one-block kernels that publish an epoch to every peer's flag
+// array with system-scope release stores and spin (bounded) on their own array.
+#include "fcm_op.cuh"
+#include "fft3d.cuh"
+#include "ibm_state.cuh"
+#include <cstring>
+
+namespace ub200 {
+
+constexpr unsigned long long kBarrierSpinLimit = 400000000ull; // ~ seconds; a lost peer must not hang the GPU forever
+
+// flags[p] of rank r = last epoch rank p announced to r. err: set when the spin limit is hit.
+__global__ void __launch_bounds__(32) peerBarrier(PeerTable<uint32_t> flags, int rank, int world, uint32_t epoch, int *err) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  __threadfence_system();
+  volatile uint32_t *remote = flags.p[p] + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const uint32_t *mine = flags.p[rank] + p;
+  unsigned long long spins = 0;
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    if (++spins > kBarrierSpinLimit) { *err = 1; break; }
+  }
+  __threadfence_system();
+}
+
+template <class T> struct FcmDistState {
+  using C = typename Vec2<T>::type;
+  using T4 = typename Real4<T>::type;
+  int rank = 0, world = 1;
+  int nzl = 0, nyl = 0, z0 = 0, y0 = 0;
+  int maxParticles = 0;
+  Fft3dPlan<T> plan;
+  GridT<T> grid;      // with the z window of this rank
+  IbmKernel<T> kern;
+  double viscosity = 1, L[3];
+  uint32_t seed = 0, seed2 = 0;
+  // one exported allocation: [flags | S | T | out]
+  void *arena = nullptr;
+  size_t arenaBytes = 0, offS = 0, offT = 0, offOut = 0;
+  void *peerArena[kMaxPeers] = {};
+  bool imported = false;
+  uint32_t epoch = 0;
+  DevBuf errFlag;
+  // particle scratch (window)
+  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedPos, sortedVal, sortedOrigin, sortedW;
+
+  size_t slabBytes() const { return (size_t)nzl * plan.ny * plan.nkx * 3 * sizeof(C); }
+  size_t tposeBytes() const { return (size_t)plan.nz * nyl * plan.nkx * 3 * sizeof(C); }
+  template <class U> U *at(void *base, size_t off) const { return reinterpret_cast<U *>(static_cast<char *>(base) + off); }
+
+  int init(const double L_[3], const int cells[3], const ub200_ibm_kernel &k, double vis, uint32_t seed_, int rank_, int world_,
+           int maxParticles_) {
+    rank = rank_; world = world_; maxParticles = maxParticles_;
+    if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world || maxParticles < 1) return UB200_ERR_INVALID_ARGUMENT;
+    if (cells[2] % world || cells[1] % world) return UB200_ERR_INVALID_ARGUMENT; // equal slabs in z and in ky
+    if (k.support != 3 && k.support != 4) return UB200_ERR_UNSUPPORTED;          // brick spread / sorted gather
+    int rc = plan.init(cells[0], cells[1], cells[2]);
+    if (rc) return rc;
+    nzl = cells[2] / world; nyl = cells[1] / world; z0 = rank * nzl; y0 = rank * nyl;
+    const int periodic[3] = {1, 1, 1};
+    grid = makeGridT<T>(L_, periodic, cells);
+    const int S = k.support;
+    const int hi = S / 2, lo = -(S - 1) + S / 2 - ((S & 1) ? 0 : 1);
+    if (nzl + (hi - lo) > cells[2]) return UB200_ERR_INVALID_ARGUMENT;
+    grid.zwin0 = ((z0 + lo) % cells[2] + cells[2]) % cells[2];
+    grid.zwinN = nzl + (hi - lo);
+    kern.kind = k.kind; kern.support = k.support; kern.invh = (T)(1.0 / k.h);
+    kern.prefactor = (T)k.prefactor; kern.tau = (T)k.tau; kern.rmax = (T)k.rmax;
+    for (int d = 0; d < 3; d++) L[d] = L_[d];
+    viscosity = vis; seed = seed_;
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    offS = align(4096);
+    offT = offS + align(slabBytes());
+    offOut = offT + align(tposeBytes());
+    arenaBytes = offOut + align(sizeof(T) * 3 * (size_t)maxParticles);
+    if (cudaMalloc(&arena, arenaBytes) != cudaSuccess) return UB200_ERR_ALLOC;
+    UB200_CUDA(cudaMemset(arena, 0, arenaBytes));
+    if ((rc = errFlag.reserve(sizeof(int)))) return rc;
+    UB200_CUDA(cudaMemset(errFlag.p, 0, sizeof(int)));
+    const int ncw = cells[0] * cells[1] * grid.zwinN;
+    if ((rc = binCount.reserve(sizeof(uint32_t) * (size_t)ncw)) || (rc = binStart.reserve(sizeof(uint32_t) * ((size_t)ncw + 1))) ||
+        (rc = tileSums.reserve(sizeof(uint32_t) * 4096)))
+      return rc;
+    UB200_CUDA(cudaMemset(binCount.p, 0, binCount.cap));
+    UB200_CUDA(cudaDeviceSynchronize());
+    peerArena[rank] = arena;
+    return UB200_OK;
+  }
+  void release() {
+    for (int p = 0; p < world; p++)
+      if (p != rank && peerArena[p]) cudaIpcCloseMemHandle(peerArena[p]);
+    if (arena) cudaFree(arena);
+    arena = nullptr;
+    DevBuf *b[] = {&errFlag, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedPos, &sortedVal, &sortedOrigin, &sortedW};
+    for (auto *x : b) x->release();
+    plan.release();
+  }
+  int ipcExport(void *blob) {
+    cudaIpcMemHandle_t h;
+    UB200_CUDA(cudaIpcGetMemHandle(&h, arena));
+    memcpy(blob, &h, sizeof(h));
+    return UB200_OK;
+  }
+  int ipcImport(const void *blobs) {
+    for (int p = 0; p < world; p++) {
+      if (p == rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char *>(blobs) + (size_t)p * sizeof(h), sizeof(h));
+      UB200_CUDA(cudaIpcOpenMemHandle(&peerArena[p], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    imported = true;
+    return UB200_OK;
+  }
+
+  int barrier(cudaStream_t st) {
+    PeerTable<uint32_t> flags;
+    for (int p = 0; p < world; p++) flags.p[p] = at<uint32_t>(peerArena[p], 0);
+    epoch++;
+    peerBarrier<<<1, 32, 0, st>>>(flags, rank, world, epoch, errFlag.as<int>());
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+
+  int mdot(const void *pos, const void *force, int N, double temperature, double prefactor, void *out3, cudaStream_t st) {
+    if (!imported) return UB200_ERR_NOT_BUILT;
+    if (N > maxParticles) return UB200_ERR_INVALID_ARGUMENT;
+    int rc;
+    T *S = at<T>(arena, offS);
+    C *Tb = at<C>(arena, offT);
+    const bool det = force != nullptr;
+    const int nb = (N + 255) / 256;
+    const int ncw = grid.n[0] * grid.n[1] * grid.zwinN;
+    // ---- particles of the window: bin, scan, scatter, order + stencil records ----
+    if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N)) || (rc = unstable.reserve(sizeof(int) * (size_t)N)) ||
+        (rc = sortedIndex.reserve(sizeof(int) * (size_t)N)) || (rc = sortedPos.reserve(sizeof(T4) * (size_t)N)) ||
+        (rc = sortedVal.reserve(sizeof(T) * 2 * (size_t)N)) || (rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N)) ||
+        (rc = sortedW.reserve(sizeof(T) * 3 * kSmallSupport * (size_t)N)))
+      return rc;
+    ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
+    UB200_LAUNCHED();
+    if ((rc = exclusiveScanAndClear(binCount.as<uint32_t>(), ncw, binStart.as<uint32_t>(), tileSums.as<uint32_t>(), st))) return rc;
+    if ((rc = scatterToBinsLaunch(codeSlot.as<uint2>(), binStart.as<uint32_t>(), N, unstable.as<int>(), st))) return rc;
+#define UB200_ORDER(SS)                                                                                                  \
+  ibmOrderSorted<T4, SS><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(), (const T4 *)pos, \
+                                             (const T *)force, 4, N, grid, kern, sortedIndex.as<int>(), sortedPos.as<T4>(),   \
+                                             sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>())
+    if (kern.support == 3) UB200_ORDER(3); else UB200_ORDER(4);
+#undef UB200_ORDER
+    UB200_LAUNCHED();
+    AddrSlabZFused<C> az;
+    az.T = Tb; az.ny = plan.ny; az.nyl = nyl; az.nkx = plan.nkx; az.nzl = nzl; az.y0 = y0;
+    for (int p = 0; p < world; p++) az.peerS[p] = at<C>(peerArena[p], offS);
+    if (det) {
+      // ---- spread into the owned planes ----
+      dim3 grd((plan.nxPad + kBrickX - 1) / kBrickX, (grid.n[1] + kBrickY - 1) / kBrickY, (nzl + kBrickZ - 1) / kBrickZ);
+#define UB200_SPREAD(SS)                                                                                                 \
+  {                                                                                                                      \
+    auto kfn = ibmSpreadBricks<T4, SS>;                                                                                  \
+    const size_t sm = BrickGeom<T, SS>::smemBytes;                                                                       \
+    UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                         \
+    kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(), \
+                                        binStart.as<uint32_t>(), grid, plan.nxPad, S, z0, nzl);                          \
+  }
+      if (kern.support == 3) UB200_SPREAD(3) else UB200_SPREAD(4)
+#undef UB200_SPREAD
+      UB200_LAUNCHED();
+      if ((rc = launchPassX<T, true>(plan, S, st, nzl))) return rc;
+      // ---- forward y pass, output scattered into the owners' transposed buffers (NVLink stores) ----
+      AddrSlabYForward<C> ay;
+      ay.S = reinterpret_cast<C *>(S); ay.ny = plan.ny; ay.nyl = nyl; ay.nkx = plan.nkx; ay.z0 = z0;
+      for (int p = 0; p < world; p++) ay.peerT[p] = at<C>(peerArena[p], offT);
+      if ((rc = launchPassAddr<T, -1, false, NoSpectralOp>(plan, ay, nzl, st))) return rc;
+    } else {
+      UB200_CUDA(cudaMemsetAsync(Tb, 0, tposeBytes(), st));
+    }
+    if ((rc = barrier(st))) return rc;
+    // ---- fused z pass on the local ky rows; output pushed back into the owners' slabs ----
+    FcmSpectralOp<T> op;
+    op.nx = plan.nx; op.ny = plan.ny; op.nz = plan.nz; op.nkx = plan.nkx;
+    op.kfx = (T)(T(2.0) * T(M_PI) / (T)L[0]); op.kfy = (T)(T(2.0) * T(M_PI) / (T)L[1]); op.kfz = (T)(T(2.0) * T(M_PI) / (T)L[2]);
+    op.vis = (T)viscosity;
+    op.invNorm = T(1.0) / T((double)plan.nx * plan.ny * plan.nz);
+    op.deterministic = det;
+    op.noise = temperature > 0.0;
+    op.noisePrefactor = T(0);
+    op.seed1 = seed; op.seed2 = seed2;
+    op.yOff = y0;
+    if (op.noise) {
+      seed2++;
+      op.seed2 = seed2;
+      const T fourierNormalization = (T)(1.0 / ((double)plan.nx * plan.ny * plan.nz));
+      op.noisePrefactor = (T)prefactor * (T)sqrt((double)(fourierNormalization * 2 * (T)temperature / grid.cellVolume));
+    }
+    if ((rc = launchPassAddr<T, 0, true, FcmSpectralOp<T>>(plan, az, nyl, st, op))) return rc;
+    if ((rc = barrier(st))) return rc;
+    // ---- inverse y and x passes on the owned planes ----
+    AddrInPlace<C> ainv;
+    ainv.grid = reinterpret_cast<C *>(S); ainv.elemStride = (size_t)plan.nkx; ainv.otherStride = (size_t)plan.nkx * plan.ny;
+    if ((rc = launchPassAddr<T, +1, false, NoSpectralOp>(plan, ainv, nzl, st))) return rc;
+    if ((rc = launchPassX<T, false>(plan, S, st, nzl))) return rc;
+    if ((rc = barrier(st))) return rc; // the neighbours' boundary planes are final
+    // ---- gather for the owned particles, rows pushed to every rank ----
+    PeerTable<T> slabs, outs;
+    for (int p = 0; p < world; p++) { slabs.p[p] = at<T>(peerArena[p], offS); outs.p[p] = at<T>(peerArena[p], offOut); }
+    const int ngb = (N + 127) / 128;
+    if (kern.support == 3)
+      ibmGatherSortedDist<T, 3><<<ngb, 128, 0, st>>>(sortedOrigin.as<int4>(), sortedW.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
+                                                    grid, plan.nxPad, slabs, z0, nzl, world, outs);
+    else
+      ibmGatherSortedDist<T, 4><<<ngb, 128, 0, st>>>(sortedOrigin.as<int4>(), sortedW.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
+                                                    grid, plan.nxPad, slabs, z0, nzl, world, outs);
+    UB200_LAUNCHED();
+    if ((rc = barrier(st))) return rc; // every rank's rows have landed; the slabs may be overwritten by the next call
+    UB200_CUDA(cudaMemcpyAsync(out3, at<T>(arena, offOut), sizeof(T) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, st));
+    return UB200_OK;
+  }
+};
+
+} // namespace ub200
+
+using namespace ub200;
+
+struct ub200_fcm_dist {
+  int precision;
+  FcmDistState<float> f;
+  FcmDistState<double> d;
+};
+
+extern "C" {
+
+int ub200_fcm_dist_create(ub200_fcm_dist **out, int precisionBytes, const double L[3], const int cells[3],
+                          const ub200_ibm_kernel *kernel, double viscosity, uint32_t seed, int rank, int world, int maxParticles) {
+  if (!out || !L || !cells || !kernel || (precisionBytes != 4 && precisionBytes != 8)) return UB200_ERR_INVALID_ARGUMENT;
+  ub200_fcm_dist *h = new (std::nothrow) ub200_fcm_dist();
+  if (!h) return UB200_ERR_ALLOC;
+  h->precision = precisionBytes;
+  const int rc = precisionBytes == 4 ? h->f.init(L, cells, *kernel, viscosity, seed, rank, world, maxParticles)
+                                     : h->d.init(L, cells, *kernel, viscosity, seed, rank, world, maxParticles);
+  if (rc) { h->f.release(); h->d.release(); delete h; return rc; }
+  *out = h;
+  return UB200_OK;
+}
+int ub200_fcm_dist_destroy(ub200_fcm_dist *h) {
+  if (!h) return UB200_OK;
+  h->f.release(); h->d.release();
+  delete h;
+  return UB200_OK;
+}
+int ub200_fcm_dist_ipc_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+int ub200_fcm_dist_ipc_export(ub200_fcm_dist *h, void *blob) {
+  if (!h || !blob) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? h->f.ipcExport(blob) : h->d.ipcExport(blob);
+}
+int ub200_fcm_dist_ipc_import(ub200_fcm_dist *h, const void *blobs) {
+  if (!h || !blobs) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? h->f.ipcImport(blobs) : h->d.ipcImport(blobs);
+}
+int ub200_fcm_dist_mdot(ub200_fcm_dist *h, const void *d_pos, const void *d_force, int N, double temperature, double prefactor,
+                        void *d_out3, void *stream) {
+  if (!h || !d_pos || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? h->f.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream)
+                           : h->d.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream);
+}
+/* reads back (synchronising the stream) whether a peer barrier ever timed out */
+int ub200_fcm_dist_error_flag(ub200_fcm_dist *h, void *stream, int *flag) {
+  if (!h || !flag) return UB200_ERR_INVALID_ARGUMENT;
+  void *p = h->precision == 4 ? h->f.errFlag.p : h->d.errFlag.p;
+  UB200_CUDA(cudaMemcpyAsync(flag, p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  UB200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return UB200_OK;
+}
+}

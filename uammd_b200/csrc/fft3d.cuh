@@ -144,14 +144,57 @@ template <class C> __device__ __forceinline__ void cpAsync(C *smemDst, const C *
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Address policies of the strided pass: where axis point i of tile (other, kx0) is loaded from / stored to.
+// In place (one GPU): the same grid for both.
+template <class C> struct AddrInPlace {
+  C *grid;
+  size_t elemStride, otherStride; // in complex3 nodes
+  __device__ __forceinline__ const C *ld(int other, int i, int kx0) const {
+    return grid + ((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * 3;
+  }
+  __device__ __forceinline__ C *st(int other, int i, int kx0) const {
+    return grid + ((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * 3;
+  }
+};
+// Slab-decomposed 3-D FFT over `world` GPUs (NVLink peer stores, no staging copy, no NCCL): rank r owns the z planes
+// [r nzl, (r+1) nzl) in S = [nzl][ny][nkx][3] and, after the transpose, the ky rows [r nyl, (r+1) nyl) in
+// T = [nz][nyl][nkx][3]. The forward y pass loads a line from the local S and scatters its output straight into
+// the owners' T buffers (the all-to-all transpose fused into the pass's store); the fused z pass loads from the
+// local T and stores the inverse-transformed lines straight back into the owners' S buffers.
+constexpr int kFftMaxPeers = 8;
+template <class C> struct AddrSlabYForward { // axis = y, other = local z plane
+  C *S;
+  C *peerT[kFftMaxPeers];
+  int ny, nyl, nkx, z0; // z0: first global plane of this rank
+  __device__ __forceinline__ const C *ld(int other, int i, int kx0) const {
+    return S + (((size_t)other * ny + i) * nkx + kx0) * 3;
+  }
+  __device__ __forceinline__ C *st(int other, int i, int kx0) const {
+    const int r = i / nyl;
+    return peerT[r] + (((size_t)(z0 + other) * nyl + (i - r * nyl)) * nkx + kx0) * 3;
+  }
+};
+template <class C> struct AddrSlabZFused { // axis = z, other = local ky row
+  C *T;
+  C *peerS[kFftMaxPeers];
+  int ny, nyl, nkx, nzl, y0; // y0: first global ky row of this rank
+  __device__ __forceinline__ const C *ld(int other, int i, int kx0) const {
+    return T + (((size_t)i * nyl + other) * nkx + kx0) * 3;
+  }
+  __device__ __forceinline__ C *st(int other, int i, int kx0) const {
+    const int r = i / nzl;
+    return peerS[r] + (((size_t)(i - r * nzl) * ny + (y0 + other)) * nkx + kx0) * 3;
+  }
+};
+
 // MODE: -1 forward, +1 inverse, 0 fused (forward, op, inverse).
 // Persistent CTAs walk the tiles; three shared buffers rotate as {current, ping-pong scratch, prefetch}: the
 // cp.async loads of the NEXT tile are in flight while the current tile is transformed and stored, so HBM/L2
 // latency is hidden even at 3 CTAs per SM.
-template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX>
+template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX, class Addr>
 __global__ void __launch_bounds__(kFftThreads)
-fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int nRuntime, int nkx, int nOther, int tile, size_t elemStride,
-               size_t otherStride, FftAxis ax, const typename Vec2<T>::type *__restrict__ tw, Op op) {
+fftPassStrided(Addr addr, int nRuntime, int nkx, int nOther, int tile, FftAxis ax,
+               const typename Vec2<T>::type *__restrict__ tw, Op op) {
   using C = typename Vec2<T>::type;
   const int n = NFIX > 0 ? NFIX : nRuntime;
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -171,9 +214,8 @@ fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int nRuntime, int nkx,
     const int tx = t % ntx, other = t / ntx;
     const int kx0 = tx * tile;
     const int w = min(tile, nkx - kx0) * 3;
-    const C *base = grid + ((size_t)other * otherStride + kx0) * 3;
     if (gf < nf) {
-      if (gf < w) for (int i = gi; i < n; i += gstep) cpAsync(dst + gf * fstride + i, base + (size_t)i * elemStride * 3 + gf);
+      if (gf < w) for (int i = gi; i < n; i += gstep) cpAsync(dst + gf * fstride + i, addr.ld(other, i, kx0) + gf);
       else for (int i = gi; i < n; i += gstep) dst[gf * fstride + i] = mk2<T>(T(0), T(0));
     }
     cpAsyncCommit();
@@ -189,7 +231,6 @@ fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int nRuntime, int nkx,
     const int tx = t % ntx, other = t / ntx;
     const int kx0 = tx * tile;
     const int w = min(tile, nkx - kx0) * 3;
-    C *base = grid + ((size_t)other * otherStride + kx0) * 3;
     C *res;
     if (MODE <= 0) res = fftShared<T, -1, NFIX>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
     else res = fftShared<T, +1, NFIX>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
@@ -210,7 +251,7 @@ fftPassStrided(typename Vec2<T>::type *__restrict__ grid, int nRuntime, int nkx,
       res = fftShared<T, +1, NFIX>(res, other1, ax, fstride, nf, tw);
     }
     if (gf < w)
-      for (int i = gi; i < n; i += gstep) base[(size_t)i * elemStride * 3 + gf] = res[gf * fstride + i];
+      for (int i = gi; i < n; i += gstep) addr.st(other, i, kx0)[gf] = res[gf * fstride + i];
     __syncthreads(); // result consumed: current + scratch may be overwritten by the next iterations
     cur = pre;
   }
@@ -253,27 +294,28 @@ template <int NFIX> constexpr int fftThreads() { return NFIX > 0 ? 192 : kFftThr
   default: { constexpr int NFIX = 0; CALL; } break;                                                         \
   }
 
-template <class T, bool FORWARD, int NFIX> int launchPassXFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st) {
+template <class T, bool FORWARD, int NFIX> int launchPassXFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, int nzLocal) {
   auto kern = fftPassX<T, FORWARD, NFIX>;
   int rc = fftEnsureSmem<T>((const void *)kern, p.smemX);
   if (rc) return rc;
-  const int nlines = p.ny * p.nz;
+  const int nlines = p.ny * (nzLocal > 0 ? nzLocal : p.nz);
   const int nb = (nlines + p.linesPerCta - 1) / p.linesPerCta;
   kern<<<nb, fftThreads<NFIX>(), p.smemX, st>>>((T *)grid, p.nx, p.nkx, nlines, p.linesPerCta, p.ax,
                                                 p.twx.template as<typename Vec2<T>::type>());
   UB200_LAUNCHED();
   return UB200_OK;
 }
-template <class T, bool FORWARD> int launchPassX(const Fft3dPlan<T> &p, void *grid, cudaStream_t st) {
+// nzLocal > 0: only that many z planes are held in `grid` (slab decomposition)
+template <class T, bool FORWARD> int launchPassX(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, int nzLocal = 0) {
   int rc = UB200_OK;
-  UB200_FFT_DISPATCH(p.nx, (rc = launchPassXFixed<T, FORWARD, NFIX>(p, grid, st)));
+  UB200_FFT_DISPATCH(p.nx, (rc = launchPassXFixed<T, FORWARD, NFIX>(p, grid, st, nzLocal)));
   return rc;
 }
 
 template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX>
 int launchPassStridedFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op) {
   using C = typename Vec2<T>::type;
-  auto kern = fftPassStrided<T, MODE, AXIS_IS_Z, Op, NFIX>;
+  auto kern = fftPassStrided<T, MODE, AXIS_IS_Z, Op, NFIX, AddrInPlace<C>>;
   const size_t smem = AXIS_IS_Z ? p.smemZ : p.smemY;
   int rc = fftEnsureSmem<T>((const void *)kern, smem);
   if (rc) return rc;
@@ -282,14 +324,42 @@ int launchPassStridedFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, O
   const int nOther = AXIS_IS_Z ? p.ny : p.nz;
   const int threads = fftThreads<NFIX>();
   const int nblocks = persistentGrid((const void *)kern, smem, ntx * nOther, threads);
-  if (AXIS_IS_Z)
-    kern<<<nblocks, threads, smem, st>>>((C *)grid, p.nz, p.nkx, p.ny, tile, (size_t)p.nkx * p.ny, (size_t)p.nkx, p.az,
-                                         p.twz.template as<C>(), op);
-  else
-    kern<<<nblocks, threads, smem, st>>>((C *)grid, p.ny, p.nkx, p.nz, tile, (size_t)p.nkx, (size_t)p.nkx * p.ny, p.ay,
-                                         p.twy.template as<C>(), op);
+  AddrInPlace<C> addr;
+  addr.grid = (C *)grid;
+  if (AXIS_IS_Z) {
+    addr.elemStride = (size_t)p.nkx * p.ny; addr.otherStride = (size_t)p.nkx;
+    kern<<<nblocks, threads, smem, st>>>(addr, p.nz, p.nkx, p.ny, tile, p.az, p.twz.template as<C>(), op);
+  } else {
+    addr.elemStride = (size_t)p.nkx; addr.otherStride = (size_t)p.nkx * p.ny;
+    kern<<<nblocks, threads, smem, st>>>(addr, p.ny, p.nkx, nOther, tile, p.ay, p.twy.template as<C>(), op);
+  }
   UB200_LAUNCHED();
   return UB200_OK;
+}
+
+// strided pass with an explicit address policy (slab-decomposed transforms); nOther = lines of the other axis held
+// locally, n = full axis length
+template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX, class Addr>
+int launchPassAddrFixed(const Fft3dPlan<T> &p, const Addr &addr, int nOther, cudaStream_t st, Op op) {
+  using C = typename Vec2<T>::type;
+  auto kern = fftPassStrided<T, MODE, AXIS_IS_Z, Op, NFIX, Addr>;
+  const size_t smem = AXIS_IS_Z ? p.smemZ : p.smemY;
+  int rc = fftEnsureSmem<T>((const void *)kern, smem);
+  if (rc) return rc;
+  const int tile = AXIS_IS_Z ? p.tileZ : p.tileY;
+  const int ntx = (p.nkx + tile - 1) / tile;
+  const int threads = fftThreads<NFIX>();
+  const int nblocks = persistentGrid((const void *)kern, smem, ntx * nOther, threads);
+  if (AXIS_IS_Z) kern<<<nblocks, threads, smem, st>>>(addr, p.nz, p.nkx, nOther, tile, p.az, p.twz.template as<C>(), op);
+  else kern<<<nblocks, threads, smem, st>>>(addr, p.ny, p.nkx, nOther, tile, p.ay, p.twy.template as<C>(), op);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+template <class T, int MODE, bool AXIS_IS_Z, class Op, class Addr>
+int launchPassAddr(const Fft3dPlan<T> &p, const Addr &addr, int nOther, cudaStream_t st, Op op = Op()) {
+  int rc = UB200_OK;
+  UB200_FFT_DISPATCH((AXIS_IS_Z ? p.nz : p.ny), (rc = launchPassAddrFixed<T, MODE, AXIS_IS_Z, Op, NFIX, Addr>(p, addr, nOther, st, op)));
+  return rc;
 }
 
 template <class T, int MODE, class Op = NoSpectralOp>

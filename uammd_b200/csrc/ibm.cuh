@@ -50,7 +50,16 @@ template <class T> struct GridT {
   T L[3], m[3], cs[3], ics[3]; // box, minusInvBoxSize (0 = non periodic), cellSize, invCellSize
   int n[3];
   T cellVolume;
+  // z window of the cells that are binned / sorted (slab decomposition over GPUs): cells zwin0 .. zwin0+zwinN-1
+  // (periodic wrap). The whole grid on one GPU: zwin0 = 0, zwinN = n[2].
+  int zwin0, zwinN;
 };
+// window-local z of global cell plane cz (valid when < zwinN)
+template <class T> __host__ __device__ __forceinline__ int windowZ(const GridT<T> &g, int cz) {
+  int lz = cz - g.zwin0;
+  if (lz < 0) lz += g.n[2];
+  return lz;
+}
 
 template <class T> inline GridT<T> makeGridT(const double L[3], const int periodic[3], const int cells[3]) {
   GridT<T> g;
@@ -66,6 +75,8 @@ template <class T> inline GridT<T> makeGridT(const double L[3], const int period
   if (g.L[2] == T(0)) g.ics[2] = T(0);
   g.cellVolume = g.cs[0] * g.cs[1];
   if (g.n[2] > 1) g.cellVolume *= g.cs[2];
+  g.zwin0 = 0;
+  g.zwinN = g.n[2];
   return g;
 }
 
@@ -118,7 +129,9 @@ ibmBinByCell(const T4 *__restrict__ pos, int N, GridT<decltype(T4::x)> g, uint32
   cx = min(max(cx, 0), g.n[0] - 1);
   cy = min(max(cy, 0), g.n[1] - 1);
   cz = min(max(cz, 0), g.n[2] - 1);
-  const uint32_t code = (uint32_t)cx + (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)cz);
+  const int lz = windowZ(g, cz);
+  if (lz >= g.zwinN) { codeSlot[i] = make_uint2(0xffffffffu, 0u); return; }
+  const uint32_t code = (uint32_t)cx + (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)lz);
   const unsigned active = __activemask();
   const unsigned peers = __match_any_sync(active, code);
   const int lane = threadIdx.x & 31;
@@ -143,6 +156,7 @@ ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
   using T = decltype(T4::x);
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= N) return;
+  if (g.zwinN != g.n[2] && slot >= (int)binStart[g.n[0] * g.n[1] * g.zwinN]) return; // only the window's particles are sorted
   const int i = unstable[slot];
   const uint32_t code = codeSlot[i].x;
   const int s = (int)binStart[code], e = (int)binStart[code + 1];
@@ -166,7 +180,7 @@ ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
 #pragma unroll
     for (int i = 0; i < S; i++) wout[d * S + i] = supportWeight(g, k, d, pr[d], o[d], i);
   }
-  sortedOrigin[dst] = make_int4(o[0], o[1], o[2], 0);
+  sortedOrigin[dst] = make_int4(o[0], o[1], o[2], cellOfT(g, 2, pr[2])); // .w: the particle's own z plane (slab ownership)
   p.w = v0; // {x, y, z, v.x} in one record, {v.y, v.z} next to it
   sortedPos[dst] = p;
   sortedVal[2 * (size_t)dst] = v1;
@@ -197,7 +211,9 @@ __global__ void __launch_bounds__(kBrickThreads)
 ibmSpreadBricks(const T4 *__restrict__ sortedPos, const decltype(T4::x) *__restrict__ sortedVal,
                 const int4 *__restrict__ sortedOrigin, const decltype(T4::x) *__restrict__ sortedW,
                 const uint32_t *__restrict__ binStart, GridT<decltype(T4::x)> g, int nxPad,
-                decltype(T4::x) *__restrict__ grid3) {
+                decltype(T4::x) *__restrict__ grid3, int zPlane0, int nzLocal) {
+  // zPlane0 / nzLocal: the z planes [zPlane0, zPlane0 + nzLocal) this launch writes; grid3 starts at plane zPlane0
+  // (the whole grid on one GPU: 0, n[2])
   using T = decltype(T4::x);
   using G = BrickGeom<T, S>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -208,7 +224,7 @@ ibmSpreadBricks(const T4 *__restrict__ sortedPos, const decltype(T4::x) *__restr
   __shared__ int warpTot[kBrickThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = tid % kBrickY, tz = tid / kBrickY;
-  const int bx0 = blockIdx.x * kBrickX, by0 = blockIdx.y * kBrickY, bz0 = blockIdx.z * kBrickZ;
+  const int bx0 = blockIdx.x * kBrickX, by0 = blockIdx.y * kBrickY, bz0 = zPlane0 + blockIdx.z * kBrickZ;
 
   // ---- region cell populations -> exclusive prefix (block scan); thread t owns cells [t*per, (t+1)*per) ----
   constexpr int per = (G::ncells + kBrickThreads - 1) / kBrickThreads;
@@ -228,8 +244,10 @@ ibmSpreadBricks(const T4 *__restrict__ sortedPos, const decltype(T4::x) *__restr
       if (cy < 0 || cy >= g.n[1]) { if (g.m[1] != T(0)) cy += cy < 0 ? g.n[1] : -g.n[1]; else ok = false; }
       if (cz < 0 || cz >= g.n[2]) { if (g.m[2] != T(0)) cz += cz < 0 ? g.n[2] : -g.n[2]; else ok = false; }
       ok = ok && cx >= 0 && cx < g.n[0] && cy >= 0 && cy < g.n[1] && cz >= 0 && cz < g.n[2];
+      int lz = 0;
+      if (ok) { lz = windowZ(g, cz); ok = lz < g.zwinN; }
       if (ok) {
-        const uint32_t cell = (uint32_t)cx + (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)cz);
+        const uint32_t cell = (uint32_t)cx + (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)lz);
         const uint32_t s0 = __ldg(binStart + cell), s1 = __ldg(binStart + cell + 1);
         gs = (int)s0;
         cnt[q] = (int)(s1 - s0);
@@ -330,12 +348,12 @@ ibmSpreadBricks(const T4 *__restrict__ sortedPos, const decltype(T4::x) *__restr
     __syncthreads();
   }
   const int Y = by0 + ty, Z = bz0 + tz;
-  if (Y < g.n[1] && Z < g.n[2]) {
+  if (Y < g.n[1] && Z < zPlane0 + nzLocal) {
 #pragma unroll
     for (int lx = 0; lx < kBrickX; lx++) {
       const int X = bx0 + lx;
       if (X < nxPad) {
-        T *out = grid3 + 3 * ((size_t)X + (size_t)nxPad * ((size_t)Y + (size_t)g.n[1] * Z));
+        T *out = grid3 + 3 * ((size_t)X + (size_t)nxPad * ((size_t)Y + (size_t)g.n[1] * (Z - zPlane0)));
         const bool real = X < g.n[0];
         out[0] = real ? acc[lx][0] : T(0);
         out[1] = real ? acc[lx][1] : T(0);
@@ -384,6 +402,60 @@ ibmGatherSorted(const int4 *__restrict__ sortedOrigin, const T *__restrict__ sor
   T *op = out3 + 3 * (size_t)sortedIndex[slot];
   if (ACCUMULATE) { op[0] += ax; op[1] += ay; op[2] += az; }
   else { op[0] = ax; op[1] = ay; op[2] = az; }
+}
+
+// Slab-decomposed interpolation: this rank owns the z planes [z0, z0 + nzl) of the grid and the particles whose
+// cell lies in them; the sorted window also holds the neighbours' boundary particles (needed by the spread), which
+// are skipped here. Grid planes are read through a table of peer-mapped slab pointers (NVLink loads for the
+// support planes that belong to the neighbouring slabs) and the result row is pushed to every rank's copy of the
+// output (peer-mapped stores), so that all ranks hold the full result after the closing barrier.
+constexpr int kMaxPeers = 8;
+template <class T> struct PeerTable { T *p[kMaxPeers]; };
+
+template <class T, int S>
+__global__ void __launch_bounds__(128)
+ibmGatherSortedDist(const int4 *__restrict__ sortedOrigin, const T *__restrict__ sortedW,
+                    const int *__restrict__ sortedIndex, const uint32_t *__restrict__ binStart, GridT<T> g, int nxPad,
+                    PeerTable<T> slabs, int z0, int nzl, int world, PeerTable<T> outs) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= (int)binStart[g.n[0] * g.n[1] * g.zwinN]) return;
+  const int4 og = sortedOrigin[slot];
+  if (og.w < z0 || og.w >= z0 + nzl) return; // a neighbour's particle
+  const int o[3] = {og.x, og.y, og.z};
+  T w[3][S];
+  int cidx[3][S];
+  const T *wsrc = sortedW + (size_t)slot * (3 * S);
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      const int cj = wrapCell(g, d, o[d] + i);
+      cidx[d][i] = (cj >= 0 && cj < g.n[d]) ? cj : -1;
+      w[d][i] = wsrc[d * S + i];
+    }
+  T ax = T(0), ay = T(0), az = T(0);
+#pragma unroll
+  for (int kk = 0; kk < S; kk++) {
+    if (cidx[2][kk] < 0) continue;
+    const int owner = cidx[2][kk] / nzl;
+    const T *plane = slabs.p[owner] + 3 * (size_t)nxPad * g.n[1] * (size_t)(cidx[2][kk] - owner * nzl);
+#pragma unroll
+    for (int jj = 0; jj < S; jj++)
+#pragma unroll
+      for (int ii = 0; ii < S; ii++) {
+        if (cidx[0][ii] < 0 || cidx[1][jj] < 0) continue;
+        const T *gp = plane + 3 * ((size_t)cidx[0][ii] + (size_t)nxPad * (size_t)cidx[1][jj]);
+        const T wx = w[0][ii], wy = w[1][jj], wz = w[2][kk];
+        ax += g.cellVolume * (gp[0] * wx * wy * wz);
+        ay += g.cellVolume * (gp[1] * wx * wy * wz);
+        az += g.cellVolume * (gp[2] * wx * wy * wz);
+      }
+  }
+  const size_t row = 3 * (size_t)sortedIndex[slot];
+  for (int r = 0; r < world; r++) {
+    T *op = outs.p[r] + row;
+    op[0] = ax; op[1] = ay; op[2] = az;
+  }
 }
 
 // ---------------- any support: one warp per particle ----------------

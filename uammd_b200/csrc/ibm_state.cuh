@@ -90,13 +90,13 @@ template <class T> struct IbmState {
         const size_t sm = BrickGeom<T, 3>::smemBytes;
         UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(),
-                                            binStart.as<uint32_t>(), grid, nxPad, grid3);
+                                            binStart.as<uint32_t>(), grid, nxPad, grid3, 0, grid.n[2]);
       } else {
         auto kfn = ibmSpreadBricks<T4, 4>;
         const size_t sm = BrickGeom<T, 4>::smemBytes;
         UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(),
-                                            binStart.as<uint32_t>(), grid, nxPad, grid3);
+                                            binStart.as<uint32_t>(), grid, nxPad, grid3, 0, grid.n[2]);
       }
       UB200_LAUNCHED();
       return UB200_OK;

@@ -113,3 +113,81 @@ class DistributedLJMD:
                 self.eng.half(2, pb, vel_blk, fb)
             else:
                 self.eng.kick_kick_drift(pb, vel_blk, fb)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Slab-decomposed FCM (ub200_fcm_dist_*): z slabs of the grid, NVLink peer stores fused into the FFT passes.
+# ---------------------------------------------------------------------------------------------------------------
+def slab_ranges(n, world):
+    """[lo, hi) plane range of every rank (equal slabs; the C ABI requires divisibility)."""
+    if n % world:
+        raise ValueError(f"slab decomposition needs the grid dimension ({n}) divisible by the number of ranks ({world})")
+    b = n // world
+    return [(r * b, (r + 1) * b) for r in range(world)]
+
+
+def exchange_blobs(blob, group=None):
+    """All ranks' opaque set-up blobs in rank order (host-side plumbing only; works on gloo and nccl)."""
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, bytes(blob), group=group)
+    return b"".join(out)
+
+
+class DistributedFCM:
+    """FCM_impl::computeHydrodynamicDisplacements over `world` GPUs. pos / force: replicated real4 [N,4] tensors
+    (every rank passes the same data); returns the full real3 [N,3] result on every rank."""
+
+    def __init__(self, box, cells, kernel, viscosity, maxParticles, seed=1, dtype=torch.float64, group=None):
+        from . import _lib
+        from .fcm import _declare as _fcm_declare, _prec
+        from ._lib import check, d3, i3
+        self.lib, self.check = _lib.lib(), check
+        _fcm_declare()
+        vp, i, d, u32 = C.c_void_p, C.c_int, C.c_double, C.c_uint32
+        l = self.lib
+        l.ub200_fcm_dist_create.restype = i
+        l.ub200_fcm_dist_create.argtypes = [C.POINTER(vp), i, C.c_double * 3, C.c_int * 3, vp, d, u32, i, i, i]
+        l.ub200_fcm_dist_destroy.argtypes = [vp]
+        l.ub200_fcm_dist_ipc_size.restype = i
+        l.ub200_fcm_dist_ipc_export.argtypes = [vp, vp]
+        l.ub200_fcm_dist_ipc_import.argtypes = [vp, vp]
+        l.ub200_fcm_dist_mdot.restype = i
+        l.ub200_fcm_dist_mdot.argtypes = [vp, vp, vp, i, d, d, vp, vp]
+        l.ub200_fcm_dist_error_flag.argtypes = [vp, vp, C.POINTER(i)]
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        L = (box, box, box) if np.isscalar(box) else tuple(box)
+        self.cells, self.dtype = tuple(int(c) for c in cells), dtype
+        self.zrange = slab_ranges(self.cells[2], self.world)[self.rank]
+        slab_ranges(self.cells[1], self.world)
+        self._h = vp()
+        ks = kernel.struct()
+        check(l.ub200_fcm_dist_create(C.byref(self._h), _prec(dtype), d3(L), i3(self.cells), C.cast(C.byref(ks), vp),
+                                      float(viscosity), seed & 0xFFFFFFFF, self.rank, self.world, int(maxParticles)))
+        blob = C.create_string_buffer(l.ub200_fcm_dist_ipc_size())
+        check(l.ub200_fcm_dist_ipc_export(self._h, blob))
+        allb = exchange_blobs(blob.raw, group)
+        self._blobs = C.create_string_buffer(allb, len(allb))
+        check(l.ub200_fcm_dist_ipc_import(self._h, self._blobs))
+        dist.barrier(group)
+
+    def computeHydrodynamicDisplacements(self, pos, force, temperature=0.0, prefactor=0.0, out=None, stream=None):
+        from .md import _ptr, _stream_ptr
+        N = pos.shape[0]
+        if out is None:
+            out = torch.empty(N, 3, dtype=self.dtype, device=pos.device)
+        self.check(self.lib.ub200_fcm_dist_mdot(self._h, _ptr(pos), _ptr(force) if force is not None else None, N,
+                                                float(temperature), float(prefactor), _ptr(out), _stream_ptr(stream)))
+        return out
+
+    def errorFlag(self):
+        from .md import _stream_ptr
+        f = C.c_int(0)
+        self.check(self.lib.ub200_fcm_dist_error_flag(self._h, _stream_ptr(None), C.byref(f)))
+        return f.value
+
+    def close(self):
+        if self._h:
+            self.lib.ub200_fcm_dist_destroy(self._h)
+            self._h = None
