@@ -394,7 +394,16 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
                          "unit": "GB/s", "frac": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9 / world / peak, "traffic": None,
                          "note": "whole-step pipeline bytes per GPU (216 B/particle/step over all ranks); see the N=1 line for the pair kernel"},
         }
-        print(json.dumps(line))
+        line_out = line
+    fcm_line = None
+    if not args.no_fcm:
+        from uammd_b200 import fcm_bench
+        peak, _ = measured_peaks()
+        fcm_line = fcm_bench.run_distributed(dev, peak, steps=args.fcm_steps)
+    if rank == 0:
+        if fcm_line is not None:
+            line_out["fcm"] = fcm_line
+        print(json.dumps(line_out))
     dist.destroy_process_group()
     return 0
 

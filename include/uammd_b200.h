@@ -210,6 +210,8 @@ int ub200_fcm_dist_ipc_export(ub200_fcm_dist *fcm, void *blob);
 int ub200_fcm_dist_ipc_import(ub200_fcm_dist *fcm, const void *blobsOfAllRanks);
 int ub200_fcm_dist_mdot(ub200_fcm_dist *fcm, const void *d_pos, const void *d_force, int N, double temperature,
                         double prefactor, void *d_out3, void *stream);
+/* diagnostics (environment UB200_DIST_PROFILE=1, makes every call synchronous): mean ms of the 12 phases of mdot */
+int ub200_fcm_dist_profile(ub200_fcm_dist *fcm, double phases[12]);
 /* synchronises the stream; *flag != 0 when a peer barrier timed out (a rank died) */
 int ub200_fcm_dist_error_flag(ub200_fcm_dist *fcm, void *stream, int *flag);
 

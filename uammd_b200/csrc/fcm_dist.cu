@@ -27,6 +27,7 @@
 #include "fcm_op.cuh"
 #include "fft3d.cuh"
 #include "ibm_state.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace ub200 {
@@ -69,6 +70,12 @@ template <class T> struct FcmDistState {
   bool imported = false;
   uint32_t epoch = 0;
   DevBuf errFlag;
+  // optional phase timing (UB200_DIST_PROFILE=1): events between the phases of mdot, summed on the host
+  static constexpr int kPhases = 12;
+  bool profile = false;
+  cudaEvent_t ev[kPhases + 1] = {};
+  double phaseMs[kPhases] = {};
+  int profiledCalls = 0;
   // particle scratch (window)
   DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedPos, sortedVal, sortedOrigin, sortedW;
 
@@ -112,7 +119,16 @@ template <class T> struct FcmDistState {
     UB200_CUDA(cudaMemset(binCount.p, 0, binCount.cap));
     UB200_CUDA(cudaDeviceSynchronize());
     peerArena[rank] = arena;
+    profile = getenv("UB200_DIST_PROFILE") != nullptr;
+    if (profile) for (auto &e : ev) cudaEventCreate(&e);
     return UB200_OK;
+  }
+  void mark(int k, cudaStream_t st) { if (profile) cudaEventRecord(ev[k], st); }
+  void collect(int nmarks, cudaStream_t st) {
+    if (!profile) return;
+    cudaStreamSynchronize(st);
+    for (int k = 0; k + 1 < nmarks; k++) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); phaseMs[k] += ms; }
+    profiledCalls++;
   }
   void release() {
     for (int p = 0; p < world; p++)
@@ -164,6 +180,7 @@ template <class T> struct FcmDistState {
         (rc = sortedVal.reserve(sizeof(T) * 2 * (size_t)N)) || (rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N)) ||
         (rc = sortedW.reserve(sizeof(T) * 3 * kSmallSupport * (size_t)N)))
       return rc;
+    mark(0, st);
     ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
     UB200_LAUNCHED();
     if ((rc = exclusiveScanAndClear(binCount.as<uint32_t>(), ncw, binStart.as<uint32_t>(), tileSums.as<uint32_t>(), st))) return rc;
@@ -175,6 +192,7 @@ template <class T> struct FcmDistState {
     if (kern.support == 3) UB200_ORDER(3); else UB200_ORDER(4);
 #undef UB200_ORDER
     UB200_LAUNCHED();
+    mark(1, st);
     AddrSlabZFused<C> az;
     az.T = Tb; az.ny = plan.ny; az.nyl = nyl; az.nkx = plan.nkx; az.nzl = nzl; az.y0 = y0;
     for (int p = 0; p < world; p++) az.peerS[p] = at<C>(peerArena[p], offS);
@@ -192,7 +210,9 @@ template <class T> struct FcmDistState {
       if (kern.support == 3) UB200_SPREAD(3) else UB200_SPREAD(4)
 #undef UB200_SPREAD
       UB200_LAUNCHED();
+      mark(2, st);
       if ((rc = launchPassX<T, true>(plan, S, st, nzl))) return rc;
+      mark(3, st);
       // ---- forward y pass, output scattered into the owners' transposed buffers (NVLink stores) ----
       AddrSlabYForward<C> ay;
       ay.S = reinterpret_cast<C *>(S); ay.ny = plan.ny; ay.nyl = nyl; ay.nkx = plan.nkx; ay.z0 = z0;
@@ -201,7 +221,9 @@ template <class T> struct FcmDistState {
     } else {
       UB200_CUDA(cudaMemsetAsync(Tb, 0, tposeBytes(), st));
     }
+    mark(4, st);
     if ((rc = barrier(st))) return rc;
+    mark(5, st);
     // ---- fused z pass on the local ky rows; output pushed back into the owners' slabs ----
     FcmSpectralOp<T> op;
     op.nx = plan.nx; op.ny = plan.ny; op.nz = plan.nz; op.nkx = plan.nkx;
@@ -220,13 +242,17 @@ template <class T> struct FcmDistState {
       op.noisePrefactor = (T)prefactor * (T)sqrt((double)(fourierNormalization * 2 * (T)temperature / grid.cellVolume));
     }
     if ((rc = launchPassAddr<T, 0, true, FcmSpectralOp<T>>(plan, az, nyl, st, op))) return rc;
+    mark(6, st);
     if ((rc = barrier(st))) return rc;
+    mark(7, st);
     // ---- inverse y and x passes on the owned planes ----
     AddrInPlace<C> ainv;
     ainv.grid = reinterpret_cast<C *>(S); ainv.elemStride = (size_t)plan.nkx; ainv.otherStride = (size_t)plan.nkx * plan.ny;
     if ((rc = launchPassAddr<T, +1, false, NoSpectralOp>(plan, ainv, nzl, st))) return rc;
     if ((rc = launchPassX<T, false>(plan, S, st, nzl))) return rc;
+    mark(8, st);
     if ((rc = barrier(st))) return rc; // the neighbours' boundary planes are final
+    mark(9, st);
     // ---- gather for the owned particles, rows pushed to every rank ----
     PeerTable<T> slabs, outs;
     for (int p = 0; p < world; p++) { slabs.p[p] = at<T>(peerArena[p], offS); outs.p[p] = at<T>(peerArena[p], offOut); }
@@ -238,8 +264,12 @@ template <class T> struct FcmDistState {
       ibmGatherSortedDist<T, 4><<<ngb, 128, 0, st>>>(sortedOrigin.as<int4>(), sortedW.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
                                                     grid, plan.nxPad, slabs, z0, nzl, world, outs);
     UB200_LAUNCHED();
+    mark(10, st);
     if ((rc = barrier(st))) return rc; // every rank's rows have landed; the slabs may be overwritten by the next call
+    mark(11, st);
     UB200_CUDA(cudaMemcpyAsync(out3, at<T>(arena, offOut), sizeof(T) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, st));
+    mark(12, st);
+    collect(13, st);
     return UB200_OK;
   }
 };
@@ -273,6 +303,14 @@ int ub200_fcm_dist_destroy(ub200_fcm_dist *h) {
   h->f.release(); h->d.release();
   delete h;
   return UB200_OK;
+}
+/* UB200_DIST_PROFILE=1: mean milliseconds of the 12 phases of mdot (sort, spread, fft x, fft y + transpose, barrier,
+ * fused z + transpose, barrier, ifft y+x, barrier, gather, barrier, copy); returns the number of profiled calls */
+int ub200_fcm_dist_profile(ub200_fcm_dist *h, double phases[12]) {
+  if (!h || !phases) return 0;
+  const int n = h->precision == 4 ? h->f.profiledCalls : h->d.profiledCalls;
+  for (int k = 0; k < 12; k++) phases[k] = n ? (h->precision == 4 ? h->f.phaseMs[k] : h->d.phaseMs[k]) / n : 0.0;
+  return n;
 }
 int ub200_fcm_dist_ipc_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 int ub200_fcm_dist_ipc_export(ub200_fcm_dist *h, void *blob) {

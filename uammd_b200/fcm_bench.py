@@ -6,6 +6,7 @@ import json
 import math
 import os
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -79,6 +80,76 @@ def run(dev, hbm_peak, steps=100, warmup=10):
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                      "traffic": None, "algorithmic_bytes_per_step": ALG_BYTES,
                      "note": "whole step against the compulsory 7 grid passes + particle I/O (SURVEY 8(d))"},
+    }
+
+
+def run_distributed(dev, hbm_peak, steps=100, warmup=10):
+    """Strong scaling of the SAME config over all ranks (z-slab FCM, uammd_b200.multigpu.DistributedFCM): every rank
+    steps the replicated particle set; device time per step, max over ranks. Returns None except on rank 0."""
+    import torch.distributed as dist
+    from .fcm import Peskin3, _declare, _prec
+    from .md import _ptr, _stream_ptr
+    from .multigpu import DistributedFCM
+    from ._lib import check
+    from . import lib
+    world, rank = dist.get_world_size(), dist.get_rank()
+    pos, force = inputs()
+    dpos, dforce = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)
+    fcm = DistributedFCM(L, (NGRID,) * 3, Peskin3(L / NGRID), ETA, N, seed=1234)
+    MF = torch.zeros(N, 3, dtype=torch.float64, device=dev)
+    l = _declare()
+    scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        fcm.computeHydrodynamicDisplacements(dpos, dforce, temperature=TEMP, prefactor=1.0 / math.sqrt(DT), out=MF)
+        check(l.ub200_bdhi_euler_update(_prec(dpos.dtype), _ptr(dpos), None, _ptr(MF), None, None, N,
+                                        math.sqrt(2 * DT * TEMP), DT, 0, _stream_ptr()))
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(); dist.barrier()
+    l0 = lib().ub200_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        scrub.fill_(3)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize(); dist.barrier()
+    launches = lib().ub200_launch_count() - l0
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms_b2b = e0.elapsed_time(e1) / steps
+    err = fcm.errorFlag()
+    if os.environ.get("UB200_DIST_PROFILE"):
+        import ctypes as C
+        ph = (C.c_double * 12)()
+        n = fcm.lib.ub200_fcm_dist_profile(fcm._h, ph)
+        names = ["sort", "spread", "fft_x", "fft_y+transpose", "barrier1", "fused_z+transpose", "barrier2", "ifft_y+x", "barrier3",
+                 "gather+push", "barrier4", "copy_out"]
+        print(f"[rank {rank}] phases over {n} calls (us): " + ", ".join(f"{k}={1e3 * v:.1f}" for k, v in zip(names, ph)), file=sys.stderr)
+    t = torch.tensor([ms, ms_b2b], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_b2b = (float(x) for x in t.cpu())
+    fcm.close()
+    if rank != 0:
+        return None
+    gbs = ALG_BYTES / (ms * 1e-3) / 1e9 / world
+    return {
+        "metric": "FCM Mdof.steps/s @128^3", "value": DOF / 1e6 * 1000.0 / ms, "unit": "Mdof.steps/s", "n_gpus": world,
+        "scaling": "strong", "steps_per_s": 1000.0 / ms, "ms_per_step": ms, "value_back_to_back": DOF / 1e6 * 1000.0 / ms_b2b,
+        "dtype": "f64", "steps": steps, "warmup": warmup, "gpu_launches": int(launches), "barrier_timeouts": err,
+        "config": {"workload": f"BDHI::EulerMaruyama<FCM>, N={N}, {NGRID}^3 grid, Peskin 3pt, eta={ETA}, T={TEMP}, dt={DT}",
+                   "l2": "flushed before every step (256 MiB write)",
+                   "parallelism": f"z-slab decomposition over {world} GPUs: {NGRID // world} planes per rank, FFT transposes by "
+                                  "NVLink peer stores fused into the y/z passes, 4 device-side barriers per step, no NCCL on the data path"},
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                     "note": "compulsory bytes of the whole step (SURVEY 8(d)) per GPU"},
     }
 
 
