@@ -99,6 +99,37 @@ int ub200_lj_sum_devparams_f32(ub200_celllist *cl, const void *d_params, int nty
 int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, int ownerLo,
                            int ownerHi, int accumulate, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 1d: Verlet (skin) list. Replaces VerletList::update (Interactor/NeighbourList/VerletList.cuh:111-124) and
+ * the classes beneath it (VerletList/VerletListBase.cuh:73-199, BasicList/BasicListBase.cuh:76-215): rebuild when
+ * a particle moved >= (multiplier - 1) cutOff / 2 since the last rebuild (host-synchronous flag read, like
+ * VerletListBase.cuh:191-218), list stored [k * N + i] over SORTED indices, sortPos refreshed every call.
+ * The arrays are bit-identical to the reference's VerletListData (BasicListBase.cuh:143-151).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_verletlist ub200_verletlist;
+typedef struct {
+  const int *d_neighbourList;    /* neighbour k of sorted particle i at [k * particleStride + i] (sorted indices) */
+  const int *d_numberNeighbours; /* [N] (self included, like the reference) */
+  const void *d_sortPos;         /* real4[N] current positions in the sorted order of the last rebuild */
+  const int *d_groupIndex;       /* [N] sorted slot -> group index */
+  int particleStride, numberParticles, maxNeighboursPerParticle;
+  int stepsSinceLastUpdate;      /* VerletList::getNumberOfStepsSinceLastUpdate */
+  int rebuilds;                  /* rebuilds since creation */
+} ub200_verletlist_view;
+int ub200_verletlist_create(ub200_verletlist **out);
+int ub200_verletlist_destroy(ub200_verletlist *vl);
+int ub200_verletlist_set_cutoff_multiplier(ub200_verletlist *vl, float multiplier); /* VerletList.cuh:169-172, default 1.08 */
+/* forceRebuild: the caller's "positions were written / particles were reordered" signal (VerletList.cuh:179-190);
+ * the drift check handles everything else. Synchronises the stream when it has to read the drift / overflow flag. */
+int ub200_verletlist_update_f32(ub200_verletlist *vl, const void *d_pos, const int *d_groupIdx, int N, const float L[3],
+                                const int periodic[3], float cutOff, int forceRebuild, int *rebuilt, void *stream);
+int ub200_verletlist_view_get(ub200_verletlist *vl, ub200_verletlist_view *view);
+/* LJ transverser over the Verlet list. Replaces VerletList::transverseList (VerletList.cuh:141-159 ->
+ * NeighbourList/common.cuh:10-34 with VerletListBase_ns::NeighbourContainer, BasicList/NeighbourContainer.cuh:42-125)
+ * for Radial<LJFunctor>; same argument meaning as ub200_lj_sum_f32 (outputs accumulate). */
+int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params, int ntypes, void *d_force, float *d_energy,
+                            float *d_virial, const int *d_globalIdx, void *stream);
+
 /* DPD transverser (Potential/DPD.cuh:92-159). d_vel: real3[*] indexed by GLOBAL index like getInfo(pi).
  * sigma = sqrt(2 T)/sqrt(dt) as DPD_impl computes it (:66,:84-92); seed/step are the Saru seeds (:129).
  * idStride = N used in ij = min + N*max (int32 arithmetic, wraps like the reference). */

@@ -170,3 +170,21 @@ struct ub200_celllist {
   ub200::DevBuf errorFlag;
   size_t cellStartCells = 0;
 };
+
+// Opaque handle behind ub200_verletlist (VerletList / VerletListBase / BasicNeighbourListBase of the reference)
+struct ub200_verletlist {
+  ub200_celllist *cl = nullptr;     // cell list over the stored positions, cell size >= cutOff * multiplier
+  ub200::DevBuf storedPos, sortPos; // float4[N]: positions at the last rebuild (group order) / current positions, sorted order
+  ub200::DevBuf numberNeighbours;   // int[N]
+  ub200::DevBuf neighbourList;      // int[(maxNeighbours + 1) * N], entry k of sorted particle i at [k * N + i]
+  ub200::DevBuf flags;              // uint32[2]: {particles over the drift threshold, largest overflowing neighbour count}
+  int N = 0;
+  int maxNeighbours = 32;           // BasicNeighbourListBase::maxNeighboursPerParticle, grows by 32
+  float multiplier = 1.08f;         // VerletListBase::verletRadiusMultiplier
+  float cutOff = 0.f;
+  float L[3] = {0.f, 0.f, 0.f};
+  int periodic[3] = {1, 1, 1};
+  bool forceNext = true;
+  int stepsSinceLastUpdate = 0;
+  int rebuilds = 0;
+};

@@ -218,6 +218,54 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
   }
 }
 
+// LJ over the Verlet list: one thread per sorted particle (the list is [k*N + i], so a warp reads 32 consecutive
+// entries per k), neighbour positions gathered from the sorted array (neighbours of neighbouring particles sit close
+// together: L1/L2 resident), four neighbours in flight per thread, per-pair minimum image like
+// Radial::Transverser::compute (RadialPotential.cuh:107-127). Self is in the list and contributes 0 (r2 == 0).
+template <bool ENERGY, bool VIRIAL, bool MULTITYPE>
+__global__ void __launch_bounds__(128)
+ljVerletTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex, const int *__restrict__ neighbourList,
+                  const int *__restrict__ numberNeighbours, int N, GridF g, const LJPar *__restrict__ parTable, int ntypes,
+                  float4 *__restrict__ force, float *__restrict__ energy, float *__restrict__ virial,
+                  const int *__restrict__ globalIdx) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  const float4 pi = ldg4(sortPos + id);
+  const int nn = numberNeighbours[id];
+  LJPar par = parTable[0];
+  uint32_t rcb = __float_as_uint(par.cutOff2) - 1u;
+  const int ti = (int)pi.w;
+  const int trow = MULTITYPE && (unsigned)ti < (unsigned)ntypes ? ti * ntypes : -1;
+  Acc a = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const int *lp = neighbourList + id;
+  int k = 0;
+  auto one = [&](const float4 pj) {
+    const float dx = foldCoord(pj.x - pi.x, g.Lx, g.mx), dy = foldCoord(pj.y - pi.y, g.Ly, g.my), dz = foldCoord(pj.z - pi.z, g.Lz, g.mz);
+    if (MULTITYPE) {
+      const int tj = (int)pj.w;
+      par = parTable[((unsigned)tj < (unsigned)ntypes && trow >= 0) ? trow + tj : 0];
+      rcb = __float_as_uint(par.cutOff2) - 1u;
+    }
+    ljPair<ENERGY, VIRIAL>(dx, dy, dz, par, rcb, a);
+  };
+  for (; k + 4 <= nn; k += 4) {
+    const int j0 = __ldg(lp + (size_t)k * N), j1 = __ldg(lp + (size_t)(k + 1) * N), j2 = __ldg(lp + (size_t)(k + 2) * N),
+              j3 = __ldg(lp + (size_t)(k + 3) * N);
+    const float4 p0 = ldg4(sortPos + j0), p1 = ldg4(sortPos + j1), p2 = ldg4(sortPos + j2), p3 = ldg4(sortPos + j3);
+    one(p0); one(p1); one(p2); one(p3);
+  }
+  for (; k < nn; k++) one(ldg4(sortPos + __ldg(lp + (size_t)k * N)));
+  const int gi = groupIndex[id];
+  const int ori = globalIdx ? globalIdx[gi] : gi;
+  if (force) {
+    float4 f = force[ori];
+    f.x += a.fx; f.y += a.fy; f.z += a.fz;
+    force[ori] = f;
+  }
+  if (ENERGY) energy[ori] += a.e;
+  if (VIRIAL) virial[ori] += a.v;
+}
+
 template <bool E, bool V, bool M, bool P, bool A>
 static int launchLJ(ub200_celllist *cl, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
                     const int *globalIdx, cudaStream_t st, int ownerLo, int ownerHi) {
@@ -297,6 +345,39 @@ extern "C" int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int nty
                                 float *d_virial, const int *d_globalIdx, void *stream) {
   return ljSum(cl, params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true, &g_ljTable,
                (cudaStream_t)stream, 0, 0x7fffffff);
+}
+
+extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params, int ntypes, void *d_force, float *d_energy,
+                                       float *d_virial, const int *d_globalIdx, void *stream) {
+  if (!vl || !params || ntypes < 1) return UB200_ERR_INVALID_ARGUMENT;
+  if (!vl->N) return UB200_ERR_NOT_BUILT;
+  if (!d_force && !d_energy && !d_virial) return UB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LJTableCache *cache = &g_ljTable;
+  const size_t n = (size_t)ntypes * ntypes * 4;
+  if (cache->host.size() != n || memcmp(cache->host.data(), params, n * sizeof(float)) != 0) {
+    int rc = cache->dev.reserve(n * sizeof(float));
+    if (rc) return rc;
+    cache->host.assign(params, params + n);
+    UB200_CUDA(cudaMemcpyAsync(cache->dev.p, cache->host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  const int cd1[3] = {1, 1, 1};
+  const GridF g = makeGridF(vl->L, vl->periodic, cd1);
+  const int N = vl->N, nb = (N + 127) / 128;
+  const bool E = d_energy != nullptr, V = d_virial != nullptr, M = ntypes > 1;
+#define UB200_LJV(e, v, m)                                                                                              \
+  if (E == e && V == v && M == m) {                                                                                     \
+    ljVerletTraversal<e, v, m><<<nb, 128, 0, st>>>(vl->sortPos.as<float4>(), vl->cl->groupIndex.as<int>(),               \
+                                                   vl->neighbourList.as<int>(), vl->numberNeighbours.as<int>(), N, g,     \
+                                                   cache->dev.as<LJPar>(), ntypes, (float4 *)d_force, d_energy, d_virial, \
+                                                   d_globalIdx);                                                          \
+    UB200_LAUNCHED();                                                                                                   \
+    return UB200_OK;                                                                                                    \
+  }
+  UB200_LJV(false, false, false) UB200_LJV(false, false, true) UB200_LJV(true, false, false) UB200_LJV(true, false, true)
+  UB200_LJV(false, true, false) UB200_LJV(false, true, true) UB200_LJV(true, true, false) UB200_LJV(true, true, true)
+#undef UB200_LJV
+  return UB200_ERR_UNSUPPORTED;
 }
 
 extern "C" int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, int ownerLo,

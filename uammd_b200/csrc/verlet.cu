@@ -1,0 +1,219 @@
+// Verlet (skin) neighbour list for sm_100a. Replaces VerletList::update (Interactor/NeighbourList/VerletList.cuh:111-124),
+// VerletListBase::{update,needsRebuild,isParticleDriftOverThreshold,updateSortedPositions}
+// (VerletList/VerletListBase.cuh:107-199) and BasicNeighbourListBase::{update,fillBasicNeighbourList}
+// (BasicList/BasicListBase.cuh:42-71,131-215). The list is BIT-IDENTICAL to the reference's: same cell list, same
+// visiting order (27 cells x fastest, ascending sorted index inside a cell, self included), same "<= cutOff^2" test on the
+// minimum-image separation, same [k*N + i] layout - so the reference's own VerletListBase_ns::NeighbourContainer and
+// user transversers run on it unchanged, while the LJ fast path (ljVerletTraversal, pair_lj.cu) reads it directly.
+//
+// Build: one WARP per home cell; the candidates of the 27 neighbour cells are staged once in shared memory, every
+// home particle is tested by the 32 lanes in visiting order and the hits are compacted with ballot/popc, so the
+// list comes out ordered without any sort (the reference walks the 27 cells with one thread per particle).
+#include "pair_common.cuh"
+
+namespace ub200 {
+
+// VerletListBase_ns::checkMaximumDrift (VerletListBase.cuh:57-69)
+__global__ void __launch_bounds__(256)
+verletDriftCheck(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, const float4 *__restrict__ stored, int N,
+                 GridF g, float maxDist2, uint32_t *__restrict__ flag) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  const float4 c = ldg4(pos + (groupIdx ? groupIdx[id] : id)), p = ldg4(stored + id);
+  const float dx = foldCoord(c.x - p.x, g.Lx, g.mx), dy = foldCoord(c.y - p.y, g.Ly, g.my), dz = foldCoord(c.z - p.z, g.Lz, g.mz);
+  const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+  if (r2 >= maxDist2) atomicAdd(flag, 1u);
+}
+
+// storedPos[i] = pos[group[i]] (storeCurrentPos :143-150)
+__global__ void __launch_bounds__(256)
+verletStore(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, float4 *__restrict__ stored) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  stored[id] = ldg4(pos + (groupIdx ? groupIdx[id] : id));
+}
+// sortPos[k] = pos[group[groupIndex[k]]] (updateSortedPositions :152-163), every step
+__global__ void __launch_bounds__(256)
+verletSortedPositions(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, const int *__restrict__ groupIndex, int N,
+                      float4 *__restrict__ sortPos) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const int i = groupIndex[k];
+  sortPos[k] = ldg4(pos + (groupIdx ? groupIdx[i] : i));
+}
+
+constexpr int kVerletCap = 416;
+
+// BasicNeighbourList_ns::fillBasicNeighbourList (BasicListBase.cuh:42-71)
+__global__ void __launch_bounds__(kPairThreads, 8)
+verletFill(const float4 *__restrict__ sortPos, const uint32_t *__restrict__ binStart, GridF g, int ncells, float cutOff2, int N,
+           int maxNeighbours, int *__restrict__ neighbourList, int *__restrict__ numberNeighbours, uint32_t *__restrict__ overflow) {
+  __shared__ float4 candAll[kPairWarps][kVerletCap];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 *cand = candAll[warp];
+  const int warpsTotal = gridDim.x * kPairWarps;
+  for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
+    const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
+    const NeighbourCells nc = describeNeighbours(g, cx, cy, cz, binStart, lane);
+    const int hStart = __shfl_sync(0xffffffffu, nc.start, nc.centre);
+    const int hCount = __shfl_sync(0xffffffffu, nc.count, nc.centre);
+    if (hCount == 0) continue;
+    const bool staged = nc.total <= kVerletCap;
+    __syncwarp();
+    if (staged) {
+      for (int c = 0; c < 27; c++) {
+        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+        const int st = __shfl_sync(0xffffffffu, nc.start, c);
+        const int off = __shfl_sync(0xffffffffu, nc.off, c);
+        for (int t = lane; t < cnt; t += 32) cand[off + t] = ldg4(sortPos + st + t);
+      }
+    }
+    __syncwarp();
+    for (int h = 0; h < hCount; h++) {
+      const int id = hStart + h;
+      const float4 pi = ldg4(sortPos + id);
+      int nneigh = 0; // warp uniform
+      bool over = false;
+      for (int c = 0; c < 27 && !over; c++) {
+        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+        if (cnt == 0) continue;
+        const int st = __shfl_sync(0xffffffffu, nc.start, c);
+        const int off = __shfl_sync(0xffffffffu, nc.off, c);
+        for (int t0 = 0; t0 < cnt; t0 += 32) {
+          const int t = t0 + lane;
+          bool hit = false;
+          if (t < cnt) {
+            const float4 pj = staged ? cand[off + t] : ldg4(sortPos + st + t);
+            const float dx = foldCoord(pj.x - pi.x, g.Lx, g.mx), dy = foldCoord(pj.y - pi.y, g.Ly, g.my),
+                        dz = foldCoord(pj.z - pi.z, g.Lz, g.mz);
+            hit = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) <= cutOff2;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          const int slot = nneigh + __popc(m & ((1u << lane) - 1u));
+          // the reference stops a particle as soon as its count reaches maxNeighboursPerParticle (:60-63)
+          if (hit && slot + 1 < maxNeighbours) neighbourList[(size_t)slot * N + id] = st + t;
+          nneigh += __popc(m);
+          if (nneigh >= maxNeighbours) { over = true; break; }
+        }
+      }
+      if (lane == 0) {
+        if (over) atomicMax(overflow, (uint32_t)nneigh);
+        else numberNeighbours[id] = nneigh;
+      }
+    }
+  }
+}
+
+} // namespace ub200
+
+using namespace ub200;
+
+extern "C" {
+
+int ub200_verletlist_create(ub200_verletlist **out) {
+  if (!out) return UB200_ERR_INVALID_ARGUMENT;
+  ub200_verletlist *v = new (std::nothrow) ub200_verletlist();
+  if (!v) return UB200_ERR_ALLOC;
+  int rc = ub200_celllist_create(&v->cl);
+  if (rc) { delete v; return rc; }
+  if ((rc = v->flags.reserve(2 * sizeof(uint32_t)))) { ub200_celllist_destroy(v->cl); delete v; return rc; }
+  *out = v;
+  return UB200_OK;
+}
+int ub200_verletlist_destroy(ub200_verletlist *v) {
+  if (!v) return UB200_OK;
+  ub200_celllist_destroy(v->cl);
+  v->storedPos.release(); v->sortPos.release(); v->numberNeighbours.release(); v->neighbourList.release(); v->flags.release();
+  delete v;
+  return UB200_OK;
+}
+int ub200_verletlist_set_cutoff_multiplier(ub200_verletlist *v, float multiplier) {
+  if (!v || !(multiplier >= 1.0f)) return UB200_ERR_INVALID_ARGUMENT;
+  v->forceNext = true; // VerletListBase::setCutOffMultiplier (:126-129)
+  v->multiplier = multiplier;
+  return UB200_OK;
+}
+
+int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const int *d_groupIdx, int N, const float L[3],
+                                const int periodic[3], float cutOff, int forceRebuild, int *rebuilt, void *stream) {
+  if (!v || !d_pos || N <= 0 || !L || !periodic || !(cutOff > 0.f)) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4 *pos = (const float4 *)d_pos;
+  const int nb = (N + 255) / 256;
+  int rc;
+  // ---- VerletListBase::needsRebuild (:172-190) ----
+  bool rebuild = v->forceNext || forceRebuild != 0;
+  v->forceNext = false;
+  if (!rebuild) {
+    rebuild = N != v->N || cutOff != v->cutOff;
+    for (int d = 0; d < 3; d++) rebuild = rebuild || L[d] != v->L[d] || (periodic[d] != 0) != (v->periodic[d] != 0);
+  }
+  if (!rebuild) {
+    // isParticleDriftOverThreshold (:192-218): host-synchronous flag read, like the reference
+    const float threshold = (v->multiplier * v->cutOff - v->cutOff) / 2.0f;
+    if (threshold <= 1e-6f) rebuild = true;
+    else {
+      const int cd1[3] = {1, 1, 1};
+      const GridF g = makeGridF(L, periodic, cd1);
+      UB200_CUDA(cudaMemsetAsync(v->flags.p, 0, sizeof(uint32_t), st));
+      verletDriftCheck<<<nb, 256, 0, st>>>(pos, d_groupIdx, v->storedPos.as<float4>(), N, g, threshold * threshold, v->flags.as<uint32_t>());
+      UB200_LAUNCHED();
+      uint32_t over = 0;
+      UB200_CUDA(cudaMemcpyAsync(&over, v->flags.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      UB200_CUDA(cudaStreamSynchronize(st));
+      rebuild = over > 0;
+    }
+  }
+  if (rebuild) {
+    v->stepsSinceLastUpdate = 0;
+    v->rebuilds++;
+    v->N = N; v->cutOff = cutOff;
+    for (int d = 0; d < 3; d++) { v->L[d] = L[d]; v->periodic[d] = periodic[d]; }
+    if ((rc = v->storedPos.reserve(sizeof(float4) * (size_t)N)) || (rc = v->sortPos.reserve(sizeof(float4) * (size_t)N)) ||
+        (rc = v->numberNeighbours.reserve(sizeof(int) * (size_t)N)))
+      return rc;
+    verletStore<<<nb, 256, 0, st>>>(pos, d_groupIdx, N, v->storedPos.as<float4>());
+    UB200_LAUNCHED();
+    // rebuildList (:165-168) -> BasicNeighbourListBase::update (BasicListBase.cuh:131-141)
+    const float rcut = v->cutOff * v->multiplier;
+    int cd[3];
+    if ((rc = ub200_neighbour_celldim_f32(L, rcut, cd))) return rc;
+    if ((rc = ub200_celllist_build_f32(v->cl, v->storedPos.p, nullptr, N, L, periodic, cd, st))) return rc;
+    const int needed = (v->cl->ncells + kPairWarps - 1) / kPairWarps;
+    const int grid = needed < kNumSMs * 8 ? needed : kNumSMs * 8;
+    while (true) { // fillBasicNeighbourList: retry with 32 more slots until nothing overflows (:176-181)
+      if ((rc = v->neighbourList.reserve(sizeof(int) * (size_t)N * (v->maxNeighbours + 1)))) return rc;
+      UB200_CUDA(cudaMemsetAsync(v->flags.as<uint32_t>() + 1, 0, sizeof(uint32_t), st));
+      verletFill<<<grid, kPairThreads, 0, st>>>(v->cl->sortPos.as<float4>(), v->cl->binStart.as<uint32_t>(), v->cl->grid, v->cl->ncells,
+                                               rcut * rcut, N, v->maxNeighbours, v->neighbourList.as<int>(),
+                                               v->numberNeighbours.as<int>(), v->flags.as<uint32_t>() + 1);
+      UB200_LAUNCHED();
+      uint32_t over = 0;
+      UB200_CUDA(cudaMemcpyAsync(&over, v->flags.as<uint32_t>() + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      UB200_CUDA(cudaStreamSynchronize(st));
+      if (!over) break;
+      v->maxNeighbours += 32;
+    }
+  }
+  verletSortedPositions<<<nb, 256, 0, st>>>(pos, d_groupIdx, v->cl->groupIndex.as<int>(), N, v->sortPos.as<float4>());
+  UB200_LAUNCHED();
+  v->stepsSinceLastUpdate++;
+  if (rebuilt) *rebuilt = rebuild ? 1 : 0;
+  return UB200_OK;
+}
+
+int ub200_verletlist_view_get(ub200_verletlist *v, ub200_verletlist_view *view) {
+  if (!v || !view) return UB200_ERR_INVALID_ARGUMENT;
+  if (!v->N) return UB200_ERR_NOT_BUILT;
+  view->d_neighbourList = v->neighbourList.as<int>();
+  view->d_numberNeighbours = v->numberNeighbours.as<int>();
+  view->d_sortPos = v->sortPos.p;
+  view->d_groupIndex = v->cl->groupIndex.as<int>();
+  view->particleStride = v->N;
+  view->numberParticles = v->N;
+  view->maxNeighboursPerParticle = v->maxNeighbours;
+  view->stepsSinceLastUpdate = v->stepsSinceLastUpdate - 1; // VerletListBase::getNumberOfStepsSinceLastUpdate (:131)
+  view->rebuilds = v->rebuilds;
+  return UB200_OK;
+}
+}

@@ -173,8 +173,85 @@ class CellList:
         return cs, ce
 
 
+class VerletListView(C.Structure):
+    _fields_ = [("d_neighbourList", C.c_void_p), ("d_numberNeighbours", C.c_void_p), ("d_sortPos", C.c_void_p),
+                ("d_groupIndex", C.c_void_p), ("particleStride", C.c_int), ("numberParticles", C.c_int),
+                ("maxNeighboursPerParticle", C.c_int), ("stepsSinceLastUpdate", C.c_int), ("rebuilds", C.c_int)]
+
+
+def _declare_verlet():
+    lib = _lib.lib()
+    if getattr(lib, "_verlet_declared", False):
+        return lib
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    lib.ub200_verletlist_create.argtypes = [C.POINTER(vp)]
+    lib.ub200_verletlist_destroy.argtypes = [vp]
+    lib.ub200_verletlist_set_cutoff_multiplier.argtypes = [vp, f]
+    lib.ub200_verletlist_update_f32.argtypes = [vp, vp, vp, i, C.c_float * 3, C.c_int * 3, f, i, C.POINTER(i), vp]
+    lib.ub200_verletlist_view_get.argtypes = [vp, C.POINTER(VerletListView)]
+    lib.ub200_lj_sum_verlet_f32.argtypes = [vp, C.POINTER(C.c_float), i, vp, vp, vp, vp, vp]
+    lib._verlet_declared = True
+    return lib
+
+
+class VerletList:
+    """NeighbourList concept with a skin (Interactor/NeighbourList/VerletList.cuh:83-201): update(pos, box, cutOff)
+    rebuilds only when some particle moved (multiplier - 1) cutOff / 2 since the last rebuild; getVerletList() exposes
+    VerletListData (neighbourList [k*N + i] over sorted indices, numberNeighbours, sortPos, groupIndex)."""
+
+    def __init__(self):
+        self.lib = _declare_verlet()
+        self._h = C.c_void_p()
+        check(self.lib.ub200_verletlist_create(C.byref(self._h)))
+        self.device = None
+        self.forceNextUpdate = True
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib.ub200_verletlist_destroy(self._h)
+        except Exception:
+            pass
+
+    def setCutOffMultiplier(self, m):
+        check(self.lib.ub200_verletlist_set_cutoff_multiplier(self._h, float(m)))
+
+    def update(self, pos, box, cutOff, stream=None, groupIndex=None):
+        if pos.dtype != torch.float32 or pos.dim() != 2 or pos.shape[1] != 4 or not pos.is_cuda or not pos.is_contiguous():
+            raise UB200Error("VerletList.update: pos must be a contiguous CUDA float32 [N,4] tensor (real4)")
+        N = pos.shape[0] if groupIndex is None else groupIndex.shape[0]
+        rebuilt = C.c_int(0)
+        check(self.lib.ub200_verletlist_update_f32(self._h, _ptr(pos), _ptr(groupIndex), N, f3(box.boxSize),
+                                                   i3([int(p) for p in box.periodic]), float(cutOff),
+                                                   int(self.forceNextUpdate), C.byref(rebuilt), _stream_ptr(stream)))
+        self.forceNextUpdate = False
+        self.device = pos.device
+        return bool(rebuilt.value)
+
+    def view(self):
+        v = VerletListView()
+        check(self.lib.ub200_verletlist_view_get(self._h, C.byref(v)))
+        return v
+
+    def getNumberOfStepsSinceLastUpdate(self):
+        return self.view().stepsSinceLastUpdate
+
+    def getVerletList(self):
+        v = self.view()
+        N, dev = v.numberParticles, self.device
+        return {
+            "neighbourList": _device_copy(v.d_neighbourList, (v.maxNeighboursPerParticle + 1, N), torch.int32, dev),
+            "numberNeighbours": _device_copy(v.d_numberNeighbours, (N,), torch.int32, dev),
+            "sortPos": _device_copy(v.d_sortPos, (N, 4), torch.float32, dev),
+            "groupIndex": _device_copy(v.d_groupIndex, (N,), torch.int32, dev),
+            "particleStride": v.particleStride, "maxNeighboursPerParticle": v.maxNeighboursPerParticle,
+            "rebuilds": v.rebuilds,
+        }
+
+
 class PairForces:
-    """Interactor: sum(pos, force=, energy=, virial=) accumulates (+=) like Transverser::set."""
+    """Interactor: sum(pos, force=, energy=, virial=) accumulates (+=) like Transverser::set. nl: CellList (default) or
+    VerletList, like the second template argument of the reference's PairForces."""
 
     def __init__(self, potential, box, nl=None):
         self.pot, self.box = potential, box
@@ -194,6 +271,11 @@ class PairForces:
 
     def sumWithCurrentList(self, force=None, energy=None, virial=None, stream=None, globalIndex=None):
         tab = self.pot.table()
+        if isinstance(self.nl, VerletList):
+            check(self.nl.lib.ub200_lj_sum_verlet_f32(self.nl._h, tab.ctypes.data_as(C.POINTER(C.c_float)), self.pot.ntypes,
+                                                      _ptr(force), _ptr(energy), _ptr(virial), _ptr(globalIndex),
+                                                      _stream_ptr(stream)))
+            return
         check(_lib.lib().ub200_lj_sum_f32(self.nl._h, tab.ctypes.data_as(C.POINTER(C.c_float)), self.pot.ntypes,
                                           _ptr(force), _ptr(energy), _ptr(virial), _ptr(globalIndex),
                                           _stream_ptr(stream)))
