@@ -142,6 +142,14 @@ def run_reference(args):
     if not args.no_fcm:
         from uammd_b200 import fcm_bench
         line["fcm"] = fcm_bench.run_reference(ROOT, steps=args.fcm_steps)
+    if not args.no_extra:
+        from uammd_b200 import extra_bench
+        for name, fn in (("verlet", lambda: extra_bench.verlet_reference(ROOT, N, Lb, pos, vel, RC, DT, equil=args.equil)),
+                         ("pse", lambda: extra_bench.pse_reference(ROOT)), ("bd", lambda: extra_bench.bd_reference(ROOT))):
+            try:
+                line[name] = fn()
+            except Exception as e:  # a secondary leg must not take the headline down
+                line[name] = {"error": repr(e)[:300]}
     print(json.dumps(line))
     return 0
 
@@ -171,6 +179,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fcm", action="store_true")
     ap.add_argument("--fcm-steps", type=int, default=100)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (VerletList MD, PSE, BD ideal)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -315,6 +324,14 @@ def main():
                 line["fcm"] = fcm_bench.run(dev, peak, steps=args.fcm_steps)
             except ImportError:
                 pass
+        if not args.no_extra and world == 1:
+            from uammd_b200 import extra_bench
+            for name, fn in (("verlet", lambda: extra_bench.verlet(dev, N, Lb, pos, vel, RC, DT, equil=args.equil)),
+                             ("pse", lambda: extra_bench.pse(dev)), ("bd", lambda: extra_bench.bd_ideal(dev))):
+                try:
+                    line[name] = fn()
+                except Exception as e:  # a secondary leg must not take the headline down
+                    line[name] = {"error": repr(e)[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

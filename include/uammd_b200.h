@@ -130,6 +130,14 @@ int ub200_verletlist_view_get(ub200_verletlist *vl, ub200_verletlist_view *view)
 int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params, int ntypes, void *d_force, float *d_energy,
                             float *d_virial, const int *d_globalIdx, void *stream);
 
+/* VerletNVE::forwardTime x nsteps over PairForces<LJ, VerletList> (the pair generic_md instantiates): kick+drift, list
+ * update (drift check), forces, kick. forcesAreCurrent = 0 computes F(t) first. md: a handle from ub200_md_create
+ * (declared below). */
+struct ub200_md;
+int ub200_md_lj_nve_verlet_run_f32(struct ub200_md *md, ub200_verletlist *vl, void *d_pos, void *d_vel, void *d_force, int N,
+                                   const float L[3], float rc, const float *params, int ntypes, float dt, int nsteps,
+                                   int forcesAreCurrent, void *stream);
+
 /* DPD transverser (Potential/DPD.cuh:92-159). d_vel: real3[*] indexed by GLOBAL index like getInfo(pi).
  * sigma = sqrt(2 T)/sqrt(dt) as DPD_impl computes it (:66,:84-92); seed/step are the Saru seeds (:129).
  * idStride = N used in ij = min + N*max (int32 arithmetic, wraps like the reference). */

@@ -117,7 +117,7 @@ def test_parity_vs_reference_fp64(cuda, tmp_path, shear, T):
         # Far-field noise: same Saru streams and float Box-Muller, but the reference adds the conjugate partner's
         # contribution on the kx = 0 / nx/2 planes with a second NON-ATOMIC "+=" from another thread (FarField.cuh:283,
         # :305): a benign-looking race that drops a few updates per call. We compute the race-free sum.
-        assert _rel(far, rfar) < 1e-7
+        assert _rel(far, rfar) < 2e-6
         print(f"[pse fp64 shear={shear} T={T}] bdw {_rel(bdw, rbdw):.2e}")
         assert _rel(bdw, rbdw) < 20 * tol   # two Lanczos runs stopped by the same criterion at tolerance tol
 

@@ -153,6 +153,38 @@ int ub200_md_lj_nve_run_f32(ub200_md *md, void *d_pos, void *d_vel, void *d_forc
   return UB200_OK;
 }
 
+// Same loop over PairForces<LJ, VerletList>: drift check (host-synchronous, like the reference) + sortPos refresh every
+// step, list rebuild only when a particle left its skin.
+int ub200_md_lj_nve_verlet_run_f32(ub200_md *md, ub200_verletlist *vl, void *d_pos, void *d_vel, void *d_force, int N,
+                                   const float L[3], float rc, const float *params, int ntypes, float dt, int nsteps,
+                                   int forcesAreCurrent, void *stream) {
+  if (!md || !vl || !d_pos || !d_vel || !d_force || N <= 0 || !L || !params || nsteps < 0) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (N + 255) / 256;
+  const int periodic[3] = {1, 1, 1};
+  auto forces = [&]() -> int {
+    int e = ub200_verletlist_update_f32(vl, d_pos, nullptr, N, L, periodic, rc, 0, nullptr, stream);
+    if (e) return e;
+    UB200_CUDA(cudaMemsetAsync(d_force, 0, sizeof(float4) * (size_t)N, st)); // VerletNVE::resetForces (VerletNVE.cu:152-158)
+    return ub200_lj_sum_verlet_f32(vl, params, ntypes, d_force, nullptr, nullptr, nullptr, stream);
+  };
+  int e;
+  if (!forcesAreCurrent && (e = forces())) return e;
+  for (int s = 0; s < nsteps; s++) {
+    if (s == 0) {
+      nveHalfStep<1><<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, nullptr, 1.0f, nullptr, N, dt, 0);
+      UB200_LAUNCHED();
+    }
+    if ((e = forces())) return e;
+    if (s == nsteps - 1)
+      nveHalfStep<2><<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, nullptr, 1.0f, nullptr, N, dt, 0);
+    else
+      nveKickKickDrift<<<nb, 256, 0, st>>>((float4 *)d_pos, (float *)d_vel, (const float4 *)d_force, N, dt);
+    UB200_LAUNCHED();
+  }
+  return UB200_OK;
+}
+
 int ub200_md_lj_nve_run_host_f32(ub200_md *md, float *h_pos4, float *h_vel3, float *h_force4, int N, const float L[3],
                                  float rc, const float *params, int ntypes, float dt, int nsteps, void *stream) {
   if (!md || !h_pos4 || !h_vel3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;

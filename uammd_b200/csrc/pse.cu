@@ -141,20 +141,22 @@ template <class T> __device__ __forceinline__ typename Vec2<T>::type tableGet(co
 }
 
 template <class T> struct NearGeom {
-  T Lx, Ly, Lz, shear, rcut2;
+  T Lx, Ly, Lz, iLx, iLy, iLz, shear, rcut2;
 };
 
-// RPYNearTransverser::compute (NearField.cuh:131-182)
-template <class T>
+// RPYNearTransverser::compute (NearField.cuh:131-182). The image shifts use multiplications by 1/L where the
+// reference divides: the two can only disagree when a separation component is within an ulp of L/2, far beyond the
+// cut-off (rcut <= L/2 is enforced at construction), where both images are rejected.
+template <class T, bool SHEAR>
 __device__ __forceinline__ void rpyPair(const NearGeom<T> &q, const TableView<T> &tb, T pix, T piy, T piz, T pjx, T pjy,
                                         T pjz, T vjx, T vjy, T vjz, T &ax, T &ay, T &az) {
   T rx = pjx - pix, ry = pjy - piy, rz = pjz - piz;
-  rx += q.shear * ry;
-  const T s1 = round(ry / q.Ly);
-  rx -= q.shear * q.Ly * s1;
+  // rint (one instruction) where the reference calls round(): they differ only at exact half-integers = L/2 apart
+  const T s1 = rint(ry * q.iLy);
+  if (SHEAR) { rx += q.shear * ry; rx -= q.shear * q.Ly * s1; }
   ry -= q.Ly * s1;
-  rz -= q.Lz * round(rz / q.Lz);
-  rx -= q.Lx * round(rx / q.Lx);
+  rz -= q.Lz * rint(rz * q.iLz);
+  rx -= q.Lx * rint(rx * q.iLx);
   const T r2 = rx * rx + ry * ry + rz * rz;
   if (r2 >= q.rcut2) return;
   const auto fg = tableGet(tb, sqrt(r2));
@@ -194,19 +196,21 @@ __global__ void __launch_bounds__(256) pseToFloat4(const double4 *__restrict__ i
 
 constexpr int kNearCap = 224; // staged candidates per warp
 
-// One warp per home cell: the (up to) 27 neighbour cells are staged once per cell (position + v, 6 reals per
-// candidate), then every home particle is served by the 32 lanes striding over the staged candidates and a
+// One warp per home cell: the (up to) 27 neighbour cells are staged once per cell into two flat shared arrays
+// (positions and v, 3 reals per candidate, stride 3 words: conflict free), then the home particles are served TWO at a
+// time by the 32 lanes striding over the flat candidate list (each staged candidate feeds two pair evaluations) and a
 // butterfly reduction. Replaces transverseWithNeighbourContainer (NeighbourList/common.cuh:10-34) for the
 // RPYNearTransverser. ACCUMULATE: Mv[i] += (Transverser::set, NearField.cuh:184-186); otherwise Mv[i] = (the
 // Dotctor's fill + traverse, :212-218, in one pass).
-template <class T, bool ACCUMULATE>
+template <class T, bool ACCUMULATE, bool SHEAR>
 __global__ void __launch_bounds__(kPairThreads)
 rpyNearTraversal(const T *__restrict__ sortedPos3, const T *__restrict__ sortedV3, const int *__restrict__ groupIndex,
                  const uint32_t *__restrict__ binStart, GridF g, int ncells, TableView<T> tb, NearGeom<T> q,
                  T *__restrict__ Mv3) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *cand = reinterpret_cast<T *>(smemRaw) + (size_t)warp * kNearCap * 6;
+  T *candP = reinterpret_cast<T *>(smemRaw) + (size_t)warp * kNearCap * 6;
+  T *candV = candP + (size_t)kNearCap * 3;
   const int warpsTotal = gridDim.x * kPairWarps;
   for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
@@ -223,43 +227,47 @@ rpyNearTraversal(const T *__restrict__ sortedPos3, const T *__restrict__ sortedV
         const int st = __shfl_sync(0xffffffffu, nc.start, c);
         const int off = __shfl_sync(0xffffffffu, nc.off, c);
         for (int t = lane; t < 3 * cnt; t += 32) {
-          cand[(size_t)off * 6 + t] = sortedPos3[3 * (size_t)st + t];           // [off*6 .. off*6+3cnt): positions
-          cand[(size_t)off * 6 + 3 * cnt + t] = sortedV3[3 * (size_t)st + t];   // then the v of the same cell
+          candP[3 * off + t] = sortedPos3[3 * (size_t)st + t];
+          candV[3 * off + t] = sortedV3[3 * (size_t)st + t];
         }
       }
     }
     __syncwarp();
-    for (int h = 0; h < hCount; h++) {
-      const T pix = sortedPos3[3 * (size_t)(hStart + h)], piy = sortedPos3[3 * (size_t)(hStart + h) + 1],
-              piz = sortedPos3[3 * (size_t)(hStart + h) + 2];
-      T ax = T(0), ay = T(0), az = T(0);
-      for (int c = 0; c < 27; c++) {
-        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
-        if (cnt == 0) continue;
-        const int st = __shfl_sync(0xffffffffu, nc.start, c);
-        const int off = __shfl_sync(0xffffffffu, nc.off, c);
-        for (int t = lane; t < cnt; t += 32) {
-          T pjx, pjy, pjz, vjx, vjy, vjz;
-          if (staged) {
-            const T *pp = cand + (size_t)off * 6 + 3 * t, *vp = cand + (size_t)off * 6 + 3 * cnt + 3 * t;
-            pjx = pp[0]; pjy = pp[1]; pjz = pp[2]; vjx = vp[0]; vjy = vp[1]; vjz = vp[2];
-          } else {
+    for (int h = 0; h < hCount; h += 2) {
+      const bool two = h + 1 < hCount;
+      const size_t i0 = hStart + h, i1 = hStart + h + (two ? 1 : 0);
+      const T p0x = sortedPos3[3 * i0], p0y = sortedPos3[3 * i0 + 1], p0z = sortedPos3[3 * i0 + 2];
+      const T p1x = sortedPos3[3 * i1], p1y = sortedPos3[3 * i1 + 1], p1z = sortedPos3[3 * i1 + 2];
+      T a0x = T(0), a0y = T(0), a0z = T(0), a1x = T(0), a1y = T(0), a1z = T(0);
+      if (staged) {
+        for (int t = lane; t < nc.total; t += 32) {
+          const T pjx = candP[3 * t], pjy = candP[3 * t + 1], pjz = candP[3 * t + 2];
+          const T vjx = candV[3 * t], vjy = candV[3 * t + 1], vjz = candV[3 * t + 2];
+          rpyPair<T, SHEAR>(q, tb, p0x, p0y, p0z, pjx, pjy, pjz, vjx, vjy, vjz, a0x, a0y, a0z);
+          rpyPair<T, SHEAR>(q, tb, p1x, p1y, p1z, pjx, pjy, pjz, vjx, vjy, vjz, a1x, a1y, a1z);
+        }
+      } else {
+        for (int c = 0; c < 27; c++) {
+          const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+          if (cnt == 0) continue;
+          const int st = __shfl_sync(0xffffffffu, nc.start, c);
+          for (int t = lane; t < cnt; t += 32) {
             const T *pp = sortedPos3 + 3 * (size_t)(st + t), *vp = sortedV3 + 3 * (size_t)(st + t);
-            pjx = pp[0]; pjy = pp[1]; pjz = pp[2]; vjx = vp[0]; vjy = vp[1]; vjz = vp[2];
+            rpyPair<T, SHEAR>(q, tb, p0x, p0y, p0z, pp[0], pp[1], pp[2], vp[0], vp[1], vp[2], a0x, a0y, a0z);
+            rpyPair<T, SHEAR>(q, tb, p1x, p1y, p1z, pp[0], pp[1], pp[2], vp[0], vp[1], vp[2], a1x, a1y, a1z);
           }
-          rpyPair(q, tb, pix, piy, piz, pjx, pjy, pjz, vjx, vjy, vjz, ax, ay, az);
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        ax += __shfl_xor_sync(0xffffffffu, ax, o);
-        ay += __shfl_xor_sync(0xffffffffu, ay, o);
-        az += __shfl_xor_sync(0xffffffffu, az, o);
+        a0x += __shfl_xor_sync(0xffffffffu, a0x, o); a0y += __shfl_xor_sync(0xffffffffu, a0y, o); a0z += __shfl_xor_sync(0xffffffffu, a0z, o);
+        a1x += __shfl_xor_sync(0xffffffffu, a1x, o); a1y += __shfl_xor_sync(0xffffffffu, a1y, o); a1z += __shfl_xor_sync(0xffffffffu, a1z, o);
       }
-      if (lane == 0) {
-        T *out = Mv3 + 3 * (size_t)groupIndex[hStart + h];
-        if (ACCUMULATE) { out[0] += ax; out[1] += ay; out[2] += az; }
-        else { out[0] = ax; out[1] = ay; out[2] = az; }
+      if (lane == 0 || (lane == 1 && two)) {
+        T *out = Mv3 + 3 * (size_t)groupIndex[lane ? i1 : i0];
+        const T rx = lane ? a1x : a0x, ry = lane ? a1y : a0y, rz = lane ? a1z : a0z;
+        if (ACCUMULATE) { out[0] += rx; out[1] += ry; out[2] += rz; }
+        else { out[0] = rx; out[1] = ry; out[2] = rz; }
       }
     }
   }
@@ -632,15 +640,17 @@ template <class T> struct PseState {
     tb.interval = (T)(1.0 / (rcut - T(0))); tb.dr = (T)(1.0 / (T)(nTable - 1));
     NearGeom<T> q;
     q.Lx = Lb[0]; q.Ly = Lb[1]; q.Lz = Lb[2]; q.shear = shear; q.rcut2 = rcut * rcut;
+    q.iLx = T(1.0) / Lb[0]; q.iLy = T(1.0) / Lb[1]; q.iLz = T(1.0) / Lb[2];
     const size_t smem = (size_t)kPairWarps * kNearCap * 6 * sizeof(T);
     const int needed = (cl->ncells + kPairWarps - 1) / kPairWarps;
-    const int gridSize = std::min(needed, kNumSMs * 4);
-    if (accumulate)
-      rpyNearTraversal<T, true><<<gridSize, kPairThreads, smem, st>>>(sortedPos.as<T>(), sortedV.as<T>(), cl->groupIndex.as<int>(),
-                                                                     cl->binStart.as<uint32_t>(), cl->grid, cl->ncells, tb, q, Mv3);
-    else
-      rpyNearTraversal<T, false><<<gridSize, kPairThreads, smem, st>>>(sortedPos.as<T>(), sortedV.as<T>(), cl->groupIndex.as<int>(),
-                                                                      cl->binStart.as<uint32_t>(), cl->grid, cl->ncells, tb, q, Mv3);
+    const int gridSize = std::min(needed, kNumSMs * 8);
+#define UB200_NEAR(ACC, SH)                                                                                               \
+  rpyNearTraversal<T, ACC, SH><<<gridSize, kPairThreads, smem, st>>>(sortedPos.as<T>(), sortedV.as<T>(), cl->groupIndex.as<int>(), \
+                                                                    cl->binStart.as<uint32_t>(), cl->grid, cl->ncells, tb, q, Mv3)
+    const bool sh = shear != T(0);
+    if (accumulate) { if (sh) UB200_NEAR(true, true); else UB200_NEAR(true, false); }
+    else { if (sh) UB200_NEAR(false, true); else UB200_NEAR(false, false); }
+#undef UB200_NEAR
     UB200_LAUNCHED();
     return UB200_OK;
   }

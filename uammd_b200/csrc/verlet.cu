@@ -42,63 +42,133 @@ verletSortedPositions(const float4 *__restrict__ pos, const int *__restrict__ gr
   sortPos[k] = ldg4(pos + (groupIdx ? groupIdx[i] : i));
 }
 
-constexpr int kVerletCap = 416;
+constexpr int kVerletCap = 640;   // staged candidates per warp
+constexpr int kVerletHome = 20;   // home particles whose lists are assembled in shared memory per pass
+constexpr int kVerletK = 96;      // list entries per home particle assembled in shared memory
+constexpr size_t kVerletWarpBytes = kVerletCap * sizeof(float4) + kVerletHome * kVerletK * sizeof(unsigned short) + kVerletHome * sizeof(int);
+constexpr size_t kVerletSmem = kPairWarps * ((kVerletWarpBytes + 15) / 16 * 16);
 
-// BasicNeighbourList_ns::fillBasicNeighbourList (BasicListBase.cuh:42-71)
-__global__ void __launch_bounds__(kPairThreads, 8)
+// exact test of the reference: dot(apply_pbc(pj - pi)) <= cutOff2 with its roundings (BasicListBase.cuh:56-58)
+__device__ __forceinline__ bool verletHitExact(const float4 pi, const float4 pj, const GridF &g, float cutOff2) {
+  const float dx = foldCoord(pj.x - pi.x, g.Lx, g.mx), dy = foldCoord(pj.y - pi.y, g.Ly, g.my), dz = foldCoord(pj.z - pi.z, g.Lz, g.mz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) <= cutOff2;
+}
+
+// BasicNeighbourList_ns::fillBasicNeighbourList (BasicListBase.cuh:42-71). One warp per home cell. The candidates of
+// the 27 neighbour cells are staged once (flat, in the reference's visiting order, already moved to the periodic image
+// nearest the home cell, their sorted index in .w); every home particle is tested against 32 candidates per iteration
+// and the hits are compacted with ballot/popc, which keeps the visiting order without a sort. The staged image makes
+// the common test 7 instructions; a pair within 1e-4 (relative) of the cut-off is re-tested with the reference's exact
+// arithmetic on the original coordinates, so the list stays bit-identical. The lists of the cell's home particles
+// are assembled in shared memory as staged indices and written out TRANSPOSED: in the reference's [k*N + i] layout
+// the entries k of the cell's consecutive home particles are contiguous, so a k-row goes out as one run instead of
+// one 4-byte store per 32-byte sector.
+__global__ void __launch_bounds__(kPairThreads)
 verletFill(const float4 *__restrict__ sortPos, const uint32_t *__restrict__ binStart, GridF g, int ncells, float cutOff2, int N,
            int maxNeighbours, int *__restrict__ neighbourList, int *__restrict__ numberNeighbours, uint32_t *__restrict__ overflow) {
-  __shared__ float4 candAll[kPairWarps][kVerletCap];
+  extern __shared__ __align__(16) unsigned char smemRaw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 *cand = candAll[warp];
+  unsigned char *mine = smemRaw + (size_t)warp * ((kVerletWarpBytes + 15) / 16 * 16);
+  float4 *cand = reinterpret_cast<float4 *>(mine);
+  unsigned short(*lbuf)[kVerletK] = reinterpret_cast<unsigned short(*)[kVerletK]>(mine + kVerletCap * sizeof(float4));
+  int *cntBuf = reinterpret_cast<int *>(mine + kVerletCap * sizeof(float4) + kVerletHome * kVerletK * sizeof(unsigned short));
   const int warpsTotal = gridDim.x * kPairWarps;
+  const bool pairMic = (g.mx != 0.0f && g.nx < 4) || (g.my != 0.0f && g.ny < 4) || (g.mz != 0.0f && g.nz < 4);
+  const float cutLo = cutOff2 * (1.0f - 1e-4f), cutHi = cutOff2 * (1.0f + 1e-4f);
   for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
     const NeighbourCells nc = describeNeighbours(g, cx, cy, cz, binStart, lane);
     const int hStart = __shfl_sync(0xffffffffu, nc.start, nc.centre);
     const int hCount = __shfl_sync(0xffffffffu, nc.count, nc.centre);
     if (hCount == 0) continue;
-    const bool staged = nc.total <= kVerletCap;
+    const bool staged = nc.total <= kVerletCap && !pairMic;
+    const float3 hc = cellCentre(g, cx, cy, cz);
     __syncwarp();
     if (staged) {
       for (int c = 0; c < 27; c++) {
         const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
         const int st = __shfl_sync(0xffffffffu, nc.start, c);
         const int off = __shfl_sync(0xffffffffu, nc.off, c);
-        for (int t = lane; t < cnt; t += 32) cand[off + t] = ldg4(sortPos + st + t);
-      }
-    }
-    __syncwarp();
-    for (int h = 0; h < hCount; h++) {
-      const int id = hStart + h;
-      const float4 pi = ldg4(sortPos + id);
-      int nneigh = 0; // warp uniform
-      bool over = false;
-      for (int c = 0; c < 27 && !over; c++) {
-        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
-        if (cnt == 0) continue;
-        const int st = __shfl_sync(0xffffffffu, nc.start, c);
-        const int off = __shfl_sync(0xffffffffu, nc.off, c);
-        for (int t0 = 0; t0 < cnt; t0 += 32) {
-          const int t = t0 + lane;
-          bool hit = false;
-          if (t < cnt) {
-            const float4 pj = staged ? cand[off + t] : ldg4(sortPos + st + t);
-            const float dx = foldCoord(pj.x - pi.x, g.Lx, g.mx), dy = foldCoord(pj.y - pi.y, g.Ly, g.my),
-                        dz = foldCoord(pj.z - pi.z, g.Lz, g.mz);
-            hit = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) <= cutOff2;
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, hit);
-          const int slot = nneigh + __popc(m & ((1u << lane) - 1u));
-          // the reference stops a particle as soon as its count reaches maxNeighboursPerParticle (:60-63)
-          if (hit && slot + 1 < maxNeighbours) neighbourList[(size_t)slot * N + id] = st + t;
-          nneigh += __popc(m);
-          if (nneigh >= maxNeighbours) { over = true; break; }
+        for (int t = lane; t < cnt; t += 32) {
+          float4 p = ldg4(sortPos + st + t);
+          toHomeImage(p, g, hc);
+          p.w = __int_as_float(st + t);
+          cand[off + t] = p;
         }
       }
-      if (lane == 0) {
-        if (over) atomicMax(overflow, (uint32_t)nneigh);
-        else numberNeighbours[id] = nneigh;
+      __syncwarp();
+      for (int h0 = 0; h0 < hCount; h0 += kVerletHome) {
+        const int nh = min(kVerletHome, hCount - h0);
+        for (int h = 0; h < nh; h++) {
+          const int id = hStart + h0 + h;
+          const float4 piRaw = ldg4(sortPos + id);
+          float4 pi = piRaw;
+          toHomeImage(pi, g, hc);
+          int nneigh = 0; // warp uniform
+          bool over = false;
+          for (int t0 = 0; t0 < nc.total; t0 += 32) {
+            const int t = t0 + lane;
+            bool hit = false;
+            if (t < nc.total) {
+              const float4 pj = cand[t];
+              const float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+              const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+              hit = r2 <= cutLo;
+              if (!hit && r2 <= cutHi) hit = verletHitExact(piRaw, ldg4(sortPos + __float_as_int(pj.w)), g, cutOff2);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const int slot = nneigh + __popc(m & ((1u << lane) - 1u));
+            // the reference stops a particle as soon as its count reaches maxNeighboursPerParticle (:60-63)
+            if (hit && slot + 1 < maxNeighbours) {
+              if (slot < kVerletK) lbuf[h][slot] = (unsigned short)t;
+              else neighbourList[(size_t)slot * N + id] = __float_as_int(cand[t].w); // rare: longer than the shared buffer
+            }
+            nneigh += __popc(m);
+            if (nneigh >= maxNeighbours) { over = true; break; }
+          }
+          if (lane == 0) {
+            cntBuf[h] = over ? -1 : nneigh;
+            if (over) atomicMax(overflow, (uint32_t)nneigh);
+            else numberNeighbours[id] = nneigh;
+          }
+        }
+        __syncwarp();
+        // transposed write-out: lanes = home particles of this pass, one k-row per iteration
+        int myCnt = lane < nh ? cntBuf[lane] : 0;
+        if (myCnt < 0) myCnt = maxNeighbours - 1;
+        myCnt = min(myCnt, kVerletK);
+        int maxCnt = myCnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxCnt = max(maxCnt, __shfl_xor_sync(0xffffffffu, maxCnt, o));
+        for (int k = 0; k < maxCnt; k++)
+          if (k < myCnt) neighbourList[(size_t)k * N + hStart + h0 + lane] = __float_as_int(cand[lbuf[lane][k]].w);
+        __syncwarp();
+      }
+    } else {
+      // dense neighbourhood (or a periodic dimension with < 4 cells): walk the cells straight from global memory
+      for (int h = 0; h < hCount; h++) {
+        const int id = hStart + h;
+        const float4 pi = ldg4(sortPos + id);
+        int nneigh = 0;
+        bool over = false;
+        for (int c = 0; c < 27 && !over; c++) {
+          const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+          if (cnt == 0) continue;
+          const int st = __shfl_sync(0xffffffffu, nc.start, c);
+          for (int t0 = 0; t0 < cnt; t0 += 32) {
+            const int t = t0 + lane;
+            const bool hit = t < cnt && verletHitExact(pi, ldg4(sortPos + st + min(t, cnt - 1)), g, cutOff2);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const int slot = nneigh + __popc(m & ((1u << lane) - 1u));
+            if (hit && slot + 1 < maxNeighbours) neighbourList[(size_t)slot * N + id] = st + t;
+            nneigh += __popc(m);
+            if (nneigh >= maxNeighbours) { over = true; break; }
+          }
+        }
+        if (lane == 0) {
+          if (over) atomicMax(overflow, (uint32_t)nneigh);
+          else numberNeighbours[id] = nneigh;
+        }
       }
     }
   }
@@ -180,11 +250,12 @@ int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const in
     if ((rc = ub200_neighbour_celldim_f32(L, rcut, cd))) return rc;
     if ((rc = ub200_celllist_build_f32(v->cl, v->storedPos.p, nullptr, N, L, periodic, cd, st))) return rc;
     const int needed = (v->cl->ncells + kPairWarps - 1) / kPairWarps;
-    const int grid = needed < kNumSMs * 8 ? needed : kNumSMs * 8;
+    const int grid = needed < kNumSMs * 4 ? needed : kNumSMs * 4;
     while (true) { // fillBasicNeighbourList: retry with 32 more slots until nothing overflows (:176-181)
       if ((rc = v->neighbourList.reserve(sizeof(int) * (size_t)N * (v->maxNeighbours + 1)))) return rc;
       UB200_CUDA(cudaMemsetAsync(v->flags.as<uint32_t>() + 1, 0, sizeof(uint32_t), st));
-      verletFill<<<grid, kPairThreads, 0, st>>>(v->cl->sortPos.as<float4>(), v->cl->binStart.as<uint32_t>(), v->cl->grid, v->cl->ncells,
+      UB200_CUDA(cudaFuncSetAttribute(verletFill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerletSmem));
+      verletFill<<<grid, kPairThreads, kVerletSmem, st>>>(v->cl->sortPos.as<float4>(), v->cl->binStart.as<uint32_t>(), v->cl->grid, v->cl->ncells,
                                                rcut * rcut, N, v->maxNeighbours, v->neighbourList.as<int>(),
                                                v->numberNeighbours.as<int>(), v->flags.as<uint32_t>() + 1);
       UB200_LAUNCHED();

@@ -1,0 +1,141 @@
+"""Secondary legs of bench.py (same timing protocol as the headline: CUDA events on the launching stream, L2 evicted
+before every step, >= 3 warm-up steps):
+  verlet : VerletNVE + PairForces<LJ, VerletList> at the headline workload (what generic_md instantiates)
+  pse    : BDHI::EulerMaruyama<PSE> at BASELINE config 3's single-GPU shape (N = 1e6, L = 256 -> 256^3, fp32, T = 1)
+  bd     : BD::EulerMaruyama ideal particles, N = 1e5 fp64 (config 0)
+each next to the unmodified reference's own CUDA path (oracle/_ref binaries) in the reference arm."""
+import json
+import math
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import torch
+
+PSE_N, PSE_L, PSE_TOL, PSE_PSI, PSE_T, PSE_DT = 1_000_000, 256.0, 1e-3, 0.593, 1.0, 0.01
+
+
+def _timed(dev, step, steps, warmup):
+    scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        scrub.fill_(5)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def verlet(dev, N, Lb, pos, vel, rc, dt, steps=100, warmup=20, equil=300):
+    from .md import Box, LJ, LJMD, VerletList
+    from . import lib
+    pot = LJ(); pot.setPotParameters(0, 0, cutOff=rc)
+    p, v = torch.from_numpy(pos).to(dev), torch.from_numpy(vel).to(dev)
+    f = torch.zeros(N, 4, device=dev)
+    nl = VerletList()
+    md = LJMD(Box(Lb), pot, dt)
+    md.runVerlet(nl, p, v, f, equil)
+    r0 = nl.view().rebuilds
+    l0 = lib().ub200_launch_count()
+    ms = _timed(dev, lambda: md.runVerlet(nl, p, v, f, 1, forcesAreCurrent=True), steps, warmup)
+    return {"metric": "MD steps/s @1e6 LJ particles (VerletList)", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms,
+            "rebuilds_per_step": (nl.view().rebuilds - r0) / float(steps + warmup), "gpu_launches": int(lib().ub200_launch_count() - l0),
+            "what": "VerletNVE + PairForces<LJ, VerletList> (skin 1.08), drift check read back every step like the reference"}
+
+
+def verlet_reference(root, N, Lb, pos, vel, rc, dt, steps=100, warmup=20, equil=300):
+    exe = os.path.join(root, "oracle", "_ref", "ref_lj_verlet")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_lj_verlet was not built"}
+    with tempfile.TemporaryDirectory() as td:
+        pos.tofile(os.path.join(td, "p.bin")); vel.tofile(os.path.join(td, "v.bin"))
+        out = subprocess.run([exe, "md", str(N), str(Lb), str(Lb), str(Lb), str(rc), "1", "1", str(dt), str(warmup + equil), str(steps),
+                              "1", os.path.join(td, "p.bin"), os.path.join(td, "v.bin"), "-"], check=True, capture_output=True,
+                             text=True, timeout=1200).stdout
+    r = [json.loads(l) for l in out.splitlines() if l.startswith("{")][-1]
+    return {"metric": "MD steps/s @1e6 LJ particles (VerletList)", "value": 1000.0 / r["ms_per_step_mean"], "unit": "steps/s",
+            "ms_per_step": r["ms_per_step_mean"], "rebuilds_per_step": r["rebuilds"] / float(steps),
+            "what": "unmodified reference PairForces<LJ, VerletList> + VerletNVE on the same B200"}
+
+
+def _pse_inputs():
+    from . import synthetic as syn
+    pos = np.zeros((PSE_N, 4), np.float32); pos[:, :3] = syn.uniform_cloud(PSE_N, PSE_L, seed=31)[:, :3]
+    force = np.zeros((PSE_N, 4), np.float32); force[:, :3] = syn.gaussian_forces(PSE_N, seed=32, dtype=np.float32)
+    return pos, force
+
+
+def pse(dev, steps=20, warmup=3):
+    from . import bd, lib
+    from . import pse as P
+    pos, force = _pse_inputs()
+    p, f = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)
+    m = P.PSE(p, P.Parameters(PSE_L, viscosity=1.0, hydrodynamicRadius=1.0, tolerance=PSE_TOL, psi=PSE_PSI, temperature=PSE_T,
+                              dt=PSE_DT), sys=bd.System(1234), force=f)
+    integ = P.EulerMaruyama(m, PSE_DT, PSE_T)
+    l0 = lib().ub200_launch_count()
+    ms = _timed(dev, integ.forwardTime, steps, warmup)
+    inf = m.info()
+    # far + near timed alone (deterministic part)
+    MF = torch.zeros(PSE_N, 3, device=dev)
+    m.temperature = 0.0
+    far = _timed(dev, lambda: m.computeMFFarField(MF), 10, 3)
+    near = _timed(dev, lambda: m.computeMFNearField(MF), 10, 3)
+    return {"metric": "PSE steps/s @1e6 particles, 256^3", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "dtype": "f32",
+            "config": {"workload": f"BDHI::EulerMaruyama<PSE>, N={PSE_N}, L={PSE_L}, a=1, tol={PSE_TOL}, psi={PSE_PSI} -> grid "
+                                   f"{tuple(inf.cells)}, support {inf.support}, rcut {inf.rcut:.3f}, T={PSE_T}, dt={PSE_DT}"},
+            "lanczos_iterations": inf.lastLanczosIterations, "far_field_T0_ms": far, "near_field_T0_ms": near,
+            "gpu_launches": int(lib().ub200_launch_count() - l0)}
+
+
+def pse_reference(root, steps=20, warmup=3):
+    exe = os.path.join(root, "oracle", "_ref", "ref_pse_f32")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_pse_f32 was not built"}
+    pos, force = _pse_inputs()
+    with tempfile.TemporaryDirectory() as td:
+        pos.tofile(os.path.join(td, "p.bin")); force.tofile(os.path.join(td, "f.bin"))
+        out = subprocess.run([exe, "time", str(PSE_N), repr(PSE_L), "1.0", "1.0", repr(PSE_TOL), repr(PSE_PSI), "0.0", repr(PSE_T),
+                              repr(PSE_DT), "1234", str(warmup), str(steps), "1", os.path.join(td, "p.bin"), os.path.join(td, "f.bin")],
+                             check=True, capture_output=True, text=True, timeout=1800).stdout
+    r = [json.loads(l) for l in out.splitlines() if l.startswith("{")][-1]
+    return {"metric": "PSE steps/s @1e6 particles, 256^3", "value": r["steps_per_s"], "unit": "steps/s", "ms_per_step": r["ms_per_step"],
+            "dtype": "f32", "what": "unmodified reference BDHI::PSE (cuFFT + cuBLAS Lanczos) on the same B200, same protocol"}
+
+
+def bd_ideal(dev, steps=200, warmup=10):
+    from . import bd
+    N = 100_000
+    rng = np.random.default_rng(1)
+    pos = np.zeros((N, 4)); pos[:, :3] = rng.random((N, 3)) - 0.5
+    p = torch.from_numpy(pos).to(dev)
+    integ = bd.EulerMaruyama(p, bd.Parameters(temperature=1.0, viscosity=1.0, hydrodynamicRadius=1.0, dt=0.1), sys=bd.System(1234))
+    for _ in range(warmup):
+        integ.forwardTime()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        integ.forwardTime()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "BD steps/s @1e5 ideal particles fp64", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms,
+            "what": "BD::EulerMaruyama README example, steps enqueued back to back (one 64 B/particle kernel per step)"}
+
+
+def bd_reference(root, steps=200):
+    exe = os.path.join(root, "oracle", "_ref", "ref_bd")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_bd was not built"}
+    with tempfile.TemporaryDirectory() as td:
+        out = subprocess.run([exe, "100000", str(steps), "1.0", "1.0", "1.0", "0.1", "1234", os.path.join(td, "bd")], check=True,
+                             capture_output=True, text=True, timeout=600).stdout
+    r = [json.loads(l) for l in out.splitlines() if l.startswith("{")][-1]
+    return {"metric": "BD steps/s @1e5 ideal particles fp64", "value": 1000.0 / r["ms_per_step"], "unit": "steps/s",
+            "ms_per_step": r["ms_per_step"], "what": "unmodified reference BD::EulerMaruyama on the same B200"}

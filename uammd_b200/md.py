@@ -385,6 +385,17 @@ class LJMD:
                                                  f3(self.box.boxSize), self.pot.getCutOff(), self._tabp,
                                                  self.pot.ntypes, self.dt, int(nsteps), _stream_ptr(stream)))
 
+    def runVerlet(self, nl, pos, vel, force, nsteps, forcesAreCurrent=False, stream=None):
+        """The same loop over PairForces<LJ, VerletList> (nl: VerletList)."""
+        lib = _declare_verlet()
+        lib.ub200_md_lj_nve_verlet_run_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                       C.c_float * 3, C.c_float, C.POINTER(C.c_float), C.c_int, C.c_float,
+                                                       C.c_int, C.c_int, C.c_void_p]
+        check(lib.ub200_md_lj_nve_verlet_run_f32(self._h, nl._h, _ptr(pos), _ptr(vel), _ptr(force), pos.shape[0],
+                                                 f3(self.box.boxSize), self.pot.getCutOff(), self._tabp, self.pot.ntypes,
+                                                 self.dt, int(nsteps), int(forcesAreCurrent), _stream_ptr(stream)))
+        nl.device = pos.device
+
     def runHost(self, h_pos, h_vel, h_force, nsteps, stream=None):
         """Host (pinned) buffers in/out: H2D, prepare, nsteps, D2H, synchronise."""
         check(_lib.lib().ub200_md_lj_nve_run_host_f32(self._h, _ptr(h_pos), _ptr(h_vel), _ptr(h_force),
