@@ -19,7 +19,7 @@ REF_FCM = os.path.join(ROOT, "oracle", "_ref", "ref_fcm")
 
 # ---------------- FFT ----------------
 @pytest.mark.parametrize("shape", [(16, 16, 16), (128, 128, 128), (24, 20, 18), (30, 14, 6), (9, 15, 7), (64, 32, 4),
-                                   (96, 96, 96)])
+                                   (96, 96, 96), (22, 44, 66), (256, 64, 512), (360, 8, 8)])
 def test_fft3d_matches_numpy_f64(cuda, shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(nx * 7 + ny)
@@ -49,7 +49,7 @@ def test_fft3d_f32(cuda):
 def test_fft3d_rejects_unsupported_size(cuda):
     from uammd_b200 import UB200Error
     with pytest.raises(UB200Error):
-        FFT3D(22, 16, 16)  # factor 11
+        FFT3D(26, 16, 16)  # factor 13 (2, 3, 5, 7 and 11 are supported: nextFFTWiseSize3D emits all of them)
 
 
 # ---------------- IBM ----------------

@@ -77,7 +77,7 @@ template <class T> struct FcmDistState {
   double phaseMs[kPhases] = {};
   int profiledCalls = 0;
   // particle scratch (window)
-  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedPos, sortedVal, sortedOrigin, sortedW;
+  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec, sortedOrigin, sortedW;
 
   size_t slabBytes() const { return (size_t)nzl * plan.ny * plan.nkx * 3 * sizeof(C); }
   size_t tposeBytes() const { return (size_t)plan.nz * nyl * plan.nkx * 3 * sizeof(C); }
@@ -135,7 +135,7 @@ template <class T> struct FcmDistState {
       if (p != rank && peerArena[p]) cudaIpcCloseMemHandle(peerArena[p]);
     if (arena) cudaFree(arena);
     arena = nullptr;
-    DevBuf *b[] = {&errFlag, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedPos, &sortedVal, &sortedOrigin, &sortedW};
+    DevBuf *b[] = {&errFlag, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec, &sortedOrigin, &sortedW};
     for (auto *x : b) x->release();
     plan.release();
   }
@@ -176,9 +176,9 @@ template <class T> struct FcmDistState {
     const int ncw = grid.n[0] * grid.n[1] * grid.zwinN;
     // ---- particles of the window: bin, scan, scatter, order + stencil records ----
     if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N)) || (rc = unstable.reserve(sizeof(int) * (size_t)N)) ||
-        (rc = sortedIndex.reserve(sizeof(int) * (size_t)N)) || (rc = sortedPos.reserve(sizeof(T4) * (size_t)N)) ||
-        (rc = sortedVal.reserve(sizeof(T) * 2 * (size_t)N)) || (rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N)) ||
-        (rc = sortedW.reserve(sizeof(T) * 3 * kSmallSupport * (size_t)N)))
+        (rc = sortedIndex.reserve(sizeof(int) * (size_t)N)) ||
+        (rc = sortedRec.reserve(sizeof(T) * (kern.support == 3 ? RecGeom<T, 3>::REC : RecGeom<T, 4>::REC) * (size_t)N)) ||
+        (rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N)) || (rc = sortedW.reserve(sizeof(T) * 3 * kern.support * (size_t)N)))
       return rc;
     mark(0, st);
     ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
@@ -187,8 +187,8 @@ template <class T> struct FcmDistState {
     if ((rc = scatterToBinsLaunch(codeSlot.as<uint2>(), binStart.as<uint32_t>(), N, unstable.as<int>(), st))) return rc;
 #define UB200_ORDER(SS)                                                                                                  \
   ibmOrderSorted<T4, SS><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(), (const T4 *)pos, \
-                                             (const T *)force, 4, N, grid, kern, sortedIndex.as<int>(), sortedPos.as<T4>(),   \
-                                             sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>())
+                                             (const T *)force, 4, N, grid, kern, sortedIndex.as<int>(), (T4 *)nullptr,        \
+                                             (T *)nullptr, sortedOrigin.as<int4>(), sortedW.as<T>(), sortedRec.as<T>())
     if (kern.support == 3) UB200_ORDER(3); else UB200_ORDER(4);
 #undef UB200_ORDER
     UB200_LAUNCHED();
@@ -198,14 +198,13 @@ template <class T> struct FcmDistState {
     for (int p = 0; p < world; p++) az.peerS[p] = at<C>(peerArena[p], offS);
     if (det) {
       // ---- spread into the owned planes ----
-      dim3 grd((plan.nxPad + kBrickX - 1) / kBrickX, (grid.n[1] + kBrickY - 1) / kBrickY, (nzl + kBrickZ - 1) / kBrickZ);
+      dim3 grd((plan.nxPad + kRbX - 1) / kRbX, (grid.n[1] + kRbY - 1) / kRbY, (nzl + kRbZ - 1) / kRbZ);
 #define UB200_SPREAD(SS)                                                                                                 \
   {                                                                                                                      \
-    auto kfn = ibmSpreadBricks<T4, SS>;                                                                                  \
-    const size_t sm = BrickGeom<T, SS>::smemBytes;                                                                       \
+    auto kfn = ibmSpreadRows<T, SS>;                                                                                     \
+    const size_t sm = RowBrickGeom<T, SS>::smemBytes;                                                                    \
     UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                         \
-    kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(), \
-                                        binStart.as<uint32_t>(), grid, plan.nxPad, S, z0, nzl);                          \
+    kfn<<<grd, kRbThreads, sm, st>>>(sortedRec.as<T>(), binStart.as<uint32_t>(), grid, plan.nxPad, S, z0, nzl);          \
   }
       if (kern.support == 3) UB200_SPREAD(3) else UB200_SPREAD(4)
 #undef UB200_SPREAD

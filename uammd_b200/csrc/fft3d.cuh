@@ -2,6 +2,7 @@
 // instantiate the fused z pass with their own spectral operators.
 #pragma once
 #include "fft.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace ub200 {
@@ -33,13 +34,16 @@ template <class T> struct Fft3dPlan {
       while (units > 1 && nbuf * (size_t)units * perUnit * (n + 1) * sizeof(C) > smemBudget()) units--;
       return units;
     };
-    const int pairs = fit(nx, 3, 4, 2);
+    // experiment knobs (environment): UB200_FFT_TILE = kx per strided tile (1, 2, 4), UB200_FFT_PAIRS = line pairs per x CTA
+    const char *envTile = getenv("UB200_FFT_TILE"), *envPairs = getenv("UB200_FFT_PAIRS");
+    const int maxTile = envTile ? atoi(envTile) : 4, maxPairs = envPairs ? atoi(envPairs) : 4;
+    const int pairs = fit(nx, 3, maxPairs, 2);
     linesPerCta = 2 * pairs;
     smemX = 2 * (size_t)pairs * 3 * (nx + 1) * sizeof(C);
     auto pow2 = [](int v) { return v >= 4 ? 4 : (v >= 2 ? 2 : 1); };
-    tileY = pow2(fit(ny, 3, 4));
+    tileY = pow2(fit(ny, 3, maxTile));
     smemY = 3 * (size_t)tileY * 3 * (ny + 1) * sizeof(C);
-    tileZ = pow2(fit(nz, 3, 4));
+    tileZ = pow2(fit(nz, 3, maxTile));
     smemZ = 3 * (size_t)tileZ * 3 * (nz + 1) * sizeof(C);
     if (smemX > 200 * 1024 || smemY > 200 * 1024 || smemZ > 200 * 1024) return UB200_ERR_UNSUPPORTED;
     return UB200_OK;
@@ -281,7 +285,11 @@ inline int persistentGrid(const void *kern, size_t smem, int ntiles, int threads
 }
 
 // CTA size: the specialised stages split 12 transforms * n/R butterflies evenly over 192 threads
-template <int NFIX> constexpr int fftThreads() { return NFIX > 0 ? 192 : kFftThreads; }
+template <int NFIX> inline int fftThreads() {
+  static const int envThreads = getenv("UB200_FFT_THREADS") ? atoi(getenv("UB200_FFT_THREADS")) : 0;
+  if (envThreads >= 32 && envThreads <= kFftThreads && envThreads % 16 == 0) return envThreads;
+  return NFIX > 0 ? 192 : kFftThreads;
+}
 
 // axis lengths with compile-time specialised kernels (anything else takes the generic mixed-radix path)
 #define UB200_FFT_DISPATCH(n, CALL)                                                                         \

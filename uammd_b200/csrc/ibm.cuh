@@ -115,7 +115,7 @@ __device__ __forceinline__ T supportWeight(const GridT<T> &g, const IbmKernel<T>
 }
 
 // ---------------- small supports: cell-sorted particles + brick-tiled node-centric spread ----------------
-constexpr int kSmallSupport = 4;
+constexpr int kSmallSupport = 7; // largest support served by the sorted (node-centric) kernels
 
 template <class T4>
 __global__ void __launch_bounds__(256)
@@ -143,6 +143,33 @@ ibmBinByCell(const T4 *__restrict__ pos, int N, GridT<decltype(T4::x)> g, uint32
   codeSlot[i] = make_uint2(code, base + rank);
 }
 
+// packed per-particle record of the row-brick spread: 3S one-dimensional weights, the spread value, the support origin
+template <class T, int S> struct RecGeom {
+  static constexpr int W3 = 3 * S;
+  static constexpr int REC = ((sizeof(T) == 8 ? W3 + 4 : W3 + 5)) | 1; // odd number of T words per record
+  // origin: 3 x 16 bit, biased by 16 (origins range from -S to n)
+  __device__ __forceinline__ static void packOrigin(T *rec, int ox, int oy, int oz) {
+    const uint32_t w0 = (uint32_t)((ox + 16) & 0xffff) | ((uint32_t)((oy + 16) & 0xffff) << 16), w1 = (uint32_t)((oz + 16) & 0xffff);
+    if (sizeof(T) == 8) {
+      const unsigned long long u = ((unsigned long long)w1 << 32) | w0;
+      rec[W3 + 3] = (T)__longlong_as_double((long long)u);
+    } else {
+      rec[W3 + 3] = (T)__uint_as_float(w0);
+      rec[W3 + 4] = (T)__uint_as_float(w1);
+    }
+  }
+  __device__ __forceinline__ static void unpackOrigin(const T *rec, int &ox, int &oy, int &oz) {
+    uint32_t w0, w1;
+    if (sizeof(T) == 8) {
+      const unsigned long long u = (unsigned long long)__double_as_longlong((double)rec[W3 + 3]);
+      w0 = (uint32_t)u; w1 = (uint32_t)(u >> 32);
+    } else {
+      w0 = __float_as_uint((float)rec[W3 + 3]); w1 = __float_as_uint((float)rec[W3 + 4]);
+    }
+    ox = (int)(w0 & 0xffff) - 16; oy = (int)(w0 >> 16) - 16; oz = (int)(w1 & 0xffff) - 16;
+  }
+};
+
 // stable order inside each cell; cell-sorted copies of the spread value, of the support origin and of the 3*S
 // one-dimensional weights (window evaluations happen once per particle, here)
 template <class T4, int S>
@@ -152,7 +179,7 @@ ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
                const decltype(T4::x) *__restrict__ val, int valStride, int N, GridT<decltype(T4::x)> g,
                IbmKernel<decltype(T4::x)> k, int *__restrict__ sortedIndex, T4 *__restrict__ sortedPos,
                decltype(T4::x) *__restrict__ sortedVal, int4 *__restrict__ sortedOrigin,
-               decltype(T4::x) *__restrict__ sortedW) {
+               decltype(T4::x) *__restrict__ sortedW, decltype(T4::x) *__restrict__ sortedRec) {
   using T = decltype(T4::x);
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= N) return;
@@ -181,78 +208,96 @@ ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
     for (int i = 0; i < S; i++) wout[d * S + i] = supportWeight(g, k, d, pr[d], o[d], i);
   }
   sortedOrigin[dst] = make_int4(o[0], o[1], o[2], cellOfT(g, 2, pr[2])); // .w: the particle's own z plane (slab ownership)
-  p.w = v0; // {x, y, z, v.x} in one record, {v.y, v.z} next to it
-  sortedPos[dst] = p;
-  sortedVal[2 * (size_t)dst] = v1;
-  sortedVal[2 * (size_t)dst + 1] = v2;
+  if (sortedRec) { // packed record of the row-brick spread: 3S weights, value, origin
+    using R = RecGeom<T, S>;
+    T *rec = sortedRec + (size_t)dst * R::REC;
+#pragma unroll
+    for (int q = 0; q < 3 * S; q++) rec[q] = wout[q];
+    rec[3 * S] = v0; rec[3 * S + 1] = v1; rec[3 * S + 2] = v2;
+    R::packOrigin(rec, o[0], o[1], o[2]);
+  }
+  if (sortedPos) {
+    p.w = v0; // {x, y, z, v.x} in one record, {v.y, v.z} next to it
+    sortedPos[dst] = p;
+    sortedVal[2 * (size_t)dst] = v1;
+    sortedVal[2 * (size_t)dst + 1] = v2;
+  }
 }
 
-// Brick of kBrickX x kBrickY x kBrickZ grid nodes per CTA; every THREAD owns one short x-row of kBrickX nodes
-// and keeps their 3*kBrickX accumulators in registers, so there are no atomics at all. The particles of the
-// brick's halo region (cells that can reach a node of the brick) are staged in shared memory once (origin
-// relative to the brick, 3*S precomputed weights, value); a thread then walks the particles of the (S or S+1)^2
-// region rows around its own row - contiguous in staged order for fixed z - and adds the contributions that
-// land on its nodes. The brick is written out once: no zero fill of the grid, deterministic summation order.
+// ---- row-brick spread ----
+// A CTA owns a brick of kRbX x kRbY x kRbZ grid nodes; a THREAD owns kRbX nodes in x times two consecutive z planes
+// and keeps their accumulators in registers: no atomics, every node is written exactly once (no zero fill of the
+// grid, deterministic summation order). The particles that can reach the brick lie in (kRbY+W) x (kRbZ+W) ROWS of
+// cells, and because the records are sorted by cell with x fastest, each row is ONE contiguous range of the record
+// array (two when the brick touches the periodic x boundary): the set-up is two binStart loads per row and a block
+// scan over a few hundred rows, staging is a flat coalesced copy of packed records (odd word stride: conflict-free
+// in shared memory), and a thread's candidates for a given z row-plane are one contiguous staged range.
 // Particle cells reaching node X in one dimension: X + lo .. X + hi with hi = S/2, lo = -(S-1) + S/2 - (S even)
 // (computeSupportShift lowers P by at most one).
-constexpr int kBrickX = 4, kBrickY = 16, kBrickZ = 16, kBrickThreads = kBrickY * kBrickZ;
-template <class T, int S> struct BrickGeom {
+constexpr int kRbX = 4, kRbY = 16, kRbZ = 16, kRbThreads = kRbY * kRbZ / 2;
+
+template <class T, int S> struct RowBrickGeom {
   static constexpr int hi = S / 2, lo = -(S - 1) + S / 2 - ((S & 1) ? 0 : 1);
-  static constexpr int W = hi - lo; // extra region cells per dimension
-  static constexpr int RX = kBrickX + W, RY = kBrickY + W, RZ = kBrickZ + W;
-  static constexpr int ncells = RX * RY * RZ, nrows = RY * RZ;
-  static constexpr int cap = 512;                 // staged particles per pass
-  static constexpr int REC = 3 * S + 3;           // weights + value per particle (T)
-  static constexpr size_t smemBytes = (size_t)cap * (REC * sizeof(T) + sizeof(int)) + (size_t)(2 * ncells + 1) * sizeof(int) + 64;
+  static constexpr int W = hi - lo;
+  static constexpr int RX = kRbX + W, RY = kRbY + W, RZ = kRbZ + W, nrows = RY * RZ;
+  static constexpr int REC = RecGeom<T, S>::REC;
+  static constexpr int cap = (52 * 1024) / (REC * (int)sizeof(T)); // staged records per pass
+  static constexpr size_t headBytes = (((size_t)nrows * sizeof(int4) + (size_t)(nrows + 1) * sizeof(int) + (size_t)cap * sizeof(unsigned short)) + 15) / 16 * 16;
+  static constexpr size_t smemBytes = headBytes + (size_t)cap * REC * sizeof(T);
 };
 
-template <class T4, int S>
-__global__ void __launch_bounds__(kBrickThreads)
-ibmSpreadBricks(const T4 *__restrict__ sortedPos, const decltype(T4::x) *__restrict__ sortedVal,
-                const int4 *__restrict__ sortedOrigin, const decltype(T4::x) *__restrict__ sortedW,
-                const uint32_t *__restrict__ binStart, GridT<decltype(T4::x)> g, int nxPad,
-                decltype(T4::x) *__restrict__ grid3, int zPlane0, int nzLocal) {
+// d = node - origin folded into [0, n) for periodic dimensions (a single wrap suffices: |d| < n)
+__device__ __forceinline__ int foldIndex(int d, int n, bool periodic) {
+  if (periodic) { d += d < 0 ? n : 0; d -= d >= n ? n : 0; }
+  return d;
+}
+
+template <class T, int S>
+__global__ void __launch_bounds__(kRbThreads)
+ibmSpreadRows(const T *__restrict__ sortedRec, const uint32_t *__restrict__ binStart, GridT<T> g, int nxPad,
+              T *__restrict__ grid3, int zPlane0, int nzLocal) {
   // zPlane0 / nzLocal: the z planes [zPlane0, zPlane0 + nzLocal) this launch writes; grid3 starts at plane zPlane0
   // (the whole grid on one GPU: 0, n[2])
-  using T = decltype(T4::x);
-  using G = BrickGeom<T, S>;
+  using G = RowBrickGeom<T, S>;
+  constexpr int REC = G::REC;
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  T *recs = reinterpret_cast<T *>(smemRaw);                        // [cap][REC]
-  int *org = reinterpret_cast<int *>(recs + (size_t)G::cap * G::REC); // [cap] packed origin relative to the brick
-  int *cellOff = org + G::cap;                                     // [ncells+1] staged-order prefix of region cells
-  int *cellGStart = cellOff + G::ncells + 1;                       // [ncells] first sorted slot of each region cell
-  __shared__ int warpTot[kBrickThreads / 32];
+  int4 *rowSeg = reinterpret_cast<int4 *>(smemRaw);                  // [nrows] {startA, countA, startB, countB}
+  int *rowOff = reinterpret_cast<int *>(rowSeg + G::nrows);          // [nrows + 1] staged-order prefix
+  unsigned short *recRow = reinterpret_cast<unsigned short *>(rowOff + G::nrows + 1); // [cap] row of a staged record
+  T *recs = reinterpret_cast<T *>(smemRaw + G::headBytes);           // [cap][REC]
+  __shared__ int warpTot[kRbThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ty = tid % kBrickY, tz = tid / kBrickY;
-  const int bx0 = blockIdx.x * kBrickX, by0 = blockIdx.y * kBrickY, bz0 = zPlane0 + blockIdx.z * kBrickZ;
+  const int ty = tid % kRbY, tzp = tid / kRbY; // this thread: nodes (bx0.., by0 + ty, bz0 + 2 tzp {, +1})
+  const int bx0 = blockIdx.x * kRbX, by0 = blockIdx.y * kRbY, bz0 = zPlane0 + blockIdx.z * kRbZ;
+  const bool px = g.m[0] != T(0), py = g.m[1] != T(0), pz = g.m[2] != T(0);
 
-  // ---- region cell populations -> exclusive prefix (block scan); thread t owns cells [t*per, (t+1)*per) ----
-  constexpr int per = (G::ncells + kBrickThreads - 1) / kBrickThreads;
+  // ---- rows of the region -> record ranges -> exclusive prefix (block scan) ----
+  constexpr int per = (G::nrows + kRbThreads - 1) / kRbThreads;
   int cnt[per];
   int mine = 0;
 #pragma unroll
   for (int q = 0; q < per; q++) {
-    const int c = tid * per + q;
+    const int r = tid * per + q;
     cnt[q] = 0;
-    if (c < G::ncells) {
-      int gs = 0;
-      const int rx = c % G::RX, ry = (c / G::RX) % G::RY, rz = c / (G::RX * G::RY);
-      int cx = bx0 + G::lo + rx, cy = by0 + G::lo + ry, cz = bz0 + G::lo + rz;
+    if (r < G::nrows) {
+      int4 seg = make_int4(0, 0, 0, 0);
+      int cy = by0 + G::lo + r % G::RY, cz = bz0 + G::lo + r / G::RY;
       bool ok = true;
-      // unwrapped -> actual cell (periodic image) or nothing (non periodic / beyond one wrap)
-      if (cx < 0 || cx >= g.n[0]) { if (g.m[0] != T(0)) cx += cx < 0 ? g.n[0] : -g.n[0]; else ok = false; }
-      if (cy < 0 || cy >= g.n[1]) { if (g.m[1] != T(0)) cy += cy < 0 ? g.n[1] : -g.n[1]; else ok = false; }
-      if (cz < 0 || cz >= g.n[2]) { if (g.m[2] != T(0)) cz += cz < 0 ? g.n[2] : -g.n[2]; else ok = false; }
-      ok = ok && cx >= 0 && cx < g.n[0] && cy >= 0 && cy < g.n[1] && cz >= 0 && cz < g.n[2];
+      if (cy < 0 || cy >= g.n[1]) { if (py) cy += cy < 0 ? g.n[1] : -g.n[1]; else ok = false; }
+      if (cz < 0 || cz >= g.n[2]) { if (pz) cz += cz < 0 ? g.n[2] : -g.n[2]; else ok = false; }
+      ok = ok && cy >= 0 && cy < g.n[1] && cz >= 0 && cz < g.n[2] && bx0 < g.n[0]; // bricks of pure padding write zeros
       int lz = 0;
       if (ok) { lz = windowZ(g, cz); ok = lz < g.zwinN; }
       if (ok) {
-        const uint32_t cell = (uint32_t)cx + (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)lz);
-        const uint32_t s0 = __ldg(binStart + cell), s1 = __ldg(binStart + cell + 1);
-        gs = (int)s0;
-        cnt[q] = (int)(s1 - s0);
+        const uint32_t *rowBin = binStart + (size_t)g.n[0] * ((size_t)cy + (size_t)g.n[1] * (size_t)lz);
+        const int a = bx0 + G::lo, b = bx0 + kRbX - 1 + G::hi; // unwrapped x cells of the region
+        const int a0 = max(a, 0), b0 = min(b, g.n[0] - 1);
+        if (a0 <= b0) { seg.x = (int)__ldg(rowBin + a0); seg.y = (int)__ldg(rowBin + b0 + 1) - seg.x; }
+        if (px && a < 0) { seg.z = (int)__ldg(rowBin + a + g.n[0]); seg.w = (int)__ldg(rowBin + g.n[0]) - seg.z; }
+        else if (px && b >= g.n[0]) { seg.z = (int)__ldg(rowBin); seg.w = (int)__ldg(rowBin + min(b - g.n[0], g.n[0] - 1) + 1) - seg.z; }
       }
-      cellGStart[c] = gs;
+      rowSeg[r] = seg;
+      cnt[q] = seg.y + seg.w;
     }
     mine += cnt[q];
   }
@@ -266,98 +311,96 @@ ibmSpreadBricks(const T4 *__restrict__ sortedPos, const decltype(T4::x) *__restr
   __syncthreads();
   int warpOff = 0, total = 0;
 #pragma unroll
-  for (int q = 0; q < kBrickThreads / 32; q++) {
+  for (int q = 0; q < kRbThreads / 32; q++) {
     if (q < warp) warpOff += warpTot[q];
     total += warpTot[q];
   }
   int run = warpOff + inc - mine;
 #pragma unroll
   for (int q = 0; q < per; q++) {
-    const int c = tid * per + q;
-    if (c < G::ncells) cellOff[c] = run;
+    const int r = tid * per + q;
+    if (r < G::nrows) rowOff[r] = run;
     run += cnt[q];
   }
-  if (tid == 0) cellOff[G::ncells] = total;
+  if (tid == 0) rowOff[G::nrows] = total;
   __syncthreads();
 
-  T acc[kBrickX][3];
+  T acc[kRbX][2][3];
 #pragma unroll
-  for (int q = 0; q < kBrickX; q++) acc[q][0] = acc[q][1] = acc[q][2] = T(0);
+  for (int q = 0; q < kRbX; q++)
+#pragma unroll
+    for (int z = 0; z < 2; z++) acc[q][z][0] = acc[q][z][1] = acc[q][z][2] = T(0);
+  const int Y = by0 + ty, Z0 = bz0 + 2 * tzp;
 
   for (int chunk0 = 0; chunk0 < total; chunk0 += G::cap) {
-    // ---- stage: one thread per staged particle; its region row by binary search, its cell by a short walk ----
-    const int nstage = min(G::cap, total - chunk0);
-    for (int slot = tid; slot < nstage; slot += kBrickThreads) {
-      const int t = chunk0 + slot;
-      int loc = 0, hic = G::ncells; // largest c with cellOff[c] <= t (cellOff[ncells] = total > t)
-      while (hic - loc > 1) {
-        const int mid = (loc + hic) >> 1;
-        if (cellOff[mid] <= t) loc = mid; else hic = mid;
-      }
-      const int c = loc;
-      const int src = cellGStart[c] + (t - cellOff[c]);
-      const int rx = c % G::RX, ry = (c / G::RX) % G::RY, rz = c / (G::RX * G::RY);
-      const int rc[3] = {rx, ry, rz};
-      const int b0[3] = {bx0, by0, bz0};
-      const int4 og = sortedOrigin[src];
-      const int oabs[3] = {og.x, og.y, og.z};
-      int packed = 0;
+    // ---- stage: row owners label the staged slots of this chunk, then one thread per record copies it ----
 #pragma unroll
-      for (int d = 0; d < 3; d++) {
-        // actual cell from the region coordinate; support shift P = cell - origin; origin relative to the brick
-        // from the (unwrapped) region coordinate, valid for any periodic image
-        int cell = b0[d] + G::lo + rc[d];
-        if (cell < 0) cell += g.n[d]; else if (cell >= g.n[d]) cell -= g.n[d];
-        const int rel = G::lo + rc[d] - (cell - oabs[d]);
-        packed |= ((rel + 64) & 0xff) << (8 * d);
+    for (int q = 0; q < per; q++) {
+      const int r = tid * per + q;
+      if (r < G::nrows) {
+        const int lo = max(rowOff[r], chunk0), hi2 = min(rowOff[r] + cnt[q], chunk0 + G::cap);
+        for (int j = lo; j < hi2; j++) recRow[j - chunk0] = (unsigned short)r;
       }
-      org[slot] = packed;
-      const T *wsrc = sortedW + (size_t)src * (3 * S);
-#pragma unroll
-      for (int q = 0; q < 3 * S; q++) recs[q * G::cap + slot] = wsrc[q]; // field-major: lanes hit distinct banks
-      recs[(3 * S) * G::cap + slot] = sortedPos[src].w;
-      recs[(3 * S + 1) * G::cap + slot] = sortedVal[2 * (size_t)src];
-      recs[(3 * S + 2) * G::cap + slot] = sortedVal[2 * (size_t)src + 1];
     }
     __syncthreads();
-    // ---- my row of nodes: for each dz the region rows ty .. ty+W are contiguous in staged order ----
-    for (int dz = 0; dz <= G::W; dz++) {
-      const int r0 = ty + G::RY * (tz + dz);
-      int b = cellOff[r0 * G::RX] - chunk0, e = cellOff[(r0 + G::W + 1) * G::RX] - chunk0;
+    const int nstage = min(G::cap, total - chunk0);
+    for (int slot = tid; slot < nstage; slot += kRbThreads) {
+      const int r = recRow[slot];
+      const int4 seg = rowSeg[r];
+      const int j = chunk0 + slot - rowOff[r]; // position inside the row: segment A first, then B
+      const size_t src = j < seg.y ? (size_t)seg.x + j : (size_t)seg.z + (j - seg.y);
+      const T *sp = sortedRec + src * REC;
+      T *dp = recs + (size_t)slot * REC;
+#pragma unroll
+      for (int w = 0; w < REC; w++) dp[w] = __ldg(sp + w);
+    }
+    __syncthreads();
+    // ---- candidates of my nodes: for every z row-plane the rows ty .. ty+W are one contiguous staged range ----
+    for (int rz = 2 * tzp; rz <= 2 * tzp + 1 + G::W; rz++) {
+      const int r0 = ty + G::RY * rz;
+      int b = rowOff[r0] - chunk0, e = rowOff[r0 + G::W + 1] - chunk0;
       b = max(b, 0); e = min(e, G::cap);
       for (int s = b; s < e; s++) {
-        const int pk = org[s];
-        const int iy = ty - (((pk >> 8) & 0xff) - 64), iz = tz - (((pk >> 16) & 0xff) - 64);
-        if ((unsigned)iy >= (unsigned)S || (unsigned)iz >= (unsigned)S) continue;
-        const T *rec = recs + s;
-        const T wyz = rec[(S + iy) * G::cap] * rec[(2 * S + iz) * G::cap];
-        const T v0 = rec[(3 * S) * G::cap], v1 = rec[(3 * S + 1) * G::cap], v2 = rec[(3 * S + 2) * G::cap];
-        const int relx = (pk & 0xff) - 64;
+        const T *rec = recs + (size_t)s * REC;
+        int ox, oy, oz;
+        RecGeom<T, S>::unpackOrigin(rec, ox, oy, oz);
+        const int iy = foldIndex(Y - oy, g.n[1], py);
+        if ((unsigned)iy >= (unsigned)S) continue;
+        const int iz0 = foldIndex(Z0 - oz, g.n[2], pz), iz1 = foldIndex(Z0 + 1 - oz, g.n[2], pz);
+        const bool v0ok = (unsigned)iz0 < (unsigned)S, v1ok = (unsigned)iz1 < (unsigned)S;
+        if (!v0ok && !v1ok) continue;
+        const T wy = rec[S + iy];
+        const T wz0 = v0ok ? rec[2 * S + iz0] : T(0), wz1 = v1ok ? rec[2 * S + iz1] : T(0);
+        const T f0 = rec[3 * S], f1 = rec[3 * S + 1], f2 = rec[3 * S + 2];
 #pragma unroll
-        for (int lx = 0; lx < kBrickX; lx++) {
-          const int ix = lx - relx;
+        for (int lx = 0; lx < kRbX; lx++) {
+          const int ix = foldIndex(bx0 + lx - ox, g.n[0], px);
           if ((unsigned)ix < (unsigned)S) {
-            const T wgt = rec[ix * G::cap] * wyz;
-            acc[lx][0] += v0 * wgt;
-            acc[lx][1] += v1 * wgt;
-            acc[lx][2] += v2 * wgt;
+            const T wxy = rec[ix] * wy;
+            const T w0 = wxy * wz0, w1 = wxy * wz1;
+            acc[lx][0][0] += f0 * w0; acc[lx][0][1] += f1 * w0; acc[lx][0][2] += f2 * w0;
+            acc[lx][1][0] += f0 * w1; acc[lx][1][1] += f1 * w1; acc[lx][1][2] += f2 * w1;
           }
         }
       }
     }
     __syncthreads();
   }
-  const int Y = by0 + ty, Z = bz0 + tz;
-  if (Y < g.n[1] && Z < zPlane0 + nzLocal) {
+  if (Y < g.n[1]) {
 #pragma unroll
-    for (int lx = 0; lx < kBrickX; lx++) {
-      const int X = bx0 + lx;
-      if (X < nxPad) {
-        T *out = grid3 + 3 * ((size_t)X + (size_t)nxPad * ((size_t)Y + (size_t)g.n[1] * (Z - zPlane0)));
-        const bool real = X < g.n[0];
-        out[0] = real ? acc[lx][0] : T(0);
-        out[1] = real ? acc[lx][1] : T(0);
-        out[2] = real ? acc[lx][2] : T(0);
+    for (int z = 0; z < 2; z++) {
+      const int Z = Z0 + z;
+      if (Z >= zPlane0 + nzLocal) continue;
+#pragma unroll
+      for (int lx = 0; lx < kRbX; lx++) {
+        const int X = bx0 + lx;
+        if (X < nxPad) {
+          T *out = grid3 + 3 * ((size_t)X + (size_t)nxPad * ((size_t)Y + (size_t)g.n[1] * (Z - zPlane0)));
+          const bool real = X < g.n[0];
+          out[0] = real ? acc[lx][z][0] : T(0);
+          out[1] = real ? acc[lx][z][1] : T(0);
+          out[2] = real ? acc[lx][z][2] : T(0);
+        }
       }
     }
   }

@@ -14,8 +14,17 @@ template <class T> struct IbmState {
   IbmKernel<T> kern;
   int nxPad = 0;
   bool nodeCentric = false;
-  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedPos, sortedVal, sortedOrigin, sortedW;
+  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec, sortedOrigin, sortedW;
   int sortedValidFor = -1;
+  bool sortedGather = false; // thread-per-particle gather over the sorted records (supports 3, 4)
+  int recWords() const {
+    switch (kern.support) {
+    case 3: return RecGeom<T, 3>::REC;
+    case 4: return RecGeom<T, 4>::REC;
+    case 5: return RecGeom<T, 5>::REC;
+    default: return RecGeom<T, 7>::REC;
+    }
+  }
 
   int init(const double L[3], const int periodic[3], const int cells[3], const ub200_ibm_kernel &k, int nxPad_) {
     grid = makeGridT<T>(L, periodic, cells);
@@ -28,14 +37,16 @@ template <class T> struct IbmState {
     nxPad = nxPad_;
     if (k.support < 1 || k.support > kMaxSupport) return UB200_ERR_INVALID_ARGUMENT;
     const long long ncells = (long long)grid.n[0] * grid.n[1] * grid.n[2];
-    nodeCentric = (k.support == 3 || k.support == 4) && ncells <= 4096LL * 4096LL;
+    nodeCentric = (k.support == 3 || k.support == 4 || k.support == 5 || k.support == 7) && ncells <= 4096LL * 4096LL;
     for (int d = 0; d < 3; d++)
       if (grid.m[d] != T(0) && grid.n[d] < k.support + 1) nodeCentric = false; // support would overlap itself
+    if (grid.n[0] < kRbX + k.support || grid.n[0] > 65000 || grid.n[1] > 65000 || grid.n[2] > 65000) nodeCentric = false;
+    sortedGather = nodeCentric && k.support <= 4;
     if (grid.n[2] == 1) nodeCentric = false; // 2-D grids take the generic path
     return UB200_OK;
   }
   void release() {
-    DevBuf *b[] = {&binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedPos, &sortedVal, &sortedOrigin, &sortedW};
+    DevBuf *b[] = {&binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec, &sortedOrigin, &sortedW};
     for (auto *x : b) x->release();
   }
 
@@ -53,26 +64,26 @@ template <class T> struct IbmState {
     if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N))) return rc;
     if ((rc = unstable.reserve(sizeof(int) * (size_t)N))) return rc;
     if ((rc = sortedIndex.reserve(sizeof(int) * (size_t)N))) return rc;
-    if ((rc = sortedPos.reserve(sizeof(T4) * (size_t)N))) return rc;
-    if ((rc = sortedVal.reserve(sizeof(T) * 2 * (size_t)N))) return rc;
     if ((rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N))) return rc;
-    if ((rc = sortedW.reserve(sizeof(T) * 3 * kSmallSupport * (size_t)N))) return rc;
+    if ((rc = sortedW.reserve(sizeof(T) * 3 * kern.support * (size_t)N))) return rc;
+    if ((rc = sortedRec.reserve(sizeof(T) * recWords() * (size_t)N))) return rc;
     const int nb = (N + 255) / 256;
     ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
     UB200_LAUNCHED();
     if ((rc = exclusiveScanAndClear(binCount.as<uint32_t>(), ncells, binStart.as<uint32_t>(), tileSums.as<uint32_t>(), st)))
       return rc;
     if ((rc = scatterToBinsLaunch(codeSlot.as<uint2>(), binStart.as<uint32_t>(), N, unstable.as<int>(), st))) return rc;
-    if (kern.support == 3)
-      ibmOrderSorted<T4, 3><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(),
-                                                (const T4 *)pos, (const T *)val, valStride, N, grid, kern,
-                                                sortedIndex.as<int>(), sortedPos.as<T4>(), sortedVal.as<T>(),
-                                                sortedOrigin.as<int4>(), sortedW.as<T>());
-    else
-      ibmOrderSorted<T4, 4><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(),
-                                                (const T4 *)pos, (const T *)val, valStride, N, grid, kern,
-                                                sortedIndex.as<int>(), sortedPos.as<T4>(), sortedVal.as<T>(),
-                                                sortedOrigin.as<int4>(), sortedW.as<T>());
+#define UB200_ORDER(SS)                                                                                                  \
+  ibmOrderSorted<T4, SS><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(), (const T4 *)pos, \
+                                             (const T *)val, valStride, N, grid, kern, sortedIndex.as<int>(), (T4 *)nullptr,    \
+                                             (T *)nullptr, sortedOrigin.as<int4>(), sortedW.as<T>(), sortedRec.as<T>())
+    switch (kern.support) {
+    case 3: UB200_ORDER(3); break;
+    case 4: UB200_ORDER(4); break;
+    case 5: UB200_ORDER(5); break;
+    default: UB200_ORDER(7); break;
+    }
+#undef UB200_ORDER
     UB200_LAUNCHED();
     sortedValidFor = N;
     return UB200_OK;
@@ -84,20 +95,21 @@ template <class T> struct IbmState {
     if (nodeCentric) {
       int rc = prepare(pos, val, valStride, N, st);
       if (rc) return rc;
-      dim3 grd((nxPad + kBrickX - 1) / kBrickX, (grid.n[1] + kBrickY - 1) / kBrickY, (grid.n[2] + kBrickZ - 1) / kBrickZ);
-      if (kern.support == 3) {
-        auto kfn = ibmSpreadBricks<T4, 3>;
-        const size_t sm = BrickGeom<T, 3>::smemBytes;
-        UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(),
-                                            binStart.as<uint32_t>(), grid, nxPad, grid3, 0, grid.n[2]);
-      } else {
-        auto kfn = ibmSpreadBricks<T4, 4>;
-        const size_t sm = BrickGeom<T, 4>::smemBytes;
-        UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        kfn<<<grd, kBrickThreads, sm, st>>>(sortedPos.as<T4>(), sortedVal.as<T>(), sortedOrigin.as<int4>(), sortedW.as<T>(),
-                                            binStart.as<uint32_t>(), grid, nxPad, grid3, 0, grid.n[2]);
+      dim3 grd((nxPad + kRbX - 1) / kRbX, (grid.n[1] + kRbY - 1) / kRbY, (grid.n[2] + kRbZ - 1) / kRbZ);
+#define UB200_SPREAD(SS)                                                                                                 \
+  {                                                                                                                      \
+    auto kfn = ibmSpreadRows<T, SS>;                                                                                     \
+    const size_t sm = RowBrickGeom<T, SS>::smemBytes;                                                                    \
+    UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                         \
+    kfn<<<grd, kRbThreads, sm, st>>>(sortedRec.as<T>(), binStart.as<uint32_t>(), grid, nxPad, grid3, 0, grid.n[2]);      \
+  }
+      switch (kern.support) {
+      case 3: UB200_SPREAD(3) break;
+      case 4: UB200_SPREAD(4) break;
+      case 5: UB200_SPREAD(5) break;
+      default: UB200_SPREAD(7) break;
       }
+#undef UB200_SPREAD
       UB200_LAUNCHED();
       return UB200_OK;
     }
@@ -113,7 +125,7 @@ template <class T> struct IbmState {
   // reuseRecords: positions are the ones of the preceding spread on this state
   int gather(const void *pos, int N, const T *grid3, T *out3, bool accumulate, bool reuseRecords, cudaStream_t st) {
     using T4 = typename Real4<T>::type;
-    if (nodeCentric) {
+    if (nodeCentric && sortedGather) {
       if (!(reuseRecords && sortedValidFor == N)) {
         int rc = prepare(pos, nullptr, 0, N, st);
         if (rc) return rc;

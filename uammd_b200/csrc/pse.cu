@@ -562,7 +562,6 @@ template <class T> struct PseState {
     const int periodic[3] = {1, 1, 1};
     const double Ld[3] = {par.L[0], par.L[1], par.L[2]};
     if ((rc = ibm.init(Ld, periodic, cells, k, plan.nxPad))) return rc;
-    ibm.nodeCentric = false;
     if ((rc = grid.reserve(plan.gridBytes()))) return rc;
     return UB200_OK;
   }
