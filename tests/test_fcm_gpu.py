@@ -60,6 +60,7 @@ def _cloud(N, L, seed, dtype=np.float64):
 
 
 @pytest.mark.parametrize("kname,cells,L", [("p3", (32, 32, 32), (32.0,) * 3), ("p4", (24, 20, 16), (12.0, 10.0, 8.0)),
+                                           ("p4", (40, 36, 32), (20.0, 18.0, 16.0)), ("p3", (19, 21, 23), (9.5, 10.5, 11.5)),
                                            ("p3", (64, 32, 7), (6.4, 3.2, 4.9)), ("gauss", (32, 32, 32), (32.0,) * 3)])
 def test_ibm_spread_gather_match_oracle(orc, cuda, kname, cells, L):
     h = min(L[d] / cells[d] for d in range(3))

@@ -77,7 +77,7 @@ template <class T> struct FcmDistState {
   double phaseMs[kPhases] = {};
   int profiledCalls = 0;
   // particle scratch (window)
-  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec, sortedOrigin, sortedW;
+  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec;
 
   size_t slabBytes() const { return (size_t)nzl * plan.ny * plan.nkx * 3 * sizeof(C); }
   size_t tposeBytes() const { return (size_t)plan.nz * nyl * plan.nkx * 3 * sizeof(C); }
@@ -97,6 +97,7 @@ template <class T> struct FcmDistState {
     const int S = k.support;
     const int hi = S / 2, lo = -(S - 1) + S / 2 - ((S & 1) ? 0 : 1);
     if (nzl + (hi - lo) > cells[2]) return UB200_ERR_INVALID_ARGUMENT;
+    if (cells[0] < kRbX + S || cells[1] < kRbY + S || cells[2] < kRbZ + S) return UB200_ERR_INVALID_ARGUMENT; // row-brick spread
     grid.zwin0 = ((z0 + lo) % cells[2] + cells[2]) % cells[2];
     grid.zwinN = nzl + (hi - lo);
     kern.kind = k.kind; kern.support = k.support; kern.invh = (T)(1.0 / k.h);
@@ -135,7 +136,7 @@ template <class T> struct FcmDistState {
       if (p != rank && peerArena[p]) cudaIpcCloseMemHandle(peerArena[p]);
     if (arena) cudaFree(arena);
     arena = nullptr;
-    DevBuf *b[] = {&errFlag, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec, &sortedOrigin, &sortedW};
+    DevBuf *b[] = {&errFlag, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec};
     for (auto *x : b) x->release();
     plan.release();
   }
@@ -177,8 +178,7 @@ template <class T> struct FcmDistState {
     // ---- particles of the window: bin, scan, scatter, order + stencil records ----
     if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N)) || (rc = unstable.reserve(sizeof(int) * (size_t)N)) ||
         (rc = sortedIndex.reserve(sizeof(int) * (size_t)N)) ||
-        (rc = sortedRec.reserve(sizeof(T) * (kern.support == 3 ? RecGeom<T, 3>::REC : RecGeom<T, 4>::REC) * (size_t)N)) ||
-        (rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N)) || (rc = sortedW.reserve(sizeof(T) * 3 * kern.support * (size_t)N)))
+        (rc = sortedRec.reserve(sizeof(T) * (kern.support == 3 ? RecGeom<T, 3>::REC : RecGeom<T, 4>::REC) * (size_t)N)))
       return rc;
     mark(0, st);
     ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
@@ -187,8 +187,7 @@ template <class T> struct FcmDistState {
     if ((rc = scatterToBinsLaunch(codeSlot.as<uint2>(), binStart.as<uint32_t>(), N, unstable.as<int>(), st))) return rc;
 #define UB200_ORDER(SS)                                                                                                  \
   ibmOrderSorted<T4, SS><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(), (const T4 *)pos, \
-                                             (const T *)force, 4, N, grid, kern, sortedIndex.as<int>(), (T4 *)nullptr,        \
-                                             (T *)nullptr, sortedOrigin.as<int4>(), sortedW.as<T>(), sortedRec.as<T>())
+                                             (const T *)force, 4, N, grid, kern, sortedIndex.as<int>(), sortedRec.as<T>())
     if (kern.support == 3) UB200_ORDER(3); else UB200_ORDER(4);
 #undef UB200_ORDER
     UB200_LAUNCHED();
@@ -257,10 +256,10 @@ template <class T> struct FcmDistState {
     for (int p = 0; p < world; p++) { slabs.p[p] = at<T>(peerArena[p], offS); outs.p[p] = at<T>(peerArena[p], offOut); }
     const int ngb = (N + 127) / 128;
     if (kern.support == 3)
-      ibmGatherSortedDist<T, 3><<<ngb, 128, 0, st>>>(sortedOrigin.as<int4>(), sortedW.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
+      ibmGatherSortedDist<T, 3><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
                                                     grid, plan.nxPad, slabs, z0, nzl, world, outs);
     else
-      ibmGatherSortedDist<T, 4><<<ngb, 128, 0, st>>>(sortedOrigin.as<int4>(), sortedW.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
+      ibmGatherSortedDist<T, 4><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
                                                     grid, plan.nxPad, slabs, z0, nzl, world, outs);
     UB200_LAUNCHED();
     mark(10, st);

@@ -148,8 +148,10 @@ template <class T, int S> struct RecGeom {
   static constexpr int W3 = 3 * S;
   static constexpr int REC = ((sizeof(T) == 8 ? W3 + 4 : W3 + 5)) | 1; // odd number of T words per record
   // origin: 3 x 16 bit, biased by 16 (origins range from -S to n)
-  __device__ __forceinline__ static void packOrigin(T *rec, int ox, int oy, int oz) {
-    const uint32_t w0 = (uint32_t)((ox + 16) & 0xffff) | ((uint32_t)((oy + 16) & 0xffff) << 16), w1 = (uint32_t)((oz + 16) & 0xffff);
+  // cz: the particle's own z plane (slab ownership of the distributed gather)
+  __device__ __forceinline__ static void packOrigin(T *rec, int ox, int oy, int oz, int cz) {
+    const uint32_t w0 = (uint32_t)((ox + 16) & 0xffff) | ((uint32_t)((oy + 16) & 0xffff) << 16),
+                   w1 = (uint32_t)((oz + 16) & 0xffff) | ((uint32_t)(cz & 0xffff) << 16);
     if (sizeof(T) == 8) {
       const unsigned long long u = ((unsigned long long)w1 << 32) | w0;
       rec[W3 + 3] = (T)__longlong_as_double((long long)u);
@@ -159,6 +161,10 @@ template <class T, int S> struct RecGeom {
     }
   }
   __device__ __forceinline__ static void unpackOrigin(const T *rec, int &ox, int &oy, int &oz) {
+    int cz;
+    unpackOrigin(rec, ox, oy, oz, cz);
+  }
+  __device__ __forceinline__ static void unpackOrigin(const T *rec, int &ox, int &oy, int &oz, int &cz) {
     uint32_t w0, w1;
     if (sizeof(T) == 8) {
       const unsigned long long u = (unsigned long long)__double_as_longlong((double)rec[W3 + 3]);
@@ -166,7 +172,7 @@ template <class T, int S> struct RecGeom {
     } else {
       w0 = __float_as_uint((float)rec[W3 + 3]); w1 = __float_as_uint((float)rec[W3 + 4]);
     }
-    ox = (int)(w0 & 0xffff) - 16; oy = (int)(w0 >> 16) - 16; oz = (int)(w1 & 0xffff) - 16;
+    ox = (int)(w0 & 0xffff) - 16; oy = (int)(w0 >> 16) - 16; oz = (int)(w1 & 0xffff) - 16; cz = (int)(w1 >> 16);
   }
 };
 
@@ -177,9 +183,7 @@ __global__ void __launch_bounds__(256)
 ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeSlot,
                const uint32_t *__restrict__ binStart, const T4 *__restrict__ pos,
                const decltype(T4::x) *__restrict__ val, int valStride, int N, GridT<decltype(T4::x)> g,
-               IbmKernel<decltype(T4::x)> k, int *__restrict__ sortedIndex, T4 *__restrict__ sortedPos,
-               decltype(T4::x) *__restrict__ sortedVal, int4 *__restrict__ sortedOrigin,
-               decltype(T4::x) *__restrict__ sortedW, decltype(T4::x) *__restrict__ sortedRec) {
+               IbmKernel<decltype(T4::x)> k, int *__restrict__ sortedIndex, decltype(T4::x) *__restrict__ sortedRec) {
   using T = decltype(T4::x);
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= N) return;
@@ -191,7 +195,7 @@ ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
   for (int j = s; j < e; j++) rank += (__ldg(unstable + j) < i);
   const int dst = s + rank;
   sortedIndex[dst] = i;
-  T4 p = pos[i];
+  const T4 p = pos[i];
   T v0 = T(0), v1 = T(0), v2 = T(0);
   if (val) {
     const T *vp = val + (size_t)i * valStride;
@@ -199,29 +203,17 @@ ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
   }
   const T pr[3] = {p.x, p.y, p.z};
   int o[3];
-  T *wout = sortedW + (size_t)dst * (3 * S);
+  using R = RecGeom<T, S>;
+  T *rec = sortedRec + (size_t)dst * R::REC;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     const int cell = cellOfT(g, d, pr[d]);
     o[d] = supportOrigin(g, k, d, pr[d], cell);
 #pragma unroll
-    for (int i = 0; i < S; i++) wout[d * S + i] = supportWeight(g, k, d, pr[d], o[d], i);
+    for (int i = 0; i < S; i++) rec[d * S + i] = supportWeight(g, k, d, pr[d], o[d], i);
   }
-  sortedOrigin[dst] = make_int4(o[0], o[1], o[2], cellOfT(g, 2, pr[2])); // .w: the particle's own z plane (slab ownership)
-  if (sortedRec) { // packed record of the row-brick spread: 3S weights, value, origin
-    using R = RecGeom<T, S>;
-    T *rec = sortedRec + (size_t)dst * R::REC;
-#pragma unroll
-    for (int q = 0; q < 3 * S; q++) rec[q] = wout[q];
-    rec[3 * S] = v0; rec[3 * S + 1] = v1; rec[3 * S + 2] = v2;
-    R::packOrigin(rec, o[0], o[1], o[2]);
-  }
-  if (sortedPos) {
-    p.w = v0; // {x, y, z, v.x} in one record, {v.y, v.z} next to it
-    sortedPos[dst] = p;
-    sortedVal[2 * (size_t)dst] = v1;
-    sortedVal[2 * (size_t)dst + 1] = v2;
-  }
+  rec[3 * S] = v0; rec[3 * S + 1] = v1; rec[3 * S + 2] = v2;
+  R::packOrigin(rec, o[0], o[1], o[2], cellOfT(g, 2, pr[2]));
 }
 
 // ---- row-brick spread ----
@@ -242,7 +234,7 @@ template <class T, int S> struct RowBrickGeom {
   static constexpr int RX = kRbX + W, RY = kRbY + W, RZ = kRbZ + W, nrows = RY * RZ;
   static constexpr int REC = RecGeom<T, S>::REC;
   static constexpr int cap = (52 * 1024) / (REC * (int)sizeof(T)); // staged records per pass
-  static constexpr size_t headBytes = (((size_t)nrows * sizeof(int4) + (size_t)(nrows + 1) * sizeof(int) + (size_t)cap * sizeof(unsigned short)) + 15) / 16 * 16;
+  static constexpr size_t headBytes = (((size_t)nrows * sizeof(int4) + (size_t)(nrows + 1) * sizeof(int) + (size_t)cap * sizeof(int) + (size_t)cap * sizeof(unsigned short)) + 15) / 16 * 16;
   static constexpr size_t smemBytes = headBytes + (size_t)cap * REC * sizeof(T);
 };
 
@@ -263,7 +255,8 @@ ibmSpreadRows(const T *__restrict__ sortedRec, const uint32_t *__restrict__ binS
   extern __shared__ __align__(16) unsigned char smemRaw[];
   int4 *rowSeg = reinterpret_cast<int4 *>(smemRaw);                  // [nrows] {startA, countA, startB, countB}
   int *rowOff = reinterpret_cast<int *>(rowSeg + G::nrows);          // [nrows + 1] staged-order prefix
-  unsigned short *recRow = reinterpret_cast<unsigned short *>(rowOff + G::nrows + 1); // [cap] row of a staged record
+  int *relOrg = rowOff + G::nrows + 1;                               // [cap] packed brick-relative origin of a staged record
+  unsigned short *recRow = reinterpret_cast<unsigned short *>(relOrg + G::cap); // [cap] row of a staged record
   T *recs = reinterpret_cast<T *>(smemRaw + G::headBytes);           // [cap][REC]
   __shared__ int warpTot[kRbThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -352,36 +345,49 @@ ibmSpreadRows(const T *__restrict__ sortedRec, const uint32_t *__restrict__ binS
       const T *sp = sortedRec + src * REC;
       T *dp = recs + (size_t)slot * REC;
 #pragma unroll
-      for (int w = 0; w < REC; w++) dp[w] = __ldg(sp + w);
+      for (int w = 0; w < 3 * S + 3; w++) dp[w] = __ldg(sp + w);
+      // origin relative to the brick, at the periodic image that overlaps it: the node loops then need no folding
+      int ox, oy, oz;
+      RecGeom<T, S>::unpackOrigin(sp, ox, oy, oz);
+      int rx = ox - bx0, ry = oy - by0, rzz = oz - bz0;
+      // (a staged record lies within one support of the brick, so exactly one image is in [-(S-1), brick size))
+      if (px) { if (rx > kRbX - 1) rx -= g.n[0]; else if (rx < -(S - 1)) rx += g.n[0]; }
+      if (py) { if (ry > kRbY - 1) ry -= g.n[1]; else if (ry < -(S - 1)) ry += g.n[1]; }
+      if (pz) { if (rzz > kRbZ - 1) rzz -= g.n[2]; else if (rzz < -(S - 1)) rzz += g.n[2]; }
+      relOrg[slot] = ((rx + 128) & 0xff) | (((ry + 128) & 0xff) << 8) | (((rzz + 128) & 0xff) << 16);
     }
     __syncthreads();
-    // ---- candidates of my nodes: for every z row-plane the rows ty .. ty+W are one contiguous staged range ----
-    for (int rz = 2 * tzp; rz <= 2 * tzp + 1 + G::W; rz++) {
-      const int r0 = ty + G::RY * rz;
-      int b = rowOff[r0] - chunk0, e = rowOff[r0 + G::W + 1] - chunk0;
-      b = max(b, 0); e = min(e, G::cap);
-      for (int s = b; s < e; s++) {
-        const T *rec = recs + (size_t)s * REC;
-        int ox, oy, oz;
-        RecGeom<T, S>::unpackOrigin(rec, ox, oy, oz);
-        const int iy = foldIndex(Y - oy, g.n[1], py);
-        if ((unsigned)iy >= (unsigned)S) continue;
-        const int iz0 = foldIndex(Z0 - oz, g.n[2], pz), iz1 = foldIndex(Z0 + 1 - oz, g.n[2], pz);
-        const bool v0ok = (unsigned)iz0 < (unsigned)S, v1ok = (unsigned)iz1 < (unsigned)S;
-        if (!v0ok && !v1ok) continue;
-        const T wy = rec[S + iy];
-        const T wz0 = v0ok ? rec[2 * S + iz0] : T(0), wz1 = v1ok ? rec[2 * S + iz1] : T(0);
-        const T f0 = rec[3 * S], f1 = rec[3 * S + 1], f2 = rec[3 * S + 2];
+    // ---- candidates of my nodes: for every z row-plane the rows ty .. ty+W are one contiguous staged range; the
+    //      W+2 planes are walked as ONE loop so that a lane idles only when its own candidates are exhausted ----
+    int plane = 0, sIdx = 0, sEnd = 0;
+    while (true) {
+      while (sIdx >= sEnd) {
+        if (plane > G::W + 1) break;
+        const int r0 = ty + G::RY * (2 * tzp + plane);
+        sIdx = max(rowOff[r0] - chunk0, 0);
+        sEnd = min(rowOff[r0 + G::W + 1] - chunk0, G::cap);
+        plane++;
+      }
+      if (sIdx >= sEnd) break;
+      const int s = sIdx++;
+      const int pk = relOrg[s];
+      const int iy = ty - (((pk >> 8) & 0xff) - 128);
+      const int iz0 = 2 * tzp - (((pk >> 16) & 0xff) - 128);
+      const bool v0ok = (unsigned)iz0 < (unsigned)S, v1ok = (unsigned)(iz0 + 1) < (unsigned)S;
+      if ((unsigned)iy >= (unsigned)S || !(v0ok || v1ok)) continue;
+      const T *rec = recs + (size_t)s * REC;
+      const T wy = rec[S + iy];
+      const T wz0 = v0ok ? rec[2 * S + iz0] : T(0), wz1 = v1ok ? rec[2 * S + iz0 + 1] : T(0);
+      const T wyz0 = wy * wz0, wyz1 = wy * wz1;
+      const T f0 = rec[3 * S], f1 = rec[3 * S + 1], f2 = rec[3 * S + 2];
+      const int ix0 = -((pk & 0xff) - 128);
 #pragma unroll
-        for (int lx = 0; lx < kRbX; lx++) {
-          const int ix = foldIndex(bx0 + lx - ox, g.n[0], px);
-          if ((unsigned)ix < (unsigned)S) {
-            const T wxy = rec[ix] * wy;
-            const T w0 = wxy * wz0, w1 = wxy * wz1;
-            acc[lx][0][0] += f0 * w0; acc[lx][0][1] += f1 * w0; acc[lx][0][2] += f2 * w0;
-            acc[lx][1][0] += f0 * w1; acc[lx][1][1] += f1 * w1; acc[lx][1][2] += f2 * w1;
-          }
-        }
+      for (int lx = 0; lx < kRbX; lx++) {
+        const int ix = ix0 + lx;
+        const T wx = (unsigned)ix < (unsigned)S ? rec[ix] : T(0);
+        const T w0 = wx * wyz0, w1 = wx * wyz1;
+        acc[lx][0][0] += f0 * w0; acc[lx][0][1] += f1 * w0; acc[lx][0][2] += f2 * w0;
+        acc[lx][1][0] += f0 * w1; acc[lx][1][1] += f1 * w1; acc[lx][1][2] += f2 * w1;
       }
     }
     __syncthreads();
@@ -410,16 +416,15 @@ ibmSpreadRows(const T *__restrict__ sortedRec, const uint32_t *__restrict__ binS
 // support origin and weights precomputed by ibmOrderSorted, S^3 node loads fully unrolled.
 template <class T, int S, bool ACCUMULATE>
 __global__ void __launch_bounds__(128)
-ibmGatherSorted(const int4 *__restrict__ sortedOrigin, const T *__restrict__ sortedW,
-                const int *__restrict__ sortedIndex, int N, GridT<T> g, int nxPad, const T *__restrict__ grid3,
-                T *__restrict__ out3) {
+ibmGatherSorted(const T *__restrict__ sortedRec, const int *__restrict__ sortedIndex, int N, GridT<T> g, int nxPad,
+                const T *__restrict__ grid3, T *__restrict__ out3) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= N) return;
-  const int4 og = sortedOrigin[slot];
-  const int o[3] = {og.x, og.y, og.z};
+  const T *wsrc = sortedRec + (size_t)slot * RecGeom<T, S>::REC;
+  int o[3];
+  RecGeom<T, S>::unpackOrigin(wsrc, o[0], o[1], o[2]);
   T w[3][S];
   int cidx[3][S];
-  const T *wsrc = sortedW + (size_t)slot * (3 * S);
 #pragma unroll
   for (int d = 0; d < 3; d++)
 #pragma unroll
@@ -457,17 +462,16 @@ template <class T> struct PeerTable { T *p[kMaxPeers]; };
 
 template <class T, int S>
 __global__ void __launch_bounds__(128)
-ibmGatherSortedDist(const int4 *__restrict__ sortedOrigin, const T *__restrict__ sortedW,
-                    const int *__restrict__ sortedIndex, const uint32_t *__restrict__ binStart, GridT<T> g, int nxPad,
-                    PeerTable<T> slabs, int z0, int nzl, int world, PeerTable<T> outs) {
+ibmGatherSortedDist(const T *__restrict__ sortedRec, const int *__restrict__ sortedIndex, const uint32_t *__restrict__ binStart,
+                    GridT<T> g, int nxPad, PeerTable<T> slabs, int z0, int nzl, int world, PeerTable<T> outs) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= (int)binStart[g.n[0] * g.n[1] * g.zwinN]) return;
-  const int4 og = sortedOrigin[slot];
-  if (og.w < z0 || og.w >= z0 + nzl) return; // a neighbour's particle
-  const int o[3] = {og.x, og.y, og.z};
+  const T *wsrc = sortedRec + (size_t)slot * RecGeom<T, S>::REC;
+  int o[3], cz;
+  RecGeom<T, S>::unpackOrigin(wsrc, o[0], o[1], o[2], cz);
+  if (cz < z0 || cz >= z0 + nzl) return; // a neighbour's particle
   T w[3][S];
   int cidx[3][S];
-  const T *wsrc = sortedW + (size_t)slot * (3 * S);
 #pragma unroll
   for (int d = 0; d < 3; d++)
 #pragma unroll

@@ -14,7 +14,7 @@ template <class T> struct IbmState {
   IbmKernel<T> kern;
   int nxPad = 0;
   bool nodeCentric = false;
-  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec, sortedOrigin, sortedW;
+  DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec;
   int sortedValidFor = -1;
   bool sortedGather = false; // thread-per-particle gather over the sorted records (supports 3, 4)
   int recWords() const {
@@ -40,13 +40,16 @@ template <class T> struct IbmState {
     nodeCentric = (k.support == 3 || k.support == 4 || k.support == 5 || k.support == 7) && ncells <= 4096LL * 4096LL;
     for (int d = 0; d < 3; d++)
       if (grid.m[d] != T(0) && grid.n[d] < k.support + 1) nodeCentric = false; // support would overlap itself
+    // the row-brick spread stages ONE periodic image of a particle per brick: a periodic dimension must be longer than
+    // a brick plus a support (smaller grids take the generic path); origins are packed in 16 bits
     if (grid.n[0] < kRbX + k.support || grid.n[0] > 65000 || grid.n[1] > 65000 || grid.n[2] > 65000) nodeCentric = false;
+    if ((grid.m[1] != T(0) && grid.n[1] < kRbY + k.support) || (grid.m[2] != T(0) && grid.n[2] < kRbZ + k.support)) nodeCentric = false;
     sortedGather = nodeCentric && k.support <= 4;
     if (grid.n[2] == 1) nodeCentric = false; // 2-D grids take the generic path
     return UB200_OK;
   }
   void release() {
-    DevBuf *b[] = {&binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec, &sortedOrigin, &sortedW};
+    DevBuf *b[] = {&binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec};
     for (auto *x : b) x->release();
   }
 
@@ -64,8 +67,6 @@ template <class T> struct IbmState {
     if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N))) return rc;
     if ((rc = unstable.reserve(sizeof(int) * (size_t)N))) return rc;
     if ((rc = sortedIndex.reserve(sizeof(int) * (size_t)N))) return rc;
-    if ((rc = sortedOrigin.reserve(sizeof(int4) * (size_t)N))) return rc;
-    if ((rc = sortedW.reserve(sizeof(T) * 3 * kern.support * (size_t)N))) return rc;
     if ((rc = sortedRec.reserve(sizeof(T) * recWords() * (size_t)N))) return rc;
     const int nb = (N + 255) / 256;
     ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
@@ -75,8 +76,7 @@ template <class T> struct IbmState {
     if ((rc = scatterToBinsLaunch(codeSlot.as<uint2>(), binStart.as<uint32_t>(), N, unstable.as<int>(), st))) return rc;
 #define UB200_ORDER(SS)                                                                                                  \
   ibmOrderSorted<T4, SS><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(), (const T4 *)pos, \
-                                             (const T *)val, valStride, N, grid, kern, sortedIndex.as<int>(), (T4 *)nullptr,    \
-                                             (T *)nullptr, sortedOrigin.as<int4>(), sortedW.as<T>(), sortedRec.as<T>())
+                                             (const T *)val, valStride, N, grid, kern, sortedIndex.as<int>(), sortedRec.as<T>())
     switch (kern.support) {
     case 3: UB200_ORDER(3); break;
     case 4: UB200_ORDER(4); break;
@@ -132,7 +132,7 @@ template <class T> struct IbmState {
       }
       const int nb = (N + 127) / 128;
 #define UB200_GATHER(SS, ACC)                                                                                 \
-  ibmGatherSorted<T, SS, ACC><<<nb, 128, 0, st>>>(sortedOrigin.as<int4>(), sortedW.as<T>(), sortedIndex.as<int>(), N, grid, nxPad, grid3, out3)
+  ibmGatherSorted<T, SS, ACC><<<nb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), N, grid, nxPad, grid3, out3)
       if (kern.support == 3) { if (accumulate) UB200_GATHER(3, true); else UB200_GATHER(3, false); }
       else { if (accumulate) UB200_GATHER(4, true); else UB200_GATHER(4, false); }
 #undef UB200_GATHER
