@@ -10,6 +10,12 @@
  *   uammd::b200::LJ               Potential::LJ with access to its device parameter table.
  *   uammd::b200::PairForcesLJ     Interactor (Interactor/Interactor.cuh:56-119) = PairForces<Potential::LJ, CellList>
  *                                 with the specialised LJ traversal (Interactor/PairForces.cu:43-78).
+ *   uammd::b200::VerletList       NeighbourList concept with a skin (Interactor/NeighbourList/VerletList.cuh:83-201): the list
+ *                                 is built by our CUDA path in the reference's VerletListData layout, bit for bit, so
+ *                                 PairForces<AnyPotential, b200::VerletList> runs user Transversers through the reference's
+ *                                 own kernel; b200::PairForcesLJ takes it as its neighbour list for the fast LJ path.
+ *   uammd::b200::PSE              BDHI Method concept for BDHI::EulerMaruyama<Method> = BDHI::PSE (BDHI_PSE.cuh:82-176).
+ *   uammd::b200::BDEulerMaruyama  Integrator = BD::EulerMaruyama (Integrator/BrownianDynamics.cuh:111-126).
  *   uammd::b200::FCM<Kernel>      BDHI Method concept (Integrator/BDHI/BDHI_FCM.cuh:85-153) for
  *                                 BDHI::EulerMaruyama<Method> (Integrator/BDHI/BDHI_EulerMaruyama.cuh:64-98).
  * Error codes of the C ABI are converted into the reference's exception convention (std::runtime_error).
@@ -19,6 +25,8 @@
 #include "uammd.cuh"
 #include "Interactor/Interactor.cuh"
 #include "Interactor/NeighbourList/CellList.cuh"
+#include "Interactor/NeighbourList/VerletList.cuh"
+#include "Integrator/Integrator.cuh"
 #include "Interactor/Potential/Potential.cuh"
 #include "Integrator/BDHI/BDHI.cuh"
 #include "Integrator/BDHI/FCM/FCM_kernels.cuh"
@@ -27,6 +35,7 @@
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace uammd {
 namespace b200 {
@@ -134,6 +143,92 @@ public:
   shared_ptr<ParticleGroup> getGroup() { return pg; }
 };
 
+/* ---------------------------------------------------------------- VerletList -------------------------------- */
+class VerletList {
+  shared_ptr<ParticleGroup> pg;
+  ub200_verletlist *handle = nullptr;
+  connection posWriteConnection, reorderConnection;
+  bool forceNextUpdate = true, reordered = true;
+  Box currentBox = Box();
+  real currentCutOff = 0;
+  /* BasicNeighbourListData carries a StrideIterator whose types are protected members of BasicNeighbourListBase */
+  struct MakeData : BasicNeighbourListBase {
+    static BasicNeighbourListData make(const ub200_verletlist_view &v) {
+      BasicNeighbourListData nl;
+      nl.neighbourList = v.d_neighbourList;
+      nl.numberNeighbours = v.d_numberNeighbours;
+      nl.sortPos = reinterpret_cast<const real4 *>(v.d_sortPos);
+      nl.groupIndex = v.d_groupIndex;
+      nl.particleStride = StrideIterator(CountingIterator(0), NeighbourListOffsetFunctor(v.particleStride));
+      return nl;
+    }
+  };
+
+public:
+  VerletList(shared_ptr<ParticleData> pd) : VerletList(std::make_shared<ParticleGroup>(pd, "All")) {}
+  VerletList(shared_ptr<ParticleGroup> pg) : pg(pg) {
+    check(ub200_verletlist_create(&handle), "verletlist_create");
+    auto pd = pg->getParticleData();
+    posWriteConnection = pd->getPosWriteRequestedSignal()->connect([this]() { this->forceNextUpdate = true; });
+    reorderConnection = pd->getReorderSignal()->connect([this]() { this->forceNextUpdate = true; this->reordered = true; });
+  }
+  VerletList(const VerletList &) = delete;
+  ~VerletList() {
+    posWriteConnection.disconnect();
+    reorderConnection.disconnect();
+    ub200_verletlist_destroy(handle);
+  }
+
+  /* VerletList::update (VerletList.cuh:111-124): the wrapper-level flag only gates the call; the drift check inside
+     decides about the rebuild, a particle reorder forces it (handleReorder :185-190) */
+  void update(Box box, real cutOff, cudaStream_t st = 0) {
+    if (!(forceNextUpdate or box != currentBox or cutOff != currentCutOff)) return;
+    forceNextUpdate = false;
+    auto pd = pg->getParticleData();
+    pd->hintSortByHash(box, make_real3(cutOff * 0.5));
+    currentBox = box;
+    currentCutOff = cutOff;
+    auto pos = pd->getPos(access::location::gpu, access::mode::read);
+    const int *gidx = pg->getIndicesRawPtr(access::location::gpu);
+    const float L[3] = {box.boxSize.x, box.boxSize.y, box.boxSize.z};
+    const int periodic[3] = {box.isPeriodicX(), box.isPeriodicY(), box.isPeriodicZ()};
+    check(ub200_verletlist_update_f32(handle, pos.raw(), gidx, pg->getNumberParticles(), L, periodic, cutOff, reordered, nullptr,
+                                      (void *)st),
+          "verletlist_update");
+    reordered = false;
+  }
+  void update(Box box, real3 cutOff, cudaStream_t st = 0) {
+    if (cutOff.x != cutOff.y or cutOff.x != cutOff.z) throw std::runtime_error("[VerletList] Invalid argument");
+    update(box, cutOff.x, st);
+  }
+
+  template <class Transverser> void transverseList(Transverser &tr, cudaStream_t st = 0) {
+    const int N = pg->getNumberParticles();
+    const int Nthreads = 128;
+    const int Nblocks = N / Nthreads + ((N % Nthreads) ? 1 : 0);
+    auto globalIndex = pg->getIndexIterator(access::location::gpu);
+    SFINAE::TransverserAdaptor<Transverser>::prepare(tr, pg->getParticleData());
+    size_t shMemorySize = SFINAE::SharedMemorySizeDelegator<Transverser>().getSharedMemorySize(tr);
+    NeighbourList_ns::transverseWithNeighbourContainer<<<Nblocks, Nthreads, shMemorySize, st>>>(
+        tr, globalIndex, this->getNeighbourContainer(), N);
+    CudaCheckError();
+  }
+
+  VerletListBase::VerletListData getVerletList() {
+    ub200_verletlist_view v;
+    check(ub200_verletlist_view_get(handle, &v), "verletlist_view_get");
+    return MakeData::make(v);
+  }
+  VerletListBase_ns::NeighbourContainer getNeighbourContainer() { return VerletListBase_ns::NeighbourContainer(getVerletList()); }
+  void setCutOffMultiplier(real m) { check(ub200_verletlist_set_cutoff_multiplier(handle, m), "set_cutoff_multiplier"); }
+  int getNumberOfStepsSinceLastUpdate() {
+    ub200_verletlist_view v;
+    check(ub200_verletlist_view_get(handle, &v), "verletlist_view_get");
+    return v.stepsSinceLastUpdate;
+  }
+  ub200_verletlist *getHandle() { return handle; }
+};
+
 /* ---------------------------------------------------------------- LJ ---------------------------------------- */
 /* Radial<LJFunctor> keeps its PairParameters table {cutOff2, sigma2, epsilonDivSigma2, shift} in a protected
    BasicParameterHandler (Potential/RadialPotential.cuh:55-58, ParameterHandler.cuh:41-65); deriving exposes it. */
@@ -151,6 +246,7 @@ public:
 
 class PairForcesLJ : public Interactor {
   shared_ptr<CellList> nl;
+  shared_ptr<VerletList> vl; // when set, the Verlet list is the neighbour list (PairForces<LJ, VerletList>)
   shared_ptr<LJ> pot;
   Box box;
 
@@ -158,12 +254,13 @@ public:
   struct Parameters {
     Box box = Box(std::numeric_limits<real>::infinity());
     shared_ptr<CellList> nl = nullptr;
+    shared_ptr<VerletList> verletList = nullptr;
   };
   PairForcesLJ(shared_ptr<ParticleData> pd, Parameters par, shared_ptr<LJ> pot)
       : PairForcesLJ(std::make_shared<ParticleGroup>(pd, "All"), par, pot) {}
   PairForcesLJ(shared_ptr<ParticleGroup> pg, Parameters par, shared_ptr<LJ> pot)
-      : Interactor(pg, "b200::PairForcesLJ"), nl(par.nl), pot(pot), box(par.box) {
-    if (!nl) nl = std::make_shared<CellList>(pg);
+      : Interactor(pg, "b200::PairForcesLJ"), nl(par.nl), vl(par.verletList), pot(pot), box(par.box) {
+    if (!nl and !vl) nl = std::make_shared<CellList>(pg);
   }
 
   void updateBox(Box newBox) override { box = newBox; }
@@ -173,12 +270,21 @@ public:
     const real rcut = pot->getCutOff();
     if (box.boxSize.x <= 3 * rcut and box.boxSize.y <= 3 * rcut and box.boxSize.z <= 3 * rcut)
       throw std::runtime_error("[uammd_b200] box <= 3 rcut in every dimension needs the NBody path (PairForces.cu:49-53)");
-    nl->update(box, rcut, st);
+    if (vl) vl->update(box, rcut, st);
+    else nl->update(box, rcut, st);
     auto force = comp.force ? pd->getForce(access::location::gpu, access::mode::readwrite).raw() : nullptr;
     auto energy = comp.energy ? pd->getEnergy(access::location::gpu, access::mode::readwrite).raw() : nullptr;
     auto virial = comp.virial ? pd->getVirial(access::location::gpu, access::mode::readwrite).raw() : nullptr;
     const auto table = pot->getDeviceTable();
     const int *gidx = pg->getIndicesRawPtr(access::location::gpu);
+    if (vl) {
+      // the Verlet entry point takes the host copy of the table (tiny; cached on the device by the library)
+      std::vector<float> host((size_t)table.ntypes * table.ntypes * 4);
+      CudaSafeCall(cudaMemcpyAsync(host.data(), table.d_params, host.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CudaSafeCall(cudaStreamSynchronize(st));
+      check(ub200_lj_sum_verlet_f32(vl->getHandle(), host.data(), table.ntypes, force, energy, virial, gidx, (void *)st), "lj_sum_verlet");
+      return;
+    }
     check(ub200_lj_sum_devparams_f32(nl->getHandle(), table.d_params, table.ntypes, force, energy, virial, gidx,
                                      (void *)st),
           "lj_sum");
@@ -286,6 +392,116 @@ public:
     return 1.0l / (6.0l * M_PIl * viscosity * rh) * (1.0l - c * a + (4.0l / 3.0l) * M_PIl * a3 - a6pref * a3 * a3);
   }
   ub200_fcm *getHandle() { return handle; }
+};
+
+/* ---------------------------------------------------------------- PSE --------------------------------------- */
+/* BDHI Method concept = BDHI::PSE (Integrator/BDHI/BDHI_PSE.cuh:82-176). Parameter resolution (grid, Gaussian support,
+   eta, near-field cut-off and table) happens inside ub200_pse_create with the reference constructors' rules. */
+class PSE {
+  shared_ptr<ParticleGroup> pg;
+  ub200_pse *handle = nullptr;
+  real hydrodynamicRadius, M0, temperature, dt;
+
+public:
+  struct Parameters : BDHI::Parameters {
+    real psi = 0.5;
+    real shearStrain = 0;
+  };
+  PSE(shared_ptr<ParticleData> pd, Parameters par) : PSE(std::make_shared<ParticleGroup>(pd, "All"), par) {}
+  PSE(shared_ptr<ParticleGroup> pg, Parameters par)
+      : pg(pg), hydrodynamicRadius(par.hydrodynamicRadius), temperature(par.temperature), dt(par.dt) {
+    {
+      long double rh = par.hydrodynamicRadius, L = par.box.boxSize.x, a = rh / L, a3 = a * a * a;
+      const long double c = 2.83729747948061947666591710460773907l, b = 0.19457l;
+      const long double a6pref = 16.0l * M_PIl * M_PIl / 45.0l + 630.0L * b * b;
+      M0 = 1.0l / (6.0l * M_PIl * par.viscosity * rh) * (1.0l - c * a + (4.0l / 3.0l) * M_PIl * a3 - a6pref * a3 * a3);
+    }
+    if (par.tolerance > 0.1) throw std::invalid_argument("Tolerance too high");
+    auto sys = pg->getParticleData()->getSystem();
+    const uint seedNear = sys->rng().next32(), seedFar = sys->rng().next32(); /* same draw order as the reference */
+    ub200_pse_params p;
+    p.L[0] = par.box.boxSize.x; p.L[1] = par.box.boxSize.y; p.L[2] = par.box.boxSize.z;
+    p.viscosity = par.viscosity; p.hydrodynamicRadius = par.hydrodynamicRadius; p.tolerance = par.tolerance;
+    p.psi = par.psi; p.shearStrain = par.shearStrain;
+    p.cellsOverride[0] = p.cellsOverride[1] = p.cellsOverride[2] = 0;
+    check(ub200_pse_create(&handle, (int)sizeof(real), &p, seedNear, seedFar), "pse_create");
+  }
+  PSE(const PSE &) = delete;
+  ~PSE() { ub200_pse_destroy(handle); }
+
+  void setup_step(cudaStream_t st = 0) {}
+  void finish_step(cudaStream_t st = 0) {}
+  void computeMF(real3 *MF, cudaStream_t st) {
+    auto pd = pg->getParticleData();
+    const int N = pg->getNumberParticles();
+    CudaSafeCall(cudaMemsetAsync(MF, 0, N * sizeof(real3), st));
+    auto pos = pd->getPos(access::gpu, access::read);
+    auto force = pd->getForce(access::gpu, access::read);
+    const uint seed2 = temperature > real(0) ? pd->getSystem()->rng().next32() : 0u;
+    check(ub200_pse_far_mdot(handle, pos.raw(), force.raw(), N, temperature, 1.0 / sqrt((double)dt), seed2, MF, (void *)st), "pse_far");
+    check(ub200_pse_near_mdot(handle, pos.raw(), force.raw(), 4, N, MF, (void *)st), "pse_near");
+  }
+  void computeBdW(real3 *BdW, cudaStream_t st) {
+    if (temperature == real(0)) return;
+    auto pd = pg->getParticleData();
+    auto pos = pd->getPos(access::gpu, access::read);
+    const uint seed2 = pd->getSystem()->rng().next32();
+    check(ub200_pse_near_noise(handle, pos.raw(), pg->getNumberParticles(), temperature, 1.0, seed2, BdW, nullptr, (void *)st), "pse_noise");
+  }
+  void computeDivM(real3 *divM, cudaStream_t st = 0) {}
+  void setShearStrain(real s) { check(ub200_pse_set_shear_strain(handle, s), "pse_shear"); }
+  real getHydrodynamicRadius() { return hydrodynamicRadius; }
+  real getSelfMobility() { return M0; }
+};
+
+/* ---------------------------------------------------------------- BD::EulerMaruyama ------------------------- */
+/* Integrator (Integrator/BrownianDynamics.cuh:111-126): forwardTime = steps++, interactor forces, position update
+   through ub200_bd_euler_maruyama_step (bit-identical positions, tests/test_bd_gpu.py). */
+class BDEulerMaruyama : public Integrator {
+  real temperature, dt, selfMobility;
+  bool is2D;
+  uint seed;
+  int steps = 0;
+  cudaStream_t st;
+
+public:
+  struct Parameters {
+    real temperature = 0, viscosity = 1, hydrodynamicRadius = -1, dt = 0;
+    bool is2D = false;
+  };
+  BDEulerMaruyama(shared_ptr<ParticleData> pd, Parameters par) : BDEulerMaruyama(std::make_shared<ParticleGroup>(pd, "All"), par) {}
+  BDEulerMaruyama(shared_ptr<ParticleGroup> pg, Parameters par)
+      : Integrator(pg, "b200::BDEulerMaruyama"), temperature(par.temperature), dt(par.dt), is2D(par.is2D) {
+    sys->rng().next32();
+    sys->rng().next32();
+    seed = sys->rng().next32();
+    selfMobility = 1.0 / (6.0 * M_PI * par.viscosity);
+    if (par.hydrodynamicRadius != real(-1.0)) selfMobility /= par.hydrodynamicRadius;
+    CudaSafeCall(cudaStreamCreate(&st));
+  }
+  ~BDEulerMaruyama() { cudaStreamDestroy(st); }
+  uint getSeed() const { return seed; }
+  void forwardTime() override {
+    steps++;
+    for (auto u : updatables) u->updateSimulationTime(steps * dt);
+    const int N = pg->getNumberParticles();
+    const real4 *d_force = nullptr;
+    if (!interactors.empty()) {
+      {
+        auto force = pd->getForce(access::location::gpu, access::mode::write);
+        auto fg = pg->getPropertyIterator(force);
+        thrust::fill(thrust::cuda::par.on(st), fg, fg + N, real4());
+      }
+      for (auto f : interactors) f->sum({.force = true, .energy = false, .virial = false}, st);
+    }
+    auto pos = pd->getPos(access::location::gpu, access::mode::readwrite);
+    auto force = pd->getForce(access::location::gpu, access::mode::read);
+    if (!interactors.empty()) d_force = force.raw();
+    const real *radius = nullptr;
+    check(ub200_bd_euler_maruyama_step((int)sizeof(real), pos.raw(), pg->getIndicesRawPtr(access::location::gpu), d_force, nullptr,
+                                       selfMobility, radius, dt, is2D, temperature, N, (uint)steps, seed, (void *)st),
+          "bd_euler_maruyama_step");
+  }
 };
 
 } // namespace b200

@@ -33,3 +33,14 @@ def test_fcm_dropin_matches_reference():
     print(r)
     assert r["max_dpos_vs_reference"] < 1e-12
     assert abs(r["a"] - 1.0) < 1e-12
+
+
+def test_verlet_bd_pse_dropin_matches_reference():
+    r = _run("dropin_more", 50000, 40.0)
+    print(r)
+    assert r["verlet_generic_vs_ref"] == 0.0             # reference traversal + functor over OUR Verlet list: same bits
+    assert r["verlet_fast_vs_ref"] < 1e-4                # specialised LJ traversal over the list (units of max |F|)
+    assert r["bd_max_dpos"] == 0.0                       # b200::BDEulerMaruyama: bit-identical positions after 50 steps
+    assert r["bd_force_max_dpos"] == 0.0                 # ... also with an interactor
+    assert r["pse_displacement"] > 1e-3                  # the particles did move
+    assert r["pse_max_dpos"] < 2e-5 * max(1.0, r["pse_displacement"])  # BDHI::EulerMaruyama<b200::PSE>, fp32

@@ -36,7 +36,7 @@ bdEulerMaruyama(T4 *__restrict__ pos, const int *__restrict__ groupIdx, const T4
     const T B = sqrt(T(2.0) * temperature * M * dt);
     const float2 g0 = rng.gauss2((float)B);
     const float2 g1 = rng.gauss2((float)B);
-    Rx += (T)g0.x; Ry += (T)g0.y; Rz += (T)g1.x;
+    Rx = Rx + (T)g0.x; Ry = Ry + (T)g0.y; Rz = Rz + (T)g1.x; // R += dW: a plain add of the already rounded noise
   }
   T4 out = p;
   out.x = Rx; out.y = Ry;

@@ -38,7 +38,7 @@ struct Saru {
     const float u1 = f();
     const float r = sqrtf(-2.0f * logf(u0));
     const float theta = 6.283185307179586f * u1;
-    return (r * sinf(theta)) * std;
+    return __fmul_rn(r * sinf(theta), std);
   }
   // full Box-Muller pair gf(0, std): float arithmetic even in double precision builds (saruprng.cuh:115-128)
   __device__ __forceinline__ float2 gauss2(float std) {
@@ -47,7 +47,9 @@ struct Saru {
     const float u1 = f();
     const float r = sqrtf(-2.0f * logf(u0));
     const float theta = 6.283185307179586f * u1;
-    return make_float2((r * sinf(theta)) * std, (r * cosf(theta)) * std);
+    // gf() is "(r sin, r cos) * std + mean" with mean = 0 (saruprng.cuh:127): the product is rounded on its own (an
+    // fma with a zero addend), it must never be contracted into the caller's accumulation
+    return make_float2(__fmul_rn(r * sinf(theta), std), __fmul_rn(r * cosf(theta), std));
   }
 };
 
