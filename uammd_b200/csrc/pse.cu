@@ -273,6 +273,58 @@ rpyNearTraversal(const T *__restrict__ sortedPos3, const T *__restrict__ sortedV
   }
 }
 
+// ---- list-based near-field mat-vec (Lanczos): positions are fixed over the 5-30 products of one square-root, so the
+// pairs inside the cut-off are found ONCE (our Verlet-list build with multiplier 1, 146 candidates -> ~22 neighbours
+// per particle at config 3) and every product only walks its neighbours. The reference walks the 27 cells again for
+// every product (Dotctor, NearField.cuh:201-220). Sorted {x,y,z,vx,vy,vz,-,-} records: one 32-byte sector per
+// neighbour in fp32.
+template <class T4, class T>
+__global__ void __launch_bounds__(256)
+pseGatherPV(const int *__restrict__ groupIndex, const T4 *__restrict__ pos, const T *__restrict__ v, int vStride, int N,
+            T *__restrict__ pv8) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const int i = groupIndex[k];
+  T *o = pv8 + 8 * (size_t)k;
+  if (pos) { const T4 p = pos[i]; o[0] = p.x; o[1] = p.y; o[2] = p.z; }
+  if (v) { const T *vp = v + (size_t)i * vStride; o[3] = vp[0]; o[4] = vp[1]; o[5] = vp[2]; }
+}
+
+__device__ __forceinline__ float4 ldgV4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ double4 ldgV4(const double *p) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+template <class T, bool ACCUMULATE, bool SHEAR>
+__global__ void __launch_bounds__(128)
+rpyNearList(const T *__restrict__ pv8, const int *__restrict__ groupIndex, const int *__restrict__ neighbourList,
+            const int *__restrict__ numberNeighbours, int N, TableView<T> tb, NearGeom<T> q, T *__restrict__ Mv3) {
+  using V4 = typename Real4<T>::type;
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  const V4 a = ldgV4(pv8 + 8 * (size_t)id);
+  const int nn = numberNeighbours[id];
+  const int *lp = neighbourList + id;
+  T ax = T(0), ay = T(0), az = T(0);
+  int k = 0;
+  for (; k + 2 <= nn; k += 2) {
+    const int j0 = __ldg(lp + (size_t)k * N), j1 = __ldg(lp + (size_t)(k + 1) * N);
+    const V4 b0 = ldgV4(pv8 + 8 * (size_t)j0), c0 = ldgV4(pv8 + 8 * (size_t)j0 + 4);
+    const V4 b1 = ldgV4(pv8 + 8 * (size_t)j1), c1 = ldgV4(pv8 + 8 * (size_t)j1 + 4);
+    rpyPair<T, SHEAR>(q, tb, a.x, a.y, a.z, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, ax, ay, az);
+    rpyPair<T, SHEAR>(q, tb, a.x, a.y, a.z, b1.x, b1.y, b1.z, b1.w, c1.x, c1.y, ax, ay, az);
+  }
+  for (; k < nn; k++) {
+    const int j0 = __ldg(lp + (size_t)k * N);
+    const V4 b0 = ldgV4(pv8 + 8 * (size_t)j0), c0 = ldgV4(pv8 + 8 * (size_t)j0 + 4);
+    rpyPair<T, SHEAR>(q, tb, a.x, a.y, a.z, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, ax, ay, az);
+  }
+  T *out = Mv3 + 3 * (size_t)groupIndex[id];
+  if (ACCUMULATE) { out[0] += ax; out[1] += ay; out[2] += az; }
+  else { out[0] = ax; out[1] = ay; out[2] = az; }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Lanczos helpers (vectors of n reals on the device, scalars through a small pinned-free host read)
 // ------------------------------------------------------------------------------------------------------------
@@ -481,6 +533,9 @@ template <class T> struct PseState {
   ub200_celllist *cl = nullptr;
   DevBuf posF, sortedPos, sortedV;
   int nearN = -1;
+  ub200_verletlist *vl = nullptr; // neighbours inside the cut-off, built once per Lanczos square root
+  DevBuf sortedPV;
+  int listN = -1;
   // Lanczos
   GrowBuf V;
   DevBuf w, oldBz, z, partial, scalar, coeff;
@@ -519,6 +574,8 @@ template <class T> struct PseState {
       UB200_CUDA(cudaMemcpy(table.p, h.data(), sizeof(C) * h.size(), cudaMemcpyHostToDevice));
     }
     if ((rc = ub200_celllist_create(&cl))) return rc;
+    if ((rc = ub200_verletlist_create(&vl))) return rc;
+    if ((rc = ub200_verletlist_set_cutoff_multiplier(vl, 1.0f))) return rc;
     // ---- far field: FarField::initializeGrid / initializeKernel (FarField.cuh:605-654) ----
     const T kcut = T(2) * psi * (T)sqrt(-log(tolerance));
     const double hgrid = 2 * M_PI / kcut;
@@ -570,6 +627,9 @@ template <class T> struct PseState {
     V.release(); w.release(); oldBz.release(); z.release(); partial.release(); scalar.release(); coeff.release();
     if (cl) ub200_celllist_destroy(cl);
     cl = nullptr;
+    if (vl) ub200_verletlist_destroy(vl);
+    vl = nullptr;
+    sortedPV.release();
   }
 
   // ---------------- far field ----------------
@@ -654,6 +714,60 @@ template <class T> struct PseState {
     return UB200_OK;
   }
 
+  TableView<T> tableView() const {
+    TableView<T> tb;
+    tb.table = table.as<C>(); tb.Ntable = nTable - 1; tb.rmin = T(0); tb.rmax = rcut;
+    tb.interval = (T)(1.0 / (rcut - T(0))); tb.dr = (T)(1.0 / (T)(nTable - 1));
+    return tb;
+  }
+  NearGeom<T> nearGeom() const {
+    NearGeom<T> q;
+    q.Lx = Lb[0]; q.Ly = Lb[1]; q.Lz = Lb[2]; q.shear = shear; q.rcut2 = rcut * rcut;
+    q.iLx = T(1.0) / Lb[0]; q.iLy = T(1.0) / Lb[1]; q.iLz = T(1.0) / Lb[2];
+    return q;
+  }
+  // neighbour list of the current positions: every pair the exact test of rpyPair can accept is in it (the list is
+  // built from fp32 coordinates with the unsheared minimum image, hence the shear safety factor and a rounding margin)
+  int nearPrepareList(const void *pos, int N, cudaStream_t st) {
+    int rc;
+    const double gs = shear;
+    const double safety = 1 + 0.5 * gs * gs + 0.5 * sqrt(gs * gs * (gs * gs + 4.0));
+    const float Lf[3] = {(float)Lb[0], (float)Lb[1], (float)Lb[2]};
+    const float Lmax = std::max({Lf[0], Lf[1], Lf[2]});
+    const float rcList = (float)((double)rcut * safety) * (1.0f + 1e-5f) + 16.0f * Lmax * 1.2e-7f;
+    const int periodic[3] = {1, 1, 1};
+    const void *posf = pos;
+    if (sizeof(T) == 8) {
+      if ((rc = posF.reserve(sizeof(float4) * (size_t)N))) return rc;
+      pseToFloat4<<<(N + 255) / 256, 256, 0, st>>>((const double4 *)pos, posF.as<float4>(), N);
+      UB200_LAUNCHED();
+      posf = posF.p;
+    }
+    if ((rc = ub200_verletlist_update_f32(vl, posf, nullptr, N, Lf, periodic, rcList, 1, nullptr, (void *)st))) return rc;
+    if ((rc = sortedPV.reserve(sizeof(T) * 8 * (size_t)N))) return rc;
+    pseGatherPV<T4, T><<<(N + 255) / 256, 256, 0, st>>>(vl->cl->groupIndex.as<int>(), (const T4 *)pos, (const T *)nullptr, 0, N, sortedPV.as<T>());
+    UB200_LAUNCHED();
+    listN = N;
+    return UB200_OK;
+  }
+  int nearDotList(const T *v, int vStride, int N, T *Mv3, bool accumulate, cudaStream_t st) {
+    if (listN != N) return UB200_ERR_NOT_BUILT;
+    pseGatherPV<T4, T><<<(N + 255) / 256, 256, 0, st>>>(vl->cl->groupIndex.as<int>(), (const T4 *)nullptr, v, vStride, N, sortedPV.as<T>());
+    UB200_LAUNCHED();
+    const TableView<T> tb = tableView();
+    const NearGeom<T> q = nearGeom();
+    const int nb = (N + 127) / 128;
+#define UB200_NEARL(ACC, SH)                                                                                              \
+  rpyNearList<T, ACC, SH><<<nb, 128, 0, st>>>(sortedPV.as<T>(), vl->cl->groupIndex.as<int>(), vl->neighbourList.as<int>(),  \
+                                              vl->numberNeighbours.as<int>(), N, tb, q, Mv3)
+    const bool sh = shear != T(0);
+    if (accumulate) { if (sh) UB200_NEARL(true, true); else UB200_NEARL(true, false); }
+    else { if (sh) UB200_NEARL(false, true); else UB200_NEARL(false, false); }
+#undef UB200_NEARL
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+
   // ---------------- Lanczos ----------------
   int dotHost(const T *a, const T *b, size_t n, double *out, cudaStream_t st) {
     redDotPartial<T><<<kRedBlocks, kRedThreads, 0, st>>>(a, b, n, partial.as<double>());
@@ -688,7 +802,7 @@ template <class T> struct PseState {
     for (int i = 0; i < iterationHardLimit; i++) {
       if ((rc = V.grow(sizeof(T) * n * (size_t)(i + 2), st))) return rc;
       T *Vm = (T *)V.p, *dw = w.as<T>();
-      if ((rc = nearDot(Vm + n * i, 3, N, dw, false, st))) return rc;                    // w = M v_i
+      if ((rc = nearDotList(Vm + n * i, 3, N, dw, false, st))) return rc;                // w = M v_i
       if (i > 0 && (rc = axpby((T)(-hsup[i - 1]), Vm + n * (i - 1), T(1), dw, n, st))) return rc;
       double hd;
       if ((rc = dotHost(dw, Vm + n * i, n, &hd, st))) return rc;
@@ -751,7 +865,7 @@ template <class T> struct PseState {
     if (iterations) *iterations = 0;
     if (temperature == 0.0) return UB200_OK;
     int rc;
-    if ((rc = nearPrepare(pos, N, st))) return rc;
+    if ((rc = nearPrepareList(pos, N, st))) return rc;
     if ((rc = z.reserve(sizeof(T) * 3 * (size_t)N))) return rc;
     const T noisePrefactor = (T)prefactor * (T)sqrt(2 * (T)temperature);
     pseNearNoise<T><<<(N + 255) / 256, 256, 0, st>>>(z.as<T>(), N, noisePrefactor, seedNear, seed2);
