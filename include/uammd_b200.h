@@ -222,6 +222,13 @@ int ub200_fcm_create(ub200_fcm **out, int precisionBytes, const double L[3], con
 int ub200_fcm_destroy(ub200_fcm *fcm);
 int ub200_fcm_mdot(ub200_fcm *fcm, const void *d_pos, const void *d_force, int N, double temperature,
                    double prefactor, void *d_out3, void *stream);
+/* Rotational FCM. Replaces the torque path of FCM_impl::computeHydrodynamicDisplacements (FCM_impl.cuh:306-358,583-649,
+ * 652-693): torques (real4) are spread with KernelTorque (FCM_ns::Kernels::GaussianTorque, FCM_kernels.cuh:60-80; set once
+ * with ub200_fcm_set_torque_kernel), 1/2 i dk x T is added to the force spectrum before the Stokes operator, and the
+ * angular velocities 1/2 curl v are interpolated with KernelTorque. d_force may be NULL. */
+int ub200_fcm_set_torque_kernel(ub200_fcm *fcm, const ub200_ibm_kernel *kernelTorque);
+int ub200_fcm_mdot_torque(ub200_fcm *fcm, const void *d_pos, const void *d_force, const void *d_torque, int N,
+                          double temperature, double prefactor, void *d_linear3, void *d_angular3, void *stream);
 int ub200_fcm_grid_info(ub200_fcm *fcm, int cells[3], int *nxPad, void **d_grid);
 /* BDHI::EulerMaruyama position update. Replaces EulerMaruyama_ns::integrateGPUD
  * (Integrator/BDHI/BDHI_EulerMaruyama.cu:82-113): x += dt (K x + MF) + sqrt2Tdt BdW. d_MF/d_BdW real3[N] indexed by

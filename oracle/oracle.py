@@ -290,18 +290,58 @@ def dft3_c2r(ghat, nx, nxPad):
     return out
 
 
-def fcm_mdot(L, cells, kern, viscosity, pos4, force3, temperature=0.0, prefactor=0.0, seed=0, seed2=1):
+def gaussian_torque(width, h, tolerance):
+    """FCM_ns::Kernels::GaussianTorque (Integrator/BDHI/FCM/FCM_kernels.cuh:60-80)."""
+    pref = (2.0 * np.pi * width * width) ** -0.5
+    tau = -0.5 / (width * width)
+    dr = 0.5 * h
+    r = dr
+    while pref * np.exp(tau * r * r) > tolerance:
+        r += dr
+    support = max(3, int(2 * r / h + 0.5))
+    return IBMKernel(KERNEL_GAUSSIAN, support, h, pref, tau, support * h)
+
+
+def _half_curl_fourier(L, cells, vhat):
+    """1/2 i dk x v in Fourier space with the unpaired (Nyquist) components of dk zeroed: addTorqueCurl /
+    computeVelocityCurlFourier (FCM_impl.cuh:306-325,593-615), getGradientFourier (FCM/utils.cuh:41-51)."""
+    nx, ny, nz = cells
+
+    def dk(n, Ld, m):
+        i = np.arange(m)
+        f = i - n * (i >= (n // 2 + 1))
+        k = 2.0 * np.pi / Ld * f
+        k[f == n - f] = 0.0
+        return k
+    kx = dk(nx, L[0], nx // 2 + 1)[None, None, :]
+    ky = dk(ny, L[1], ny)[None, :, None]
+    kz = dk(nz, L[2], nz)[:, None, None]
+    vx, vy, vz = vhat[..., 0], vhat[..., 1], vhat[..., 2]
+    out = np.empty_like(vhat)
+    out[..., 0] = 0.5j * (ky * vz - kz * vy)
+    out[..., 1] = 0.5j * (kz * vx - kx * vz)
+    out[..., 2] = 0.5j * (kx * vy - ky * vx)
+    return out
+
+
+def fcm_mdot(L, cells, kern, viscosity, pos4, force3, temperature=0.0, prefactor=0.0, seed=0, seed2=1, torque3=None,
+             kernTorque=None):
     """FCM pipeline FCM_impl::computeHydrodynamicDisplacements (Integrator/BDHI/FCM/FCM_impl.cuh:652-693)
-    with numpy.fft standing in for cuFFT. force3 may be None (noise only); seed2 = number of noisy calls so far."""
+    with numpy.fft standing in for cuFFT. force3 may be None (noise only); seed2 = number of noisy calls so far.
+    With torque3 (and kernTorque) returns the pair (linear, angular) like the reference."""
     g = make_grid_d(L, cells)
     nx, ny, nz = cells
     nxPad = 2 * (nx // 2 + 1)
     if force3 is not None:
         sp = ibm_spread(g, kern, pos4, force3, nxPad)
         ghat = np.fft.rfftn(sp[:, :, :nx, :], axes=(0, 1, 2))
-        ghat = fcm_force2vel(g, viscosity, ghat)
     else:
         ghat = np.zeros((nz, ny, nx // 2 + 1, 3), np.complex128)
+    if torque3 is not None:
+        spt = ibm_spread(g, kernTorque, pos4, torque3, nxPad)
+        ghat = ghat + _half_curl_fourier(L, cells, np.fft.rfftn(spt[:, :, :nx, :], axes=(0, 1, 2)))
+    if force3 is not None or torque3 is not None:
+        ghat = fcm_force2vel(g, viscosity, ghat)
     if temperature > 0:
         dV = g.cellSize[0] * g.cellSize[1] * g.cellSize[2]
         noisePrefactor = prefactor * np.sqrt((1.0 / (float(nx) * ny * nz)) * 2 * temperature / dV)
@@ -309,7 +349,12 @@ def fcm_mdot(L, cells, kern, viscosity, pos4, force3, temperature=0.0, prefactor
 
     vel = np.zeros((nz, ny, nxPad, 3))
     vel[:, :, :nx, :] = np.fft.irfftn(ghat, s=(nz, ny, nx), axes=(0, 1, 2)) * (nx * ny * nz)
-    return ibm_gather(g, kern, pos4, vel, nxPad)
+    linear = ibm_gather(g, kern, pos4, vel, nxPad)
+    if torque3 is None:
+        return linear
+    ang = np.zeros((nz, ny, nxPad, 3))
+    ang[:, :, :nx, :] = np.fft.irfftn(_half_curl_fourier(L, cells, ghat), s=(nz, ny, nx), axes=(0, 1, 2)) * (nx * ny * nz)
+    return linear, ibm_gather(g, kernTorque, pos4, ang, nxPad)
 
 
 def bd_euler_maruyama_f64(pos4, force4, selfMobility, dt, temperature, step, seed, K9=None, radius=None, is2D=False):

@@ -8,6 +8,8 @@
  *
  * usage:
  *   ref_fcm mdot  KERNEL N L n viscosity tolerance temperature prefactor seed pos.bin force.bin out.bin
+ *   ref_fcm mdott KERNEL N L n viscosity tolerance temperature prefactor seed pos.bin force.bin torque.bin lin.bin ang.bin
+ *                 (rotational FCM: KernelTorque = GaussianTorque built like detail::initializeKernelTorque, BDHI_FCM.cuh:69-80)
  *   ref_fcm time  KERNEL N L n viscosity tolerance temperature dt warmup steps flush pos.bin force.bin
  * KERNEL: peskin3 | peskin4 | gaussian ; pos.bin / force.bin: double4[N] ; out.bin: double3[N]
  * "time" runs the body of BDHI::EulerMaruyama<FCM>::forwardTime (BDHI_EulerMaruyama.cu:125-166) with fixed
@@ -63,7 +65,26 @@ template <class Kernel> int run(int argc, char **argv) {
   par.kernel = std::make_shared<Kernel>(h, tolerance);
   par.kernelTorque = std::make_shared<KernelTorque>(real(1.0), h, real(1e-3)); // unused (no torques)
   par.hydrodynamicRadius = par.kernel->fixHydrodynamicRadius(h, h);
-  if (mode == "mdot") {
+  if (mode == "mdott") {
+    const real prefactor = atof(argv[a++]);
+    par.seed = (uint)atoll(argv[a++]);
+    std::string posf = argv[a++], forcef = argv[a++], torquef = argv[a++], linf = argv[a++], angf = argv[a++];
+    const real width = par.hydrodynamicRadius / (pow(6 * sqrt(M_PI), 1 / 3.));
+    par.kernelTorque = std::make_shared<KernelTorque>(width, h, tolerance);
+    auto fcm = std::make_shared<FCM>(par);
+    auto hp = readBin<real4>(posf, N), hf = readBin<real4>(forcef, N), ht = readBin<real4>(torquef, N);
+    thrust::device_vector<real4> pos(hp), force(hf), torque(ht);
+    auto disp = fcm->computeHydrodynamicDisplacements(pos.data().get(), force.data().get(), torque.data().get(), N, temperature,
+                                                      prefactor, 0);
+    CudaSafeCall(cudaDeviceSynchronize());
+    std::vector<real3> lin(N), ang(N);
+    CudaSafeCall(cudaMemcpy(lin.data(), disp.first.data().get(), N * sizeof(real3), cudaMemcpyDeviceToHost));
+    CudaSafeCall(cudaMemcpy(ang.data(), disp.second.data().get(), N * sizeof(real3), cudaMemcpyDeviceToHost));
+    FILE *f = fopen(linf.c_str(), "wb"); fwrite(lin.data(), sizeof(real3), N, f); fclose(f);
+    f = fopen(angf.c_str(), "wb"); fwrite(ang.data(), sizeof(real3), N, f); fclose(f);
+    printf("{\"mode\":\"mdott\",\"N\":%d,\"n\":%d,\"support\":%d,\"supportTorque\":%d,\"a\":%.17g,\"widthTorque\":%.17g}\n", N, n,
+           (int)par.kernel->support, (int)par.kernelTorque->support, (double)par.hydrodynamicRadius, (double)width);
+  } else if (mode == "mdot") {
     const real prefactor = atof(argv[a++]);
     par.seed = (uint)atoll(argv[a++]);
     std::string posf = argv[a++], forcef = argv[a++], outf = argv[a++];

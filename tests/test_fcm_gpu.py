@@ -2,6 +2,7 @@
 pipeline vs the oracle (fp64 rel-L2 <= 1e-12 as BASELINE.md asks), the reference's own FCM KAT (Gaussian self
 mobility to 1e-8, test/BDHI/FCM/fcm_test.cu:85-144), Brownian noise vs the oracle restatement, and parity with
 the compiled reference (oracle/_ref/ref_fcm)."""
+import json
 import os
 import subprocess
 
@@ -231,3 +232,62 @@ def test_reference_parity(cuda, tmp_path, kname, N, n):
     err = np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref)
     print(f"[FCM parity {kname} N={N} n={n}] rel-L2 vs compiled reference {err:.3e}")
     assert err < 1e-12, err
+
+
+# ---------------- rotational FCM (torques) ----------------
+def _torque_inputs(N, L, seed):
+    pos = _cloud(N, (L,) * 3, seed)
+    force = np.zeros((N, 4)); force[:, :3] = syn.gaussian_forces(N, seed=seed + 1)
+    torque = np.zeros((N, 4)); torque[:, :3] = syn.gaussian_forces(N, seed=seed + 2)
+    return pos, force, torque
+
+
+@pytest.mark.parametrize("with_force,T", [(True, 0.0), (False, 0.0), (True, 0.8)])
+def test_fcm_torques_match_oracle(orc, cuda, with_force, T):
+    from uammd_b200.fcm import GaussianTorque
+    N, n, L, tol, eta = 3000, 32, 32.0, 1e-5, 1.3
+    h = L / n
+    pos, force, torque = _torque_inputs(N, L, 41)
+    kern = Gaussian(h, tol)
+    a = kern.fixHydrodynamicRadius(0, h)
+    kt = GaussianTorque.forHydrodynamicRadius(a, h, tol)
+    fcm = FCM_impl(L, (n, n, n), kern, eta, seed=77, kernelTorque=kt)
+    dp, df, dt_ = (torch.from_numpy(x).to(cuda) for x in (pos, force, torque))
+    lin, ang = fcm.computeHydrodynamicDisplacements(dp, df if with_force else None, temperature=T, prefactor=1.0, torque=dt_)
+    torch.cuda.synchronize()
+    ok, _ = orc.gaussian_fcm(h, tol)
+    okt = orc.gaussian_torque(kt.width, h, tol)
+    assert okt.support == kt.support
+    rlin, rang = orc.fcm_mdot((L,) * 3, (n, n, n), ok, eta, pos, force[:, :3] if with_force else None, temperature=T,
+                              prefactor=1.0, seed=77, seed2=1, torque3=torque[:, :3], kernTorque=okt)
+    rel = lambda a_, b_: np.linalg.norm(a_ - b_) / np.linalg.norm(b_)
+    tol_rel = 1e-11 if T == 0 else 1e-5   # host vs device libm in the float Box-Muller of the noise
+    assert rel(lin.cpu().numpy(), rlin) < tol_rel and rel(ang.cpu().numpy(), rang) < tol_rel
+
+
+def test_fcm_torques_match_reference(cuda, tmp_path):
+    from uammd_b200.fcm import GaussianTorque
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_fcm")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/ref_fcm not built")
+    N, n, L, tol, eta = 20000, 64, 64.0, 1e-6, 1.1
+    h = L / n
+    pos, force, torque = _torque_inputs(N, L, 51)
+    files = {k: str(tmp_path / f"{k}.bin") for k in ("p", "f", "t", "lin", "ang")}
+    pos.tofile(files["p"]); force.tofile(files["f"]); torque.tofile(files["t"])
+    out = subprocess.run([ref, "mdott", "gaussian", str(N), repr(L), str(n), repr(eta), repr(tol), "0.0", "0.0", "5", files["p"],
+                          files["f"], files["t"], files["lin"], files["ang"]], check=True, capture_output=True, text=True,
+                         timeout=600).stdout
+    info = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    kern = Gaussian(h, tol)
+    kt = GaussianTorque.forHydrodynamicRadius(info["a"], h, tol)
+    assert kt.support == info["supportTorque"] and abs(kt.width - info["widthTorque"]) < 1e-14
+    fcm = FCM_impl(L, (n, n, n), kern, eta, seed=5, kernelTorque=kt)
+    dp, df, dt_ = (torch.from_numpy(x).to(cuda) for x in (pos, force, torque))
+    lin, ang = fcm.computeHydrodynamicDisplacements(dp, df, torque=dt_)
+    torch.cuda.synchronize()
+    rlin = np.fromfile(files["lin"], np.float64).reshape(N, 3)
+    rang = np.fromfile(files["ang"], np.float64).reshape(N, 3)
+    rel = lambda a_, b_: np.linalg.norm(a_ - b_) / np.linalg.norm(b_)
+    print(f"[fcm torques vs reference] linear {rel(lin.cpu().numpy(), rlin):.2e} angular {rel(ang.cpu().numpy(), rang):.2e}")
+    assert rel(lin.cpu().numpy(), rlin) < 1e-11 and rel(ang.cpu().numpy(), rang) < 1e-11

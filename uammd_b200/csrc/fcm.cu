@@ -41,10 +41,43 @@ bdhiEulerUpdate(T4 *__restrict__ pos, const int *__restrict__ groupIdx, const de
   pos[i] = pc;
 }
 
+// Rotational FCM (FCM_impl.cuh:306-358,583-649): Fourier-space pointwise step on two grids.
+//   A (forces) += 1/2 i dk x B (torques)          addTorqueCurl :306-325
+//   A = Stokes projector / noise (op)             forceFourier2Vel + fourierBrownianNoise
+//   B = 1/2 i dk x A                              computeVelocityCurlFourier :593-615
+// dk = wave vector with its unpaired (Nyquist) components zeroed (getGradientFourier, FCM/utils.cuh:41-51).
+template <class T>
+__global__ void __launch_bounds__(256)
+fcmTorqueSpectral(typename Vec2<T>::type *__restrict__ A, typename Vec2<T>::type *__restrict__ B, FcmSpectralOp<T> op) {
+  using C = typename Vec2<T>::type;
+  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t nk = (size_t)op.nkx * op.ny * op.nz;
+  if (id >= nk) return;
+  const int ix = (int)(id % op.nkx), iy = (int)((id / op.nkx) % op.ny), iz = (int)(id / ((size_t)op.nkx * op.ny));
+  const int fx = FcmSpectralOp<T>::fold(ix, op.nx), fy = FcmSpectralOp<T>::fold(iy, op.ny), fz = FcmSpectralOp<T>::fold(iz, op.nz);
+  const T dx = (fx == op.nx - fx) ? T(0) : op.kfx * fx, dy = (fy == op.ny - fy) ? T(0) : op.kfy * fy,
+          dz = (fz == op.nz - fz) ? T(0) : op.kfz * fz;
+  const T half = T(0.5);
+  auto curl = [&](const C &gx, const C &gy, const C &gz, C &ox, C &oy, C &oz) {
+    ox = mk2<T>(half * (-dy * gz.y + dz * gy.y), half * (dy * gz.x - dz * gy.x));
+    oy = mk2<T>(half * (-dz * gx.y + dx * gz.y), half * (dz * gx.x - dx * gz.x));
+    oz = mk2<T>(half * (-dx * gy.y + dy * gx.y), half * (dx * gy.x - dy * gx.x));
+  };
+  C ax = A[3 * id], ay = A[3 * id + 1], az = A[3 * id + 2];
+  C cx, cy, cz;
+  curl(B[3 * id], B[3 * id + 1], B[3 * id + 2], cx, cy, cz);
+  ax = cadd(ax, cx); ay = cadd(ay, cy); az = cadd(az, cz);
+  op(ix, iy, iz, ax, ay, az);
+  A[3 * id] = ax; A[3 * id + 1] = ay; A[3 * id + 2] = az;
+  curl(ax, ay, az, cx, cy, cz);
+  B[3 * id] = cx; B[3 * id + 1] = cy; B[3 * id + 2] = cz;
+}
+
 template <class T> struct FcmState {
   Fft3dPlan<T> plan;
-  IbmState<T> ibm;
-  DevBuf grid;
+  IbmState<T> ibm, ibmTorque;
+  DevBuf grid, gridB;
+  bool hasTorqueKernel = false;
   double viscosity = 1;
   double L[3];
   uint32_t seed = 0, seed2 = 0;
@@ -60,7 +93,16 @@ template <class T> struct FcmState {
     seed = seed_;
     return UB200_OK;
   }
-  void release() { plan.release(); ibm.release(); grid.release(); }
+  void release() { plan.release(); ibm.release(); ibmTorque.release(); grid.release(); gridB.release(); }
+  int setTorqueKernel(const ub200_ibm_kernel &k) {
+    const int periodic[3] = {1, 1, 1};
+    const int cells[3] = {plan.nx, plan.ny, plan.nz};
+    int rc = ibmTorque.init(L, periodic, cells, k, plan.nxPad);
+    if (rc) return rc;
+    if ((rc = gridB.reserve(plan.gridBytes()))) return rc;
+    hasTorqueKernel = true;
+    return UB200_OK;
+  }
 
   FcmSpectralOp<T> makeOp(bool deterministic, double temperature, double prefactor) {
     FcmSpectralOp<T> op;
@@ -103,6 +145,38 @@ template <class T> struct FcmState {
     if ((rc = launchPassY<T, +1>(plan, g, st))) return rc;
     if ((rc = launchPassX<T, false>(plan, g, st))) return rc;
     return ibm.gather(pos, N, g, (T *)out3, false, det, st);
+  }
+
+  // FCM_impl::computeHydrodynamicDisplacements with torques (FCM_impl.cuh:652-693): unfused passes on two grids
+  int mdotTorque(const void *pos, const void *force, const void *torque, int N, double temperature, double prefactor,
+                 void *outLinear3, void *outAngular3, cudaStream_t st) {
+    if (!hasTorqueKernel) return UB200_ERR_NOT_BUILT;
+    using C = typename Vec2<T>::type;
+    int rc;
+    T *A = grid.as<T>(), *B = gridB.as<T>();
+    if (force) {
+      if ((rc = ibm.spread(pos, force, 4, N, A, false, st))) return rc;
+      if ((rc = launchPassX<T, true>(plan, A, st))) return rc;
+      if ((rc = launchPassY<T, -1>(plan, A, st))) return rc;
+      if ((rc = launchPassZ<T, -1>(plan, A, st))) return rc;
+    } else {
+      UB200_CUDA(cudaMemsetAsync(A, 0, plan.gridBytes(), st));
+    }
+    if ((rc = ibmTorque.spread(pos, torque, 4, N, B, false, st))) return rc;
+    if ((rc = launchPassX<T, true>(plan, B, st))) return rc;
+    if ((rc = launchPassY<T, -1>(plan, B, st))) return rc;
+    if ((rc = launchPassZ<T, -1>(plan, B, st))) return rc;
+    FcmSpectralOp<T> op = makeOp(true, temperature, prefactor);
+    const size_t nk = (size_t)plan.nkx * plan.ny * plan.nz;
+    fcmTorqueSpectral<T><<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(reinterpret_cast<C *>(A), reinterpret_cast<C *>(B), op);
+    UB200_LAUNCHED();
+    for (T *g : {B, A}) {
+      if ((rc = launchPassZ<T, +1>(plan, g, st))) return rc;
+      if ((rc = launchPassY<T, +1>(plan, g, st))) return rc;
+      if ((rc = launchPassX<T, false>(plan, g, st))) return rc;
+    }
+    if ((rc = ibmTorque.gather(pos, N, B, (T *)outAngular3, false, true, st))) return rc;
+    return ibm.gather(pos, N, A, (T *)outLinear3, false, force != nullptr, st);
   }
 };
 
@@ -150,6 +224,16 @@ int ub200_fcm_mdot(ub200_fcm *h, const void *d_pos, const void *d_force, int N, 
   if (!h || !d_pos || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
   return h->precision == 4 ? h->f.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream)
                            : h->d.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream);
+}
+int ub200_fcm_set_torque_kernel(ub200_fcm *h, const ub200_ibm_kernel *kernelTorque) {
+  if (!h || !kernelTorque) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? h->f.setTorqueKernel(*kernelTorque) : h->d.setTorqueKernel(*kernelTorque);
+}
+int ub200_fcm_mdot_torque(ub200_fcm *h, const void *d_pos, const void *d_force, const void *d_torque, int N, double temperature,
+                          double prefactor, void *d_linear3, void *d_angular3, void *stream) {
+  if (!h || !d_pos || !d_torque || !d_linear3 || !d_angular3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? h->f.mdotTorque(d_pos, d_force, d_torque, N, temperature, prefactor, d_linear3, d_angular3, (cudaStream_t)stream)
+                           : h->d.mdotTorque(d_pos, d_force, d_torque, N, temperature, prefactor, d_linear3, d_angular3, (cudaStream_t)stream);
 }
 int ub200_fcm_grid_info(ub200_fcm *h, int cells[3], int *nxPad, void **d_grid) {
   if (!h) return UB200_ERR_INVALID_ARGUMENT;

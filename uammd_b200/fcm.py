@@ -43,6 +43,8 @@ def _declare():
         "ub200_fcm_destroy": (i, [vp]),
         "ub200_fcm_mdot": (i, [vp, vp, vp, i, d, d, vp, vp]),
         "ub200_fcm_grid_info": (i, [vp, I3, C.POINTER(i), C.POINTER(vp)]),
+        "ub200_fcm_set_torque_kernel": (i, [vp, K]),
+        "ub200_fcm_mdot_torque": (i, [vp, vp, vp, vp, i, d, d, vp, vp, vp]),
         "ub200_bdhi_euler_update": (i, [i, vp, vp, vp, vp, vp, i, d, d, i, vp]),
     }
     for name, (res, args) in sig.items():
@@ -120,6 +122,29 @@ class Gaussian:
 
     def fixHydrodynamicRadius(self, hydrodynamicRadius, h):
         return self.a
+
+    def struct(self):
+        return IBMKernelStruct(2, self.support, self.h, self.prefactor, self.tau, self.rmax)
+
+
+class GaussianTorque:
+    """FCM_ns::Kernels::GaussianTorque (FCM_kernels.cuh:60-80): IBM_kernels::Gaussian(width) truncated where it drops below
+    the tolerance. forHydrodynamicRadius builds it like detail::initializeKernelTorque (BDHI_FCM.cuh:69-80)."""
+
+    def __init__(self, width, h, tolerance):
+        self.width, self.h = width, h
+        self.prefactor = (2.0 * math.pi * width * width) ** -0.5
+        self.tau = -0.5 / (width * width)
+        dr = 0.5 * h
+        r = dr
+        while self.prefactor * math.exp(self.tau * r * r) > tolerance:
+            r += dr
+        self.support = max(3, int(2 * r / h + 0.5))
+        self.rmax = self.support * h
+
+    @staticmethod
+    def forHydrodynamicRadius(a, h, tolerance):
+        return GaussianTorque(a / (6 * math.sqrt(math.pi)) ** (1 / 3.0), h, tolerance)
 
     def struct(self):
         return IBMKernelStruct(2, self.support, self.h, self.prefactor, self.tau, self.rmax)
@@ -213,7 +238,7 @@ def hasimotoSelfMobility(hydrodynamicRadius, viscosity, L):
 class FCM_impl:
     """FCM_impl<Kernel, KernelTorque> without torques. Parameters mirror FCM_impl::Parameters."""
 
-    def __init__(self, box, cells, kernel, viscosity, hydrodynamicRadius=None, seed=0, dtype=torch.float64):
+    def __init__(self, box, cells, kernel, viscosity, hydrodynamicRadius=None, seed=0, dtype=torch.float64, kernelTorque=None):
         self.lib = _declare()
         L = (box, box, box) if np.isscalar(box) else tuple(box)
         if L[0] <= 0:
@@ -232,6 +257,10 @@ class FCM_impl:
         ks = kernel.struct()
         check(self.lib.ub200_fcm_create(C.byref(self._h), _prec(dtype), d3(L), i3(self.cells), C.byref(ks),
                                         float(viscosity), self.seed))
+        self.kernelTorque = kernelTorque
+        if kernelTorque is not None:
+            kt = kernelTorque.struct()
+            check(self.lib.ub200_fcm_set_torque_kernel(self._h, C.byref(kt)))
 
     def __del__(self):
         try:
@@ -246,11 +275,20 @@ class FCM_impl:
     def getSelfMobility(self):
         return hasimotoSelfMobility(self.hydrodynamicRadius, self.viscosity, self.L[0])
 
-    def computeHydrodynamicDisplacements(self, pos, force, N=None, temperature=0.0, prefactor=0.0, out=None, stream=None):
-        """pos, force: real4 [N,4]; returns real3 [N,3] linear displacements (torques are not supported)."""
+    def computeHydrodynamicDisplacements(self, pos, force, N=None, temperature=0.0, prefactor=0.0, out=None, stream=None,
+                                         torque=None):
+        """pos, force, torque: real4 [N,4]; returns the real3 [N,3] linear displacements, or the pair (linear, angular)
+        when torques are given (FCM_impl::computeHydrodynamicDisplacements returns the same pair)."""
         N = pos.shape[0] if N is None else N
         if out is None:
             out = torch.empty(N, 3, dtype=self.dtype, device=pos.device)
+        if torque is not None:
+            if self.kernelTorque is None:
+                raise UB200Error("FCM_impl requires a torque kernel to compute angular displacements")
+            ang = torch.empty(N, 3, dtype=self.dtype, device=pos.device)
+            check(self.lib.ub200_fcm_mdot_torque(self._h, _ptr(pos), _ptr(force), _ptr(torque), N, float(temperature),
+                                                 float(prefactor), _ptr(out), _ptr(ang), _stream_ptr(stream)))
+            return out, ang
         check(self.lib.ub200_fcm_mdot(self._h, _ptr(pos), _ptr(force), N, float(temperature), float(prefactor),
                                       _ptr(out), _stream_ptr(stream)))
         return out
