@@ -14,12 +14,14 @@
 //   --- barrier ---
 //   fused [FFT z, Stokes, noise, iFFT z]     on T = [nz][nyl][nkx] (ky rows of this rank); stores go straight back
 //                                            into the owners' S
+//                                            into the owners' S - and the boundary planes ALSO into the neighbours' halo planes
 //   --- barrier ---
-//   iFFT y, iFFT x                           local
+//   iFFT y, iFFT x                           local, on the owned planes plus the halo planes (a few redundant lines
+//                                            instead of a halo exchange and its barrier)
+//   gather                                   owned particles, all loads local; rows packed in sorted-slot order
+//   push                                     the packed {index, row} block goes to every rank's inbox (coalesced stores)
 //   --- barrier ---
-//   gather                                   owned particles; support planes of the neighbouring slabs are read
-//                                            through peer-mapped pointers; each result row is pushed to every rank
-//   --- barrier ---
+//   scatter                                  out[index] = row for everything received
 // Buffers S, T, the result and the barrier flags of a rank live in ONE cudaMalloc allocation exported to the peers
 // through CUDA IPC (ub200_fcm_dist_ipc_export / _import; the caller moves the 64-byte handles, e.g. with
 // torch.distributed.all_gather_object). Barriers are one-block kernels that publish an epoch to every peer's flag
@@ -27,6 +29,7 @@
 #include "fcm_op.cuh"
 #include "fft3d.cuh"
 #include "ibm_state.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -56,16 +59,17 @@ template <class T> struct FcmDistState {
   using C = typename Vec2<T>::type;
   using T4 = typename Real4<T>::type;
   int rank = 0, world = 1;
-  int nzl = 0, nyl = 0, z0 = 0, y0 = 0;
+  int nzl = 0, nyl = 0, z0 = 0, y0 = 0, halo = 0;
   int maxParticles = 0;
   Fft3dPlan<T> plan;
   GridT<T> grid;      // with the z window of this rank
   IbmKernel<T> kern;
   double viscosity = 1, L[3];
   uint32_t seed = 0, seed2 = 0;
-  // one exported allocation: [flags | S | T | out]
+  // one exported allocation: [flags | S (owned planes + 2 halo) | T | inboxes: world x {count, index[], rows[]}]
   void *arena = nullptr;
-  size_t arenaBytes = 0, offS = 0, offT = 0, offOut = 0;
+  size_t arenaBytes = 0, offS = 0, offT = 0, offInbox = 0, inboxStride = 0, inboxIdxOff = 0, inboxRowsOff = 0;
+  DevBuf packIdx, packRows, packCount;
   void *peerArena[kMaxPeers] = {};
   bool imported = false;
   uint32_t epoch = 0;
@@ -79,7 +83,8 @@ template <class T> struct FcmDistState {
   // particle scratch (window)
   DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec;
 
-  size_t slabBytes() const { return (size_t)nzl * plan.ny * plan.nkx * 3 * sizeof(C); }
+  size_t planeBytes() const { return (size_t)plan.ny * plan.nkx * 3 * sizeof(C); }
+  size_t slabBytes() const { return (size_t)(nzl + 2 * halo) * planeBytes(); }
   size_t tposeBytes() const { return (size_t)plan.nz * nyl * plan.nkx * 3 * sizeof(C); }
   template <class U> U *at(void *base, size_t off) const { return reinterpret_cast<U *>(static_cast<char *>(base) + off); }
 
@@ -100,6 +105,8 @@ template <class T> struct FcmDistState {
     if (cells[0] < kRbX + S || cells[1] < kRbY + S || cells[2] < kRbZ + S) return UB200_ERR_INVALID_ARGUMENT; // row-brick spread
     grid.zwin0 = ((z0 + lo) % cells[2] + cells[2]) % cells[2];
     grid.zwinN = nzl + (hi - lo);
+    halo = std::max(-lo, hi);
+    if (halo > nzl) return UB200_ERR_INVALID_ARGUMENT;
     kern.kind = k.kind; kern.support = k.support; kern.invh = (T)(1.0 / k.h);
     kern.prefactor = (T)k.prefactor; kern.tau = (T)k.tau; kern.rmax = (T)k.rmax;
     for (int d = 0; d < 3; d++) L[d] = L_[d];
@@ -107,8 +114,14 @@ template <class T> struct FcmDistState {
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     offS = align(4096);
     offT = offS + align(slabBytes());
-    offOut = offT + align(tposeBytes());
-    arenaBytes = offOut + align(sizeof(T) * 3 * (size_t)maxParticles);
+    offInbox = offT + align(tposeBytes());
+    inboxIdxOff = 256;
+    inboxRowsOff = inboxIdxOff + align(sizeof(int) * (size_t)maxParticles);
+    inboxStride = inboxRowsOff + align(sizeof(T) * 3 * (size_t)maxParticles);
+    arenaBytes = offInbox + inboxStride * world;
+    if ((rc = packIdx.reserve(sizeof(int) * (size_t)maxParticles)) || (rc = packRows.reserve(sizeof(T) * 3 * (size_t)maxParticles)) ||
+        (rc = packCount.reserve(sizeof(int))))
+      return rc;
     if (cudaMalloc(&arena, arenaBytes) != cudaSuccess) return UB200_ERR_ALLOC;
     UB200_CUDA(cudaMemset(arena, 0, arenaBytes));
     if ((rc = errFlag.reserve(sizeof(int)))) return rc;
@@ -136,7 +149,7 @@ template <class T> struct FcmDistState {
       if (p != rank && peerArena[p]) cudaIpcCloseMemHandle(peerArena[p]);
     if (arena) cudaFree(arena);
     arena = nullptr;
-    DevBuf *b[] = {&errFlag, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec};
+    DevBuf *b[] = {&errFlag, &packIdx, &packRows, &packCount, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec};
     for (auto *x : b) x->release();
     plan.release();
   }
@@ -170,7 +183,8 @@ template <class T> struct FcmDistState {
     if (!imported) return UB200_ERR_NOT_BUILT;
     if (N > maxParticles) return UB200_ERR_INVALID_ARGUMENT;
     int rc;
-    T *S = at<T>(arena, offS);
+    T *Sall = at<T>(arena, offS);                                         // first halo plane
+    T *S = reinterpret_cast<T *>(reinterpret_cast<char *>(Sall) + (size_t)halo * planeBytes()); // first owned plane
     C *Tb = at<C>(arena, offT);
     const bool det = force != nullptr;
     const int nb = (N + 255) / 256;
@@ -193,7 +207,7 @@ template <class T> struct FcmDistState {
     UB200_LAUNCHED();
     mark(1, st);
     AddrSlabZFused<C> az;
-    az.T = Tb; az.ny = plan.ny; az.nyl = nyl; az.nkx = plan.nkx; az.nzl = nzl; az.y0 = y0;
+    az.T = Tb; az.ny = plan.ny; az.nyl = nyl; az.nkx = plan.nkx; az.nzl = nzl; az.y0 = y0; az.halo = halo; az.world = world;
     for (int p = 0; p < world; p++) az.peerS[p] = at<C>(peerArena[p], offS);
     if (det) {
       // ---- spread into the owned planes ----
@@ -243,29 +257,45 @@ template <class T> struct FcmDistState {
     mark(6, st);
     if ((rc = barrier(st))) return rc;
     mark(7, st);
-    // ---- inverse y and x passes on the owned planes ----
+    // ---- inverse y and x passes on the owned planes AND the halo planes the neighbours pushed ----
     AddrInPlace<C> ainv;
-    ainv.grid = reinterpret_cast<C *>(S); ainv.elemStride = (size_t)plan.nkx; ainv.otherStride = (size_t)plan.nkx * plan.ny;
-    if ((rc = launchPassAddr<T, +1, false, NoSpectralOp>(plan, ainv, nzl, st))) return rc;
-    if ((rc = launchPassX<T, false>(plan, S, st, nzl))) return rc;
+    ainv.grid = reinterpret_cast<C *>(Sall); ainv.elemStride = (size_t)plan.nkx; ainv.otherStride = (size_t)plan.nkx * plan.ny;
+    if ((rc = launchPassAddr<T, +1, false, NoSpectralOp>(plan, ainv, nzl + 2 * halo, st))) return rc;
+    if ((rc = launchPassX<T, false>(plan, Sall, st, nzl + 2 * halo))) return rc;
     mark(8, st);
-    if ((rc = barrier(st))) return rc; // the neighbours' boundary planes are final
-    mark(9, st);
-    // ---- gather for the owned particles, rows pushed to every rank ----
-    PeerTable<T> slabs, outs;
-    for (int p = 0; p < world; p++) { slabs.p[p] = at<T>(peerArena[p], offS); outs.p[p] = at<T>(peerArena[p], offOut); }
+    // ---- gather for the owned particles (local loads), packed rows ----
     const int ngb = (N + 127) / 128;
     if (kern.support == 3)
-      ibmGatherSortedDist<T, 3><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
-                                                    grid, plan.nxPad, slabs, z0, nzl, world, outs);
+      ibmGatherSortedSlab<T, 3><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(), grid, plan.nxPad,
+                                                    Sall, z0, nzl, halo, packIdx.as<int>(), packRows.as<T>(), packCount.as<int>());
     else
-      ibmGatherSortedDist<T, 4><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(),
-                                                    grid, plan.nxPad, slabs, z0, nzl, world, outs);
+      ibmGatherSortedSlab<T, 4><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(), grid, plan.nxPad,
+                                                    Sall, z0, nzl, halo, packIdx.as<int>(), packRows.as<T>(), packCount.as<int>());
+    UB200_LAUNCHED();
+    mark(9, st);
+    // ---- push the packed block into inbox[rank] of every rank ----
+    PeerTable<int> ibCount, ibIdx;
+    PeerTable<T> ibRows;
+    for (int p = 0; p < world; p++) {
+      char *box = at<char>(peerArena[p], offInbox) + inboxStride * (size_t)rank;
+      ibCount.p[p] = reinterpret_cast<int *>(box);
+      ibIdx.p[p] = reinterpret_cast<int *>(box + inboxIdxOff);
+      ibRows.p[p] = reinterpret_cast<T *>(box + inboxRowsOff);
+    }
+    slabPushPacked<T><<<dim3(96, world), 256, 0, st>>>(packCount.as<int>(), packIdx.as<int>(), packRows.as<T>(), ibCount, ibIdx, ibRows, world);
     UB200_LAUNCHED();
     mark(10, st);
-    if ((rc = barrier(st))) return rc; // every rank's rows have landed; the slabs may be overwritten by the next call
+    if ((rc = barrier(st))) return rc; // every rank's block has landed; slabs and T may be overwritten by the next call
     mark(11, st);
-    UB200_CUDA(cudaMemcpyAsync(out3, at<T>(arena, offOut), sizeof(T) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, st));
+    // ---- scatter what the ranks sent me ----
+    for (int p = 0; p < world; p++) {
+      char *box = at<char>(arena, offInbox) + inboxStride * (size_t)p;
+      ibCount.p[p] = reinterpret_cast<int *>(box);
+      ibIdx.p[p] = reinterpret_cast<int *>(box + inboxIdxOff);
+      ibRows.p[p] = reinterpret_cast<T *>(box + inboxRowsOff);
+    }
+    slabScatterInbox<T><<<dim3(64, world), 256, 0, st>>>(ibCount, ibIdx, ibRows, world, (T *)out3);
+    UB200_LAUNCHED();
     mark(12, st);
     collect(13, st);
     return UB200_OK;
@@ -303,7 +333,7 @@ int ub200_fcm_dist_destroy(ub200_fcm_dist *h) {
   return UB200_OK;
 }
 /* UB200_DIST_PROFILE=1: mean milliseconds of the 12 phases of mdot (sort, spread, fft x, fft y + transpose, barrier,
- * fused z + transpose, barrier, ifft y+x, barrier, gather, barrier, copy); returns the number of profiled calls */
+ * fused z + transpose, barrier, ifft y+x, gather, push, barrier, scatter); returns the number of profiled calls */
 int ub200_fcm_dist_profile(ub200_fcm_dist *h, double phases[12]) {
   if (!h || !phases) return 0;
   const int n = h->precision == 4 ? h->f.profiledCalls : h->d.profiledCalls;

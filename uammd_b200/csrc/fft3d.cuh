@@ -156,8 +156,8 @@ template <class C> struct AddrInPlace {
   __device__ __forceinline__ const C *ld(int other, int i, int kx0) const {
     return grid + ((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * 3;
   }
-  __device__ __forceinline__ C *st(int other, int i, int kx0) const {
-    return grid + ((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * 3;
+  __device__ __forceinline__ void store(int other, int i, int kx0, int gf, const C &v) const {
+    grid[((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * 3 + gf] = v;
   }
 };
 // Slab-decomposed 3-D FFT over `world` GPUs (NVLink peer stores, no staging copy, no NCCL): rank r owns the z planes
@@ -173,21 +173,33 @@ template <class C> struct AddrSlabYForward { // axis = y, other = local z plane
   __device__ __forceinline__ const C *ld(int other, int i, int kx0) const {
     return S + (((size_t)other * ny + i) * nkx + kx0) * 3;
   }
-  __device__ __forceinline__ C *st(int other, int i, int kx0) const {
+  __device__ __forceinline__ void store(int other, int i, int kx0, int gf, const C &v) const {
     const int r = i / nyl;
-    return peerT[r] + (((size_t)(z0 + other) * nyl + (i - r * nyl)) * nkx + kx0) * 3;
+    peerT[r][(((size_t)(z0 + other) * nyl + (i - r * nyl)) * nkx + kx0) * 3 + gf] = v;
   }
 };
+// The slabs carry `halo` extra planes below and above the owned ones ([nzl + 2 halo][ny][nkx][3], owned planes start at
+// index halo): the boundary planes of a slab are ALSO stored into the neighbours' halo planes, so that the inverse y / x
+// passes and the interpolation of the neighbours never touch remote memory (and need no barrier of their own).
 template <class C> struct AddrSlabZFused { // axis = z, other = local ky row
   C *T;
   C *peerS[kFftMaxPeers];
-  int ny, nyl, nkx, nzl, y0; // y0: first global ky row of this rank
+  int ny, nyl, nkx, nzl, y0, halo, world; // y0: first global ky row of this rank
   __device__ __forceinline__ const C *ld(int other, int i, int kx0) const {
     return T + (((size_t)i * nyl + other) * nkx + kx0) * 3;
   }
-  __device__ __forceinline__ C *st(int other, int i, int kx0) const {
-    const int r = i / nzl;
-    return peerS[r] + (((size_t)(i - r * nzl) * ny + (y0 + other)) * nkx + kx0) * 3;
+  __device__ __forceinline__ void store(int other, int i, int kx0, int gf, const C &v) const {
+    const int r = i / nzl, lz = i - r * nzl;
+    const size_t inPlane = ((size_t)(y0 + other) * nkx + kx0) * 3 + gf, plane = (size_t)ny * nkx * 3;
+    peerS[r][(size_t)(lz + halo) * plane + inPlane] = v;
+    if (lz < halo) { // upper halo of the slab below
+      const int rb = r == 0 ? world - 1 : r - 1;
+      peerS[rb][(size_t)(nzl + halo + lz) * plane + inPlane] = v;
+    }
+    if (lz >= nzl - halo) { // lower halo of the slab above
+      const int ra = r == world - 1 ? 0 : r + 1;
+      peerS[ra][(size_t)(lz - (nzl - halo)) * plane + inPlane] = v;
+    }
   }
 };
 
@@ -255,7 +267,7 @@ fftPassStrided(Addr addr, int nRuntime, int nkx, int nOther, int tile, FftAxis a
       res = fftShared<T, +1, NFIX>(res, other1, ax, fstride, nf, tw);
     }
     if (gf < w)
-      for (int i = gi; i < n; i += gstep) addr.st(other, i, kx0)[gf] = res[gf * fstride + i];
+      for (int i = gi; i < n; i += gstep) addr.store(other, i, kx0, gf, res[gf * fstride + i]);
     __syncthreads(); // result consumed: current + scratch may be overwritten by the next iterations
     cur = pre;
   }

@@ -453,39 +453,44 @@ ibmGatherSorted(const T *__restrict__ sortedRec, const int *__restrict__ sortedI
 }
 
 // Slab-decomposed interpolation: this rank owns the z planes [z0, z0 + nzl) of the grid and the particles whose
-// cell lies in them; the sorted window also holds the neighbours' boundary particles (needed by the spread), which
-// are skipped here. Grid planes are read through a table of peer-mapped slab pointers (NVLink loads for the
-// support planes that belong to the neighbouring slabs) and the result row is pushed to every rank's copy of the
-// output (peer-mapped stores), so that all ranks hold the full result after the closing barrier.
+// cell lies in them; its slab carries `halo` planes of its neighbours on either side (pushed there by the fused z
+// pass), so every load is local. The sorted window also holds the neighbours' boundary particles (needed by the
+// spread), which are skipped. Results go, in sorted-slot order, into a packed local buffer {index, row}; a separate
+// kernel pushes that buffer to every rank with wide coalesced stores and the ranks scatter what they received.
 constexpr int kMaxPeers = 8;
 template <class T> struct PeerTable { T *p[kMaxPeers]; };
 
 template <class T, int S>
 __global__ void __launch_bounds__(128)
-ibmGatherSortedDist(const T *__restrict__ sortedRec, const int *__restrict__ sortedIndex, const uint32_t *__restrict__ binStart,
-                    GridT<T> g, int nxPad, PeerTable<T> slabs, int z0, int nzl, int world, PeerTable<T> outs) {
+ibmGatherSortedSlab(const T *__restrict__ sortedRec, const int *__restrict__ sortedIndex, const uint32_t *__restrict__ binStart,
+                    GridT<T> g, int nxPad, const T *__restrict__ slab, int z0, int nzl, int halo, int *__restrict__ packIdx,
+                    T *__restrict__ packRows, int *__restrict__ packCount) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= (int)binStart[g.n[0] * g.n[1] * g.zwinN]) return;
+  const int nLocal = (int)binStart[g.n[0] * g.n[1] * g.zwinN];
+  if (slot == 0) *packCount = nLocal;
+  if (slot >= nLocal) return;
   const T *wsrc = sortedRec + (size_t)slot * RecGeom<T, S>::REC;
   int o[3], cz;
   RecGeom<T, S>::unpackOrigin(wsrc, o[0], o[1], o[2], cz);
-  if (cz < z0 || cz >= z0 + nzl) return; // a neighbour's particle
+  if (cz < z0 || cz >= z0 + nzl) { packIdx[slot] = -1; return; } // a neighbour's particle
   T w[3][S];
-  int cidx[3][S];
+  int cidx[2][S];
 #pragma unroll
   for (int d = 0; d < 3; d++)
 #pragma unroll
     for (int i = 0; i < S; i++) {
-      const int cj = wrapCell(g, d, o[d] + i);
-      cidx[d][i] = (cj >= 0 && cj < g.n[d]) ? cj : -1;
       w[d][i] = wsrc[d * S + i];
+      if (d < 2) {
+        const int cj = wrapCell(g, d, o[d] + i);
+        cidx[d][i] = (cj >= 0 && cj < g.n[d]) ? cj : -1;
+      }
     }
+  // support planes relative to the slab: the origin is at most one support below the particle's own plane
+  const int lz0 = (o[2] - cz) + (cz - z0) + halo;
   T ax = T(0), ay = T(0), az = T(0);
 #pragma unroll
   for (int kk = 0; kk < S; kk++) {
-    if (cidx[2][kk] < 0) continue;
-    const int owner = cidx[2][kk] / nzl;
-    const T *plane = slabs.p[owner] + 3 * (size_t)nxPad * g.n[1] * (size_t)(cidx[2][kk] - owner * nzl);
+    const T *plane = slab + 3 * (size_t)nxPad * g.n[1] * (size_t)(lz0 + kk);
 #pragma unroll
     for (int jj = 0; jj < S; jj++)
 #pragma unroll
@@ -493,15 +498,43 @@ ibmGatherSortedDist(const T *__restrict__ sortedRec, const int *__restrict__ sor
         if (cidx[0][ii] < 0 || cidx[1][jj] < 0) continue;
         const T *gp = plane + 3 * ((size_t)cidx[0][ii] + (size_t)nxPad * (size_t)cidx[1][jj]);
         const T wx = w[0][ii], wy = w[1][jj], wz = w[2][kk];
-        ax += g.cellVolume * (gp[0] * wx * wy * wz);
-        ay += g.cellVolume * (gp[1] * wx * wy * wz);
-        az += g.cellVolume * (gp[2] * wx * wy * wz);
+        ax += g.cellVolume * (__ldg(gp) * wx * wy * wz);
+        ay += g.cellVolume * (__ldg(gp + 1) * wx * wy * wz);
+        az += g.cellVolume * (__ldg(gp + 2) * wx * wy * wz);
       }
   }
-  const size_t row = 3 * (size_t)sortedIndex[slot];
-  for (int r = 0; r < world; r++) {
-    T *op = outs.p[r] + row;
-    op[0] = ax; op[1] = ay; op[2] = az;
+  packIdx[slot] = sortedIndex[slot];
+  packRows[3 * (size_t)slot] = ax; packRows[3 * (size_t)slot + 1] = ay; packRows[3 * (size_t)slot + 2] = az;
+}
+
+// push the packed {count, index[], rows[]} block of this rank into inbox[rank] of every peer (coalesced remote stores)
+template <class T>
+__global__ void __launch_bounds__(256)
+slabPushPacked(const int *__restrict__ packCount, const int *__restrict__ packIdx, const T *__restrict__ packRows,
+               PeerTable<int> inboxCount, PeerTable<int> inboxIdx, PeerTable<T> inboxRows, int world) {
+  const int n = *packCount;
+  const int dest = blockIdx.y;
+  if (dest >= world) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inboxCount.p[dest] = n;
+  int *di = inboxIdx.p[dest];
+  T *dr = inboxRows.p[dest];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) di[i] = packIdx[i];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 3 * (size_t)n; i += (size_t)gridDim.x * blockDim.x) dr[i] = packRows[i];
+}
+
+// out3[index] = row for everything the ranks pushed into my inboxes (each particle is owned by exactly one rank)
+template <class T>
+__global__ void __launch_bounds__(256)
+slabScatterInbox(PeerTable<int> inboxCount, PeerTable<int> inboxIdx, PeerTable<T> inboxRows, int world, T *__restrict__ out3) {
+  const int src = blockIdx.y;
+  if (src >= world) return;
+  const int n = *inboxCount.p[src];
+  const int *ii = inboxIdx.p[src];
+  const T *rr = inboxRows.p[src];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int idx = ii[i];
+    if (idx < 0) continue;
+    out3[3 * (size_t)idx] = rr[3 * (size_t)i]; out3[3 * (size_t)idx + 1] = rr[3 * (size_t)i + 1]; out3[3 * (size_t)idx + 2] = rr[3 * (size_t)i + 2];
   }
 }
 

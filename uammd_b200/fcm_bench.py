@@ -130,8 +130,8 @@ def run_distributed(dev, hbm_peak, steps=100, warmup=10):
         import ctypes as C
         ph = (C.c_double * 12)()
         n = fcm.lib.ub200_fcm_dist_profile(fcm._h, ph)
-        names = ["sort", "spread", "fft_x", "fft_y+transpose", "barrier1", "fused_z+transpose", "barrier2", "ifft_y+x", "barrier3",
-                 "gather+push", "barrier4", "copy_out"]
+        names = ["sort", "spread", "fft_x", "fft_y+transpose", "barrier1", "fused_z+transpose", "barrier2", "ifft_y+x", "gather",
+                 "push", "barrier3", "scatter"]
         print(f"[rank {rank}] phases over {n} calls (us): " + ", ".join(f"{k}={1e3 * v:.1f}" for k, v in zip(names, ph)), file=sys.stderr)
     t = torch.tensor([ms, ms_b2b], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -147,7 +147,7 @@ def run_distributed(dev, hbm_peak, steps=100, warmup=10):
         "config": {"workload": f"BDHI::EulerMaruyama<FCM>, N={N}, {NGRID}^3 grid, Peskin 3pt, eta={ETA}, T={TEMP}, dt={DT}",
                    "l2": "flushed before every step (256 MiB write)",
                    "parallelism": f"z-slab decomposition over {world} GPUs: {NGRID // world} planes per rank, FFT transposes by "
-                                  "NVLink peer stores fused into the y/z passes, 4 device-side barriers per step, no NCCL on the data path"},
+                                  "NVLink peer stores fused into the y/z passes (halo planes included), 3 device-side barriers per step, no NCCL on the data path"},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
                      "note": "compulsory bytes of the whole step (SURVEY 8(d)) per GPU"},
     }
