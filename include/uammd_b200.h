@@ -145,6 +145,13 @@ int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A, float gamm
                       uint32_t seed, uint32_t step, int idStride, void *d_force, const int *d_globalIdx,
                       void *stream);
 
+/* Multi-GPU particle decomposition of the DPD forces (BASELINE config 4 shape): every rank holds all positions and
+ * velocities, forces only for the particles whose index lies in [ownerLo, ownerHi). The noise is keyed on the global
+ * pair indices, so the result does not depend on the number of ranks. accumulate = 0 writes (x,y,z,0), 1 adds. */
+int ub200_dpd_sum_owned_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
+                            uint32_t seed, uint32_t step, int idStride, void *d_force, int ownerLo, int ownerHi,
+                            int accumulate, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Path 1c: velocity Verlet. Replaces VerletNVE_ns::integrateGPU<1|2> (Integrator/VerletNVE.cu:64-85)
  * and VerletNVE::resetForces (:152-158). d_mass may be NULL (defaultMass used). step==1 also drifts.

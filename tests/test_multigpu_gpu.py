@@ -104,3 +104,57 @@ def test_slab_fcm_matches_single_gpu(tmp_path, T):
         got = np.load(out + f".{r}.npy")
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), \
             f"rank {r}: max |d| = {np.abs(got - want).max()} (rel {np.abs(got - want).max() / np.abs(want).max():.2e})"
+
+
+def _dpd_gpu_worker(rank, world, port, N, steps, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from uammd_b200 import synthetic as syn
+    from uammd_b200.md import Box, DPD
+    from uammd_b200.multigpu import DistributedDPDMD
+    dev = torch.device("cuda", rank)
+    L = (N / 3.0) ** (1.0 / 3.0)
+    p = torch.from_numpy(syn.uniform_cloud(N, L, seed=21)).to(dev)
+    v = torch.from_numpy(syn.maxwell_velocities(N, 1.0, seed=22)).to(dev)
+    f = torch.zeros(N, 4, device=dev)
+    md = DistributedDPDMD(Box(L), DPD(cutOff=1.0, dt=0.01, gamma=4.5, temperature=1.0, A=25.0, seed=99), 0.01, N)
+    for _ in range(steps):
+        md.forwardTime(p, v, f)
+    md.gatherState(p, v)
+    torch.cuda.synchronize()
+    if rank == 0:
+        np.save(out, np.concatenate([p.cpu().numpy().ravel(), v.cpu().numpy().ravel()]))
+    dist.destroy_process_group()
+
+
+def test_dpd_decomposition_matches_single_gpu(tmp_path):
+    """BASELINE config 4 shape (rho = 3, rc = 1, A = 25, gamma = 4.5) at N = 240 000: 2 ranks vs the single-GPU
+    VerletNVE + PairForcesDPD classes, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from uammd_b200 import synthetic as syn
+    from uammd_b200.md import Box, DPD, PairForcesDPD, VerletNVE
+    N, steps = 240_000, 5
+    out = str(tmp_path / "dpd.npy")
+    mp.spawn(_dpd_gpu_worker, args=(2, 29547, N, steps, out), nprocs=2, join=True)
+    got = np.load(out)
+    dev = torch.device("cuda:0")
+    L = (N / 3.0) ** (1.0 / 3.0)
+    p = torch.from_numpy(syn.uniform_cloud(N, L, seed=21)).to(dev)
+    v = torch.from_numpy(syn.maxwell_velocities(N, 1.0, seed=22)).to(dev)
+    pf = PairForcesDPD(DPD(cutOff=1.0, dt=0.01, gamma=4.5, temperature=1.0, A=25.0, seed=99), Box(L))
+
+    class _It:
+        def sum(self, pos, force=None):
+            pf.sum(pos, v, force)
+    integ = VerletNVE(p, v, 0.01)
+    integ.addInteractor(_It())
+    for _ in range(steps):
+        integ.forwardTime()
+    torch.cuda.synchronize()
+    assert np.array_equal(got[:4 * N].view(np.uint32), p.cpu().numpy().ravel().view(np.uint32))
+    assert np.array_equal(got[4 * N:].view(np.uint32), v.cpu().numpy().ravel().view(np.uint32))

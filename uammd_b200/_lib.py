@@ -62,6 +62,7 @@ def _declare(lib):
         "ub200_md_lj_nve_run_host_f32": (i, [vp, vp, vp, vp, i, _F3, f, fp, i, f, i, vp]),
     }
     sig["ub200_dpd_sum_f32"] = (i, [vp, vp, f, f, f, f, u32, u32, i, vp, vp, vp])
+    sig["ub200_dpd_sum_owned_f32"] = (i, [vp, vp, f, f, f, f, u32, u32, i, vp, i, i, i, vp])
     optional = {}
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

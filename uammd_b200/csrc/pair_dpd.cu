@@ -48,7 +48,9 @@ template <bool PAIRMIC>
 __global__ void __launch_bounds__(kPairThreads)
 dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
                  const uint32_t *__restrict__ binStart, GridF g, int ncells, const float *__restrict__ vel, DPDPar par,
-                 float4 *__restrict__ force, const int *__restrict__ globalIdx) {
+                 float4 *__restrict__ force, const int *__restrict__ globalIdx, int ownerLo, int ownerHi, int accumulate) {
+  // ownerLo/ownerHi: only home particles whose (global) index lies in [ownerLo, ownerHi) are computed and written
+  // (multi-GPU particle decomposition, like ub200_lj_sum_owned_f32)
   __shared__ float4 cand[kDpdCap];
   __shared__ float4 candVel[kDpdCap]; // vx, vy, vz, id (bits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -92,6 +94,7 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
         vi = make_float4(vel[3 * (size_t)id], vel[3 * (size_t)id + 1], vel[3 * (size_t)id + 2], __int_as_float(id));
       }
       const int idi = __float_as_int(vi.w);
+      if (idi < ownerLo || idi >= ownerHi) continue; // warp uniform
       float fx = 0.f, fy = 0.f, fz = 0.f;
       if (staged) {
         for (int t = lane; t < nc.total; t += 32) {
@@ -135,7 +138,7 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
       fz = warpSum(fz);
       if (lane == 0) {
         // ForceTransverser::set: force[pi] += make_real4(total) (make_real4(real3) zero-fills w)
-        float4 f = force[idi];
+        float4 f = accumulate ? force[idi] : make_float4(0.f, 0.f, 0.f, 0.f);
         f.x += fx; f.y += fy; f.z += fz;
         force[idi] = f;
       }
@@ -148,9 +151,9 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
 
 using namespace ub200;
 
-extern "C" int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
-                                 uint32_t seed, uint32_t step, int idStride, void *d_force, const int *d_globalIdx,
-                                 void *stream) {
+static int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut, uint32_t seed,
+                  uint32_t step, int idStride, void *d_force, const int *d_globalIdx, int ownerLo, int ownerHi, int accumulate,
+                  void *stream) {
   if (!cl || !d_vel || !d_force || !(rcut > 0)) return UB200_ERR_INVALID_ARGUMENT;
   if (!cl->built) return UB200_ERR_NOT_BUILT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -175,11 +178,23 @@ extern "C" int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A,
   if (pairMic)
     dpdCellTraversal<true><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
                                                           cl->binStart.as<uint32_t>(), g, cl->ncells,
-                                                          (const float *)d_vel, par, (float4 *)d_force, d_globalIdx);
+                                                          (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate);
   else
     dpdCellTraversal<false><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
                                                            cl->binStart.as<uint32_t>(), g, cl->ncells,
-                                                           (const float *)d_vel, par, (float4 *)d_force, d_globalIdx);
+                                                           (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate);
   UB200_LAUNCHED();
   return UB200_OK;
+}
+
+extern "C" int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
+                                 uint32_t seed, uint32_t step, int idStride, void *d_force, const int *d_globalIdx,
+                                 void *stream) {
+  return dpdSum(cl, d_vel, A, gamma, sigma, rcut, seed, step, idStride, d_force, d_globalIdx, 0, 0x7fffffff, 1, stream);
+}
+extern "C" int ub200_dpd_sum_owned_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
+                                       uint32_t seed, uint32_t step, int idStride, void *d_force, int ownerLo, int ownerHi,
+                                       int accumulate, void *stream) {
+  if (ownerLo < 0 || ownerHi < ownerLo) return UB200_ERR_INVALID_ARGUMENT;
+  return dpdSum(cl, d_vel, A, gamma, sigma, rcut, seed, step, idStride, d_force, nullptr, ownerLo, ownerHi, accumulate, stream);
 }

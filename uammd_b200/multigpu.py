@@ -115,6 +115,71 @@ class DistributedLJMD:
                 self.eng.kick_kick_drift(pb, vel_blk, fb)
 
 
+class DistributedDPDMD:
+    """VerletNVE + PairForces<DPD> over `world` ranks by the same particle decomposition (BASELINE config 4 shape): the
+    DPD force depends on the velocities, so positions AND velocities are all-gathered every step (28 B per particle);
+    the pairwise noise is keyed on global particle indices, hence independent of the number of ranks. pos [N,4] and vel
+    [N,3] are full-size tensors replicated on every rank; force [N,4] is meaningful on the owned block."""
+
+    def __init__(self, box, pot, dt, N, engine="cuda", group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dec = BlockDecomposition(N, self.world, self.rank)
+        self.box, self.pot, self.dt, self.N, self.engine = box, pot, float(dt), N, engine
+        if engine == "cuda":
+            from . import _lib
+            from .md import CellList, _ptr, _stream_ptr
+            self.lib, self.check, self._ptr, self._stream = _lib.lib(), _lib.check, _ptr, _stream_ptr
+            self.nl = CellList()
+        else:
+            from oracle import oracle as orc
+            self.orc = orc
+        self.steps = 0
+
+    def _gather(self, t):
+        if self.world > 1:
+            lo, hi = self.dec.lo, self.dec.hi
+            dist.all_gather_into_tensor(t, t[lo:hi].clone() if t.device.type == "cpu" else t[lo:hi], group=self.group)
+
+    def _forces(self, pos, vel, force):
+        lo, hi, p = self.dec.lo, self.dec.hi, self.pot
+        p.step += 1  # DPD_impl::getForceTransverser increments the step before every evaluation (DPD.cuh:161-170)
+        if self.engine == "cuda":
+            self.nl.update(pos, self.box, p.getCutOff())
+            self.check(self.lib.ub200_dpd_sum_owned_f32(self.nl._h, self._ptr(vel), p.A, p.gamma, p.sigma, p.rcut, p.seed,
+                                                        p.step & 0xFFFFFFFF, self.N, self._ptr(force), lo, hi, 0, self._stream()))
+        else:
+            L = self.box.boxSize
+            g = self.orc.make_grid_f(L, self.orc.neighbour_celldim(L, p.getCutOff()))
+            cl = self.orc.celllist_build(g, pos.numpy())
+            f32, _ = self.orc.dpd_f32(g, cl, vel.numpy(), p.A, p.gamma, p.sigma, p.rcut, p.seed, p.step & 0xFFFFFFFF, self.N)
+            force.numpy()[lo:hi] = f32[lo:hi]
+
+    def _half(self, step, pos, vel, force):
+        lo, hi = self.dec.lo, self.dec.hi
+        pb, vb, fb = pos[lo:hi], vel[lo:hi], force[lo:hi]
+        if self.engine == "cuda":
+            self.check(self.lib.ub200_nve_half_step_f32(self._ptr(pb), self._ptr(vb), self._ptr(fb), C.c_void_p(0), 1.0,
+                                                        C.c_void_p(0), pb.shape[0], self.dt, 0, step, self._stream()))
+        else:
+            self.orc.nve_half(pb.numpy(), vb.numpy(), fb.numpy(), self.dt, 1.0, step)
+
+    def forwardTime(self, pos, vel, force):
+        """VerletNVE::forwardTime (VerletNVE.cu:174-188) with the DPD interactor."""
+        self.steps += 1
+        if self.steps == 1:
+            self._forces(pos, vel, force)
+        self._half(1, pos, vel, force)
+        self._gather(pos); self._gather(vel)
+        self._forces(pos, vel, force)
+        self._half(2, pos, vel, force)
+
+    def gatherState(self, pos, vel):
+        """Make the replicated copies consistent (the other ranks' blocks lag by the last kick otherwise)."""
+        self._gather(pos); self._gather(vel)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Slab-decomposed FCM (ub200_fcm_dist_*): z slabs of the grid, NVLink peer stores fused into the FFT passes.
 # ---------------------------------------------------------------------------------------------------------------
