@@ -34,6 +34,7 @@ RHO, RC, DT, TEMP = 0.8, 2.5, 0.005, 1.0
 ALG_BYTES_PAIR = 52          # per particle: R sortPos 16 + R groupIndex 4 + RMW force 32
 ALG_BYTES_STEP = 216         # per particle and step: build 36 + traverse 52 + integrate 112 + zero 16
 FLOP_PER_CANDIDATE = 25
+NCU_TRAFFIC_PAIR = 47.26e6   # bytes per ljCellTraversal launch at N = 1e6 (20.38 MB read + 26.88 MB written), profiles/r01b_lj_raw.csv
 FP32_PEAK_TFLOPS = 74.4      # 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
@@ -267,7 +268,8 @@ def main():
     pair_tflops = cand * FLOP_PER_CANDIDATE * N / (t_pair_ms * 1e-3) / 1e12
     roofline = {
         "kernel": "ljCellTraversal", "bound": "hbm", "achieved": pair_gbs, "peak": peak, "unit": "GB/s",
-        "frac": pair_gbs / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": t_pair_ms,
+        "frac": pair_gbs / peak, "traffic": NCU_TRAFFIC_PAIR if N == 1_000_000 else None, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_lj_raw.csv",
+        "peak_source": peak_src, "kernel_ms": t_pair_ms,
         "algorithmic_bytes_per_launch": ALG_BYTES_PAIR * N,
         "note": "the pair kernel is FP32-ALU/shared-memory bound, not HBM bound (SURVEY 8(d)); see fp32 and pipeline",
         "fp32": {"achieved_tflops": pair_tflops, "peak_tflops": FP32_PEAK_TFLOPS, "frac": pair_tflops / FP32_PEAK_TFLOPS,

@@ -78,7 +78,9 @@ def run(dev, hbm_peak, steps=100, warmup=10):
         "e2e": {"value": DOF / 1e6 * 1000.0 / e2e_ms, "unit": "Mdof.steps/s", "h2d_bytes_per_step": N * 64,
                 "d2h_bytes_per_step": N * 24},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                     "traffic": None, "algorithmic_bytes_per_step": ALG_BYTES,
+                     "traffic": 5.6e8, "traffic_source": "sum of dram bytes over the kernels of one step, profiles/r01b_fcm_raw.csv "
+                                                         "(cold-cache replays: an upper bound, the 51 MB grid stays in L2 between passes)",
+                     "algorithmic_bytes_per_step": ALG_BYTES,
                      "note": "whole step against the compulsory 7 grid passes + particle I/O (SURVEY 8(d))"},
     }
 
