@@ -291,3 +291,25 @@ def test_fcm_torques_match_reference(cuda, tmp_path):
     rel = lambda a_, b_: np.linalg.norm(a_ - b_) / np.linalg.norm(b_)
     print(f"[fcm torques vs reference] linear {rel(lin.cpu().numpy(), rlin):.2e} angular {rel(ang.cpu().numpy(), rang):.2e}")
     assert rel(lin.cpu().numpy(), rlin) < 1e-11 and rel(ang.cpu().numpy(), rang) < 1e-11
+
+
+def test_spread_dense_cloud_multiple_staging_chunks(orc, cuda):
+    """1.5 particles per cell: the row-brick spread stages its region in several chunks (capacity 512 records)."""
+    cells, L, N = (32, 32, 32), (32.0,) * 3, 50000
+    h = 1.0
+    pos = _cloud(N, L, 13)
+    val = syn.gaussian_forces(N, seed=14)
+    g = orc.make_grid_d(L, cells)
+    ref = orc.ibm_spread(g, orc.peskin3(h), pos, val, 34)
+    ibm = IBM(Peskin3(h), L, cells, 34)
+    grid = torch.full((32, 32, 34, 3), -3.0, dtype=torch.float64, device=cuda)
+    ibm.spread(torch.from_numpy(pos).to(cuda), torch.from_numpy(val).to(cuda), grid, overwrite=True)
+    sp = grid.cpu().numpy()
+    assert np.abs(sp[:, :, :32] - ref[:, :, :32]).max() < 1e-12 * np.abs(ref).max()
+    assert np.all(sp[:, :, 32:] == 0)
+    # a clustered cloud: every particle in one corner brick, the rest of the grid must come out exactly zero
+    pos2 = pos.copy(); pos2[:, :3] = pos2[:, :3] * 0.1 - 14.0
+    ref2 = orc.ibm_spread(g, orc.peskin3(h), pos2, val, 34)
+    ibm.spread(torch.from_numpy(pos2).to(cuda), torch.from_numpy(val).to(cuda), grid, overwrite=True)
+    sp2 = grid.cpu().numpy()
+    assert np.abs(sp2[:, :, :32] - ref2[:, :, :32]).max() < 1e-11 * np.abs(ref2).max()

@@ -111,3 +111,22 @@ def test_md_trajectory_matches_cell_list_engine(cuda):
     rebuilds = nl.getVerletList()["rebuilds"]
     assert 2 <= rebuilds < steps, rebuilds             # the skin is actually used
     assert (p - p2).abs().max().item() < 2e-3          # chaotic divergence of fp32 round-off over 60 steps stays tiny
+
+
+def test_dense_cloud_takes_the_unstaged_path(orc, cuda, tmp_path):
+    """rho = 2.5: ~1400 candidates per home cell (beyond the 640 staged per warp) and ~210 neighbours per particle (beyond the
+    96 assembled in shared memory): the global-memory walk and the long-list stores must give the same bits."""
+    N = 20000
+    Lb = float(np.float32((N / 2.5) ** (1.0 / 3.0)))
+    pos = syn.uniform_cloud(N, Lb, seed=77)
+    L = (Lb,) * 3
+    ref = _run_ref(tmp_path, pos, L)
+    pot = LJ(); pot.setPotParameters(0, 0, cutOff=2.5)
+    nl = VerletList()
+    nl.update(torch.from_numpy(pos).to(cuda), Box(L), 2.5)
+    d = nl.getVerletList()
+    nn = d["numberNeighbours"].cpu().numpy()
+    assert np.array_equal(nn, ref["nn"]) and nn.max() > 150
+    maxk = int(nn.max())
+    valid = np.arange(maxk)[:, None] < nn[None, :]
+    assert np.array_equal(d["neighbourList"].cpu().numpy()[:maxk][valid], ref["list"][valid])

@@ -65,6 +65,8 @@ struct ub200_md {
   ub200_celllist *cl = nullptr;
   LJTableCache ljTable;
   DevBuf dpos, dvel, dforce; // device state for the host-buffer entry point
+  cudaStream_t copyStream = nullptr; // host-buffer entry point: transfers overlapped with the force evaluations
+  cudaEvent_t evPosUp = nullptr, evVelUp = nullptr, evDrift = nullptr, evPosDown = nullptr;
 };
 
 extern "C" {
@@ -106,6 +108,10 @@ int ub200_md_destroy(ub200_md *md) {
   if (!md) return UB200_OK;
   ub200_celllist_destroy(md->cl);
   md->ljTable.dev.release(); md->dpos.release(); md->dvel.release(); md->dforce.release();
+  if (md->copyStream) {
+    cudaStreamDestroy(md->copyStream);
+    cudaEventDestroy(md->evPosUp); cudaEventDestroy(md->evVelUp); cudaEventDestroy(md->evDrift); cudaEventDestroy(md->evPosDown);
+  }
   delete md;
   return UB200_OK;
 }
@@ -187,21 +193,45 @@ int ub200_md_lj_nve_verlet_run_f32(ub200_md *md, ub200_verletlist *vl, void *d_p
 
 int ub200_md_lj_nve_run_host_f32(ub200_md *md, float *h_pos4, float *h_vel3, float *h_force4, int N, const float L[3],
                                  float rc, const float *params, int ntypes, float dt, int nsteps, void *stream) {
-  if (!md || !h_pos4 || !h_vel3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  if (!md || !h_pos4 || !h_vel3 || N <= 0 || nsteps < 1) return UB200_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   int e;
   if ((e = md->dpos.reserve(sizeof(float4) * (size_t)N))) return e;
   if ((e = md->dvel.reserve(sizeof(float) * 3 * (size_t)N))) return e;
   if ((e = md->dforce.reserve(sizeof(float4) * (size_t)N))) return e;
+  if (!md->copyStream) {
+    UB200_CUDA(cudaStreamCreateWithFlags(&md->copyStream, cudaStreamNonBlocking));
+    UB200_CUDA(cudaEventCreateWithFlags(&md->evPosUp, cudaEventDisableTiming));
+    UB200_CUDA(cudaEventCreateWithFlags(&md->evVelUp, cudaEventDisableTiming));
+    UB200_CUDA(cudaEventCreateWithFlags(&md->evDrift, cudaEventDisableTiming));
+    UB200_CUDA(cudaEventCreateWithFlags(&md->evPosDown, cudaEventDisableTiming));
+  }
+  cudaStream_t cs = md->copyStream;
+  const int nb = (N + 255) / 256;
+  // positions up on the compute stream; velocities up on the copy stream while F(t) is evaluated (it needs positions only)
   UB200_CUDA(cudaMemcpyAsync(md->dpos.p, h_pos4, sizeof(float4) * (size_t)N, cudaMemcpyHostToDevice, st));
-  UB200_CUDA(cudaMemcpyAsync(md->dvel.p, h_vel3, sizeof(float) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
+  UB200_CUDA(cudaEventRecord(md->evPosUp, st));
+  UB200_CUDA(cudaStreamWaitEvent(cs, md->evPosUp, 0)); // also orders the copy stream after the caller's earlier work
+  UB200_CUDA(cudaMemcpyAsync(md->dvel.p, h_vel3, sizeof(float) * 3 * (size_t)N, cudaMemcpyHostToDevice, cs));
+  UB200_CUDA(cudaEventRecord(md->evVelUp, cs));
   if ((e = ub200_md_lj_nve_prepare_f32(md, md->dpos.p, md->dforce.p, N, L, rc, params, ntypes, stream))) return e;
-  if ((e = ub200_md_lj_nve_run_f32(md, md->dpos.p, md->dvel.p, md->dforce.p, N, L, rc, params, ntypes, dt, nsteps, stream)))
+  UB200_CUDA(cudaStreamWaitEvent(st, md->evVelUp, 0));
+  if (nsteps > 1 && (e = ub200_md_lj_nve_run_f32(md, md->dpos.p, md->dvel.p, md->dforce.p, N, L, rc, params, ntypes, dt, nsteps - 1, stream)))
     return e;
-  UB200_CUDA(cudaMemcpyAsync(h_pos4, md->dpos.p, sizeof(float4) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  // last step by hand: after its drift the positions are final and go down while F(t+dt) and the last kick run
+  nveHalfStep<1><<<nb, 256, 0, st>>>(md->dpos.as<float4>(), md->dvel.as<float>(), md->dforce.as<float4>(), nullptr, 1.0f, nullptr, N, dt, 0);
+  UB200_LAUNCHED();
+  UB200_CUDA(cudaEventRecord(md->evDrift, st));
+  UB200_CUDA(cudaStreamWaitEvent(cs, md->evDrift, 0));
+  UB200_CUDA(cudaMemcpyAsync(h_pos4, md->dpos.p, sizeof(float4) * (size_t)N, cudaMemcpyDeviceToHost, cs));
+  UB200_CUDA(cudaEventRecord(md->evPosDown, cs));
+  if ((e = mdForces(md, md->dpos.p, md->dforce.p, N, L, rc, params, ntypes, st))) return e;
+  nveHalfStep<2><<<nb, 256, 0, st>>>(md->dpos.as<float4>(), md->dvel.as<float>(), md->dforce.as<float4>(), nullptr, 1.0f, nullptr, N, dt, 0);
+  UB200_LAUNCHED();
   UB200_CUDA(cudaMemcpyAsync(h_vel3, md->dvel.p, sizeof(float) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
   if (h_force4)
     UB200_CUDA(cudaMemcpyAsync(h_force4, md->dforce.p, sizeof(float4) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  UB200_CUDA(cudaStreamWaitEvent(st, md->evPosDown, 0));
   UB200_CUDA(cudaStreamSynchronize(st));
   return UB200_OK;
 }
