@@ -263,6 +263,12 @@ int ub200_fcm_dist_ipc_export(ub200_fcm_dist *fcm, void *blob);
 int ub200_fcm_dist_ipc_import(ub200_fcm_dist *fcm, const void *blobsOfAllRanks);
 int ub200_fcm_dist_mdot(ub200_fcm_dist *fcm, const void *d_pos, const void *d_force, int N, double temperature,
                         double prefactor, void *d_out3, void *stream);
+/* PSE far field on the same slab machinery (BASELINE config 3: "slab-decomposed FFT over 8 GPUs"): switch the spectral
+ * operator of a handle created with the PSE Gaussian window (supports 3, 5, 7) to the Hasimoto-split RPY Green's function
+ * (FarField.cuh:85-153). seedFar / seed2 as in ub200_pse_far_mdot; noise prefactor = prefactor sqrt(2 T / dV) (:467-492).
+ * ub200_fcm_dist_mdot then returns Mw F + noise (overwriting d_out3; the caller accumulates like IBM::gather would). */
+int ub200_fcm_dist_set_pse_operator(ub200_fcm_dist *fcm, double hydrodynamicRadius, double psi, double eta, double shearStrain);
+int ub200_fcm_dist_set_noise_seed2(ub200_fcm_dist *fcm, uint32_t seed2);
 /* diagnostics (environment UB200_DIST_PROFILE=1, makes every call synchronous): mean ms of the 12 phases of mdot */
 int ub200_fcm_dist_profile(ub200_fcm_dist *fcm, double phases[12]);
 /* synchronises the stream; *flag != 0 when a peer barrier timed out (a rank died) */
@@ -289,6 +295,7 @@ typedef struct {
   double eta, rcut;
   const void *d_table; /* real2[nTable]: F, G divided by 6 pi eta a */
   void *d_grid;
+  ub200_ibm_kernel kernel; /* the far-field Gaussian window (pse_ns::Kernel, FarField.cuh:25-41) as resolved by create */
 } ub200_pse_info_t;
 int ub200_pse_create(ub200_pse **out, int precisionBytes, const ub200_pse_params *par, uint32_t seedNear, uint32_t seedFar);
 int ub200_pse_destroy(ub200_pse *pse);

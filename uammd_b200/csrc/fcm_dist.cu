@@ -27,6 +27,7 @@
 // torch.distributed.all_gather_object). Barriers are one-block kernels that publish an epoch to every peer's flag
 // array with system-scope release stores and spin (bounded) on their own array.
 #include "fcm_op.cuh"
+#include "pse_op.cuh"
 #include "fft3d.cuh"
 #include "ibm_state.cuh"
 #include <algorithm>
@@ -66,6 +67,8 @@ template <class T> struct FcmDistState {
   IbmKernel<T> kern;
   double viscosity = 1, L[3];
   uint32_t seed = 0, seed2 = 0;
+  bool pseOperator = false; // spectral operator: FCM Stokes (default) or the PSE far-field Green's function
+  double pseRh = 0, psePsi = 0, pseEta = 0, pseShear = 0;
   // one exported allocation: [flags | S (owned planes + 2 halo) | T | inboxes: world x {count, index[], rows[]}]
   void *arena = nullptr;
   size_t arenaBytes = 0, offS = 0, offT = 0, offInbox = 0, inboxStride = 0, inboxIdxOff = 0, inboxRowsOff = 0;
@@ -83,6 +86,14 @@ template <class T> struct FcmDistState {
   // particle scratch (window)
   DevBuf binCount, binStart, tileSums, codeSlot, unstable, sortedIndex, sortedRec;
 
+  int recWords() const {
+    switch (kern.support) {
+    case 3: return RecGeom<T, 3>::REC;
+    case 4: return RecGeom<T, 4>::REC;
+    case 5: return RecGeom<T, 5>::REC;
+    default: return RecGeom<T, 7>::REC;
+    }
+  }
   size_t planeBytes() const { return (size_t)plan.ny * plan.nkx * 3 * sizeof(C); }
   size_t slabBytes() const { return (size_t)(nzl + 2 * halo) * planeBytes(); }
   size_t tposeBytes() const { return (size_t)plan.nz * nyl * plan.nkx * 3 * sizeof(C); }
@@ -93,7 +104,7 @@ template <class T> struct FcmDistState {
     rank = rank_; world = world_; maxParticles = maxParticles_;
     if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world || maxParticles < 1) return UB200_ERR_INVALID_ARGUMENT;
     if (cells[2] % world || cells[1] % world) return UB200_ERR_INVALID_ARGUMENT; // equal slabs in z and in ky
-    if (k.support != 3 && k.support != 4) return UB200_ERR_UNSUPPORTED;          // brick spread / sorted gather
+    if (k.support != 3 && k.support != 4 && k.support != 5 && k.support != 7) return UB200_ERR_UNSUPPORTED; // row-brick spread
     int rc = plan.init(cells[0], cells[1], cells[2]);
     if (rc) return rc;
     nzl = cells[2] / world; nyl = cells[1] / world; z0 = rank * nzl; y0 = rank * nyl;
@@ -192,7 +203,7 @@ template <class T> struct FcmDistState {
     // ---- particles of the window: bin, scan, scatter, order + stencil records ----
     if ((rc = codeSlot.reserve(sizeof(uint2) * (size_t)N)) || (rc = unstable.reserve(sizeof(int) * (size_t)N)) ||
         (rc = sortedIndex.reserve(sizeof(int) * (size_t)N)) ||
-        (rc = sortedRec.reserve(sizeof(T) * (kern.support == 3 ? RecGeom<T, 3>::REC : RecGeom<T, 4>::REC) * (size_t)N)))
+        (rc = sortedRec.reserve(sizeof(T) * recWords() * (size_t)N)))
       return rc;
     mark(0, st);
     ibmBinByCell<T4><<<nb, 256, 0, st>>>((const T4 *)pos, N, grid, binCount.as<uint32_t>(), codeSlot.as<uint2>());
@@ -202,7 +213,12 @@ template <class T> struct FcmDistState {
 #define UB200_ORDER(SS)                                                                                                  \
   ibmOrderSorted<T4, SS><<<nb, 256, 0, st>>>(unstable.as<int>(), codeSlot.as<uint2>(), binStart.as<uint32_t>(), (const T4 *)pos, \
                                              (const T *)force, 4, N, grid, kern, sortedIndex.as<int>(), sortedRec.as<T>())
-    if (kern.support == 3) UB200_ORDER(3); else UB200_ORDER(4);
+    switch (kern.support) {
+    case 3: UB200_ORDER(3); break;
+    case 4: UB200_ORDER(4); break;
+    case 5: UB200_ORDER(5); break;
+    default: UB200_ORDER(7); break;
+    }
 #undef UB200_ORDER
     UB200_LAUNCHED();
     mark(1, st);
@@ -219,7 +235,12 @@ template <class T> struct FcmDistState {
     UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                         \
     kfn<<<grd, kRbThreads, sm, st>>>(sortedRec.as<T>(), binStart.as<uint32_t>(), grid, plan.nxPad, S, z0, nzl);          \
   }
-      if (kern.support == 3) UB200_SPREAD(3) else UB200_SPREAD(4)
+      switch (kern.support) {
+      case 3: UB200_SPREAD(3) break;
+      case 4: UB200_SPREAD(4) break;
+      case 5: UB200_SPREAD(5) break;
+      default: UB200_SPREAD(7) break;
+      }
 #undef UB200_SPREAD
       UB200_LAUNCHED();
       mark(2, st);
@@ -237,23 +258,37 @@ template <class T> struct FcmDistState {
     if ((rc = barrier(st))) return rc;
     mark(5, st);
     // ---- fused z pass on the local ky rows; output pushed back into the owners' slabs ----
-    FcmSpectralOp<T> op;
-    op.nx = plan.nx; op.ny = plan.ny; op.nz = plan.nz; op.nkx = plan.nkx;
-    op.kfx = (T)(T(2.0) * T(M_PI) / (T)L[0]); op.kfy = (T)(T(2.0) * T(M_PI) / (T)L[1]); op.kfz = (T)(T(2.0) * T(M_PI) / (T)L[2]);
-    op.vis = (T)viscosity;
-    op.invNorm = T(1.0) / T((double)plan.nx * plan.ny * plan.nz);
-    op.deterministic = det;
-    op.noise = temperature > 0.0;
-    op.noisePrefactor = T(0);
-    op.seed1 = seed; op.seed2 = seed2;
-    op.yOff = y0;
-    if (op.noise) {
-      seed2++;
-      op.seed2 = seed2;
-      const T fourierNormalization = (T)(1.0 / ((double)plan.nx * plan.ny * plan.nz));
-      op.noisePrefactor = (T)prefactor * (T)sqrt((double)(fourierNormalization * 2 * (T)temperature / grid.cellVolume));
+    if (!pseOperator) {
+      FcmSpectralOp<T> op;
+      op.nx = plan.nx; op.ny = plan.ny; op.nz = plan.nz; op.nkx = plan.nkx;
+      op.kfx = (T)(T(2.0) * T(M_PI) / (T)L[0]); op.kfy = (T)(T(2.0) * T(M_PI) / (T)L[1]); op.kfz = (T)(T(2.0) * T(M_PI) / (T)L[2]);
+      op.vis = (T)viscosity;
+      op.invNorm = T(1.0) / T((double)plan.nx * plan.ny * plan.nz);
+      op.deterministic = det;
+      op.noise = temperature > 0.0;
+      op.noisePrefactor = T(0);
+      op.seed1 = seed; op.seed2 = seed2;
+      op.yOff = y0;
+      if (op.noise) {
+        seed2++;
+        op.seed2 = seed2;
+        const T fourierNormalization = (T)(1.0 / ((double)plan.nx * plan.ny * plan.nz));
+        op.noisePrefactor = (T)prefactor * (T)sqrt((double)(fourierNormalization * 2 * (T)temperature / grid.cellVolume));
+      }
+      if ((rc = launchPassAddr<T, 0, true, FcmSpectralOp<T>>(plan, az, nyl, st, op))) return rc;
+    } else { // PseState::farMdot
+      PseSpectralOp<T> op;
+      op.nx = plan.nx; op.ny = plan.ny; op.nz = plan.nz; op.nkx = plan.nkx;
+      op.kfx = T(2.0) * T(M_PI) / (T)L[0]; op.kfy = T(2.0) * T(M_PI) / (T)L[1]; op.kfz = T(2.0) * T(M_PI) / (T)L[2];
+      op.shear = (T)pseShear; op.rh = (T)pseRh; op.vis = (T)viscosity; op.split = (T)psePsi; op.eta = (T)pseEta;
+      op.nTot = (T)(plan.nx * plan.ny * plan.nz);
+      op.deterministic = det;
+      op.noise = temperature > 0.0;
+      op.seed1 = seed; op.seed2 = seed2; // seed2: set by the caller before every noisy call (ub200_fcm_dist_set_noise_seed2)
+      op.yOff = y0;
+      op.noisePrefactor = op.noise ? (T)prefactor * (T)sqrt(2 * (T)temperature / grid.cellVolume) : T(0);
+      if ((rc = launchPassAddr<T, 0, true, PseSpectralOp<T>>(plan, az, nyl, st, op))) return rc;
     }
-    if ((rc = launchPassAddr<T, 0, true, FcmSpectralOp<T>>(plan, az, nyl, st, op))) return rc;
     mark(6, st);
     if ((rc = barrier(st))) return rc;
     mark(7, st);
@@ -265,12 +300,16 @@ template <class T> struct FcmDistState {
     mark(8, st);
     // ---- gather for the owned particles (local loads), packed rows ----
     const int ngb = (N + 127) / 128;
-    if (kern.support == 3)
-      ibmGatherSortedSlab<T, 3><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(), grid, plan.nxPad,
-                                                    Sall, z0, nzl, halo, packIdx.as<int>(), packRows.as<T>(), packCount.as<int>());
-    else
-      ibmGatherSortedSlab<T, 4><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(), grid, plan.nxPad,
-                                                    Sall, z0, nzl, halo, packIdx.as<int>(), packRows.as<T>(), packCount.as<int>());
+#define UB200_GSLAB(SS)                                                                                                       \
+  ibmGatherSortedSlab<T, SS><<<ngb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), binStart.as<uint32_t>(), grid, plan.nxPad, \
+                                                  Sall, z0, nzl, halo, packIdx.as<int>(), packRows.as<T>(), packCount.as<int>())
+    switch (kern.support) {
+    case 3: UB200_GSLAB(3); break;
+    case 4: UB200_GSLAB(4); break;
+    case 5: UB200_GSLAB(5); break;
+    default: UB200_GSLAB(7); break;
+    }
+#undef UB200_GSLAB
     UB200_LAUNCHED();
     mark(9, st);
     // ---- push the packed block into inbox[rank] of every rank ----
@@ -354,6 +393,17 @@ int ub200_fcm_dist_mdot(ub200_fcm_dist *h, const void *d_pos, const void *d_forc
   if (!h || !d_pos || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
   return h->precision == 4 ? h->f.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream)
                            : h->d.mdot(d_pos, d_force, N, temperature, prefactor, d_out3, (cudaStream_t)stream);
+}
+int ub200_fcm_dist_set_pse_operator(ub200_fcm_dist *h, double hydrodynamicRadius, double psi, double eta, double shearStrain) {
+  if (!h || !(hydrodynamicRadius > 0) || !(psi > 0)) return UB200_ERR_INVALID_ARGUMENT;
+  auto set = [&](auto &s) { s.pseOperator = true; s.pseRh = hydrodynamicRadius; s.psePsi = psi; s.pseEta = eta; s.pseShear = shearStrain; };
+  set(h->f); set(h->d);
+  return UB200_OK;
+}
+int ub200_fcm_dist_set_noise_seed2(ub200_fcm_dist *h, uint32_t seed2) {
+  if (!h) return UB200_ERR_INVALID_ARGUMENT;
+  h->f.seed2 = seed2; h->d.seed2 = seed2;
+  return UB200_OK;
 }
 /* reads back (synchronising the stream) whether a peer barrier ever timed out */
 int ub200_fcm_dist_error_flag(ub200_fcm_dist *h, void *stream, int *flag) {

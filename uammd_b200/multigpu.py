@@ -256,3 +256,40 @@ class DistributedFCM:
         if self._h:
             self.lib.ub200_fcm_dist_destroy(self._h)
             self._h = None
+
+
+class DistributedPSEFarField:
+    """pse_ns::FarField::computeHydrodynamicDisplacements (PSE/FarField.cuh:535-553) over `world` GPUs: the slab machinery of
+    DistributedFCM with the PSE Gaussian window and the Hasimoto-split RPY Green's function (BASELINE config 3:
+    "slab-decomposed FFT over 8 GPUs"). Grid, support and eta are resolved by the single-GPU ub200_pse_create, so the two
+    paths cannot drift apart; the grids are bit-identical to the single-GPU ones, the interpolation differs in fp32 summation order."""
+
+    def __init__(self, par, maxParticles, seedFar, dtype=torch.float32, group=None):
+        from . import pse as P
+        from .bd import System
+        # a throw-away single-GPU handle only to resolve the derived parameters like the reference constructors do
+        probe = P.PSE(torch.zeros(1, 4, dtype=dtype, device="cuda"), par, sys=System(1))
+        inf = probe.info()
+        self.cells, self.support, self.eta = tuple(inf.cells), inf.support, inf.eta
+
+        class _K:
+            def struct(_self):
+                from .fcm import IBMKernelStruct
+                k = inf.kernel
+                return IBMKernelStruct(k.kind, k.support, k.h, k.prefactor, k.tau, k.rmax)
+        self.fcm = DistributedFCM(par.box, self.cells, _K(), par.viscosity, maxParticles, seed=seedFar, dtype=dtype, group=group)
+        l = self.fcm.lib
+        l.ub200_fcm_dist_set_pse_operator.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+        l.ub200_fcm_dist_set_noise_seed2.argtypes = [C.c_void_p, C.c_uint32]
+        self.fcm.check(l.ub200_fcm_dist_set_pse_operator(self.fcm._h, par.hydrodynamicRadius, par.psi, self.eta, par.shearStrain))
+        del probe
+
+    def computeHydrodynamicDisplacements(self, pos, force, MF, temperature=0.0, prefactor=0.0, seed2=0, stream=None):
+        """MF += Mw F + prefactor sqrt(2T) Mw^1/2 dW (the reference's gather accumulates)."""
+        self.fcm.check(self.fcm.lib.ub200_fcm_dist_set_noise_seed2(self.fcm._h, seed2 & 0xFFFFFFFF))
+        out = self.fcm.computeHydrodynamicDisplacements(pos, force, temperature=temperature, prefactor=prefactor, stream=stream)
+        MF += out
+        return MF
+
+    def close(self):
+        self.fcm.close()

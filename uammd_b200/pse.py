@@ -19,9 +19,15 @@ class PSEParams(C.Structure):
                 ("cellsOverride", C.c_int * 3)]
 
 
+class IBMKernelStruct(C.Structure):
+    _fields_ = [("kind", C.c_int), ("support", C.c_int), ("h", C.c_double), ("prefactor", C.c_double),
+                ("tau", C.c_double), ("rmax", C.c_double)]
+
+
 class PSEInfo(C.Structure):
     _fields_ = [("cells", C.c_int * 3), ("support", C.c_int), ("nTable", C.c_int), ("lastLanczosIterations", C.c_int),
-                ("eta", C.c_double), ("rcut", C.c_double), ("d_table", C.c_void_p), ("d_grid", C.c_void_p)]
+                ("eta", C.c_double), ("rcut", C.c_double), ("d_table", C.c_void_p), ("d_grid", C.c_void_p),
+                ("kernel", IBMKernelStruct)]
 
 
 def _declare():
