@@ -125,12 +125,13 @@ ibmBinByCell(const T4 *__restrict__ pos, int N, GridT<decltype(T4::x)> g, uint32
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const T4 p = pos[i];
-  int cx = cellOfT(g, 0, p.x), cy = cellOfT(g, 1, p.y), cz = cellOfT(g, 2, p.z);
-  cx = min(max(cx, 0), g.n[0] - 1);
-  cy = min(max(cy, 0), g.n[1] - 1);
+  int cz = cellOfT(g, 2, p.z);
   cz = min(max(cz, 0), g.n[2] - 1);
   const int lz = windowZ(g, cz);
-  if (lz >= g.zwinN) { codeSlot[i] = make_uint2(0xffffffffu, 0u); return; }
+  if (lz >= g.zwinN) { codeSlot[i] = make_uint2(0xffffffffu, 0u); return; } // slab sort: most particles leave here
+  int cx = cellOfT(g, 0, p.x), cy = cellOfT(g, 1, p.y);
+  cx = min(max(cx, 0), g.n[0] - 1);
+  cy = min(max(cy, 0), g.n[1] - 1);
   const uint32_t code = (uint32_t)cx + (uint32_t)g.n[0] * ((uint32_t)cy + (uint32_t)g.n[1] * (uint32_t)lz);
   const unsigned active = __activemask();
   const unsigned peers = __match_any_sync(active, code);
