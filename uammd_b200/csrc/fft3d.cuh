@@ -107,18 +107,19 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
       if (2 * p + 1 < nl) cbase[(size_t)(2 * p + 1) * nkx * 3 + rem] = B;
     }
   } else {
-    // build Z_k = A_k + i B_k for all k from the stored halves (Hermitian symmetry for k > nx/2); like a C2R
-    // transform, the imaginary parts of the self-conjugate modes (k = 0, and k = nx/2 for even nx) are ignored
+    // build Z_k = A_k + i B_k for all k from the stored halves: every stored mode is loaded ONCE and also written to its
+    // Hermitian mirror k' = nx - k (A_k' = conj A_k, B_k' = conj B_k); like a C2R transform, the imaginary parts of the
+    // self-conjugate modes (k = 0, and k = nx/2 for even nx) are ignored
     for (int p = 0; p < pairs; p++)
-    for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
+    for (int rem = threadIdx.x; rem < nkx * 3; rem += blockDim.x) {
       const int k = rem / 3, c = rem - 3 * k;
-      const int ks = k < nkx ? k : nx - k;
       C A = mk2<T>(T(0), T(0)), B = A;
-      if (2 * p < nl) A = cbase[(size_t)(2 * p) * nkx * 3 + ks * 3 + c];
-      if (2 * p + 1 < nl) B = cbase[(size_t)(2 * p + 1) * nkx * 3 + ks * 3 + c];
-      if (k >= nkx) { A.y = -A.y; B.y = -B.y; }
+      if (2 * p < nl) A = cbase[(size_t)(2 * p) * nkx * 3 + rem];
+      if (2 * p + 1 < nl) B = cbase[(size_t)(2 * p + 1) * nkx * 3 + rem];
       if (k == 0 || 2 * k == nx) { A.y = T(0); B.y = T(0); }
-      buf0[(p * 3 + c) * fstride + k] = mk2<T>(A.x - B.y, A.y + B.x);
+      C *row = buf0 + (p * 3 + c) * fstride;
+      row[k] = mk2<T>(A.x - B.y, A.y + B.x);
+      if (k > 0 && 2 * k < nx) row[nx - k] = mk2<T>(A.x + B.y, B.x - A.y);
     }
     __syncthreads();
     C *res = fftShared<T, +1, NFIX>(buf0, buf1, ax, fstride, nf, tw);

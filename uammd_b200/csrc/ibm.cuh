@@ -544,12 +544,15 @@ template <class T4, class V, bool SPREAD, bool ACCUMULATE>
 __global__ void __launch_bounds__(128)
 ibmWarpPerParticle(const T4 *__restrict__ pos, const V *__restrict__ val, int valStride, int N,
                    GridT<decltype(T4::x)> g, IbmKernel<decltype(T4::x)> k, int nxPad,
-                   decltype(T4::x) *__restrict__ grid3, decltype(T4::x) *__restrict__ out3) {
+                   decltype(T4::x) *__restrict__ grid3, decltype(T4::x) *__restrict__ out3, const int *__restrict__ order) {
+  // order: optional cell-sorted permutation (the sort of a preceding spread): neighbouring warps then touch neighbouring
+  // nodes and the grid is served from L1/L2 instead of being gathered at random from HBM
   using T = decltype(T4::x);
   __shared__ T wsh[4][3 * kMaxSupport];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 4 + warp;
-  if (i >= N) return;
+  const int slot = blockIdx.x * 4 + warp;
+  if (slot >= N) return;
+  const int i = order ? order[slot] : slot;
   const T4 p = pos[i];
   const T pr[3] = {p.x, p.y, p.z};
   int o[3];

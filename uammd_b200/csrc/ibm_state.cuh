@@ -116,7 +116,7 @@ template <class T> struct IbmState {
     if (!gridIsZero)
       UB200_CUDA(cudaMemsetAsync(grid3, 0, sizeof(T) * 3 * (size_t)nxPad * grid.n[1] * grid.n[2], st));
     ibmWarpPerParticle<T4, T, true, false><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)val, valStride, N,
-                                                                         grid, kern, nxPad, grid3, nullptr);
+                                                                         grid, kern, nxPad, grid3, nullptr, nullptr);
     UB200_LAUNCHED();
     sortedValidFor = -1;
     return UB200_OK;
@@ -139,12 +139,14 @@ template <class T> struct IbmState {
       UB200_LAUNCHED();
       return UB200_OK;
     }
+    // supports 5 / 7: the spread of the same positions left a cell-sorted permutation behind
+    const int *order = (nodeCentric && reuseRecords && sortedValidFor == N) ? sortedIndex.as<int>() : nullptr;
     if (accumulate)
       ibmWarpPerParticle<T4, T, false, true><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)nullptr, 0, N, grid,
-                                                                         kern, nxPad, const_cast<T *>(grid3), out3);
+                                                                         kern, nxPad, const_cast<T *>(grid3), out3, order);
     else
       ibmWarpPerParticle<T4, T, false, false><<<(N + 3) / 4, 128, 0, st>>>((const T4 *)pos, (const T *)nullptr, 0, N,
-                                                                          grid, kern, nxPad, const_cast<T *>(grid3), out3);
+                                                                          grid, kern, nxPad, const_cast<T *>(grid3), out3, order);
     UB200_LAUNCHED();
     return UB200_OK;
   }

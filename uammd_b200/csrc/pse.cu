@@ -563,7 +563,7 @@ template <class T> struct PseState {
     if ((rc = launchPassZ<T, 0, PseSpectralOp<T>>(plan, g, st, op))) return rc;
     if ((rc = launchPassY<T, +1>(plan, g, st))) return rc;
     if ((rc = launchPassX<T, false>(plan, g, st))) return rc;
-    return ibm.gather(pos, N, g, (T *)MF3, true, false, st); // IBM::gather accumulates (misc/IBM.cu:231-233)
+    return ibm.gather(pos, N, g, (T *)MF3, true, det, st); // IBM::gather accumulates (misc/IBM.cu:231-233); reuses the spread's sort
   }
 
   // ---------------- near field ----------------

@@ -99,37 +99,59 @@ verletFill(const float4 *__restrict__ sortPos, const uint32_t *__restrict__ binS
       __syncwarp();
       for (int h0 = 0; h0 < hCount; h0 += kVerletHome) {
         const int nh = min(kVerletHome, hCount - h0);
-        for (int h = 0; h < nh; h++) {
-          const int id = hStart + h0 + h;
-          const float4 piRaw = ldg4(sortPos + id);
-          float4 pi = piRaw;
-          toHomeImage(pi, g, hc);
-          int nneigh = 0; // warp uniform
-          bool over = false;
-          for (int t0 = 0; t0 < nc.total; t0 += 32) {
+        for (int h = 0; h < nh; h += 2) { // two home particles per pass: one shared-memory load feeds two tests
+          const bool two = h + 1 < nh;
+          const int id0 = hStart + h0 + h, id1 = id0 + (two ? 1 : 0);
+          const float4 raw0 = ldg4(sortPos + id0), raw1 = ldg4(sortPos + id1);
+          float4 p0 = raw0, p1 = raw1;
+          toHomeImage(p0, g, hc);
+          toHomeImage(p1, g, hc);
+          int n0 = 0, n1 = 0; // warp uniform
+          bool over0 = false, over1 = !two;
+          for (int t0 = 0; t0 < nc.total && !(over0 && over1); t0 += 32) {
             const int t = t0 + lane;
-            bool hit = false;
+            bool hit0 = false, hit1 = false;
             if (t < nc.total) {
               const float4 pj = cand[t];
-              const float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-              const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-              hit = r2 <= cutLo;
-              if (!hit && r2 <= cutHi) hit = verletHitExact(piRaw, ldg4(sortPos + __float_as_int(pj.w)), g, cutOff2);
+              const float ax = pj.x - p0.x, ay = pj.y - p0.y, az = pj.z - p0.z;
+              const float bx = pj.x - p1.x, by = pj.y - p1.y, bz = pj.z - p1.z;
+              const float ra = __fmaf_rn(az, az, __fmaf_rn(ay, ay, ax * ax)), rb = __fmaf_rn(bz, bz, __fmaf_rn(by, by, bx * bx));
+              hit0 = ra <= cutLo;
+              hit1 = rb <= cutLo;
+              if ((!hit0 && ra <= cutHi) || (!hit1 && rb <= cutHi)) { // rare: within 1e-4 of the cut-off -> the reference's arithmetic
+                const float4 pjRaw = ldg4(sortPos + __float_as_int(pj.w));
+                if (!hit0 && ra <= cutHi) hit0 = verletHitExact(raw0, pjRaw, g, cutOff2);
+                if (!hit1 && rb <= cutHi) hit1 = verletHitExact(raw1, pjRaw, g, cutOff2);
+              }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            const int slot = nneigh + __popc(m & ((1u << lane) - 1u));
+            hit0 = hit0 && !over0;
+            hit1 = hit1 && !over1;
+            const unsigned m0 = __ballot_sync(0xffffffffu, hit0), m1 = __ballot_sync(0xffffffffu, hit1);
+            const unsigned below = (1u << lane) - 1u;
+            const int s0 = n0 + __popc(m0 & below), s1 = n1 + __popc(m1 & below);
             // the reference stops a particle as soon as its count reaches maxNeighboursPerParticle (:60-63)
-            if (hit && slot + 1 < maxNeighbours) {
-              if (slot < kVerletK) lbuf[h][slot] = (unsigned short)t;
-              else neighbourList[(size_t)slot * N + id] = __float_as_int(cand[t].w); // rare: longer than the shared buffer
+            if (hit0 && s0 + 1 < maxNeighbours) {
+              if (s0 < kVerletK) lbuf[h][s0] = (unsigned short)t;
+              else neighbourList[(size_t)s0 * N + id0] = __float_as_int(cand[t].w); // rare: longer than the shared buffer
             }
-            nneigh += __popc(m);
-            if (nneigh >= maxNeighbours) { over = true; break; }
+            if (hit1 && s1 + 1 < maxNeighbours) {
+              if (s1 < kVerletK) lbuf[h + 1][s1] = (unsigned short)t;
+              else neighbourList[(size_t)s1 * N + id1] = __float_as_int(cand[t].w);
+            }
+            n0 += __popc(m0);
+            n1 += __popc(m1);
+            if (n0 >= maxNeighbours) over0 = true;
+            if (n1 >= maxNeighbours) over1 = true;
           }
           if (lane == 0) {
-            cntBuf[h] = over ? -1 : nneigh;
-            if (over) atomicMax(overflow, (uint32_t)nneigh);
-            else numberNeighbours[id] = nneigh;
+            cntBuf[h] = over0 ? -1 : n0;
+            if (over0) atomicMax(overflow, (uint32_t)n0);
+            else numberNeighbours[id0] = n0;
+            if (two) {
+              cntBuf[h + 1] = over1 ? -1 : n1;
+              if (over1) atomicMax(overflow, (uint32_t)n1);
+              else numberNeighbours[id1] = n1;
+            }
           }
         }
         __syncwarp();
