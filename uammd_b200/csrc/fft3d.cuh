@@ -2,6 +2,7 @@
 // instantiate the fused z pass with their own spectral operators.
 #pragma once
 #include "fft.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -36,7 +37,7 @@ template <class T> struct Fft3dPlan {
     };
     // experiment knobs (environment): UB200_FFT_TILE = kx per strided tile (1, 2, 4), UB200_FFT_PAIRS = line pairs per x CTA
     const char *envTile = getenv("UB200_FFT_TILE"), *envPairs = getenv("UB200_FFT_PAIRS");
-    const int maxTile = envTile ? atoi(envTile) : 4, maxPairs = envPairs ? atoi(envPairs) : 4;
+    const int maxTile = envTile ? atoi(envTile) : 4, maxPairs = envPairs ? std::min(atoi(envPairs), 4) : 4;
     const int pairs = fit(nx, 3, maxPairs, 2);
     linesPerCta = 2 * pairs;
     smemX = 2 * (size_t)pairs * 3 * (nx + 1) * sizeof(C);
@@ -66,6 +67,21 @@ private:
   }
 };
 
+// 16- or 8-byte asynchronous global->shared copy (LDGSTS): no registers, completion through commit groups
+template <class C> __device__ __forceinline__ void cpAsync(C *smemDst, const C *gmemSrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+// 4- or 8-byte variant for real-valued lines (x pass)
+template <class T> __device__ __forceinline__ void cpAsyncReal(T *smemDst, const T *gmemSrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmemSrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---------------- X pass: real <-> complex along the contiguous axis, in place ----------------
 template <class T, bool FORWARD, int NFIX>
 __global__ void __launch_bounds__(kFftThreads)
@@ -86,13 +102,17 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
   C *cbase = reinterpret_cast<C *>(base);
   if (FORWARD) {
     // load real lines: line l, sample x, component c -> transform (l/2)*3+c, real (l even) or imaginary part
+    // (asynchronous copies: every load of the CTA's lines is in flight at once instead of one dependent load -> store
+    //  round trip per element; measured 1.8 TB/s with plain loads)
     for (int l = 0; l < linesPerCta; l++)
       for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
         const int x = rem / 3, c = rem - 3 * x;
-        const T v = l < nl ? base[(size_t)l * lineReals + rem] : T(0);
-        T *dst = reinterpret_cast<T *>(buf0 + ((l >> 1) * 3 + c) * fstride + x);
-        dst[l & 1] = v;
+        T *dst = reinterpret_cast<T *>(buf0 + ((l >> 1) * 3 + c) * fstride + x) + (l & 1);
+        if (l < nl) cpAsyncReal(dst, base + (size_t)l * lineReals + rem);
+        else *dst = T(0);
       }
+    cpAsyncCommit();
+    cpAsyncWait<0>();
     __syncthreads();
     C *res = fftShared<T, -1, NFIX>(buf0, buf1, ax, fstride, nf, tw);
     // untangle the two real transforms and store the Hermitian halves
@@ -110,16 +130,24 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
     // build Z_k = A_k + i B_k for all k from the stored halves: every stored mode is loaded ONCE and also written to its
     // Hermitian mirror k' = nx - k (A_k' = conj A_k, B_k' = conj B_k); like a C2R transform, the imaginary parts of the
     // self-conjugate modes (k = 0, and k = nx/2 for even nx) are ignored
-    for (int p = 0; p < pairs; p++)
     for (int rem = threadIdx.x; rem < nkx * 3; rem += blockDim.x) {
       const int k = rem / 3, c = rem - 3 * k;
-      C A = mk2<T>(T(0), T(0)), B = A;
-      if (2 * p < nl) A = cbase[(size_t)(2 * p) * nkx * 3 + rem];
-      if (2 * p + 1 < nl) B = cbase[(size_t)(2 * p + 1) * nkx * 3 + rem];
-      if (k == 0 || 2 * k == nx) { A.y = T(0); B.y = T(0); }
-      C *row = buf0 + (p * 3 + c) * fstride;
-      row[k] = mk2<T>(A.x - B.y, A.y + B.x);
-      if (k > 0 && 2 * k < nx) row[nx - k] = mk2<T>(A.x + B.y, B.x - A.y);
+      C A[4], B[4]; // pairs <= 4: all loads of this thread are issued back to back
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        A[p] = mk2<T>(T(0), T(0)); B[p] = A[p];
+        if (p < pairs && 2 * p < nl) A[p] = cbase[(size_t)(2 * p) * nkx * 3 + rem];
+        if (p < pairs && 2 * p + 1 < nl) B[p] = cbase[(size_t)(2 * p + 1) * nkx * 3 + rem];
+      }
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        if (p >= pairs) break;
+        C a = A[p], b = B[p];
+        if (k == 0 || 2 * k == nx) { a.y = T(0); b.y = T(0); }
+        C *row = buf0 + (p * 3 + c) * fstride;
+        row[k] = mk2<T>(a.x - b.y, a.y + b.x);
+        if (k > 0 && 2 * k < nx) row[nx - k] = mk2<T>(a.x + b.y, b.x - a.y);
+      }
     }
     __syncthreads();
     C *res = fftShared<T, +1, NFIX>(buf0, buf1, ax, fstride, nf, tw);
@@ -139,15 +167,6 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
 struct NoSpectralOp {
   template <class C> __device__ __forceinline__ void operator()(int, int, int, C &, C &, C &) const {}
 };
-
-// 16- or 8-byte asynchronous global->shared copy (LDGSTS): no registers, completion through commit groups
-template <class C> __device__ __forceinline__ void cpAsync(C *smemDst, const C *gmemSrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
-  if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmemSrc) : "memory");
-}
-__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Address policies of the strided pass: where axis point i of tile (other, kx0) is loaded from / stored to.
 // In place (one GPU): the same grid for both.
