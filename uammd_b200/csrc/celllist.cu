@@ -120,22 +120,41 @@ __global__ void __launch_bounds__(kScanThreads) scanApply(uint32_t *__restrict__
                                                           const uint32_t *__restrict__ tileOffsets,
                                                           uint32_t *__restrict__ out) {
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  static_assert(kScanItems == 8, "vector path below moves 2 x uint4 per thread");
   uint32_t v[kScanItems];
   uint32_t s = 0;
+  const bool full = base + kScanItems <= M; // whole 32-byte run of this thread inside the array: 128-bit accesses
+  if (full) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(in + base), b = *reinterpret_cast<const uint4 *>(in + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    v[k] = (base + k < M) ? in[base + k] : 0;
-    s += v[k];
+    for (int k = 0; k < kScanItems; k++) s += v[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      v[k] = (base + k < M) ? in[base + k] : 0;
+      s += v[k];
+    }
   }
   uint32_t total;
   uint32_t ex = blockExclusiveScan<kScanThreads>(s, &total) + tileOffsets[blockIdx.x];
+  if (full) {
+    uint32_t o[kScanItems];
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    if (base + k < M) {
-      out[base + k] = ex;
-      in[base + k] = 0;
+    for (int k = 0; k < kScanItems; k++) { o[k] = ex; ex += v[k]; }
+    *reinterpret_cast<uint4 *>(out + base) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4 *>(out + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<uint4 *>(in + base) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4 *>(in + base + 4) = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      if (base + k < M) {
+        out[base + k] = ex;
+        in[base + k] = 0;
+      }
+      ex += v[k];
     }
-    ex += v[k];
   }
   if (base <= M - 1 && M - 1 < base + kScanItems) out[M] = ex; // thread owning the last item: ex == grand total
 }
