@@ -164,3 +164,21 @@ def test_noise_is_hermitian_and_projected(orc):
     inner = np.ones_like(div, bool)
     inner[n // 2, :, :] = inner[:, n // 2, :] = inner[:, :, n // 2] = False
     assert np.abs(div[inner]).max() < 1e-12 and np.isfinite(back).all()
+
+
+def test_rotational_self_mobility_known_answer(orc):
+    """Rotational FCM (torque path, FCM_impl.cuh:306-358,583-649): with the torque kernel the reference derives from the
+    hydrodynamic radius (width = a / (6 sqrt(pi))^(1/3), BDHI_FCM.cuh:69-80) a unit torque spins the particle with
+    1/(8 pi eta a^3), the rotational mobility of a sphere, up to periodic corrections O((a/L)^3); a pure torque moves nothing."""
+    import math
+    eta, tol, n, L = 1.3, 1e-6, 64, 40.0
+    h = L / n
+    kern, a = orc.gaussian_fcm(h, tol)
+    kt = orc.gaussian_torque(a / (6 * math.sqrt(math.pi)) ** (1 / 3.0), h, tol)
+    want = 1.0 / (8 * math.pi * eta * a ** 3)
+    for d, p in ((0, (0.3, -0.2, 0.1)), (2, (-11.1, 7.7, 19.9))):
+        pos = np.zeros((1, 4)); pos[0, :3] = p
+        tor = np.zeros((1, 3)); tor[0, d] = 1.0
+        lin, ang = orc.fcm_mdot((L,) * 3, (n,) * 3, kern, eta, pos, None, torque3=tor, kernTorque=kt)
+        assert abs(ang[0, d] - want) < 5e-4 * want
+        assert np.abs(np.delete(ang[0], d)).max() < 1e-12 and np.abs(lin).max() < 1e-5 * want
