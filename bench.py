@@ -351,7 +351,7 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
     import uammd_b200
     from uammd_b200.multigpu import DistributedLJMD
     lib = uammd_b200.lib()
-    md = DistributedLJMD(box, pot, DT, N, engine="cuda")
+    md = DistributedLJMD(box, pot, DT, N)
     lo, hi = md.dec.lo, md.dec.hi
     p = torch.from_numpy(pos).to(dev)
     f = torch.zeros(N, 4, device=dev)

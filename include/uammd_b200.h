@@ -99,6 +99,25 @@ int ub200_lj_sum_devparams_f32(ub200_celllist *cl, const void *d_params, int nty
 int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, int ownerLo,
                            int ownerHi, int accumulate, void *stream);
 
+/* All-pairs fallback of PairForces: the reference switches to NBody::transverse when the box is no larger than
+ * 3 cut-offs in every dimension (Interactor/PairForces.cu:49-53,61-66 -> Interactor/NBodyBase.cuh:46-116). One thread
+ * per particle, the others visited in ascending group order and accumulated sequentially like the reference kernel,
+ * per-pair minimum image (RadialPotential.cuh:107-127). d_globalIdx: optional group index list (N entries);
+ * outputs accumulate (+=). */
+int ub200_lj_nbody_f32(const void *d_pos, const int *d_globalIdx, int N, const float L[3], const int periodic[3],
+                       const float *params, int ntypes, void *d_force, float *d_energy, float *d_virial, void *stream);
+
+/* Brick domain decomposition of the pair path over the GPUs of one box (the reference is single-GPU: new functionality,
+ * SURVEY 8(e); BASELINE config 4 "ghost-cell halo exchange"). Defined on the reference's neighbour grid
+ * (CellList::createUpdateGrid, CellList.cuh:100-126; Grid::getCell, utils/Grid.cuh:49-71, same roundings as
+ * ub200_celllist_build_f32): rank (kx,ky,kz) of rankGrid owns the cells [floor(k n/p), floor((k+1) n/p)) of every
+ * dimension and the particles in them; rank r needs as ghosts the particles of the cells adjacent (27-neighbourhood,
+ * periodic wrap like Grid::pbc_cell, utils/Grid.cuh:81-106) to its own. Per particle: d_cell (optional) linear cell
+ * index x-fastest, d_owner the owning rank (kx + px (ky + py kz)), d_ghostMask bit r set iff rank r != owner needs the
+ * particle as a ghost. At most 32 ranks; every brick must hold at least one cell per dimension. */
+int ub200_brick_classify_f32(const void *d_pos, int N, const float L[3], const int periodic[3], const int cellDim[3],
+                             const int rankGrid[3], int *d_cell, int *d_owner, uint32_t *d_ghostMask, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Path 1d: Verlet (skin) list. Replaces VerletList::update (Interactor/NeighbourList/VerletList.cuh:111-124) and
  * the classes beneath it (VerletList/VerletListBase.cuh:73-199, BasicList/BasicListBase.cuh:76-215): rebuild when
@@ -151,6 +170,13 @@ int ub200_dpd_sum_f32(ub200_celllist *cl, const void *d_vel, float A, float gamm
 int ub200_dpd_sum_owned_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
                             uint32_t seed, uint32_t step, int idStride, void *d_force, int ownerLo, int ownerHi,
                             int accumulate, void *stream);
+
+/* Brick decomposition of the DPD forces: the local arrays hold owned particles [ownerLo, ownerHi) followed by ghosts;
+ * d_noiseId[i] is the GLOBAL id of local particle i, used only in the Saru key ij = min + idStride*max (DPD.cuh:128),
+ * with idStride = global N, so the pairwise noise is the single-GPU one whatever the decomposition. */
+int ub200_dpd_sum_owned_ids_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
+                                uint32_t seed, uint32_t step, int idStride, void *d_force, int ownerLo, int ownerHi,
+                                int accumulate, const int *d_noiseId, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Path 1c: velocity Verlet. Replaces VerletNVE_ns::integrateGPU<1|2> (Integrator/VerletNVE.cu:64-85)

@@ -65,6 +65,13 @@ void orc_lj_f64(const orc_grid_f *g, const float *sortPos4, const int *index, co
 void orc_dpd_f32(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
                  const int *cellEnd, int N, const float *vel3, float A, float gamma, float sigma, float rcut,
                  uint32_t seed, uint32_t step, int use_double_acc, float *force4, double *force3d);
+void orc_dpd_ids_f32(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
+                     const int *cellEnd, int N, const float *vel3, float A, float gamma, float sigma, float rcut,
+                     uint32_t seed, uint32_t step, int use_double_acc, float *force4, double *force3d,
+                     const int *noiseId, int idStride);
+/* brick domain decomposition (uammd_b200/csrc/domain.cu): owner rank and ghost-destination mask per particle */
+void orc_brick_classify_f(const orc_grid_f *g, const float *pos4, int N, const int rankGrid[3], int *cell, int *owner,
+                          uint32_t *ghostMask);
 /* Saru known-answer helpers */
 void orc_saru3_u32(uint32_t s1, uint32_t s2, uint32_t s3, int n, uint32_t *out);
 void orc_saru3_gf(uint32_t s1, uint32_t s2, uint32_t s3, float mean, float std, float out[2]);

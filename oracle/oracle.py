@@ -168,6 +168,26 @@ def dpd_f32(grid, cl, vel3, A, gamma, sigma, rcut, seed, step, N):
     return force, force64
 
 
+def dpd_ids_f32(grid, cl, vel3, A, gamma, sigma, rcut, seed, step, N, noiseId, idStride):
+    """DPD forces on local arrays with the noise keyed on noiseId[array index] (brick decomposition)."""
+    force = np.zeros((N, 4), np.float32)
+    vel3 = np.ascontiguousarray(vel3, np.float32)
+    noiseId = np.ascontiguousarray(noiseId, np.int32)
+    lib().orc_dpd_ids_f32(C.byref(grid), _p(cl["sortPos"]), _p(cl["index"]), _p(cl["cellStart"]), _p(cl["cellEnd"]),
+                          N, _p(vel3), C.c_float(A), C.c_float(gamma), C.c_float(sigma), C.c_float(rcut),
+                          C.c_uint32(seed), C.c_uint32(step), 0, _p(force), None, _p(noiseId), int(idStride))
+    return force
+
+
+def brick_classify(grid, pos4, rankGrid):
+    pos4 = np.ascontiguousarray(pos4, dtype=np.float32)
+    N = pos4.shape[0]
+    cell, owner, mask = np.zeros(N, np.int32), np.zeros(N, np.int32), np.zeros(N, np.uint32)
+    lib().orc_brick_classify_f(C.byref(grid), _p(pos4), N, (C.c_int * 3)(*[int(p) for p in rankGrid]), _p(cell), _p(owner),
+                               _p(mask))
+    return cell, owner, mask
+
+
 def saru3_u32(s1, s2, s3, n):
     out = np.zeros(n, np.uint32)
     lib().orc_saru3_u32(C.c_uint32(s1), C.c_uint32(s2), C.c_uint32(s3), n, _p(out))

@@ -290,9 +290,22 @@ void orc_lj_f64(const orc_grid_f *g, const float *sortPos4, const int *index, co
 /* ---------- DPD ---------- */
 /* DPD_impl::ForceTransverser::compute Interactor/Potential/DPD.cuh:121-158; getInfo(pi) = {vel[pi], pi}
    with pi the GLOBAL (array) index (:154, common.cuh:17,29-31). ij = i + N*j wraps in int32 like the reference. */
+void orc_dpd_ids_f32(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
+                     const int *cellEnd, int N, const float *vel3, float A, float gamma, float sigma, float rcut,
+                     uint32_t seed, uint32_t step, int use_double_acc, float *force4, double *force3d,
+                     const int *noiseId, int idStride);
 void orc_dpd_f32(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
                  const int *cellEnd, int N, const float *vel3, float A, float gamma, float sigma, float rcut,
                  uint32_t seed, uint32_t step, int use_double_acc, float *force4, double *force3d) {
+  orc_dpd_ids_f32(g, sortPos4, index, cellStart, cellEnd, N, vel3, A, gamma, sigma, rcut, seed, step, use_double_acc,
+                  force4, force3d, 0, N);
+}
+/* same with the Saru key taken from noiseId[array index] and an explicit stride (brick decomposition of
+   uammd_b200/domain.py: local arrays, noise keyed on global ids; new functionality, no reference counterpart) */
+void orc_dpd_ids_f32(const orc_grid_f *g, const float *sortPos4, const int *index, const int *cellStart,
+                     const int *cellEnd, int N, const float *vel3, float A, float gamma, float sigma, float rcut,
+                     uint32_t seed, uint32_t step, int use_double_acc, float *force4, double *force3d,
+                     const int *noiseId, int idStride) {
   const float invrcut = 1.0f / rcut; /* host double 1.0/rcut narrowed to real (DPD.cuh:110) */
 #pragma omp parallel for schedule(dynamic, 256)
   for (int id = 0; id < N; id++) {
@@ -315,9 +328,9 @@ void orc_dpd_f32(const orc_grid_f *g, const float *sortPos4, const int *index, c
           rij[d] = pbc1_f(pi[d] - pj[d], g->L[d], g->minusInvL[d]);
           vij[d] = vel3[3 * (size_t)gi + d] - vel3[3 * (size_t)gj + d];
         }
-        int i = gi, jj = gj;
+        int i = noiseId ? noiseId[gi] : gi, jj = noiseId ? noiseId[gj] : gj;
         if (i > jj) { int t = i; i = jj; jj = t; }
-        const uint32_t ij = (uint32_t)i + (uint32_t)N * (uint32_t)jj; /* int32 wrap == uint32 wrap */
+        const uint32_t ij = (uint32_t)i + (uint32_t)idStride * (uint32_t)jj; /* int32 wrap == uint32 wrap */
         const float r2 = fmaf(rij[2], rij[2], fmaf(rij[1], rij[1], rij[0] * rij[0]));
         const float rmod = sqrtf(r2);
         if (rmod == 0.0f) continue;
@@ -437,5 +450,42 @@ void orc_bd_euler_maruyama_f64(double *pos4, const double *force4, const double 
     pos4[4 * (size_t)i] = out[0];
     pos4[4 * (size_t)i + 1] = out[1];
     if (!is2D) pos4[4 * (size_t)i + 2] = out[2];
+  }
+}
+
+/* ---------- brick domain decomposition (uammd_b200/csrc/domain.cu; new functionality, no reference counterpart) ----------
+   Defined on the reference's neighbour grid: owner = brick holding the particle's cell (Grid::getCell, utils/Grid.cuh:49-71),
+   ghost mask = ranks owning a cell of the 27-neighbourhood (wrap like Grid::pbc_cell, utils/Grid.cuh:81-106). */
+static int brick_of_cell(int c, int n, int p) {
+  int k = 0; /* largest k with floor(k n / p) <= c */
+  while (k + 1 < p && ((k + 1) * n) / p <= c) k++;
+  return k;
+}
+void orc_brick_classify_f(const orc_grid_f *g, const float *pos4, int N, const int rankGrid[3], int *cell, int *owner,
+                          uint32_t *ghostMask) {
+  const int *n = g->cellDim;
+  for (int i = 0; i < N; i++) {
+    int c[3];
+    orc_get_cell_f(g, pos4 + 4 * (size_t)i, c);
+    for (int d = 0; d < 3; d++) c[d] = c[d] < 0 ? 0 : (c[d] >= n[d] ? n[d] - 1 : c[d]);
+    const int own = brick_of_cell(c[0], n[0], rankGrid[0]) +
+                    rankGrid[0] * (brick_of_cell(c[1], n[1], rankGrid[1]) + rankGrid[1] * brick_of_cell(c[2], n[2], rankGrid[2]));
+    uint32_t mask = 0;
+    for (int o = 0; o < 27; o++) {
+      int j[3] = {c[0] + o % 3 - 1, c[1] + (o / 3) % 3 - 1, c[2] + o / 9 - 1};
+      int skip = 0;
+      for (int d = 0; d < 3; d++) {
+        const int periodic = g->minusInvL[d] != 0.0f;
+        if (j[d] < 0) { if (periodic) j[d] += n[d]; else skip = 1; }
+        else if (j[d] >= n[d]) { if (periodic) j[d] -= n[d]; else skip = 1; }
+      }
+      if (skip) continue;
+      const int r = brick_of_cell(j[0], n[0], rankGrid[0]) +
+                    rankGrid[0] * (brick_of_cell(j[1], n[1], rankGrid[1]) + rankGrid[1] * brick_of_cell(j[2], n[2], rankGrid[2]));
+      mask |= 1u << r;
+    }
+    if (cell) cell[i] = c[0] + n[0] * (c[1] + n[1] * c[2]);
+    owner[i] = own;
+    ghostMask[i] = mask & ~(1u << own);
   }
 }

@@ -1,5 +1,6 @@
-"""CPU: the multi-GPU particle decomposition (uammd_b200/multigpu.py) exercised with world_size 2 over gloo, the CPU
-oracle standing in for the CUDA engine: two ranks must reproduce the single-process trajectory bit for bit."""
+"""CPU: the multi-GPU particle decomposition (uammd_b200/multigpu.py) exercised with world_size 2 over gloo, with the
+checker engines of tests/_checker_engines.py (oracle arithmetic) injected in place of the CUDA engine: two ranks must
+reproduce the single-process trajectory bit for bit."""
 import os
 import sys
 
@@ -9,6 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [p for p in (ROOT, os.path.join(ROOT, "tests")) if p not in sys.path]  # also in the spawned workers
 
 
 def _worker(rank, world, port, N, steps, out):
@@ -22,7 +24,8 @@ def _worker(rank, world, port, N, steps, out):
     pos = torch.from_numpy(syn.fcc_lattice(N, Lb))
     vel = torch.from_numpy(syn.maxwell_velocities(N, 1.0))
     pot = LJ(); pot.setPotParameters(0, 0, cutOff=2.5)
-    md = DistributedLJMD(Box(Lb), pot, 0.004, N, engine="oracle")
+    from _checker_engines import OracleLJEngine
+    md = DistributedLJMD(Box(Lb), pot, 0.004, N, engine=OracleLJEngine(Box(Lb), pot, 0.004))
     force = torch.zeros(N, 4)
     vb = vel[md.dec.lo:md.dec.hi].clone()
     md.run(pos, vb, force, steps)
@@ -105,7 +108,8 @@ def _dpd_worker(rank, world, port, N, steps, out):
     from uammd_b200.multigpu import DistributedDPDMD
     box, pot, pos, vel = _dpd_setup(N)
     p, v, f = torch.from_numpy(pos), torch.from_numpy(vel), torch.zeros(N, 4)
-    md = DistributedDPDMD(box, pot, 0.01, N, engine="oracle")
+    from _checker_engines import OracleDPDEngine
+    md = DistributedDPDMD(box, pot, 0.01, N, engine=OracleDPDEngine(box, pot, 0.01, N))
     for _ in range(steps):
         md.forwardTime(p, v, f)
     md.gatherState(p, v)
@@ -125,7 +129,8 @@ def test_dpd_two_ranks_reproduce_single_process(tmp_path, orc):
     got = np.load(out)
     box, pot, pos, vel = _dpd_setup(N)
     p, v, f = torch.from_numpy(pos.copy()), torch.from_numpy(vel.copy()), torch.zeros(N, 4)
-    md = DistributedDPDMD(box, pot, 0.01, N, engine="oracle")
+    from _checker_engines import OracleDPDEngine
+    md = DistributedDPDMD(box, pot, 0.01, N, engine=OracleDPDEngine(box, pot, 0.01, N))
     for _ in range(steps):
         md.forwardTime(p, v, f)
     assert np.array_equal(got[:4 * N].view(np.uint32), p.numpy().ravel().view(np.uint32))

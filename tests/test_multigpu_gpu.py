@@ -25,7 +25,7 @@ def _worker(rank, world, port, N, steps, out):
     pos = torch.from_numpy(syn.fcc_lattice(N, Lb)).to(dev)
     vel = syn.maxwell_velocities(N, 1.0)
     pot = LJ(); pot.setPotParameters(0, 0, cutOff=2.5)
-    md = DistributedLJMD(Box(Lb), pot, 0.005, N, engine="cuda")
+    md = DistributedLJMD(Box(Lb), pot, 0.005, N)
     vb = torch.from_numpy(vel[md.dec.lo:md.dec.hi].copy()).to(dev)
     force = torch.zeros(N, 4, device=dev)
     md.run(pos, vb, force, steps)

@@ -48,9 +48,12 @@ template <bool PAIRMIC>
 __global__ void __launch_bounds__(kPairThreads)
 dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
                  const uint32_t *__restrict__ binStart, GridF g, int ncells, const float *__restrict__ vel, DPDPar par,
-                 float4 *__restrict__ force, const int *__restrict__ globalIdx, int ownerLo, int ownerHi, int accumulate) {
+                 float4 *__restrict__ force, const int *__restrict__ globalIdx, int ownerLo, int ownerHi, int accumulate,
+                 const int *__restrict__ noiseId) {
   // ownerLo/ownerHi: only home particles whose (global) index lies in [ownerLo, ownerHi) are computed and written
   // (multi-GPU particle decomposition, like ub200_lj_sum_owned_f32)
+  // noiseId: optional id of every particle used ONLY in the Saru key of a pair (brick decomposition: the local
+  // arrays hold owned + ghost particles, the noise stays keyed on the global particle ids)
   __shared__ float4 cand[kDpdCap];
   __shared__ float4 candVel[kDpdCap]; // vx, vy, vz, id (bits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,25 +79,26 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
           const int id = globalIdx ? globalIdx[gi] : gi;
           cand[off + t] = p;
           candVel[off + t] = make_float4(__ldg(vel + 3 * (size_t)id), __ldg(vel + 3 * (size_t)id + 1),
-                                         __ldg(vel + 3 * (size_t)id + 2), __int_as_float(id));
+                                         __ldg(vel + 3 * (size_t)id + 2), __int_as_float(noiseId ? __ldg(noiseId + id) : id));
         }
       }
     }
     __syncthreads();
     for (int h = warp; h < hCount; h += kPairWarps) {
       float4 pi, vi;
+      const int gih = groupIndex[hStart + h];
+      const int idi = globalIdx ? globalIdx[gih] : gih; // array index of the home particle (velocity, force, ownership)
+      if (idi < ownerLo || idi >= ownerHi) continue; // warp uniform
       if (staged) {
         pi = cand[hOff + h];
         vi = candVel[hOff + h];
       } else {
         pi = ldg4(sortPos + hStart + h);
         if (!PAIRMIC) toHomeImage(pi, g, hc);
-        const int gi = groupIndex[hStart + h];
-        const int id = globalIdx ? globalIdx[gi] : gi;
-        vi = make_float4(vel[3 * (size_t)id], vel[3 * (size_t)id + 1], vel[3 * (size_t)id + 2], __int_as_float(id));
+        vi = make_float4(vel[3 * (size_t)idi], vel[3 * (size_t)idi + 1], vel[3 * (size_t)idi + 2],
+                         __int_as_float(noiseId ? noiseId[idi] : idi));
       }
-      const int idi = __float_as_int(vi.w);
-      if (idi < ownerLo || idi >= ownerHi) continue; // warp uniform
+      const int nidi = __float_as_int(vi.w); // id of the home particle in the Saru key
       float fx = 0.f, fy = 0.f, fz = 0.f;
       if (staged) {
         for (int t = lane; t < nc.total; t += 32) {
@@ -106,7 +110,7 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
             ry = foldCoord(ry, g.Ly, g.my);
             rz = foldCoord(rz, g.Lz, g.mz);
           }
-          dpdPair(rx, ry, rz, vi.x - vj.x, vi.y - vj.y, vi.z - vj.z, idi, __float_as_int(vj.w), par, fx, fy, fz);
+          dpdPair(rx, ry, rz, vi.x - vj.x, vi.y - vj.y, vi.z - vj.z, nidi, __float_as_int(vj.w), par, fx, fy, fz);
         }
       } else {
         for (int c = 0; c < 27; c++) {
@@ -129,7 +133,7 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
               rz = pi.z - pj.z;
             }
             dpdPair(rx, ry, rz, vi.x - vel[3 * (size_t)idj], vi.y - vel[3 * (size_t)idj + 1],
-                    vi.z - vel[3 * (size_t)idj + 2], idi, idj, par, fx, fy, fz);
+                    vi.z - vel[3 * (size_t)idj + 2], nidi, noiseId ? noiseId[idj] : idj, par, fx, fy, fz);
           }
         }
       }
@@ -153,7 +157,7 @@ using namespace ub200;
 
 static int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut, uint32_t seed,
                   uint32_t step, int idStride, void *d_force, const int *d_globalIdx, int ownerLo, int ownerHi, int accumulate,
-                  void *stream) {
+                  void *stream, const int *d_noiseId = nullptr) {
   if (!cl || !d_vel || !d_force || !(rcut > 0)) return UB200_ERR_INVALID_ARGUMENT;
   if (!cl->built) return UB200_ERR_NOT_BUILT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -178,11 +182,13 @@ static int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, f
   if (pairMic)
     dpdCellTraversal<true><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
                                                           cl->binStart.as<uint32_t>(), g, cl->ncells,
-                                                          (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate);
+                                                          (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate,
+                                                          d_noiseId);
   else
     dpdCellTraversal<false><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
                                                            cl->binStart.as<uint32_t>(), g, cl->ncells,
-                                                           (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate);
+                                                           (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate,
+                                                          d_noiseId);
   UB200_LAUNCHED();
   return UB200_OK;
 }
@@ -197,4 +203,11 @@ extern "C" int ub200_dpd_sum_owned_f32(ub200_celllist *cl, const void *d_vel, fl
                                        int accumulate, void *stream) {
   if (ownerLo < 0 || ownerHi < ownerLo) return UB200_ERR_INVALID_ARGUMENT;
   return dpdSum(cl, d_vel, A, gamma, sigma, rcut, seed, step, idStride, d_force, nullptr, ownerLo, ownerHi, accumulate, stream);
+}
+extern "C" int ub200_dpd_sum_owned_ids_f32(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut,
+                                           uint32_t seed, uint32_t step, int idStride, void *d_force, int ownerLo, int ownerHi,
+                                           int accumulate, const int *d_noiseId, void *stream) {
+  if (ownerLo < 0 || ownerHi < ownerLo || !d_noiseId) return UB200_ERR_INVALID_ARGUMENT;
+  return dpdSum(cl, d_vel, A, gamma, sigma, rcut, seed, step, idStride, d_force, nullptr, ownerLo, ownerHi, accumulate, stream,
+                d_noiseId);
 }

@@ -266,6 +266,57 @@ ljVerletTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gr
   if (VIRIAL) virial[ori] += a.v;
 }
 
+// All-pairs fallback of PairForces for boxes no larger than 3 cut-offs in every dimension (PairForces.cu:49-53 ->
+// NBody::transverse, Interactor/NBodyBase.cuh:46-116): one thread per particle, the particles visited tile by tile
+// through shared memory in ascending group order and accumulated sequentially like the reference kernel, per-pair
+// minimum image like Radial::Transverser::compute (RadialPotential.cuh:107-127). Such boxes hold a few hundred
+// particles at most, so this kernel is never on the hot path.
+constexpr int kNBodyThreads = 128;
+template <bool ENERGY, bool VIRIAL, bool MULTITYPE>
+__global__ void __launch_bounds__(kNBodyThreads)
+ljNBody(const float4 *__restrict__ pos, const int *__restrict__ globalIdx, int N, GridF g,
+        const LJPar *__restrict__ parTable, int ntypes, float4 *__restrict__ force, float *__restrict__ energy,
+        float *__restrict__ virial) {
+  __shared__ float4 tile[kNBodyThreads];
+  const int tid = blockIdx.x * kNBodyThreads + threadIdx.x;
+  const bool active = tid < N;
+  const int ori = active ? (globalIdx ? globalIdx[tid] : tid) : 0;
+  const float4 pi = active ? ldg4(pos + ori) : make_float4(0.f, 0.f, 0.f, 0.f);
+  LJPar par = parTable[0];
+  uint32_t rcb = __float_as_uint(par.cutOff2) - 1u;
+  const int ti = (int)pi.w;
+  const int trow = MULTITYPE && (unsigned)ti < (unsigned)ntypes ? ti * ntypes : -1;
+  Acc a = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t0 = 0; t0 < N; t0 += kNBodyThreads) {
+    const int jl = t0 + threadIdx.x;
+    if (jl < N) tile[threadIdx.x] = ldg4(pos + (globalIdx ? globalIdx[jl] : jl));
+    __syncthreads();
+    const int cnt = min(kNBodyThreads, N - t0);
+    if (active) {
+      for (int c = 0; c < cnt; c++) {
+        const float4 pj = tile[c];
+        const float dx = foldCoord(pj.x - pi.x, g.Lx, g.mx), dy = foldCoord(pj.y - pi.y, g.Ly, g.my),
+                    dz = foldCoord(pj.z - pi.z, g.Lz, g.mz);
+        if (MULTITYPE) {
+          const int tj = (int)pj.w;
+          par = parTable[((unsigned)tj < (unsigned)ntypes && trow >= 0) ? trow + tj : 0];
+          rcb = __float_as_uint(par.cutOff2) - 1u;
+        }
+        ljPair<ENERGY, VIRIAL>(dx, dy, dz, par, rcb, a);
+      }
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+  if (force) {
+    float4 f = force[ori];
+    f.x += a.fx; f.y += a.fy; f.z += a.fz;
+    force[ori] = f;
+  }
+  if (ENERGY) energy[ori] += a.e;
+  if (VIRIAL) virial[ori] += a.v;
+}
+
 template <bool E, bool V, bool M, bool P, bool A>
 static int launchLJ(ub200_celllist *cl, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
                     const int *globalIdx, cudaStream_t st, int ownerLo, int ownerHi) {
@@ -322,9 +373,7 @@ int ljSumDev(ub200_celllist *cl, const LJPar *d_table, int ntypes, float4 *force
 }
 
 // host parameter table: uploaded into `cache` only when it changed since the last call
-int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
-          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st, int ownerLo, int ownerHi) {
-  if (!params || ntypes < 1 || !cache) return UB200_ERR_INVALID_ARGUMENT;
+static int uploadLJTable(LJTableCache *cache, const float *params, int ntypes, cudaStream_t st) {
   const size_t n = (size_t)ntypes * ntypes * 4;
   if (cache->host.size() != n || memcmp(cache->host.data(), params, n * sizeof(float)) != 0) {
     int rc = cache->dev.reserve(n * sizeof(float));
@@ -332,6 +381,13 @@ int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, fl
     cache->host.assign(params, params + n);
     UB200_CUDA(cudaMemcpyAsync(cache->dev.p, cache->host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
   }
+  return UB200_OK;
+}
+int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
+          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st, int ownerLo, int ownerHi) {
+  if (!params || ntypes < 1 || !cache) return UB200_ERR_INVALID_ARGUMENT;
+  const int rc = uploadLJTable(cache, params, ntypes, st);
+  if (rc) return rc;
   return ljSumDev(cl, cache->dev.as<LJPar>(), ntypes, force, energy, virial, globalIdx, accumulate, st, ownerLo, ownerHi);
 }
 
@@ -354,13 +410,7 @@ extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params
   if (!d_force && !d_energy && !d_virial) return UB200_OK;
   cudaStream_t st = (cudaStream_t)stream;
   LJTableCache *cache = &g_ljTable;
-  const size_t n = (size_t)ntypes * ntypes * 4;
-  if (cache->host.size() != n || memcmp(cache->host.data(), params, n * sizeof(float)) != 0) {
-    int rc = cache->dev.reserve(n * sizeof(float));
-    if (rc) return rc;
-    cache->host.assign(params, params + n);
-    UB200_CUDA(cudaMemcpyAsync(cache->dev.p, cache->host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-  }
+  if (const int rc = uploadLJTable(cache, params, ntypes, st)) return rc;
   const int cd1[3] = {1, 1, 1};
   const GridF g = makeGridF(vl->L, vl->periodic, cd1);
   const int N = vl->N, nb = (N + 127) / 128;
@@ -391,4 +441,29 @@ extern "C" int ub200_lj_sum_devparams_f32(ub200_celllist *cl, const void *d_para
                                           float *d_energy, float *d_virial, const int *d_globalIdx, void *stream) {
   return ljSumDev(cl, (const LJPar *)d_params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true,
                   (cudaStream_t)stream);
+}
+
+extern "C" int ub200_lj_nbody_f32(const void *d_pos, const int *d_globalIdx, int N, const float L[3], const int periodic[3],
+                                  const float *params, int ntypes, void *d_force, float *d_energy, float *d_virial,
+                                  void *stream) {
+  if (!d_pos || !L || !periodic || !params || ntypes < 1 || N < 0) return UB200_ERR_INVALID_ARGUMENT;
+  if (N == 0 || (!d_force && !d_energy && !d_virial)) return UB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LJTableCache *cache = &g_ljTable;
+  if (const int rc = uploadLJTable(cache, params, ntypes, st)) return rc;
+  const int cd1[3] = {1, 1, 1};
+  const GridF g = makeGridF(L, periodic, cd1);
+  const int nb = (N + kNBodyThreads - 1) / kNBodyThreads;
+  const bool E = d_energy != nullptr, V = d_virial != nullptr, M = ntypes > 1;
+#define UB200_LJN(e, v, m)                                                                                          \
+  if (E == e && V == v && M == m) {                                                                                 \
+    ljNBody<e, v, m><<<nb, kNBodyThreads, 0, st>>>((const float4 *)d_pos, d_globalIdx, N, g, cache->dev.as<LJPar>(), \
+                                                   ntypes, (float4 *)d_force, d_energy, d_virial);                   \
+    UB200_LAUNCHED();                                                                                               \
+    return UB200_OK;                                                                                                \
+  }
+  UB200_LJN(false, false, false) UB200_LJN(false, false, true) UB200_LJN(true, false, false) UB200_LJN(true, false, true)
+  UB200_LJN(false, true, false) UB200_LJN(false, true, true) UB200_LJN(true, true, false) UB200_LJN(true, true, true)
+#undef UB200_LJN
+  return UB200_ERR_UNSUPPORTED;
 }

@@ -8,8 +8,9 @@ same global input. Scheme ("replicated positions, block-owned particles"):
     (ub200_lj_sum_owned_f32 skips cells without owned home particles);
   * each particle's force is computed by exactly one rank with the same kernel, list and summation order as on one
     GPU, so the trajectory is bit-identical to the single-GPU trajectory.
-The host logic is backend agnostic: `engine="cuda"` drives the C ABI, `engine="oracle"` (tests only) drives the CPU
-oracle so that the decomposition is covered by world_size-2 gloo tests on CPU.
+The host logic is written against a small engine interface (half / kick_kick_drift / forces_owned); the product engine
+below drives the C ABI and raises when the CUDA library is missing. The world_size-2 gloo tests on CPU inject their own
+checker engine from tests/ - nothing in this package computes on the CPU.
 """
 import ctypes as C
 
@@ -55,39 +56,16 @@ class _CudaEngine:
                                                    self._stream()))
 
 
-class _OracleEngine:
-    """CPU stand-in used by the gloo tests (tests/ only): same call sequence, oracle arithmetic."""
-
-    def __init__(self, box, pot, dt):
-        from oracle import oracle as orc
-        self.orc, self.box, self.pot, self.dt = orc, box, pot, float(dt)
-
-    def half(self, step, pos_blk, vel_blk, force_blk):
-        p, v, f = pos_blk.numpy(), vel_blk.numpy(), force_blk.numpy()
-        self.orc.nve_half(p, v, f, self.dt, 1.0, step)
-
-    def kick_kick_drift(self, pos_blk, vel_blk, force_blk):
-        self.half(2, pos_blk, vel_blk, force_blk)
-        self.half(1, pos_blk, vel_blk, force_blk)
-
-    def forces_owned(self, pos, force, lo, hi):
-        L = self.box.boxSize
-        g = self.orc.make_grid_f(L, self.orc.neighbour_celldim(L, self.pot.getCutOff()))
-        cl = self.orc.celllist_build(g, pos.numpy())
-        f, _, _ = self.orc.lj_f32(g, cl, self.pot.table(), self.pot.ntypes, pos.shape[0])
-        force.numpy()[lo:hi] = f[lo:hi]
-
-
 class DistributedLJMD:
     """VerletNVE + PairForces<LJ, CellList> over `world` ranks. pos/force are full-size [N,4] tensors replicated on
     every rank (only the owned block of force is meaningful), vel is the rank's own [N/world,3] block."""
 
-    def __init__(self, box, pot, dt, N, engine="cuda", group=None):
+    def __init__(self, box, pot, dt, N, engine=None, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dec = BlockDecomposition(N, self.world, self.rank)
-        self.eng = _CudaEngine(box, pot, dt) if engine == "cuda" else _OracleEngine(box, pot, dt)
+        self.eng = engine if engine is not None else _CudaEngine(box, pot, dt)
         self.prepared = False
 
     def _gather(self, pos):
@@ -115,26 +93,39 @@ class DistributedLJMD:
                 self.eng.kick_kick_drift(pb, vel_blk, fb)
 
 
+class _CudaDPDEngine:
+    def __init__(self, box, pot, dt, N):
+        from . import _lib
+        from .md import CellList, _ptr, _stream_ptr
+        self.lib, self.check, self._ptr, self._stream = _lib.lib(), _lib.check, _ptr, _stream_ptr
+        self.box, self.pot, self.dt, self.N = box, pot, float(dt), N
+        self.nl = CellList()
+
+    def forces_owned(self, pos, vel, force, lo, hi):
+        p = self.pot
+        self.nl.update(pos, self.box, p.getCutOff())
+        self.check(self.lib.ub200_dpd_sum_owned_f32(self.nl._h, self._ptr(vel), p.A, p.gamma, p.sigma, p.rcut, p.seed,
+                                                    p.step & 0xFFFFFFFF, self.N, self._ptr(force), lo, hi, 0, self._stream()))
+
+    def half(self, step, pb, vb, fb):
+        self.check(self.lib.ub200_nve_half_step_f32(self._ptr(pb), self._ptr(vb), self._ptr(fb), C.c_void_p(0), 1.0,
+                                                    C.c_void_p(0), pb.shape[0], self.dt, 0, step, self._stream()))
+
+
 class DistributedDPDMD:
     """VerletNVE + PairForces<DPD> over `world` ranks by the same particle decomposition (BASELINE config 4 shape): the
     DPD force depends on the velocities, so positions AND velocities are all-gathered every step (28 B per particle);
     the pairwise noise is keyed on global particle indices, hence independent of the number of ranks. pos [N,4] and vel
-    [N,3] are full-size tensors replicated on every rank; force [N,4] is meaningful on the owned block."""
+    [N,3] are full-size tensors replicated on every rank; force [N,4] is meaningful on the owned block.
+    (uammd_b200/domain.py holds the brick decomposition with a ghost-cell halo exchange instead of the all-gather.)"""
 
-    def __init__(self, box, pot, dt, N, engine="cuda", group=None):
+    def __init__(self, box, pot, dt, N, engine=None, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dec = BlockDecomposition(N, self.world, self.rank)
-        self.box, self.pot, self.dt, self.N, self.engine = box, pot, float(dt), N, engine
-        if engine == "cuda":
-            from . import _lib
-            from .md import CellList, _ptr, _stream_ptr
-            self.lib, self.check, self._ptr, self._stream = _lib.lib(), _lib.check, _ptr, _stream_ptr
-            self.nl = CellList()
-        else:
-            from oracle import oracle as orc
-            self.orc = orc
+        self.box, self.pot, self.dt, self.N = box, pot, float(dt), N
+        self.eng = engine if engine is not None else _CudaDPDEngine(box, pot, dt, N)
         self.steps = 0
 
     def _gather(self, t):
@@ -143,27 +134,12 @@ class DistributedDPDMD:
             dist.all_gather_into_tensor(t, t[lo:hi].clone() if t.device.type == "cpu" else t[lo:hi], group=self.group)
 
     def _forces(self, pos, vel, force):
-        lo, hi, p = self.dec.lo, self.dec.hi, self.pot
-        p.step += 1  # DPD_impl::getForceTransverser increments the step before every evaluation (DPD.cuh:161-170)
-        if self.engine == "cuda":
-            self.nl.update(pos, self.box, p.getCutOff())
-            self.check(self.lib.ub200_dpd_sum_owned_f32(self.nl._h, self._ptr(vel), p.A, p.gamma, p.sigma, p.rcut, p.seed,
-                                                        p.step & 0xFFFFFFFF, self.N, self._ptr(force), lo, hi, 0, self._stream()))
-        else:
-            L = self.box.boxSize
-            g = self.orc.make_grid_f(L, self.orc.neighbour_celldim(L, p.getCutOff()))
-            cl = self.orc.celllist_build(g, pos.numpy())
-            f32, _ = self.orc.dpd_f32(g, cl, vel.numpy(), p.A, p.gamma, p.sigma, p.rcut, p.seed, p.step & 0xFFFFFFFF, self.N)
-            force.numpy()[lo:hi] = f32[lo:hi]
+        self.pot.step += 1  # DPD_impl::getForceTransverser increments the step before every evaluation (DPD.cuh:161-170)
+        self.eng.forces_owned(pos, vel, force, self.dec.lo, self.dec.hi)
 
     def _half(self, step, pos, vel, force):
         lo, hi = self.dec.lo, self.dec.hi
-        pb, vb, fb = pos[lo:hi], vel[lo:hi], force[lo:hi]
-        if self.engine == "cuda":
-            self.check(self.lib.ub200_nve_half_step_f32(self._ptr(pb), self._ptr(vb), self._ptr(fb), C.c_void_p(0), 1.0,
-                                                        C.c_void_p(0), pb.shape[0], self.dt, 0, step, self._stream()))
-        else:
-            self.orc.nve_half(pb.numpy(), vb.numpy(), fb.numpy(), self.dt, 1.0, step)
+        self.eng.half(step, pos[lo:hi], vel[lo:hi], force[lo:hi])
 
     def forwardTime(self, pos, vel, force):
         """VerletNVE::forwardTime (VerletNVE.cu:174-188) with the DPD interactor."""
