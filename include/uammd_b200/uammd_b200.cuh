@@ -268,15 +268,29 @@ public:
   /* Interactor::sum: accumulates into pd's force / energy / virial like Radial::Transverser::set */
   void sum(Computables comp, cudaStream_t st = 0) override {
     const real rcut = pot->getCutOff();
-    if (box.boxSize.x <= 3 * rcut and box.boxSize.y <= 3 * rcut and box.boxSize.z <= 3 * rcut)
-      throw std::runtime_error("[uammd_b200] box <= 3 rcut in every dimension needs the NBody path (PairForces.cu:49-53)");
-    if (vl) vl->update(box, rcut, st);
-    else nl->update(box, rcut, st);
+    // PairForces.cu:49-53: a box no larger than 3 cut-offs in every dimension takes the all-pairs NBody path
+    const bool nbody = box.boxSize.x <= 3 * rcut and box.boxSize.y <= 3 * rcut and box.boxSize.z <= 3 * rcut;
+    if (!nbody) {
+      if (vl) vl->update(box, rcut, st);
+      else nl->update(box, rcut, st);
+    }
     auto force = comp.force ? pd->getForce(access::location::gpu, access::mode::readwrite).raw() : nullptr;
     auto energy = comp.energy ? pd->getEnergy(access::location::gpu, access::mode::readwrite).raw() : nullptr;
     auto virial = comp.virial ? pd->getVirial(access::location::gpu, access::mode::readwrite).raw() : nullptr;
     const auto table = pot->getDeviceTable();
     const int *gidx = pg->getIndicesRawPtr(access::location::gpu);
+    if (nbody) {
+      std::vector<float> host((size_t)table.ntypes * table.ntypes * 4);
+      CudaSafeCall(cudaMemcpyAsync(host.data(), table.d_params, host.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CudaSafeCall(cudaStreamSynchronize(st));
+      auto pos = pd->getPos(access::location::gpu, access::mode::read);
+      const float L[3] = {(float)box.boxSize.x, (float)box.boxSize.y, (float)box.boxSize.z};
+      const int periodic[3] = {box.isPeriodicX(), box.isPeriodicY(), box.isPeriodicZ()};
+      check(ub200_lj_nbody_f32(pos.raw(), gidx, pg->getNumberParticles(), L, periodic, host.data(), table.ntypes, force, energy,
+                               virial, (void *)st),
+            "lj_nbody");
+      return;
+    }
     if (vl) {
       // the Verlet entry point takes the host copy of the table (tiny; cached on the device by the library)
       std::vector<float> host((size_t)table.ntypes * table.ntypes * 4);

@@ -51,6 +51,15 @@ def test_invalid_arguments_are_reported_not_crashed():
     assert lib.ub200_neighbour_celldim_f32(f3((1, 1, 1)), 0.0, i3((0, 0, 0))) == -1
     with pytest.raises(uammd_b200.UB200Error):
         uammd_b200._lib.check(-4)
+    # brick decomposition: a brick without a cell, more ranks than mask bits, missing outputs; empty input is fine
+    L, per = f3((10, 10, 10)), i3((1, 1, 1))
+    assert lib.ub200_brick_classify_f32(None, 0, L, per, i3((4, 4, 4)), i3((5, 1, 1)), None, None, None, None) == -1
+    assert lib.ub200_brick_classify_f32(None, 0, L, per, i3((4, 4, 4)), i3((4, 4, 4)), None, None, None, None) == -6
+    assert lib.ub200_brick_classify_f32(None, 8, L, per, i3((4, 4, 4)), i3((2, 2, 2)), None, None, None, None) == -1
+    assert lib.ub200_brick_classify_f32(None, 0, L, per, i3((4, 4, 4)), i3((2, 2, 2)), None, None, None, None) == 0
+    assert lib.ub200_lj_nbody_f32(None, None, 8, L, per, None, 1, None, None, None, None) == -1
+    assert lib.ub200_dpd_sum_owned_ids_f32(None, None, C.c_float(1), C.c_float(1), C.c_float(1), C.c_float(1), 0, 0, 8, None, 0,
+                                           8, 0, None, None) == -1
 
 
 def test_lj_parameter_table_matches_reference_rule():

@@ -28,6 +28,14 @@ def test_pairforces_dropin_matches_reference():
     assert r["nve20_max_dpos"] < 1e-4                    # 20 VerletNVE steps next to the reference
 
 
+def test_nbody_fallback_dropin_matches_reference():
+    """Box <= 3 cut-offs: the reference's PairForces takes NBody::transverse (PairForces.cu:49-53); ours ub200_lj_nbody_f32."""
+    r = _run("dropin_nbody", 300, 7.0)
+    print(r)
+    assert r["nbody"] == 1
+    assert r["force_vs_ref"] < 1e-5 and r["energy_vs_ref"] < 1e-5 and r["virial_vs_ref"] < 1e-5
+
+
 def test_fcm_dropin_matches_reference():
     r = _run("dropin_fcm", 20000, 64)
     print(r)

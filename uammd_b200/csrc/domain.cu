@@ -73,8 +73,6 @@ extern "C" int ub200_brick_classify_f32(const void *d_pos, int N, const float L[
                                         const int cellDim[3], const int rankGrid[3], int *d_cell, int *d_owner,
                                         uint32_t *d_ghostMask, void *stream) {
   if (!L || !periodic || !cellDim || !rankGrid || N < 0) return UB200_ERR_INVALID_ARGUMENT;
-  if (N == 0) return UB200_OK;
-  if (!d_pos || !d_owner || !d_ghostMask) return UB200_ERR_INVALID_ARGUMENT;
   long world = 1;
   for (int d = 0; d < 3; d++) {
     // every brick needs at least one cell; the ghost mask has one bit per rank
@@ -82,6 +80,8 @@ extern "C" int ub200_brick_classify_f32(const void *d_pos, int N, const float L[
     world *= rankGrid[d];
   }
   if (world > 32) return UB200_ERR_UNSUPPORTED;
+  if (N == 0) return UB200_OK;
+  if (!d_pos || !d_owner || !d_ghostMask) return UB200_ERR_INVALID_ARGUMENT;
   const GridF g = makeGridF(L, periodic, cellDim);
   const BrickGrid b = {rankGrid[0], rankGrid[1], rankGrid[2]};
   brickClassify<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4 *)d_pos, N, g, b, d_cell, d_owner, d_ghostMask);

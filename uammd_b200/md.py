@@ -264,10 +264,25 @@ class PairForces:
         rcut = self.pot.getCutOff()
         L = self.box.boxSize
         if all(l <= 3 * rcut for l in L):
-            # PairForces.cu:49-53 switches to NBody here; that O(N^2) fallback is out of scope
-            raise UB200Error("PairForces: box <= 3*rcut in every dimension needs the NBody fallback (out of scope)")
+            # PairForces.cu:49-53,61-66: no neighbour list for such a box, NBody::transverse over all pairs
+            self.sumNBody(pos, force, energy, virial, stream, globalIndex)
+            return
         self.nl.update(pos, self.box, rcut, stream)
         self.sumWithCurrentList(force, energy, virial, stream, globalIndex)
+
+    def sumNBody(self, pos, force=None, energy=None, virial=None, stream=None, globalIndex=None):
+        """NBody::transverse (Interactor/NBodyBase.cuh:46-116) with the LJ transverser: all pairs, minimum image."""
+        lib = _lib.lib()
+        lib.ub200_lj_nbody_f32.restype = C.c_int
+        lib.ub200_lj_nbody_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float * 3, C.c_int * 3, C.POINTER(C.c_float),
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        if pos.dtype != torch.float32 or pos.dim() != 2 or pos.shape[1] != 4 or not pos.is_cuda or not pos.is_contiguous():
+            raise UB200Error("PairForces.sumNBody: pos must be a contiguous CUDA float32 [N,4] tensor (real4)")
+        tab = self.pot.table()
+        N = pos.shape[0] if globalIndex is None else globalIndex.shape[0]
+        check(lib.ub200_lj_nbody_f32(_ptr(pos), _ptr(globalIndex), N, f3(self.box.boxSize),
+                                     i3([int(p) for p in self.box.periodic]), tab.ctypes.data_as(C.POINTER(C.c_float)),
+                                     self.pot.ntypes, _ptr(force), _ptr(energy), _ptr(virial), _stream_ptr(stream)))
 
     def sumWithCurrentList(self, force=None, energy=None, virial=None, stream=None, globalIndex=None):
         tab = self.pot.table()
