@@ -141,10 +141,10 @@ def run_reference(args):
         "wall_s": wall,
     }
     if not args.no_fcm:
-        from uammd_b200 import fcm_bench
+        import bench_fcm as fcm_bench
         line["fcm"] = fcm_bench.run_reference(ROOT, steps=args.fcm_steps)
     if not args.no_extra:
-        from uammd_b200 import extra_bench
+        import bench_extra as extra_bench
         for name, fn in (("verlet", lambda: extra_bench.verlet_reference(ROOT, N, Lb, pos, vel, RC, DT, equil=args.equil)),
                          ("pse", lambda: extra_bench.pse_reference(ROOT)), ("bd", lambda: extra_bench.bd_reference(ROOT))):
             try:
@@ -326,12 +326,12 @@ def main():
             line["cpu_baseline"] = cpu_baseline(N)
         if not args.no_fcm and world == 1:
             try:
-                from uammd_b200 import fcm_bench
+                import bench_fcm as fcm_bench
                 line["fcm"] = fcm_bench.run(dev, peak, steps=args.fcm_steps)
             except ImportError:
                 pass
         if not args.no_extra and world == 1:
-            from uammd_b200 import extra_bench
+            import bench_extra as extra_bench
             for name, fn in (("verlet", lambda: extra_bench.verlet(dev, N, Lb, pos, vel, RC, DT, equil=args.equil)),
                              ("pse", lambda: extra_bench.pse(dev)), ("bd", lambda: extra_bench.bd_ideal(dev))):
                 try:
@@ -420,7 +420,7 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
         line_out = line
     fcm_line = None
     if not args.no_fcm:
-        from uammd_b200 import fcm_bench
+        import bench_fcm as fcm_bench
         peak, _ = measured_peaks()
         fcm_line = fcm_bench.run_distributed(dev, peak, steps=args.fcm_steps)
     if rank == 0:

@@ -32,8 +32,8 @@ def _timed(dev, step, steps, warmup):
 
 
 def verlet(dev, N, Lb, pos, vel, rc, dt, steps=100, warmup=20, equil=300):
-    from .md import Box, LJ, LJMD, VerletList
-    from . import lib
+    from uammd_b200.md import Box, LJ, LJMD, VerletList
+    from uammd_b200 import lib
     pot = LJ(); pot.setPotParameters(0, 0, cutOff=rc)
     p, v = torch.from_numpy(pos).to(dev), torch.from_numpy(vel).to(dev)
     f = torch.zeros(N, 4, device=dev)
@@ -64,15 +64,15 @@ def verlet_reference(root, N, Lb, pos, vel, rc, dt, steps=100, warmup=20, equil=
 
 
 def _pse_inputs():
-    from . import synthetic as syn
+    from uammd_b200 import synthetic as syn
     pos = np.zeros((PSE_N, 4), np.float32); pos[:, :3] = syn.uniform_cloud(PSE_N, PSE_L, seed=31)[:, :3]
     force = np.zeros((PSE_N, 4), np.float32); force[:, :3] = syn.gaussian_forces(PSE_N, seed=32, dtype=np.float32)
     return pos, force
 
 
 def pse(dev, steps=20, warmup=3):
-    from . import bd, lib
-    from . import pse as P
+    from uammd_b200 import bd, lib
+    from uammd_b200 import pse as P
     pos, force = _pse_inputs()
     p, f = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)
     m = P.PSE(p, P.Parameters(PSE_L, viscosity=1.0, hydrodynamicRadius=1.0, tolerance=PSE_TOL, psi=PSE_PSI, temperature=PSE_T,
@@ -109,7 +109,7 @@ def pse_reference(root, steps=20, warmup=3):
 
 
 def bd_ideal(dev, steps=200, warmup=10):
-    from . import bd
+    from uammd_b200 import bd
     N = 100_000
     rng = np.random.default_rng(1)
     pos = np.zeros((N, 4)); pos[:, :3] = rng.random((N, 3)) - 0.5

@@ -20,15 +20,15 @@ ALG_BYTES = 7 * GR + N * (32 * 2 + 32 + 24)
 
 
 def inputs():
-    from . import synthetic as syn
+    from uammd_b200 import synthetic as syn
     pos = np.zeros((N, 4)); pos[:, :3] = syn.uniform_cloud(N, L, seed=11)[:, :3].astype(np.float64)
     force = np.zeros((N, 4)); force[:, :3] = syn.gaussian_forces(N, seed=12)
     return pos, force
 
 
 def run(dev, hbm_peak, steps=100, warmup=10):
-    from .fcm import EulerMaruyama, FCM, Peskin3
-    from . import lib
+    from uammd_b200.fcm import EulerMaruyama, FCM, Peskin3
+    from uammd_b200 import lib
     pos, force = inputs()
     dpos, dforce = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)
     method = FCM(L, (NGRID,) * 3, Peskin3(L / NGRID), ETA, TEMP, DT, seed=1234)
@@ -89,11 +89,11 @@ def run_distributed(dev, hbm_peak, steps=100, warmup=10):
     """Strong scaling of the SAME config over all ranks (z-slab FCM, uammd_b200.multigpu.DistributedFCM): every rank
     steps the replicated particle set; device time per step, max over ranks. Returns None except on rank 0."""
     import torch.distributed as dist
-    from .fcm import Peskin3, _declare, _prec
-    from .md import _ptr, _stream_ptr
-    from .multigpu import DistributedFCM
-    from ._lib import check
-    from . import lib
+    from uammd_b200.fcm import Peskin3, _declare, _prec
+    from uammd_b200.md import _ptr, _stream_ptr
+    from uammd_b200.multigpu import DistributedFCM
+    from uammd_b200._lib import check
+    from uammd_b200 import lib
     world, rank = dist.get_world_size(), dist.get_rank()
     pos, force = inputs()
     dpos, dforce = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)

@@ -2,7 +2,8 @@
 import sys; sys.path.insert(0, '.')
 import json
 import torch
-from uammd_b200 import extra_bench, synthetic as syn
+import bench_extra as extra_bench
+from uammd_b200 import synthetic as syn
 dev = torch.device('cuda:0')
 which = sys.argv[1:] or ['verlet', 'pse', 'bd']
 if 'verlet' in which:

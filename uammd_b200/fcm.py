@@ -343,20 +343,3 @@ class EulerMaruyama:
         check(_declare().ub200_bdhi_euler_update(_prec(self.pos.dtype), _ptr(self.pos), None, _ptr(self.MF), None, None,
                                                  self.pos.shape[0], math.sqrt(2 * self.dt * T), self.dt, 0,
                                                  _stream_ptr()))
-
-
-def smoke(dev):
-    """Tiny FCM invocation checked against the oracle (called by __graft_entry__.smoke)."""
-    from oracle import oracle as orc
-    from . import synthetic as syn
-    N, n, L = 2000, 32, 32.0
-    pos = syn.uniform_cloud(N, L, seed=11).astype(np.float64)
-    force = np.zeros((N, 4))
-    force[:, :3] = syn.gaussian_forces(N, seed=12)
-    fcm = FCM_impl(L, (n, n, n), Peskin3(L / n), viscosity=1.0, seed=1)
-    out = fcm.computeHydrodynamicDisplacements(torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev))
-    torch.cuda.synchronize()
-    ref = orc.fcm_mdot((L, L, L), (n, n, n), orc.peskin3(L / n), 1.0, pos, force[:, :3])
-    err = np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref)
-    assert err < 1e-11, f"FCM mdot rel-L2 error {err}"
-    return f"path2 FCM N={N} {n}^3 rel-L2 {err:.1e}"
