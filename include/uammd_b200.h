@@ -179,6 +179,20 @@ int ub200_dpd_sum_owned_ids_f32(ub200_celllist *cl, const void *d_vel, float A, 
                                 int accumulate, const int *d_noiseId, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Path 1e: Langevin velocity Verlet (Gronbech-Jensen & Farago). Replaces VerletNVT::GronbechJensen_ns::integrateGPU<1|2>
+ * (Integrator/VerletNVT/GronbechJensen.cu:30-66), the integrator generic_md and examples/misc/benchmark.cu drive.
+ * step 1 moves positions and velocities with the noise Saru(index in group, stepNum, seed) and ZEROES the forces, step 2
+ * is the closing half kick. noiseAmplitude = sqrt(2 dt friction T) as VerletNVT::Basic computes it (Basic.cu:45);
+ * defaultMass > 0 overrides d_mass (Basic.cu:46-50). Bit-identical to the reference kernel.
+ * ub200_nvt_initial_velocities_f32 replaces Basic_ns::initialVelocities (Basic.cu:12-29, velAmplitude = sqrt(3 T)).
+ * ------------------------------------------------------------------------------------------------ */
+int ub200_nvt_gj_half_step_f32(void *d_pos, void *d_vel, void *d_force, const float *d_mass, float defaultMass,
+                               const int *d_groupIdx, int N, float dt, float friction, int is2D, float noiseAmplitude,
+                               uint32_t stepNum, uint32_t seed, int step, void *stream);
+int ub200_nvt_initial_velocities_f32(void *d_vel, const int *d_groupIdx, int N, float velAmplitude, int is2D, uint32_t seed,
+                                     void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Path 1c: velocity Verlet. Replaces VerletNVE_ns::integrateGPU<1|2> (Integrator/VerletNVE.cu:64-85)
  * and VerletNVE::resetForces (:152-158). d_mass may be NULL (defaultMass used). step==1 also drifts.
  * ------------------------------------------------------------------------------------------------ */

@@ -84,6 +84,12 @@ int orc_md_step_f32(const float L[3], float rc, const float *params4, float dt, 
 void *orc_md_scratch_new(int N, int ncells);
 void orc_md_scratch_free(void *);
 
+/* VerletNVT::GronbechJensen half steps (Integrator/VerletNVT/GronbechJensen.cu:30-66) and Basic_ns::initialVelocities
+   (Integrator/VerletNVT/Basic.cu:12-29), single precision */
+void orc_nvt_gj_half_f32(float *pos4, float *vel3, float *force4, const float *mass, float defaultMass, int N, float dt,
+                         float friction, int is2D, float noiseAmplitude, uint32_t stepNum, uint32_t seed, int step);
+void orc_nvt_initial_velocities_f32(float *vel3, int N, float vamp, int is2D, uint32_t seed);
+
 /* ---------------- path 2: IBM + FCM (fp64) ---------------- */
 /* kernel ids */
 #define ORC_KERNEL_PESKIN3 0

@@ -204,6 +204,20 @@ def nve_half(pos4, vel3, force4, dt, mass, step):
     lib().orc_nve_half_f32(_p(pos4), _p(vel3), _p(force4), pos4.shape[0], C.c_float(dt), C.c_float(mass), step)
 
 
+def nvt_gj_half(pos4, vel3, force4, dt, friction, noiseAmplitude, stepNum, seed, step, defaultMass=1.0, mass=None,
+                is2D=False):
+    """In place VerletNVT::GronbechJensen half step (float32 arrays)."""
+    lib().orc_nvt_gj_half_f32(_p(pos4), _p(vel3), _p(force4), _p(mass), C.c_float(defaultMass), pos4.shape[0],
+                              C.c_float(dt), C.c_float(friction), int(is2D), C.c_float(noiseAmplitude),
+                              C.c_uint32(stepNum), C.c_uint32(seed), int(step))
+
+
+def nvt_initial_velocities(N, vamp, seed, is2D=False):
+    vel = np.zeros((N, 3), np.float32)
+    lib().orc_nvt_initial_velocities_f32(_p(vel), N, C.c_float(vamp), int(is2D), C.c_uint32(seed))
+    return vel
+
+
 class MDOracle:
     """CPU (OpenMP) VerletNVE + PairForces<LJ,CellList>; used as correctness oracle and cpu_baseline."""
 

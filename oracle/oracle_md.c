@@ -489,3 +489,60 @@ void orc_brick_classify_f(const orc_grid_f *g, const float *pos4, int N, const i
     ghostMask[i] = mask & ~(1u << own);
   }
 }
+
+/* ---------- VerletNVT::GronbechJensen ---------- */
+/* GronbechJensen_ns::integrateGPU<step> Integrator/VerletNVT/GronbechJensen.cu:30-66, single precision build:
+ *   step 1: Saru(id, stepNum, seed); beta = (gf.x, gf.y, gf'.x) with std = noiseAmplitude * rsqrt(1/m);
+ *           b = 1/(1 + friction dt/2), a = (1 - friction dt/2) b;
+ *           p += b dt v + (1/2)(1/m) dt b (dt f + beta);  v = a v + dt (1/2)(1/m) a f + b (1/m) beta;  f = 0
+ *   step 2: v += dt (1/2)(1/m) f
+ * fmaf() spells out the contractions nvcc applies to the reference kernel for sm_100a (read from its PTX). The host
+ * libm logf/sinf/cosf and the exact 1/sqrt used here differ from the device's in the last ulp, so against the GPU
+ * this oracle agrees to ~1e-6 of the noise amplitude; bit parity is pinned by the compiled reference (oracle/_ref/ref_nvt). */
+void orc_nvt_gj_half_f32(float *pos4, float *vel3, float *force4, const float *mass, float defaultMass, int N, float dt,
+                         float friction, int is2D, float noiseAmplitude, uint32_t stepNum, uint32_t seed, int step) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < N; i++) {
+    const float invMass = 1.0f / (defaultMass > 0.0f ? defaultMass : mass[i]);
+    float *p = pos4 + 4 * (size_t)i, *v = vel3 + 3 * (size_t)i, *f = force4 + 4 * (size_t)i;
+    if (step == 1) {
+      orc_saru rng = orc_saru_seed3((uint32_t)i, stepNum, seed);
+      const float amp = noiseAmplitude * (1.0f / sqrtf(invMass));
+      float n[3] = {0, 0, 0}, g2[2];
+      orc_saru_gf(&rng, 0.0f, amp, g2);
+      n[0] = g2[0]; n[1] = g2[1];
+      if (!is2D) { orc_saru_gf(&rng, 0.0f, amp, g2); n[2] = g2[0]; }
+      const float g = (dt * friction) * 0.5f;
+      const float b = 1.0f / (g + 1.0f);
+      const float a = (1.0f - g) * b;
+      const float bdt = dt * b;
+      const float c2 = b * (dt * (invMass * 0.5f));
+      const float c3 = a * ((dt * 0.5f) * invMass);
+      const float c4 = b * invMass;
+      for (int d = 0; d < 3; d++) {
+        const float pd = fmaf(c2, fmaf(dt, f[d], n[d]), fmaf(bdt, v[d], p[d]));
+        const float vd = fmaf(c4, n[d], fmaf(a, v[d], c3 * f[d]));
+        p[d] = pd;
+        v[d] = vd;
+      }
+      f[0] = f[1] = f[2] = f[3] = 0.0f;
+    } else {
+      const float c = (dt * 0.5f) * invMass;
+      for (int d = 0; d < 3; d++) v[d] = fmaf(f[d], c, v[d]);
+    }
+    if (is2D) v[2] = 0.0f;
+  }
+}
+
+/* Basic_ns::initialVelocities Integrator/VerletNVT/Basic.cu:12-29 (mass ignored: mass_i = 1; no group here) */
+void orc_nvt_initial_velocities_f32(float *vel3, int N, float vamp, int is2D, uint32_t seed) {
+  for (int i = 0; i < N; i++) {
+    orc_saru rng = orc_saru_seed2((uint32_t)i, seed);
+    double g0[2], g1[2] = {0.0, 0.0};
+    orc_saru_gd(&rng, 0.0, (double)(vamp / 1.0f), g0);
+    if (!is2D) orc_saru_gd(&rng, 0.0, (double)(vamp / 1.0f), g1);
+    vel3[3 * (size_t)i] = (float)g0[0];
+    vel3[3 * (size_t)i + 1] = (float)g0[1];
+    vel3[3 * (size_t)i + 2] = (float)g1[0];
+  }
+}

@@ -41,6 +41,19 @@ static inline orc_saru orc_saru_seed3(uint32_t s1, uint32_t s2, uint32_t s3) {
   return orc_saru_finish(s1, s2);
 }
 
+/* two-seed constructor (saruprng.cuh:236-251) */
+static inline orc_saru orc_saru_seed2(uint32_t seed1, uint32_t seed2) {
+  seed2 += seed1 << 16;
+  seed1 += seed2 << 11;
+  seed2 += (uint32_t)orc_sar(seed1, 7);
+  seed1 ^= (uint32_t)orc_sar(seed2, 3);
+  seed2 *= 0xA5366B4Du;
+  seed2 ^= seed2 >> 10;
+  seed2 ^= (uint32_t)orc_sar(seed2, 19);
+  seed1 += seed2 ^ 0x6d2d4e11u;
+  return orc_saru_finish(seed1, seed2);
+}
+
 static inline uint32_t orc_saru_u32(orc_saru *r) {
   r->lcg = 0x4beb5d59u * r->lcg + 0x2600e1f7u;                                /* LCG, one step */
   r->weyl = r->weyl + 0x8009d14bu + ((uint32_t)orc_sar(r->weyl, 31) & 0xda879addu); /* offset Weyl, one step */
@@ -62,5 +75,18 @@ static inline void orc_saru_gf(orc_saru *r, float mean, float std, float out[2])
   const float theta = pi2 * u1;
   out[0] = (rad * sinf(theta)) * std + mean;
   out[1] = (rad * cosf(theta)) * std + mean;
+}
+/* Box-Muller pair gd: float uniforms, float log/sqrt/sin/cos, double products (saruprng.cuh:130-143) */
+static inline void orc_saru_gd(orc_saru *r, double mean, double std, double out[2]) {
+  const double pi2 = 2.0 * M_PI;
+  double u0;
+  do {
+    u0 = orc_saru_f(r);
+  } while (u0 <= DBL_MIN);
+  const double u1 = orc_saru_f(r);
+  const double rad = sqrtf((float)(-2.0 * logf((float)u0)));
+  const double theta = pi2 * u1;
+  out[0] = (rad * sinf((float)theta)) * std + mean;
+  out[1] = (rad * cosf((float)theta)) * std + mean;
 }
 #endif
