@@ -518,6 +518,83 @@ public:
   }
 };
 
+#ifndef DOUBLE_PRECISION
+/* ---------------------------------------------------------------- VerletNVT::GronbechJensen ----------------- */
+/* Integrator (Integrator/VerletNVT.cuh:100-117, VerletNVT/Basic.cu:31-77, VerletNVT/GronbechJensen.cu:96-127): the
+   Langevin integrator generic_md and examples/misc/benchmark.cu drive. Same constructor side effects as
+   VerletNVT::Basic (Saru seed = third next32() of the system generator, optional initial velocities with the fourth),
+   same forwardTime sequence; the two half steps run through ub200_nvt_gj_half_step_f32 (bit-identical). */
+class VerletNVTGronbechJensen : public Integrator {
+  real noiseAmplitude, dt, temperature, friction, defaultMass;
+  bool is2D;
+  uint seed;
+  int steps = 0;
+  cudaStream_t st;
+
+  void half(int step) {
+    const int N = pg->getNumberParticles();
+    auto pos = pd->getPos(access::location::gpu, access::mode::readwrite);
+    auto vel = pd->getVel(access::location::gpu, access::mode::readwrite);
+    auto force = pd->getForce(access::location::gpu, access::mode::readwrite);
+    auto mass = pd->getMassIfAllocated(access::location::gpu, access::mode::read).raw();
+    check(ub200_nvt_gj_half_step_f32(pos.raw(), vel.raw(), force.raw(), defaultMass > 0 ? nullptr : mass, defaultMass > 0 ? defaultMass : 0,
+                                     pg->getIndicesRawPtr(access::location::gpu), N, dt, friction, is2D, noiseAmplitude, (uint)steps,
+                                     seed, step, (void *)st),
+          "nvt_gj_half_step");
+  }
+
+public:
+  struct Parameters {
+    real temperature = 0, dt = 0, friction = 1.0;
+    bool is2D = false, initVelocities = true;
+    real mass = -1.0;
+  };
+  VerletNVTGronbechJensen(shared_ptr<ParticleData> pd, Parameters par)
+      : VerletNVTGronbechJensen(std::make_shared<ParticleGroup>(pd, "All"), par) {}
+  VerletNVTGronbechJensen(shared_ptr<ParticleGroup> pg, Parameters par)
+      : Integrator(pg, "b200::VerletNVTGronbechJensen"), dt(par.dt), temperature(par.temperature), friction(par.friction),
+        is2D(par.is2D) {
+    sys->rng().next32();
+    sys->rng().next32();
+    seed = sys->rng().next32();
+    noiseAmplitude = sqrt(2 * dt * friction * temperature);
+    defaultMass = par.mass;
+    if (!pd->isMassAllocated() and defaultMass < 0) defaultMass = 1.0;
+    CudaSafeCall(cudaStreamCreate(&st));
+    if (par.initVelocities) {
+      auto vel = pd->getVel(access::location::gpu, access::mode::write);
+      const real velAmplitude = sqrt(3.0 * temperature);
+      check(ub200_nvt_initial_velocities_f32(vel.raw(), pg->getIndicesRawPtr(access::location::gpu), pg->getNumberParticles(),
+                                             velAmplitude, is2D, sys->rng().next32(), nullptr),
+            "nvt_initial_velocities");
+      CudaSafeCall(cudaDeviceSynchronize());
+    }
+  }
+  ~VerletNVTGronbechJensen() { cudaStreamDestroy(st); }
+  uint getSeed() const { return seed; }
+  void forwardTime() override {
+    for (auto u : updatables) u->updateSimulationTime(steps * dt);
+    steps++;
+    if (steps == 1) {
+      {
+        auto force = pd->getForce(access::location::gpu, access::mode::write);
+        auto fg = pg->getPropertyIterator(force);
+        thrust::fill(thrust::cuda::par.on(st), fg, fg + pg->getNumberParticles(), real4());
+      }
+      for (auto u : updatables) {
+        u->updateTemperature(temperature);
+        u->updateTimeStep(dt);
+      }
+      for (auto f : interactors) f->sum({.force = true, .energy = false, .virial = false}, st);
+      CudaSafeCall(cudaDeviceSynchronize());
+    }
+    half(1);
+    for (auto f : interactors) f->sum({.force = true, .energy = false, .virial = false}, st);
+    half(2);
+  }
+};
+#endif /* !DOUBLE_PRECISION */
+
 } // namespace b200
 } // namespace uammd
 #endif

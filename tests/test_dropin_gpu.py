@@ -36,6 +36,14 @@ def test_nbody_fallback_dropin_matches_reference():
     assert r["force_vs_ref"] < 1e-5 and r["energy_vs_ref"] < 1e-5 and r["virial_vs_ref"] < 1e-5
 
 
+def test_langevin_verlet_dropin_matches_reference():
+    """benchmark.cu's configuration: VerletNVT::GronbechJensen + PairForces<LJ, VerletList> with both modules swapped."""
+    r = _run("dropin_nvt", 32768, 38.0, 20)
+    print(r)
+    assert r["ideal_mismatch_words"] == 0                # b200::VerletNVTGronbechJensen alone: the reference's bits
+    assert r["lj_max_dpos"] < 1e-4 and r["lj_max_dvel"] < 1e-2   # with the LJ forces: fp32 summation order only
+
+
 def test_fcm_dropin_matches_reference():
     r = _run("dropin_fcm", 20000, 64)
     print(r)
