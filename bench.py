@@ -146,7 +146,8 @@ def run_reference(args):
     if not args.no_extra:
         import bench_extra as extra_bench
         for name, fn in (("verlet", lambda: extra_bench.verlet_reference(ROOT, N, Lb, pos, vel, RC, DT, equil=args.equil)),
-                         ("pse", lambda: extra_bench.pse_reference(ROOT)), ("bd", lambda: extra_bench.bd_reference(ROOT))):
+                         ("pse", lambda: extra_bench.pse_reference(ROOT)), ("bd", lambda: extra_bench.bd_reference(ROOT)),
+                         ("langevin", lambda: extra_bench.langevin_reference(ROOT))):
             try:
                 line[name] = fn()
             except Exception as e:  # a secondary leg must not take the headline down
@@ -333,7 +334,8 @@ def main():
         if not args.no_extra and world == 1:
             import bench_extra as extra_bench
             for name, fn in (("verlet", lambda: extra_bench.verlet(dev, N, Lb, pos, vel, RC, DT, equil=args.equil)),
-                             ("pse", lambda: extra_bench.pse(dev)), ("bd", lambda: extra_bench.bd_ideal(dev))):
+                             ("pse", lambda: extra_bench.pse(dev)), ("bd", lambda: extra_bench.bd_ideal(dev)),
+                             ("langevin", lambda: extra_bench.langevin(dev)), ("dpd", lambda: extra_bench.dpd(dev))):
                 try:
                     line[name] = fn()
                 except Exception as e:  # a secondary leg must not take the headline down

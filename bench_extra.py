@@ -63,6 +63,75 @@ def verlet_reference(root, N, Lb, pos, vel, rc, dt, steps=100, warmup=20, equil=
             "what": "unmodified reference PairForces<LJ, VerletList> + VerletNVE on the same B200"}
 
 
+def dpd(dev, steps=30, warmup=5, equil=20):
+    """BASELINE config 4 shape on ONE GPU: DPD fluid, N = 4e6, rho = 3, rc = 1, A = 25, gamma = 4.5, T = 1, dt = 0.01;
+    VerletNVE + PairForces<DPD, CellList>. (The reference's Potential::DPD is a silent no-op through PairForces at this
+    commit - SURVEY F3 - so there is no reference arm for this leg.)"""
+    from uammd_b200 import lib, synthetic as syn
+    from uammd_b200.md import Box, DPD
+    from uammd_b200.multigpu import DistributedDPDMD
+    N = 4_000_000
+    L = (N / 3.0) ** (1.0 / 3.0)
+    p = torch.from_numpy(syn.uniform_cloud(N, L, seed=21)).to(dev)
+    v = torch.from_numpy(syn.maxwell_velocities(N, 1.0, seed=22)).to(dev)
+    f = torch.zeros(N, 4, device=dev)
+    md = DistributedDPDMD(Box(L), DPD(cutOff=1.0, dt=0.01, gamma=4.5, temperature=1.0, A=25.0, seed=99), 0.01, N)
+    for _ in range(equil):
+        md.forwardTime(p, v, f)
+    l0 = lib().ub200_launch_count()
+    ms = _timed(dev, lambda: md.forwardTime(p, v, f), steps, warmup)
+    return {"metric": "DPD MD steps/s @4e6 particles", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms,
+            "gpu_launches": int(lib().ub200_launch_count() - l0), "kT_from_velocities": float((v * v).sum().item()) / (3.0 * N),
+            "what": "VerletNVE + PairForces<DPD, CellList>, N = 4e6, rho = 3, rc = 1, A = 25, gamma = 4.5, single GPU"}
+
+
+LANGEVIN_N, LANGEVIN_L = 1 << 20, 128.0
+
+
+def langevin(dev, steps=100, warmup=20, equil=300):
+    """The reference's own published benchmark (examples/misc/benchmark.cu:8,69-108,172-181: "~90 FPS on a GTX 980"):
+    N = 1 048 576 LJ particles in a 128^3 box (rho = 0.5) from an FCC lattice, VerletNVT::GronbechJensen (T = 1, friction = 1,
+    dt = 0.01) + PairForces<LJ, VerletList> with a 1.2 cut-off multiplier."""
+    from uammd_b200 import lib, synthetic as syn
+    from uammd_b200.bd import System
+    from uammd_b200.md import Box, LJ, PairForces, VerletList
+    from uammd_b200.nvt import GronbechJensen, Parameters
+    N, L = LANGEVIN_N, LANGEVIN_L
+    p = torch.from_numpy(syn.fcc_lattice(N, L)).to(dev)
+    v = torch.zeros(N, 3, device=dev)
+    nvt = GronbechJensen(p, v, Parameters(temperature=1.0, dt=0.01, friction=1.0, initVelocities=True), sys=System(1234))
+    pot = LJ(); pot.setPotParameters(0, 0, cutOff=2.5)
+    nl = VerletList(); nl.setCutOffMultiplier(1.2)
+    nvt.addInteractor(PairForces(pot, Box(L), nl=nl))
+    for _ in range(equil):
+        nvt.forwardTime()
+    r0, l0 = nl.view().rebuilds, lib().ub200_launch_count()
+    ms = _timed(dev, nvt.forwardTime, steps, warmup)
+    ke = float((v * v).sum().item()) / (3.0 * N)
+    return {"metric": "Langevin MD steps/s @2^20 LJ particles (benchmark.cu)", "value": 1000.0 / ms, "unit": "steps/s",
+            "ms_per_step": ms, "rebuilds_per_step": (nl.view().rebuilds - r0) / float(steps + warmup),
+            "gpu_launches": int(lib().ub200_launch_count() - l0), "kT_from_velocities": ke, "published_gtx980_steps_per_s": 90,
+            "what": "VerletNVT::GronbechJensen + PairForces<LJ, VerletList> (skin 1.2), N = 1048576, box 128^3, dt 0.01, T 1"}
+
+
+def langevin_reference(root, steps=100, warmup=20, equil=300):
+    from uammd_b200 import synthetic as syn
+    exe = os.path.join(root, "oracle", "_ref", "ref_nvt")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_nvt was not built"}
+    N, L = LANGEVIN_N, LANGEVIN_L
+    with tempfile.TemporaryDirectory() as td:
+        syn.fcc_lattice(N, L).tofile(os.path.join(td, "p.bin")); np.zeros((N, 3), np.float32).tofile(os.path.join(td, "v.bin"))
+        out = subprocess.run([exe, str(N), str(L), str(steps), "1.0", "1.0", "0.01", "1234", "1", "1", os.path.join(td, "o"),
+                              os.path.join(td, "p.bin"), os.path.join(td, "v.bin"), "1.2", str(warmup + equil)], check=True,
+                             capture_output=True, text=True, timeout=1200).stdout
+    r = [json.loads(l) for l in out.splitlines() if l.startswith("{")][-1]
+    return {"metric": "Langevin MD steps/s @2^20 LJ particles (benchmark.cu)", "value": 1000.0 / r["ms_per_step"], "unit": "steps/s",
+            "ms_per_step": r["ms_per_step"], "published_gtx980_steps_per_s": 90,
+            "what": "unmodified reference VerletNVT::GronbechJensen + PairForces<LJ, VerletList> (skin 1.2) on the same B200; "
+                    "back-to-back steps (no L2 flush between steps)"}
+
+
 def _pse_inputs():
     from uammd_b200 import synthetic as syn
     pos = np.zeros((PSE_N, 4), np.float32); pos[:, :3] = syn.uniform_cloud(PSE_N, PSE_L, seed=31)[:, :3]

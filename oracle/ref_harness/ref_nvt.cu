@@ -4,8 +4,9 @@
  * (Integrator/VerletNVT/GronbechJensen.cu:96-127), optionally with PairForces<Potential::LJ, VerletList> like benchmark.cu.
  * Compiled by oracle/Makefile into oracle/_ref/ref_nvt (single precision). Never linked by the product.
  *
- * usage: ref_nvt N L steps temperature friction dt sysseed lj(0|1) initVelocities(0|1) outprefix [pos.bin vel.bin]
+ * usage: ref_nvt N L steps temperature friction dt sysseed lj(0|1) initVelocities(0|1) outprefix [pos.bin vel.bin [rcutmult warmup]]
  *   positions / velocities: float4[N] / float3[N] files, or (without them) a jittered lattice and zero velocities.
+ *   rcutmult: VerletList::setCutOffMultiplier (benchmark.cu uses 1.2; default 1.08); warmup: untimed steps before `steps`.
  * writes outprefix.pos0.bin .vel0.bin (state after construction, i.e. after initVelocities) and .pos.bin .vel.bin
  * (after `steps` steps); prints {"seed": <Saru seed the integrator drew>, "ms_per_step": ...}
  */
@@ -95,8 +96,15 @@ int main(int argc, char **argv) {
     using PF = PairForces<Potential::LJ, VerletList>;
     PF::Parameters pp;
     pp.box = Box(make_real3(L));
+    if (argc > 13) {
+      auto nl = std::make_shared<VerletList>(pd);
+      nl->setCutOffMultiplier(atof(argv[13]));
+      pp.nl = nl;
+    }
     nvt->addInteractor(std::make_shared<PF>(pd, pp, pot));
   }
+  const int warmup = argc > 14 ? atoi(argv[14]) : 0;
+  for (int i = 0; i < warmup; i++) nvt->forwardTime();
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaDeviceSynchronize();
