@@ -254,6 +254,7 @@ def _brick_dpd_worker(rank, world, port, N, steps, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 def test_brick_dpd_halo_exchange_matches_single_gpu(tmp_path):
     """BASELINE config 4 ("DPD fluid, ghost-cell halo exchange, domain-decomposed"): bricks of cells, migration and halo
     all-to-alls over NCCL, every visible GPU one rank; the trajectory equals the single-GPU one bit for bit."""

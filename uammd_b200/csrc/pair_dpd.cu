@@ -56,6 +56,7 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
   // arrays hold owned + ghost particles, the noise stays keyed on the global particle ids)
   __shared__ float4 cand[kDpdCap];
   __shared__ float4 candVel[kDpdCap]; // vx, vy, vz, id (bits)
+  __shared__ unsigned short queue[kPairWarps][64]; // per warp: staged indices of the candidates that passed the distance test
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
@@ -101,7 +102,12 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
       const int nidi = __float_as_int(vi.w); // id of the home particle in the Saru key
       float fx = 0.f, fy = 0.f, fz = 0.f;
       if (staged) {
-        for (int t = lane; t < nc.total; t += 32) {
+        // Only ~15 % of the candidates are within the cut-off and an in-range pair costs ~10x a rejected one (Saru
+        // seeding + Box-Muller), so the warp first filters 32 candidates with the cheap distance test - the very
+        // test dpdPair applies - and queues the survivors; the expensive body then runs on full warps.
+        unsigned short *q = queue[warp];
+        int qn = 0; // warp uniform
+        auto body = [&](int t) {
           const float4 pj = cand[t];
           const float4 vj = candVel[t];
           float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
@@ -111,7 +117,37 @@ dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
             rz = foldCoord(rz, g.Lz, g.mz);
           }
           dpdPair(rx, ry, rz, vi.x - vj.x, vi.y - vj.y, vi.z - vj.z, nidi, __float_as_int(vj.w), par, fx, fy, fz);
+        };
+        for (int t0 = 0; t0 < nc.total; t0 += 32) {
+          const int t = t0 + lane;
+          bool in = false;
+          if (t < nc.total) {
+            const float4 pj = cand[t];
+            float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+            if (PAIRMIC) {
+              rx = foldCoord(rx, g.Lx, g.mx);
+              ry = foldCoord(ry, g.Ly, g.my);
+              rz = foldCoord(rz, g.Lz, g.mz);
+            }
+            const float rmod = __fsqrt_rn(__fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx)));
+            in = rmod != 0.0f && __frcp_rn(rmod) > par.invrcut;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, in);
+          if (in) q[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)t;
+          qn += __popc(m);
+          __syncwarp();
+          if (qn >= 32) {
+            body(q[lane]);
+            const int rem = qn - 32;
+            const unsigned short mv = lane < rem ? q[32 + lane] : (unsigned short)0;
+            __syncwarp();
+            if (lane < rem) q[lane] = mv;
+            __syncwarp();
+            qn = rem;
+          }
         }
+        if (lane < qn) body(q[lane]);
+        __syncwarp();
       } else {
         for (int c = 0; c < 27; c++) {
           const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
