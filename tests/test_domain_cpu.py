@@ -155,3 +155,40 @@ def test_dpd_two_gloo_ranks_with_halo_exchange(tmp_path, orc):
         single.forwardTime(p, v, f)
     assert np.array_equal(got[:4 * N].view(np.uint32), p.numpy().ravel().view(np.uint32))
     assert np.array_equal(got[4 * N:].view(np.uint32), v.numpy().ravel().view(np.uint32))
+
+
+@pytest.mark.parametrize("periodic,L,rankGrid", [((1, 1, 0), (12.0, 12.0, 9.0), (2, 2, 1)),     # open z: no wrap across it
+                                                  ((1, 1, 1), (12.0, 6.0, 2.9), (2, 2, 1)),      # a one-cell dimension
+                                                  ((0, 0, 0), (10.0, 10.0, 10.0), (2, 1, 2))])
+def test_classify_against_brute_force_neighbourhoods(orc, periodic, L, rankGrid):
+    """Independent statement of the ghost rule: rank r needs particle i iff some particle position in r's bricks could sit in
+    a cell the traversal visits from i's cell, i.e. iff a cell of the reference's neighbour stencil around cell(i) (wrap only in
+    periodic dimensions, Grid::pbc_cell) belongs to r."""
+    from uammd_b200.domain import BrickDecomposition
+    rng = np.random.default_rng(4)
+    N = 1500
+    pos = np.zeros((N, 4), np.float32)
+    pos[:, :3] = (rng.random((N, 3)) - 0.5) * np.array(L)
+    cd = orc.neighbour_celldim(L, 2.5)
+    g = orc.make_grid_f(L, cd, periodic)
+    _, owner, mask = orc.brick_classify(g, pos, rankGrid)
+    cells = orc.get_cells(g, pos)
+    world = rankGrid[0] * rankGrid[1] * rankGrid[2]
+    own_of = lambda c: sum(BrickDecomposition.brickOfCell(int(c[d]), cd[d], rankGrid[d]) * m
+                           for d, m in enumerate((1, rankGrid[0], rankGrid[0] * rankGrid[1])))
+    for i in range(0, N, 7):
+        want = set()
+        for o in np.ndindex(3, 3, 3):
+            c = cells[i] + np.array(o) - 1
+            ok = True
+            for d in range(3):
+                if c[d] < 0 or c[d] >= cd[d]:
+                    if periodic[d]:
+                        c[d] %= cd[d]
+                    else:
+                        ok = False
+            if ok:
+                want.add(own_of(c))
+        assert owner[i] == own_of(cells[i])
+        want.discard(int(owner[i]))
+        assert {r for r in range(world) if (int(mask[i]) >> r) & 1} == want
