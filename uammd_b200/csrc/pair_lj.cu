@@ -12,6 +12,7 @@
 // body is branch free, and a half-warp split butterfly reduces both particles at once. The reference instead
 // runs one thread per particle through a divergent 27-cell iterator with ~340 dependent global loads.
 #include "pair_common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace ub200 {
@@ -19,6 +20,31 @@ namespace ub200 {
 struct Acc {
   float fx, fy, fz, e, v;
 };
+
+// Packed single precision (sm_100: add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2, two IEEE fp32 operations per issued
+// instruction; a {s, s} pair built from one register is folded by ptxas into the instruction's scalar-broadcast operand).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 
 // One LJ pair, branch free. r2 is a non negative float, so its bit pattern orders like an unsigned integer:
 // (bits(r2) - 1) < (bits(rc2) - 1) <=> 0 < r2 < rc2 (r2 == 0 wraps to 0xffffffff) - two integer-pipe
@@ -81,7 +107,13 @@ constexpr int kWarpCap = 416; // staged candidates per warp (6.5 KB, 8 CTAs/SM);
 // minimum image.
 // ownerLo/ownerHi: only home particles whose group index lies in [ownerLo, ownerHi) are computed and written
 // (multi-GPU particle decomposition: every rank holds all positions and the full list, and computes its block).
-template <bool ENERGY, bool VIRIAL, bool MULTITYPE, bool PAIRMIC, bool ACCUMULATE>
+// PACKED (force only, single type, cell image shifts): the two home particles of a pass ride in the two halves of
+// f32x2 registers, so every arithmetic instruction of the pair body serves both pairs - the operation sequence per pair is
+// the one of ljPair, hence the same bits (checked on a B200: 0 differing words at N = 1e6, profiles/r01e_lj_packed_ab.json).
+// It is NOT faster (0.4997 vs 0.4955 ms): FFMA2 does two lanes' work in two pipe cycles, and the kernel is bound by the
+// total issue slots, 42 % of which are spent outside this loop (staging, neighbour description, reductions). Kept as an
+// experiment behind UB200_LJ_PACKED=1; the default path is the scalar one.
+template <bool ENERGY, bool VIRIAL, bool MULTITYPE, bool PAIRMIC, bool ACCUMULATE, bool PACKED = false>
 __global__ void __launch_bounds__(kPairThreads, 8)
 ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
                 const uint32_t *__restrict__ binStart, GridF g, int ncells,
@@ -153,7 +185,35 @@ ljCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ grou
       const int ty0 = (int)pi0.w, ty1 = (int)pi1.w;
       const int t0 = MULTITYPE && (unsigned)ty0 < (unsigned)ntypes ? ty0 * ntypes : -1;
       const int t1 = MULTITYPE && (unsigned)ty1 < (unsigned)ntypes ? ty1 * ntypes : -1;
-      if (staged) {
+      if (staged && PACKED && !ENERGY && !VIRIAL && !MULTITYPE && !PAIRMIC) {
+        const f32x2 NPX = pack2(-pi0.x, -pi1.x), NPY = pack2(-pi0.y, -pi1.y), NPZ = pack2(-pi0.z, -pi1.z);
+        const f32x2 S2 = pack2(par0.sigma2, par0.sigma2), EPS = pack2(par0.epsDivSigma2, par0.epsDivSigma2);
+        const f32x2 M48 = pack2(-48.0f, -48.0f), C24 = pack2(24.0f, 24.0f);
+        f32x2 AX = pack2(0.f, 0.f), AY = AX, AZ = AX;
+#pragma unroll 2
+        for (int t = lane; t < nc.total; t += 32) {
+          const float4 pj = cand[t];
+          const f32x2 DX = add2(pack2(pj.x, pj.x), NPX), DY = add2(pack2(pj.y, pj.y), NPY), DZ = add2(pack2(pj.z, pj.z), NPZ);
+          const f32x2 R2 = fma2(DZ, DZ, fma2(DY, DY, mul2(DX, DX)));
+          float r2a, r2b;
+          unpack2(R2, r2a, r2b);
+          const bool ina = (__float_as_uint(r2a) - 1u) < rc2bitsm1, inb = (__float_as_uint(r2b) - 1u) < rc2bitsm1;
+          const float sa = ina ? r2a : __int_as_float(0x7f800000), sb = inb ? r2b : __int_as_float(0x7f800000);
+          float ia, ib;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ia) : "f"(sa));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ib) : "f"(sb));
+          const f32x2 U = mul2(S2, pack2(ia, ib));
+          const f32x2 U2 = mul2(U, U);
+          const f32x2 U3 = mul2(U2, U);
+          const f32x2 FM = mul2(mul2(EPS, fma2(M48, U3, C24)), mul2(U2, U2));
+          AX = fma2(FM, DX, AX);
+          AY = fma2(FM, DY, AY);
+          AZ = fma2(FM, DZ, AZ);
+        }
+        unpack2(AX, a0.fx, a1.fx);
+        unpack2(AY, a0.fy, a1.fy);
+        unpack2(AZ, a0.fz, a1.fz);
+      } else if (staged) {
 #pragma unroll 2
         for (int t = lane; t < nc.total; t += 32) {
           const float4 pj = cand[t];
@@ -317,10 +377,10 @@ ljNBody(const float4 *__restrict__ pos, const int *__restrict__ globalIdx, int N
   if (VIRIAL) virial[ori] += a.v;
 }
 
-template <bool E, bool V, bool M, bool P, bool A>
+template <bool E, bool V, bool M, bool P, bool A, bool PK = false>
 static int launchLJ(ub200_celllist *cl, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
                     const int *globalIdx, cudaStream_t st, int ownerLo, int ownerHi) {
-  auto kern = ljCellTraversal<E, V, M, P, A>;
+  auto kern = ljCellTraversal<E, V, M, P, A, PK>;
   static int blocksPerSM = 0; // per instantiation
   if (!blocksPerSM) {
     UB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kPairThreads, 0));
@@ -346,6 +406,12 @@ int ljSumDev(ub200_celllist *cl, const LJPar *d_table, int ntypes, float4 *force
   // a periodic dimension with fewer than 4 cells needs the per-pair minimum image
   const bool pairMic = (g.mx != 0.0f && g.nx < 4) || (g.my != 0.0f && g.ny < 4) || (g.mz != 0.0f && g.nz < 4);
   const bool E = energy != nullptr, V = virial != nullptr, M = ntypes > 1;
+  // experimental packed-fp32 (FFMA2) body of the force-only, single-type traversal: UB200_LJ_PACKED=1 (same bits, same speed)
+  const char *pk = getenv("UB200_LJ_PACKED");
+  if (pk && pk[0] == '1' && !E && !V && !M && !pairMic) {
+    if (accumulate) return launchLJ<false, false, false, false, true, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st, ownerLo, ownerHi);
+    return launchLJ<false, false, false, false, false, true>(cl, d_table, ntypes, force, energy, virial, globalIdx, st, ownerLo, ownerHi);
+  }
 #define UB200_LJ_DISPATCH(e, v, m, p, a)                                                                     \
   if (E == e && V == v && M == m && pairMic == p && accumulate == a)                                         \
     return launchLJ<e, v, m, p, a>(cl, d_table, ntypes, force, energy, virial, globalIdx, st, ownerLo, ownerHi);
