@@ -192,3 +192,36 @@ def test_classify_against_brute_force_neighbourhoods(orc, periodic, L, rankGrid)
         assert owner[i] == own_of(cells[i])
         want.discard(int(owner[i]))
         assert {r for r in range(world) if (int(mask[i]) >> r) & 1} == want
+
+
+def _solo_group_worker(rank, world, port, N, steps, out):
+    """The flow of scripts/brick_dpd.py: brick run on all ranks, then a single-rank reference run on rank 0 INSIDE the same
+    process group - which must use a one-rank subgroup, or its all-gathers wait for ranks that never join."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    solo = dist.new_group(ranks=[0])
+    from _checker_engines import OracleDPDBrickEngine, OracleDPDEngine
+    from uammd_b200.domain import DomainDecomposedMD, TorchFabric
+    from uammd_b200.multigpu import DistributedDPDMD
+    box, pot, pos, vel = _dpd_setup(N)
+    md = DomainDecomposedMD(OracleDPDBrickEngine(box, pot, 0.01), N, rank, world, fabric=TorchFabric())
+    md.setGlobalState(torch.from_numpy(pos), torch.from_numpy(vel))
+    for _ in range(steps):
+        md.forwardTime()
+    gp, gv = md.gatherGlobalState()
+    if rank == 0:
+        box, pot, pos, vel = _dpd_setup(N)
+        p, v, f = torch.from_numpy(pos.copy()), torch.from_numpy(vel.copy()), torch.zeros(N, 4)
+        single = DistributedDPDMD(box, pot, 0.01, N, engine=OracleDPDEngine(box, pot, 0.01, N), group=solo)
+        assert single.world == 1
+        for _ in range(steps):
+            single.forwardTime(p, v, f)
+        same = torch.equal(gp.view(torch.int32), p.view(torch.int32)) and torch.equal(gv.view(torch.int32), v.view(torch.int32))
+        open(out, "w").write("same" if same else "different")
+    dist.destroy_process_group()
+
+
+def test_single_rank_check_inside_a_two_rank_group_does_not_hang(tmp_path):
+    out = str(tmp_path / "solo.txt")
+    mp.spawn(_solo_group_worker, args=(2, 29529, 2000, 2, out), nprocs=2, join=True)
+    assert open(out).read() == "same"
