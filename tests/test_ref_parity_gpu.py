@@ -83,3 +83,44 @@ def test_reference_parity(orc, cuda, tmp_path, N, kind):
         re_, rv_ = (np.abs(ee - e64) / tol_e).max(), (np.abs(vv - v64) / tol_v).max()
         print(f"[parity N={N} {kind}] {name}: energy {re_:.3f}, virial {rv_:.3f} x fp32 tolerance")
         assert re_ < 1.0 and rv_ < 1.0
+
+
+REF_DPD = os.path.join(ROOT, "oracle", "_ref", "ref_dpd")
+
+
+@pytest.mark.parametrize("N,L", [(24000, 20.0), (192000, 40.0)])
+def test_dpd_reference_parity(orc, cuda, tmp_path, N, L):
+    """DPD against the reference's own compiled transverser. The stock PairForces<Potential::DPD> is a silent no-op at this
+    commit; oracle/ref_harness/ref_dpd.cu adds the ten-line getTransverser adaptor so that the reference's
+    PairForces + CellList drive the reference's DPD_impl::ForceTransverser (DPD.cuh:92-159) unchanged. Same Saru seed and step
+    -> the same noise; the two kernels differ in summation order only (and both in the last ulp of libm from the C oracle)."""
+    import json
+    from uammd_b200.md import DPD, PairForcesDPD
+    if not os.path.exists(REF_DPD):
+        pytest.skip("oracle/_ref/ref_dpd not built (needs the reference tree at build time)")
+    pos = syn.uniform_cloud(N, L, seed=21)
+    vel = syn.maxwell_velocities(N, 1.0, seed=22)
+    pos.tofile(tmp_path / "p.bin"); vel.tofile(tmp_path / "v.bin")
+    out = str(tmp_path / "ref")
+    r = subprocess.run([REF_DPD, str(N), repr(L), "1.0", "25.0", "4.5", "1.0", "0.01", "4321", "2", str(tmp_path / "p.bin"),
+                        str(tmp_path / "v.bin"), out], check=True, capture_output=True, text=True, timeout=600).stdout
+    info = json.loads([l for l in r.splitlines() if l.startswith("{")][-1])
+    assert info["step"] == 2
+    fref = np.fromfile(out + ".force.bin", np.float32).reshape(N, 4)
+    pot = DPD(cutOff=1.0, dt=0.01, gamma=4.5, temperature=1.0, A=25.0, seed=info["seed"])
+    pot.step = 1                                        # the evaluation below is the second one, like the reference's last
+    pf = PairForcesDPD(pot, Box(L))
+    force = torch.zeros(N, 4, device=cuda)
+    pf.sum(torch.from_numpy(pos).to(cuda), torch.from_numpy(vel).to(cuda), force)
+    torch.cuda.synchronize()
+    F = force.cpu().numpy()
+    scale = np.abs(fref[:, :3]).max()
+    assert scale > 10.0                                  # the reference did compute DPD forces through the adaptor
+    d_new = np.abs(F[:, :3] - fref[:, :3]).max() / scale
+    g = orc.make_grid_f((L,) * 3, orc.neighbour_celldim((L,) * 3, 1.0))
+    cl = orc.celllist_build(g, pos)
+    f32, _ = orc.dpd_f32(g, cl, vel, 25.0, 4.5, pot.sigma, 1.0, info["seed"], 2, N)
+    d_orc = np.abs(f32[:, :3] - fref[:, :3]).max() / scale
+    print(f"[dpd parity N={N}] new vs reference {d_new:.2e}, C oracle vs reference {d_orc:.2e} (units of the largest force)")
+    assert d_new < 2e-5                                  # same device arithmetic, different summation order
+    assert d_orc < 2e-4                                  # the oracle is pinned by the reference up to the host libm's last ulp

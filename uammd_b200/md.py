@@ -305,7 +305,9 @@ class DPD:
         self._updateSigma()
 
     def _updateSigma(self):
-        self.sigma = float(np.float32(np.sqrt(2.0 * self.temperature) / np.sqrt(self.dt)))
+        # sigma = sqrt(2.0 * temperature) / sqrt(dt) with `real` members (DPD.cuh:66): a double square root over a float one
+        f = np.float32
+        self.sigma = float(f(np.sqrt(2.0 * float(f(self.temperature))) / float(np.sqrt(f(self.dt)))))
 
     def getCutOff(self):
         return self.rcut
