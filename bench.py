@@ -34,7 +34,8 @@ RHO, RC, DT, TEMP = 0.8, 2.5, 0.005, 1.0
 ALG_BYTES_PAIR = 52          # per particle: R sortPos 16 + R groupIndex 4 + RMW force 32
 ALG_BYTES_STEP = 216         # per particle and step: build 36 + traverse 52 + integrate 112 + zero 16
 FLOP_PER_CANDIDATE = 25
-NCU_TRAFFIC_PAIR = 47.26e6   # bytes per ljCellTraversal launch at N = 1e6 (20.38 MB read + 26.88 MB written), profiles/r01b_lj_raw.csv
+NCU_TRAFFIC_PAIR = 22.61e6   # DRAM bytes per ljColumnTraversal launch at N = 1e6 (22.60 MB read + 0.01 MB written: the force writes
+                             # stay in the 126 MB L2), profiles/r02_lj_raw.csv
 FP32_PEAK_TFLOPS = 74.4      # 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
@@ -134,7 +135,8 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
                    "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
-                   "device": "B200 GPU: the reference's only implementation of this path is CUDA (unmodified, sm_100a build)"},
+                   },
+        "arm": "reference on the B200 GPU: the reference's only implementation of this path is CUDA (unmodified, sm_100a build)",
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": 1, "kind": "reference",
                          "sample": f"{args.steps} steps of the full workload; 1 host thread driving the reference's CUDA kernels"},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,32 +251,38 @@ def main():
     barrier()
     ms_b2b = e0.elapsed_time(e1) / args.steps
 
-    # ---- roofline of the dominant kernel (LJ cell traversal), timed alone on its stream ----
-    pf = PairForces(pot, box)
-    pf.nl.update(p, box, RC)
+    # ---- roofline of the dominant kernel (LJ column traversal), timed alone on its stream ----
+    from uammd_b200.md import CellList, LJEngine
+    eng = LJEngine()
+    ftmp = torch.zeros(N, 4, device=dev)
+    eng.sum(p, box, pot.table(), pot.ntypes, force=ftmp, accumulate=False)
+    assert eng.lastPath() == "column", eng.lastPath()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
     for a, b in kev:
         scrub.fill_(2)
         a.record()
-        pf.sumWithCurrentList(force=f)
+        eng.traverse(ftmp, accumulate=False)
         b.record()
     torch.cuda.synchronize()
     t_pair_ms = float(np.median([a.elapsed_time(b) for a, b in kev]))
-    pf.nl.update(p, box, RC)
-    md.prepared = False  # f was accumulated into by the roofline probe: recompute before any further stepping
     peak, peak_src = measured_peaks()
-    ncells = int(np.prod(pf.nl.cellDim))
-    cand = 27.0 * N / ncells
+    ncells = int(np.prod(CellList.gridFor(box, RC)))
+    cand = 27.0 * N / ncells                       # candidates of the reference's 27-cell walk: the ALGORITHMIC work
+    cand_exec = 125.0 * N / float(np.prod(eng.grid()))  # candidates the engine actually tests (5^3 half cells)
     pair_gbs = ALG_BYTES_PAIR * N / (t_pair_ms * 1e-3) / 1e9
     pair_tflops = cand * FLOP_PER_CANDIDATE * N / (t_pair_ms * 1e-3) / 1e12
     roofline = {
-        "kernel": "ljCellTraversal", "bound": "hbm", "achieved": pair_gbs, "peak": peak, "unit": "GB/s",
-        "frac": pair_gbs / peak, "traffic": NCU_TRAFFIC_PAIR if N == 1_000_000 else None, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_lj_raw.csv",
+        "kernel": "ljColumnTraversal", "bound": "hbm", "achieved": pair_gbs, "peak": peak, "unit": "GB/s",
+        "frac": pair_gbs / peak, "traffic": NCU_TRAFFIC_PAIR if N == 1_000_000 else None, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r02_lj_raw.csv",
         "peak_source": peak_src, "kernel_ms": t_pair_ms,
         "algorithmic_bytes_per_launch": ALG_BYTES_PAIR * N,
-        "note": "the pair kernel is FP32-ALU/shared-memory bound, not HBM bound (SURVEY 8(d)); see fp32 and pipeline",
+        "note": "the pair kernel is bound by instruction issue, not HBM (SURVEY 8(d)); see fp32 and pipeline",
         "fp32": {"achieved_tflops": pair_tflops, "peak_tflops": FP32_PEAK_TFLOPS, "frac": pair_tflops / FP32_PEAK_TFLOPS,
-                 "candidates_per_particle": cand, "flop_per_candidate": FLOP_PER_CANDIDATE},
+                 "candidates_per_particle": cand, "flop_per_candidate": FLOP_PER_CANDIDATE,
+                 "what": "algorithmic flops of the reference's 27-cell walk (SURVEY 8(d): 339.6 candidates x 25 flop) per kernel time, "
+                         "against the nominal non-tensor FP32 peak; the engine tests fewer candidates to get the same forces",
+                 "candidates_tested_per_particle": cand_exec,
+                 "executed_tflops": cand_exec * FLOP_PER_CANDIDATE * N / (t_pair_ms * 1e-3) / 1e12},
         "pipeline": {"bytes_per_step": ALG_BYTES_STEP * N, "achieved": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9,
                      "unit": "GB/s", "frac": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9 / peak},
     }
@@ -292,11 +300,22 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
     # device-resident state through the same public API, one scalar (kinetic energy) read back per step
+    import ctypes
+    cudart = ctypes.CDLL("libcudart.so.12")
+    cudart.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    ke_host = torch.zeros(n_e2e, dtype=torch.float32).pin_memory()
+    ke_dev = torch.zeros(1, device=dev)
+    vflat = v.view(-1)
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
+    for k in range(n_e2e):
         md.run(p, v, f, 1)
-        ke = float((v * v).sum()) * 0.5
+        torch.dot(vflat, vflat, out=ke_dev[0])  # the step's result: 2 x kinetic energy, copied down asynchronously
+        cudart.cudaMemcpyAsync(ke_host.data_ptr() + 4 * k, ke_dev.data_ptr(), 4, 2, stream)
+    torch.cuda.synchronize()
     e2e_res_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    ke = 0.5 * float(ke_host[-1])
 
     # ---- aggregate over ranks ----
     t = torch.tensor([ms_per_step, ms_b2b, e2e_ms, e2e_res_ms], device=dev, dtype=torch.float64)
@@ -310,7 +329,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
                        "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no path-1 decomposition yet)"},
+                       },
+            "arm": "uammd_b200, single GPU",
             "value_back_to_back": world * 1000.0 / ms_b2b,
             "clocks": clk.summary(),
             "e2e": {"value": world * 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": N * 28,
@@ -319,7 +339,8 @@ def main():
                             "step taken and pos + vel downloaded (transfers overlapped with the two force evaluations). The reference arm "
                             "keeps its state on the device (0 bytes/step): like for like is `value`, or e2e_resident"},
             "e2e_resident": {"value": world * 1000.0 / e2e_res_ms, "unit": "steps/s", "d2h_bytes_per_step": 4,
-                             "what": "same API with device-resident state, kinetic energy read back every step", "last_ke": ke},
+                             "what": "same API with device-resident state, kinetic energy copied to pinned host memory every step "
+                                     "(asynchronously; one synchronisation after the last step)", "last_ke": ke},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

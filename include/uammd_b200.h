@@ -107,6 +107,39 @@ int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, 
 int ub200_lj_nbody_f32(const void *d_pos, const int *d_globalIdx, int N, const float L[3], const int periodic[3],
                        const float *params, int ntypes, void *d_force, float *d_energy, float *d_virial, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 1b': PairForces<Potential::LJ, CellList>::sum in ONE call (Interactor/PairForces.cu:43-78: neighbour-list update +
+ * traversal with Radial<LJFunctor>::Transverser, or NBody::transverse for boxes <= 3 cut-offs, :49-53). The forces,
+ * energies and virials are the reference's (every pair within the cut-off once, minimum image, self excluded); the
+ * neighbour search behind them is the engine's own: particles are binned on a grid of HALF cells (edge >= cutOff / 2,
+ * sorted x-fastest, coordinates folded into the box) and every column of half cells is traversed by one warp whose
+ * 5 x 5 x (6 + 4) halo is staged into shared memory by the TMA engine (cp.async.bulk + mbarrier). 196 candidates per
+ * particle at rho = 0.8, rc = 2.5 instead of the 340 of the 27-cell walk (CellList/NeighbourContainer.cuh:95-138).
+ * Grids with a periodic dimension under five half cells fall back to ub200_celllist_build_f32 + ub200_lj_sum_f32.
+ * d_pos real4[*]; d_groupIdx optional int[N] indirection (ParticleGroup::getIndexIterator); params as ub200_lj_sum_f32;
+ * outputs indexed by d_globalIdx[group index] (NULL = identity). accumulate = 1 adds like Transverser::set,
+ * accumulate = 0 writes (fx, fy, fz, 0) (sole interactor: replaces VerletNVE::resetForces + sum; forces only).
+ * [ownerLo, ownerHi): only particles whose group index lies in the range are computed and written (0, INT_MAX = all;
+ * multi-GPU decompositions, forces only).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_ljengine ub200_ljengine;
+int ub200_ljengine_create(ub200_ljengine **out);
+int ub200_ljengine_destroy(ub200_ljengine *e);
+int ub200_ljengine_sum_f32(ub200_ljengine *e, const void *d_pos, const int *d_groupIdx, int N, const float L[3],
+                           const int periodic[3], const float *params, int ntypes, void *d_force, float *d_energy,
+                           float *d_virial, const int *d_globalIdx, int accumulate, int ownerLo, int ownerHi, void *stream);
+/* the traversal kernel alone over the list of the last ub200_ljengine_sum_f32 call (positions unchanged; kernel timing
+ * and profiling). Forces only; UB200_ERR_NOT_BUILT unless that call took the column path. */
+int ub200_ljengine_traverse_f32(ub200_ljengine *e, void *d_force, int accumulate, void *stream);
+/* path of the last call: 0 = column traversal over the half-cell list, 1 = cell traversal over the reference-layout
+ * list, 2 = all pairs (NBody) */
+int ub200_ljengine_last_path(ub200_ljengine *e);
+/* half cells per dimension of the last column traversal */
+int ub200_ljengine_grid(ub200_ljengine *e, int cells[3]);
+/* synchronises the stream; 1 = a particle outside a non periodic box / NaN (like CellList_ns::fillCellList's errorFlag,
+ * CellListBase.cuh:68-95), 2 = a bulk copy never completed */
+int ub200_ljengine_error_flag(ub200_ljengine *e, void *stream, int *flag);
+
 /* Brick domain decomposition of the pair path over the GPUs of one box (the reference is single-GPU: new functionality,
  * SURVEY 8(e); BASELINE config 4 "ghost-cell halo exchange"). Defined on the reference's neighbour grid
  * (CellList::createUpdateGrid, CellList.cuh:100-126; Grid::getCell, utils/Grid.cuh:49-71, same roundings as
@@ -219,7 +252,7 @@ int ub200_md_lj_nve_run_f32(ub200_md *md, void *d_pos, void *d_vel, void *d_forc
 int ub200_md_lj_nve_run_host_f32(ub200_md *md, float *h_pos4, float *h_vel3, float *h_force4, int N,
                                  const float L[3], float rc, const float *params, int ntypes, float dt,
                                  int nsteps, void *stream);
-ub200_celllist *ub200_md_celllist(ub200_md *md);
+struct ub200_ljengine *ub200_md_engine(ub200_md *md); /* the pair-force engine the fused loop drives (declared below) */
 /* ------------------------------------------------------------------------------------------------
  * Path 2: FFT-based hydrodynamics. Precision is chosen at create time (precisionBytes = 4 | 8, the
  * reference's global `real`); positions/forces are real4, per-particle outputs real3, grids real3 AoS

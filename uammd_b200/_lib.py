@@ -56,7 +56,14 @@ def _declare(lib):
         "ub200_nve_kick_kick_drift_f32": (i, [vp, vp, vp, i, f, vp]),
         "ub200_md_create": (i, [C.POINTER(vp)]),
         "ub200_md_destroy": (i, [vp]),
-        "ub200_md_celllist": (vp, [vp]),
+        "ub200_md_engine": (vp, [vp]),
+        "ub200_ljengine_create": (i, [C.POINTER(vp)]),
+        "ub200_ljengine_destroy": (i, [vp]),
+        "ub200_ljengine_sum_f32": (i, [vp, vp, vp, i, _F3, _I3, fp, i, vp, vp, vp, vp, i, i, i, vp]),
+        "ub200_ljengine_traverse_f32": (i, [vp, vp, i, vp]),
+        "ub200_ljengine_last_path": (i, [vp]),
+        "ub200_ljengine_grid": (i, [vp, _I3]),
+        "ub200_ljengine_error_flag": (i, [vp, vp, C.POINTER(i)]),
         "ub200_md_lj_nve_prepare_f32": (i, [vp, vp, vp, i, _F3, f, fp, i, vp]),
         "ub200_md_lj_nve_run_f32": (i, [vp, vp, vp, vp, i, _F3, f, fp, i, f, i, vp]),
         "ub200_md_lj_nve_run_host_f32": (i, [vp, vp, vp, vp, i, _F3, f, fp, i, f, i, vp]),

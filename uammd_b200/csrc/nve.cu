@@ -1,11 +1,8 @@
 // Velocity Verlet (NVE) half steps and the fused LJ molecular dynamics engine, sm_100a.
 // Replaces VerletNVE_ns::integrateGPU<step> / VerletNVE::forwardTime (Integrator/VerletNVE.cu:64-85,174-188).
-#include "common.cuh"
+#include "lj_engine.cuh"
 
 namespace ub200 {
-
-int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
-          const int *globalIdx, bool accumulate, LJTableCache *cache, cudaStream_t st, int ownerLo, int ownerHi);
 
 // v += (F/m) dt/2 ; step 1 also x += v dt. Same operation order as the reference (force/m is (1/m)*force,
 // utils/vector.cuh:191-193; the trailing multiply-adds are contracted by nvcc there, spelled out here).
@@ -62,8 +59,7 @@ nveKickKickDrift(float4 *__restrict__ pos, float *__restrict__ vel, const float4
 using namespace ub200;
 
 struct ub200_md {
-  ub200_celllist *cl = nullptr;
-  LJTableCache ljTable;
+  ub200_ljengine *eng = nullptr; // PairForces<LJ, CellList>::sum: private half-cell list + column traversal (lj_column.cu)
   DevBuf dpos, dvel, dforce; // device state for the host-buffer entry point
   cudaStream_t copyStream = nullptr; // host-buffer entry point: transfers overlapped with the force evaluations
   cudaEvent_t evPosUp = nullptr, evVelUp = nullptr, evDrift = nullptr, evPosDown = nullptr;
@@ -98,7 +94,7 @@ int ub200_md_create(ub200_md **out) {
   if (!out) return UB200_ERR_INVALID_ARGUMENT;
   ub200_md *md = new (std::nothrow) ub200_md();
   if (!md) return UB200_ERR_ALLOC;
-  int rc = ub200_celllist_create(&md->cl);
+  int rc = ub200_ljengine_create(&md->eng);
   if (rc) { delete md; return rc; }
   *out = md;
   return UB200_OK;
@@ -106,8 +102,8 @@ int ub200_md_create(ub200_md **out) {
 
 int ub200_md_destroy(ub200_md *md) {
   if (!md) return UB200_OK;
-  ub200_celllist_destroy(md->cl);
-  md->ljTable.dev.release(); md->dpos.release(); md->dvel.release(); md->dforce.release();
+  ub200_ljengine_destroy(md->eng);
+  md->dpos.release(); md->dvel.release(); md->dforce.release();
   if (md->copyStream) {
     cudaStreamDestroy(md->copyStream);
     cudaEventDestroy(md->evPosUp); cudaEventDestroy(md->evVelUp); cudaEventDestroy(md->evDrift); cudaEventDestroy(md->evPosDown);
@@ -116,17 +112,15 @@ int ub200_md_destroy(ub200_md *md) {
   return UB200_OK;
 }
 
-ub200_celllist *ub200_md_celllist(ub200_md *md) { return md ? md->cl : nullptr; }
+ub200_ljengine *ub200_md_engine(ub200_md *md) { return md ? md->eng : nullptr; }
 
 static int mdForces(ub200_md *md, void *d_pos, void *d_force, int N, const float L[3], float rc, const float *params,
                     int ntypes, cudaStream_t st) {
   const int periodic[3] = {1, 1, 1};
-  int cellDim[3];
-  int e = ub200_neighbour_celldim_f32(L, rc, cellDim);
-  if (e) return e;
-  if ((e = ub200_celllist_build_f32(md->cl, d_pos, nullptr, N, L, periodic, cellDim, st))) return e;
+  (void)rc; // the neighbour search radius is the largest pair cut-off of the table, as Radial::getCutOff returns it
   // sole interactor: forces are written, not accumulated (replaces resetForces + sum)
-  return ljSum(md->cl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, false, &md->ljTable, st, 0, 0x7fffffff);
+  return ljEngineSum(md->eng, (const float4 *)d_pos, nullptr, N, L, periodic, params, ntypes, (float4 *)d_force, nullptr,
+                     nullptr, nullptr, false, 0, 0x7fffffff, st);
 }
 
 int ub200_md_lj_nve_prepare_f32(ub200_md *md, void *d_pos, void *d_force, int N, const float L[3], float rc,

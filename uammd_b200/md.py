@@ -249,18 +249,83 @@ class VerletList:
         }
 
 
+class LJEngine:
+    """ub200_ljengine: PairForces<Potential::LJ, CellList>::sum in one call (Interactor/PairForces.cu:43-78) over the
+    engine's private half-cell list (column traversal, uammd_b200/csrc/lj_column.cu)."""
+
+    PATHS = {0: "column", 1: "cell", 2: "nbody", -1: "none"}
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(_lib.lib().ub200_ljengine_create(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().ub200_ljengine_destroy(self._h)
+        except Exception:
+            pass
+
+    def sum(self, pos, box, table, ntypes, force=None, energy=None, virial=None, stream=None, groupIndex=None,
+            globalIndex=None, accumulate=True, owner=(0, 0x7fffffff)):
+        if pos.dtype != torch.float32 or pos.dim() != 2 or pos.shape[1] != 4 or not pos.is_cuda or not pos.is_contiguous():
+            raise UB200Error("PairForces.sum: pos must be a contiguous CUDA float32 [N,4] tensor (real4)")
+        N = pos.shape[0] if groupIndex is None else groupIndex.shape[0]
+        check(_lib.lib().ub200_ljengine_sum_f32(self._h, _ptr(pos), _ptr(groupIndex), N, f3(box.boxSize),
+                                                i3([int(p) for p in box.periodic]), table.ctypes.data_as(C.POINTER(C.c_float)),
+                                                ntypes, _ptr(force), _ptr(energy), _ptr(virial), _ptr(globalIndex),
+                                                int(accumulate), int(owner[0]), int(owner[1]), _stream_ptr(stream)))
+
+    def traverse(self, force, accumulate=True, stream=None):
+        """The traversal kernel alone over the list of the last sum() (kernel timing)."""
+        check(_lib.lib().ub200_ljengine_traverse_f32(self._h, _ptr(force), int(accumulate), _stream_ptr(stream)))
+
+    def lastPath(self):
+        return self.PATHS[_lib.lib().ub200_ljengine_last_path(self._h)]
+
+    def grid(self):
+        cd = i3((0, 0, 0))
+        check(_lib.lib().ub200_ljengine_grid(self._h, cd))
+        return tuple(cd)
+
+    def errorFlag(self):
+        flag = C.c_int(0)
+        check(_lib.lib().ub200_ljengine_error_flag(self._h, _stream_ptr(), C.byref(flag)))
+        return flag.value
+
+
 class PairForces:
-    """Interactor: sum(pos, force=, energy=, virial=) accumulates (+=) like Transverser::set. nl: CellList (default) or
-    VerletList, like the second template argument of the reference's PairForces."""
+    """Interactor: sum(pos, force=, energy=, virial=) accumulates (+=) like Transverser::set. nl: the second template
+    argument of the reference's PairForces - None (default) lets the engine search neighbours its own way (LJEngine: the
+    forces are the reference's, the list is private); a CellList or VerletList instance keeps the reference-layout list,
+    which getCellList() / getVerletList() expose. With the default, `nl` is a CellList built on demand from the positions
+    of the last sum()."""
 
     def __init__(self, potential, box, nl=None):
         self.pot, self.box = potential, box
-        self.nl = nl if nl is not None else CellList()
+        self._nl = nl
+        self._engine = LJEngine() if nl is None else None
+        self._last = None
+
+    @property
+    def nl(self):
+        if self._nl is None:
+            self._nl = CellList()
+        if self._engine is not None and self._last is not None:
+            pos, stream = self._last
+            self._nl.update(pos, self.box, self.pot.getCutOff(), stream)
+            self._last = None
+        return self._nl
 
     def updateBox(self, box):
         self.box = box
 
     def sum(self, pos, force=None, energy=None, virial=None, stream=None, globalIndex=None):
+        if self._engine is not None:
+            self._engine.sum(pos, self.box, self.pot.table(), self.pot.ntypes, force, energy, virial, stream,
+                             globalIndex=globalIndex)
+            self._last = (pos, stream)
+            return
         rcut = self.pot.getCutOff()
         L = self.box.boxSize
         if all(l <= 3 * rcut for l in L):
