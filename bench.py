@@ -12,9 +12,9 @@ launching stream with a 256 MiB L2-evicting write before every step (the working
 otherwise sit in the 126 MB L2); ms_per_step = sum(step times)/K, max over ranks. `value_back_to_back`
 reports the same K steps enqueued back to back (how an application runs them).
 
-Multi GPU (N > 1, launched by torchrun): ONE 1e6-particle system over all ranks (strong scaling) by particle
-decomposition: block-owned particles, NCCL all-gather of the position blocks every step, forces only for the
-owned block (uammd_b200/multigpu.py). value = steps/s of that single system.
+Multi GPU (N > 1, launched by torchrun): ONE 1e6-particle system over all ranks (strong scaling) by brick domain
+decomposition with a device-side halo exchange (uammd_b200/brickmd.py, uammd_b200/csrc/brick_md.cu): owned particles +
+ghost half cells, one peer-to-peer exchange per step. value = steps/s of that single system.
 """
 import argparse
 import json
@@ -300,22 +300,15 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
     # device-resident state through the same public API, one scalar (kinetic energy) read back per step
-    import ctypes
-    cudart = ctypes.CDLL("libcudart.so.12")
-    cudart.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
-    ke_host = torch.zeros(n_e2e, dtype=torch.float32).pin_memory()
-    ke_dev = torch.zeros(1, device=dev)
-    vflat = v.view(-1)
-    stream = torch.cuda.current_stream().cuda_stream
+    ke_host = torch.zeros(n_e2e, dtype=torch.float64).pin_memory()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(n_e2e):
         md.run(p, v, f, 1)
-        torch.dot(vflat, vflat, out=ke_dev[0])  # the step's result: 2 x kinetic energy, copied down asynchronously
-        cudart.cudaMemcpyAsync(ke_host.data_ptr() + 4 * k, ke_dev.data_ptr(), 4, 2, stream)
+        md.kineticEnergy(v, ke_host, k)  # the step's result (ub200_md_kinetic_energy_f32), copied down asynchronously
     torch.cuda.synchronize()
     e2e_res_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-    ke = 0.5 * float(ke_host[-1])
+    ke = float(ke_host[-1])
 
     # ---- aggregate over ranks ----
     t = torch.tensor([ms_per_step, ms_b2b, e2e_ms, e2e_res_ms], device=dev, dtype=torch.float64)
@@ -368,19 +361,18 @@ def main():
 
 
 def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
-    """N > 1: strong scaling of the single 1e6-particle system (uammd_b200.multigpu.DistributedLJMD)."""
+    """N > 1: strong scaling of the single 1e6-particle system over bricks with a device-side halo exchange
+    (uammd_b200.brickmd.BrickLJMD: ub200_brick_* / ub200_halo_exchange_* in the C ABI)."""
     import torch
     import torch.distributed as dist
     import uammd_b200
-    from uammd_b200.multigpu import DistributedLJMD
+    from uammd_b200.brickmd import BrickLJMD
     lib = uammd_b200.lib()
-    md = DistributedLJMD(box, pot, DT, N)
-    lo, hi = md.dec.lo, md.dec.hi
-    p = torch.from_numpy(pos).to(dev)
-    f = torch.zeros(N, 4, device=dev)
-    vb = torch.from_numpy(vel[lo:hi].copy()).to(dev)
+    md = BrickLJMD(box, pot, DT, N, rank, world)
+    md.connect()
+    md.setGlobalState(torch.from_numpy(pos).to(dev), torch.from_numpy(vel).to(dev))
     scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    md.run(p, vb, f, args.equil + args.warmup)
+    md.run(args.equil + args.warmup)
 
     def barrier():
         dist.barrier()
@@ -393,7 +385,7 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
         for a, b in evs:
             scrub.fill_(1)
             a.record()
-            md.run(p, vb, f, 1)
+            md.run(1)
             b.record()
         barrier()
     launches = lib.ub200_launch_count() - launches0
@@ -401,26 +393,32 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    md.run(p, vb, f, args.steps)
+    md.run(args.steps)
     e1.record()
     barrier()
     ms_b2b = e0.elapsed_time(e1) / args.steps
-    # e2e: every rank round-trips ITS block (pos + vel) through pinned host memory every step
-    hp, hv = p[lo:hi].cpu().pin_memory(), vb.cpu().pin_memory()
+    # e2e: every rank round-trips ITS owned block (pos + vel) through pinned host memory every step
+    cap = md.info().capacity
+    hp, hv = torch.zeros(cap, 4).pin_memory(), torch.zeros(cap, 3).pin_memory()
     n_e2e = max(10, min(args.steps, 50))
+    moved = 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        p[lo:hi].copy_(hp, non_blocking=True); vb.copy_(hv, non_blocking=True)
-        md.prepared = False
-        md._gather(p)
-        md.run(p, vb, f, 1)
-        hp.copy_(p[lo:hi], non_blocking=True); hv.copy_(vb, non_blocking=True)
+        md.run(1)
+        no, _, _ = md.counts()          # synchronises: the host needs the size of its block
+        md.downloadOwned(hp, hv, no)
         torch.cuda.synchronize()
+        md.uploadOwned(hp, hv, no)
+        moved += no * 28
+    torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    no, nl, err = md.counts()
     t = torch.tensor([ms_per_step, ms_b2b, e2e_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step, ms_b2b, e2e_ms = (float(x) for x in t.cpu())
+    tot = torch.tensor([moved / n_e2e, float(no), float(nl), float(err)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     if rank == 0:
         peak, peak_src = measured_peaks()
         line = {
@@ -429,12 +427,14 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
                        "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
-                       "parallelism": f"particle decomposition over {world} GPUs: block-owned particles, NCCL all-gather of positions "
-                                      f"({N * 16} B) every step, forces for the owned block only"},
+                       },
+            "arm": f"uammd_b200, {world} GPUs: brick decomposition {md.rankGrid} with ghost half cells, one peer-to-peer halo "
+                   f"exchange per step (NVLink stores, no NCCL and no host round trip on the step path)",
+            "bricks": {"rank_grid": list(md.rankGrid), "owned_total": int(tot[1]), "local_total_with_ghosts": int(tot[2]),
+                       "error_flags": int(tot[3])},
             "value_back_to_back": 1000.0 / ms_b2b, "clocks": clk.summary(),
-            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": (hi - lo) * 28 * world,
-                    "d2h_bytes_per_step": (hi - lo) * 28 * world,
-                    "what": "each rank uploads its pinned pos+vel block, positions are all-gathered, forces recomputed, 1 step, block downloaded"},
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(tot[0]), "d2h_bytes_per_step": int(tot[0]),
+                    "what": "after every step each rank downloads its owned block (pos + vel) to pinned host memory and uploads it again"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9 / world, "peak": peak,
                          "unit": "GB/s", "frac": ALG_BYTES_STEP * N / (ms_per_step * 1e-3) / 1e9 / world / peak, "traffic": None,

@@ -152,6 +152,64 @@ int ub200_brick_classify_f32(const void *d_pos, int N, const float L[3], const i
                              const int rankGrid[3], int *d_cell, int *d_owner, uint32_t *d_ghostMask, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU pair path: brick domain decomposition with a ghost-cell halo exchange, one process per GPU of one NVSwitch
+ * box (new functionality: the reference is single-GPU; BASELINE config 4). The engine's half-cell grid
+ * (ub200_ljengine_*) is cut into rankGrid[0] x rankGrid[1] x rankGrid[2] bricks of whole half cells; a rank owns the
+ * particles of its brick and holds, as ghosts, the particles of the two half-cell layers (>= cutOff) around it; its list
+ * is built on that window only. The particle state {pos real4, vel real3, global id} lives in the handle, on the device.
+ * ONE exchange per step: after the drift every rank stores each particle's 32-byte row straight into the inboxes of its
+ * new owner and of every rank that needs it as a ghost (peer-to-peer stores over NVLink, CUDA IPC mappings), raises its
+ * flag in every peer, and the receivers append what arrived; particle counts never leave the device and no call below
+ * synchronises except ub200_brick_counts. Trajectories are bit-identical to the single-GPU engine's
+ * (ub200_md_lj_nve_run_f32) for every rank grid: cells list their particles by global id and the image shifts are the
+ * single-GPU ones.
+ * Set-up (like ub200_fcm_dist_*): create on every rank, exchange the ub200_comm_ipc_size()-byte blobs of
+ * ub200_brick_ipc_export between the ranks (rank order), hand all of them to ub200_brick_ipc_import. Virtual ranks inside
+ * one process (tests on one GPU) pass each other's ub200_brick_arena pointers to ub200_brick_attach_local instead and
+ * drive the step in two phases (ub200_brick_lj_nve_phase_f32: phase 0 of every rank before phase 1 of any).
+ * At most 8 ranks; every brick at least two half cells thick; capacity = 0 picks 1.3 x the mean window population.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_brick ub200_brick;
+typedef struct {
+  void *d_pos, *d_vel;  /* real4[capacity], real3[capacity]: owned block first, ghosts behind it */
+  int *d_gid;           /* global particle ids */
+  void *d_force;        /* real4[capacity], meaningful on the owned block */
+  int *d_counts;        /* device {nOwned, nLocal} */
+  int capacity, rank, world;
+  int halfCells[3], window[3], windowOrigin[3];
+} ub200_brick_info_t;
+int ub200_brick_create(ub200_brick **out, int rank, const int rankGrid[3], const float L[3], const int periodic[3], float cutOff,
+                       int numberParticles, int capacity);
+int ub200_brick_destroy(ub200_brick *b);
+int ub200_comm_ipc_size(void);
+int ub200_brick_ipc_export(ub200_brick *b, void *blob);
+int ub200_brick_ipc_import(ub200_brick *b, const void *blobsOfAllRanks);
+int ub200_brick_arena(ub200_brick *b, void **arena);
+int ub200_brick_attach_local(ub200_brick *b, void *const *arenasOfAllRanks);
+/* every rank passes the same full arrays (replicated initial condition) and keeps the particles it owns */
+int ub200_brick_set_global_state_f32(ub200_brick *b, const void *d_pos, const void *d_vel, int N, void *stream);
+/* ownership + ghosts for the current positions: the exchange alone (migration and halo in one pass) */
+int ub200_halo_exchange_f32(ub200_brick *b, void *stream);
+int ub200_halo_exchange_phase_f32(ub200_brick *b, int phase, void *stream);
+/* LJ forces of the owned block over [owned | ghosts] (ub200_ljengine_sum_f32 restricted to the owned particles) */
+int ub200_brick_lj_forces_f32(ub200_brick *b, const float *params, int ntypes, void *stream);
+/* VerletNVE::forwardTime x nsteps with one PairForces<LJ, CellList> interactor (Integrator/VerletNVE.cu:174-188) on the
+ * bricks: kick + drift + exchange, list build over the window, forces of the owned block, kick. */
+int ub200_brick_lj_nve_run_f32(ub200_brick *b, const float *params, int ntypes, float dt, int nsteps, void *stream);
+int ub200_brick_lj_nve_phase_f32(ub200_brick *b, int phase, const float *params, int ntypes, float dt, int doKick, void *stream);
+int ub200_brick_info(ub200_brick *b, ub200_brick_info_t *info);
+/* owned block <-> host buffers (pinned for asynchronous copies): pos real4[n], vel real3[n], ids int[n] (may be NULL);
+ * n = the owned count ub200_brick_counts reported. The upload replaces the owned block in place. */
+int ub200_brick_download_owned_f32(ub200_brick *b, void *h_pos, void *h_vel, int *h_gid, int n, void *stream);
+int ub200_brick_upload_owned_f32(ub200_brick *b, const void *h_pos, const void *h_vel, const int *h_gid, int n, void *stream);
+/* diagnostics (environment UB200_BRICK_PROFILE=1 at create time, makes every step synchronous): mean ms per step of
+ * push, unpack (including the wait for the peers), list build, traversal, kick */
+int ub200_brick_profile(ub200_brick *b, double phases[5]);
+/* synchronises the stream: particle counts and the error flag (0 clean; 3 particle outside the window, 4 capacity,
+ * 5 inbox overflow, 6 a peer's flag never arrived) */
+int ub200_brick_counts(ub200_brick *b, void *stream, int *nOwned, int *nLocal, int *errorFlag);
+
+/* ------------------------------------------------------------------------------------------------
  * Path 1d: Verlet (skin) list. Replaces VerletList::update (Interactor/NeighbourList/VerletList.cuh:111-124) and
  * the classes beneath it (VerletList/VerletListBase.cuh:73-199, BasicList/BasicListBase.cuh:76-215): rebuild when
  * a particle moved >= (multiplier - 1) cutOff / 2 since the last rebuild (host-synchronous flag read, like
@@ -252,6 +310,10 @@ int ub200_md_lj_nve_run_f32(ub200_md *md, void *d_pos, void *d_vel, void *d_forc
 int ub200_md_lj_nve_run_host_f32(ub200_md *md, float *h_pos4, float *h_vel3, float *h_force4, int N,
                                  const float L[3], float rc, const float *params, int ntypes, float dt,
                                  int nsteps, void *stream);
+/* Observable of a run: kinetic energy sum v^2 / 2 (unit mass, double accumulation, fixed summation order) of d_vel
+ * real3[N], copied asynchronously into *h_out (pinned host memory for a truly asynchronous copy); the value is valid
+ * once the stream has been synchronised. */
+int ub200_md_kinetic_energy_f32(ub200_md *md, const void *d_vel, int N, double *h_out, void *stream);
 struct ub200_ljengine *ub200_md_engine(ub200_md *md); /* the pair-force engine the fused loop drives (declared below) */
 /* ------------------------------------------------------------------------------------------------
  * Path 2: FFT-based hydrodynamics. Precision is chosen at create time (precisionBytes = 4 | 8, the

@@ -50,6 +50,7 @@ static int check(ColGrid g, int TZ) {
           const ColRow row = columnRow(g, x0, y0, z0, 5 * (hz + 2) + 2);
           const int cc = x0 + g.nx * (y0 + g.ny * (z0 + hz));
           const int seg = row.sx[0] < 0 ? 1 : 0;
+          if (seg != row.hs) { bad++; if (bad < 5) fprintf(stderr, "hs mismatch\n"); }
           if (!(cc >= row.c0[seg] && cc < row.c0[seg] + row.n[seg] && row.sx[seg] == 0 && row.sy == 0 && row.sz == 0)) {
             if (bad < 5) fprintf(stderr, "home cell not in segment %d: grid %dx%dx%d col (%d,%d,%d) hz %d\n", seg, g.nx, g.ny, g.nz, x0, y0, z0, hz);
             bad++;
@@ -64,7 +65,8 @@ int main() {
   const int dims[][3] = {{5, 5, 5}, {6, 5, 7}, {8, 9, 13}, {12, 7, 6}, {5, 11, 20}, {1, 5, 9}, {3, 2, 1}, {16, 16, 1}, {7, 1, 4}};
   for (auto &d : dims)
     for (int per = 0; per < 8; per++) {
-      ColGrid g{d[0], d[1], d[2], per & 1, (per >> 1) & 1, (per >> 2) & 1};
+      const int pp[3] = {per & 1, (per >> 1) & 1, (per >> 2) & 1};
+      ColGrid g = makeWholeColGrid(d, pp);
       if ((g.px && g.nx < 5) || (g.py && g.ny < 5) || (g.pz && g.nz < 5)) continue; // callers never build such grids
       for (int TZ : {1, 4, 6, 8}) { bad += check(g, TZ); grids++; }
     }

@@ -57,6 +57,7 @@ def _declare(lib):
         "ub200_md_create": (i, [C.POINTER(vp)]),
         "ub200_md_destroy": (i, [vp]),
         "ub200_md_engine": (vp, [vp]),
+        "ub200_md_kinetic_energy_f32": (i, [vp, vp, i, vp, vp]),
         "ub200_ljengine_create": (i, [C.POINTER(vp)]),
         "ub200_ljengine_destroy": (i, [vp]),
         "ub200_ljengine_sum_f32": (i, [vp, vp, vp, i, _F3, _I3, fp, i, vp, vp, vp, vp, i, i, i, vp]),

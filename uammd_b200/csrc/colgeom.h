@@ -9,6 +9,12 @@
 // staged plane by plane: plane p (z = z0 - 2 + p) holds the 5 rows y = y0 - 2 .. y0 + 2, and a row is the x-run
 // x0 - 2 .. x0 + 2, which is contiguous in the sorted arrays (two pieces when it crosses the periodic boundary).
 // With that order the neighbourhood of home cell hz is the contiguous range of planes hz .. hz + 4.
+//
+// Windows (multi-GPU bricks). A rank of the brick decomposition bins its owned particles and ghosts on a WINDOW of the
+// global half-cell grid: local cell l of a windowed dimension is global cell (o + l) mod g, the local grid is not
+// periodic in that dimension, and a neighbour reached across the global periodic boundary carries the image shift
+// floor((o + l) / g) - floor((o + l_home) / g) - exactly the shift the single-GPU traversal applies, so that both
+// evaluate bit-identical separations. A dimension that is not decomposed is "whole": o = 0, g = n, periodic or not.
 #pragma once
 
 #ifdef __CUDACC__
@@ -20,31 +26,49 @@
 namespace ub200 {
 
 struct ColGrid {
-  int nx, ny, nz;       // half cells per dimension
-  int px, py, pz;       // periodic flags
+  int nx, ny, nz;       // (local) half cells per dimension
+  int px, py, pz;       // the local grid wraps in this dimension (whole periodic dimension)
+  int ox, oy, oz;       // global index of local cell 0 (0 for a whole dimension; may be negative for a window)
+  int gx, gy, gz;       // half cells of the global grid (= n for a whole dimension)
+  int wx, wy, wz;       // windowed dimension: local cells 0, 1 and n - 2, n - 1 are the ghost layers of a brick
 };
 
-// One staged row: up to two x segments of consecutive cells. c0[s] = linear index of the first cell, n[s] = number of
-// cells (0 = absent), sx[s] = image shift of the segment in box lengths; sy, sz = image shift of the row.
+inline ColGrid makeWholeColGrid(const int dims[3], const int periodic[3]) {
+  return ColGrid{dims[0], dims[1], dims[2], periodic[0], periodic[1], periodic[2], 0, 0, 0, dims[0], dims[1], dims[2], 0, 0, 0};
+}
+
+// One staged row: up to two x segments of consecutive cells. c0[s] = linear (local) index of the first cell, n[s] =
+// number of cells (0 = absent), sx[s] = image shift of the segment in box lengths; sy, sz = image shift of the row;
+// hs = segment holding the home cell x0 (meaningful for the dy = 0 row of a home plane).
 struct ColRow {
   int c0[2], n[2], sx[2];
-  int sy, sz;
+  int sy, sz, hs;
 };
 
-// v -> wrapped index in [0, n) and the number of box lengths the unwrapped cell lies away (image shift).
-// Returns false when v is outside a non periodic dimension.
-UB200_HD bool colWrap(int v, int n, int periodic, int &w, int &shift) {
-  shift = 0;
+// floor(u / g) without a division for -g <= u < 2 g
+UB200_HD int colFloorDiv(int u, int g) {
+  if (u >= 0) {
+    if (u < g) return 0;
+    if (u < 2 * g) return 1;
+    return u / g;
+  }
+  if (u >= -g) return -1;
+  return -((-u + g - 1) / g);
+}
+
+// Cell v of one dimension (n local cells, wraps locally iff per, window origin o on a global grid of g cells): local
+// index w and image shift floor((o + v) / g). Home cells that are computed always lie in image 0 (a whole dimension has
+// its cells in [0, n); the owned cells of a window are cells of the global grid proper), so the shift is also the
+// shift relative to the home cell. False when v lies outside a non-wrapping grid.
+UB200_HD bool colNeighbour(int v, int n, int per, int o, int g, int &w, int &shift) {
   w = v;
-  if (v >= 0 && v < n) return true;
-  if (!periodic) return false;
-  // one box length away in all but degenerate cases (no division on the common path)
-  if (v < 0) { w = v + n; shift = -1; } else { w = v - n; shift = 1; }
-  if (w >= 0 && w < n) return true;
-  int q = v / n;
-  if (v - q * n < 0) q--; // floor division
-  shift = q;
-  w = v - q * n;
+  shift = 0;
+  if (v < 0 || v >= n) {
+    if (!per) return false;
+    const int q = colFloorDiv(v, n);
+    w = v - q * n;
+  }
+  shift = colFloorDiv(o + v, g);
   return true;
 }
 
@@ -54,18 +78,19 @@ UB200_HD ColRow columnRow(const ColGrid &g, int x0, int y0, int z0, int r) {
   row.c0[0] = row.c0[1] = 0;
   row.n[0] = row.n[1] = 0;
   row.sx[0] = row.sx[1] = 0;
-  row.sy = row.sz = 0;
+  row.sy = row.sz = row.hs = 0;
   const int p = r / 5, dy = r - 5 * p - 2;
   int y, z;
-  if (!colWrap(y0 + dy, g.ny, g.py, y, row.sy)) return row;
-  if (!colWrap(z0 - 2 + p, g.nz, g.pz, z, row.sz)) return row;
+  if (!colNeighbour(y0 + dy, g.ny, g.py, g.oy, g.gy, y, row.sy)) return row;
+  if (!colNeighbour(z0 - 2 + p, g.nz, g.pz, g.oz, g.gz, z, row.sz)) return row;
   const int base = g.nx * (y + g.ny * z);
   const int xa = x0 - 2, xb = x0 + 2;
   if (g.px) {
-    // callers guarantee nx >= 5 in a periodic dimension: at most one wrap
+    // whole periodic dimension (o = 0, g = n >= 5): at most one wrap
     if (xa < 0) {
       row.c0[0] = base + xa + g.nx; row.n[0] = -xa; row.sx[0] = -1;
       row.c0[1] = base;             row.n[1] = xb + 1; row.sx[1] = 0;
+      row.hs = 1;
     } else if (xb >= g.nx) {
       row.c0[0] = base + xa; row.n[0] = g.nx - xa;      row.sx[0] = 0;
       row.c0[1] = base;      row.n[1] = xb - g.nx + 1;  row.sx[1] = 1;
@@ -74,7 +99,15 @@ UB200_HD ColRow columnRow(const ColGrid &g, int x0, int y0, int z0, int r) {
     }
   } else {
     const int a = xa < 0 ? 0 : xa, b = xb >= g.nx ? g.nx - 1 : xb;
-    row.c0[0] = base + a; row.n[0] = b - a + 1;
+    const int qa = colFloorDiv(g.ox + a, g.gx), qb = colFloorDiv(g.ox + b, g.gx);
+    if (qa == qb) {
+      row.c0[0] = base + a; row.n[0] = b - a + 1; row.sx[0] = qa;
+    } else {
+      const int ls = qb * g.gx - g.ox; // first local cell of the upper image
+      row.c0[0] = base + a;  row.n[0] = ls - a;     row.sx[0] = qa;
+      row.c0[1] = base + ls; row.n[1] = b - ls + 1; row.sx[1] = qb;
+      row.hs = x0 >= ls ? 1 : 0;
+    }
   }
   return row;
 }

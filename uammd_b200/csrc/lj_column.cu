@@ -209,8 +209,9 @@ ljColumnTraversal(const float4 *__restrict__ finePos, const int *__restrict__ fi
                   const uint32_t *__restrict__ binStart, ColGrid cg, float Lx, float Ly, float Lz,
                   const LJPar *__restrict__ parTable, int ntypes, float4 *__restrict__ force, float *__restrict__ energy,
                   float *__restrict__ virial, const int *__restrict__ globalIdx, int ownerLo, int ownerHi,
-                  int *__restrict__ errFlag, int *__restrict__ nextColumn) {
+                  const int *__restrict__ ownerHiDev, int *__restrict__ errFlag, int *__restrict__ nextColumn, int widen) {
   __shared__ __align__(16) float4 candAll[kColWarps][kColCap];
+  if (OWNED && ownerHiDev) ownerHi = *ownerHiDev; // multi-GPU bricks: the owned block [0, nOwned) is counted on the device
   __shared__ __align__(8) unsigned long long barAll[kColWarps];
   __shared__ int metaAll[kColWarps][kColMeta];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -240,6 +241,8 @@ ljColumnTraversal(const float4 *__restrict__ finePos, const int *__restrict__ fi
     const int x0 = col % cg.nx, t1 = col / cg.nx, y0 = t1 % cg.ny, z0 = (t1 / cg.ny) * kColTZ;
     const int nHome = min(kColTZ, cg.nz - z0);
     const int nRows = 5 * (nHome + 4);
+    // bricks: the two outer cell layers of a windowed dimension hold ghosts - nothing to compute for them
+    if (OWNED && ownerHiDev && ((cg.wx && (x0 < 2 || x0 >= cg.nx - 2)) || (cg.wy && (y0 < 2 || y0 >= cg.ny - 2)))) continue;
     // ---- two rows per lane: global ranges of the row pieces, image shifts, the home cell of the row (dy == 0 rows)
     int g0[2][2], cn[2][2], shp[2], hG[2], hC[2], hRel[2];
 #pragma unroll
@@ -261,15 +264,16 @@ ljColumnTraversal(const float4 *__restrict__ finePos, const int *__restrict__ fi
         if (r - 5 * p == 2 && p >= 2 && p < 2 + nHome) {
           const int cc = x0 + cg.nx * (y0 + cg.ny * (z0 + p - 2));
           const uint32_t a = __ldg(binStart + cc), b = __ldg(binStart + cc + 1);
+          const bool ghostCell = OWNED && ownerHiDev && cg.wz && (z0 + p - 2 < 2 || z0 + p - 2 >= cg.nz - 2);
           hG[q] = (int)a;
-          hC[q] = (int)(b - a);
-          // the home cell lies in piece 0 unless the row starts on the far side of the periodic boundary
-          hRel[q] = row.sx[0] < 0 ? cn[q][0] + ((int)a - g0[q][1]) : (int)a - g0[q][0];
+          hC[q] = ghostCell ? 0 : (int)(b - a);
+          // offset of the home cell inside its row (piece row.hs)
+          hRel[q] = row.hs ? cn[q][0] + ((int)a - g0[q][1]) : (int)a - g0[q][0];
         }
       }
     }
     if (!__any_sync(0xffffffffu, hC[0] > 0 || hC[1] > 0)) continue; // no home particle in this column
-    if (OWNED) { // multi-GPU owner restriction: skip columns without an owned home particle
+    if (OWNED && !ownerHiDev) { // owner restriction by index range: skip columns without an owned home particle
       bool mine = false;
 #pragma unroll
       for (int q = 0; q < 2; q++)
@@ -387,8 +391,11 @@ ljColumnTraversal(const float4 *__restrict__ finePos, const int *__restrict__ fi
       }
       // Passes of four particles, eight lanes each; the last pass of a column widens to 16 or 32 lanes per particle when
       // only two or one are left.
+      // (widen = 0 keeps eight lanes per particle throughout: the summation order of a particle then depends on its own
+      // neighbourhood only, not on what else shares its column - the multi-GPU bricks rely on it to reproduce the
+      // single-GPU forces bit for bit)
       int q0 = 0;
-      for (; nHomeP - q0 >= 3; q0 += 4)
+      for (; nHomeP - q0 >= (widen ? 3 : 1); q0 += 4)
         columnPass<8, ENERGY, VIRIAL, MULTITYPE, ACCUMULATE, OWNED>(cand, lane, q0, nHomeP, recC0, recC1, recSlot, recGi, parTable,
                                                                     ntypes, par0, fold, force, energy, virial, globalIdx,
                                                                     ownerLo, ownerHi);
@@ -455,10 +462,27 @@ __device__ __forceinline__ void canonicalCoord(float r, float L, float m, float 
   }
 }
 
+// global half cell -> cell of the (windowed) local grid; false when it falls outside the window
+__device__ __forceinline__ bool localCell(int c, int o, int g, int n, bool globallyPeriodic, int &l) {
+  l = c - o;
+  if (globallyPeriodic) {
+    if (l < 0) l += g;
+    else if (l >= g) l -= g;
+  }
+  if ((unsigned)l >= (unsigned)n) {
+    l = min(max(l, 0), n - 1);
+    return false;
+  }
+  return true;
+}
+
+// nDev: optional device-side particle count (multi-GPU bricks: the arrays are sized for the worst case, the count of the
+// step lives on the device); the launch covers N particles and the excess threads leave.
 __global__ void __launch_bounds__(256)
-fineBin(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, GridF g,
-        uint32_t *__restrict__ binCount, uint2 *__restrict__ codeSlot, int *__restrict__ errorFlag) {
+fineBin(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, const int *__restrict__ nDev, GridF g,
+        ColGrid cg, uint32_t *__restrict__ binCount, uint2 *__restrict__ codeSlot, int *__restrict__ errorFlag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nDev) N = min(N, *nDev);
   if (i >= N) return;
   const float4 p = ldg4(pos + (groupIdx ? groupIdx[i] : i));
   int cx, cy, cz;
@@ -468,7 +492,11 @@ fineBin(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N,
   canonicalCoord(p.y, g.Ly, g.my, g.hLy, g.iy, g.ny, cy, y, bad);
   canonicalCoord(p.z, g.Lz, g.mz, g.hLz, g.iz, g.nz, cz, z, bad);
   if (bad) *errorFlag = 1;
-  const uint32_t cell = (uint32_t)(cx + g.nx * (cy + g.ny * cz));
+  int lx, ly, lz;
+  const bool in = localCell(cx, cg.ox, cg.gx, cg.nx, g.mx != 0.0f, lx) & localCell(cy, cg.oy, cg.gy, cg.ny, g.my != 0.0f, ly) &
+                  localCell(cz, cg.oz, cg.gz, cg.nz, g.mz != 0.0f, lz);
+  if (!in) *errorFlag = 3; // a particle outside the rank's window: the halo exchange missed it
+  const uint32_t cell = (uint32_t)(lx + cg.nx * (ly + cg.ny * lz));
   const unsigned active = __activemask();
   const unsigned peers = __match_any_sync(active, cell);
   const int lane = threadIdx.x & 31;
@@ -481,16 +509,34 @@ fineBin(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N,
 }
 
 __global__ void __launch_bounds__(256)
+fineScatter(const uint2 *__restrict__ codeSlot, const uint32_t *__restrict__ binStart, int N, const int *__restrict__ nDev,
+            int *__restrict__ unstable) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nDev) N = min(N, *nDev);
+  if (i >= N) return;
+  const uint2 cs = codeSlot[i];
+  unstable[binStart[cs.x] + cs.y] = i;
+}
+
+// sortKey: optional per-particle key deciding the order inside a cell (multi-GPU bricks pass the global particle ids, so
+// that every cell lists its particles in the single-GPU order whatever the order of the local arrays); default: the index.
+__global__ void __launch_bounds__(256)
 fineOrder(const int *__restrict__ unstable, const uint2 *__restrict__ codeSlot, const uint32_t *__restrict__ binStart,
-          const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, GridF g, float4 *__restrict__ finePos,
-          int *__restrict__ fineIdx) {
+          const float4 *__restrict__ pos, const int *__restrict__ groupIdx, const int *__restrict__ sortKey, int N,
+          const int *__restrict__ nDev, GridF g, float4 *__restrict__ finePos, int *__restrict__ fineIdx) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nDev) N = min(N, *nDev);
   if (k >= N) return;
   const int i = unstable[k];
   const uint32_t cell = codeSlot[i].x;
   const int s = (int)binStart[cell], e = (int)binStart[cell + 1];
   int rank = 0;
-  for (int j = s; j < e; j++) rank += (__ldg(unstable + j) < i);
+  if (sortKey) {
+    const int ki = sortKey[i];
+    for (int j = s; j < e; j++) rank += (sortKey[__ldg(unstable + j)] < ki);
+  } else {
+    for (int j = s; j < e; j++) rank += (__ldg(unstable + j) < i);
+  }
   const float4 p = ldg4(pos + (groupIdx ? groupIdx[i] : i));
   int c;
   bool bad = false;
@@ -504,7 +550,7 @@ fineOrder(const int *__restrict__ unstable, const uint2 *__restrict__ codeSlot, 
 }
 
 // half-cell grid for this box and cut-off; false when the column traversal does not apply
-static bool fineDims(const float L[3], const int periodic[3], float rc, int dims[3], int per[3]) {
+bool ljEngineDims(const float L[3], const int periodic[3], float rc, int dims[3], int per[3]) {
   double cells = 1.0;
   for (int d = 0; d < 3; d++) {
     if (isinf(L[d]) || isnan(L[d]) || L[d] < 0.0f) return false;
@@ -516,10 +562,12 @@ static bool fineDims(const float L[3], const int periodic[3], float rc, int dims
   return cells <= (double)(1 << 24);
 }
 
-static int buildFine(ub200_ljengine *e, const float4 *pos, const int *groupIdx, int N, const float L[3], const int per[3],
-                     const int dims[3], cudaStream_t st) {
+// pos [N] (N = launch bound; nDev = optional device-side count <= N), binned on the window cg of the global half-cell
+// grid `dims` (a whole grid for single-GPU use)
+static int buildFine(ub200_ljengine *e, const float4 *pos, const int *groupIdx, const int *sortKey, int N, const int *nDev,
+                     const float L[3], const int per[3], const int dims[3], const ColGrid &cg, cudaStream_t st) {
   const GridF g = makeGridF(L, per, dims);
-  const int ncells = dims[0] * dims[1] * dims[2];
+  const int ncells = cg.nx * cg.ny * cg.nz;
   int rc;
   if ((rc = e->pos.reserve(sizeof(float4) * (size_t)N))) return rc;
   if ((rc = e->idx.reserve(sizeof(int) * (size_t)N))) return rc;
@@ -538,24 +586,26 @@ static int buildFine(ub200_ljengine *e, const float4 *pos, const int *groupIdx, 
     e->binCells = ncells;
   }
   e->grid = g;
-  e->cg = ColGrid{dims[0], dims[1], dims[2], per[0], per[1], per[2]};
+  e->cg = cg;
   e->N = N;
   e->ncells = ncells;
   const int nb = (N + 255) / 256;
-  fineBin<<<nb, 256, 0, st>>>(pos, groupIdx, N, g, e->binCount.as<uint32_t>(), e->codeSlot.as<uint2>(), e->errorFlag.as<int>());
+  fineBin<<<nb, 256, 0, st>>>(pos, groupIdx, N, nDev, g, cg, e->binCount.as<uint32_t>(), e->codeSlot.as<uint2>(),
+                              e->errorFlag.as<int>());
   UB200_LAUNCHED();
   if ((rc = exclusiveScanAndClear(e->binCount.as<uint32_t>(), ncells, e->binStart.as<uint32_t>(), e->blockSums.as<uint32_t>(), st)))
     return rc;
-  if ((rc = scatterToBinsLaunch(e->codeSlot.as<uint2>(), e->binStart.as<uint32_t>(), N, e->unstable.as<int>(), st))) return rc;
-  fineOrder<<<nb, 256, 0, st>>>(e->unstable.as<int>(), e->codeSlot.as<uint2>(), e->binStart.as<uint32_t>(), pos, groupIdx, N, g,
-                                e->pos.as<float4>(), e->idx.as<int>());
+  fineScatter<<<nb, 256, 0, st>>>(e->codeSlot.as<uint2>(), e->binStart.as<uint32_t>(), N, nDev, e->unstable.as<int>());
+  UB200_LAUNCHED();
+  fineOrder<<<nb, 256, 0, st>>>(e->unstable.as<int>(), e->codeSlot.as<uint2>(), e->binStart.as<uint32_t>(), pos, groupIdx, sortKey,
+                                N, nDev, g, e->pos.as<float4>(), e->idx.as<int>());
   UB200_LAUNCHED();
   return UB200_OK;
 }
 
 template <bool E, bool V, bool M, bool A, bool O, bool T>
 static int launchColumnT(ub200_ljengine *e, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
-                        const int *globalIdx, int ownerLo, int ownerHi, cudaStream_t st) {
+                        const int *globalIdx, int ownerLo, int ownerHi, const int *ownerHiDev, cudaStream_t st) {
   auto kern = ljColumnTraversal<E, V, M, A, O, T>;
   static int blocksPerSM = 0; // per instantiation
   if (!blocksPerSM) {
@@ -564,6 +614,8 @@ static int launchColumnT(ub200_ljengine *e, const LJPar *table, int ntypes, floa
     if (blocksPerSM < 1) blocksPerSM = 1;
   }
   const ColGrid &cg = e->cg;
+  const char *wsel = getenv("UB200_LJ_WIDEN"); // "0": eight lanes per particle in every pass (decomposition-independent sums)
+  const int widen = ownerHiDev ? 0 : !(wsel && wsel[0] == '0');
   const int ncols = cg.nx * cg.ny * ((cg.nz + kColTZ - 1) / kColTZ);
   int grid = kNumSMs * blocksPerSM;
   const int needed = (ncols + kColWarps - 1) / kColWarps;
@@ -571,7 +623,7 @@ static int launchColumnT(ub200_ljengine *e, const LJPar *table, int ntypes, floa
   UB200_CUDA(cudaMemsetAsync(e->errorFlag.as<int>() + 1, 0, sizeof(int), st)); // the column counter
   kern<<<grid, kColThreads, 0, st>>>(e->pos.as<float4>(), e->idx.as<int>(), e->binStart.as<uint32_t>(), cg, e->grid.Lx,
                                      e->grid.Ly, e->grid.Lz, table, ntypes, force, energy, virial, globalIdx, ownerLo,
-                                     ownerHi, e->errorFlag.as<int>(), e->errorFlag.as<int>() + 1);
+                                     ownerHi, ownerHiDev, e->errorFlag.as<int>(), e->errorFlag.as<int>() + 1, widen);
   UB200_LAUNCHED();
   return UB200_OK;
 }
@@ -579,20 +631,21 @@ static int launchColumnT(ub200_ljengine *e, const LJPar *table, int ntypes, floa
 // staging of the column halo: TMA bulk copies (default) or per-lane row copies (UB200_LJ_STAGE=ldg), same results
 template <bool E, bool V, bool M, bool A, bool O>
 static int launchColumn(ub200_ljengine *e, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
-                        const int *globalIdx, int ownerLo, int ownerHi, cudaStream_t st) {
+                        const int *globalIdx, int ownerLo, int ownerHi, const int *ownerHiDev, cudaStream_t st) {
   const char *sel = getenv("UB200_LJ_STAGE");
   if (sel && strcmp(sel, "ldg") == 0)
-    return launchColumnT<E, V, M, A, O, false>(e, table, ntypes, force, energy, virial, globalIdx, ownerLo, ownerHi, st);
-  return launchColumnT<E, V, M, A, O, true>(e, table, ntypes, force, energy, virial, globalIdx, ownerLo, ownerHi, st);
+    return launchColumnT<E, V, M, A, O, false>(e, table, ntypes, force, energy, virial, globalIdx, ownerLo, ownerHi, ownerHiDev, st);
+  return launchColumnT<E, V, M, A, O, true>(e, table, ntypes, force, energy, virial, globalIdx, ownerLo, ownerHi, ownerHiDev, st);
 }
 
 static int columnSum(ub200_ljengine *e, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
-                     const int *globalIdx, bool accumulate, int ownerLo, int ownerHi, cudaStream_t st) {
-  const bool E = energy != nullptr, V = virial != nullptr, M = ntypes > 1, O = ownerLo > 0 || ownerHi < 0x7fffffff;
+                     const int *globalIdx, bool accumulate, int ownerLo, int ownerHi, cudaStream_t st,
+                     const int *ownerHiDev = nullptr) {
+  const bool E = energy != nullptr, V = virial != nullptr, M = ntypes > 1, O = ownerLo > 0 || ownerHi < 0x7fffffff || ownerHiDev;
   const bool A = accumulate;
 #define UB200_COL(ee, vv, mm, aa, oo)                                                                                   \
   if (E == ee && V == vv && M == mm && A == aa && O == oo)                                                              \
-    return launchColumn<ee, vv, mm, aa, oo>(e, table, ntypes, force, energy, virial, globalIdx, ownerLo, ownerHi, st);
+    return launchColumn<ee, vv, mm, aa, oo>(e, table, ntypes, force, energy, virial, globalIdx, ownerLo, ownerHi, ownerHiDev, st);
   // forces only: every combination of multi-type / accumulate / owner restriction
   UB200_COL(false, false, false, false, false) UB200_COL(false, false, false, true, false)
   UB200_COL(false, false, true, false, false) UB200_COL(false, false, true, true, false)
@@ -603,14 +656,40 @@ static int columnSum(ub200_ljengine *e, const LJPar *table, int ntypes, float4 *
   if (!A || O) return UB200_ERR_UNSUPPORTED;
 #define UB200_COL_EV(mm)                                                                                                \
   if (M == mm) {                                                                                                        \
-    if (E && V) return launchColumn<true, true, mm, true, false>(e, table, ntypes, force, energy, virial, globalIdx, 0, 0x7fffffff, st); \
-    if (E) return launchColumn<true, false, mm, true, false>(e, table, ntypes, force, energy, virial, globalIdx, 0, 0x7fffffff, st);     \
-    return launchColumn<false, true, mm, true, false>(e, table, ntypes, force, energy, virial, globalIdx, 0, 0x7fffffff, st);            \
+    if (E && V) return launchColumn<true, true, mm, true, false>(e, table, ntypes, force, energy, virial, globalIdx, 0, 0x7fffffff, nullptr, st); \
+    if (E) return launchColumn<true, false, mm, true, false>(e, table, ntypes, force, energy, virial, globalIdx, 0, 0x7fffffff, nullptr, st);     \
+    return launchColumn<false, true, mm, true, false>(e, table, ntypes, force, energy, virial, globalIdx, 0, 0x7fffffff, nullptr, st);            \
   }
   UB200_COL_EV(false)
   UB200_COL_EV(true)
 #undef UB200_COL_EV
   return UB200_ERR_UNSUPPORTED;
+}
+
+static int uploadTable(ub200_ljengine *e, const float *params, int ntypes, cudaStream_t st) {
+  const size_t n = (size_t)ntypes * ntypes * 4;
+  LJTableCache *cache = &e->table;
+  if (cache->host.size() != n || memcmp(cache->host.data(), params, n * sizeof(float)) != 0) {
+    if (const int rc = cache->dev.reserve(n * sizeof(float))) return rc;
+    cache->host.assign(params, params + n);
+    UB200_CUDA(cudaMemcpyAsync(cache->dev.p, cache->host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  return UB200_OK;
+}
+
+// Multi-GPU bricks: forces of the owned block [0, *nOwnedDev) of a rank's local arrays [owned | ghosts] (*nLocalDev
+// particles, at most maxN), binned on the rank's window cg of the global half-cell grid globalDims. sortKey = global ids.
+int ljEngineBuildWindow(ub200_ljengine *e, const float4 *pos, const int *sortKey, int maxN, const int *nLocalDev,
+                        const float L[3], const int periodic[3], const int globalDims[3], const ColGrid &cg, cudaStream_t st) {
+  if (!e || !pos || maxN <= 0 || !nLocalDev) return UB200_ERR_INVALID_ARGUMENT;
+  return buildFine(e, pos, nullptr, sortKey, maxN, nLocalDev, L, periodic, globalDims, cg, st);
+}
+int ljEngineTraverseWindow(ub200_ljengine *e, const int *nOwnedDev, const float *params, int ntypes, float4 *force,
+                           bool accumulate, cudaStream_t st) {
+  if (!e || !nOwnedDev || !params || ntypes < 1 || !force) return UB200_ERR_INVALID_ARGUMENT;
+  if (const int rcode = uploadTable(e, params, ntypes, st)) return rcode;
+  e->lastPath = 0;
+  return columnSum(e, e->table.dev.as<LJPar>(), ntypes, force, nullptr, nullptr, nullptr, accumulate, 0, 0x7fffffff, st, nOwnedDev);
 }
 
 int ljEngineSum(ub200_ljengine *e, const float4 *pos, const int *groupIdx, int N, const float L[3], const int periodic[3],
@@ -636,16 +715,10 @@ int ljEngineSum(ub200_ljengine *e, const float4 *pos, const int *groupIdx, int N
   int dims[3], per[3];
   const char *sel = getenv("UB200_LJ_ENGINE"); // "cell" forces the reference-layout traversal (A/B runs, tests)
   const bool wantColumn = !(sel && strcmp(sel, "cell") == 0);
-  if (wantColumn && fineDims(L, periodic, rc, dims, per)) {
-    // upload of the parameter table shared with the cell traversal
-    const size_t n = (size_t)ntypes * ntypes * 4;
+  if (wantColumn && ljEngineDims(L, periodic, rc, dims, per)) {
+    if ((rcode = uploadTable(e, params, ntypes, st))) return rcode;
     LJTableCache *cache = &e->table;
-    if (cache->host.size() != n || memcmp(cache->host.data(), params, n * sizeof(float)) != 0) {
-      if ((rcode = cache->dev.reserve(n * sizeof(float)))) return rcode;
-      cache->host.assign(params, params + n);
-      UB200_CUDA(cudaMemcpyAsync(cache->dev.p, cache->host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-    }
-    if ((rcode = buildFine(e, pos, groupIdx, N, L, per, dims, st))) return rcode;
+    if ((rcode = buildFine(e, pos, groupIdx, nullptr, N, nullptr, L, per, dims, makeWholeColGrid(dims, per), st))) return rcode;
     e->lastPath = 0;
     return columnSum(e, cache->dev.as<LJPar>(), ntypes, force, energy, virial, globalIdx, accumulate, ownerLo, ownerHi, st);
   }

@@ -22,4 +22,12 @@ namespace ub200 {
 int ljEngineSum(ub200_ljengine *e, const float4 *pos, const int *groupIdx, int N, const float L[3], const int periodic[3],
                 const float *params, int ntypes, float4 *force, float *energy, float *virial, const int *globalIdx,
                 bool accumulate, int ownerLo, int ownerHi, cudaStream_t st);
+// multi-GPU bricks (brick_md.cu): list of a rank's local arrays [owned | ghosts] (*nLocalDev particles, at most maxN) on its
+// window cg of the global half-cell grid, cells ordered by sortKey (global ids); then the forces of the owned block
+int ljEngineBuildWindow(ub200_ljengine *e, const float4 *pos, const int *sortKey, int maxN, const int *nLocalDev,
+                        const float L[3], const int periodic[3], const int globalDims[3], const ColGrid &cg, cudaStream_t st);
+int ljEngineTraverseWindow(ub200_ljengine *e, const int *nOwnedDev, const float *params, int ntypes, float4 *force,
+                           bool accumulate, cudaStream_t st);
+// half cells per dimension for this box and cut-off; false when the column traversal does not apply
+bool ljEngineDims(const float L[3], const int periodic[3], float rc, int dims[3], int per[3]);
 } // namespace ub200

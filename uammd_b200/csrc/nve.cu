@@ -54,6 +54,35 @@ nveKickKickDrift(float4 *__restrict__ pos, float *__restrict__ vel, const float4
   pos[i] = p;
 }
 
+// sum of m v^2 / 2 (unit mass) in double: per-block partial sums, then one block adds them up (deterministic order)
+__global__ void __launch_bounds__(256) kineticPartial(const float *__restrict__ vel, int N, double *__restrict__ partial) {
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const float x = vel[3 * (size_t)i], y = vel[3 * (size_t)i + 1], z = vel[3 * (size_t)i + 2];
+    s += (double)x * x + (double)y * y + (double)z * z;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) kineticFinal(const double *__restrict__ partial, int n, double *__restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = 0.5 * sh[0];
+}
+
 } // namespace ub200
 
 using namespace ub200;
@@ -61,6 +90,7 @@ using namespace ub200;
 struct ub200_md {
   ub200_ljengine *eng = nullptr; // PairForces<LJ, CellList>::sum: private half-cell list + column traversal (lj_column.cu)
   DevBuf dpos, dvel, dforce; // device state for the host-buffer entry point
+  DevBuf keScratch;                  // kinetic energy: per-block partial sums + the result
   cudaStream_t copyStream = nullptr; // host-buffer entry point: transfers overlapped with the force evaluations
   cudaEvent_t evPosUp = nullptr, evVelUp = nullptr, evDrift = nullptr, evPosDown = nullptr;
 };
@@ -103,7 +133,7 @@ int ub200_md_create(ub200_md **out) {
 int ub200_md_destroy(ub200_md *md) {
   if (!md) return UB200_OK;
   ub200_ljengine_destroy(md->eng);
-  md->dpos.release(); md->dvel.release(); md->dforce.release();
+  md->dpos.release(); md->dvel.release(); md->dforce.release(); md->keScratch.release();
   if (md->copyStream) {
     cudaStreamDestroy(md->copyStream);
     cudaEventDestroy(md->evPosUp); cudaEventDestroy(md->evVelUp); cudaEventDestroy(md->evDrift); cudaEventDestroy(md->evPosDown);
@@ -113,6 +143,20 @@ int ub200_md_destroy(ub200_md *md) {
 }
 
 ub200_ljengine *ub200_md_engine(ub200_md *md) { return md ? md->eng : nullptr; }
+
+int ub200_md_kinetic_energy_f32(ub200_md *md, const void *d_vel, int N, double *h_out, void *stream) {
+  if (!md || !d_vel || N <= 0 || !h_out) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = 2 * kNumSMs;
+  if (const int e = md->keScratch.reserve(sizeof(double) * (nb + 1))) return e;
+  double *part = md->keScratch.as<double>();
+  kineticPartial<<<nb, 256, 0, st>>>((const float *)d_vel, N, part + 1);
+  UB200_LAUNCHED();
+  kineticFinal<<<1, 256, 0, st>>>(part + 1, nb, part);
+  UB200_LAUNCHED();
+  UB200_CUDA(cudaMemcpyAsync(h_out, part, sizeof(double), cudaMemcpyDeviceToHost, st));
+  return UB200_OK;
+}
 
 static int mdForces(ub200_md *md, void *d_pos, void *d_force, int N, const float L[3], float rc, const float *params,
                     int ntypes, cudaStream_t st) {

@@ -467,6 +467,11 @@ class LJMD:
                                                  f3(self.box.boxSize), self.pot.getCutOff(), self._tabp,
                                                  self.pot.ntypes, self.dt, int(nsteps), _stream_ptr(stream)))
 
+    def kineticEnergy(self, vel, out, index=0, stream=None):
+        """sum v^2 / 2 of vel [N,3] -> out[index] (a pinned float64 host tensor), asynchronously on the stream."""
+        check(_lib.lib().ub200_md_kinetic_energy_f32(self._h, _ptr(vel), vel.shape[0], C.c_void_p(out.data_ptr() + 8 * index),
+                                                     _stream_ptr(stream)))
+
     def runVerlet(self, nl, pos, vel, force, nsteps, forcesAreCurrent=False, stream=None):
         """The same loop over PairForces<LJ, VerletList> (nl: VerletList)."""
         lib = _declare_verlet()
