@@ -18,6 +18,14 @@
  *   uammd::b200::BDEulerMaruyama  Integrator = BD::EulerMaruyama (Integrator/BrownianDynamics.cuh:111-126).
  *   uammd::b200::FCM<Kernel>      BDHI Method concept (Integrator/BDHI/BDHI_FCM.cuh:85-153) for
  *                                 BDHI::EulerMaruyama<Method> (Integrator/BDHI/BDHI_EulerMaruyama.cuh:64-98).
+ *   uammd::b200::FCM_impl<K, KT>  the class the reference's own tests drive (Integrator/BDHI/FCM/FCM_impl.cuh:36-129):
+ *                                 same Parameters, computeHydrodynamicDisplacements returns the reference's pair of
+ *                                 cached vectors (linear, angular).
+ *   uammd::b200::IBM<Kernel>      spread / gather of misc/IBM.cuh:99-203 for the Peskin and Gaussian windows.
+ *   uammd::b200::DPDPotential     Potential::DPD plus the getTransverser PairForces looks for (the stock class only has
+ *                                 the pre-v2 getForceTransverser and is silently skipped): drops into
+ *                                 PairForces<b200::DPDPotential, AnyNeighbourList>.
+ *   uammd::b200::PairForcesDPD    Interactor = PairForces<Potential::DPD, CellList> with the specialised DPD traversal.
  * Error codes of the C ABI are converted into the reference's exception convention (std::runtime_error).
  */
 #ifndef UAMMD_B200_GLUE_CUH
@@ -30,6 +38,12 @@
 #include "Interactor/Potential/Potential.cuh"
 #include "Integrator/BDHI/BDHI.cuh"
 #include "Integrator/BDHI/FCM/FCM_kernels.cuh"
+#include "Integrator/BDHI/FCM/utils.cuh"
+#include "Interactor/Potential/DPD.cuh"
+#include "misc/IBM_kernels.cuh"
+#include <thrust/device_vector.h>
+#include <thrust/transform.h>
+#include <thrust/iterator/counting_iterator.h>
 #include "../uammd_b200.h"
 #include <cmath>
 #include <limits>
@@ -245,10 +259,24 @@ public:
 };
 
 class PairForcesLJ : public Interactor {
-  shared_ptr<CellList> nl;
+  shared_ptr<CellList> nl;   // when set, the reference-layout cell list is built and traversed (users reading getNeighbourList())
   shared_ptr<VerletList> vl; // when set, the Verlet list is the neighbour list (PairForces<LJ, VerletList>)
   shared_ptr<LJ> pot;
   Box box;
+  ub200_ljengine *engine = nullptr; // default: the engine's own half-cell list + column traversal (ub200_ljengine_sum_f32)
+  std::vector<float> hostTable;     // host copy of the pair parameters, refreshed when the potential's table changes size
+  const void *hostTableSource = nullptr;
+
+  const std::vector<float> &tableOnHost(const LJ::DeviceTable &table, cudaStream_t st) {
+    const size_t n = (size_t)table.ntypes * table.ntypes * 4;
+    if (hostTable.size() != n or hostTableSource != table.d_params) {
+      hostTable.resize(n);
+      CudaSafeCall(cudaMemcpyAsync(hostTable.data(), table.d_params, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CudaSafeCall(cudaStreamSynchronize(st));
+      hostTableSource = table.d_params;
+    }
+    return hostTable;
+  }
 
 public:
   struct Parameters {
@@ -260,14 +288,32 @@ public:
       : PairForcesLJ(std::make_shared<ParticleGroup>(pd, "All"), par, pot) {}
   PairForcesLJ(shared_ptr<ParticleGroup> pg, Parameters par, shared_ptr<LJ> pot)
       : Interactor(pg, "b200::PairForcesLJ"), nl(par.nl), vl(par.verletList), pot(pot), box(par.box) {
-    if (!nl and !vl) nl = std::make_shared<CellList>(pg);
+    if (!nl and !vl) check(ub200_ljengine_create(&engine), "ljengine_create");
   }
+  ~PairForcesLJ() { ub200_ljengine_destroy(engine); }
+  /* setPotParameters after the first sum(): call this so that the host copy of the table is fetched again */
+  void parametersChanged() { hostTableSource = nullptr; }
 
   void updateBox(Box newBox) override { box = newBox; }
 
   /* Interactor::sum: accumulates into pd's force / energy / virial like Radial::Transverser::set */
   void sum(Computables comp, cudaStream_t st = 0) override {
     const real rcut = pot->getCutOff();
+    if (engine) { // neighbour search, traversal and the NBody fallback in one call
+      auto force = comp.force ? pd->getForce(access::location::gpu, access::mode::readwrite).raw() : nullptr;
+      auto energy = comp.energy ? pd->getEnergy(access::location::gpu, access::mode::readwrite).raw() : nullptr;
+      auto virial = comp.virial ? pd->getVirial(access::location::gpu, access::mode::readwrite).raw() : nullptr;
+      auto pos = pd->getPos(access::location::gpu, access::mode::read);
+      const int *gidx = pg->getIndicesRawPtr(access::location::gpu);
+      const auto table = pot->getDeviceTable();
+      const auto &host = tableOnHost(table, st);
+      const float L[3] = {(float)box.boxSize.x, (float)box.boxSize.y, (float)box.boxSize.z};
+      const int periodic[3] = {box.isPeriodicX(), box.isPeriodicY(), box.isPeriodicZ()};
+      check(ub200_ljengine_sum_f32(engine, pos.raw(), gidx, pg->getNumberParticles(), L, periodic, host.data(), table.ntypes, force,
+                                   energy, virial, gidx, 1, 0, 0x7fffffff, (void *)st),
+            "ljengine_sum");
+      return;
+    }
     // PairForces.cu:49-53: a box no larger than 3 cut-offs in every dimension takes the all-pairs NBody path
     const bool nbody = box.boxSize.x <= 3 * rcut and box.boxSize.y <= 3 * rcut and box.boxSize.z <= 3 * rcut;
     if (!nbody) {
@@ -302,6 +348,71 @@ public:
     check(ub200_lj_sum_devparams_f32(nl->getHandle(), table.d_params, table.ntypes, force, energy, virial, gidx,
                                      (void *)st),
           "lj_sum");
+  }
+  shared_ptr<CellList> getNeighbourList() { return nl; }
+};
+
+/* ---------------------------------------------------------------- DPD --------------------------------------- */
+/* Potential::DPD (Interactor/Potential/DPD.cuh:40-180) with the method PairForces looks for. At this commit the stock class
+   only exposes getForceTransverser(box, pd); Potential::has_getTransverser<Potential::DPD> is false and
+   PairForces<Potential::DPD> silently sums a null transverser. The arithmetic - ForceTransverser::{getInfo,
+   compute, set}, :92-159 - is the reference's own, untouched. */
+class DPDPotential : public Potential::DPD {
+public:
+  using Potential::DPD::DPD;
+  auto getTransverser(Interactor::Computables comp, Box box, shared_ptr<ParticleData> pd) {
+    return this->getForceTransverser(box, pd);
+  }
+  /* what the specialised traversal needs; advance() increments the step like getForceTransverser does (:165) */
+  struct Step {
+    real rcut, gamma, sigma, A;
+    int step;
+  };
+  Step advance() {
+    step++;
+    return {rcut, gamma.gamma, sigma, A, step};
+  }
+};
+static_assert(Potential::has_getTransverser<DPDPotential>::value, "PairForces does not see b200::DPDPotential's transverser");
+
+/* Interactor = PairForces<Potential::DPD, CellList> (Interactor/PairForces.cu:43-78) with the specialised traversal
+   (ub200_dpd_sum_f32: cell blocks staged once, Saru / Box-Muller body on full warps). The Saru seed of the reference is a
+   function-local static of getForceTransverser (DPD.cuh:165) and cannot be read: this class draws its own from the system
+   generator, once, like the reference does. */
+class PairForcesDPD : public Interactor {
+  shared_ptr<CellList> nl;
+  shared_ptr<DPDPotential> pot;
+  Box box;
+  uint seed;
+
+public:
+  struct Parameters {
+    Box box = Box(std::numeric_limits<real>::infinity());
+    shared_ptr<CellList> nl = nullptr;
+  };
+  PairForcesDPD(shared_ptr<ParticleData> pd, Parameters par, shared_ptr<DPDPotential> pot)
+      : PairForcesDPD(std::make_shared<ParticleGroup>(pd, "All"), par, pot) {}
+  PairForcesDPD(shared_ptr<ParticleGroup> pg, Parameters par, shared_ptr<DPDPotential> pot)
+      : Interactor(pg, "b200::PairForcesDPD"), nl(par.nl), pot(pot), box(par.box) {
+    if (!nl) nl = std::make_shared<CellList>(pg);
+    seed = (uint)sys->rng().next(); /* Saru takes 32-bit seeds: the reference's 64-bit draw is truncated the same way */
+  }
+  void updateBox(Box newBox) override { box = newBox; }
+  void updateTemperature(real T) override { pot->updateTemperature(T); }
+  void updateTimeStep(real dt) override { pot->updateTimeStep(dt); }
+  void setSeed(uint s) { seed = s; }
+  uint getSeed() const { return seed; }
+
+  void sum(Computables comp, cudaStream_t st = 0) override {
+    if (!comp.force) return; /* no energy in DPD (DPD.cuh:172-180) */
+    nl->update(box, pot->getCutOff(), st);
+    const auto p = pot->advance();
+    auto vel = pd->getVel(access::location::gpu, access::mode::read);
+    auto force = pd->getForce(access::location::gpu, access::mode::readwrite);
+    const int *gidx = pg->getIndicesRawPtr(access::location::gpu);
+    check(ub200_dpd_sum_f32(nl->getHandle(), vel.raw(), p.A, p.gamma, p.sigma, p.rcut, seed, (uint)p.step, pd->getNumParticles(),
+                            force.raw(), gidx, (void *)st),
+          "dpd_sum");
   }
   shared_ptr<CellList> getNeighbourList() { return nl; }
 };
@@ -342,6 +453,175 @@ template <> struct KernelDescriptor<BDHI::FCM_ns::Kernels::Gaussian> {
   static real radius(real h, real tolerance) { return h * upsampling(tolerance) * std::sqrt(M_PI); }
 };
 } // namespace detail
+
+/* descriptor of a kernel INSTANCE (FCM_impl / IBM receive the objects the caller built). The Gaussians keep width and
+   prefactor private: prefactor = phi(0), tau = log(phi(r)/phi(0)) / r^2 from two host evaluations of their own phi. */
+inline ub200_ibm_kernel describeKernel(const BDHI::FCM_ns::Kernels::Peskin::threePoint &, real h) {
+  return {UB200_KERNEL_PESKIN3, 3, (double)h, 0, 0, 0};
+}
+inline ub200_ibm_kernel describeKernel(const BDHI::FCM_ns::Kernels::Peskin::fourPoint &, real h) {
+  return {UB200_KERNEL_PESKIN4, 4, (double)h, 0, 0, 0};
+}
+inline ub200_ibm_kernel describeKernel(const IBM_kernels::Peskin::threePoint &k, real) { return {UB200_KERNEL_PESKIN3, 3, 1.0 / (double)k.invh, 0, 0, 0}; }
+inline ub200_ibm_kernel describeKernel(const IBM_kernels::Peskin::fourPoint &k, real) { return {UB200_KERNEL_PESKIN4, 4, 1.0 / (double)k.invh, 0, 0, 0}; }
+template <class G> inline ub200_ibm_kernel describeGaussian(const G &k, real h) {
+  ub200_ibm_kernel d;
+  d.kind = UB200_KERNEL_GAUSSIAN;
+  d.support = k.support;
+  d.h = h;
+  d.rmax = k.rmax;
+  const double p0 = k.phi(real(0), real3()), r1 = 0.25 * (double)k.rmax, p1 = k.phi(real(r1), real3());
+  d.prefactor = p0;
+  d.tau = std::log(p1 / p0) / (r1 * r1);
+  return d;
+}
+inline ub200_ibm_kernel describeKernel(const BDHI::FCM_ns::Kernels::Gaussian &k, real h) { return describeGaussian(k, h); }
+inline ub200_ibm_kernel describeKernel(const BDHI::FCM_ns::Kernels::GaussianTorque &k, real h) { return describeGaussian(k, h); }
+
+/* ---------------------------------------------------------------- FCM_impl ---------------------------------- */
+/* The class the reference's tests construct directly (test/BDHI/FCM/fcm_test.cu:85-144): same Parameters, same return
+   type (std::pair of uammd's pool-backed cached vectors: linear and, with torques, angular velocities). */
+template <class Kernel, class KernelTorque> class FCM_impl {
+public:
+  template <class T> using cached_vector = BDHI::cached_vector<T>;
+  struct Parameters : BDHI::Parameters {
+    int3 cells = make_int3(-1, -1, -1);
+    uint seed = 0;
+    std::shared_ptr<Kernel> kernel = nullptr;
+    std::shared_ptr<KernelTorque> kernelTorque = nullptr;
+    bool adaptBoxSize = false;
+  };
+
+  FCM_impl(Parameters par) : viscosity(par.viscosity), hydrodynamicRadius(par.hydrodynamicRadius), box(par.box) {
+    if (par.box.boxSize.x <= 0 or par.cells.x <= 0 or not par.kernel or not par.kernelTorque) {
+      System::log<System::EXCEPTION>("FCM_impl requires a valid box, grid and instances of the spreading kernels");
+      throw std::runtime_error("Invalid arguments");
+    }
+    if (par.seed == 0) par.seed = 0x9e3779b9u;
+    Grid grid(par.box, par.cells);
+    const real h = std::min({grid.cellSize.x, grid.cellSize.y, grid.cellSize.z});
+    const ub200_ibm_kernel k = describeKernel(*par.kernel, h), kt = describeKernel(*par.kernelTorque, h);
+    const double L[3] = {(double)box.boxSize.x, (double)box.boxSize.y, (double)box.boxSize.z};
+    const int cells[3] = {par.cells.x, par.cells.y, par.cells.z};
+    check(ub200_fcm_create(&handle, (int)sizeof(real), L, cells, &k, (double)viscosity, par.seed), "fcm_create");
+    check(ub200_fcm_set_torque_kernel(handle, &kt), "fcm_set_torque_kernel");
+  }
+  FCM_impl(const FCM_impl &) = delete;
+  ~FCM_impl() { ub200_fcm_destroy(handle); }
+
+  real getHydrodynamicRadius() { return hydrodynamicRadius; }
+  /* FCM_impl::getSelfMobility (FCM_impl.cuh:102-119) */
+  real getSelfMobility() {
+    long double rh = hydrodynamicRadius, L = box.boxSize.x, a = rh / L, a3 = a * a * a;
+    const long double c = 2.83729747948061947666591710460773907l, b = 0.19457l;
+    const long double a6pref = 16.0l * M_PIl * M_PIl / 45.0l + 630.0L * b * b;
+    return 1.0l / (6.0l * M_PIl * viscosity * rh) * (1.0l - c * a + (4.0l / 3.0l) * M_PIl * a3 - a6pref * a3 * a3);
+  }
+  Box getBox() { return box; }
+
+  /* FCM_impl::computeHydrodynamicDisplacements (FCM_impl.cuh:652-693): torque == nullptr skips the rotational part and
+     leaves the second vector empty; force may be nullptr (noise only) */
+  std::pair<cached_vector<real3>, cached_vector<real3>> computeHydrodynamicDisplacements(real4 *pos, real4 *force, real4 *torque,
+                                                                                         int numberParticles, real temperature,
+                                                                                         real prefactor, cudaStream_t st) {
+    cached_vector<real3> linear(numberParticles), angular(torque ? numberParticles : 0);
+    real3 *lin = thrust::raw_pointer_cast(linear.data());
+    if (torque) {
+      check(ub200_fcm_mdot_torque(handle, pos, force, torque, numberParticles, (double)temperature, (double)prefactor, lin,
+                                  thrust::raw_pointer_cast(angular.data()), (void *)st),
+            "fcm_mdot_torque");
+    } else {
+      check(ub200_fcm_mdot(handle, pos, force, numberParticles, (double)temperature, (double)prefactor, lin, (void *)st), "fcm_mdot");
+    }
+    return {std::move(linear), std::move(angular)};
+  }
+
+private:
+  ub200_fcm *handle = nullptr;
+  real viscosity, hydrodynamicRadius;
+  Box box;
+};
+
+/* ---------------------------------------------------------------- IBM --------------------------------------- */
+/* spread / gather of misc/IBM.cuh:99-203 on a regular grid (LinearIndex3D: i + nx (j + ny k)) for the windows the library
+   builds (Peskin 3 / 4 point, truncated Gaussian). The library moves real3 quantities between real4 positions and a real3
+   grid; other combinations the reference's templates accept (real3 positions, scalar or real4 quantities, scalar grids)
+   are converted through scratch vectors here. Both calls ADD into their output like the reference. */
+namespace detail {
+template <class T> struct Components;
+template <> struct Components<real> { static constexpr int n = 1; };
+template <> struct Components<real2> { static constexpr int n = 2; };
+template <> struct Components<real3> { static constexpr int n = 3; };
+template <> struct Components<real4> { static constexpr int n = 4; };
+struct ToReal4Pos {
+  __host__ __device__ real4 operator()(real3 p) const { return make_real4(p.x, p.y, p.z, 0); }
+  __host__ __device__ real4 operator()(real4 p) const { return p; }
+};
+struct ToReal3 {
+  __host__ __device__ real3 operator()(real v) const { return make_real3(v, 0, 0); }
+  __host__ __device__ real3 operator()(real3 v) const { return v; }
+  __host__ __device__ real3 operator()(real4 v) const { return make_real3(v.x, v.y, v.z); }
+};
+template <class T> struct AddFromReal3;
+template <> struct AddFromReal3<real> { __host__ __device__ real operator()(real o, real3 v) const { return o + v.x; } };
+template <> struct AddFromReal3<real3> { __host__ __device__ real3 operator()(real3 o, real3 v) const { return o + v; } };
+template <> struct AddFromReal3<real4> { __host__ __device__ real4 operator()(real4 o, real3 v) const { return o + make_real4(v.x, v.y, v.z, 0); } };
+} // namespace detail
+
+template <class Kernel> class IBM {
+  shared_ptr<Kernel> kernel;
+  Grid grid;
+  ub200_ibm *handle = nullptr;
+  mutable thrust::device_vector<real4> pos4;
+  mutable thrust::device_vector<real3> val3, grid3, out3;
+
+  template <class PosIterator> const real4 *positions(PosIterator pos, int N, cudaStream_t st) const {
+    pos4.resize(N);
+    thrust::transform(thrust::cuda::par.on(st), pos, pos + N, pos4.begin(), detail::ToReal4Pos());
+    return thrust::raw_pointer_cast(pos4.data());
+  }
+
+public:
+  IBM(shared_ptr<Kernel> kern, Grid a_grid) : kernel(kern), grid(a_grid) {
+    const real h = std::min({grid.cellSize.x, grid.cellSize.y, grid.cellSize.z});
+    const ub200_ibm_kernel k = describeKernel(*kernel, h);
+    const double L[3] = {(double)grid.box.boxSize.x, (double)grid.box.boxSize.y, (double)grid.box.boxSize.z};
+    const int periodic[3] = {grid.box.isPeriodicX(), grid.box.isPeriodicY(), grid.box.isPeriodicZ()};
+    const int cells[3] = {grid.cellDim.x, grid.cellDim.y, grid.cellDim.z};
+    check(ub200_ibm_create(&handle, (int)sizeof(real), L, periodic, cells, &k, grid.cellDim.x), "ibm_create");
+  }
+  IBM(const IBM &) = delete;
+  ~IBM() { ub200_ibm_destroy(handle); }
+
+  /* gridData[c] += v_p phi(x) phi(y) phi(z) over the support of every particle (IBM::spread, misc/IBM.cuh:117-138) */
+  template <class PosIterator, class QuantityIterator, class GridQuantity>
+  void spread(PosIterator pos, QuantityIterator v, GridQuantity *gridData, int numberParticles, cudaStream_t st = 0) const {
+    const int ncells = grid.cellDim.x * grid.cellDim.y * grid.cellDim.z;
+    const real4 *p = positions(pos, numberParticles, st);
+    val3.resize(numberParticles);
+    thrust::transform(thrust::cuda::par.on(st), v, v + numberParticles, val3.begin(), detail::ToReal3());
+    grid3.assign(ncells, real3());
+    check(ub200_ibm_spread(handle, p, thrust::raw_pointer_cast(val3.data()), 3, numberParticles, thrust::raw_pointer_cast(grid3.data()),
+                           (void *)st),
+          "ibm_spread");
+    thrust::transform(thrust::cuda::par.on(st), gridData, gridData + ncells, grid3.begin(), gridData, detail::AddFromReal3<GridQuantity>());
+  }
+
+  /* Jq[p] += sum_c gridData[c] phi phi phi dV (IBM::gather with the default quadrature weights, misc/IBM.cuh:140-184) */
+  template <class PosIterator, class ResultQuantity, class GridQuantityIterator>
+  void gather(PosIterator pos, ResultQuantity *Jq, GridQuantityIterator gridData, int numberParticles, cudaStream_t st = 0) const {
+    const int ncells = grid.cellDim.x * grid.cellDim.y * grid.cellDim.z;
+    const real4 *p = positions(pos, numberParticles, st);
+    grid3.resize(ncells);
+    thrust::transform(thrust::cuda::par.on(st), gridData, gridData + ncells, grid3.begin(), detail::ToReal3());
+    out3.assign(numberParticles, real3());
+    check(ub200_ibm_gather(handle, p, numberParticles, thrust::raw_pointer_cast(grid3.data()), thrust::raw_pointer_cast(out3.data()),
+                           (void *)st),
+          "ibm_gather");
+    thrust::transform(thrust::cuda::par.on(st), Jq, Jq + numberParticles, out3.begin(), Jq, detail::AddFromReal3<ResultQuantity>());
+  }
+  shared_ptr<Kernel> getKernel() { return kernel; }
+};
 
 template <class Kernel = BDHI::FCM_ns::Kernels::Gaussian> class FCM {
   shared_ptr<ParticleGroup> pg;

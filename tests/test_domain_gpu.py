@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [p for p in (ROOT, os.path.join(ROOT, "tests")) if p not in sys.path]
 
 from uammd_b200 import synthetic as syn  # noqa: E402
-from uammd_b200.md import Box, DPD, LJ, PairForces, VerletNVE  # noqa: E402
+from uammd_b200.md import Box, CellList, DPD, LJ, PairForces, VerletNVE  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -89,7 +89,7 @@ def test_lj_bricks_bit_identical_to_single_gpu(cuda, rankGrid):
     gp, gv = gather_lockstep(ranks, N)
     p, v = torch.from_numpy(pos).to(cuda), torch.from_numpy(vel).to(cuda)
     nve = VerletNVE(p, v, dt)
-    nve.addInteractor(PairForces(pot, box))
+    nve.addInteractor(PairForces(pot, box, nl=CellList()))  # the cell traversal these (legacy) bricks use: same bits
     for _ in range(steps):
         nve.forwardTime()
     torch.cuda.synchronize()

@@ -60,3 +60,25 @@ def test_verlet_bd_pse_dropin_matches_reference():
     assert r["bd_force_max_dpos"] == 0.0                 # ... also with an interactor
     assert r["pse_displacement"] > 1e-3                  # the particles did move
     assert r["pse_max_dpos"] < 2e-5 * max(1.0, r["pse_displacement"])  # BDHI::EulerMaruyama<b200::PSE>, fp32
+
+
+def test_dpd_dropin_matches_reference_and_thermostats():
+    """b200::DPDPotential lets the reference's PairForces drive its own DPD transverser; b200::PairForcesDPD is the fast
+    path. Same Saru seed and step: forces agree to fp32 summation order. Then 2000 VerletNVE steps of the DPD fluid at
+    rho = 3 from a random cloud: the kinetic temperature must settle at kT = 1 (fluctuation-dissipation: a wrong sign or
+    scale of the dissipative / random force would pass force parity against our own restatement but not this)."""
+    r = _run("dropin_dpd", 81000, 2000)
+    print(r)
+    assert r["fast_vs_ref"] < 2e-5
+    assert abs(r["kT_measured"] - r["kT_target"]) < 0.03
+
+
+def test_fcm_impl_and_ibm_glue_pass_the_reference_tests():
+    """test/BDHI/FCM/fcm_test.cu:85-144 and test/misc/ibm/test_ibm_regular.cu:113-136,156-214,240-274 re-hosted on
+    b200::FCM_impl<Gaussian, GaussianTorque> and b200::IBM<Peskin::threePoint> (double precision build)."""
+    r = _run("dropin_fcm_impl")
+    print(r)
+    assert r["worst_vs_hasimoto"] < r["tolerance"]          # the reference's own assertion (1e-8)
+    assert r["max_vs_reference_fcm_impl"] < 1e-10           # next to the reference's FCM_impl on the same inputs
+    assert r["ibm_spread_vs_manual"] < 1e-10 and r["ibm_gather_vs_manual"] < 1e-10
+    assert r["ibm_spread_vs_reference"] < 1e-12 and r["ibm_adjointness"] < 1e-10

@@ -52,7 +52,11 @@ def test_nccl_decomposition_matches_single_gpu(tmp_path):
     p = torch.from_numpy(syn.fcc_lattice(N, Lb)).to(dev)
     v = torch.from_numpy(syn.maxwell_velocities(N, 1.0)).to(dev)
     f = torch.zeros(N, 4, device=dev)
-    LJMD(Box(Lb), pot, 0.005).run(p, v, f, steps)
+    os.environ["UB200_LJ_ENGINE"] = "cell"  # the particle decomposition runs the cell traversal: compare with the same kernel
+    try:
+        LJMD(Box(Lb), pot, 0.005).run(p, v, f, steps)
+    finally:
+        del os.environ["UB200_LJ_ENGINE"]
     assert np.array_equal(got.view(np.uint32), p.cpu().numpy().view(np.uint32))
 
 
