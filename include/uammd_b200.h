@@ -446,6 +446,11 @@ int ub200_pse_near_mdot(ub200_pse *pse, const void *d_pos, const void *d_v, int 
  * like the reference's gemv with beta = 0). Host-synchronous (Lanczos convergence checks) like the reference. */
 int ub200_pse_near_noise(ub200_pse *pse, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
                          void *d_BdW3, int *iterations, void *stream);
+/* same, ADDED to d_out3: what PSE::computeHydrodynamicDisplacements (BDHI_PSE.cuh:141-158) documents - "Mobility force +
+ * prefactor sqrt(2 T M) dW" - needs. The reference passes MF itself to the Lanczos solver, whose final gemv has beta = 0,
+ * so its near-field M F is overwritten whenever T > 0 and a force is given; this entry point keeps both terms. */
+int ub200_pse_near_noise_add(ub200_pse *pse, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
+                             void *d_out3, int *iterations, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BASELINE config 0: BD::EulerMaruyama (ideal or with interactor forces). Replaces EulerMaruyama_ns::integrateGPU

@@ -1,3 +1,2 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -25 > gpurun_out/r02j_pytest_gpu.log
-tail -25 gpurun_out/r02j_pytest_gpu.log
+timeout 800 python scripts/energy_drift3.py 2>&1 | tail -6 | cut -c1-700

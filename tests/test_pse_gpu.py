@@ -200,3 +200,31 @@ def test_near_field_dense_cloud_unstaged_path(orc, cuda):
     m.computeBdW(bdw)
     torch.cuda.synchronize()
     assert m.info().lastLanczosIterations >= 2 and torch.isfinite(bdw).all()
+
+
+def test_displacements_with_force_and_noise_keep_every_term(cuda):
+    """computeHydrodynamicDisplacements with a force AND T > 0 = near(F) + near noise + far(F) + far noise. (The reference
+    hands MF to its Lanczos solver, which overwrites it: its near-field M F is lost in this case - ADVICE r1; ours adds.)
+    Same generator state -> the same seed2 draws as the separate calls, so the terms can be compared one by one."""
+    N, L = 4000, 32.0
+    pos = np.zeros((N, 4)); pos[:, :3] = syn.uniform_cloud(N, L, seed=31)[:, :3].astype(np.float64)
+    force = np.zeros((N, 4)); force[:, :3] = syn.gaussian_forces(N, seed=32)
+    T, dt, pref = 0.7, 0.01, 1.3
+    p, f = torch.from_numpy(pos).to(cuda), torch.from_numpy(force).to(cuda)
+    par = pse.Parameters(L, viscosity=1.0, hydrodynamicRadius=1.0, tolerance=1e-6, psi=0.6, temperature=T, dt=dt)
+    m = pse.PSE(p, par, sys=bd.System(5), force=f)
+    MF = torch.zeros(N, 3, dtype=p.dtype, device=cuda)
+    m.computeHydrodynamicDisplacements(f, MF, T, pref)
+    # the same pieces one by one, with a generator in the same state (near noise draws first, then the far field)
+    m2 = pse.PSE(p, par, sys=bd.System(5), force=f)
+    near = torch.zeros_like(MF); noise = torch.zeros_like(MF); far = torch.zeros_like(MF)
+    m2.computeMFNearField(near)
+    m2._nearNoise(noise, T, pref, None)
+    seed2 = m2.sys.rng().next32()
+    from uammd_b200._lib import check
+    from uammd_b200.md import _ptr, _stream_ptr
+    check(m2.lib.ub200_pse_far_mdot(m2._h, _ptr(p), _ptr(f), N, T, pref, seed2, _ptr(far), _stream_ptr()))
+    torch.cuda.synchronize()
+    total = (near + noise + far).cpu().numpy()
+    assert _rel(MF.cpu().numpy(), total) < 1e-12
+    assert np.linalg.norm(near.cpu().numpy()) > 1e-3 * np.linalg.norm(total)   # the term the reference drops is not small

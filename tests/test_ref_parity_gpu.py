@@ -72,6 +72,29 @@ def test_reference_parity(orc, cuda, tmp_path, N, kind):
     print(f"[parity N={N} {kind}] in units of the fp32 tolerance: reference vs fp64 {err_ref:.3f}; "
           f"new vs fp64 {err_new:.3f}; new vs reference {direct:.3f}")
     assert err_new < 1.0 and err_ref < 1.0 and direct < 2.0
+    if kind == "fcc":
+        # BASELINE.md 3.4, flat bounds on the liquid-like cloud (no overlapping pairs): rel-Linf <= 1e-5 of the largest force
+        # against the compiled reference, <= 1e-6 |F|inf against the fp64 truth (an fp32 coordinate of box scale carries
+        # ulp(L/2) = 4e-6, i.e. a few 1e-7 |F|inf through the steepest pair: the bound has no slack to hide a missed pair,
+        # whose force at the cut-off is 0.04 = 1e-4 |F|inf)
+        # Particles with a neighbour inside the rounding band of the cut-off are left out: the unshifted LJ force jumps by
+        # |f(rc)| = 0.039 there and either implementation may count such a pair (the reference differs from the fp64
+        # truth by the same jump); they are a fraction of a per cent and stay under the sensitivity model above.
+        clean = np.asarray(sc.edge) == 0
+        Fn, Fr = force.cpu().numpy()[:, :3].astype(np.float64), ref["force"][:, :3].astype(np.float64)
+        finf = np.abs(f64).max()
+        flat_ref = np.abs(Fn - Fr)[clean].max() / np.abs(Fr).max()
+        flat_64 = np.abs(Fn - f64)[clean].max() / finf
+        ref_64 = np.abs(Fr - f64)[clean].max() / finf
+        print(f"[parity N={N} fcc] flat bounds on {clean.mean() * 100:.2f} % of the particles: new vs reference {flat_ref:.2e} |F|inf, "
+              f"new vs fp64 {flat_64:.2e} |F|inf, reference vs fp64 {ref_64:.2e} |F|inf (|F|inf = {finf:.4g}); "
+              f"with the band pairs: new vs reference {np.abs(Fn - Fr).max() / np.abs(Fr).max():.2e}")
+        assert clean.mean() > 0.98
+        # measured on a B200 (N = 1e6): ours 5.1e-7 |F|inf from the truth, the reference 1.8e-5 (it differences raw,
+        # box-scale fp32 coordinates pair by pair; the engine subtracts coordinates already brought next to the home
+        # particle). The distance between the two is therefore the reference's own error, above BASELINE's 1e-5.
+        assert flat_64 <= 1e-6
+        assert flat_ref <= max(1e-5, 1.05 * ref_64 + flat_64)
     # the restated fp32 oracle in reference order should be (nearly) the reference's bits
     f32, _, _ = orc.lj_f32(g, ocl, pot.table(), 1, N)
     assert (np.abs(f32[:, :3] - ref["force"][:, :3]).max(axis=1) / tol).max() < 1.0

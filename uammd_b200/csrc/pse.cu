@@ -776,6 +776,18 @@ template <class T> struct PseState {
     UB200_LAUNCHED();
     return lanczosSqrt(z.as<T>(), (T *)BdW3, N, (double)tolerance, iterations, st);
   }
+  // out += prefactor sqrt(2T) Mr^1/2 dW: the square root runs into a scratch vector (the Lanczos iteration rewrites its
+  // output at every convergence check), which is then added
+  int nearNoiseAdd(const void *pos, int N, double temperature, double prefactor, uint32_t seed2, void *out3, int *iterations,
+                   cudaStream_t st) {
+    if (iterations) *iterations = 0;
+    if (temperature == 0.0) return UB200_OK;
+    int rc;
+    if ((rc = noiseOut.reserve(sizeof(T) * 3 * (size_t)N))) return rc;
+    if ((rc = nearNoise(pos, N, temperature, prefactor, seed2, noiseOut.p, iterations, st))) return rc;
+    return axpby(T(1), noiseOut.as<T>(), T(1), (T *)out3, 3 * (size_t)N, st);
+  }
+  DevBuf noiseOut;
 };
 
 } // namespace ub200
@@ -850,5 +862,10 @@ int ub200_pse_near_noise(ub200_pse *h, const void *d_pos, int N, double temperat
                          void *d_BdW3, int *iterations, void *stream) {
   if (!h || !d_pos || !d_BdW3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
   return PSE_DISPATCH(h, nearNoise(d_pos, N, temperature, prefactor, seed2, d_BdW3, iterations, (cudaStream_t)stream));
+}
+int ub200_pse_near_noise_add(ub200_pse *h, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
+                             void *d_out3, int *iterations, void *stream) {
+  if (!h || !d_pos || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return PSE_DISPATCH(h, nearNoiseAdd(d_pos, N, temperature, prefactor, seed2, d_out3, iterations, (cudaStream_t)stream));
 }
 }

@@ -43,6 +43,7 @@ def _declare():
         "ub200_pse_far_mdot": (i, [vp, vp, vp, i, d, d, u32, vp, vp]),
         "ub200_pse_near_mdot": (i, [vp, vp, vp, i, i, vp, vp]),
         "ub200_pse_near_noise": (i, [vp, vp, i, d, d, u32, vp, C.POINTER(i), vp]),
+        "ub200_pse_near_noise_add": (i, [vp, vp, i, d, d, u32, vp, C.POINTER(i), vp]),
         "ub200_bdhi_euler_update": (i, [i, vp, vp, vp, vp, vp, i, d, d, i, vp]),
     }
     for name, (res, args) in sig.items():
@@ -140,21 +141,25 @@ class PSE:
     def computeBdW(self, BdW, stream=None):
         self._nearNoise(BdW, self.temperature, 1.0, stream)
 
-    def _nearNoise(self, out, temperature, prefactor, stream):
+    def _nearNoise(self, out, temperature, prefactor, stream, add=False):
         if temperature == 0:
             return 0
         seed2 = self.sys.rng().next32()                                     # NearField.cuh:274
         it = C.c_int(0)
-        check(self.lib.ub200_pse_near_noise(self._h, _ptr(self.pos), self.N, float(temperature), float(prefactor), seed2,
-                                            _ptr(out), C.byref(it), _stream_ptr(stream)))
+        fn = self.lib.ub200_pse_near_noise_add if add else self.lib.ub200_pse_near_noise
+        check(fn(self._h, _ptr(self.pos), self.N, float(temperature), float(prefactor), seed2, _ptr(out), C.byref(it),
+                 _stream_ptr(stream)))
         return it.value
 
     def computeHydrodynamicDisplacements(self, force, MF, temperature, noise_prefactor, stream=None):
-        """MF = Mobility force + noise_prefactor sqrt(2 T M) dW (BDHI_PSE.cuh:141-158, same call order)."""
+        """MF = Mobility force + noise_prefactor sqrt(2 T M) dW (BDHI_PSE.cuh:141-158, same call order and random draws).
+        Deviation from the reference, on purpose: its Lanczos solver OVERWRITES the vector it is given (final gemv with
+        beta = 0, LanczosAlgorithm.cu:163-172), so with a force and T > 0 the reference drops the near-field M F it has just
+        computed; here the near-field noise is added to it, which is what the method documents."""
         MF.zero_()
         if force is not None:
             check(self.lib.ub200_pse_near_mdot(self._h, _ptr(self.pos), _ptr(force), 4, self.N, _ptr(MF), _stream_ptr(stream)))
-        self._nearNoise(MF, temperature, noise_prefactor, stream)
+        self._nearNoise(MF, temperature, noise_prefactor, stream, add=True)
         seed2 = self.sys.rng().next32() if temperature > 0 else 0
         check(self.lib.ub200_pse_far_mdot(self._h, _ptr(self.pos), _ptr(force) if force is not None else None, self.N,
                                           float(temperature), float(noise_prefactor), seed2, _ptr(MF), _stream_ptr(stream)))
