@@ -72,6 +72,31 @@ def test_virtual_ranks_bit_identical_to_single_gpu(cuda, rankGrid):
         assert sum(r.counts()[1] - r.counts()[0] for r in ranks) > 0  # ghosts were exchanged
 
 
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_one_rank_run_entry_point_with_and_without_graph(cuda, graph):
+    """ub200_brick_lj_nve_run_f32 (the entry point multi-process runs use): a captured CUDA graph of four steps replayed on
+    an internal stream, closing kicks fused into the next step's push; 26 steps = 6 graphs + 2 plain steps. One rank is a
+    1 x 1 x 1 brick exchanging with itself: every kernel of the path runs, and the result must be the single-GPU bits."""
+    N, Lb, pos, vel, pot = _system(14)
+    steps = 26
+    old = os.environ.get("UB200_BRICK_GRAPH")
+    os.environ["UB200_BRICK_GRAPH"] = graph
+    try:
+        md = BrickLJMD(Box(Lb), pot, 0.005, N, 0, 1, (1, 1, 1))
+    finally:
+        if old is None:
+            del os.environ["UB200_BRICK_GRAPH"]
+        else:
+            os.environ["UB200_BRICK_GRAPH"] = old
+    md.setGlobalState(torch.from_numpy(pos).to(cuda), torch.from_numpy(vel).to(cuda))
+    md.run(10)
+    md.run(steps - 10)
+    p, v, f = assemble([md.owned()], N)
+    assert md.counts()[2] == 0
+    ps, vs, fs = _single(cuda, N, Lb, pos, vel, pot, steps)
+    assert np.array_equal(p, ps) and np.array_equal(v, vs) and np.array_equal(f[:, :3], fs[:, :3])
+
+
 def test_particles_migrate_between_bricks(cuda):
     """A drifting gas: after enough steps a good share of the particles has changed owner; nothing is lost or duplicated
     and the trajectory still equals the single-GPU one."""

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace ub200 {
 
@@ -135,12 +136,16 @@ constexpr int kWorkInts = 2 + 2 * kBrickMaxRanks;
 // The kick and the drift spell out the roundings of VerletNVE_ns::integrateGPU<1> (Integrator/VerletNVE.cu:64-85) exactly
 // like nveHalfStep<1> (nve.cu), unit mass.
 __global__ void __launch_bounds__(256)
-brickAdvancePush(BrickGeom b, BrickArena ar, int parity, uint32_t epoch, const float4 *__restrict__ pos,
+brickAdvancePush(BrickGeom b, BrickArena ar, const float4 *__restrict__ pos,
                  const float *__restrict__ vel, const int *__restrict__ gid, const float4 *__restrict__ force,
                  const int *__restrict__ counts, float dt, int doKick, float4 *__restrict__ posN, float *__restrict__ velN,
                  int *__restrict__ gidN, int *__restrict__ work, int *__restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
   const int nOwned = counts[0];
+  // number of this exchange (counted on the device by brickBegin, so that a captured CUDA graph of the step can be
+  // replayed): the flag value the peers wait for; its parity selects the inbox buffer
+  const uint32_t epoch = (uint32_t)counts[2];
+  const int parity = (int)((epoch - 1u) & 1u);
   const bool active = i < nOwned;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
   float vx = 0.f, vy = 0.f, vz = 0.f;
@@ -153,6 +158,11 @@ brickAdvancePush(BrickGeom b, BrickArena ar, int parity, uint32_t epoch, const f
     id = gid[i];
     if (doKick) {
       const float4 f = force[i];
+      if (doKick == 2) { // the closing kick of the previous step first (nveKickKickDrift: same roundings as two passes)
+        vx = __fmaf_rn(__fmul_rn(__fmul_rn(1.0f, f.x), dt), 0.5f, vx);
+        vy = __fmaf_rn(__fmul_rn(__fmul_rn(1.0f, f.y), dt), 0.5f, vy);
+        vz = __fmaf_rn(__fmul_rn(__fmul_rn(1.0f, f.z), dt), 0.5f, vz);
+      }
       vx = __fmaf_rn(__fmul_rn(__fmul_rn(1.0f, f.x), dt), 0.5f, vx);
       vy = __fmaf_rn(__fmul_rn(__fmul_rn(1.0f, f.y), dt), 0.5f, vy);
       vz = __fmaf_rn(__fmul_rn(__fmul_rn(1.0f, f.z), dt), 0.5f, vz);
@@ -214,11 +224,13 @@ brickAdvancePush(BrickGeom b, BrickArena ar, int parity, uint32_t epoch, const f
 // Receiver side: wait for every rank's flag of this exchange, append the migrants to the kept block and the ghosts behind
 // them, publish {nOwned, nLocal} on the device.
 __global__ void __launch_bounds__(256)
-brickUnpack(BrickArena ar, int me, int world, int parity, uint32_t epoch, int cap, float4 *__restrict__ posN,
+brickUnpack(BrickArena ar, int me, int world, int cap, float4 *__restrict__ posN,
             float *__restrict__ velN, int *__restrict__ gidN, const int *__restrict__ work, int *__restrict__ counts,
             int *__restrict__ err) {
   __shared__ int sOff[2 * kBrickMaxRanks + 1];
   __shared__ int sKept;
+  const uint32_t epoch = (uint32_t)counts[2];
+  const int parity = (int)((epoch - 1u) & 1u);
   if (threadIdx.x == 0) {
     const uint32_t *flags = arenaFlags(ar.p[me]);
     for (int s = 0; s < world; s++) {
@@ -262,6 +274,12 @@ brickUnpack(BrickArena ar, int me, int world, int parity, uint32_t epoch, int ca
       gidN[dst] = __float_as_int(v.w);
     }
   }
+}
+
+// opens an exchange: clears the slot counters and counts the exchange
+__global__ void brickBegin(int *__restrict__ work, int *__restrict__ counts) {
+  if (threadIdx.x < kWorkInts) work[threadIdx.x] = 0;
+  if (threadIdx.x == 0) counts[2] += 1;
 }
 
 // second kick of velocity Verlet on the owned block (nveHalfStep<2>, unit mass)
@@ -312,9 +330,19 @@ struct ub200_brick {
   size_t arenaBytes = 0;
   BrickArena ar;
   bool attached = false, ipcOpened[kBrickMaxRanks] = {};
-  uint32_t exchanges = 0;
   bool prepared = false;
   ub200_ljengine *eng = nullptr;
+  // CUDA graph of kGraphSteps consecutive steps (the whole step is device driven: counts, exchange number and inbox parity
+  // live on the device, so one captured sequence replays for every step). Runs on an internal stream joined to the caller's
+  // by events (the legacy default stream cannot be captured). exec[c]: graph captured with state buffer c current.
+  bool useGraph = true;
+  cudaStream_t gs = nullptr;
+  cudaEvent_t evIn = nullptr, evOut = nullptr;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};  // kGraphSteps steps starting with state buffer c
+  cudaGraphExec_t exec1[2] = {nullptr, nullptr}; // one step (callers that step one at a time: the host enqueues one graph
+                                                 // instead of a dozen launches)
+  std::vector<float> graphParams;
+  float graphDt = 0.f;
   // optional phase timing (UB200_BRICK_PROFILE=1; makes every step synchronous): push, unpack (incl. waiting for the
   // peers), list build, traversal, kick
   static constexpr int kPhases = 5;
@@ -337,51 +365,37 @@ static void brickCollect(ub200_brick *h, cudaStream_t st) {
   h->profiledSteps++;
 }
 
-static int brickExchange(ub200_brick *h, float dt, int doKick, cudaStream_t st) {
-  if (!h->attached) return UB200_ERR_NOT_BUILT;
-  const int parity = (int)(h->exchanges & 1u);
-  const uint32_t epoch = ++h->exchanges;
+static int brickPush(ub200_brick *h, float dt, int doKick, cudaStream_t st) {
   const int c = h->cur, n = c ^ 1;
-  UB200_CUDA(cudaMemsetAsync(h->work.p, 0, sizeof(int) * kWorkInts, st));
+  brickBegin<<<1, 32, 0, st>>>(h->work.as<int>(), h->counts.as<int>());
+  UB200_LAUNCHED();
   brickMark(h, 0, st);
-  brickAdvancePush<<<(h->cap + 255) / 256, 256, 0, st>>>(h->geom, h->ar, parity, epoch, h->pos[c].as<float4>(), h->vel[c].as<float>(),
+  brickAdvancePush<<<(h->cap + 255) / 256, 256, 0, st>>>(h->geom, h->ar, h->pos[c].as<float4>(), h->vel[c].as<float>(),
                                                         h->gid[c].as<int>(), h->force.as<float4>(), h->counts.as<int>(), dt, doKick,
                                                         h->pos[n].as<float4>(), h->vel[n].as<float>(), h->gid[n].as<int>(),
                                                         h->work.as<int>(), h->err.as<int>());
   UB200_LAUNCHED();
   brickMark(h, 1, st);
-  brickUnpack<<<2 * kNumSMs, 256, 0, st>>>(h->ar, h->geom.me, h->geom.world, parity, epoch, h->cap, h->pos[n].as<float4>(),
-                                          h->vel[n].as<float>(), h->gid[n].as<int>(), h->work.as<int>(), h->counts.as<int>(),
-                                          h->err.as<int>());
+  return UB200_OK;
+}
+static int brickPull(ub200_brick *h, cudaStream_t st) {
+  const int n = h->cur ^ 1;
+  brickUnpack<<<2 * kNumSMs, 256, 0, st>>>(h->ar, h->geom.me, h->geom.world, h->cap, h->pos[n].as<float4>(), h->vel[n].as<float>(),
+                                          h->gid[n].as<int>(), h->work.as<int>(), h->counts.as<int>(), h->err.as<int>());
   UB200_LAUNCHED();
   brickMark(h, 2, st);
   h->cur = n;
   return UB200_OK;
 }
-
+static int brickExchange(ub200_brick *h, float dt, int doKick, cudaStream_t st) {
+  if (!h->attached) return UB200_ERR_NOT_BUILT;
+  if (const int rc = brickPush(h, dt, doKick, st)) return rc;
+  return brickPull(h, st);
+}
 // phase 0 of an exchange alone / phase 1 alone (virtual ranks of one process enqueue phase 0 of every rank first)
 static int brickExchangePhase(ub200_brick *h, int phase, float dt, int doKick, cudaStream_t st) {
   if (!h->attached) return UB200_ERR_NOT_BUILT;
-  const int c = h->cur, n = c ^ 1;
-  if (phase == 0) {
-    const int parity = (int)(h->exchanges & 1u);
-    const uint32_t epoch = ++h->exchanges;
-    UB200_CUDA(cudaMemsetAsync(h->work.p, 0, sizeof(int) * kWorkInts, st));
-    brickAdvancePush<<<(h->cap + 255) / 256, 256, 0, st>>>(h->geom, h->ar, parity, epoch, h->pos[c].as<float4>(), h->vel[c].as<float>(),
-                                                          h->gid[c].as<int>(), h->force.as<float4>(), h->counts.as<int>(), dt,
-                                                          doKick, h->pos[n].as<float4>(), h->vel[n].as<float>(), h->gid[n].as<int>(),
-                                                          h->work.as<int>(), h->err.as<int>());
-    UB200_LAUNCHED();
-    return UB200_OK;
-  }
-  const uint32_t epoch = h->exchanges;
-  const int parity = (int)((epoch - 1u) & 1u);
-  brickUnpack<<<2 * kNumSMs, 256, 0, st>>>(h->ar, h->geom.me, h->geom.world, parity, epoch, h->cap, h->pos[n].as<float4>(),
-                                          h->vel[n].as<float>(), h->gid[n].as<int>(), h->work.as<int>(), h->counts.as<int>(),
-                                          h->err.as<int>());
-  UB200_LAUNCHED();
-  h->cur = n;
-  return UB200_OK;
+  return phase == 0 ? brickPush(h, dt, doKick, st) : brickPull(h, st);
 }
 
 static int brickForcesLJ(ub200_brick *h, const float *params, int ntypes, cudaStream_t st) {
@@ -454,6 +468,8 @@ int ub200_brick_create(ub200_brick **out, int rank, const int rankGrid[3], const
   ar.p[rank] = (char *)h->arena;
   if ((rc = ub200_ljengine_create(&h->eng))) { cudaFree(h->arena); delete h; return rc; }
   h->attached = world == 1;
+  const char *gr = getenv("UB200_BRICK_GRAPH"); // "0": plain launches instead of the captured step graph
+  h->useGraph = !(gr && gr[0] == '0');
   const char *pf = getenv("UB200_BRICK_PROFILE");
   if (pf && pf[0] == '1') {
     h->profile = true;
@@ -468,6 +484,11 @@ int ub200_brick_destroy(ub200_brick *h) {
   for (int p = 0; p < h->geom.world; p++)
     if (h->ipcOpened[p]) cudaIpcCloseMemHandle(h->ar.p[p]);
   if (h->arena) cudaFree(h->arena);
+  for (auto &e : h->exec)
+    if (e) cudaGraphExecDestroy(e);
+  for (auto &e : h->exec1)
+    if (e) cudaGraphExecDestroy(e);
+  if (h->gs) { cudaStreamDestroy(h->gs); cudaEventDestroy(h->evIn); cudaEventDestroy(h->evOut); }
   ub200_ljengine_destroy(h->eng);
   DevBuf *b[] = {&h->pos[0], &h->pos[1], &h->vel[0], &h->vel[1], &h->gid[0], &h->gid[1], &h->force, &h->counts, &h->work, &h->err};
   for (auto *x : b) x->release();
@@ -546,6 +567,23 @@ int ub200_brick_lj_forces_f32(ub200_brick *h, const float *params, int ntypes, v
   return rc;
 }
 
+// nsteps consecutive steps: the closing kick of a step is fused with the opening kick + drift of the next one
+static int brickSteps(ub200_brick *h, const float *params, int ntypes, float dt, int nsteps, cudaStream_t st) {
+  int rc;
+  for (int s = 0; s < nsteps; s++) {
+    if ((rc = brickExchange(h, dt, s == 0 || h->profile ? 1 : 2, st)) || (rc = brickForcesLJ(h, params, ntypes, st))) return rc;
+    if (s == nsteps - 1 || h->profile) {
+      brickKick2<<<(h->cap + 255) / 256, 256, 0, st>>>(h->vel[h->cur].as<float>(), h->force.as<float4>(), h->counts.as<int>(), dt);
+      UB200_LAUNCHED();
+    }
+    brickMark(h, 5, st);
+    brickCollect(h, st);
+  }
+  return UB200_OK;
+}
+
+constexpr int kGraphSteps = 4; // even: the double-buffered state is back in the same buffer after one graph
+
 int ub200_brick_lj_nve_run_f32(ub200_brick *h, const float *params, int ntypes, float dt, int nsteps, void *stream) {
   if (!h || !params || ntypes < 1 || nsteps < 0) return UB200_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -554,13 +592,73 @@ int ub200_brick_lj_nve_run_f32(ub200_brick *h, const float *params, int ntypes, 
     if ((rc = brickExchange(h, 0.0f, 0, st)) || (rc = brickForcesLJ(h, params, ntypes, st))) return rc;
     h->prepared = true;
   }
-  for (int s = 0; s < nsteps; s++) {
-    if ((rc = brickExchange(h, dt, 1, st)) || (rc = brickForcesLJ(h, params, ntypes, st))) return rc;
-    brickKick2<<<(h->cap + 255) / 256, 256, 0, st>>>(h->vel[h->cur].as<float>(), h->force.as<float4>(), h->counts.as<int>(), dt);
-    UB200_LAUNCHED();
-    brickMark(h, 5, st);
-    brickCollect(h, st);
+  if (!h->useGraph || h->profile || nsteps < 1) return brickSteps(h, params, ntypes, dt, nsteps, st);
+  if (!h->gs) {
+    UB200_CUDA(cudaStreamCreateWithFlags(&h->gs, cudaStreamNonBlocking));
+    UB200_CUDA(cudaEventCreateWithFlags(&h->evIn, cudaEventDisableTiming));
+    UB200_CUDA(cudaEventCreateWithFlags(&h->evOut, cudaEventDisableTiming));
   }
+  const size_t np = (size_t)ntypes * ntypes * 4;
+  if (h->graphDt != dt || h->graphParams.size() != np || memcmp(h->graphParams.data(), params, np * sizeof(float)) != 0) {
+    for (auto &e : h->exec)
+      if (e) { cudaGraphExecDestroy(e); e = nullptr; }
+    for (auto &e : h->exec1)
+      if (e) { cudaGraphExecDestroy(e); e = nullptr; }
+    h->graphParams.assign(params, params + np);
+    h->graphDt = dt;
+  }
+  UB200_CUDA(cudaEventRecord(h->evIn, st));
+  UB200_CUDA(cudaStreamWaitEvent(h->gs, h->evIn, 0));
+  int done = 0;
+  while (nsteps - done >= kGraphSteps) {
+    const int c = h->cur;
+    if (!h->exec[c]) {
+      cudaGraph_t graph = nullptr;
+      UB200_CUDA(cudaStreamBeginCapture(h->gs, cudaStreamCaptureModeRelaxed));
+      rc = brickSteps(h, params, ntypes, dt, kGraphSteps, h->gs);
+      const cudaError_t ce = cudaStreamEndCapture(h->gs, &graph);
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        h->useGraph = false; // fall back to plain launches for good
+        h->cur = c;
+        if ((rc = brickSteps(h, params, ntypes, dt, nsteps - done, h->gs))) return rc;
+        done = nsteps;
+        break;
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&h->exec[c], graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) return cudaFail(ie);
+      // capturing ran the host side of the steps only (kGraphSteps is even: h->cur is back at c)
+    }
+    UB200_CUDA(cudaGraphLaunch(h->exec[c], h->gs));
+    g_launchCount += 11 * kGraphSteps; // kernels of the replayed steps
+    done += kGraphSteps;
+  }
+  while (h->useGraph && done < nsteps) { // left-over steps one by one, each a graph of its own
+    const int c = h->cur;
+    if (!h->exec1[c]) {
+      cudaGraph_t graph = nullptr;
+      UB200_CUDA(cudaStreamBeginCapture(h->gs, cudaStreamCaptureModeRelaxed));
+      rc = brickSteps(h, params, ntypes, dt, 1, h->gs);
+      const cudaError_t ce = cudaStreamEndCapture(h->gs, &graph);
+      h->cur = c; // capturing ran the host side only
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        h->useGraph = false;
+        break;
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&h->exec1[c], graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) return cudaFail(ie);
+    }
+    UB200_CUDA(cudaGraphLaunch(h->exec1[c], h->gs));
+    g_launchCount += 12;
+    h->cur = c ^ 1;
+    done++;
+  }
+  if (done < nsteps && (rc = brickSteps(h, params, ntypes, dt, nsteps - done, h->gs))) return rc;
+  UB200_CUDA(cudaEventRecord(h->evOut, h->gs));
+  UB200_CUDA(cudaStreamWaitEvent(st, h->evOut, 0));
   return UB200_OK;
 }
 

@@ -39,9 +39,12 @@ namespace ub200 {
 constexpr unsigned long long kBarrierSpinLimit = 400000000ull; // ~ seconds; a lost peer must not hang the GPU forever
 
 // flags[p] of rank r = last epoch rank p announced to r. err: set when the spin limit is hit.
-__global__ void __launch_bounds__(32) peerBarrier(PeerTable<uint32_t> flags, int rank, int world, uint32_t epoch, int *err) {
+// epoch = *epochBase + offset: the base is uploaded before every call, so that the captured graph of a call replays
+__global__ void __launch_bounds__(32) peerBarrier(PeerTable<uint32_t> flags, int rank, int world, const uint32_t *epochBase,
+                                                  uint32_t offset, int *err) {
   const int p = threadIdx.x;
   if (p >= world) return;
+  const uint32_t epoch = *epochBase + offset;
   __threadfence_system();
   volatile uint32_t *remote = flags.p[p] + rank;
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
@@ -77,6 +80,24 @@ template <class T> struct FcmDistState {
   bool imported = false;
   uint32_t epoch = 0;
   DevBuf errFlag;
+  DevBuf callVars;            // device {epoch base of this call, noise seed2 of this call}
+  uint32_t callVarsHost[2] = {0, 0};
+  int barriersThisCall = 0;
+  // CUDA graph of one call (19 launches), replayed while the arguments stay the same; runs on an internal stream joined to
+  // the caller's by events (the legacy default stream cannot be captured). UB200_DIST_GRAPH=0 disables it.
+  bool useGraph = true;
+  cudaStream_t gs = nullptr;
+  cudaEvent_t evIn = nullptr, evOut = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  struct CallKey {
+    const void *pos, *force, *out;
+    int N;
+    double temperature, prefactor;
+    bool operator==(const CallKey &o) const {
+      return pos == o.pos && force == o.force && out == o.out && N == o.N && temperature == o.temperature && prefactor == o.prefactor;
+    }
+  } key = {nullptr, nullptr, nullptr, 0, 0.0, 0.0};
+  int callsWithKey = 0;
   // optional phase timing (UB200_DIST_PROFILE=1): events between the phases of mdot, summed on the host
   static constexpr int kPhases = 12;
   bool profile = false;
@@ -102,6 +123,7 @@ template <class T> struct FcmDistState {
   int init(const double L_[3], const int cells[3], const ub200_ibm_kernel &k, double vis, uint32_t seed_, int rank_, int world_,
            int maxParticles_) {
     rank = rank_; world = world_; maxParticles = maxParticles_;
+    { const char *g = getenv("UB200_DIST_GRAPH"); useGraph = !(g && g[0] == '0'); }
     if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world || maxParticles < 1) return UB200_ERR_INVALID_ARGUMENT;
     if (cells[2] % world || cells[1] % world) return UB200_ERR_INVALID_ARGUMENT; // equal slabs in z and in ky
     if (k.support != 3 && k.support != 4 && k.support != 5 && k.support != 7) return UB200_ERR_UNSUPPORTED; // row-brick spread
@@ -160,7 +182,9 @@ template <class T> struct FcmDistState {
       if (p != rank && peerArena[p]) cudaIpcCloseMemHandle(peerArena[p]);
     if (arena) cudaFree(arena);
     arena = nullptr;
-    DevBuf *b[] = {&errFlag, &packIdx, &packRows, &packCount, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec};
+    if (exec) cudaGraphExecDestroy(exec);
+    if (gs) { cudaStreamDestroy(gs); cudaEventDestroy(evIn); cudaEventDestroy(evOut); }
+    DevBuf *b[] = {&callVars, &errFlag, &packIdx, &packRows, &packCount, &binCount, &binStart, &tileSums, &codeSlot, &unstable, &sortedIndex, &sortedRec};
     for (auto *x : b) x->release();
     plan.release();
   }
@@ -184,8 +208,8 @@ template <class T> struct FcmDistState {
   int barrier(cudaStream_t st) {
     PeerTable<uint32_t> flags;
     for (int p = 0; p < world; p++) flags.p[p] = at<uint32_t>(peerArena[p], 0);
-    epoch++;
-    peerBarrier<<<1, 32, 0, st>>>(flags, rank, world, epoch, errFlag.as<int>());
+    barriersThisCall++;
+    peerBarrier<<<1, 32, 0, st>>>(flags, rank, world, callVars.as<uint32_t>(), (uint32_t)barriersThisCall, errFlag.as<int>());
     UB200_LAUNCHED();
     return UB200_OK;
   }
@@ -194,6 +218,66 @@ template <class T> struct FcmDistState {
     if (!imported) return UB200_ERR_NOT_BUILT;
     if (N > maxParticles) return UB200_ERR_INVALID_ARGUMENT;
     int rc;
+    if ((rc = callVars.reserve(sizeof(uint32_t) * 2))) return rc;
+    // per-call variables go to the device first: barrier epochs of this call = base + 1, 2, 3; the noise seed
+    const bool noisy = temperature > 0.0;
+    if (noisy && !pseOperator) seed2++; // fourierBrownianNoise's call counter (FCM_impl.cuh:517,523)
+    callVarsHost[0] = epoch;
+    callVarsHost[1] = seed2;
+    epoch += 3;
+    const CallKey k = {pos, force, out3, N, temperature, prefactor};
+    if (!useGraph || profile) {
+      UB200_CUDA(cudaMemcpyAsync(callVars.p, callVarsHost, sizeof(callVarsHost), cudaMemcpyHostToDevice, st));
+      return enqueue(pos, force, N, temperature, prefactor, out3, st);
+    }
+    if (!gs) {
+      UB200_CUDA(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+      UB200_CUDA(cudaEventCreateWithFlags(&evIn, cudaEventDisableTiming));
+      UB200_CUDA(cudaEventCreateWithFlags(&evOut, cudaEventDisableTiming));
+    }
+    if (!(k == key)) {
+      if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+      key = k;
+      callsWithKey = 0;
+    }
+    callsWithKey++;
+    UB200_CUDA(cudaEventRecord(evIn, st));
+    UB200_CUDA(cudaStreamWaitEvent(gs, evIn, 0));
+    UB200_CUDA(cudaMemcpyAsync(callVars.p, callVarsHost, sizeof(callVarsHost), cudaMemcpyHostToDevice, gs));
+    if (callsWithKey == 1) { // first call with these arguments: plain launches (scratch allocation, function attributes)
+      rc = enqueue(pos, force, N, temperature, prefactor, out3, gs);
+    } else {
+      if (!exec) {
+        cudaGraph_t graph = nullptr;
+        UB200_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeRelaxed));
+        rc = enqueue(pos, force, N, temperature, prefactor, out3, gs);
+        const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+        if (rc || ce != cudaSuccess || !graph) {
+          if (graph) cudaGraphDestroy(graph);
+          useGraph = false;
+          if (!rc) rc = enqueue(pos, force, N, temperature, prefactor, out3, gs);
+        } else {
+          const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+          cudaGraphDestroy(graph);
+          if (ie != cudaSuccess) return cudaFail(ie);
+        }
+      }
+      if (exec) {
+        UB200_CUDA(cudaGraphLaunch(exec, gs));
+        g_launchCount += 19;
+        rc = UB200_OK;
+      }
+    }
+    if (rc) return rc;
+    UB200_CUDA(cudaEventRecord(evOut, gs));
+    UB200_CUDA(cudaStreamWaitEvent(st, evOut, 0));
+    return UB200_OK;
+  }
+
+  // the launches of one call; no host state changes, so that the sequence can be captured into a CUDA graph
+  int enqueue(const void *pos, const void *force, int N, double temperature, double prefactor, void *out3, cudaStream_t st) {
+    int rc;
+    barriersThisCall = 0;
     T *Sall = at<T>(arena, offS);                                         // first halo plane
     T *S = reinterpret_cast<T *>(reinterpret_cast<char *>(Sall) + (size_t)halo * planeBytes()); // first owned plane
     C *Tb = at<C>(arena, offT);
@@ -268,10 +352,9 @@ template <class T> struct FcmDistState {
       op.noise = temperature > 0.0;
       op.noisePrefactor = T(0);
       op.seed1 = seed; op.seed2 = seed2;
+      op.seed2Dev = callVars.as<uint32_t>() + 1;
       op.yOff = y0;
       if (op.noise) {
-        seed2++;
-        op.seed2 = seed2;
         const T fourierNormalization = (T)(1.0 / ((double)plan.nx * plan.ny * plan.nz));
         op.noisePrefactor = (T)prefactor * (T)sqrt((double)(fourierNormalization * 2 * (T)temperature / grid.cellVolume));
       }
@@ -285,6 +368,7 @@ template <class T> struct FcmDistState {
       op.deterministic = det;
       op.noise = temperature > 0.0;
       op.seed1 = seed; op.seed2 = seed2; // seed2: set by the caller before every noisy call (ub200_fcm_dist_set_noise_seed2)
+      op.seed2Dev = callVars.as<uint32_t>() + 1;
       op.yOff = y0;
       op.noisePrefactor = op.noise ? (T)prefactor * (T)sqrt(2 * (T)temperature / grid.cellVolume) : T(0);
       if ((rc = launchPassAddr<T, 0, true, PseSpectralOp<T>>(plan, az, nyl, st, op))) return rc;

@@ -16,6 +16,7 @@ template <class T> struct FcmSpectralOp {
   int noise;
   T noisePrefactor;
   uint32_t seed1, seed2;
+  const uint32_t *seed2Dev = nullptr; // when set, the second seed is read from the device (captured CUDA graphs of the step)
   int yOff = 0; // slab-decomposed transform: global ky of the first local row
 
   __device__ __forceinline__ static int fold(int i, int n) { return i - n * (i >= (n / 2 + 1)); }
@@ -36,7 +37,7 @@ template <class T> struct FcmSpectralOp {
   }
   // fcm_detail::generateNoise (FCM/utils.cuh:115-130): three float Box-Muller pairs from Saru(id, seed1, seed2)
   __device__ __forceinline__ void drawNoise(uint32_t id, C &a, C &b, C &c) const {
-    Saru rng(id, seed1, seed2);
+    Saru rng(id, seed1, seed2Dev ? *seed2Dev : seed2);
     const float sc = (float)(T(0.707106781186547) * noisePrefactor);
     float2 g = rng.gauss2(sc); a = mk2<T>((T)g.x, (T)g.y);
     g = rng.gauss2(sc); b = mk2<T>((T)g.x, (T)g.y);

@@ -16,6 +16,7 @@ template <class T> struct PseSpectralOp {
   int deterministic, noise;
   T noisePrefactor;
   uint32_t seed1, seed2;
+  const uint32_t *seed2Dev = nullptr; // when set, the second seed is read from the device (captured CUDA graphs of the step)
   int yOff = 0; // slab-decomposed transform: global ky of the first local row
 
   __device__ __forceinline__ static int fold(int i, int n) { return i - n * (i >= (n / 2 + 1)); }
@@ -33,7 +34,7 @@ template <class T> struct PseSpectralOp {
            (nxq && iy == 0 && nzq) || (ix == 0 && iy == 0 && nzq) || (ix == 0 && nyq && nzq) || (nxq && nyq && nzq);
   }
   __device__ __forceinline__ void drawNoise(uint32_t id, C &a, C &b, C &c) const { // generateNoise :161-177
-    Saru rng(id, seed1, seed2);
+    Saru rng(id, seed1, seed2Dev ? *seed2Dev : seed2);
     const float sc = (float)(T(0.707106781186547) * noisePrefactor);
     float2 g = rng.gauss2(sc); a = mk2<T>((T)g.x, (T)g.y);
     g = rng.gauss2(sc); b = mk2<T>((T)g.x, (T)g.y);
