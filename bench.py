@@ -441,6 +441,13 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
                          "note": "whole-step pipeline bytes per GPU (216 B/particle/step over all ranks); see the N=1 line for the pair kernel"},
         }
         line_out = line
+    dpd_line = None
+    if not args.no_extra:
+        import bench_extra as extra_bench
+        try:
+            dpd_line = extra_bench.dpd(dev, world=world, rank=rank)
+        except Exception as e:  # a secondary leg must not take the headline down
+            dpd_line = {"error": repr(e)[:300]}
     fcm_line = None
     if not args.no_fcm:
         import bench_fcm as fcm_bench
@@ -449,6 +456,8 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
     if rank == 0:
         if fcm_line is not None:
             line_out["fcm"] = fcm_line
+        if dpd_line is not None:
+            line_out["dpd"] = dpd_line
         print(json.dumps(line_out))
     dist.destroy_process_group()
     return 0

@@ -63,26 +63,43 @@ def verlet_reference(root, N, Lb, pos, vel, rc, dt, steps=100, warmup=20, equil=
             "what": "unmodified reference PairForces<LJ, VerletList> + VerletNVE on the same B200"}
 
 
-def dpd(dev, steps=30, warmup=5, equil=20):
-    """BASELINE config 4 shape on ONE GPU: DPD fluid, N = 4e6, rho = 3, rc = 1, A = 25, gamma = 4.5, T = 1, dt = 0.01;
-    VerletNVE + PairForces<DPD, CellList>. (The reference's Potential::DPD is a silent no-op through PairForces at this
-    commit - SURVEY F3 - so there is no reference arm for this leg.)"""
+def dpd(dev, steps=30, warmup=5, equil=300, world=1, rank=0):
+    """BASELINE config 4: DPD fluid, N = 4e6, rho = 3, rc = 1, A = 25, gamma = 4.5, T = 1, dt = 0.01; VerletNVE +
+    PairForces<DPD, CellList> on bricks with the device-side halo exchange (uammd_b200.brickmd.BrickDPDMD; one rank is a
+    1 x 1 x 1 brick, world > 1 runs under torchrun). The reference's Potential::DPD is a silent no-op through PairForces at
+    this commit, so there is no reference arm for this leg. Returns None except on rank 0."""
     from uammd_b200 import lib, synthetic as syn
+    from uammd_b200.brickmd import BrickDPDMD
     from uammd_b200.md import Box, DPD
-    from uammd_b200.multigpu import DistributedDPDMD
     N = 4_000_000
     L = (N / 3.0) ** (1.0 / 3.0)
-    p = torch.from_numpy(syn.uniform_cloud(N, L, seed=21)).to(dev)
-    v = torch.from_numpy(syn.maxwell_velocities(N, 1.0, seed=22)).to(dev)
-    f = torch.zeros(N, 4, device=dev)
-    md = DistributedDPDMD(Box(L), DPD(cutOff=1.0, dt=0.01, gamma=4.5, temperature=1.0, A=25.0, seed=99), 0.01, N)
-    for _ in range(equil):
-        md.forwardTime(p, v, f)
+    md = BrickDPDMD(Box(L), DPD(cutOff=1.0, dt=0.01, gamma=4.5, temperature=1.0, A=25.0, seed=99), 0.01, N, rank, world)
+    md.connect()
+    md.setGlobalState(torch.from_numpy(syn.uniform_cloud(N, L, seed=21)).to(dev),
+                      torch.from_numpy(syn.maxwell_velocities(N, 1.0, seed=22)).to(dev))
+    md.run(equil)
     l0 = lib().ub200_launch_count()
-    ms = _timed(dev, lambda: md.forwardTime(p, v, f), steps, warmup)
-    return {"metric": "DPD MD steps/s @4e6 particles", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms,
-            "gpu_launches": int(lib().ub200_launch_count() - l0), "kT_from_velocities": float((v * v).sum().item()) / (3.0 * N),
-            "what": "VerletNVE + PairForces<DPD, CellList>, N = 4e6, rho = 3, rc = 1, A = 25, gamma = 4.5, single GPU"}
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize(); dist.barrier()
+    ms = _timed(dev, lambda: md.run(1), steps, warmup)
+    no, nl, err = md.counts()
+    _, v, _, _ = md.owned()
+    stats = torch.tensor([ms, float((v.double() ** 2).sum()), float(no), float(nl), float(err)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = stats[:1].clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        stats[0] = mx[0]
+    if rank != 0:
+        return None
+    ms = float(stats[0])
+    return {"metric": "DPD MD steps/s @4e6 particles", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "n_gpus": world,
+            "gpu_launches": int(lib().ub200_launch_count() - l0), "kT_from_velocities": float(stats[1]) / (3.0 * N),
+            "rank_grid": list(md.rankGrid), "owned_total": int(stats[2]), "local_total_with_ghosts": int(stats[3]),
+            "error_flags": int(stats[4]),
+            "what": "VerletNVE + PairForces<DPD, CellList>, N = 4e6, rho = 3, rc = 1, A = 25, gamma = 4.5: bricks with ghost half "
+                    "cells, one peer-to-peer halo exchange per step (ghosts carry velocities, noise keyed on global ids)"}
 
 
 LANGEVIN_N, LANGEVIN_L = 1 << 20, 128.0

@@ -5,6 +5,8 @@
  *           (B) generic PairForces<Potential::LJ, b200::CellList>          (our list + the reference's own
  *                                                                           traversal kernel and user functor)
  *           (C) fast    b200::PairForcesLJ                                 (our list + our LJ traversal)
+ *           (D) column  PairForces<Potential::LJ, b200::ColumnList>        (the reference's own LJ functor through the B200
+ *                                                                           generic-Transverser column traversal)
  * It prints the largest force deviation of (B) and (C) from (A) in units of the largest force, checks that the
  * CellListData of (A) and (B) are bit identical, and runs VerletNVE with (C) for a few steps next to (A).
  * Built by oracle/Makefile (needs the reference tree) into oracle/_ref/dropin_lj; run by tests/test_dropin_gpu.py.
@@ -71,13 +73,39 @@ int main(int argc, char **argv) {
   auto A = std::make_shared<PFA>(pd, pa, potA);
   auto B = std::make_shared<PFB>(pd, pb, potA);
   auto C = std::make_shared<b200::PairForcesLJ>(pd, pc, potC);
+  using PFD = PairForces<Potential::LJ, b200::ColumnList>;
+  PFD::Parameters pdd; pdd.box = box;
+  auto D = std::make_shared<PFD>(pd, pdd, potA);
 
-  auto fA = forcesOf(pd, A), fB = forcesOf(pd, B), fC = forcesOf(pd, C);
-  double fmax = 0, dB = 0, dC = 0;
+  auto fA = forcesOf(pd, A), fB = forcesOf(pd, B), fC = forcesOf(pd, C), fD = forcesOf(pd, D);
+  double fmax = 0, dB = 0, dC = 0, dD = 0;
   for (int i = 0; i < N; i++) {
     fmax = std::max({fmax, (double)std::abs(fA[i].x), (double)std::abs(fA[i].y), (double)std::abs(fA[i].z)});
     dB = std::max({dB, (double)std::abs(fA[i].x - fB[i].x), (double)std::abs(fA[i].y - fB[i].y), (double)std::abs(fA[i].z - fB[i].z)});
     dC = std::max({dC, (double)std::abs(fA[i].x - fC[i].x), (double)std::abs(fA[i].y - fC[i].y), (double)std::abs(fA[i].z - fC[i].z)});
+    dD = std::max({dD, (double)std::abs(fA[i].x - fD[i].x), (double)std::abs(fA[i].y - fD[i].y), (double)std::abs(fA[i].z - fD[i].z)});
+  }
+  // energy + virial through the reference's own functor (a five-word quantity) over the column traversal
+  double dE = 0, dV = 0, emax = 0, vmax = 0;
+  {
+    auto ev = [&](std::shared_ptr<Interactor> it, std::vector<real> &e, std::vector<real> &v) {
+      {
+        auto en = pd->getEnergy(access::gpu, access::write); thrust::fill(thrust::cuda::par, en.begin(), en.end(), real());
+        auto vi = pd->getVirial(access::gpu, access::write); thrust::fill(thrust::cuda::par, vi.begin(), vi.end(), real());
+        auto f = pd->getForce(access::gpu, access::write); thrust::fill(thrust::cuda::par, f.begin(), f.end(), real4());
+      }
+      Interactor::Computables comp; comp.force = true; comp.energy = true; comp.virial = true;
+      it->sum(comp, 0);
+      CudaSafeCall(cudaDeviceSynchronize());
+      auto en = pd->getEnergy(access::cpu, access::read); e.assign(en.begin(), en.end());
+      auto vi = pd->getVirial(access::cpu, access::read); v.assign(vi.begin(), vi.end());
+    };
+    std::vector<real> eA, vA, eD, vD;
+    ev(A, eA, vA); ev(D, eD, vD);
+    for (int i = 0; i < N; i++) {
+      emax = std::max(emax, (double)std::abs(eA[i])); vmax = std::max(vmax, (double)std::abs(vA[i]));
+      dE = std::max(dE, (double)std::abs(eA[i] - eD[i])); dV = std::max(dV, (double)std::abs(vA[i] - vD[i]));
+    }
   }
   // CellListData bit parity between the reference list and ours
   auto clA = pa.nl->getCellList();
@@ -121,8 +149,9 @@ int main(int argc, char **argv) {
     for (int i = 0; i < N; i++)
       dpos = std::max({dpos, (double)std::abs(p1[i].x - p2[i].x), (double)std::abs(p1[i].y - p2[i].y), (double)std::abs(p1[i].z - p2[i].z)});
   }
-  printf("{\"N\":%d,\"fmax\":%.6g,\"generic_vs_ref\":%.6g,\"fast_vs_ref\":%.6g,\"celllist_mismatches\":%ld,\"nve20_max_dpos\":%.6g}\n",
-         N, fmax, dB / fmax, dC / fmax, mismatches, dpos);
+  printf("{\"N\":%d,\"fmax\":%.6g,\"generic_vs_ref\":%.6g,\"fast_vs_ref\":%.6g,\"column_generic_vs_ref\":%.6g,\"column_energy_vs_ref\":%.6g,"
+         "\"column_virial_vs_ref\":%.6g,\"celllist_mismatches\":%ld,\"nve20_max_dpos\":%.6g}\n",
+         N, fmax, dB / fmax, dC / fmax, dD / fmax, dE / emax, dV / vmax, mismatches, dpos);
   sys->finish();
   return 0;
 }

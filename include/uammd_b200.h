@@ -128,6 +128,23 @@ int ub200_ljengine_destroy(ub200_ljengine *e);
 int ub200_ljengine_sum_f32(ub200_ljengine *e, const void *d_pos, const int *d_groupIdx, int N, const float L[3],
                            const int periodic[3], const float *params, int ntypes, void *d_force, float *d_energy,
                            float *d_virial, const int *d_globalIdx, int accumulate, int ownerLo, int ownerHi, void *stream);
+/* The neighbour search alone: builds the half-cell list for this cut-off (UB200_ERR_UNSUPPORTED when a periodic dimension has
+ * fewer than five half cells: use ub200_celllist_build_f32 there). ub200_ljengine_view_get exposes it to the header-template
+ * traversal of include/uammd_b200/uammd_b200.cuh (b200::ColumnList::transverseList), which runs ANY user Transverser
+ * (utils/TransverserUtils.cuh:151-274) over it: d_pos real4[N] in list order, folded into the box and consistent with the
+ * cells (w = type); d_index[k] = group index of list slot k; d_cellStart[c] .. d_cellStart[c + 1] = slots of half cell
+ * c = x + cells[0] (y + cells[1] z). */
+typedef struct {
+  const void *d_pos;
+  const int *d_index;
+  const uint32_t *d_cellStart;
+  int cells[3], periodic[3];
+  float L[3];
+  int numberParticles;
+} ub200_ljengine_view;
+int ub200_ljengine_build_f32(ub200_ljengine *e, const void *d_pos, const int *d_groupIdx, int N, const float L[3],
+                             const int periodic[3], float cutOff, void *stream);
+int ub200_ljengine_view_get(ub200_ljengine *e, ub200_ljengine_view *view);
 /* the traversal kernel alone over the list of the last ub200_ljengine_sum_f32 call (positions unchanged; kernel timing
  * and profiling). Forces only; UB200_ERR_NOT_BUILT unless that call took the column path. */
 int ub200_ljengine_traverse_f32(ub200_ljengine *e, void *d_force, int accumulate, void *stream);
@@ -197,6 +214,15 @@ int ub200_brick_lj_forces_f32(ub200_brick *b, const float *params, int ntypes, v
  * bricks: kick + drift + exchange, list build over the window, forces of the owned block, kick. */
 int ub200_brick_lj_nve_run_f32(ub200_brick *b, const float *params, int ntypes, float dt, int nsteps, void *stream);
 int ub200_brick_lj_nve_phase_f32(ub200_brick *b, int phase, const float *params, int ntypes, float dt, int doKick, void *stream);
+/* The same loop with one PairForces<Potential::DPD> interactor (BASELINE config 4: "DPD fluid, ghost-cell halo exchange,
+ * domain-decomposed over 8 GPUs"). Create the bricks with cutOff = rcut. DPD_impl::ForceTransverser (Potential/DPD.cuh:92-159);
+ * sigma = sqrt(2 T) / sqrt(dt) as DPD_impl computes it; ghosts carry their velocities and the pair noise is keyed on the
+ * GLOBAL ids (ij = min + N max), so the trajectory is the single-GPU one for every rank grid. The step counter of the noise
+ * starts at 1 with the first force evaluation and advances by one per evaluation (DPD.cuh:165). */
+int ub200_brick_dpd_nve_run_f32(ub200_brick *b, float A, float gamma, float sigma, float rcut, uint32_t seed, float dt, int nsteps,
+                                void *stream);
+int ub200_brick_dpd_nve_phase_f32(ub200_brick *b, int phase, float A, float gamma, float sigma, float rcut, uint32_t seed, float dt,
+                                  int doKick, void *stream);
 int ub200_brick_info(ub200_brick *b, ub200_brick_info_t *info);
 /* owned block <-> host buffers (pinned for asynchronous copies): pos real4[n], vel real3[n], ids int[n] (may be NULL);
  * n = the owned count ub200_brick_counts reported. The upload replaces the owned block in place. */

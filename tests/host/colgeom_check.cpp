@@ -1,7 +1,7 @@
-// Host check of uammd_b200/csrc/colgeom.h: for every home half cell of every column of a set of grids, the cells (and
+// Host check of include/uammd_b200/colgeom.h: for every home half cell of every column of a set of grids, the cells (and
 // image shifts) reached through planes hz .. hz+4 of the column's staged rows must be exactly the 5 x 5 x 5 stencil
 // around the home cell (each periodic image once, nothing outside a non periodic box), in ascending (z, y, x) order.
-#include "../../uammd_b200/csrc/colgeom.h"
+#include "../../include/uammd_b200/colgeom.h"
 #include <cstdio>
 #include <cstdlib>
 #include <tuple>

@@ -1,7 +1,7 @@
 // Host emulation of the column traversal's data path (uammd_b200/csrc/lj_column.cu + colgeom.h): bin random particles on
 // the half-cell grid with canonical coordinates, stage every column row by row with the image shifts, and check that
 // the in-range pair set of every home particle equals the brute-force minimum-image pair set.
-#include "../../uammd_b200/csrc/colgeom.h"
+#include "../../include/uammd_b200/colgeom.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

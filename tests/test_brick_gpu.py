@@ -13,8 +13,8 @@ import pytest
 import torch
 
 from uammd_b200 import synthetic as syn
-from uammd_b200.brickmd import BrickLJMD, assemble
-from uammd_b200.md import Box, LJ, LJMD
+from uammd_b200.brickmd import BrickDPDMD, BrickLJMD, assemble
+from uammd_b200.md import Box, DPD, LJ, LJMD, PairForcesDPD, VerletNVE
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -116,6 +116,44 @@ def test_particles_migrate_between_bricks(cuda):
     p, v, _ = assemble(parts, N)
     ps, vs, _ = _single(cuda, N, Lb, pos, vel, pot, steps)
     assert np.array_equal(p, ps) and np.array_equal(v, vs)
+
+
+@pytest.mark.parametrize("rankGrid", [(1, 1, 1), (2, 1, 1), (2, 2, 2)])
+def test_dpd_bricks_bit_identical_to_single_gpu(cuda, rankGrid):
+    """BASELINE config 4 scaled down (DPD fluid at rho = 3, rc = 1, A = 25, gamma = 4.5, kT = 1, dt = 0.01): ghosts carry
+    velocities, the pair noise is keyed on global ids, particles migrate during the run. Oracle: VerletNVE +
+    PairForcesDPD on one GPU (itself checked against the reference's compiled transverser)."""
+    N, steps, dt = 24000, 15, 0.01
+    L = (N / 3.0) ** (1.0 / 3.0)
+    pos, vel = syn.uniform_cloud(N, L, seed=21), syn.maxwell_velocities(N, 1.0, seed=22)
+    box = Box(L)
+    mk = lambda: DPD(cutOff=1.0, dt=dt, gamma=4.5, temperature=1.0, A=25.0, seed=4321)
+    world = int(np.prod(rankGrid))
+    ranks = [BrickDPDMD(box, mk(), dt, N, r, world, rankGrid) for r in range(world)]
+    BrickLJMD.connectLocal(ranks)
+    dp, dv = torch.from_numpy(pos).to(cuda), torch.from_numpy(vel).to(cuda)
+    for r in ranks:
+        r.setGlobalState(dp, dv)
+    BrickLJMD.runLocal(ranks, steps)
+    parts = [r.owned() for r in ranks]
+    assert all(r.counts()[2] == 0 for r in ranks)
+    p, v, f = assemble(parts, N)
+
+    class _It:  # Interactor over the single-GPU DPD path: VerletNVE hands it positions, it needs the velocities too
+        def __init__(self, vel):
+            self.pf, self.vel = PairForcesDPD(mk(), box), vel
+
+        def sum(self, pos, force=None, **kw):
+            self.pf.sum(pos, self.vel, force)
+
+    ps, vs = dp.clone(), dv.clone()
+    nve = VerletNVE(ps, vs, dt)
+    nve.addInteractor(_It(vs))
+    for _ in range(steps):
+        nve.forwardTime()
+    torch.cuda.synchronize()
+    assert np.array_equal(p, ps.cpu().numpy()) and np.array_equal(v, vs.cpu().numpy())
+    assert np.array_equal(f[:, :3], nve.force.cpu().numpy()[:, :3])
 
 
 def test_unsupported_decompositions_are_reported(cuda):

@@ -1,4 +1,4 @@
-"""CPU: the index geometry of the column traversal (uammd_b200/csrc/colgeom.h), compiled for the host.
+"""CPU: the index geometry of the column traversal (include/uammd_b200/colgeom.h), compiled for the host.
 
 colgeom_check: every home half cell reaches exactly the 5 x 5 x 5 stencil (cells + image shifts, in staging order).
 colpairs_check: emulation of the staged data path (canonical coordinates, row pieces, image shifts) finds exactly the

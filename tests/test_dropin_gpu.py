@@ -25,6 +25,8 @@ def test_pairforces_dropin_matches_reference():
     assert r["celllist_mismatches"] == 0                 # CellListData bit identical to the reference's
     assert r["generic_vs_ref"] == 0.0                    # reference kernel + user functor on our list: same bits
     assert r["fast_vs_ref"] < 1e-4                       # specialised traversal: fp32 rounding only (units of max |F|)
+    # the reference's LJ functor through the generic-Transverser column traversal (b200::ColumnList): force, energy, virial
+    assert r["column_generic_vs_ref"] < 1e-4 and r["column_energy_vs_ref"] < 1e-4 and r["column_virial_vs_ref"] < 1e-4
     assert r["nve20_max_dpos"] < 1e-4                    # 20 VerletNVE steps next to the reference
 
 
@@ -70,6 +72,7 @@ def test_dpd_dropin_matches_reference_and_thermostats():
     r = _run("dropin_dpd", 81000, 2000)
     print(r)
     assert r["fast_vs_ref"] < 2e-5
+    assert r["column_generic_vs_ref"] < 2e-5                # general transverser (getInfo) through b200::ColumnList
     assert abs(r["kT_measured"] - r["kT_target"]) < 0.03
 
 

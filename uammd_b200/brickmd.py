@@ -44,6 +44,8 @@ def _declare():
         "ub200_brick_lj_forces_f32": [vp, fp, i, vp],
         "ub200_brick_lj_nve_run_f32": [vp, fp, i, f, i, vp],
         "ub200_brick_lj_nve_phase_f32": [vp, i, fp, i, f, i, vp],
+        "ub200_brick_dpd_nve_run_f32": [vp, f, f, f, f, C.c_uint32, f, i, vp],
+        "ub200_brick_dpd_nve_phase_f32": [vp, i, f, f, f, f, C.c_uint32, f, i, vp],
         "ub200_brick_info": [vp, C.POINTER(BrickInfo)],
         "ub200_brick_counts": [vp, vp, ip, ip, ip],
         "ub200_brick_profile": [vp, C.POINTER(C.c_double)],
@@ -58,7 +60,7 @@ def _declare():
 
 
 def half_cells(box, cutOff):
-    """Half cells per dimension of the engine's grid (colCellsFor in uammd_b200/csrc/colgeom.h)."""
+    """Half cells per dimension of the engine's grid (colCellsFor in include/uammd_b200/colgeom.h)."""
     return tuple(1 if l == 0.0 else max(1, int(2.0 * l / (cutOff * 1.00001))) for l in box.boxSize)
 
 
@@ -183,6 +185,34 @@ class BrickLJMD:
             parts = [None] * self.world
             dist.all_gather_object(parts, tuple(t.cpu() for t in (pos, vel, gid, force)), group=group)
         return assemble(parts, self.N)
+
+
+class BrickDPDMD(BrickLJMD):
+    """One rank of the brick-decomposed DPD fluid (BASELINE config 4). pot: uammd_b200.md.DPD (cutOff, dt, gamma,
+    temperature, A, seed); the oracle is VerletNVE + PairForcesDPD on one GPU, reproduced bit for bit."""
+
+    def __init__(self, box, pot, dt, N, rank, world, rankGrid=None, capacity=0):
+        class _Cut:  # the brick geometry only needs the cut-off
+            ntypes = 1
+
+            def getCutOff(self_inner):
+                return pot.getCutOff()
+
+            def table(self_inner):
+                return np.zeros(4, np.float32)
+        super().__init__(box, _Cut(), dt, N, rank, world, rankGrid, capacity)
+        self.dpd = pot
+
+    def _args(self):
+        p = self.dpd
+        return (float(p.A), float(p.gamma), float(p.sigma), float(p.rcut), int(p.seed) & 0xFFFFFFFF, self.dt)
+
+    def run(self, nsteps, stream=None):
+        check(self.lib.ub200_brick_dpd_nve_run_f32(self._h, *self._args(), int(nsteps), _stream_ptr(stream)))
+
+    def phase(self, phase, doKick=True, stream=None):
+        a = self._args()
+        check(self.lib.ub200_brick_dpd_nve_phase_f32(self._h, int(phase), *a, int(doKick), _stream_ptr(stream)))
 
 
 def assemble(parts, N):

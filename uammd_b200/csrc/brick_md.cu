@@ -332,6 +332,8 @@ struct ub200_brick {
   bool attached = false, ipcOpened[kBrickMaxRanks] = {};
   bool prepared = false;
   ub200_ljengine *eng = nullptr;
+  ub200_celllist *cl = nullptr; // DPD: reference-layout list over the local arrays (cells >= cutOff, global grid)
+  uint32_t dpdStep = 0;         // DPD_impl::step: incremented before every force evaluation (DPD.cuh:165)
   // CUDA graph of kGraphSteps consecutive steps (the whole step is device driven: counts, exchange number and inbox parity
   // live on the device, so one captured sequence replays for every step). Runs on an internal stream joined to the caller's
   // by events (the legacy default stream cannot be captured). exec[c]: graph captured with state buffer c current.
@@ -443,7 +445,20 @@ int ub200_brick_create(ub200_brick **out, int rank, const int rankGrid[3], const
                   rankGrid[0] > 1, rankGrid[1] > 1, rankGrid[2] > 1};
   h->rc = cutOff;
   h->N = numberParticles;
-  h->cap = capacity > 0 ? capacity : (int)std::min<double>(numberParticles + 4096.0, 1.3 * numberParticles * frac + 16384.0);
+  // Capacity: the senders address the receivers' inboxes with THEIR OWN layout constants, so every rank must arrive at the
+  // same numbers: the default is derived from the LARGEST window of the rank grid, not from this rank's.
+  double maxFrac = 0.0;
+  for (int r = 0; r < world; r++) {
+    const int kr[3] = {r % rankGrid[0], (r / rankGrid[0]) % rankGrid[1], r / (rankGrid[0] * rankGrid[1])};
+    double f = 1.0;
+    for (int d = 0; d < 3; d++) {
+      const int lo = brickLo(kr[d], dims[d], rankGrid[d]), hi = brickLo(kr[d] + 1, dims[d], rankGrid[d]);
+      f *= rankGrid[d] == 1 ? 1.0 : (double)(hi - lo + 4) / dims[d];
+    }
+    maxFrac = std::max(maxFrac, f);
+  }
+  (void)frac;
+  h->cap = capacity > 0 ? capacity : (int)std::min<double>(numberParticles + 4096.0, 1.3 * numberParticles * maxFrac + 16384.0);
   int rc;
   for (int s = 0; s < 2; s++) {
     if ((rc = h->pos[s].reserve(sizeof(float4) * (size_t)h->cap)) || (rc = h->vel[s].reserve(sizeof(float) * 3 * (size_t)h->cap)) ||
@@ -466,7 +481,7 @@ int ub200_brick_create(ub200_brick **out, int rank, const int rankGrid[3], const
   for (int p = 0; p < 2 * world; p++) cudaMemset((char *)h->arena + ar.inboxOff + p * ar.segBytes, 0, kHdrBytes);
   for (int p = 0; p < kBrickMaxRanks; p++) ar.p[p] = nullptr;
   ar.p[rank] = (char *)h->arena;
-  if ((rc = ub200_ljengine_create(&h->eng))) { cudaFree(h->arena); delete h; return rc; }
+  if ((rc = ub200_ljengine_create(&h->eng)) || (rc = ub200_celllist_create(&h->cl))) { cudaFree(h->arena); delete h; return rc; }
   h->attached = world == 1;
   const char *gr = getenv("UB200_BRICK_GRAPH"); // "0": plain launches instead of the captured step graph
   h->useGraph = !(gr && gr[0] == '0');
@@ -490,6 +505,7 @@ int ub200_brick_destroy(ub200_brick *h) {
     if (e) cudaGraphExecDestroy(e);
   if (h->gs) { cudaStreamDestroy(h->gs); cudaEventDestroy(h->evIn); cudaEventDestroy(h->evOut); }
   ub200_ljengine_destroy(h->eng);
+  ub200_celllist_destroy(h->cl);
   DevBuf *b[] = {&h->pos[0], &h->pos[1], &h->vel[0], &h->vel[1], &h->gid[0], &h->gid[1], &h->force, &h->counts, &h->work, &h->err};
   for (auto *x : b) x->release();
   delete h;
@@ -567,6 +583,41 @@ int ub200_brick_lj_forces_f32(ub200_brick *h, const float *params, int ntypes, v
   return rc;
 }
 
+// DPD forces of the owned block (DPD_impl::ForceTransverser, Interactor/Potential/DPD.cuh:92-159): cell list over
+// [owned | ghosts] with the cells ordered by global id, ghosts bring their velocities, the pairwise noise is keyed on global
+// ids (ij = min + N max with N the GLOBAL particle number), so every pair draws the single-GPU random force.
+struct BrickDPD {
+  float A, gamma, sigma, rcut;
+  uint32_t seed;
+};
+static int brickForcesDPD(ub200_brick *h, const BrickDPD &p, cudaStream_t st) {
+  const int c = h->cur;
+  int cd[3], rc;
+  if ((rc = ub200_neighbour_celldim_f32(h->L, p.rcut, cd))) return rc;
+  if ((rc = celllistBuildEx(h->cl, h->pos[c].p, nullptr, h->cap, h->counts.as<int>() + 1, h->gid[c].as<int>(), h->L, h->periodic, cd,
+                            (void *)st)))
+    return rc;
+  brickMark(h, 3, st);
+  h->dpdStep++;
+  rc = dpdSum(h->cl, h->vel[c].p, p.A, p.gamma, p.sigma, p.rcut, p.seed, h->dpdStep, h->N, h->force.p, nullptr, 0, 0x7fffffff, 0,
+              (void *)st, h->gid[c].as<int>(), h->counts.as<int>());
+  brickMark(h, 4, st);
+  return rc;
+}
+static int brickStepsDPD(ub200_brick *h, const BrickDPD &p, float dt, int nsteps, cudaStream_t st) {
+  int rc;
+  for (int s = 0; s < nsteps; s++) {
+    if ((rc = brickExchange(h, dt, s == 0 || h->profile ? 1 : 2, st)) || (rc = brickForcesDPD(h, p, st))) return rc;
+    if (s == nsteps - 1 || h->profile) {
+      brickKick2<<<(h->cap + 255) / 256, 256, 0, st>>>(h->vel[h->cur].as<float>(), h->force.as<float4>(), h->counts.as<int>(), dt);
+      UB200_LAUNCHED();
+    }
+    brickMark(h, 5, st);
+    brickCollect(h, st);
+  }
+  return UB200_OK;
+}
+
 // nsteps consecutive steps: the closing kick of a step is fused with the opening kick + drift of the next one
 static int brickSteps(ub200_brick *h, const float *params, int ntypes, float dt, int nsteps, cudaStream_t st) {
   int rc;
@@ -607,8 +658,8 @@ int ub200_brick_lj_nve_run_f32(ub200_brick *h, const float *params, int ntypes, 
     h->graphParams.assign(params, params + np);
     h->graphDt = dt;
   }
-  UB200_CUDA(cudaEventRecord(h->evIn, st));
-  UB200_CUDA(cudaStreamWaitEvent(h->gs, h->evIn, 0));
+  // graphs are CAPTURED on the internal stream (the caller's may be the legacy default stream, which cannot capture) and
+  // LAUNCHED on the caller's stream: no event hops between streams on the step path
   int done = 0;
   while (nsteps - done >= kGraphSteps) {
     const int c = h->cur;
@@ -621,7 +672,7 @@ int ub200_brick_lj_nve_run_f32(ub200_brick *h, const float *params, int ntypes, 
         if (graph) cudaGraphDestroy(graph);
         h->useGraph = false; // fall back to plain launches for good
         h->cur = c;
-        if ((rc = brickSteps(h, params, ntypes, dt, nsteps - done, h->gs))) return rc;
+        if ((rc = brickSteps(h, params, ntypes, dt, nsteps - done, st))) return rc;
         done = nsteps;
         break;
       }
@@ -630,7 +681,7 @@ int ub200_brick_lj_nve_run_f32(ub200_brick *h, const float *params, int ntypes, 
       if (ie != cudaSuccess) return cudaFail(ie);
       // capturing ran the host side of the steps only (kGraphSteps is even: h->cur is back at c)
     }
-    UB200_CUDA(cudaGraphLaunch(h->exec[c], h->gs));
+    UB200_CUDA(cudaGraphLaunch(h->exec[c], st));
     g_launchCount += 11 * kGraphSteps; // kernels of the replayed steps
     done += kGraphSteps;
   }
@@ -651,14 +702,42 @@ int ub200_brick_lj_nve_run_f32(ub200_brick *h, const float *params, int ntypes, 
       cudaGraphDestroy(graph);
       if (ie != cudaSuccess) return cudaFail(ie);
     }
-    UB200_CUDA(cudaGraphLaunch(h->exec1[c], h->gs));
+    UB200_CUDA(cudaGraphLaunch(h->exec1[c], st));
     g_launchCount += 12;
     h->cur = c ^ 1;
     done++;
   }
-  if (done < nsteps && (rc = brickSteps(h, params, ntypes, dt, nsteps - done, h->gs))) return rc;
-  UB200_CUDA(cudaEventRecord(h->evOut, h->gs));
-  UB200_CUDA(cudaStreamWaitEvent(st, h->evOut, 0));
+  if (done < nsteps && (rc = brickSteps(h, params, ntypes, dt, nsteps - done, st))) return rc;
+  return UB200_OK;
+}
+
+// VerletNVE::forwardTime x nsteps with one PairForces<Potential::DPD> interactor on the bricks (BASELINE config 4)
+int ub200_brick_dpd_nve_run_f32(ub200_brick *h, float A, float gamma, float sigma, float rcut, uint32_t seed, float dt, int nsteps,
+                                void *stream) {
+  if (!h || !(rcut > 0) || nsteps < 0) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const BrickDPD p = {A, gamma, sigma, rcut, seed};
+  int rc;
+  if (!h->prepared) {
+    if ((rc = brickExchange(h, 0.0f, 0, st)) || (rc = brickForcesDPD(h, p, st))) return rc;
+    h->prepared = true;
+  }
+  return brickStepsDPD(h, p, dt, nsteps, st);
+}
+int ub200_brick_dpd_nve_phase_f32(ub200_brick *h, int phase, float A, float gamma, float sigma, float rcut, uint32_t seed, float dt,
+                                  int doKick, void *stream) {
+  if (!h || !(rcut > 0) || (phase != 0 && phase != 1)) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const BrickDPD p = {A, gamma, sigma, rcut, seed};
+  int rc;
+  if ((rc = brickExchangePhase(h, phase, dt, doKick, st))) return rc;
+  if (phase == 0) return UB200_OK;
+  if ((rc = brickForcesDPD(h, p, st))) return rc;
+  h->prepared = true;
+  if (doKick) {
+    brickKick2<<<(h->cap + 255) / 256, 256, 0, st>>>(h->vel[h->cur].as<float>(), h->force.as<float4>(), h->counts.as<int>(), dt);
+    UB200_LAUNCHED();
+  }
   return UB200_OK;
 }
 

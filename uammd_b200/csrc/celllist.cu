@@ -18,9 +18,10 @@ thread_local int g_lastCudaError = 0;
 unsigned long long g_launchCount = 0;
 
 __global__ void __launch_bounds__(256)
-binParticles(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, GridF g,
+binParticles(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, const int *__restrict__ nDev, GridF g,
              uint32_t *__restrict__ binCount, uint2 *__restrict__ codeSlot, int *__restrict__ errorFlag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nDev) N = min(N, *nDev); // optional device-side particle count (multi-GPU bricks)
   if (i >= N) return;
   const float4 p = ldg4(pos + (groupIdx ? groupIdx[i] : i));
   int cx = cellCoord(p.x, g.Lx, g.mx, g.hLx, g.ix, g.nx);
@@ -161,8 +162,9 @@ __global__ void __launch_bounds__(kScanThreads) scanApply(uint32_t *__restrict__
 
 __global__ void __launch_bounds__(256)
 scatterToBins(const uint2 *__restrict__ codeSlot, const uint32_t *__restrict__ binStart, int N,
-              int *__restrict__ unstable) {
+              int *__restrict__ unstable, const int *__restrict__ nDev = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nDev) N = min(N, *nDev);
   if (i >= N) return;
   const uint2 cs = codeSlot[i];
   if (cs.x == 0xffffffffu) return; // particle outside the caller's window (slab-decomposed IBM)
@@ -174,14 +176,20 @@ orderAndGather(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
                const uint32_t *__restrict__ binStart, const float4 *__restrict__ pos,
                const int *__restrict__ groupIdx, int N, GridF g, uint32_t validCell,
                float4 *__restrict__ sortPos, int *__restrict__ groupIndex, uint32_t *__restrict__ cellStart,
-               int *__restrict__ cellEnd) {
+               int *__restrict__ cellEnd, const int *__restrict__ nDev = nullptr, const int *__restrict__ sortKey = nullptr) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nDev) N = min(N, *nDev);
   if (k >= N) return;
   const int i = unstable[k];
   const uint32_t code = codeSlot[i].x;
   const int s = (int)binStart[code], e = (int)binStart[code + 1];
   int rank = 0;
-  for (int j = s; j < e; j++) rank += (__ldg(unstable + j) < i);
+  if (sortKey) { // order inside a cell by a caller-supplied key (global particle ids of a multi-GPU brick)
+    const int ki = sortKey[i];
+    for (int j = s; j < e; j++) rank += (sortKey[__ldg(unstable + j)] < ki);
+  } else {
+    for (int j = s; j < e; j++) rank += (__ldg(unstable + j) < i);
+  }
   const int dst = s + rank;
   groupIndex[dst] = i;
   sortPos[dst] = ldg4(pos + (groupIdx ? groupIdx[i] : i));
@@ -234,7 +242,7 @@ int ub200_celllist_create(ub200_celllist **out) {
 int ub200_celllist_destroy(ub200_celllist *cl) {
   if (!cl) return UB200_OK;
   DevBuf *bufs[] = {&cl->sortPos, &cl->groupIndex, &cl->cellStart, &cl->cellEnd, &cl->binCount,
-                    &cl->binStart, &cl->blockSums, &cl->codeSlot, &cl->unstable, &cl->errorFlag};
+                    &cl->binStart, &cl->blockSums, &cl->codeSlot, &cl->unstable, &cl->errorFlag, &cl->ljTable.dev};
   for (DevBuf *b : bufs) b->release();
   delete cl;
   return UB200_OK;
@@ -252,6 +260,13 @@ int ub200_neighbour_celldim_f32(const float L[3], float rc, int cellDim[3]) {
 
 int ub200_celllist_build_f32(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx, int N,
                              const float L[3], const int periodic[3], const int cellDim[3], void *stream) {
+  return ub200::celllistBuildEx(cl, d_pos, d_groupIdx, N, nullptr, nullptr, L, periodic, cellDim, stream);
+}
+}
+
+// N: launch bound; nDev: optional device-side particle count (<= N); sortKey: optional order key inside a cell
+int ub200::celllistBuildEx(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx, int N, const int *nDev, const int *sortKey,
+                           const float L[3], const int periodic[3], const int cellDim[3], void *stream) {
   if (!cl || !d_pos || N <= 0 || !L || !periodic || !cellDim) return UB200_ERR_INVALID_ARGUMENT;
   for (int d = 0; d < 3; d++)
     if (cellDim[d] < 1 || cellDim[d] > 1024) return UB200_ERR_INVALID_ARGUMENT; // 10 bit Morton fields
@@ -311,22 +326,24 @@ int ub200_celllist_build_f32(ub200_celllist *cl, const void *d_pos, const int *d
   for (int d = 0; d < 3; d++) cl->cellDim[d] = cellDim[d];
 
   const int nb = (N + 255) / 256;
-  binParticles<<<nb, 256, 0, st>>>((const float4 *)d_pos, d_groupIdx, N, g, cl->binCount.as<uint32_t>(),
+  binParticles<<<nb, 256, 0, st>>>((const float4 *)d_pos, d_groupIdx, N, nDev, g, cl->binCount.as<uint32_t>(),
                                    cl->codeSlot.as<uint2>(), cl->errorFlag.as<int>());
   UB200_LAUNCHED();
   if ((rc = exclusiveScanAndClear(cl->binCount.as<uint32_t>(), nbins, cl->binStart.as<uint32_t>(),
                                   cl->blockSums.as<uint32_t>(), st)))
     return rc;
-  scatterToBins<<<nb, 256, 0, st>>>(cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(), N, cl->unstable.as<int>());
+  scatterToBins<<<nb, 256, 0, st>>>(cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(), N, cl->unstable.as<int>(), nDev);
   UB200_LAUNCHED();
   orderAndGather<<<nb, 256, 0, st>>>(cl->unstable.as<int>(), cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(),
                                      (const float4 *)d_pos, d_groupIdx, N, g, cl->validCell,
                                      cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
-                                     cl->cellStart.as<uint32_t>(), cl->cellEnd.as<int>());
+                                     cl->cellStart.as<uint32_t>(), cl->cellEnd.as<int>(), nDev, sortKey);
   UB200_LAUNCHED();
   cl->built = 1;
   return UB200_OK;
 }
+
+extern "C" {
 
 int ub200_celllist_view_get(ub200_celllist *cl, ub200_celllist_view *v) {
   if (!cl || !v) return UB200_ERR_INVALID_ARGUMENT;

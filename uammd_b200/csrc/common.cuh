@@ -152,6 +152,18 @@ int scatterToBinsLaunch(const uint2 *codeSlot, const uint32_t *binStart, int N, 
 
 } // namespace ub200
 
+struct ub200_celllist;
+namespace ub200 {
+// ub200_celllist_build_f32 with an optional device-side particle count (N = launch bound) and an optional key deciding the
+// order inside a cell (multi-GPU bricks: global particle ids)
+// DPD forces over a built cell list (pair_dpd.cu); ownerHiDev: optional device-side upper bound of the owned index range
+int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut, uint32_t seed, uint32_t step,
+           int idStride, void *d_force, const int *d_globalIdx, int ownerLo, int ownerHi, int accumulate, void *stream,
+           const int *d_noiseId = nullptr, const int *ownerHiDev = nullptr);
+int celllistBuildEx(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx, int N, const int *nDev, const int *sortKey,
+                    const float L[3], const int periodic[3], const int cellDim[3], void *stream);
+} // namespace ub200
+
 // Opaque handle behind ub200_celllist
 struct ub200_celllist {
   ub200::GridF grid;
@@ -169,6 +181,8 @@ struct ub200_celllist {
   ub200::DevBuf unstable;                                // scatter target before the stable fix-up
   ub200::DevBuf errorFlag;
   size_t cellStartCells = 0;
+  ub200::LJTableCache ljTable;                           // parameter table of the LJ traversals over this list (per handle:
+                                                         // two interactors never share or re-upload each other's table)
 };
 
 // Opaque handle behind ub200_verletlist (VerletList / VerletListBase / BasicNeighbourListBase of the reference)

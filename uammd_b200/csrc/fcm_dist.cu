@@ -241,11 +241,11 @@ template <class T> struct FcmDistState {
       callsWithKey = 0;
     }
     callsWithKey++;
-    UB200_CUDA(cudaEventRecord(evIn, st));
-    UB200_CUDA(cudaStreamWaitEvent(gs, evIn, 0));
-    UB200_CUDA(cudaMemcpyAsync(callVars.p, callVarsHost, sizeof(callVarsHost), cudaMemcpyHostToDevice, gs));
+    // the graph is CAPTURED on the internal stream (the caller's may be the legacy default stream, which cannot capture) and
+    // LAUNCHED on the caller's stream
+    UB200_CUDA(cudaMemcpyAsync(callVars.p, callVarsHost, sizeof(callVarsHost), cudaMemcpyHostToDevice, st));
     if (callsWithKey == 1) { // first call with these arguments: plain launches (scratch allocation, function attributes)
-      rc = enqueue(pos, force, N, temperature, prefactor, out3, gs);
+      rc = enqueue(pos, force, N, temperature, prefactor, out3, st);
     } else {
       if (!exec) {
         cudaGraph_t graph = nullptr;
@@ -255,7 +255,7 @@ template <class T> struct FcmDistState {
         if (rc || ce != cudaSuccess || !graph) {
           if (graph) cudaGraphDestroy(graph);
           useGraph = false;
-          if (!rc) rc = enqueue(pos, force, N, temperature, prefactor, out3, gs);
+          if (!rc) rc = enqueue(pos, force, N, temperature, prefactor, out3, st);
         } else {
           const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
           cudaGraphDestroy(graph);
@@ -263,15 +263,12 @@ template <class T> struct FcmDistState {
         }
       }
       if (exec) {
-        UB200_CUDA(cudaGraphLaunch(exec, gs));
+        UB200_CUDA(cudaGraphLaunch(exec, st));
         g_launchCount += 19;
         rc = UB200_OK;
       }
     }
-    if (rc) return rc;
-    UB200_CUDA(cudaEventRecord(evOut, gs));
-    UB200_CUDA(cudaStreamWaitEvent(st, evOut, 0));
-    return UB200_OK;
+    return rc;
   }
 
   // the launches of one call; no host state changes, so that the sequence can be captured into a CUDA graph

@@ -773,6 +773,31 @@ int ub200_ljengine_traverse_f32(ub200_ljengine *e, void *d_force, int accumulate
                    0x7fffffff, (cudaStream_t)stream);
 }
 
+// the half-cell list alone (neighbour search without a traversal): what b200::ColumnList::update calls before it runs a
+// user Transverser through the header-template traversal over ub200_ljengine_view
+int ub200_ljengine_build_f32(ub200_ljengine *e, const void *d_pos, const int *d_groupIdx, int N, const float L[3],
+                             const int periodic[3], float cutOff, void *stream) {
+  if (!e || !d_pos || N <= 0 || !L || !periodic || !(cutOff > 0)) return UB200_ERR_INVALID_ARGUMENT;
+  int dims[3], per[3];
+  if (!ljEngineDims(L, periodic, cutOff, dims, per)) return UB200_ERR_UNSUPPORTED;
+  const int rc = buildFine(e, (const float4 *)d_pos, d_groupIdx, nullptr, N, nullptr, L, per, dims, makeWholeColGrid(dims, per),
+                           (cudaStream_t)stream);
+  if (!rc) e->lastPath = 0;
+  return rc;
+}
+int ub200_ljengine_view_get(ub200_ljengine *e, ub200_ljengine_view *v) {
+  if (!e || !v) return UB200_ERR_INVALID_ARGUMENT;
+  if (e->lastPath != 0 || !e->pos.p) return UB200_ERR_NOT_BUILT;
+  v->d_pos = e->pos.p;
+  v->d_index = e->idx.as<int>();
+  v->d_cellStart = e->binStart.as<uint32_t>();
+  v->cells[0] = e->cg.nx; v->cells[1] = e->cg.ny; v->cells[2] = e->cg.nz;
+  v->periodic[0] = e->cg.px; v->periodic[1] = e->cg.py; v->periodic[2] = e->cg.pz;
+  v->L[0] = e->grid.Lx; v->L[1] = e->grid.Ly; v->L[2] = e->grid.Lz;
+  v->numberParticles = e->N;
+  return UB200_OK;
+}
+
 int ub200_ljengine_last_path(ub200_ljengine *e) { return e ? e->lastPath : -1; }
 
 int ub200_ljengine_error_flag(ub200_ljengine *e, void *stream, int *flag) {

@@ -1,7 +1,7 @@
 // Handle of the LJ pair-force engine: PairForces<Potential::LJ, CellList>::sum (Interactor/PairForces.cu:43-78) in one call.
 #pragma once
 #include "common.cuh"
-#include "colgeom.h"
+#include "../../include/uammd_b200/colgeom.h"
 
 // Engine-private half-cell list (see colgeom.h): particles sorted by linear half-cell index (x fastest), stable inside a
 // cell, coordinates folded into the primary box and made consistent with the cell (a coordinate that rounds into cell n

@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(kPairThreads)
 dpdCellTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
                  const uint32_t *__restrict__ binStart, GridF g, int ncells, const float *__restrict__ vel, DPDPar par,
                  float4 *__restrict__ force, const int *__restrict__ globalIdx, int ownerLo, int ownerHi, int accumulate,
-                 const int *__restrict__ noiseId) {
+                 const int *__restrict__ noiseId, const int *__restrict__ ownerHiDev) {
+  if (ownerHiDev) ownerHi = *ownerHiDev; // multi-GPU bricks: the owned block [0, nOwned) is counted on the device
   // ownerLo/ownerHi: only home particles whose (global) index lies in [ownerLo, ownerHi) are computed and written
   // (multi-GPU particle decomposition, like ub200_lj_sum_owned_f32)
   // noiseId: optional id of every particle used ONLY in the Saru key of a pair (brick decomposition: the local
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(kPairThreads)
 dpdTileTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ groupIndex,
                  const uint32_t *__restrict__ binStart, GridF g, int tilesX, int tilesY, const float *__restrict__ vel,
                  DPDPar par, float4 *__restrict__ force, const int *__restrict__ globalIdx, int ownerLo, int ownerHi,
-                 int accumulate, const int *__restrict__ noiseId) {
+                 int accumulate, const int *__restrict__ noiseId, const int *__restrict__ ownerHiDev) {
+  if (ownerHiDev) ownerHi = *ownerHiDev;
   __shared__ float4 sPos[kTileCap];
   __shared__ float4 sVel[kTileCap]; // vx, vy, vz, noise id (bits)
   __shared__ int sOff[kTileHalo + 1];  // exclusive prefix of the staged particles per halo cell
@@ -488,9 +490,9 @@ dpdTileTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
 
 using namespace ub200;
 
-static int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut, uint32_t seed,
+int ub200::dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut, uint32_t seed,
                   uint32_t step, int idStride, void *d_force, const int *d_globalIdx, int ownerLo, int ownerHi, int accumulate,
-                  void *stream, const int *d_noiseId = nullptr) {
+                  void *stream, const int *d_noiseId, const int *ownerHiDev) {
   if (!cl || !d_vel || !d_force || !(rcut > 0)) return UB200_ERR_INVALID_ARGUMENT;
   if (!cl->built) return UB200_ERR_NOT_BUILT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -516,7 +518,7 @@ static int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, f
     const int tx = (g.nx + kTileB - 1) / kTileB, ty = (g.ny + kTileB - 1) / kTileB, tz = (g.nz + kTileB - 1) / kTileB;
     dpdTileTraversal<<<tx * ty * tz, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
                                                             cl->binStart.as<uint32_t>(), g, tx, ty, (const float *)d_vel, par,
-                                                            (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate, d_noiseId);
+                                                            (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate, d_noiseId, ownerHiDev);
     UB200_LAUNCHED();
     return UB200_OK;
   }
@@ -532,12 +534,12 @@ static int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, f
     dpdCellTraversal<true><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
                                                           cl->binStart.as<uint32_t>(), g, cl->ncells,
                                                           (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate,
-                                                          d_noiseId);
+                                                          d_noiseId, ownerHiDev);
   else
     dpdCellTraversal<false><<<grid, kPairThreads, 0, st>>>(cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
                                                            cl->binStart.as<uint32_t>(), g, cl->ncells,
                                                            (const float *)d_vel, par, (float4 *)d_force, d_globalIdx, ownerLo, ownerHi, accumulate,
-                                                          d_noiseId);
+                                                          d_noiseId, ownerHiDev);
   UB200_LAUNCHED();
   return UB200_OK;
 }

@@ -379,11 +379,14 @@ int ljSum(ub200_celllist *cl, const float *params, int ntypes, float4 *force, fl
 
 using namespace ub200;
 
-static LJTableCache g_ljTable; // parameter table of the stateless ub200_lj_sum_f32 entry point
+// parameter table of ub200_lj_nbody_f32, the one entry point without a handle (boxes of a few hundred particles). Not
+// thread safe; the list-based entry points keep their table in the list handle.
+static LJTableCache g_ljTable;
 
 extern "C" int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, float *d_energy,
                                 float *d_virial, const int *d_globalIdx, void *stream) {
-  return ljSum(cl, params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true, &g_ljTable,
+  if (!cl) return UB200_ERR_INVALID_ARGUMENT;
+  return ljSum(cl, params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true, &cl->ljTable,
                (cudaStream_t)stream, 0, 0x7fffffff);
 }
 
@@ -393,7 +396,7 @@ extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params
   if (!vl->N) return UB200_ERR_NOT_BUILT;
   if (!d_force && !d_energy && !d_virial) return UB200_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  LJTableCache *cache = &g_ljTable;
+  LJTableCache *cache = &vl->cl->ljTable;
   if (const int rc = uploadLJTable(cache, params, ntypes, st)) return rc;
   const int cd1[3] = {1, 1, 1};
   const GridF g = makeGridF(vl->L, vl->periodic, cd1);
@@ -417,7 +420,8 @@ extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params
 extern "C" int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, int ownerLo,
                                       int ownerHi, int accumulate, void *stream) {
   if (ownerLo < 0 || ownerHi < ownerLo) return UB200_ERR_INVALID_ARGUMENT;
-  return ljSum(cl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, accumulate != 0, &g_ljTable,
+  if (!cl) return UB200_ERR_INVALID_ARGUMENT;
+  return ljSum(cl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, accumulate != 0, &cl->ljTable,
                (cudaStream_t)stream, ownerLo, ownerHi);
 }
 

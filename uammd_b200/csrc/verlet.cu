@@ -74,7 +74,11 @@ verletFill(const float4 *__restrict__ sortPos, const uint32_t *__restrict__ binS
   int *cntBuf = reinterpret_cast<int *>(mine + kVerletCap * sizeof(float4) + kVerletHome * kVerletK * sizeof(unsigned short));
   const int warpsTotal = gridDim.x * kPairWarps;
   const bool pairMic = (g.mx != 0.0f && g.nx < 4) || (g.my != 0.0f && g.ny < 4) || (g.mz != 0.0f && g.nz < 4);
-  const float cutLo = cutOff2 * (1.0f - 1e-4f), cutHi = cutOff2 * (1.0f + 1e-4f);
+  // rounding band around the cut-off inside which the reference's exact arithmetic decides: the staged image of a
+  // coordinate carries an error of a few ulp(L / 2), i.e. a relative error ~ 2^-21 L / cutOff in r2; 1e-4 covers boxes up to
+  // ~200 cut-offs, larger ones widen the band
+  const float band = fmaxf(1e-4f, 4.8e-7f * fmaxf(g.Lx, fmaxf(g.Ly, g.Lz)) * rsqrtf(cutOff2));
+  const float cutLo = cutOff2 * (1.0f - band), cutHi = cutOff2 * (1.0f + band);
   for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
     const NeighbourCells nc = describeNeighbours(g, cx, cy, cz, binStart, lane);
