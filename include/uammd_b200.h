@@ -239,8 +239,14 @@ int ub200_brick_counts(ub200_brick *b, void *stream, int *nOwned, int *nLocal, i
  * Path 1d: Verlet (skin) list. Replaces VerletList::update (Interactor/NeighbourList/VerletList.cuh:111-124) and
  * the classes beneath it (VerletList/VerletListBase.cuh:73-199, BasicList/BasicListBase.cuh:76-215): rebuild when
  * a particle moved >= (multiplier - 1) cutOff / 2 since the last rebuild (host-synchronous flag read, like
- * VerletListBase.cuh:191-218), list stored [k * N + i] over SORTED indices, sortPos refreshed every call.
- * The arrays are bit-identical to the reference's VerletListData (BasicListBase.cuh:143-151).
+ * VerletListBase.cuh:191-218). Two lists live behind the handle:
+ *  - the ROW LIST of the built-in LJ traversal (ub200_lj_sum_verlet_f32, the fused MD loops): filled from the engine's
+ *    half-cell columns, one row per particle, image of each neighbour stored in the entry (lj_vlist.cu). Built at every
+ *    rebuild when the grid allows it (>= 5 half cells per periodic dimension, N < 2^27);
+ *  - the REFERENCE-LAYOUT list, [k * N + i] over SORTED indices, sortPos refreshed every call, bit-identical to the
+ *    reference's VerletListData (BasicListBase.cuh:143-151). Built at every rebuild when the row list does not apply,
+ *    otherwise from the first ub200_verletlist_view_get on (which builds it from the positions stored at the last
+ *    rebuild; the arrays given to the last update must still be alive) - callers that never read it never pay for it.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct ub200_verletlist ub200_verletlist;
 typedef struct {
@@ -260,6 +266,19 @@ int ub200_verletlist_set_cutoff_multiplier(ub200_verletlist *vl, float multiplie
 int ub200_verletlist_update_f32(ub200_verletlist *vl, const void *d_pos, const int *d_groupIdx, int N, const float L[3],
                                 const int periodic[3], float cutOff, int forceRebuild, int *rebuilt, void *stream);
 int ub200_verletlist_view_get(ub200_verletlist *vl, ub200_verletlist_view *view);
+/* VerletList::getNumberOfStepsSinceLastUpdate (VerletListBase.cuh:131) and the rebuild count, without touching the lists */
+int ub200_verletlist_stats(ub200_verletlist *vl, int *stepsSinceLastUpdate, int *rebuilds);
+/* The row list (tests, tools): neighbour k of the particle in half-cell slot i at d_list[i * stride + k] =
+ * slot | image << indexBits, image = (sx + 1) + 3 (sy + 1) + 9 (sz + 1) box lengths to add to the neighbour (13 = none);
+ * self excluded. UB200_ERR_NOT_BUILT when the last rebuild made the reference-layout list only. */
+typedef struct {
+  const int *d_list;
+  const int *d_count;            /* [N] */
+  const void *d_pos;             /* real4[N] current positions in half-cell order */
+  const int *d_index;            /* [N] half-cell slot -> group index */
+  int stride, numberParticles, indexBits;
+} ub200_verletlist_rows;
+int ub200_verletlist_rows_get(ub200_verletlist *vl, ub200_verletlist_rows *rows);
 /* LJ transverser over the Verlet list. Replaces VerletList::transverseList (VerletList.cuh:141-159 ->
  * NeighbourList/common.cuh:10-34 with VerletListBase_ns::NeighbourContainer, BasicList/NeighbourContainer.cuh:42-125)
  * for Radial<LJFunctor>; same argument meaning as ub200_lj_sum_f32 (outputs accumulate). */

@@ -1,2 +1,3 @@
 cd /root/repo
-timeout 1200 python -m pytest tests/test_dropin_gpu.py tests/test_brick_gpu.py tests/test_lj_gpu.py tests/test_verlet_gpu.py -q -m gpu 2>&1 | tail -12
+timeout 900 python -m pytest tests/test_vlist_gpu.py tests/test_verlet_gpu.py -q -m gpu -x 2>&1 | tail -25
+timeout 600 python scripts/vlist_time.py > gpurun_out/r02v_vlist_time.json 2> gpurun_out/r02v_vlist_time.err; tail -3 gpurun_out/r02v_vlist_time.err; cat gpurun_out/r02v_vlist_time.json

@@ -153,15 +153,25 @@ int scatterToBinsLaunch(const uint2 *codeSlot, const uint32_t *binStart, int N, 
 } // namespace ub200
 
 struct ub200_celllist;
+struct ub200_verletlist;
 namespace ub200 {
-// ub200_celllist_build_f32 with an optional device-side particle count (N = launch bound) and an optional key deciding the
-// order inside a cell (multi-GPU bricks: global particle ids)
 // DPD forces over a built cell list (pair_dpd.cu); ownerHiDev: optional device-side upper bound of the owned index range
 int dpdSum(ub200_celllist *cl, const void *d_vel, float A, float gamma, float sigma, float rcut, uint32_t seed, uint32_t step,
            int idStride, void *d_force, const int *d_globalIdx, int ownerLo, int ownerHi, int accumulate, void *stream,
            const int *d_noiseId = nullptr, const int *ownerHiDev = nullptr);
+// ub200_celllist_build_f32 with an optional device-side particle count (N = launch bound) and an optional key deciding the
+// order inside a cell (multi-GPU bricks: global particle ids)
 int celllistBuildEx(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx, int N, const int *nDev, const int *sortKey,
                     const float L[3], const int periodic[3], const int cellDim[3], void *stream);
+// lj_vlist.cu: row list over the half-cell columns
+bool vlistApplies(const float L[3], const int periodic[3], float rcut, int N);
+int vlistRebuild(ub200_verletlist *v, cudaStream_t st);
+int vlistRefreshPositions(ub200_verletlist *v, const float4 *pos, const int *groupIdx, cudaStream_t st);
+int vlistSum(ub200_verletlist *v, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
+             const int *globalIdx, bool accumulate, cudaStream_t st);
+// LJ forces over a Verlet list handle, whichever list it holds (pair_lj.cu)
+int ljVerletSum(ub200_verletlist *vl, const float *params, int ntypes, float4 *force, float *energy, float *virial,
+                const int *globalIdx, bool accumulate, cudaStream_t st);
 } // namespace ub200
 
 // Opaque handle behind ub200_celllist
@@ -185,6 +195,7 @@ struct ub200_celllist {
                                                          // two interactors never share or re-upload each other's table)
 };
 
+struct ub200_ljengine;
 // Opaque handle behind ub200_verletlist (VerletList / VerletListBase / BasicNeighbourListBase of the reference)
 struct ub200_verletlist {
   ub200_celllist *cl = nullptr;     // cell list over the stored positions, cell size >= cutOff * multiplier
@@ -201,4 +212,15 @@ struct ub200_verletlist {
   bool forceNext = true;
   int stepsSinceLastUpdate = 0;
   int rebuilds = 0;
+  // ---- row list of the built-in LJ traversal (lj_vlist.cu); the reference-layout arrays above are then built on demand
+  ub200_ljengine *eng = nullptr;    // half-cell list of the stored positions, cells >= cutOff * multiplier / 2
+  ub200::DevBuf fastPos;            // float4[N] current positions in half-cell order, image nearest the build-time one
+  ub200::DevBuf fastList, fastCount;// int[N * fastStride] rows, int[N]
+  int fastStride = 64;
+  bool fast = false;                // the row list is the one the last rebuild made
+  bool refValid = false;            // the reference-layout list matches the stored positions
+  bool wantRef = false;             // somebody read the reference-layout list: keep it current from now on
+  const void *lastPos = nullptr;    // arguments of the last update (lazy build of the reference layout in view_get)
+  const int *lastGroupIdx = nullptr;
+  cudaStream_t lastStream = nullptr;
 };

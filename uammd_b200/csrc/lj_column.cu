@@ -129,34 +129,6 @@ __device__ __forceinline__ void storeHome(const Acc &a, int ori, float4 *__restr
   if (VIRIAL) virial[ori] += a.v;
 }
 
-// Force-only, single-type pair with the parameters folded into two constants: |F|/r = inv^4 (c24 - c48 inv^3), inv = 1/r2,
-// c24 = 24 eps sigma^6, c48 = 48 eps sigma^12 (the same function as ljPair: epsDivSigma2 (24 - 48 u^3) u^4 with u = sigma2 inv;
-// two multiplications less per pair, roundings differ in the last bits only).
-struct LJFold {
-  float c24, c48;
-  uint32_t rcb;
-};
-__device__ __forceinline__ LJFold foldLJ(const LJPar &p) {
-  const float s4 = p.sigma2 * p.sigma2, s8 = s4 * s4;
-  LJFold f;
-  f.c24 = 24.0f * p.epsDivSigma2 * s8;
-  f.c48 = 48.0f * p.epsDivSigma2 * s8 * s4 * p.sigma2;
-  f.rcb = __float_as_uint(p.cutOff2) - 1u;
-  return f;
-}
-__device__ __forceinline__ void ljPairFolded(float dx, float dy, float dz, const LJFold &p, Acc &a) {
-  const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-  const bool in = (__float_as_uint(r2) - 1u) < p.rcb; // 0 < r2 < rc2 (see ljPair)
-  const float r2s = in ? r2 : __int_as_float(0x7f800000);
-  float inv;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r2s));
-  const float i2 = inv * inv;
-  const float fm = (i2 * i2) * __fmaf_rn(-p.c48, i2 * inv, p.c24);
-  a.fx = __fmaf_rn(fm, dx, a.fx);
-  a.fy = __fmaf_rn(fm, dy, a.fy);
-  a.fz = __fmaf_rn(fm, dz, a.fz);
-}
-
 // One pass over the staged slice: 32 / W home particles, W lanes each. src = lane of the warp that holds the particle's
 // record (c0, c1: candidate range, slot: its own position in the slice, gi: group index); W is a compile-time constant so
 // that the candidate loads are base + immediate and the reduction unrolls.

@@ -209,8 +209,8 @@ int ub200_md_lj_nve_verlet_run_f32(ub200_md *md, ub200_verletlist *vl, void *d_p
   auto forces = [&]() -> int {
     int e = ub200_verletlist_update_f32(vl, d_pos, nullptr, N, L, periodic, rc, 0, nullptr, stream);
     if (e) return e;
-    UB200_CUDA(cudaMemsetAsync(d_force, 0, sizeof(float4) * (size_t)N, st)); // VerletNVE::resetForces (VerletNVE.cu:152-158)
-    return ub200_lj_sum_verlet_f32(vl, params, ntypes, d_force, nullptr, nullptr, nullptr, stream);
+    // sole interactor: the forces are written, which replaces VerletNVE::resetForces (VerletNVE.cu:152-158) + sum
+    return ljVerletSum(vl, params, ntypes, (float4 *)d_force, nullptr, nullptr, nullptr, false, st);
   };
   int e;
   if (!forcesAreCurrent && (e = forces())) return e;

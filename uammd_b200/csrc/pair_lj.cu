@@ -390,14 +390,17 @@ extern "C" int ub200_lj_sum_f32(ub200_celllist *cl, const float *params, int nty
                (cudaStream_t)stream, 0, 0x7fffffff);
 }
 
-extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params, int ntypes, void *d_force, float *d_energy,
-                                       float *d_virial, const int *d_globalIdx, void *stream) {
+// LJ forces over a Verlet list handle: the row list when the last rebuild made one (lj_vlist.cu), else the
+// reference-layout list
+int ub200::ljVerletSum(ub200_verletlist *vl, const float *params, int ntypes, float4 *force, float *d_energy, float *d_virial,
+                       const int *d_globalIdx, bool accumulate, cudaStream_t st) {
   if (!vl || !params || ntypes < 1) return UB200_ERR_INVALID_ARGUMENT;
   if (!vl->N) return UB200_ERR_NOT_BUILT;
-  if (!d_force && !d_energy && !d_virial) return UB200_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (!force && !d_energy && !d_virial) return UB200_OK;
   LJTableCache *cache = &vl->cl->ljTable;
   if (const int rc = uploadLJTable(cache, params, ntypes, st)) return rc;
+  if (vl->fast) return vlistSum(vl, cache->dev.as<LJPar>(), ntypes, force, d_energy, d_virial, d_globalIdx, accumulate, st);
+  if (!accumulate && force) UB200_CUDA(cudaMemsetAsync(force, 0, sizeof(float4) * (size_t)vl->N, st));
   const int cd1[3] = {1, 1, 1};
   const GridF g = makeGridF(vl->L, vl->periodic, cd1);
   const int N = vl->N, nb = (N + 127) / 128;
@@ -406,8 +409,7 @@ extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params
   if (E == e && V == v && M == m) {                                                                                     \
     ljVerletTraversal<e, v, m><<<nb, 128, 0, st>>>(vl->sortPos.as<float4>(), vl->cl->groupIndex.as<int>(),               \
                                                    vl->neighbourList.as<int>(), vl->numberNeighbours.as<int>(), N, g,     \
-                                                   cache->dev.as<LJPar>(), ntypes, (float4 *)d_force, d_energy, d_virial, \
-                                                   d_globalIdx);                                                          \
+                                                   cache->dev.as<LJPar>(), ntypes, force, d_energy, d_virial, d_globalIdx); \
     UB200_LAUNCHED();                                                                                                   \
     return UB200_OK;                                                                                                    \
   }
@@ -415,6 +417,11 @@ extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params
   UB200_LJV(false, true, false) UB200_LJV(false, true, true) UB200_LJV(true, true, false) UB200_LJV(true, true, true)
 #undef UB200_LJV
   return UB200_ERR_UNSUPPORTED;
+}
+
+extern "C" int ub200_lj_sum_verlet_f32(ub200_verletlist *vl, const float *params, int ntypes, void *d_force, float *d_energy,
+                                       float *d_virial, const int *d_globalIdx, void *stream) {
+  return ljVerletSum(vl, params, ntypes, (float4 *)d_force, d_energy, d_virial, d_globalIdx, true, (cudaStream_t)stream);
 }
 
 extern "C" int ub200_lj_sum_owned_f32(ub200_celllist *cl, const float *params, int ntypes, void *d_force, int ownerLo,

@@ -10,6 +10,7 @@
 // home particle is tested by the 32 lanes in visiting order and the hits are compacted with ballot/popc, so the
 // list comes out ordered without any sort (the reference walks the 27 cells with one thread per particle).
 #include "pair_common.cuh"
+#include "lj_engine.cuh"
 
 namespace ub200 {
 
@@ -204,6 +205,39 @@ verletFill(const float4 *__restrict__ sortPos, const uint32_t *__restrict__ binS
 
 using namespace ub200;
 
+// rebuildList (VerletListBase.cuh:165-168) -> BasicNeighbourListBase::update (BasicListBase.cuh:131-141): the
+// reference-layout list of the stored positions
+static int buildReferenceList(ub200_verletlist *v, cudaStream_t st) {
+  const int N = v->N;
+  const float *L = v->L;
+  const int *periodic = v->periodic;
+  int rc;
+  {
+    const float rcut = v->cutOff * v->multiplier;
+    int cd[3];
+    if ((rc = ub200_neighbour_celldim_f32(L, rcut, cd))) return rc;
+    if ((rc = ub200_celllist_build_f32(v->cl, v->storedPos.p, nullptr, N, L, periodic, cd, st))) return rc;
+    const int needed = (v->cl->ncells + kPairWarps - 1) / kPairWarps;
+    const int grid = needed < kNumSMs * 4 ? needed : kNumSMs * 4;
+    while (true) { // fillBasicNeighbourList: retry with 32 more slots until nothing overflows (:176-181)
+      if ((rc = v->neighbourList.reserve(sizeof(int) * (size_t)N * (v->maxNeighbours + 1)))) return rc;
+      UB200_CUDA(cudaMemsetAsync(v->flags.as<uint32_t>() + 1, 0, sizeof(uint32_t), st));
+      UB200_CUDA(cudaFuncSetAttribute(verletFill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerletSmem));
+      verletFill<<<grid, kPairThreads, kVerletSmem, st>>>(v->cl->sortPos.as<float4>(), v->cl->binStart.as<uint32_t>(), v->cl->grid, v->cl->ncells,
+                                               rcut * rcut, N, v->maxNeighbours, v->neighbourList.as<int>(),
+                                               v->numberNeighbours.as<int>(), v->flags.as<uint32_t>() + 1);
+      UB200_LAUNCHED();
+      uint32_t over = 0;
+      UB200_CUDA(cudaMemcpyAsync(&over, v->flags.as<uint32_t>() + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      UB200_CUDA(cudaStreamSynchronize(st));
+      if (!over) break;
+      v->maxNeighbours += 32;
+    }
+  }
+  v->refValid = true;
+  return UB200_OK;
+}
+
 extern "C" {
 
 int ub200_verletlist_create(ub200_verletlist **out) {
@@ -212,14 +246,17 @@ int ub200_verletlist_create(ub200_verletlist **out) {
   if (!v) return UB200_ERR_ALLOC;
   int rc = ub200_celllist_create(&v->cl);
   if (rc) { delete v; return rc; }
-  if ((rc = v->flags.reserve(2 * sizeof(uint32_t)))) { ub200_celllist_destroy(v->cl); delete v; return rc; }
+  if ((rc = ub200_ljengine_create(&v->eng))) { ub200_celllist_destroy(v->cl); delete v; return rc; }
+  if ((rc = v->flags.reserve(2 * sizeof(uint32_t)))) { ub200_ljengine_destroy(v->eng); ub200_celllist_destroy(v->cl); delete v; return rc; }
   *out = v;
   return UB200_OK;
 }
 int ub200_verletlist_destroy(ub200_verletlist *v) {
   if (!v) return UB200_OK;
   ub200_celllist_destroy(v->cl);
+  ub200_ljengine_destroy(v->eng);
   v->storedPos.release(); v->sortPos.release(); v->numberNeighbours.release(); v->neighbourList.release(); v->flags.release();
+  v->fastPos.release(); v->fastList.release(); v->fastCount.release();
   delete v;
   return UB200_OK;
 }
@@ -270,30 +307,17 @@ int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const in
       return rc;
     verletStore<<<nb, 256, 0, st>>>(pos, d_groupIdx, N, v->storedPos.as<float4>());
     UB200_LAUNCHED();
-    // rebuildList (:165-168) -> BasicNeighbourListBase::update (BasicListBase.cuh:131-141)
-    const float rcut = v->cutOff * v->multiplier;
-    int cd[3];
-    if ((rc = ub200_neighbour_celldim_f32(L, rcut, cd))) return rc;
-    if ((rc = ub200_celllist_build_f32(v->cl, v->storedPos.p, nullptr, N, L, periodic, cd, st))) return rc;
-    const int needed = (v->cl->ncells + kPairWarps - 1) / kPairWarps;
-    const int grid = needed < kNumSMs * 4 ? needed : kNumSMs * 4;
-    while (true) { // fillBasicNeighbourList: retry with 32 more slots until nothing overflows (:176-181)
-      if ((rc = v->neighbourList.reserve(sizeof(int) * (size_t)N * (v->maxNeighbours + 1)))) return rc;
-      UB200_CUDA(cudaMemsetAsync(v->flags.as<uint32_t>() + 1, 0, sizeof(uint32_t), st));
-      UB200_CUDA(cudaFuncSetAttribute(verletFill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVerletSmem));
-      verletFill<<<grid, kPairThreads, kVerletSmem, st>>>(v->cl->sortPos.as<float4>(), v->cl->binStart.as<uint32_t>(), v->cl->grid, v->cl->ncells,
-                                               rcut * rcut, N, v->maxNeighbours, v->neighbourList.as<int>(),
-                                               v->numberNeighbours.as<int>(), v->flags.as<uint32_t>() + 1);
-      UB200_LAUNCHED();
-      uint32_t over = 0;
-      UB200_CUDA(cudaMemcpyAsync(&over, v->flags.as<uint32_t>() + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-      UB200_CUDA(cudaStreamSynchronize(st));
-      if (!over) break;
-      v->maxNeighbours += 32;
-    }
+    v->fast = vlistApplies(L, periodic, v->cutOff * v->multiplier, N);
+    v->refValid = false;
+    if (v->fast && (rc = vlistRebuild(v, st))) return rc;
+    if ((!v->fast || v->wantRef) && (rc = buildReferenceList(v, st))) return rc;
   }
-  verletSortedPositions<<<nb, 256, 0, st>>>(pos, d_groupIdx, v->cl->groupIndex.as<int>(), N, v->sortPos.as<float4>());
-  UB200_LAUNCHED();
+  v->lastPos = d_pos; v->lastGroupIdx = d_groupIdx; v->lastStream = st;
+  if (v->fast && (rc = vlistRefreshPositions(v, pos, d_groupIdx, st))) return rc;
+  if (v->refValid) {
+    verletSortedPositions<<<nb, 256, 0, st>>>(pos, d_groupIdx, v->cl->groupIndex.as<int>(), N, v->sortPos.as<float4>());
+    UB200_LAUNCHED();
+  }
   v->stepsSinceLastUpdate++;
   if (rebuilt) *rebuilt = rebuild ? 1 : 0;
   return UB200_OK;
@@ -302,6 +326,17 @@ int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const in
 int ub200_verletlist_view_get(ub200_verletlist *v, ub200_verletlist_view *view) {
   if (!v || !view) return UB200_ERR_INVALID_ARGUMENT;
   if (!v->N) return UB200_ERR_NOT_BUILT;
+  if (!v->refValid) {
+    // first reader of the reference layout: build it from the positions stored at the last rebuild and keep it current
+    // from now on (the positions given to the last update are read for sortPos)
+    cudaStream_t st = v->lastStream;
+    if (const int rc = buildReferenceList(v, st)) return rc;
+    verletSortedPositions<<<(v->N + 255) / 256, 256, 0, st>>>((const float4 *)v->lastPos, v->lastGroupIdx,
+                                                             v->cl->groupIndex.as<int>(), v->N, v->sortPos.as<float4>());
+    UB200_LAUNCHED();
+    UB200_CUDA(cudaStreamSynchronize(st));
+    v->wantRef = true;
+  }
   view->d_neighbourList = v->neighbourList.as<int>();
   view->d_numberNeighbours = v->numberNeighbours.as<int>();
   view->d_sortPos = v->sortPos.p;
@@ -311,6 +346,13 @@ int ub200_verletlist_view_get(ub200_verletlist *v, ub200_verletlist_view *view) 
   view->maxNeighboursPerParticle = v->maxNeighbours;
   view->stepsSinceLastUpdate = v->stepsSinceLastUpdate - 1; // VerletListBase::getNumberOfStepsSinceLastUpdate (:131)
   view->rebuilds = v->rebuilds;
+  return UB200_OK;
+}
+
+int ub200_verletlist_stats(ub200_verletlist *v, int *stepsSinceLastUpdate, int *rebuilds) {
+  if (!v) return UB200_ERR_INVALID_ARGUMENT;
+  if (stepsSinceLastUpdate) *stepsSinceLastUpdate = v->stepsSinceLastUpdate - 1;
+  if (rebuilds) *rebuilds = v->rebuilds;
   return UB200_OK;
 }
 }

@@ -179,6 +179,11 @@ class VerletListView(C.Structure):
                 ("maxNeighboursPerParticle", C.c_int), ("stepsSinceLastUpdate", C.c_int), ("rebuilds", C.c_int)]
 
 
+class VerletListRows(C.Structure):
+    _fields_ = [("d_list", C.c_void_p), ("d_count", C.c_void_p), ("d_pos", C.c_void_p), ("d_index", C.c_void_p),
+                ("stride", C.c_int), ("numberParticles", C.c_int), ("indexBits", C.c_int)]
+
+
 def _declare_verlet():
     lib = _lib.lib()
     if getattr(lib, "_verlet_declared", False):
@@ -190,6 +195,8 @@ def _declare_verlet():
     lib.ub200_verletlist_update_f32.argtypes = [vp, vp, vp, i, C.c_float * 3, C.c_int * 3, f, i, C.POINTER(i), vp]
     lib.ub200_verletlist_view_get.argtypes = [vp, C.POINTER(VerletListView)]
     lib.ub200_lj_sum_verlet_f32.argtypes = [vp, C.POINTER(C.c_float), i, vp, vp, vp, vp, vp]
+    lib.ub200_verletlist_stats.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    lib.ub200_verletlist_rows_get.argtypes = [vp, C.POINTER(VerletListRows)]
     lib._verlet_declared = True
     return lib
 
@@ -234,7 +241,25 @@ class VerletList:
         return v
 
     def getNumberOfStepsSinceLastUpdate(self):
-        return self.view().stepsSinceLastUpdate
+        steps = C.c_int(0)
+        check(self.lib.ub200_verletlist_stats(self._h, C.byref(steps), None))
+        return steps.value
+
+    def rebuilds(self):
+        n = C.c_int(0)
+        check(self.lib.ub200_verletlist_stats(self._h, None, C.byref(n)))
+        return n.value
+
+    def getRowList(self):
+        """The row list of the built-in LJ traversal (ub200_verletlist_rows_get): list [N, stride] over half-cell slots
+        (entry = slot | image << indexBits), count [N], pos [N, 4] in half-cell order, index [N] slot -> group index."""
+        r = VerletListRows()
+        check(self.lib.ub200_verletlist_rows_get(self._h, C.byref(r)))
+        N, dev = r.numberParticles, self.device
+        return {"list": _device_copy(r.d_list, (N, r.stride), torch.int32, dev),
+                "count": _device_copy(r.d_count, (N,), torch.int32, dev),
+                "pos": _device_copy(r.d_pos, (N, 4), torch.float32, dev),
+                "index": _device_copy(r.d_index, (N,), torch.int32, dev), "stride": r.stride, "indexBits": r.indexBits}
 
     def getVerletList(self):
         v = self.view()
