@@ -40,11 +40,11 @@ def verlet(dev, N, Lb, pos, vel, rc, dt, steps=100, warmup=20, equil=300):
     nl = VerletList()
     md = LJMD(Box(Lb), pot, dt)
     md.runVerlet(nl, p, v, f, equil)
-    r0 = nl.view().rebuilds
+    r0 = nl.rebuilds()
     l0 = lib().ub200_launch_count()
     ms = _timed(dev, lambda: md.runVerlet(nl, p, v, f, 1, forcesAreCurrent=True), steps, warmup)
     return {"metric": "MD steps/s @1e6 LJ particles (VerletList)", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms,
-            "rebuilds_per_step": (nl.view().rebuilds - r0) / float(steps + warmup), "gpu_launches": int(lib().ub200_launch_count() - l0),
+            "rebuilds_per_step": (nl.rebuilds() - r0) / float(steps + warmup), "gpu_launches": int(lib().ub200_launch_count() - l0),
             "what": "VerletNVE + PairForces<LJ, VerletList> (skin 1.08), drift check read back every step like the reference"}
 
 
@@ -122,11 +122,11 @@ def langevin(dev, steps=100, warmup=20, equil=300):
     nvt.addInteractor(PairForces(pot, Box(L), nl=nl))
     for _ in range(equil):
         nvt.forwardTime()
-    r0, l0 = nl.view().rebuilds, lib().ub200_launch_count()
+    r0, l0 = nl.rebuilds(), lib().ub200_launch_count()
     ms = _timed(dev, nvt.forwardTime, steps, warmup)
     ke = float((v * v).sum().item()) / (3.0 * N)
     return {"metric": "Langevin MD steps/s @2^20 LJ particles (benchmark.cu)", "value": 1000.0 / ms, "unit": "steps/s",
-            "ms_per_step": ms, "rebuilds_per_step": (nl.view().rebuilds - r0) / float(steps + warmup),
+            "ms_per_step": ms, "rebuilds_per_step": (nl.rebuilds() - r0) / float(steps + warmup),
             "gpu_launches": int(lib().ub200_launch_count() - l0), "kT_from_velocities": ke, "published_gtx980_steps_per_s": 90,
             "what": "VerletNVT::GronbechJensen + PairForces<LJ, VerletList> (skin 1.2), N = 1048576, box 128^3, dt 0.01, T 1"}
 

@@ -17,7 +17,8 @@
  *   uammd::b200::PairForcesLJ     Interactor (Interactor/Interactor.cuh:56-119) = PairForces<Potential::LJ, CellList>
  *                                 with the specialised LJ traversal (Interactor/PairForces.cu:43-78).
  *   uammd::b200::VerletList       NeighbourList concept with a skin (Interactor/NeighbourList/VerletList.cuh:83-201): the list
- *                                 is built by our CUDA path in the reference's VerletListData layout, bit for bit, so
+ *                                 is built by our CUDA path in the reference's VerletListData layout, bit for bit (from the
+ *                                 first getVerletList()/transverseList() on; b200::PairForcesLJ walks the engine's row list), so
  *                                 PairForces<AnyPotential, b200::VerletList> runs user Transversers through the reference's
  *                                 own kernel; b200::PairForcesLJ takes it as its neighbour list for the fast LJ path.
  *   uammd::b200::PSE              BDHI Method concept for BDHI::EulerMaruyama<Method> = BDHI::PSE (BDHI_PSE.cuh:82-176).
@@ -456,9 +457,9 @@ public:
   VerletListBase_ns::NeighbourContainer getNeighbourContainer() { return VerletListBase_ns::NeighbourContainer(getVerletList()); }
   void setCutOffMultiplier(real m) { check(ub200_verletlist_set_cutoff_multiplier(handle, m), "set_cutoff_multiplier"); }
   int getNumberOfStepsSinceLastUpdate() {
-    ub200_verletlist_view v;
-    check(ub200_verletlist_view_get(handle, &v), "verletlist_view_get");
-    return v.stepsSinceLastUpdate;
+    int steps = 0;
+    check(ub200_verletlist_stats(handle, &steps, nullptr), "verletlist_stats");
+    return steps;
   }
   ub200_verletlist *getHandle() { return handle; }
 };

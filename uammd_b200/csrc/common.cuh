@@ -220,6 +220,7 @@ struct ub200_verletlist {
   bool fast = false;                // the row list is the one the last rebuild made
   bool refValid = false;            // the reference-layout list matches the stored positions
   bool wantRef = false;             // somebody read the reference-layout list: keep it current from now on
+  bool refOnly = false;             // owner reads the reference-layout arrays directly (PSE near field): no row list
   const void *lastPos = nullptr;    // arguments of the last update (lazy build of the reference layout in view_get)
   const int *lastGroupIdx = nullptr;
   cudaStream_t lastStream = nullptr;

@@ -478,6 +478,7 @@ template <class T> struct PseState {
     }
     if ((rc = ub200_celllist_create(&cl))) return rc;
     if ((rc = ub200_verletlist_create(&vl))) return rc;
+    vl->refOnly = true; // rpyNearList walks the reference-layout arrays
     if ((rc = ub200_verletlist_set_cutoff_multiplier(vl, 1.0f))) return rc;
     // ---- far field: FarField::initializeGrid / initializeKernel (FarField.cuh:605-654) ----
     const T kcut = T(2) * psi * (T)sqrt(-log(tolerance));

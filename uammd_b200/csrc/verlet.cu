@@ -307,7 +307,7 @@ int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const in
       return rc;
     verletStore<<<nb, 256, 0, st>>>(pos, d_groupIdx, N, v->storedPos.as<float4>());
     UB200_LAUNCHED();
-    v->fast = vlistApplies(L, periodic, v->cutOff * v->multiplier, N);
+    v->fast = !v->refOnly && vlistApplies(L, periodic, v->cutOff * v->multiplier, N);
     v->refValid = false;
     if (v->fast && (rc = vlistRebuild(v, st))) return rc;
     if ((!v->fast || v->wantRef) && (rc = buildReferenceList(v, st))) return rc;
