@@ -370,11 +370,15 @@ struct ub200_ljengine *ub200_md_engine(ub200_md *md); /* the pair-force engine t
 #define UB200_KERNEL_PESKIN3 0  /* IBM_kernels::Peskin::threePoint  misc/IBM_kernels.cuh:118-137 */
 #define UB200_KERNEL_PESKIN4 1  /* IBM_kernels::Peskin::fourPoint   misc/IBM_kernels.cuh:140-157 */
 #define UB200_KERNEL_GAUSSIAN 2 /* FCM_ns::Kernels::Gaussian        Integrator/BDHI/FCM/FCM_kernels.cuh:22-58 */
+#define UB200_KERNEL_BARNETT_MAGLAND 3 /* IBM_kernels::BarnettMagland          misc/IBM_kernels.cuh:83-113 */
+#define UB200_KERNEL_SIXPOINT 4        /* IBM_kernels::GaussianFlexible::sixPoint misc/IBM_kernels.cuh:163-237 */
 typedef struct {
   int kind;
   int support;  /* points per dimension (Kernel::support / getMaxSupport) */
-  double h;     /* Peskin: grid spacing */
-  double prefactor, tau, rmax; /* Gaussian: prefactor*exp(tau r^2) for r < rmax */
+  double h;     /* Peskin, six point: grid spacing */
+  double prefactor, tau, rmax; /* Gaussian: prefactor*exp(tau r^2) for r < rmax.
+                                  Barnett-Magland: prefactor = 1/norm (= phi(0)), tau = beta, rmax = alpha (half support):
+                                  phi(r) = exp(beta (sqrt(1 - (r/alpha)^2) - 1)) / norm for |r| <= alpha */
 } ub200_ibm_kernel;
 
 /* 3-D real FFT, hand written (no cuFFT). Replaces the cuFFT plans + cufftExecR2C/D2Z/C2R/Z2D calls

@@ -696,6 +696,15 @@ template <class G> inline ub200_ibm_kernel describeGaussian(const G &k, real h) 
   d.tau = std::log(p1 / p0) / (r1 * r1);
   return d;
 }
+/* IBM_kernels::BarnettMagland (misc/IBM_kernels.cuh:91-113) keeps its norm private: 1/norm = phi(0). It declares no
+   support (the reference leaves that to the kernel that wraps it), so the caller states it. */
+inline ub200_ibm_kernel describeBarnettMagland(const IBM_kernels::BarnettMagland &k, int support) {
+  return {UB200_KERNEL_BARNETT_MAGLAND, support, 2.0 * (double)k.alpha / support, (double)k.phi(real(0)), (double)k.beta, (double)k.alpha};
+}
+/* IBM_kernels::GaussianFlexible::sixPoint (misc/IBM_kernels.cuh:163-237): closed form, support 6, grid spacing h */
+inline ub200_ibm_kernel describeKernel(const IBM_kernels::GaussianFlexible::sixPoint &, real h) {
+  return {UB200_KERNEL_SIXPOINT, 6, (double)h, 0, 0, 0};
+}
 inline ub200_ibm_kernel describeKernel(const BDHI::FCM_ns::Kernels::Gaussian &k, real h) { return describeGaussian(k, h); }
 inline ub200_ibm_kernel describeKernel(const BDHI::FCM_ns::Kernels::GaussianTorque &k, real h) { return describeGaussian(k, h); }
 

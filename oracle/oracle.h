@@ -95,6 +95,8 @@ void orc_nvt_initial_velocities_f32(float *vel3, int N, float vamp, int is2D, ui
 #define ORC_KERNEL_PESKIN3 0
 #define ORC_KERNEL_PESKIN4 1
 #define ORC_KERNEL_GAUSSIAN 2
+#define ORC_KERNEL_BARNETT_MAGLAND 3 /* prefactor = 1/norm, tau = beta, rmax = alpha */
+#define ORC_KERNEL_SIXPOINT 4
 typedef struct {
   int kind;
   int support;
@@ -103,6 +105,8 @@ typedef struct {
 } orc_ibm_kernel;
 
 double orc_ibm_phi(const orc_ibm_kernel *k, double r);
+/* BarnettMagland::computeNorm misc/IBM_kernels.cuh:93-97 (Simpson over [0, alpha], 20000 intervals, Kahan sums) */
+double orc_ibm_bm_norm(double alpha, double beta);
 /* IBM spread: misc/IBM.cu:83-147. grid is real3 AoS with row pitch nxPad (nxPad = 2(nx/2+1) for FCM) */
 void orc_ibm_spread_d(const orc_grid_d *g, const orc_ibm_kernel *k, const double *pos4, const double *val3,
                       int N, int nxPad, double *grid3);

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
-KERNEL_PESKIN3, KERNEL_PESKIN4, KERNEL_GAUSSIAN = 0, 1, 2
+KERNEL_PESKIN3, KERNEL_PESKIN4, KERNEL_GAUSSIAN, KERNEL_BARNETT_MAGLAND, KERNEL_SIXPOINT = 0, 1, 2, 3, 4
 
 
 class GridF(C.Structure):
@@ -257,6 +257,18 @@ def peskin3(h):
 
 def peskin4(h):
     return IBMKernel(KERNEL_PESKIN4, 4, h, 0.0, 0.0, 0.0)
+
+
+def barnett_magland(alpha, beta, support):
+    """IBM_kernels::BarnettMagland(alpha, beta) (misc/IBM_kernels.cuh:99-113) with the support its wrapper declares."""
+    _lib.orc_ibm_bm_norm.restype = C.c_double
+    _lib.orc_ibm_bm_norm.argtypes = [C.c_double, C.c_double]
+    norm = _lib.orc_ibm_bm_norm(alpha, beta)
+    return IBMKernel(KERNEL_BARNETT_MAGLAND, support, 2.0 * alpha / support, 1.0 / norm, beta, alpha)
+
+
+def six_point(h):
+    return IBMKernel(KERNEL_SIXPOINT, 6, h, 0.0, 0.0, 0.0)
 
 
 def gaussian_fcm(h, tolerance):

@@ -27,12 +27,60 @@ static double peskin4(double rr, double invh) {
   if (r < 2.0) return invh * 0.125 * (5.0 - 2.0 * r - sqrt(-7.0 + 12.0 * r - 4.0 * r * r));
   return 0.0;
 }
+/* IBM_kernels::BM misc/IBM_kernels.cuh:83-90 */
+static double bm(double zz, double alpha, double beta) {
+  const double z = zz / alpha;
+  const double dz2 = 1.0 - z * z;
+  return dz2 < 0.0 ? 0.0 : exp(beta * (sqrt(dz2) - 1.0));
+}
+/* detail::kahanSum / detail::integrate misc/IBM_kernels.cuh:44-78: composite Simpson, the three partial sums compensated */
+static double kahan_add(double *sum, double *c, double x) {
+  const double y = x - *c, t = *sum + y;
+  *c = (t - *sum) - y;
+  *sum = t;
+  return t;
+}
+double orc_ibm_bm_norm(double alpha, double beta) {
+  const int n = 20000; /* even */
+  const double dx = alpha / n;
+  double s = 0.0, c = 0.0;
+  kahan_add(&s, &c, bm(0.0, alpha, beta));
+  for (int i = 1; i < n; i++) kahan_add(&s, &c, (i % 2 ? 4.0 : 2.0) * bm(i * dx, alpha, beta));
+  kahan_add(&s, &c, bm(alpha, alpha, beta));
+  return 2.0 * (dx / 3.0 * s);
+}
+/* GaussianFlexible::sixPoint::phi_impl misc/IBM_kernels.cuh:168-216, r = |distance| / h */
+static double six_point(double r) {
+  if (r >= 3.0) return 0.0;
+  const double K = 0.714075092976608;
+  const double R = r - ceil(r) + 1.0, R2 = R * R, R3 = R2 * R;
+  const double alpha = 28.0;
+  const double beta = 9.0 / 4.0 - 1.5 * (K + R2) + (22.0 / 3 - 7.0 * K) * R - 7.0 / 3.0 * R3;
+  const double gamma = 0.25 * (0.5 * (161.0 / 36 - 59.0 / 6 * K + 5 * K * K) * R2 + 1.0 / 3 * (-109.0 / 24 + 5 * K) * R2 * R2 +
+                               5.0 / 18 * R3 * R3);
+  const double discr = beta * beta - 4.0 * alpha * gamma;
+  const int sgn = (1.5 - K) > 0 ? 1 : -1;
+  const double pre = 1.0 / (2 * alpha) * (-beta + sgn * sqrt(discr));
+  if (r <= 0) {
+    const double rp1 = r + 1.0;
+    return 2.0 * pre + 0.25 + 1.0 / 6 * (4 - 3 * K) * rp1 - 1.0 / 6 * rp1 * rp1 * rp1;
+  } else if (r <= 1) {
+    return 2.0 * pre + 5.0 / 8 - 0.25 * (K + r * r);
+  } else if (r <= 2) {
+    const double rm1 = r - 1.0;
+    return -3.0 * pre + 0.25 - 1.0 / 6.0 * (4 - 3 * K) * rm1 + 1.0 / 6 * rm1 * rm1 * rm1;
+  }
+  const double rm2 = r - 2.0;
+  return pre - 1.0 / 16 + 1.0 / 8 * (K + rm2 * rm2) - 1.0 / 12 * (3 * K - 1) * rm2 - 1.0 / 12 * rm2 * rm2 * rm2;
+}
 /* FCM_ns::Kernels::Gaussian::phi Integrator/BDHI/FCM/FCM_kernels.cuh:54-56 over IBM_kernels::Gaussian
    misc/IBM_kernels.cuh:28-40 */
 double orc_ibm_phi(const orc_ibm_kernel *k, double r) {
   switch (k->kind) {
   case ORC_KERNEL_PESKIN3: return peskin3(r, 1.0 / k->h);
   case ORC_KERNEL_PESKIN4: return peskin4(r, 1.0 / k->h);
+  case ORC_KERNEL_BARNETT_MAGLAND: return bm(r, k->rmax, k->tau) * k->prefactor;
+  case ORC_KERNEL_SIXPOINT: return six_point(fabs(r) / k->h) / k->h;
   default: return r >= k->rmax ? 0.0 : k->prefactor * exp(k->tau * r * r);
   }
 }

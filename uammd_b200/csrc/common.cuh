@@ -167,6 +167,7 @@ int celllistBuildEx(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx
 bool vlistApplies(const float L[3], const int periodic[3], float rcut, int N);
 int vlistRebuild(ub200_verletlist *v, cudaStream_t st);
 int vlistRefreshPositions(ub200_verletlist *v, const float4 *pos, const int *groupIdx, cudaStream_t st);
+int vlistRefreshAndCheck(ub200_verletlist *v, const float4 *pos, const int *groupIdx, float maxDist, bool *over, cudaStream_t st);
 int vlistSum(ub200_verletlist *v, const LJPar *table, int ntypes, float4 *force, float *energy, float *virial,
              const int *globalIdx, bool accumulate, cudaStream_t st);
 // LJ forces over a Verlet list handle, whichever list it holds (pair_lj.cu)
@@ -220,6 +221,7 @@ struct ub200_verletlist {
   bool fast = false;                // the row list is the one the last rebuild made
   bool refValid = false;            // the reference-layout list matches the stored positions
   bool wantRef = false;             // somebody read the reference-layout list: keep it current from now on
+  uint32_t driftEpoch = 0;          // value the fused refresh + drift check writes into flags[0] when a particle is over
   bool refOnly = false;             // owner reads the reference-layout arrays directly (PSE near field): no row list
   const void *lastPos = nullptr;    // arguments of the last update (lazy build of the reference layout in view_get)
   const int *lastGroupIdx = nullptr;

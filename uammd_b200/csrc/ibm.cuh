@@ -17,16 +17,43 @@
 
 namespace ub200 {
 
-enum { kKernelPeskin3 = 0, kKernelPeskin4 = 1, kKernelGaussian = 2 };
+enum { kKernelPeskin3 = 0, kKernelPeskin4 = 1, kKernelGaussian = 2, kKernelBarnettMagland = 3, kKernelSixPoint = 4 };
 constexpr int kMaxSupport = 32;
 
 template <class T> struct IbmKernel {
   int kind, support;
-  T invh;                // Peskin
-  T prefactor, tau, rmax; // Gaussian
+  T invh;                // Peskin, six point
+  T prefactor, tau, rmax; // Gaussian: prefactor exp(tau r^2), r < rmax. Barnett-Magland: 1/norm, beta, alpha
 };
 
-// window functions: misc/IBM_kernels.cuh:118-137 (3 point), :140-157 (4 point), :28-40 + FCM_kernels.cuh:54-56
+// GaussianFlexible::sixPoint::phi_impl (misc/IBM_kernels.cuh:168-216): the C3 six-point kernel of Bao, Kaye and Peskin
+// (J. Comput. Phys. 316 (2016) 139) for r = |distance| / h in [0, 3); every branch shares one root of a quadratic in the
+// fractional part R of r.
+template <class T> __host__ __device__ __forceinline__ T ibmSixPoint(T r) {
+  if (r >= T(3)) return T(0);
+  const T K = T(0.714075092976608); // 59/60 - sqrt(29)/20
+  const T R = r - ceil(r) + T(1.0), R2 = R * R, R3 = R2 * R;
+  const T alpha = T(28.);
+  const T beta = T(9.0 / 4.0) - T(1.5) * (K + R2) + (T(22. / 3) - T(7.0) * K) * R - T(7. / 3.) * R3;
+  const T gamma = T(0.25) * (T(0.5) * (T(161.) / T(36) - T(59.) / T(6) * K + T(5) * K * K) * R2 +
+                             T(1.) / T(3) * (T(-109.) / T(24) + T(5) * K) * R2 * R2 + T(5.) / T(18) * R3 * R3);
+  const T discr = beta * beta - T(4.0) * alpha * gamma;
+  const T pre = T(1.) / (T(2) * alpha) * (-beta + sqrt(discr)); // sign(3/2 - K) = +1
+  if (r <= T(0)) {
+    const T rp1 = r + T(1.0);
+    return T(2.) * pre + T(0.25) + T(1. / 6) * (T(4) - T(3) * K) * rp1 - T(1. / 6) * rp1 * rp1 * rp1;
+  }
+  if (r <= T(1)) return T(2.0) * pre + T(5. / 8) - T(0.25) * (K + r * r);
+  if (r <= T(2)) {
+    const T rm1 = r + T(-1.0);
+    return T(-3.0) * pre + T(0.25) - T(1. / 6.) * (T(4) - T(3) * K) * rm1 + T(1. / 6) * rm1 * rm1 * rm1;
+  }
+  const T rm2 = r + T(-2.0);
+  return pre - T(1. / 16) + T(1. / 8) * (K + rm2 * rm2) - T(1. / 12) * (T(3) * K - T(1)) * rm2 - T(1. / 12) * rm2 * rm2 * rm2;
+}
+
+// window functions: misc/IBM_kernels.cuh:118-137 (3 point), :140-157 (4 point), :28-40 + FCM_kernels.cuh:54-56 (Gaussian),
+// :83-113 (Barnett-Magland "exponential of a semicircle"), :163-237 (six point)
 template <class T> __device__ __forceinline__ T ibmPhi(const IbmKernel<T> &k, T rr) {
   if (k.kind == kKernelPeskin3) {
     const T r = fabs(rr) * k.invh;
@@ -42,6 +69,12 @@ template <class T> __device__ __forceinline__ T ibmPhi(const IbmKernel<T> &k, T 
     if (r < T(2.0)) return k.invh * T(0.125) * (T(5.0) - T(2.0) * r - sqrt(T(-7.0) + T(12.0) * r - T(4.0) * r * r));
     return T(0);
   }
+  if (k.kind == kKernelBarnettMagland) { // BM(zz, alpha, beta) / norm, IBM_kernels.cuh:83-90,110-112
+    const T z = rr / k.rmax;
+    const T dz2 = T(1.0) - z * z;
+    return dz2 < T(0.0) ? T(0) : exp(k.tau * (sqrt(dz2) - T(1.0))) * k.prefactor;
+  }
+  if (k.kind == kKernelSixPoint) return ibmSixPoint(fabs(rr) * k.invh) * k.invh;
   return rr >= k.rmax ? T(0) : k.prefactor * exp(k.tau * rr * rr);
 }
 

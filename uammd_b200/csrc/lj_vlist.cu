@@ -64,6 +64,22 @@ vlistPositions(const float4 *__restrict__ pos, const int *__restrict__ groupIdx,
                            c.z + foldCoord(cur.z - c.z, g.Lz, g.mz), cur.w);
 }
 
+// The same refresh fused with VerletListBase_ns::checkMaximumDrift (VerletListBase.cuh:57-69): the displacement since the
+// rebuild is the folded difference to the build-time coordinate, already at hand. A particle at or over the threshold writes
+// `epoch` into the flag word (no memset between calls: the host compares with the epoch it passed).
+__global__ void __launch_bounds__(256)
+vlistPositionsCheck(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, const int *__restrict__ fineIdx,
+                    const float4 *__restrict__ canon, int N, GridF g, float maxDist2, uint32_t epoch, float4 *__restrict__ fastPos,
+                    uint32_t *__restrict__ flag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const int i = fineIdx[k];
+  const float4 cur = ldg4(pos + (groupIdx ? groupIdx[i] : i)), c = canon[k];
+  const float dx = foldCoord(cur.x - c.x, g.Lx, g.mx), dy = foldCoord(cur.y - c.y, g.Ly, g.my), dz = foldCoord(cur.z - c.z, g.Lz, g.mz);
+  fastPos[k] = make_float4(c.x + dx, c.y + dy, c.z + dz, cur.w);
+  if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) >= maxDist2) *flag = epoch;
+}
+
 // One warp per column of kVlTZ half cells; see the header. list rows hold at most `stride` entries: a particle with more
 // neighbours reports its count through `overflow` and the host retries with longer rows (BasicListBase.cuh:176-181).
 __global__ void __launch_bounds__(kVlThreads, 5)
@@ -488,6 +504,22 @@ int vlistRefreshPositions(ub200_verletlist *v, const float4 *pos, const int *gro
   vlistPositions<<<(v->N + 255) / 256, 256, 0, st>>>(pos, groupIdx, e->idx.as<int>(), e->pos.as<float4>(), v->N, g,
                                                      v->fastPos.as<float4>());
   UB200_LAUNCHED();
+  return UB200_OK;
+}
+
+// refresh + drift check in one pass; *over = some particle moved maxDist or more since the rebuild (synchronises the stream)
+int vlistRefreshAndCheck(ub200_verletlist *v, const float4 *pos, const int *groupIdx, float maxDist, bool *over, cudaStream_t st) {
+  const int cd1[3] = {1, 1, 1};
+  const GridF g = makeGridF(v->L, v->periodic, cd1);
+  ub200_ljengine *e = v->eng;
+  const uint32_t epoch = ++v->driftEpoch;
+  vlistPositionsCheck<<<(v->N + 255) / 256, 256, 0, st>>>(pos, groupIdx, e->idx.as<int>(), e->pos.as<float4>(), v->N, g,
+                                                          maxDist * maxDist, epoch, v->fastPos.as<float4>(), v->flags.as<uint32_t>());
+  UB200_LAUNCHED();
+  uint32_t seen = 0;
+  UB200_CUDA(cudaMemcpyAsync(&seen, v->flags.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  UB200_CUDA(cudaStreamSynchronize(st));
+  *over = seen == epoch;
   return UB200_OK;
 }
 

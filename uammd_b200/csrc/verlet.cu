@@ -275,7 +275,7 @@ int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const in
   const int nb = (N + 255) / 256;
   int rc;
   // ---- VerletListBase::needsRebuild (:172-190) ----
-  bool rebuild = v->forceNext || forceRebuild != 0;
+  bool rebuild = v->forceNext || forceRebuild != 0, refreshed = false;
   v->forceNext = false;
   if (!rebuild) {
     rebuild = N != v->N || cutOff != v->cutOff;
@@ -285,7 +285,13 @@ int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const in
     // isParticleDriftOverThreshold (:192-218): host-synchronous flag read, like the reference
     const float threshold = (v->multiplier * v->cutOff - v->cutOff) / 2.0f;
     if (threshold <= 1e-6f) rebuild = true;
-    else {
+    else if (v->fast) {
+      // the row list refreshes its positions every call anyway: the same pass measures the drift
+      bool over = false;
+      if ((rc = vlistRefreshAndCheck(v, pos, d_groupIdx, threshold, &over, st))) return rc;
+      rebuild = over;
+      refreshed = !over;
+    } else {
       const int cd1[3] = {1, 1, 1};
       const GridF g = makeGridF(L, periodic, cd1);
       UB200_CUDA(cudaMemsetAsync(v->flags.p, 0, sizeof(uint32_t), st));
@@ -313,7 +319,7 @@ int ub200_verletlist_update_f32(ub200_verletlist *v, const void *d_pos, const in
     if ((!v->fast || v->wantRef) && (rc = buildReferenceList(v, st))) return rc;
   }
   v->lastPos = d_pos; v->lastGroupIdx = d_groupIdx; v->lastStream = st;
-  if (v->fast && (rc = vlistRefreshPositions(v, pos, d_groupIdx, st))) return rc;
+  if (v->fast && !refreshed && (rc = vlistRefreshPositions(v, pos, d_groupIdx, st))) return rc;
   if (v->refValid) {
     verletSortedPositions<<<nb, 256, 0, st>>>(pos, d_groupIdx, v->cl->groupIndex.as<int>(), N, v->sortPos.as<float4>());
     UB200_LAUNCHED();

@@ -150,6 +150,46 @@ class GaussianTorque:
         return IBMKernelStruct(2, self.support, self.h, self.prefactor, self.tau, self.rmax)
 
 
+class BarnettMagland:
+    """IBM_kernels::BarnettMagland (misc/IBM_kernels.cuh:83-113), the "exponential of a semicircle" window of Barnett, Magland
+    and af Klinteberg: phi(r) = exp(beta (sqrt(1 - (r/alpha)^2) - 1)) / norm for |r| <= alpha. alpha = half the support width,
+    `support` = grid points per dimension (the reference leaves it to the wrapping kernel). The norm follows computeNorm
+    (:93-97): 2 x composite Simpson over [0, alpha] with 20000 intervals, compensated sums."""
+
+    def __init__(self, alpha, beta, support):
+        self.alpha, self.beta, self.support = float(alpha), float(beta), int(support)
+        n = 20000
+        dx = self.alpha / n
+        terms = []
+        for i in range(n + 1):
+            z = (i * dx) / self.alpha
+            dz2 = 1.0 - z * z
+            w = 1.0 if i in (0, n) else (4.0 if i % 2 else 2.0)
+            terms.append(w * (0.0 if dz2 < 0.0 else math.exp(self.beta * (math.sqrt(dz2) - 1.0))))
+        self.norm = 2.0 * (dx / 3.0 * math.fsum(terms))
+        self.h = 2.0 * self.alpha / self.support
+
+    def phi(self, r):
+        z = r / self.alpha
+        dz2 = 1.0 - z * z
+        return 0.0 if dz2 < 0.0 else math.exp(self.beta * (math.sqrt(dz2) - 1.0)) / self.norm
+
+    def struct(self):
+        return IBMKernelStruct(3, self.support, self.h, 1.0 / self.norm, self.beta, self.alpha)
+
+
+class SixPoint:
+    """IBM_kernels::GaussianFlexible::sixPoint (misc/IBM_kernels.cuh:163-237): the C3 six-point kernel of Bao, Kaye and
+    Peskin; support 6."""
+    support = 6
+
+    def __init__(self, h, tolerance=None):
+        self.h = float(h)
+
+    def struct(self):
+        return IBMKernelStruct(4, 6, self.h, 0.0, 0.0, 0.0)
+
+
 def _prec(dtype):
     if dtype == torch.float64:
         return 8
