@@ -1,3 +1,3 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_vlist_gpu.py tests/test_verlet_gpu.py tests/test_nvt_gpu.py tests/test_pse_gpu.py -q -m gpu -x 2>&1 | grep -v "^\[W" | tail -5
-timeout 600 python scripts/vlist_time.py > gpurun_out/r02y_vlist_time.json 2> gpurun_out/r02y_vlist_time.err; tail -3 gpurun_out/r02y_vlist_time.err; cat gpurun_out/r02y_vlist_time.json
+oracle/_ref/gen_golden_windows gpurun_out six; ls -la gpurun_out/windows_six_f64.bin
+timeout 900 python -m pytest tests/test_fcm_gpu.py tests/test_oracle_fcm.py -q -x 2>&1 | grep -v "^\[W" | tail -8

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from uammd_b200 import synthetic as syn
-from uammd_b200.fcm import FCM_impl, FFT3D, Gaussian, IBM, Peskin3, Peskin4, hasimotoSelfMobility
+from uammd_b200.fcm import BarnettMagland, SixPoint, FCM_impl, FFT3D, Gaussian, IBM, Peskin3, Peskin4, hasimotoSelfMobility
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -62,10 +62,18 @@ def _cloud(N, L, seed, dtype=np.float64):
 
 @pytest.mark.parametrize("kname,cells,L", [("p3", (32, 32, 32), (32.0,) * 3), ("p4", (24, 20, 16), (12.0, 10.0, 8.0)),
                                            ("p4", (40, 36, 32), (20.0, 18.0, 16.0)), ("p3", (19, 21, 23), (9.5, 10.5, 11.5)),
-                                           ("p3", (64, 32, 7), (6.4, 3.2, 4.9)), ("gauss", (32, 32, 32), (32.0,) * 3)])
+                                           ("p3", (64, 32, 7), (6.4, 3.2, 4.9)), ("gauss", (32, 32, 32), (32.0,) * 3),
+                                           ("six", (32, 30, 28), (16.0, 15.0, 14.0)), ("bm", (32, 32, 32), (32.0,) * 3),
+                                           ("bm5", (36, 32, 40), (18.0, 16.0, 20.0))])
 def test_ibm_spread_gather_match_oracle(orc, cuda, kname, cells, L):
     h = min(L[d] / cells[d] for d in range(3))
-    if kname == "p3":
+    if kname == "six":    # GaussianFlexible::sixPoint: even support, warp-per-particle path
+        kern, ok = SixPoint(h), orc.six_point(h)
+    elif kname == "bm":   # Barnett-Magland, w = 6 points (alpha = w h / 2, beta = 1.8 w)
+        kern, ok = BarnettMagland(3.0 * h, 1.8 * 6, 6), orc.barnett_magland(3.0 * h, 1.8 * 6, 6)
+    elif kname == "bm5":  # w = 5: takes the node-centred (atomic-free) spread
+        kern, ok = BarnettMagland(2.5 * h, 1.8 * 5, 5), orc.barnett_magland(2.5 * h, 1.8 * 5, 5)
+    elif kname == "p3":
         kern, ok = Peskin3(h), orc.peskin3(h)
     elif kname == "p4":
         kern, ok = Peskin4(h), orc.peskin4(h)

@@ -16,6 +16,50 @@ def test_peskin_kernels_match_reference(orc, golden_dir):
         assert abs(orc.lib().orc_ibm_phi(k4, r) - p4) <= 1e-15 * max(1.0, abs(p4))
 
 
+def test_barnett_magland_window_matches_reference(orc, golden_dir):
+    """IBM_kernels::BarnettMagland (misc/IBM_kernels.cuh:83-113) evaluated by the reference's own host code
+    (tests/golden/gen_golden_windows.cu): the oracle and the host-side mirror of the product bindings."""
+    from uammd_b200.fcm import BarnettMagland
+    raw = np.fromfile(f"{golden_dir}/windows_bm_f64.bin", dtype=np.float64).reshape(3, 3 + 129)
+    for row in raw:
+        alpha, beta, phi0 = row[:3]
+        k = orc.barnett_magland(alpha, beta, 6)
+        mine = BarnettMagland(alpha, beta, 6)
+        assert abs(k.prefactor - phi0) <= 1e-13 * phi0 and abs(1.0 / mine.norm - phi0) <= 1e-13 * phi0
+        for i, v in enumerate(row[3:]):
+            r = (-1.05 + 2.1 * i / 128.0) * alpha
+            assert abs(orc.lib().orc_ibm_phi(k, r) - v) <= 1e-13 * max(1.0, abs(v))
+            assert abs(mine.phi(r) - v) <= 1e-13 * max(1.0, abs(v))
+        # unit integral (what the norm is for)
+        x = np.linspace(-alpha, alpha, 20001)
+        assert abs(np.trapezoid([orc.lib().orc_ibm_phi(k, float(t)) for t in x], x) - 1.0) < 1e-6
+
+
+def test_six_point_window(orc, golden_dir):
+    """GaussianFlexible::sixPoint (misc/IBM_kernels.cuh:163-237). Its constructor fills a device-side table, so the golden
+    vector comes from a GPU box (windows_six_f64.bin, same generator); without it the defining moment conditions of Bao, Kaye
+    and Peskin pin the closed form: sum_j phi(r - j) = 1, sum_j (r - j) phi = 0, sum_j (r - j)^2 phi = K, sum_j (r - j)^3 phi
+    = 0, even/odd sums 1/2 each, at every r."""
+    import os
+    K = 59.0 / 60.0 - np.sqrt(29.0) / 20.0
+    k = orc.six_point(1.0)
+    phi = lambda r: orc.lib().orc_ibm_phi(k, float(r))
+    for r in np.linspace(0.0, 1.0, 41):
+        j = np.arange(-4, 5)
+        w = np.array([phi(r - jj) for jj in j])
+        d = r - j
+        assert abs(w.sum() - 1.0) < 1e-13 and abs((d * w).sum()) < 1e-13
+        assert abs((d * d * w).sum() - K) < 1e-13 and abs((d ** 3 * w).sum()) < 1e-12
+        assert abs(w[j % 2 == 0].sum() - 0.5) < 1e-13
+    path = f"{golden_dir}/windows_six_f64.bin"
+    if os.path.exists(path):
+        raw = np.fromfile(path, dtype=np.float64)
+        h, rows = raw[0], raw[1:].reshape(-1, 2)
+        kh = orc.six_point(h)
+        for r, v in rows:
+            assert abs(orc.lib().orc_ibm_phi(kh, r) - v) <= 1e-14 * max(1.0, abs(v))
+
+
 def test_gaussian_kernel_parameters_match_reference(orc, golden_dir):
     from uammd_b200.fcm import Gaussian
     raw = np.fromfile(f"{golden_dir}/gaussian_f64.bin", dtype=np.float64).reshape(6, 70)
