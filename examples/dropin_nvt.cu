@@ -2,6 +2,7 @@
  * VerletNVT::GronbechJensen + PairForces<Potential::LJ, VerletList>.
  *   (A) stock   VerletNVT::GronbechJensen + PairForces<Potential::LJ, VerletList>            (the reference)
  *   (B) ours    b200::VerletNVTGronbechJensen, no interactor vs the reference integrator alone (bit identical expected)
+ *   (B') ours   b200::VerletNVTBasic vs the reference's VerletNVT::Basic alone                (bit identical expected)
  *   (C) ours    b200::VerletNVTGronbechJensen + b200::PairForcesLJ over b200::VerletList      next to (A)
  * Both systems start from the same System seed, so the integrators draw the same Saru seeds and initial velocities.
  * Built by oracle/Makefile into oracle/_ref/dropin_nvt; run by tests/test_dropin_gpu.py.  usage: dropin_nvt N L steps
@@ -47,6 +48,13 @@ static Diff compare(std::shared_ptr<ParticleData> a, std::shared_ptr<ParticleDat
   return d;
 }
 
+/* VerletNVT::Basic's public constructor is declared (VerletNVT.cuh:92) but never defined in the reference; a derived class
+   reaches the protected one. What runs is the unmodified Basic. */
+struct BasicExposed : VerletNVT::Basic {
+  BasicExposed(std::shared_ptr<ParticleData> pd, VerletNVT::Basic::Parameters par)
+      : VerletNVT::Basic(std::make_shared<ParticleGroup>(pd, "All"), par, "VerletNVT::Basic") {}
+};
+
 int main(int argc, char **argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 32768;
   const real L = argc > 2 ? atof(argv[2]) : 38.0;
@@ -72,6 +80,19 @@ int main(int argc, char **argv) {
     CudaSafeCall(cudaDeviceSynchronize());
     ideal = compare(pdA, pdB, N);
   }
+  // ---- VerletNVT::Basic alone: bit identity -------------------------------------------------------------------
+  Diff basic;
+  {
+    auto sysA = std::make_shared<System>(); sysA->rng().setSeed(99);
+    auto sysB = std::make_shared<System>(); sysB->rng().setSeed(99);
+    auto pdA = std::make_shared<ParticleData>(N, sysA), pdB = std::make_shared<ParticleData>(N, sysB);
+    lattice(pdA, N, L); lattice(pdB, N, L);
+    auto A = std::make_shared<BasicExposed>(pdA, np);
+    auto B = std::make_shared<b200::VerletNVTBasic>(pdB, bp);
+    for (int s = 0; s < steps; s++) { A->forwardTime(); B->forwardTime(); }
+    CudaSafeCall(cudaDeviceSynchronize());
+    basic = compare(pdA, pdB, N);
+  }
   // ---- with the LJ interactor over the Verlet list (benchmark.cu) ---------------------------------------------
   Diff lj;
   {
@@ -93,7 +114,7 @@ int main(int argc, char **argv) {
     lj = compare(pdA, pdC, N);
   }
   printf("{\"N\":%d,\"steps\":%d,\"ideal_mismatch_words\":%ld,\"ideal_max_dpos\":%.6g,\"ideal_max_dvel\":%.6g,"
-         "\"lj_max_dpos\":%.6g,\"lj_max_dvel\":%.6g}\n",
-         N, steps, ideal.words, ideal.dpos, ideal.dvel, lj.dpos, lj.dvel);
+         "\"basic_mismatch_words\":%ld,\"basic_max_dvel\":%.6g,\"lj_max_dpos\":%.6g,\"lj_max_dvel\":%.6g}\n",
+         N, steps, ideal.words, ideal.dpos, ideal.dvel, basic.words, basic.dvel, lj.dpos, lj.dvel);
   return 0;
 }

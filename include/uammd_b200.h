@@ -325,6 +325,12 @@ int ub200_dpd_sum_owned_ids_f32(ub200_celllist *cl, const void *d_vel, float A, 
 int ub200_nvt_gj_half_step_f32(void *d_pos, void *d_vel, void *d_force, const float *d_mass, float defaultMass,
                                const int *d_groupIdx, int N, float dt, float friction, int is2D, float noiseAmplitude,
                                uint32_t stepNum, uint32_t seed, int step, void *stream);
+/* VerletNVT::Basic_ns::integrateGPU<1|2> (Integrator/VerletNVT/Basic.cu:87-117): the plain Langevin velocity Verlet, same
+ * arguments as ub200_nvt_gj_half_step_f32; BOTH half steps kick with friction and a fresh noise draw
+ * (Saru(index + N (step - 1), stepNum, seed)), step 1 also drifts and zeroes the force. Bit-identical to the reference. */
+int ub200_nvt_basic_half_step_f32(void *d_pos, void *d_vel, void *d_force, const float *d_mass, float defaultMass,
+                                  const int *d_groupIdx, int N, float dt, float friction, int is2D, float noiseAmplitude,
+                                  uint32_t stepNum, uint32_t seed, int step, void *stream);
 int ub200_nvt_initial_velocities_f32(void *d_vel, const int *d_groupIdx, int N, float velAmplitude, int is2D, uint32_t seed,
                                      void *stream);
 

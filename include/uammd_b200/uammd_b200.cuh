@@ -22,6 +22,8 @@
  *                                 PairForces<AnyPotential, b200::VerletList> runs user Transversers through the reference's
  *                                 own kernel; b200::PairForcesLJ takes it as its neighbour list for the fast LJ path.
  *   uammd::b200::PSE              BDHI Method concept for BDHI::EulerMaruyama<Method> = BDHI::PSE (BDHI_PSE.cuh:82-176).
+ *   uammd::b200::VerletNVTGronbechJensen / VerletNVTBasic   Integrators = VerletNVT::GronbechJensen / VerletNVT::Basic
+ *                                 (Integrator/VerletNVT.cuh:59-117), bit-identical half steps.
  *   uammd::b200::BDEulerMaruyama  Integrator = BD::EulerMaruyama (Integrator/BrownianDynamics.cuh:111-126).
  *   uammd::b200::FCM<Kernel>      BDHI Method concept (Integrator/BDHI/BDHI_FCM.cuh:85-153) for
  *                                 BDHI::EulerMaruyama<Method> (Integrator/BDHI/BDHI_EulerMaruyama.cuh:64-98).
@@ -1029,12 +1031,20 @@ public:
 };
 
 #ifndef DOUBLE_PRECISION
-/* ---------------------------------------------------------------- VerletNVT::GronbechJensen ----------------- */
+/* ---------------------------------------------------------------- VerletNVT::{GronbechJensen, Basic} -------- */
 /* Integrator (Integrator/VerletNVT.cuh:100-117, VerletNVT/Basic.cu:31-77, VerletNVT/GronbechJensen.cu:96-127): the
    Langevin integrator generic_md and examples/misc/benchmark.cu drive. Same constructor side effects as
    VerletNVT::Basic (Saru seed = third next32() of the system generator, optional initial velocities with the fourth),
-   same forwardTime sequence; the two half steps run through ub200_nvt_gj_half_step_f32 (bit-identical). */
-class VerletNVTGronbechJensen : public Integrator {
+   same forwardTime sequence; the two half steps run through ub200_nvt_gj_half_step_f32 (bit-identical).
+   VerletNVTBasic = VerletNVT::Basic (Basic.cu:87-172), the scheme GronbechJensen derives from: same class, its half steps
+   run through ub200_nvt_basic_half_step_f32. (The reference declares Basic's public constructor, VerletNVT.cuh:92, but
+   never defines it - a program that constructs VerletNVT::Basic does not link; this one does.) */
+struct VerletNVTParameters { /* VerletNVT::Basic::Parameters (VerletNVT.cuh:64-71) */
+  real temperature = 0, dt = 0, friction = 1.0;
+  bool is2D = false, initVelocities = true;
+  real mass = -1.0;
+};
+template <bool GRONBECH_JENSEN> class VerletNVTScheme : public Integrator {
   real noiseAmplitude, dt, temperature, friction, defaultMass;
   bool is2D;
   uint seed;
@@ -1047,22 +1057,17 @@ class VerletNVTGronbechJensen : public Integrator {
     auto vel = pd->getVel(access::location::gpu, access::mode::readwrite);
     auto force = pd->getForce(access::location::gpu, access::mode::readwrite);
     auto mass = pd->getMassIfAllocated(access::location::gpu, access::mode::read).raw();
-    check(ub200_nvt_gj_half_step_f32(pos.raw(), vel.raw(), force.raw(), defaultMass > 0 ? nullptr : mass, defaultMass > 0 ? defaultMass : 0,
-                                     pg->getIndicesRawPtr(access::location::gpu), N, dt, friction, is2D, noiseAmplitude, (uint)steps,
-                                     seed, step, (void *)st),
-          "nvt_gj_half_step");
+    auto fn = GRONBECH_JENSEN ? ub200_nvt_gj_half_step_f32 : ub200_nvt_basic_half_step_f32;
+    check(fn(pos.raw(), vel.raw(), force.raw(), defaultMass > 0 ? nullptr : mass, defaultMass > 0 ? defaultMass : 0,
+             pg->getIndicesRawPtr(access::location::gpu), N, dt, friction, is2D, noiseAmplitude, (uint)steps, seed, step, (void *)st),
+          "nvt_half_step");
   }
 
 public:
-  struct Parameters {
-    real temperature = 0, dt = 0, friction = 1.0;
-    bool is2D = false, initVelocities = true;
-    real mass = -1.0;
-  };
-  VerletNVTGronbechJensen(shared_ptr<ParticleData> pd, Parameters par)
-      : VerletNVTGronbechJensen(std::make_shared<ParticleGroup>(pd, "All"), par) {}
-  VerletNVTGronbechJensen(shared_ptr<ParticleGroup> pg, Parameters par)
-      : Integrator(pg, "b200::VerletNVTGronbechJensen"), dt(par.dt), temperature(par.temperature), friction(par.friction),
+  using Parameters = VerletNVTParameters;
+  VerletNVTScheme(shared_ptr<ParticleData> pd, Parameters par) : VerletNVTScheme(std::make_shared<ParticleGroup>(pd, "All"), par) {}
+  VerletNVTScheme(shared_ptr<ParticleGroup> pg, Parameters par)
+      : Integrator(pg, GRONBECH_JENSEN ? "b200::VerletNVTGronbechJensen" : "b200::VerletNVTBasic"), dt(par.dt), temperature(par.temperature), friction(par.friction),
         is2D(par.is2D) {
     sys->rng().next32();
     sys->rng().next32();
@@ -1080,7 +1085,7 @@ public:
       CudaSafeCall(cudaDeviceSynchronize());
     }
   }
-  ~VerletNVTGronbechJensen() { cudaStreamDestroy(st); }
+  ~VerletNVTScheme() { cudaStreamDestroy(st); }
   uint getSeed() const { return seed; }
   void forwardTime() override {
     for (auto u : updatables) u->updateSimulationTime(steps * dt);
@@ -1103,6 +1108,8 @@ public:
     half(2);
   }
 };
+using VerletNVTGronbechJensen = VerletNVTScheme<true>;
+using VerletNVTBasic = VerletNVTScheme<false>;
 #endif /* !DOUBLE_PRECISION */
 
 } // namespace b200

@@ -88,6 +88,9 @@ void orc_md_scratch_free(void *);
    (Integrator/VerletNVT/Basic.cu:12-29), single precision */
 void orc_nvt_gj_half_f32(float *pos4, float *vel3, float *force4, const float *mass, float defaultMass, int N, float dt,
                          float friction, int is2D, float noiseAmplitude, uint32_t stepNum, uint32_t seed, int step);
+/* VerletNVT::Basic_ns::integrateGPU<step> Integrator/VerletNVT/Basic.cu:87-117 */
+void orc_nvt_basic_half_f32(float *pos4, float *vel3, float *force4, const float *mass, float defaultMass, int N, int Ngroup,
+                            float dt, float friction, int is2D, float noiseAmplitude, uint32_t stepNum, uint32_t seed, int step);
 void orc_nvt_initial_velocities_f32(float *vel3, int N, float vamp, int is2D, uint32_t seed);
 
 /* ---------------- path 2: IBM + FCM (fp64) ---------------- */

@@ -212,6 +212,14 @@ def nvt_gj_half(pos4, vel3, force4, dt, friction, noiseAmplitude, stepNum, seed,
                               C.c_uint32(stepNum), C.c_uint32(seed), int(step))
 
 
+def nvt_basic_half(pos4, vel3, force4, dt, friction, noiseAmplitude, stepNum, seed, step, defaultMass=1.0, mass=None,
+                   is2D=False, Ngroup=None):
+    """In place VerletNVT::Basic half step (float32 arrays). Ngroup: size of the whole group when the arrays hold a prefix."""
+    lib().orc_nvt_basic_half_f32(_p(pos4), _p(vel3), _p(force4), _p(mass), C.c_float(defaultMass), pos4.shape[0],
+                                 int(Ngroup if Ngroup is not None else pos4.shape[0]), C.c_float(dt), C.c_float(friction), int(is2D), C.c_float(noiseAmplitude),
+                                 C.c_uint32(stepNum), C.c_uint32(seed), int(step))
+
+
 def nvt_initial_velocities(N, vamp, seed, is2D=False):
     vel = np.zeros((N, 3), np.float32)
     lib().orc_nvt_initial_velocities_f32(_p(vel), N, C.c_float(vamp), int(is2D), C.c_uint32(seed))

@@ -534,6 +534,36 @@ void orc_nvt_gj_half_f32(float *pos4, float *vel3, float *force4, const float *m
   }
 }
 
+/* VerletNVT::Basic_ns::integrateGPU<step> Integrator/VerletNVT/Basic.cu:87-117, single precision build: in BOTH half
+ * steps v += (f/m - friction v) dt/2 + noise with noise = gf(0, noiseAmplitude sqrt(1/(2m))) drawn from
+ * Saru(id + N (step - 1), stepNum, seed); step 1 then drifts (x += v dt) and zeroes the force. fmaf() marks the
+ * contractions nvcc applies to the reference kernel (read from its PTX). */
+void orc_nvt_basic_half_f32(float *pos4, float *vel3, float *force4, const float *mass, float defaultMass, int N, int Ngroup,
+                            float dt, float friction, int is2D, float noiseAmplitude, uint32_t stepNum, uint32_t seed, int step) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < N; i++) {
+    const float invMass = 1.0f / (defaultMass > 0.0f ? defaultMass : mass[i]);
+    float *p = pos4 + 4 * (size_t)i, *v = vel3 + 3 * (size_t)i, *f = force4 + 4 * (size_t)i;
+    orc_saru rng = orc_saru_seed3((uint32_t)(i + Ngroup * (step - 1)), stepNum, seed); /* Ngroup: particles of the group (N may be a prefix of it) */
+    const float amp = noiseAmplitude * sqrtf(invMass * 0.5f);
+    float n[3], g2[2];
+    orc_saru_gf(&rng, 0.0f, amp, g2);
+    n[0] = g2[0]; n[1] = g2[1];
+    orc_saru_gf(&rng, 0.0f, amp, g2);
+    n[2] = g2[0];
+    const float hdt = dt * 0.5f;
+    for (int d = 0; d < 3; d++) {
+      const float t = invMass * f[d], u = friction * v[d];
+      v[d] = v[d] + fmaf(hdt, t - u, n[d]);
+    }
+    if (is2D) v[2] = 0.0f;
+    if (step == 1) {
+      for (int d = 0; d < 3; d++) p[d] = fmaf(dt, v[d], p[d]);
+      f[0] = f[1] = f[2] = f[3] = 0.0f;
+    }
+  }
+}
+
 /* Basic_ns::initialVelocities Integrator/VerletNVT/Basic.cu:12-29 (mass ignored: mass_i = 1; no group here) */
 void orc_nvt_initial_velocities_f32(float *vel3, int N, float vamp, int is2D, uint32_t seed) {
   for (int i = 0; i < N; i++) {

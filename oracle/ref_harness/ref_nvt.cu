@@ -37,6 +37,14 @@ template <class T> static void writeBin(const std::string &fn, const T *p, size_
   fclose(f);
 }
 
+/* The reference declares Basic(shared_ptr<ParticleGroup>, Parameters) (VerletNVT.cuh:92) but defines only the protected
+   three-argument constructor (Basic.cu:31-52): a program that constructs VerletNVT::Basic does not link. A derived class
+   reaches the protected constructor; everything that runs is the unmodified Basic. */
+struct BasicExposed : VerletNVT::Basic {
+  BasicExposed(std::shared_ptr<ParticleData> pd, VerletNVT::Basic::Parameters par)
+      : VerletNVT::Basic(std::make_shared<ParticleGroup>(pd, "All"), par, "VerletNVT::Basic") {}
+};
+
 int main(int argc, char **argv) {
   if (argc < 11) return 1;
   const int N = atoi(argv[1]);
@@ -80,7 +88,12 @@ int main(int argc, char **argv) {
   par.dt = dt;
   par.friction = friction;
   par.initVelocities = initVel;
-  auto nvt = std::make_shared<VerletNVT::GronbechJensen>(pd, par);
+  // REF_NVT_SCHEME=basic drives VerletNVT::Basic (Integrator/VerletNVT/Basic.cu:87-172), the class GronbechJensen derives from
+  const char *scheme = getenv("REF_NVT_SCHEME");
+  const bool basic = scheme && std::string(scheme) == "basic";
+  std::shared_ptr<VerletNVT::Basic> nvt;
+  if (basic) nvt = std::make_shared<BasicExposed>(pd, par);
+  else nvt = std::make_shared<VerletNVT::GronbechJensen>(pd, par);
   CudaSafeCall(cudaDeviceSynchronize());
   {
     auto pos = pd->getPos(access::location::cpu, access::mode::read);
@@ -121,7 +134,7 @@ int main(int argc, char **argv) {
     writeBin(out + ".pos.bin", pos.raw(), N);
     writeBin(out + ".vel.bin", vel.raw(), N);
   }
-  printf("{\"mode\":\"nvt_gj\",\"N\":%d,\"steps\":%d,\"seed\":%u,\"vel_seed\":%u,\"ms_per_step\":%.6f}\n", N, steps, seed, velSeed,
+  printf("{\"mode\":\"%s\",\"N\":%d,\"steps\":%d,\"seed\":%u,\"vel_seed\":%u,\"ms_per_step\":%.6f}\n", basic ? "nvt_basic" : "nvt_gj", N, steps, seed, velSeed,
          steps ? ms / steps : 0.f);
   sys->finish();
   return 0;

@@ -43,6 +43,7 @@ def test_langevin_verlet_dropin_matches_reference():
     r = _run("dropin_nvt", 32768, 38.0, 20)
     print(r)
     assert r["ideal_mismatch_words"] == 0                # b200::VerletNVTGronbechJensen alone: the reference's bits
+    assert r["basic_mismatch_words"] == 0                # b200::VerletNVTBasic alone: the bits of VerletNVT::Basic
     assert r["lj_max_dpos"] < 1e-4 and r["lj_max_dvel"] < 1e-2   # with the LJ forces: fp32 summation order only
 
 

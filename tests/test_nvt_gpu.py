@@ -15,19 +15,20 @@ import torch
 
 from uammd_b200.bd import System
 from uammd_b200.md import Box, LJ, PairForces, VerletList
-from uammd_b200.nvt import GronbechJensen, Parameters
+from uammd_b200.nvt import Basic, GronbechJensen, Parameters
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _ref(tmp_path, N, L, steps, T, friction, dt, sysseed, lj, initVel):
+def _ref(tmp_path, N, L, steps, T, friction, dt, sysseed, lj, initVel, scheme="gj"):
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_nvt")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/ref_nvt not built (needs the reference tree at build time)")
     out = str(tmp_path / "nvt")
     r = subprocess.run([exe, str(N), repr(L), str(steps), repr(T), repr(friction), repr(dt), str(sysseed), str(int(lj)),
-                        str(int(initVel)), out], check=True, capture_output=True, text=True, timeout=600).stdout
+                        str(int(initVel)), out], check=True, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, REF_NVT_SCHEME="basic" if scheme == "basic" else "gj")).stdout
     info = json.loads([l for l in r.splitlines() if l.startswith("{")][-1])
     rd = lambda name, w: np.fromfile(f"{out}.{name}.bin", dtype=np.float32).reshape(N, w)
     return info, rd("pos0", 4), rd("vel0", 3), rd("pos", 4), rd("vel", 3)
@@ -40,9 +41,14 @@ def _record(name, payload):
             json.dump(payload, f)
 
 
-def test_ideal_langevin_gas_bit_identical_to_reference(cuda, tmp_path):
+@pytest.mark.parametrize("scheme", ["gj", "basic"])
+def test_ideal_langevin_gas_bit_identical_to_reference(cuda, tmp_path, scheme):
+    """scheme "basic": VerletNVT::Basic (Basic.cu:87-172) through a derived class in the harness - the reference never defines
+    its public constructor."""
     N, L, steps, T, friction, dt, sysseed = 4096, 32.0, 25, 1.3, 0.7, 0.01, 1234
-    info, pos0, vel0, rpos, rvel = _ref(tmp_path, N, L, steps, T, friction, dt, sysseed, lj=False, initVel=True)
+    info, pos0, vel0, rpos, rvel = _ref(tmp_path, N, L, steps, T, friction, dt, sysseed, lj=False, initVel=True, scheme=scheme)
+    assert info["mode"] == ("nvt_basic" if scheme == "basic" else "nvt_gj")
+    GronbechJensen = Basic if scheme == "basic" else globals()["GronbechJensen"]
     pos = torch.from_numpy(pos0.copy()).to(cuda)
     vel = torch.zeros(N, 3, device=cuda)
     sys_ = System(sysseed)
@@ -57,19 +63,20 @@ def test_ideal_langevin_gas_bit_identical_to_reference(cuda, tmp_path):
     p, v = pos.cpu().numpy(), vel.cpu().numpy()
     mism_p = int((p.view(np.uint32) != rpos.view(np.uint32)).sum())
     mism_v = int((v.view(np.uint32) != rvel.view(np.uint32)).sum())
-    _record("nvt_parity.json", {"N": N, "steps": steps, "mismatch_words": {"vel0": mism_v0, "pos": mism_p, "vel": mism_v},
+    _record("nvt_parity.json" if scheme == "gj" else "nvt_basic_parity.json", {"N": N, "steps": steps, "mismatch_words": {"vel0": mism_v0, "pos": mism_p, "vel": mism_v},
                                 "max_abs": {"vel0": float(np.abs(v0 - vel0).max()), "pos": float(np.abs(p - rpos).max()),
                                             "vel": float(np.abs(v - rvel).max())}})
     g = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(g):   # golden vectors for the CPU oracle test (tests/golden/nvt_gj_ref.npz is made from these)
-        np.savez_compressed(os.path.join(g, "nvt_gj_ref.npz"), pos0=pos0[:512], vel0=vel0[:512], pos=rpos[:512], vel=rvel[:512],
+        np.savez_compressed(os.path.join(g, f"nvt_{scheme}_ref.npz"), pos0=pos0[:512], vel0=vel0[:512], pos=rpos[:512], vel=rvel[:512],
                             seed=info["seed"], vel_seed=info["vel_seed"], meta=np.array([N, L, steps, T, friction, dt, sysseed]))
     assert np.abs(vel0).max() > 1.0 and np.abs(rpos - pos0).max() > 1e-2          # the reference did move
     assert mism_v0 == 0, f"initial velocities differ from the reference in {mism_v0} words"
     assert mism_p == 0 and mism_v == 0, f"trajectory differs from the reference: {mism_p} pos / {mism_v} vel words"
 
 
-def test_half_steps_match_oracle_with_forces_masses_and_2d(orc, cuda):
+@pytest.mark.parametrize("scheme", ["gj", "basic"])
+def test_half_steps_match_oracle_with_forces_masses_and_2d(orc, cuda, scheme):
     """Random forces, per-particle masses, 2-D mode, a group index list: against the C restatement. The host libm's
     logf/sinf/cosf differ from the device's in the last ulp: tolerance 2e-6 of the noise amplitude scale."""
     N = 5000
@@ -81,7 +88,8 @@ def test_half_steps_match_oracle_with_forces_masses_and_2d(orc, cuda):
         mass = rng.uniform(0.5, 3.0, N).astype(np.float32) if use_mass else None
         par = Parameters(temperature=0.9, dt=0.005, friction=2.0, is2D=is2D, initVelocities=False)
         dp, dv = torch.from_numpy(pos.copy()).to(cuda), torch.from_numpy(vel.copy()).to(cuda)
-        nvt = GronbechJensen(dp, dv, par, sys=System(77), mass=torch.from_numpy(mass).to(cuda) if use_mass else None)
+        cls, half = (Basic, orc.nvt_basic_half) if scheme == "basic" else (GronbechJensen, orc.nvt_gj_half)
+        nvt = cls(dp, dv, par, sys=System(77), mass=torch.from_numpy(mass).to(cuda) if use_mass else None)
         nvt.force.copy_(torch.from_numpy(force))
         nvt.steps = 5
         nvt._half(1)
@@ -92,9 +100,9 @@ def test_half_steps_match_oracle_with_forces_masses_and_2d(orc, cuda):
         torch.cuda.synchronize()
         op, ov, of = pos.copy(), vel.copy(), force.copy()
         kw = dict(defaultMass=0.0 if use_mass else 1.0, mass=mass, is2D=is2D)
-        orc.nvt_gj_half(op, ov, of, par.dt, par.friction, nvt.noiseAmplitude, 5, nvt.seed, 1, **kw)
+        half(op, ov, of, par.dt, par.friction, nvt.noiseAmplitude, 5, nvt.seed, 1, **kw)
         assert np.all(of == 0)
-        orc.nvt_gj_half(op, ov, force.copy(), par.dt, par.friction, nvt.noiseAmplitude, 5, nvt.seed, 2, **kw)
+        half(op, ov, force.copy(), par.dt, par.friction, nvt.noiseAmplitude, 5, nvt.seed, 2, **kw)
         assert np.abs(dp.cpu().numpy() - op).max() <= 2e-6 * (1.0 + np.abs(op).max())   # an ulp of the largest coordinate
         assert np.abs(dv.cpu().numpy() - ov).max() <= 2e-6 * (1.0 + np.abs(ov).max())
         if is2D:

@@ -42,3 +42,25 @@ def test_ideal_gas_trajectory_matches_reference(orc):
     assert np.abs(g["pos"] - g["pos0"]).max() > 1e-2
     assert np.abs(pos - g["pos"]).max() <= 1e-5
     assert np.abs(vel - g["vel"]).max() <= 1e-5
+
+
+def test_basic_scheme_trajectory_matches_reference(orc):
+    """VerletNVT::Basic (Basic.cu:87-172): golden vector from the compiled reference on a B200 (tests/golden/nvt_basic_ref.npz,
+    same generator as above with REF_NVT_SCHEME=basic). Both half steps draw noise; the second one's Saru index is offset by
+    the group size."""
+    import pytest
+    path = GOLD.replace("nvt_gj_ref", "nvt_basic_ref")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/nvt_basic_ref.npz not generated yet")
+    g = np.load(path)
+    N, L, steps, T, friction, dt, sysseed = g["meta"]
+    f = np.float32
+    amp = float(np.sqrt(f(f(f(f(2.0) * f(dt)) * f(friction)) * f(T))))
+    pos, vel = g["pos0"].copy(), g["vel0"].copy()
+    force = np.zeros_like(pos)
+    for s in range(1, int(steps) + 1):
+        orc.nvt_basic_half(pos, vel, force, float(f(dt)), float(f(friction)), amp, s, int(g["seed"]), 1, Ngroup=int(N))
+        orc.nvt_basic_half(pos, vel, force, float(f(dt)), float(f(friction)), amp, s, int(g["seed"]), 2, Ngroup=int(N))
+    assert np.abs(g["pos"] - g["pos0"]).max() > 1e-2
+    assert np.abs(pos - g["pos"]).max() <= 1e-5
+    assert np.abs(vel - g["vel"]).max() <= 1e-5

@@ -59,6 +59,43 @@ gjIntegrate(float4 *__restrict__ pos, float *__restrict__ vel, float4 *__restric
   }
 }
 
+// VerletNVT::Basic_ns::integrateGPU<step> (Integrator/VerletNVT/Basic.cu:87-117): the plain Langevin velocity Verlet,
+//   both half steps: v += (f/m - friction v) dt/2 + noise,  noise ~ N(0, noiseAmplitude^2 / (2 m)) from
+//   Saru(index in group + N (step - 1), stepNum, seed) - a fresh draw in EACH half step;  step 1 then: x += v dt, f = 0.
+// Roundings as nvcc contracts the reference kernel for sm_100a (read from its PTX): two products and a difference, one
+// fma with the noise as addend, an addition; the drift is one fma.
+template <int STEP>
+__global__ void __launch_bounds__(128)
+basicIntegrate(float4 *__restrict__ pos, float *__restrict__ vel, float4 *__restrict__ force, const float *__restrict__ mass,
+               float defaultMass, const int *__restrict__ groupIdx, int N, float dt, float friction, int is2D,
+               float noiseAmplitude, uint32_t stepNum, uint32_t seed) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  const int i = groupIdx ? groupIdx[id] : id;
+  const float invMass = __frcp_rn(defaultMass > 0.0f ? defaultMass : mass[i]);
+  Saru rng((uint32_t)(id + N * (STEP - 1)), stepNum, seed);
+  const float amp = __fmul_rn(noiseAmplitude, __fsqrt_rn(__fmul_rn(invMass, 0.5f)));
+  const float2 n01 = rng.gauss2(amp);
+  const float nz = rng.gauss2(amp).x;
+  float *v = vel + 3 * (size_t)i;
+  const float4 f = force[i];
+  const float hdt = __fmul_rn(dt, 0.5f);
+  const float v0 = v[0], v1 = v[1], v2 = v[2];
+  const float vx = __fadd_rn(v0, __fmaf_rn(hdt, __fsub_rn(__fmul_rn(invMass, f.x), __fmul_rn(friction, v0)), n01.x));
+  const float vy = __fadd_rn(v1, __fmaf_rn(hdt, __fsub_rn(__fmul_rn(invMass, f.y), __fmul_rn(friction, v1)), n01.y));
+  float vz = __fadd_rn(__fmaf_rn(hdt, __fsub_rn(__fmul_rn(invMass, f.z), __fmul_rn(friction, v2)), nz), v2);
+  if (is2D) vz = 0.0f;
+  v[0] = vx; v[1] = vy; v[2] = vz;
+  if (STEP == 1) {
+    float4 p = pos[i];
+    p.x = __fmaf_rn(dt, vx, p.x);
+    p.y = __fmaf_rn(dt, vy, p.y);
+    p.z = __fmaf_rn(dt, vz, p.z);
+    pos[i] = p;
+    force[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // Basic_ns::initialVelocities (Basic.cu:12-29): Saru(id, seed) two-seed constructor (saruprng.cuh:236-251), gd() =
 // Box-Muller on float uniforms with float log/sin/cos/sqrt and a double product (saruprng.cuh:130-143). The reference
 // ignores the mass here (mass_i = 1) and indexes the group twice (vel[index[index[id]]]); both are kept.
@@ -115,6 +152,23 @@ extern "C" int ub200_nvt_gj_half_step_f32(void *d_pos, void *d_vel, void *d_forc
   else
     gjIntegrate<2><<<nb, 128, 0, st>>>((float4 *)d_pos, (float *)d_vel, (float4 *)d_force, d_mass, defaultMass, d_groupIdx, N,
                                        dt, friction, is2D, noiseAmplitude, stepNum, seed);
+  UB200_LAUNCHED();
+  return UB200_OK;
+}
+
+extern "C" int ub200_nvt_basic_half_step_f32(void *d_pos, void *d_vel, void *d_force, const float *d_mass, float defaultMass,
+                                             const int *d_groupIdx, int N, float dt, float friction, int is2D,
+                                             float noiseAmplitude, uint32_t stepNum, uint32_t seed, int step, void *stream) {
+  if (!d_pos || !d_vel || !d_force || N <= 0 || (step != 1 && step != 2)) return UB200_ERR_INVALID_ARGUMENT;
+  if (!(defaultMass > 0.0f) && !d_mass) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (N + 127) / 128;
+  if (step == 1)
+    basicIntegrate<1><<<nb, 128, 0, st>>>((float4 *)d_pos, (float *)d_vel, (float4 *)d_force, d_mass, defaultMass, d_groupIdx,
+                                          N, dt, friction, is2D, noiseAmplitude, stepNum, seed);
+  else
+    basicIntegrate<2><<<nb, 128, 0, st>>>((float4 *)d_pos, (float *)d_vel, (float4 *)d_force, d_mass, defaultMass, d_groupIdx,
+                                          N, dt, friction, is2D, noiseAmplitude, stepNum, seed);
   UB200_LAUNCHED();
   return UB200_OK;
 }

@@ -17,6 +17,8 @@ def _declare():
     vp, i, f, u32 = C.c_void_p, C.c_int, C.c_float, C.c_uint32
     l.ub200_nvt_gj_half_step_f32.restype = i
     l.ub200_nvt_gj_half_step_f32.argtypes = [vp, vp, vp, vp, f, vp, i, f, f, i, f, u32, u32, i, vp]
+    l.ub200_nvt_basic_half_step_f32.restype = i
+    l.ub200_nvt_basic_half_step_f32.argtypes = [vp, vp, vp, vp, f, vp, i, f, f, i, f, u32, u32, i, vp]
     l.ub200_nvt_initial_velocities_f32.restype = i
     l.ub200_nvt_initial_velocities_f32.argtypes = [vp, vp, i, f, i, u32, vp]
     return l
@@ -68,9 +70,11 @@ class GronbechJensen:
         check(self.l.ub200_nvt_initial_velocities_f32(_ptr(self.vel), _ptr(self.groupIndex), self.N, velAmplitude,
                                                       int(self.is2D), self.sys.rng().next32(), _stream_ptr()))
 
+    _half_step_symbol = "ub200_nvt_gj_half_step_f32"
+
     def _half(self, step):
         mass = None if self.defaultMass > 0 else self.mass
-        check(self.l.ub200_nvt_gj_half_step_f32(_ptr(self.pos), _ptr(self.vel), _ptr(self.force), _ptr(mass),
+        check(getattr(self.l, self._half_step_symbol)(_ptr(self.pos), _ptr(self.vel), _ptr(self.force), _ptr(mass),
                                                 self.defaultMass if self.defaultMass > 0 else 0.0, _ptr(self.groupIndex),
                                                 self.N, float(self.dt), float(self.friction), int(self.is2D),
                                                 self.noiseAmplitude, self.steps & 0xFFFFFFFF, self.seed, step, _stream_ptr()))
@@ -88,6 +92,13 @@ class GronbechJensen:
         self._half(1)
         self._sumForces()
         self._half(2)
+
+
+class Basic(GronbechJensen):
+    """VerletNVT::Basic(pd, par) (Integrator/VerletNVT/Basic.cu:31-52,87-172): the plain Langevin velocity Verlet - friction and a
+    fresh noise draw in both half kicks. Same constructor, seed draws, initial velocities and forwardTime sequence as
+    GronbechJensen (which derives from it in the reference, VerletNVT.cuh:59-117)."""
+    _half_step_symbol = "ub200_nvt_basic_half_step_f32"
 
 
 def f32(x):
