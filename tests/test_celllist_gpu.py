@@ -41,6 +41,26 @@ def test_non_cubic_box_and_explicit_grid(orc, cuda):
     _check_against_oracle(orc, cuda, syn.uniform_cloud(50000, L, seed=5), L, cellDim=(64, 32, 7))
 
 
+@pytest.mark.parametrize("cells,N", [((520, 4, 4), 20000), ((4, 300, 5), 10000), ((129, 129, 129), 100000), ((1, 700, 1), 3000)])
+def test_grids_beyond_256_cells_per_dimension_and_awkward_shapes(orc, cuda, cells, N):
+    """One bin per cell in Morton order (rank table): more than 256 cells in a dimension (the reference's 10-bit Morton fields
+    allow 1024), shapes whose largest Morton code has far more bits than the grid has cells, collapsed dimensions. The lists
+    that hang off the cell list must agree too: LJ forces over it against the half-cell engine."""
+    from uammd_b200.md import LJ, PairForces
+    L = tuple(2.5 * c for c in cells)
+    pos = syn.uniform_cloud(N, L, seed=cells[0])
+    cl = _check_against_oracle(orc, cuda, pos, L, cellDim=cells, rebuilds=2)
+    if min(cells) >= 4:
+        pot = LJ(); pot.setPotParameters(0, 0, cutOff=2.5)
+        dpos = torch.from_numpy(pos).to(cuda)
+        f0, f1 = torch.zeros(N, 4, device=cuda), torch.zeros(N, 4, device=cuda)
+        PairForces(pot, Box(L)).sum(dpos, f0)
+        nl = CellList()
+        PairForces(pot, Box(L), nl=nl).sum(dpos, f1)
+        scale = max(1.0, f0[:, :3].abs().max().item())
+        assert (f0 - f1)[:, :3].abs().max().item() < 2e-5 * scale
+
+
 def test_particles_outside_primary_box_are_folded(orc, cuda):
     L = (30.0, 22.0, 41.0)
     pos = syn.uniform_cloud(30000, L, seed=8)

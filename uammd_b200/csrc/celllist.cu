@@ -1,16 +1,20 @@
-// Cell list build for sm_100a: warp-aggregated counting sort over Morton-code bins.
+// Cell list build for sm_100a: warp-aggregated counting sort over the cells in Morton order.
 //
 // Replaces the reference chain assignHash -> cub::DeviceRadixSort::SortPairs -> permutation gather ->
 // fillCellList (utils/ParticleSorter.cuh:102-111,243-274,179-187; CellList/CellListBase.cuh:68-95) by
 //   1. binParticles   : cell of each particle (reference-exact fp32 arithmetic), Morton code, slot in the
 //                       bin from a warp-aggregated atomicAdd                       R 16 B  W 8 B / particle
-//   2. scan (3 tiny kernels over the 2^maxbit Morton codes)                         ~4 B / code
+//   2. scan (3 tiny kernels over the ncells bins)                                   ~4 B / cell
 //   3. scatterToBins  : unstable[binStart[code]+slot] = i                           R 8 B   W 4 B
 //   4. orderAndGather : restores the STABLE order inside each bin (rank = #smaller indices in the bin,
 //                       bins hold ~N/ncells entries and sit in L1), writes groupIndex, gathers sortPos and
 //                       emits cellStart/cellEnd in the reference layout            R 12+16 B W 20 B
-// The result is bit-identical to the reference's stable radix sort by Morton hash.
+// The result is bit-identical to the reference's stable radix sort by Morton hash. A bin is a CELL: its index is the
+// rank of the cell's Morton code among the cells of the grid (a table per grid shape, made once with a radix sort of the
+// ncells codes), so the bin table has ncells entries for any grid - 129^3 or 512 x 4 x 4 alike - instead of the
+// 2^(bits of the largest code) of a table indexed by the code itself.
 #include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace ub200 {
 
@@ -34,7 +38,7 @@ binParticles(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, i
     cy = min(max(cy, 0), g.ny - 1);
     cz = min(max(cz, 0), g.nz - 1);
   }
-  const uint32_t code = mortonCode(cx, cy, cz);
+  const uint32_t code = cellBin(g, cx, cy, cz);
   // warp-aggregated increment: one atomic per distinct bin per warp
   const unsigned active = __activemask();
   const unsigned peers = __match_any_sync(active, code);
@@ -176,7 +180,8 @@ orderAndGather(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
                const uint32_t *__restrict__ binStart, const float4 *__restrict__ pos,
                const int *__restrict__ groupIdx, int N, GridF g, uint32_t validCell,
                float4 *__restrict__ sortPos, int *__restrict__ groupIndex, uint32_t *__restrict__ cellStart,
-               int *__restrict__ cellEnd, const int *__restrict__ nDev = nullptr, const int *__restrict__ sortKey = nullptr) {
+               int *__restrict__ cellEnd, const uint32_t *__restrict__ cellOfRank, const int *__restrict__ nDev = nullptr,
+               const int *__restrict__ sortKey = nullptr) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (nDev) N = min(N, *nDev);
   if (k >= N) return;
@@ -194,8 +199,7 @@ orderAndGather(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
   groupIndex[dst] = i;
   sortPos[dst] = ldg4(pos + (groupIdx ? groupIdx[i] : i));
   if (rank == 0) {
-    const int cx = compactBits10(code), cy = compactBits10(code >> 1), cz = compactBits10(code >> 2);
-    const int lin = cx + g.nx * (cy + g.ny * cz);
+    const int lin = (int)cellOfRank[code];
     cellStart[lin] = (uint32_t)s + validCell;
     cellEnd[lin] = e;
   }
@@ -242,7 +246,7 @@ int ub200_celllist_create(ub200_celllist **out) {
 int ub200_celllist_destroy(ub200_celllist *cl) {
   if (!cl) return UB200_OK;
   DevBuf *bufs[] = {&cl->sortPos, &cl->groupIndex, &cl->cellStart, &cl->cellEnd, &cl->binCount,
-                    &cl->binStart, &cl->blockSums, &cl->codeSlot, &cl->unstable, &cl->errorFlag, &cl->ljTable.dev};
+                    &cl->binStart, &cl->blockSums, &cl->codeSlot, &cl->unstable, &cl->errorFlag, &cl->ljTable.dev, &cl->cellRank, &cl->cellOfRank};
   for (DevBuf *b : bufs) b->release();
   delete cl;
   return UB200_OK;
@@ -265,23 +269,62 @@ int ub200_celllist_build_f32(ub200_celllist *cl, const void *d_pos, const int *d
 }
 
 // N: launch bound; nDev: optional device-side particle count (<= N); sortKey: optional order key inside a cell
+namespace ub200 {
+__global__ void __launch_bounds__(256) cellCodes(GridF g, int ncells, uint32_t *__restrict__ code, uint32_t *__restrict__ cell) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  code[c] = mortonCode(c % g.nx, (c / g.nx) % g.ny, c / (g.nx * g.ny));
+  cell[c] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(256) cellRanks(const uint32_t *__restrict__ cellOfRank, int ncells, uint32_t *__restrict__ rank) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < ncells) rank[cellOfRank[r]] = (uint32_t)r;
+}
+// rank tables of a grid shape (Sorter::MortonHash order of the cells, utils/ParticleSorter.cuh:51-76); runs when the shape
+// changes, not per build
+static int buildCellRanks(ub200_celllist *cl, const GridF &g, int ncells, cudaStream_t st) {
+  int rc;
+  if ((rc = cl->cellRank.reserve(sizeof(uint32_t) * (size_t)ncells)) || (rc = cl->cellOfRank.reserve(sizeof(uint32_t) * (size_t)ncells)))
+    return rc;
+  DevBuf codeIn, codeOut, cellIn, temp;
+  if ((rc = codeIn.reserve(sizeof(uint32_t) * (size_t)ncells)) || (rc = codeOut.reserve(sizeof(uint32_t) * (size_t)ncells)) ||
+      (rc = cellIn.reserve(sizeof(uint32_t) * (size_t)ncells)))
+    return rc;
+  cellCodes<<<(ncells + 255) / 256, 256, 0, st>>>(g, ncells, codeIn.as<uint32_t>(), cellIn.as<uint32_t>());
+  UB200_LAUNCHED();
+  size_t bytes = 0;
+  UB200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, codeIn.as<uint32_t>(), codeOut.as<uint32_t>(), cellIn.as<uint32_t>(),
+                                             cl->cellOfRank.as<uint32_t>(), ncells, 0, 30, st));
+  if ((rc = temp.reserve(bytes ? bytes : 16))) return rc;
+  UB200_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, bytes, codeIn.as<uint32_t>(), codeOut.as<uint32_t>(), cellIn.as<uint32_t>(),
+                                             cl->cellOfRank.as<uint32_t>(), ncells, 0, 30, st));
+  cellRanks<<<(ncells + 255) / 256, 256, 0, st>>>(cl->cellOfRank.as<uint32_t>(), ncells, cl->cellRank.as<uint32_t>());
+  UB200_LAUNCHED();
+  UB200_CUDA(cudaStreamSynchronize(st)); // the scratch buffers go out of scope
+  codeIn.release(); codeOut.release(); cellIn.release(); temp.release();
+  return UB200_OK;
+}
+} // namespace ub200
+
 int ub200::celllistBuildEx(ub200_celllist *cl, const void *d_pos, const int *d_groupIdx, int N, const int *nDev, const int *sortKey,
                            const float L[3], const int periodic[3], const int cellDim[3], void *stream) {
   if (!cl || !d_pos || N <= 0 || !L || !periodic || !cellDim) return UB200_ERR_INVALID_ARGUMENT;
   for (int d = 0; d < 3; d++)
     if (cellDim[d] < 1 || cellDim[d] > 1024) return UB200_ERR_INVALID_ARGUMENT; // 10 bit Morton fields
   cudaStream_t st = (cudaStream_t)stream;
-  const GridF g = makeGridF(L, periodic, cellDim);
-  const int ncells = g.nx * g.ny * g.nz;
-  // ParticleSorter::updateOrderByCellHash: maxHash = hash(cellDim-1), sort bits [0, 32-clz(maxHash))
-  const uint32_t maxHash = mortonCode(g.nx - 1, g.ny - 1, g.nz - 1);
-  const int maxbit = highestBit(maxHash);
-  if (maxbit > 24) return UB200_ERR_GRID_TOO_LARGE;
-  const int nbins = 1 << maxbit;
-  const int ntiles = (nbins + kScanTile - 1) / kScanTile;
-  if (ntiles > 4096) return UB200_ERR_GRID_TOO_LARGE;
+  GridF g = makeGridF(L, periodic, cellDim);
+  const long long ncellsLong = (long long)g.nx * g.ny * g.nz;
+  // one bin per cell; the two-level scan covers 4096 tiles of 4096 bins
+  if (ncellsLong > (long long)kScanTile * 4096) return UB200_ERR_GRID_TOO_LARGE;
+  const int ncells = (int)ncellsLong;
+  const int nbins = ncells;
 
   int rc;
+  if (cl->rankDims[0] != g.nx || cl->rankDims[1] != g.ny || cl->rankDims[2] != g.nz || !cl->cellRank.p) {
+    if ((rc = buildCellRanks(cl, g, ncells, st))) return rc;
+    cl->rankDims[0] = g.nx; cl->rankDims[1] = g.ny; cl->rankDims[2] = g.nz;
+  }
+  g.rank = cl->cellRank.as<uint32_t>();
   if ((rc = cl->sortPos.reserve(sizeof(float4) * (size_t)N))) return rc;
   if ((rc = cl->groupIndex.reserve(sizeof(int) * (size_t)N))) return rc;
   if ((rc = cl->codeSlot.reserve(sizeof(uint2) * (size_t)N))) return rc;
@@ -337,7 +380,8 @@ int ub200::celllistBuildEx(ub200_celllist *cl, const void *d_pos, const int *d_g
   orderAndGather<<<nb, 256, 0, st>>>(cl->unstable.as<int>(), cl->codeSlot.as<uint2>(), cl->binStart.as<uint32_t>(),
                                      (const float4 *)d_pos, d_groupIdx, N, g, cl->validCell,
                                      cl->sortPos.as<float4>(), cl->groupIndex.as<int>(),
-                                     cl->cellStart.as<uint32_t>(), cl->cellEnd.as<int>(), nDev, sortKey);
+                                     cl->cellStart.as<uint32_t>(), cl->cellEnd.as<int>(), cl->cellOfRank.as<uint32_t>(), nDev,
+                                     sortKey);
   UB200_LAUNCHED();
   cl->built = 1;
   return UB200_OK;

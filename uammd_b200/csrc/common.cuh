@@ -67,6 +67,9 @@ struct GridF {
   float ix, iy, iz; // invCellSize
   float csx, csy, csz; // cellSize
   int nx, ny, nz;
+  // cell list grids: rank[linear cell] = position of the cell in Morton order (the bin of its particles); filled by the
+  // cell list build, null elsewhere
+  const uint32_t *rank;
 };
 
 inline GridF makeGridF(const float L[3], const int periodic[3], const int cellDim[3]) {
@@ -89,6 +92,7 @@ inline GridF makeGridF(const float L[3], const int periodic[3], const int cellDi
   g.ix = inv[0]; g.iy = inv[1]; g.iz = inv[2];
   g.csx = csz[0]; g.csy = csz[1]; g.csz = csz[2];
   g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+  g.rank = nullptr;
   return g;
 }
 
@@ -117,6 +121,12 @@ __host__ __device__ __forceinline__ uint32_t spreadBits10(uint32_t v) {
 }
 __host__ __device__ __forceinline__ uint32_t mortonCode(int cx, int cy, int cz) {
   return spreadBits10((uint32_t)cx) | (spreadBits10((uint32_t)cy) << 1) | (spreadBits10((uint32_t)cz) << 2);
+}
+// Bin of cell (cx, cy, cz) of a built cell list: the rank of its Morton code among the cells of the grid. Particles sorted
+// by bin are sorted by Morton hash (ParticleSorter.cuh:102-111) while the bin table has exactly one entry per cell,
+// whatever the shape of the grid.
+__device__ __forceinline__ uint32_t cellBin(const GridF &g, int cx, int cy, int cz) {
+  return __ldg(g.rank + (cx + g.nx * (cy + g.ny * cz)));
 }
 __host__ __device__ __forceinline__ uint32_t compactBits10(uint32_t x) {
   x &= 0x9249249u;
@@ -180,7 +190,7 @@ struct ub200_celllist {
   ub200::GridF grid;
   int N = 0;
   int ncells = 0;
-  int nbins = 0;       // 2^maxbit Morton codes
+  int nbins = 0;       // = ncells: one bin per cell, in Morton order
   int built = 0;
   uint32_t validCell = 0; // VALID_CELL epoch (CellListBase.cuh:210-230)
   int validCounter = -1;
@@ -191,6 +201,8 @@ struct ub200_celllist {
   ub200::DevBuf codeSlot;                                // per particle {code, slot}
   ub200::DevBuf unstable;                                // scatter target before the stable fix-up
   ub200::DevBuf errorFlag;
+  ub200::DevBuf cellRank, cellOfRank;                    // uint32[ncells]: linear cell -> Morton rank and back (per grid shape)
+  int rankDims[3] = {0, 0, 0};
   size_t cellStartCells = 0;
   ub200::LJTableCache ljTable;                           // parameter table of the LJ traversals over this list (per handle:
                                                          // two interactors never share or re-upload each other's table)

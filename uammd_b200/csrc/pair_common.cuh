@@ -36,7 +36,7 @@ __device__ __forceinline__ NeighbourCells describeNeighbours(const GridF &g, int
     if (jz < 0) { if (g.mz != 0.0f) jz += g.nz; else valid = false; }
     else if (jz >= g.nz) { if (g.mz != 0.0f) jz -= g.nz; else valid = false; }
     if (valid) {
-      const uint32_t code = mortonCode(jx, jy, jz);
+      const uint32_t code = cellBin(g, jx, jy, jz);
       const uint32_t s = __ldg(binStart + code), e = __ldg(binStart + code + 1);
       nc.start = (int)s;
       nc.count = (int)(e - s);

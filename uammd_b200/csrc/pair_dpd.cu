@@ -341,7 +341,7 @@ dpdTileTraversal(const float4 *__restrict__ sortPos, const int *__restrict__ gro
     else if (jz >= g.nz) { if (g.mz != 0.0f && jz == g.nz) jz = 0; else valid = false; }
     int s = 0, cnt = 0;
     if (valid) {
-      const uint32_t code = mortonCode(jx, jy, jz);
+      const uint32_t code = cellBin(g, jx, jy, jz);
       s = (int)__ldg(binStart + code);
       cnt = (int)__ldg(binStart + code + 1) - s;
     }
