@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | grep -v "^\[W" | tail -8 > gpurun_out/r02z_pytest_gpu.log; tail -6 gpurun_out/r02z_pytest_gpu.log
+timeout 300 scripts/_bin/fft_vs_cufft 20 > gpurun_out/r02z_fft_vs_cufft.jsonl 2> gpurun_out/r02z_fft_vs_cufft.err; cat gpurun_out/r02z_fft_vs_cufft.jsonl; tail -2 gpurun_out/r02z_fft_vs_cufft.err
