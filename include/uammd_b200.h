@@ -236,6 +236,38 @@ int ub200_brick_profile(ub200_brick *b, double phases[5]);
 int ub200_brick_counts(ub200_brick *b, void *stream, int *nOwned, int *nLocal, int *errorFlag);
 
 /* ------------------------------------------------------------------------------------------------
+ * Path 3: spectral Ewald Poisson solver for Gaussian charges in a triply periodic box. Replaces
+ * Poisson (Interactor/SpectralEwaldPoisson.cuh:84-184, SpectralEwaldPoisson.cu:74-580): same parameter resolution (grid
+ * spacing from the tolerance, FFT-friendly grid, Gaussian support, near-field cut-off and table sizes), far field through
+ * spread -> FFT -> (-ik, 1) rho / (eps k^2) -> inverse FFT -> interpolation, near field (split > 0) as the reference's three
+ * Transversers over a cell list with its two tabulated Green's functions. Precision = the reference's `real` (4 | 8).
+ * The reference's Parameters::cells and ::support are accepted but, like there, not used by the constructor.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_poisson ub200_poisson;
+typedef struct {
+  double L[3];
+  double epsilon;     /* permittivity */
+  double tolerance;   /* default 1e-5 */
+  double gw;          /* Gaussian width of the sources */
+  double split;       /* Ewald splitting parameter; <= 0: no splitting (far field only) */
+  double upsampling;  /* > 0: grid spacing = 1 / upsampling; <= 0: from the tolerance */
+} ub200_poisson_params;
+typedef struct {
+  int cells[3], support, nTable;
+  double h, farFieldGaussianWidth, nearFieldCutOff;
+} ub200_poisson_info_t;
+int ub200_poisson_create(ub200_poisson **out, int precisionBytes, const ub200_poisson_params *par);
+int ub200_poisson_destroy(ub200_poisson *p);
+int ub200_poisson_info(ub200_poisson *p, ub200_poisson_info_t *info);
+/* Poisson::sum (SpectralEwaldPoisson.cuh:110-122): d_force4 (real4[N], may be NULL) += q E, d_energy (real[N], may be NULL)
+ * += q phi; positions real4[N], charges real[N]. */
+int ub200_poisson_sum(ub200_poisson *p, const void *d_pos, const void *d_charge, int N, void *d_force4, void *d_energy,
+                      void *stream);
+/* Poisson::computeFieldPotentialAtParticles (:124-135): (Ex, Ey, Ez, phi) ADDED to d_fieldPotential4 (real4[N]). */
+int ub200_poisson_field_potential(ub200_poisson *p, const void *d_pos, const void *d_charge, int N, void *d_fieldPotential4,
+                                  void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Path 1d: Verlet (skin) list. Replaces VerletList::update (Interactor/NeighbourList/VerletList.cuh:111-124) and
  * the classes beneath it (VerletList/VerletListBase.cuh:73-199, BasicList/BasicListBase.cuh:76-215): rebuild when
  * a particle moved >= (multiplier - 1) cutOff / 2 since the last rebuild (host-synchronous flag read, like

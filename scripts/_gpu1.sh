@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 300 scripts/_bin/fft_vs_cufft 20 > gpurun_out/r02z_fft_vs_cufft.jsonl 2> gpurun_out/r02z_fft_vs_cufft.err; cat gpurun_out/r02z_fft_vs_cufft.jsonl; tail -2 gpurun_out/r02z_fft_vs_cufft.err
+timeout 900 python -m pytest tests/test_poisson_gpu.py -q -x 2>&1 | grep -v "^\[W" | tail -30

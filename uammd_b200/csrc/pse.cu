@@ -370,6 +370,8 @@ inline int nextFFTWiseSize(int n) {
   return best >= (1LL << 31) ? -1 : (int)best;
 }
 
+int nextFFTWiseSizeOf(int n) { return nextFFTWiseSize(n); } // for poisson.cu
+
 // RPYPSE_near::FandG (PSE/RPY_PSE.cuh:45-128): host, double precision
 inline void rpyNearFG(double r, double rh, double psi, double rcut, double &F, double &G) {
   if (r >= rcut) { F = G = 0; return; }
