@@ -263,6 +263,10 @@ int ub200_poisson_info(ub200_poisson *p, ub200_poisson_info_t *info);
  * += q phi; positions real4[N], charges real[N]. */
 int ub200_poisson_sum(ub200_poisson *p, const void *d_pos, const void *d_charge, int N, void *d_force4, void *d_energy,
                       void *stream);
+/* The reference's exact call pattern: its far field interpolates into the force AND the energy array on every sum() whatever
+ * was requested (SpectralEwaldPoisson.cu:561-578), the near field follows the requested computables (:368-410). */
+int ub200_poisson_sum_ex(ub200_poisson *p, const void *d_pos, const void *d_charge, int N, void *d_force4, void *d_energy,
+                         int nearFieldForce, int nearFieldEnergy, void *stream);
 /* Poisson::computeFieldPotentialAtParticles (:124-135): (Ex, Ey, Ez, phi) ADDED to d_fieldPotential4 (real4[N]). */
 int ub200_poisson_field_potential(ub200_poisson *p, const void *d_pos, const void *d_charge, int N, void *d_fieldPotential4,
                                   void *stream);

@@ -1030,6 +1030,71 @@ public:
   }
 };
 
+/* ---------------------------------------------------------------- Poisson (SpectralEwaldPoisson) ------------ */
+/* Interactor = Poisson (Interactor/SpectralEwaldPoisson.cuh:84-184): same Parameters fields, sum(Computables) adds q E to the
+   forces and q phi to the energies of the group's particles (charges from pd->getCharge), computeFieldPotentialAtParticles()
+   returns (Ex, Ey, Ez, phi). Like the reference it works on the whole ParticleData (positions by particle index). */
+class Poisson : public Interactor {
+  ub200_poisson *handle = nullptr;
+
+public:
+  struct Parameters {
+    real upsampling = -1.0;
+    int3 cells = make_int3(-1, -1, -1); /* accepted and, like in the reference's constructor, not used */
+    Box box;
+    real epsilon = -1;
+    real tolerance = 1e-5;
+    real gw = -1;
+    int support = -1;                   /* idem */
+    real split = -1;
+  };
+  Poisson(shared_ptr<ParticleData> pd, Parameters par) : Poisson(std::make_shared<ParticleGroup>(pd, "All"), par) {}
+  Poisson(shared_ptr<ParticleGroup> pg, Parameters par) : Interactor(pg, "b200::Poisson") {
+    ub200_poisson_params p;
+    p.L[0] = par.box.boxSize.x; p.L[1] = par.box.boxSize.y; p.L[2] = par.box.boxSize.z;
+    p.epsilon = par.epsilon; p.tolerance = par.tolerance; p.gw = par.gw; p.split = par.split; p.upsampling = par.upsampling;
+    const int rc = ub200_poisson_create(&handle, (int)sizeof(real), &p);
+    if (rc == UB200_ERR_UNSUPPORTED) throw std::invalid_argument("[Poisson] Kernel support is too large");
+    if (rc == UB200_ERR_INVALID_ARGUMENT) throw std::invalid_argument("[Poisson] Near field cut off is too large");
+    check(rc, "poisson_create");
+    ub200_poisson_info_t info;
+    check(ub200_poisson_info(handle, &info), "poisson_info");
+    System::log<System::MESSAGE>("[b200::Poisson] cells %d %d %d, support %d, near field cut off %g", info.cells[0], info.cells[1],
+                                 info.cells[2], info.support, info.nearFieldCutOff);
+  }
+  Poisson(const Poisson &) = delete;
+  ~Poisson() { ub200_poisson_destroy(handle); }
+
+  void sum(Computables comp, cudaStream_t st = 0) override {
+    if (comp.virial) {
+      System::log<System::EXCEPTION>("[Poisson] Virial functionality not implemented.");
+      throw std::runtime_error("[Poisson] not implemented");
+    }
+    const int N = pg->getNumberParticles();
+    auto pos = pd->getPos(access::location::gpu, access::mode::read);
+    auto charge = pd->getCharge(access::location::gpu, access::mode::read);
+    real4 *force = nullptr;
+    real *energy = nullptr;
+    // the reference's far field interpolates into BOTH arrays on every call (SpectralEwaldPoisson.cu:561-578)
+    auto f = pd->getForce(access::location::gpu, access::mode::readwrite);
+    auto e = pd->getEnergy(access::location::gpu, access::mode::readwrite);
+    force = f.raw();
+    energy = e.raw();
+    check(ub200_poisson_sum_ex(handle, pos.raw(), charge.raw(), N, force, energy, comp.force, comp.energy, (void *)st), "poisson_sum");
+  }
+  thrust::device_vector<real4> computeFieldPotentialAtParticles() {
+    const int N = pg->getNumberParticles();
+    thrust::device_vector<real4> out(N);
+    thrust::fill(out.begin(), out.end(), real4());
+    auto pos = pd->getPos(access::location::gpu, access::mode::read);
+    auto charge = pd->getCharge(access::location::gpu, access::mode::read);
+    check(ub200_poisson_field_potential(handle, pos.raw(), charge.raw(), N, thrust::raw_pointer_cast(out.data()), nullptr),
+          "poisson_field_potential");
+    CudaSafeCall(cudaDeviceSynchronize());
+    return out;
+  }
+};
+
 #ifndef DOUBLE_PRECISION
 /* ---------------------------------------------------------------- VerletNVT::{GronbechJensen, Basic} -------- */
 /* Integrator (Integrator/VerletNVT.cuh:100-117, VerletNVT/Basic.cu:31-77, VerletNVT/GronbechJensen.cu:96-127): the

@@ -47,6 +47,17 @@ def test_langevin_verlet_dropin_matches_reference():
     assert r["lj_max_dpos"] < 1e-4 and r["lj_max_dvel"] < 1e-2   # with the LJ forces: fp32 summation order only
 
 
+def test_poisson_dropin_matches_reference():
+    """b200::Poisson next to the unmodified reference Poisson (double precision): the reference test's analytic known answer
+    for both, then forces / energies / field / potential of a neutral cloud of 2000 charges against each other."""
+    r = _run("dropin_poisson", 2000)
+    print(r)
+    assert r["kat_reference"] < 1e-3 and r["kat_ours"] < 1e-3 and r["kat_field_ours"] < 1e-3   # test_poisson.cu:206,217
+    # same algorithm, same tables; the FFTs differ (hand written vs cuFFT) and so does the order of the atomic spreading
+    assert r["force_vs_ref"] < 1e-9 and r["energy_vs_ref"] < 1e-9
+    assert r["field_vs_ref"] < 1e-9 and r["potential_vs_ref"] < 1e-9
+
+
 def test_fcm_dropin_matches_reference():
     r = _run("dropin_fcm", 20000, 64)
     print(r)

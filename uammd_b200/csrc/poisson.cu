@@ -388,16 +388,19 @@ template <class T> struct PoissonState {
 
   // Poisson::sum (SpectralEwaldPoisson.cuh:110-122): far field always (it interpolates forces AND energies into whichever
   // array is given), near field per requested computable
-  int sum(const void *pos, const void *charge, int N, void *force4, void *energy, cudaStream_t st) {
+  int sum(const void *pos, const void *charge, int N, void *force4, void *energy, bool nearForce, bool nearEnergy,
+          cudaStream_t st) {
     int rc;
     if ((rc = farField(pos, charge, N, energy != nullptr, st))) return rc;
     poissonCombine<T4, T><<<(N + 255) / 256, 256, 0, st>>>(Eout.as<T>(), energy ? Pout.as<T>() : nullptr, (const T *)charge, N,
                                                             (T4 *)force4, (T *)energy, (T4 *)nullptr);
     UB200_LAUNCHED();
-    if (split > 0 && (force4 || energy)) {
+    nearForce = nearForce && force4;
+    nearEnergy = nearEnergy && energy;
+    if (split > 0 && (nearForce || nearEnergy)) {
       if ((rc = nearPrepare(pos, charge, N, st))) return rc;
-      if (force4 && (rc = nearLaunch<0>((T4 *)force4, nullptr, st))) return rc;
-      if (energy && (rc = nearLaunch<1>(nullptr, (T *)energy, st))) return rc;
+      if (nearForce && (rc = nearLaunch<0>((T4 *)force4, nullptr, st))) return rc;
+      if (nearEnergy && (rc = nearLaunch<1>(nullptr, (T *)energy, st))) return rc;
     }
     return UB200_OK;
   }
@@ -454,11 +457,16 @@ int ub200_poisson_info(ub200_poisson *h, ub200_poisson_info_t *info) {
 #undef UB200_PINFO
   return UB200_OK;
 }
+int ub200_poisson_sum_ex(ub200_poisson *h, const void *d_pos, const void *d_charge, int N, void *d_force4, void *d_energy,
+                         int nearFieldForce, int nearFieldEnergy, void *stream) {
+  if (!h || !d_pos || !d_charge || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4
+             ? h->f.sum(d_pos, d_charge, N, d_force4, d_energy, nearFieldForce != 0, nearFieldEnergy != 0, (cudaStream_t)stream)
+             : h->d.sum(d_pos, d_charge, N, d_force4, d_energy, nearFieldForce != 0, nearFieldEnergy != 0, (cudaStream_t)stream);
+}
 int ub200_poisson_sum(ub200_poisson *h, const void *d_pos, const void *d_charge, int N, void *d_force4, void *d_energy,
                       void *stream) {
-  if (!h || !d_pos || !d_charge || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
-  return h->precision == 4 ? h->f.sum(d_pos, d_charge, N, d_force4, d_energy, (cudaStream_t)stream)
-                           : h->d.sum(d_pos, d_charge, N, d_force4, d_energy, (cudaStream_t)stream);
+  return ub200_poisson_sum_ex(h, d_pos, d_charge, N, d_force4, d_energy, 1, 1, stream);
 }
 int ub200_poisson_field_potential(ub200_poisson *h, const void *d_pos, const void *d_charge, int N, void *d_fieldPotential4,
                                   void *stream) {
