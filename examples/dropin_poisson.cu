@@ -103,9 +103,40 @@ int main(int argc, char **argv) {
       sPhi = std::max(sPhi, (double)std::abs(a.fp[i].w));
     }
   }
-  printf("{\"N\":%d,\"kat_reference\":%.3e,\"kat_ours\":%.3e,\"kat_field_ours\":%.3e,\"force_vs_ref\":%.3e,\"energy_vs_ref\":%.3e,"
+  // ---- 3. timing of sum(force + energy) on a larger neutral cloud (argv[2] charges at number density 0.1, 0 skips it)
+  const int Nt = argc > 2 ? atoi(argv[2]) : 0;
+  double msRef = 0, msOurs = 0;
+  if (Nt > 0) {
+    const real L = std::cbrt(Nt / 0.1), tol = 1e-4, gw = 0.25, split = 1.0, eps = 1.0;
+    std::mt19937_64 gen(11);
+    std::uniform_real_distribution<double> U(-0.5, 0.5);
+    auto pd = std::make_shared<ParticleData>(Nt, sys);
+    {
+      auto p = pd->getPos(access::location::cpu, access::mode::write);
+      auto c = pd->getCharge(access::location::cpu, access::mode::write);
+      for (int i = 0; i < Nt; i++) { p[i] = make_real4(U(gen) * L, U(gen) * L, U(gen) * L, 0); c[i] = (i % 2) ? 1.0 : -1.0; }
+    }
+    auto timeIt = [&](auto poisson) {
+      for (int w = 0; w < 2; w++) poisson->sum({.force = true, .energy = true, .virial = false}, 0);
+      CudaSafeCall(cudaDeviceSynchronize());
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0, 0);
+      for (int w = 0; w < 10; w++) poisson->sum({.force = true, .energy = true, .virial = false}, 0);
+      cudaEventRecord(e1, 0);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      return (double)ms / 10;
+    };
+    Poisson::Parameters pa; fill<Poisson>(pa, L, tol, gw, split, eps);
+    b200::Poisson::Parameters pb; fill<b200::Poisson>(pb, L, tol, gw, split, eps);
+    msRef = timeIt(std::make_shared<Poisson>(pd, pa));
+    msOurs = timeIt(std::make_shared<b200::Poisson>(pd, pb));
+  }
+  printf("{\"N\":%d,\"timing_N\":%d,\"sum_ms_reference\":%.4f,\"sum_ms_ours\":%.4f,\"kat_reference\":%.3e,\"kat_ours\":%.3e,\"kat_field_ours\":%.3e,\"force_vs_ref\":%.3e,\"energy_vs_ref\":%.3e,"
          "\"field_vs_ref\":%.3e,\"potential_vs_ref\":%.3e}\n",
-         N, katRef, katOurs, katFieldOurs, dForce / sF, dEnergy / sE, dField / sFld, dPhi / sPhi);
+         N, Nt, msRef, msOurs, katRef, katOurs, katFieldOurs, dForce / sF, dEnergy / sE, dField / sFld, dPhi / sPhi);
   sys->finish();
   return 0;
 }

@@ -172,37 +172,50 @@ __global__ void __launch_bounds__(kPairThreads)
 poissonNearTraversal(const T4 *__restrict__ sortedPQ, const int *__restrict__ groupIndex, const uint32_t *__restrict__ binStart,
                      GridF g, int ncells, ScalarTable<T> tabG, ScalarTable<T> tabF, PoissonBox<T> box, T4 *__restrict__ out4,
                      T *__restrict__ out1) {
+  constexpr int kStage = 512; // candidate slots of the 27 cells listed flat per warp (denser neighbourhoods walk cell by cell)
+  __shared__ int candAll[kPairWarps][kStage];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int *cand = candAll[warp];
   const int warpsTotal = gridDim.x * kPairWarps;
   for (int cell = blockIdx.x * kPairWarps + warp; cell < ncells; cell += warpsTotal) {
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
     const NeighbourCells nc = describeNeighbours(g, cx, cy, cz, binStart, lane);
     const int hStart = __shfl_sync(0xffffffffu, nc.start, nc.centre);
     const int hCount = __shfl_sync(0xffffffffu, nc.count, nc.centre);
+    if (hCount == 0) continue;
+    const bool flat = nc.total <= kStage;
+    __syncwarp();
+    if (flat)
+      for (int t = 0; t < nc.count; t++) cand[nc.off + t] = nc.start + t; // lane = neighbour cell: a few entries each
+    __syncwarp();
     for (int h = 0; h < hCount; h++) {
       const T4 pi = sortedPQ[hStart + h];
       T ax = T(0), ay = T(0), az = T(0), aw = T(0);
-      for (int c = 0; c < 27; c++) {
-        const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
-        const int st = __shfl_sync(0xffffffffu, nc.start, c);
-        for (int t = lane; t < cnt; t += 32) {
-          const T4 pj = sortedPQ[st + t];
-          // Box::apply_pbc (utils/Box.cuh:51-58)
-          T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-          dx += floor(dx * box.mx + T(0.5)) * box.Lx;
-          dy += floor(dy * box.my + T(0.5)) * box.Ly;
-          dz += floor(dz * box.mz + T(0.5)) * box.Lz;
-          const T r2 = dx * dx + dy * dy + dz * dz;
-          if (MODE == 1) {
-            aw += pi.w * pj.w * tableValue(tabG, r2);
-          } else {
-            if (MODE == 2) aw += pj.w * tableValue(tabG, r2);
-            if (r2 > T(0)) {
-              const T r = sqrt(r2);
-              const T fmod = (MODE == 0 ? -pi.w * pj.w : -pj.w) * tableValue(tabF, r);
-              ax += fmod * dx / r; ay += fmod * dy / r; az += fmod * dz / r;
-            }
+      auto pair = [&](const T4 pj) {
+        // Box::apply_pbc (utils/Box.cuh:51-58)
+        T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+        dx += floor(dx * box.mx + T(0.5)) * box.Lx;
+        dy += floor(dy * box.my + T(0.5)) * box.Ly;
+        dz += floor(dz * box.mz + T(0.5)) * box.Lz;
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        if (MODE == 1) {
+          aw += pi.w * pj.w * tableValue(tabG, r2);
+        } else {
+          if (MODE == 2) aw += pj.w * tableValue(tabG, r2);
+          if (r2 > T(0)) {
+            const T r = sqrt(r2);
+            const T fmod = (MODE == 0 ? -pi.w * pj.w : -pj.w) * tableValue(tabF, r);
+            ax += fmod * dx / r; ay += fmod * dy / r; az += fmod * dz / r;
           }
+        }
+      };
+      if (flat) {
+        for (int t = lane; t < nc.total; t += 32) pair(sortedPQ[cand[t]]);
+      } else {
+        for (int c = 0; c < 27; c++) {
+          const int cnt = __shfl_sync(0xffffffffu, nc.count, c);
+          const int st = __shfl_sync(0xffffffffu, nc.start, c);
+          for (int t = lane; t < cnt; t += 32) pair(sortedPQ[st + t]);
         }
       }
 #pragma unroll
