@@ -132,7 +132,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "MD steps/s @1e6 LJ particles", "value": val, "unit": "steps/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
                    "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
                    },
@@ -319,7 +319,7 @@ def main():
         line = {
             "metric": "MD steps/s @1e6 LJ particles", "value": world * 1000.0 / ms_per_step, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"PairForces<LJ,CellList> + VerletNVE, N={N}, rho={RHO}, rc={RC}, dt={DT}, FCC start T={TEMP}",
                        "l2": "flushed before every step (256 MiB write)", "equilibration_steps": args.equil,
                        },
