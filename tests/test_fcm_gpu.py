@@ -20,7 +20,7 @@ REF_FCM = os.path.join(ROOT, "oracle", "_ref", "ref_fcm")
 
 # ---------------- FFT ----------------
 @pytest.mark.parametrize("shape", [(16, 16, 16), (128, 128, 128), (24, 20, 18), (30, 14, 6), (9, 15, 7), (64, 32, 4),
-                                   (96, 96, 96), (22, 44, 66), (256, 64, 512), (360, 8, 8)])
+                                   (96, 96, 96), (22, 44, 66), (256, 64, 512), (360, 8, 8), (250, 50, 25)])
 def test_fft3d_matches_numpy_f64(cuda, shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(nx * 7 + ny)

@@ -117,7 +117,28 @@ __device__ __forceinline__ void stockhamStage(const typename Vec2<T>::type *__re
       dst[0] = cadd(v0, t);
       dst[Ns] = cadd(m1, d);
       dst[2 * Ns] = csub(m1, d);
-    } else { // generic small radix (5, 7, 11): direct DFT with roots taken from the twiddle table
+    } else if (R == 5) { // 5-point butterfly with the two cosines / sines of 2 pi / 5 (Rader-free, 8 real products per part)
+      C v0 = src[j], v1 = src[j + nb], v2 = src[j + 2 * nb], v3 = src[j + 3 * nb], v4 = src[j + 4 * nb];
+      if (Ns > 1) {
+        const int t1 = k * twStep;
+        v1 = cmul(v1, twid(t1));
+        v2 = cmul(v2, twid(2 * t1));
+        v3 = cmul(v3, twid(3 * t1));
+        v4 = cmul(v4, twid(4 * t1));
+      }
+      const T c1 = T(0.30901699437494742410229341718282), c2 = T(-0.80901699437494742410229341718282);
+      const T s1 = T(0.95105651629515357211643933337938), s2 = T(0.58778525229247312916870595463907);
+      const C t1 = cadd(v1, v4), t2 = cadd(v2, v3), t3 = csub(v1, v4), t4 = csub(v2, v3);
+      const C a1 = mk2<T>(v0.x + c1 * t1.x + c2 * t2.x, v0.y + c1 * t1.y + c2 * t2.y);
+      const C a2 = mk2<T>(v0.x + c2 * t1.x + c1 * t2.x, v0.y + c2 * t1.y + c1 * t2.y);
+      const C b1 = mulI<DIR>(mk2<T>(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+      const C b2 = mulI<DIR>(mk2<T>(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+      dst[0] = cadd(v0, cadd(t1, t2));
+      dst[Ns] = cadd(a1, b1);
+      dst[2 * Ns] = cadd(a2, b2);
+      dst[3 * Ns] = csub(a2, b2);
+      dst[4 * Ns] = csub(a1, b1);
+    } else { // generic small radix (7, 11): direct DFT with roots taken from the twiddle table
       C v[11];
       for (int p = 0; p < R; p++) {
         v[p] = src[j + p * nb];
