@@ -138,17 +138,34 @@ __device__ __forceinline__ void stockhamStage(const typename Vec2<T>::type *__re
       dst[2 * Ns] = cadd(a2, b2);
       dst[3 * Ns] = csub(a2, b2);
       dst[4 * Ns] = csub(a1, b1);
-    } else { // generic small radix (7, 11): direct DFT with roots taken from the twiddle table
-      C v[11];
-      for (int p = 0; p < R; p++) {
-        v[p] = src[j + p * nb];
-        if (Ns > 1 && p > 0) v[p] = cmul(v[p], twid(p * k * twStep));
+    } else { // prime radix 7 / 11: the inputs p and R - p enter through their sum and difference, so that the outputs q and
+             // R - q share (R - 1) / 2 real-by-complex products each instead of R - 1 complex products
+      C v0 = src[j];
+      C tp[5], tm[5];
+      const int H = (R - 1) >> 1;
+      C sum = v0;
+      for (int p = 1; p <= H; p++) {
+        C x = src[j + p * nb], y = src[j + (R - p) * nb];
+        if (Ns > 1) {
+          x = cmul(x, twid(p * k * twStep));
+          y = cmul(y, twid((R - p) * k * twStep));
+        }
+        tp[p - 1] = cadd(x, y);
+        tm[p - 1] = csub(x, y);
+        sum = cadd(sum, tp[p - 1]);
       }
+      dst[0] = sum;
       const int rootStep = n / R;
-      for (int q = 0; q < R; q++) {
-        C acc = v[0];
-        for (int p = 1; p < R; p++) acc = cadd(acc, cmul(v[p], twid(((p * q) % R) * rootStep)));
-        dst[q * Ns] = acc;
+      for (int q = 1; q <= H; q++) {
+        C a = v0, bsum = mk2<T>(T(0), T(0));
+        for (int p = 1; p <= H; p++) {
+          const C w = tw[((p * q) % R) * rootStep]; // (cos, -sin)(2 pi p q / R)
+          a = mk2<T>(a.x + w.x * tp[p - 1].x, a.y + w.x * tp[p - 1].y);
+          bsum = mk2<T>(bsum.x - w.y * tm[p - 1].x, bsum.y - w.y * tm[p - 1].y);
+        }
+        const C bi = mulI<DIR>(bsum);
+        dst[q * Ns] = cadd(a, bi);
+        dst[(R - q) * Ns] = csub(a, bi);
       }
     }
   }
