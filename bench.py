@@ -149,7 +149,8 @@ def run_reference(args):
         import bench_extra as extra_bench
         for name, fn in (("verlet", lambda: extra_bench.verlet_reference(ROOT, N, Lb, pos, vel, RC, DT, equil=args.equil)),
                          ("pse", lambda: extra_bench.pse_reference(ROOT)), ("bd", lambda: extra_bench.bd_reference(ROOT)),
-                         ("langevin", lambda: extra_bench.langevin_reference(ROOT))):
+                         ("langevin", lambda: extra_bench.langevin_reference(ROOT)),
+                         ("poisson", lambda: extra_bench.poisson_reference(ROOT))):
             try:
                 line[name] = fn()
             except Exception as e:  # a secondary leg must not take the headline down
@@ -349,7 +350,8 @@ def main():
             import bench_extra as extra_bench
             for name, fn in (("verlet", lambda: extra_bench.verlet(dev, N, Lb, pos, vel, RC, DT, equil=args.equil)),
                              ("pse", lambda: extra_bench.pse(dev)), ("bd", lambda: extra_bench.bd_ideal(dev)),
-                             ("langevin", lambda: extra_bench.langevin(dev)), ("dpd", lambda: extra_bench.dpd(dev))):
+                             ("langevin", lambda: extra_bench.langevin(dev)), ("dpd", lambda: extra_bench.dpd(dev)),
+                             ("poisson", lambda: extra_bench.poisson(dev))):
                 try:
                     line[name] = fn()
                 except Exception as e:  # a secondary leg must not take the headline down

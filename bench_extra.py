@@ -194,6 +194,39 @@ def pse_reference(root, steps=20, warmup=3):
             "dtype": "f32", "what": "unmodified reference BDHI::PSE (cuFFT + cuBLAS Lanczos) on the same B200, same protocol"}
 
 
+POISSON_N, POISSON_RHO = 200_000, 0.1
+
+
+def poisson(dev, steps=10, warmup=2):
+    """SURVEY 8(f) rank 2: Poisson::sum (forces + energies) on 2e5 unit charges at number density 0.1, gw = 0.25, split = 1,
+    tolerance 1e-4, double precision - the workload examples/dropin_poisson.cu times for both implementations."""
+    from uammd_b200.poisson import Parameters, Poisson
+    N = POISSON_N
+    L = (N / POISSON_RHO) ** (1.0 / 3.0)
+    rng = np.random.default_rng(11)
+    pos = np.zeros((N, 4)); pos[:, :3] = (rng.random((N, 3)) - 0.5) * L
+    q = np.where(np.arange(N) % 2 == 1, 1.0, -1.0)
+    p, c = torch.from_numpy(pos).to(dev), torch.from_numpy(q).to(dev)
+    solver = Poisson(p, c, Parameters(L, epsilon=1.0, tolerance=1e-4, gw=0.25, split=1.0))
+    force, energy = torch.zeros(N, 4, dtype=torch.float64, device=dev), torch.zeros(N, dtype=torch.float64, device=dev)
+    ms = _timed(dev, lambda: solver.sum(force=force, energy=energy), steps, warmup)
+    inf = solver.info()
+    return {"metric": "Poisson sums/s @2e5 charges fp64", "value": 1000.0 / ms, "unit": "sums/s", "ms_per_step": ms,
+            "cells": list(inf.cells), "support": inf.support, "near_field_cut_off": inf.nearFieldCutOff,
+            "what": "Poisson::sum(force, energy), Ewald split 1.0, tolerance 1e-4, L2 flushed between calls"}
+
+
+def poisson_reference(root):
+    exe = os.path.join(root, "oracle", "_ref", "dropin_poisson")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/dropin_poisson was not built"}
+    out = subprocess.run([exe, "2000", str(POISSON_N)], check=True, capture_output=True, text=True, timeout=600).stdout
+    r = [json.loads(l) for l in out.splitlines() if l.startswith("{")][-1]
+    return {"metric": "Poisson sums/s @2e5 charges fp64", "value": 1000.0 / r["sum_ms_reference"], "unit": "sums/s",
+            "ms_per_step": r["sum_ms_reference"], "what": "unmodified reference Poisson::sum on the same B200, calls back to back; "
+            "the same binary also ran b200::Poisson: %.3f ms" % r["sum_ms_ours"]}
+
+
 def bd_ideal(dev, steps=200, warmup=10):
     from uammd_b200 import bd
     N = 100_000

@@ -75,5 +75,8 @@ int main(int argc, char **argv) {
   run(128, false, reps, scrub);
   run(256, false, reps, scrub);  // BASELINE config 3: PSE 256^3 fp32
   run(256, true, reps, scrub);
+  run(250, true, reps, scrub);   // 2 5^3: the grid the Poisson parameter resolution picks for 2e5 charges (generic radix path)
+  run(216, true, reps, scrub);   // 2^3 3^3
+  run(154, true, reps, scrub);   // 2 7 11
   return 0;
 }
