@@ -10,7 +10,8 @@ namespace ub200 {
 
 constexpr int kFftThreads = 256;
 
-template <class T> struct Fft3dPlan {
+// NC: interleaved components per grid node (3: the real3 grids of the hydrodynamic solvers; 1 and 4: the Poisson solver)
+template <class T, int NC = 3> struct Fft3dPlan {
   using C = typename Vec2<T>::type;
   int nx = 0, ny = 0, nz = 0, nkx = 0, nxPad = 0;
   FftAxis ax, ay, az;
@@ -38,19 +39,19 @@ template <class T> struct Fft3dPlan {
     // experiment knobs (environment): UB200_FFT_TILE = kx per strided tile (1, 2, 4), UB200_FFT_PAIRS = line pairs per x CTA
     const char *envTile = getenv("UB200_FFT_TILE"), *envPairs = getenv("UB200_FFT_PAIRS");
     const int maxTile = envTile ? atoi(envTile) : 4, maxPairs = envPairs ? std::min(atoi(envPairs), 4) : 4;
-    const int pairs = fit(nx, 3, maxPairs, 2);
+    const int pairs = fit(nx, NC, maxPairs, 2);
     linesPerCta = 2 * pairs;
-    smemX = 2 * (size_t)pairs * 3 * (nx + 1) * sizeof(C);
+    smemX = 2 * (size_t)pairs * NC * (nx + 1) * sizeof(C);
     auto pow2 = [](int v) { return v >= 4 ? 4 : (v >= 2 ? 2 : 1); };
-    tileY = pow2(fit(ny, 3, maxTile));
-    smemY = 3 * (size_t)tileY * 3 * (ny + 1) * sizeof(C);
-    tileZ = pow2(fit(nz, 3, maxTile));
-    smemZ = 3 * (size_t)tileZ * 3 * (nz + 1) * sizeof(C);
+    tileY = pow2(fit(ny, NC, maxTile));
+    smemY = 3 * (size_t)tileY * NC * (ny + 1) * sizeof(C);
+    tileZ = pow2(fit(nz, NC, maxTile));
+    smemZ = 3 * (size_t)tileZ * NC * (nz + 1) * sizeof(C);
     if (smemX > 200 * 1024 || smemY > 200 * 1024 || smemZ > 200 * 1024) return UB200_ERR_UNSUPPORTED;
     return UB200_OK;
   }
   void release() { twx.release(); twy.release(); twz.release(); }
-  size_t gridBytes() const { return (size_t)nz * ny * nkx * 3 * sizeof(C); }
+  size_t gridBytes() const { return (size_t)nz * ny * nkx * NC * sizeof(C); }
 
 private:
   static int upload(DevBuf &buf, int n) {
@@ -83,7 +84,7 @@ __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------- X pass: real <-> complex along the contiguous axis, in place ----------------
-template <class T, bool FORWARD, int NFIX>
+template <class T, bool FORWARD, int NFIX, int NC = 3>
 __global__ void __launch_bounds__(kFftThreads)
 fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int linesPerCta, FftAxis ax,
          const typename Vec2<T>::type *__restrict__ tw) {
@@ -92,12 +93,12 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int fstride = nx + 1;
   const int pairs = linesPerCta / 2;
-  const int nf = pairs * 3;
+  const int nf = pairs * NC;
   C *buf0 = reinterpret_cast<C *>(smemRaw);
   C *buf1 = buf0 + (size_t)nf * fstride;
   const int line0 = blockIdx.x * linesPerCta;
   const int nl = min(linesPerCta, nlines - line0);
-  const size_t lineReals = (size_t)2 * nkx * 3; // reals per line (padded) == 2 * complex per line
+  const size_t lineReals = (size_t)2 * nkx * NC; // reals per line (padded) == 2 * complex per line
   T *base = grid + (size_t)line0 * lineReals;
   C *cbase = reinterpret_cast<C *>(base);
   if (FORWARD) {
@@ -105,9 +106,9 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
     // (asynchronous copies: every load of the CTA's lines is in flight at once instead of one dependent load -> store
     //  round trip per element; measured 1.8 TB/s with plain loads)
     for (int l = 0; l < linesPerCta; l++)
-      for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
-        const int x = rem / 3, c = rem - 3 * x;
-        T *dst = reinterpret_cast<T *>(buf0 + ((l >> 1) * 3 + c) * fstride + x) + (l & 1);
+      for (int rem = threadIdx.x; rem < nx * NC; rem += blockDim.x) {
+        const int x = rem / NC, c = rem - NC * x;
+        T *dst = reinterpret_cast<T *>(buf0 + ((l >> 1) * NC + c) * fstride + x) + (l & 1);
         if (l < nl) cpAsyncReal(dst, base + (size_t)l * lineReals + rem);
         else *dst = T(0);
       }
@@ -117,34 +118,34 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
     C *res = fftShared<T, -1, NFIX>(buf0, buf1, ax, fstride, nf, tw);
     // untangle the two real transforms and store the Hermitian halves
     for (int p = 0; p < pairs; p++)
-    for (int rem = threadIdx.x; rem < nkx * 3; rem += blockDim.x) {
-      const int k = rem / 3, c = rem - 3 * k;
-      const C zk = res[(p * 3 + c) * fstride + k];
-      const C zn = res[(p * 3 + c) * fstride + (k == 0 ? 0 : nx - k)];
+    for (int rem = threadIdx.x; rem < nkx * NC; rem += blockDim.x) {
+      const int k = rem / NC, c = rem - NC * k;
+      const C zk = res[(p * NC + c) * fstride + k];
+      const C zn = res[(p * NC + c) * fstride + (k == 0 ? 0 : nx - k)];
       const C A = mk2<T>(T(0.5) * (zk.x + zn.x), T(0.5) * (zk.y - zn.y));
       const C B = mk2<T>(T(0.5) * (zk.y + zn.y), T(0.5) * (zn.x - zk.x));
-      if (2 * p < nl) cbase[(size_t)(2 * p) * nkx * 3 + rem] = A;
-      if (2 * p + 1 < nl) cbase[(size_t)(2 * p + 1) * nkx * 3 + rem] = B;
+      if (2 * p < nl) cbase[(size_t)(2 * p) * nkx * NC + rem] = A;
+      if (2 * p + 1 < nl) cbase[(size_t)(2 * p + 1) * nkx * NC + rem] = B;
     }
   } else {
     // build Z_k = A_k + i B_k for all k from the stored halves: every stored mode is loaded ONCE and also written to its
     // Hermitian mirror k' = nx - k (A_k' = conj A_k, B_k' = conj B_k); like a C2R transform, the imaginary parts of the
     // self-conjugate modes (k = 0, and k = nx/2 for even nx) are ignored
-    for (int rem = threadIdx.x; rem < nkx * 3; rem += blockDim.x) {
-      const int k = rem / 3, c = rem - 3 * k;
+    for (int rem = threadIdx.x; rem < nkx * NC; rem += blockDim.x) {
+      const int k = rem / NC, c = rem - NC * k;
       C A[4], B[4]; // pairs <= 4: all loads of this thread are issued back to back
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         A[p] = mk2<T>(T(0), T(0)); B[p] = A[p];
-        if (p < pairs && 2 * p < nl) A[p] = cbase[(size_t)(2 * p) * nkx * 3 + rem];
-        if (p < pairs && 2 * p + 1 < nl) B[p] = cbase[(size_t)(2 * p + 1) * nkx * 3 + rem];
+        if (p < pairs && 2 * p < nl) A[p] = cbase[(size_t)(2 * p) * nkx * NC + rem];
+        if (p < pairs && 2 * p + 1 < nl) B[p] = cbase[(size_t)(2 * p + 1) * nkx * NC + rem];
       }
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         if (p >= pairs) break;
         C a = A[p], b = B[p];
         if (k == 0 || 2 * k == nx) { a.y = T(0); b.y = T(0); }
-        C *row = buf0 + (p * 3 + c) * fstride;
+        C *row = buf0 + (p * NC + c) * fstride;
         row[k] = mk2<T>(a.x - b.y, a.y + b.x);
         if (k > 0 && 2 * k < nx) row[nx - k] = mk2<T>(a.x + b.y, b.x - a.y);
       }
@@ -152,9 +153,9 @@ fftPassX(T *__restrict__ grid, int nxRuntime, int nkxRuntime, int nlines, int li
     __syncthreads();
     C *res = fftShared<T, +1, NFIX>(buf0, buf1, ax, fstride, nf, tw);
     for (int l = 0; l < nl; l++)
-      for (int rem = threadIdx.x; rem < nx * 3; rem += blockDim.x) {
-        const int x = rem / 3, c = rem - 3 * x;
-        const T *src = reinterpret_cast<const T *>(res + ((l >> 1) * 3 + c) * fstride + x);
+      for (int rem = threadIdx.x; rem < nx * NC; rem += blockDim.x) {
+        const int x = rem / NC, c = rem - NC * x;
+        const T *src = reinterpret_cast<const T *>(res + ((l >> 1) * NC + c) * fstride + x);
         base[(size_t)l * lineReals + rem] = src[l & 1];
       }
   }
@@ -170,14 +171,15 @@ struct NoSpectralOp {
 
 // Address policies of the strided pass: where axis point i of tile (other, kx0) is loaded from / stored to.
 // In place (one GPU): the same grid for both.
-template <class C> struct AddrInPlace {
+template <class C, int NC = 3> struct AddrInPlace {
+  static constexpr int kComp = NC;
   C *grid;
-  size_t elemStride, otherStride; // in complex3 nodes
+  size_t elemStride, otherStride; // in nodes of NC complex numbers
   __device__ __forceinline__ const C *ld(int other, int i, int kx0) const {
-    return grid + ((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * 3;
+    return grid + ((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * NC;
   }
   __device__ __forceinline__ void store(int other, int i, int kx0, int gf, const C &v) const {
-    grid[((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * 3 + gf] = v;
+    grid[((size_t)other * otherStride + kx0 + (size_t)i * elemStride) * NC + gf] = v;
   }
 };
 // Slab-decomposed 3-D FFT over `world` GPUs (NVLink peer stores, no staging copy, no NCCL): rank r owns the z planes
@@ -187,6 +189,7 @@ template <class C> struct AddrInPlace {
 // local T and stores the inverse-transformed lines straight back into the owners' S buffers.
 constexpr int kFftMaxPeers = 8;
 template <class C> struct AddrSlabYForward { // axis = y, other = local z plane
+  static constexpr int kComp = 3;
   C *S;
   C *peerT[kFftMaxPeers];
   int ny, nyl, nkx, z0; // z0: first global plane of this rank
@@ -202,6 +205,7 @@ template <class C> struct AddrSlabYForward { // axis = y, other = local z plane
 // index halo): the boundary planes of a slab are ALSO stored into the neighbours' halo planes, so that the inverse y / x
 // passes and the interpolation of the neighbours never touch remote memory (and need no barrier of their own).
 template <class C> struct AddrSlabZFused { // axis = z, other = local ky row
+  static constexpr int kComp = 3;
   C *T;
   C *peerS[kFftMaxPeers];
   int ny, nyl, nkx, nzl, y0, halo, world; // y0: first global ky row of this rank
@@ -232,12 +236,14 @@ __global__ void __launch_bounds__(kFftThreads)
 fftPassStrided(Addr addr, int nRuntime, int nkx, int nOther, int tile, FftAxis ax,
                const typename Vec2<T>::type *__restrict__ tw, Op op) {
   using C = typename Vec2<T>::type;
+  constexpr int NC = Addr::kComp; // interleaved components per node
+  static_assert(MODE != 0 || NC == 3, "the fused spectral operators work on three components");
   const int n = NFIX > 0 ? NFIX : nRuntime;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int fstride = n + 1;
   const int ntx = (nkx + tile - 1) / tile;
   const int ntiles = ntx * nOther;
-  const int nf = tile * 3;
+  const int nf = tile * NC;
   C *const bufBase = reinterpret_cast<C *>(smemRaw);
   const int bufStride = nf * fstride;
 #define bufs(k) (bufBase + (k) * bufStride)
@@ -249,7 +255,7 @@ fftPassStrided(Addr addr, int nRuntime, int nkx, int nOther, int tile, FftAxis a
   auto issueLoad = [&](int t, C *dst) {
     const int tx = t % ntx, other = t / ntx;
     const int kx0 = tx * tile;
-    const int w = min(tile, nkx - kx0) * 3;
+    const int w = min(tile, nkx - kx0) * NC;
     if (gf < nf) {
       if (gf < w) for (int i = gi; i < n; i += gstep) cpAsync(dst + gf * fstride + i, addr.ld(other, i, kx0) + gf);
       else for (int i = gi; i < n; i += gstep) dst[gf * fstride + i] = mk2<T>(T(0), T(0));
@@ -266,7 +272,7 @@ fftPassStrided(Addr addr, int nRuntime, int nkx, int nOther, int tile, FftAxis a
     __syncthreads();
     const int tx = t % ntx, other = t / ntx;
     const int kx0 = tx * tile;
-    const int w = min(tile, nkx - kx0) * 3;
+    const int w = min(tile, nkx - kx0) * NC;
     C *res;
     if (MODE <= 0) res = fftShared<T, -1, NFIX>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
     else res = fftShared<T, +1, NFIX>(bufs(cur), bufs(scratch), ax, fstride, nf, tw);
@@ -275,7 +281,7 @@ fftPassStrided(Addr addr, int nRuntime, int nkx, int nOther, int tile, FftAxis a
       for (int idx = threadIdx.x; idx < n * tile; idx += blockDim.x) {
         const int i = idx >> tlog, tt = idx & (tile - 1);
         if (kx0 + tt < nkx) {
-          C *v = res + (tt * 3) * fstride + i;
+          C *v = res + (tt * NC) * fstride + i;
           C vx = v[0], vy = v[fstride], vz = v[2 * fstride];
           if (AXIS_IS_Z) op(kx0 + tt, other, i, vx, vy, vz);
           else op(kx0 + tt, i, other, vx, vy, vz);
@@ -334,8 +340,9 @@ template <int NFIX> inline int fftThreads() {
   default: { constexpr int NFIX = 0; CALL; } break;                                                         \
   }
 
-template <class T, bool FORWARD, int NFIX> int launchPassXFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, int nzLocal) {
-  auto kern = fftPassX<T, FORWARD, NFIX>;
+template <class T, bool FORWARD, int NFIX, int NC>
+int launchPassXFixed(const Fft3dPlan<T, NC> &p, void *grid, cudaStream_t st, int nzLocal) {
+  auto kern = fftPassX<T, FORWARD, NFIX, NC>;
   int rc = fftEnsureSmem<T>((const void *)kern, p.smemX);
   if (rc) return rc;
   const int nlines = p.ny * (nzLocal > 0 ? nzLocal : p.nz);
@@ -346,16 +353,16 @@ template <class T, bool FORWARD, int NFIX> int launchPassXFixed(const Fft3dPlan<
   return UB200_OK;
 }
 // nzLocal > 0: only that many z planes are held in `grid` (slab decomposition)
-template <class T, bool FORWARD> int launchPassX(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, int nzLocal = 0) {
+template <class T, bool FORWARD, int NC> int launchPassX(const Fft3dPlan<T, NC> &p, void *grid, cudaStream_t st, int nzLocal = 0) {
   int rc = UB200_OK;
-  UB200_FFT_DISPATCH(p.nx, (rc = launchPassXFixed<T, FORWARD, NFIX>(p, grid, st, nzLocal)));
+  UB200_FFT_DISPATCH(p.nx, (rc = launchPassXFixed<T, FORWARD, NFIX, NC>(p, grid, st, nzLocal)));
   return rc;
 }
 
-template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX>
-int launchPassStridedFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op) {
+template <class T, int MODE, bool AXIS_IS_Z, class Op, int NFIX, int NC>
+int launchPassStridedFixed(const Fft3dPlan<T, NC> &p, void *grid, cudaStream_t st, Op op) {
   using C = typename Vec2<T>::type;
-  auto kern = fftPassStrided<T, MODE, AXIS_IS_Z, Op, NFIX, AddrInPlace<C>>;
+  auto kern = fftPassStrided<T, MODE, AXIS_IS_Z, Op, NFIX, AddrInPlace<C, NC>>;
   const size_t smem = AXIS_IS_Z ? p.smemZ : p.smemY;
   int rc = fftEnsureSmem<T>((const void *)kern, smem);
   if (rc) return rc;
@@ -364,7 +371,7 @@ int launchPassStridedFixed(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, O
   const int nOther = AXIS_IS_Z ? p.ny : p.nz;
   const int threads = fftThreads<NFIX>();
   const int nblocks = persistentGrid((const void *)kern, smem, ntx * nOther, threads);
-  AddrInPlace<C> addr;
+  AddrInPlace<C, NC> addr;
   addr.grid = (C *)grid;
   if (AXIS_IS_Z) {
     addr.elemStride = (size_t)p.nkx * p.ny; addr.otherStride = (size_t)p.nkx;
@@ -402,17 +409,17 @@ int launchPassAddr(const Fft3dPlan<T> &p, const Addr &addr, int nOther, cudaStre
   return rc;
 }
 
-template <class T, int MODE, class Op = NoSpectralOp>
-int launchPassY(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()) {
+template <class T, int MODE, class Op = NoSpectralOp, int NC = 3>
+int launchPassY(const Fft3dPlan<T, NC> &p, void *grid, cudaStream_t st, Op op = Op()) {
   int rc = UB200_OK;
-  UB200_FFT_DISPATCH(p.ny, (rc = launchPassStridedFixed<T, MODE, false, Op, NFIX>(p, grid, st, op)));
+  UB200_FFT_DISPATCH(p.ny, (rc = launchPassStridedFixed<T, MODE, false, Op, NFIX, NC>(p, grid, st, op)));
   return rc;
 }
 
-template <class T, int MODE, class Op = NoSpectralOp>
-int launchPassZ(const Fft3dPlan<T> &p, void *grid, cudaStream_t st, Op op = Op()) {
+template <class T, int MODE, class Op = NoSpectralOp, int NC = 3>
+int launchPassZ(const Fft3dPlan<T, NC> &p, void *grid, cudaStream_t st, Op op = Op()) {
   int rc = UB200_OK;
-  UB200_FFT_DISPATCH(p.nz, (rc = launchPassStridedFixed<T, MODE, true, Op, NFIX>(p, grid, st, op)));
+  UB200_FFT_DISPATCH(p.nz, (rc = launchPassStridedFixed<T, MODE, true, Op, NFIX, NC>(p, grid, st, op)));
   return rc;
 }
 

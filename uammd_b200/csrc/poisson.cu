@@ -5,13 +5,14 @@
 //   far field : spread the charges with a Gaussian of width sqrt(gw^2 + 1/(4 split^2)) -> FFT -> (E, phi)(k) =
 //               (-i k, 1) rho(k) / (eps k^2 N) -> inverse FFT -> interpolate: F_i += q_i E(x_i), U_i += q_i phi(x_i)
 //   near field: pair sum within the cut-off of the tabulated real-space corrections G(r^2) and G'(r) (split > 0)
-// built from the pieces paths 2 and 1 already have: IbmState (spread / gather), the hand-written 3-D FFT (three interleaved
-// components per grid: the charge grid carries (rho, 0, 0), the field grid (Ex, Ey, Ez) and, only when energies or
-// potentials are wanted, a second grid carries (phi, 0, 0)), and the reference-layout cell list.
+// built from the pieces paths 2 and 1 already have: the IBM stencil arithmetic (ibm.cuh), the hand-written 3-D FFT with the
+// component count as a template parameter (one scalar transform forward, one four-component transform back: the
+// reference's cufftPlan3d + batch-4 cufftPlanMany, SpectralEwaldPoisson.cu:158-210) and the reference-layout cell list.
 #include "fft3d.cuh"
 #include "ibm_state.cuh"
 #include "pair_common.cuh"
 #include <cmath>
+#include <limits>
 #include <vector>
 
 namespace ub200 {
@@ -72,25 +73,107 @@ template <class T> __device__ __forceinline__ T tableValue(const ScalarTable<T> 
   return fma(t, v1, fma(-t, v0, v0));
 }
 
+// IBM<Kernel>::spread of the scalar charges (particles2GridD, misc/IBM.cu:83-147): one warp per particle, atomics into the
+// zero-filled charge grid [nz][ny][nxPad]
 template <class T4, class T>
-__global__ void __launch_bounds__(256) poissonChargeValues(const T *__restrict__ charge, int N, T4 *__restrict__ qv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+poissonSpreadCharges(const T4 *__restrict__ pos, const T *__restrict__ charge, int N, GridT<T> g, IbmKernel<T> k, int nxPad,
+                     T *__restrict__ gridQ) {
+  __shared__ T wsh[4][3 * kMaxSupport];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 4 + warp;
   if (i >= N) return;
-  T4 v;
-  v.x = charge[i]; v.y = T(0); v.z = T(0); v.w = T(0);
-  qv[i] = v;
+  const T4 p = pos[i];
+  const T pr[3] = {p.x, p.y, p.z};
+  int o[3];
+  T *w = wsh[warp];
+  const int S = k.support;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int c = cellOfT(g, d, pr[d]);
+    o[d] = supportOrigin(g, k, d, pr[d], c);
+    if (lane < S) w[d * kMaxSupport + lane] = supportWeight(g, k, d, pr[d], o[d], lane);
+  }
+  __syncwarp();
+  const T q = charge[i];
+  const int total = S * S * S;
+  for (int t = lane; t < total; t += 32) {
+    const int ii = t % S, jj = (t / S) % S, kk = t / (S * S);
+    const int cx = wrapCell(g, 0, o[0] + ii), cy = wrapCell(g, 1, o[1] + jj), cz = wrapCell(g, 2, o[2] + kk);
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
+    const T v = q * w[ii] * w[kMaxSupport + jj] * w[2 * kMaxSupport + kk];
+    if (v != T(0)) atomicAdd(gridQ + ((size_t)cx + (size_t)nxPad * ((size_t)cy + (size_t)g.n[1] * cz)), v);
+  }
+}
+
+// IBM<Kernel>::gather of the real4 grid (Ex, Ey, Ez, phi) (grid2ParticlesDTPP, misc/IBM.cu:168-235; quadrature weight = cell
+// volume) into UnZip2Real4 (SpectralEwaldPoisson.cu:535-559): force_i += q_i (E, 0), energy_i += q_i phi - or, for
+// computeFieldPotentialAtParticles, fieldPotential_i += (E, phi)
+template <class T4, class T>
+__global__ void __launch_bounds__(128)
+poissonGatherField(const T4 *__restrict__ pos, const T *__restrict__ charge, int N, GridT<T> g, IbmKernel<T> k, int nxPad,
+                   const T4 *__restrict__ gridF, T4 *__restrict__ force, T *__restrict__ energy, T4 *__restrict__ fieldPotential) {
+  __shared__ T wsh[4][3 * kMaxSupport];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 4 + warp;
+  if (i >= N) return;
+  const T4 p = pos[i];
+  const T pr[3] = {p.x, p.y, p.z};
+  int o[3];
+  T *w = wsh[warp];
+  const int S = k.support;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int c = cellOfT(g, d, pr[d]);
+    o[d] = supportOrigin(g, k, d, pr[d], c);
+    if (lane < S) w[d * kMaxSupport + lane] = supportWeight(g, k, d, pr[d], o[d], lane);
+  }
+  __syncwarp();
+  T ax = T(0), ay = T(0), az = T(0), aw = T(0);
+  const int total = S * S * S;
+  for (int t = lane; t < total; t += 32) {
+    const int ii = t % S, jj = (t / S) % S, kk = t / (S * S);
+    const int cx = wrapCell(g, 0, o[0] + ii), cy = wrapCell(g, 1, o[1] + jj), cz = wrapCell(g, 2, o[2] + kk);
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
+    const T4 v = gridF[(size_t)cx + (size_t)nxPad * ((size_t)cy + (size_t)g.n[1] * cz)];
+    const T wgt = w[ii] * w[kMaxSupport + jj] * w[2 * kMaxSupport + kk];
+    ax += g.cellVolume * (v.x * wgt);
+    ay += g.cellVolume * (v.y * wgt);
+    az += g.cellVolume * (v.z * wgt);
+    aw += g.cellVolume * (v.w * wgt);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ax += __shfl_xor_sync(0xffffffffu, ax, off);
+    ay += __shfl_xor_sync(0xffffffffu, ay, off);
+    az += __shfl_xor_sync(0xffffffffu, az, off);
+    aw += __shfl_xor_sync(0xffffffffu, aw, off);
+  }
+  if (lane != 0) return;
+  if (fieldPotential) {
+    T4 v = fieldPotential[i];
+    v.x += ax; v.y += ay; v.z += az; v.w += aw;
+    fieldPotential[i] = v;
+    return;
+  }
+  const T q = charge[i];
+  if (force) {
+    T4 f = force[i];
+    f.x += q * ax; f.y += q * ay; f.z += q * az;
+    force[i] = f;
+  }
+  if (energy) energy[i] += q * aw;
 }
 
 // Poisson_ns::chargeFourier2FieldAndPotential (SpectralEwaldPoisson.cu:446-478) with isNyquist (:428-444) and
-// cellToWaveNumber (:412-426). A holds rho(k) in its first component on entry and (Ex, Ey, Ez)(k) on exit; P, when given,
-// receives (phi(k), 0, 0).
+// cellToWaveNumber (:412-426): rho(k) [nz][ny][nkx] -> (Ex, Ey, Ez, phi)(k) [nz][ny][nkx][4]
 template <class T> struct PoissonSpectral {
   int nx, ny, nz, nkx;
   T kfx, kfy, kfz, epsilon, ncells;
 };
 template <class T>
 __global__ void __launch_bounds__(256)
-poissonFieldAndPotential(typename Vec2<T>::type *__restrict__ A, typename Vec2<T>::type *__restrict__ P, PoissonSpectral<T> s) {
+poissonFieldAndPotential(const typename Vec2<T>::type *__restrict__ Q, typename Vec2<T>::type *__restrict__ F, PoissonSpectral<T> s) {
   using C = typename Vec2<T>::type;
   const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t nk = (size_t)s.nkx * s.ny * s.nz;
@@ -108,40 +191,14 @@ poissonFieldAndPotential(typename Vec2<T>::type *__restrict__ A, typename Vec2<T
     if (cy >= s.ny / 2 + 1) ky -= T(s.ny) * s.kfy;
     if (cz >= s.nz / 2 + 1) kz -= T(s.nz) * s.kfz;
     const T k2 = kx * kx + ky * ky + kz * kz;
-    const C fk = A[3 * id];
+    const C fk = Q[id];
     const T B = T(1.0) / (k2 * s.epsilon * s.ncells);
     ex = mk2<T>(kx * fk.y * B, -kx * fk.x * B);
     ey = mk2<T>(ky * fk.y * B, -ky * fk.x * B);
     ez = mk2<T>(kz * fk.y * B, -kz * fk.x * B);
     ph = mk2<T>(fk.x * B, fk.y * B);
   }
-  A[3 * id] = ex; A[3 * id + 1] = ey; A[3 * id + 2] = ez;
-  if (P) { P[3 * id] = ph; P[3 * id + 1] = zero; P[3 * id + 2] = zero; }
-}
-
-// UnZip2Real4::operator+= (SpectralEwaldPoisson.cu:535-559) / the real4 gather of computeFieldPotentialAtParticles:
-//   force_i += q_i (E, 0), energy_i += q_i phi   |   fieldPotential_i += (E, phi)
-template <class T4, class T>
-__global__ void __launch_bounds__(256)
-poissonCombine(const T *__restrict__ E3, const T *__restrict__ P3, const T *__restrict__ charge, int N, T4 *__restrict__ force,
-               T *__restrict__ energy, T4 *__restrict__ fieldPotential) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const T ex = E3[3 * (size_t)i], ey = E3[3 * (size_t)i + 1], ez = E3[3 * (size_t)i + 2];
-  const T ph = P3 ? P3[3 * (size_t)i] : T(0);
-  if (fieldPotential) {
-    T4 v = fieldPotential[i];
-    v.x += ex; v.y += ey; v.z += ez; v.w += ph;
-    fieldPotential[i] = v;
-    return;
-  }
-  const T q = charge[i];
-  if (force) {
-    T4 f = force[i];
-    f.x += q * ex; f.y += q * ey; f.z += q * ez;
-    force[i] = f;
-  }
-  if (energy) energy[i] += q * ph;
+  F[4 * id] = ex; F[4 * id + 1] = ey; F[4 * id + 2] = ez; F[4 * id + 3] = ph;
 }
 
 // positions + charge in the sorted order of the cell list, in the precision of the solver
@@ -243,9 +300,11 @@ poissonNearTraversal(const T4 *__restrict__ sortedPQ, const int *__restrict__ gr
 template <class T> struct PoissonState {
   using T4 = typename Real4<T>::type;
   using C = typename Vec2<T>::type;
-  Fft3dPlan<T> plan;
-  IbmState<T> ibm;
-  DevBuf A, P, qv, Eout, Pout, tableG, tableF, posF, sortedPQ;
+  Fft3dPlan<T, 1> planQ; // charges
+  Fft3dPlan<T, 4> planF; // (Ex, Ey, Ez, phi)
+  GridT<T> grid;
+  IbmKernel<T> kern;
+  DevBuf Q, F, tableG, tableF, posF, sortedPQ;
   ub200_celllist *cl = nullptr;
   double L[3] = {0, 0, 0}, epsilon = 1, split = -1, gw = 1, tolerance = 1e-5, nearCut = 0, farWidth = 0, h = 0;
   int support = 0, nTable = 0, cells[3] = {0, 0, 0};
@@ -283,14 +342,15 @@ template <class T> struct PoissonState {
       nearCut = (double)(T)r;
       if (nearCut > (T)L[0] / 2.0) return UB200_ERR_INVALID_ARGUMENT; // "Near field cut off is too large"
     }
-    int rc = plan.init(cells[0], cells[1], cells[2]);
-    if (rc) return rc;
-    ub200_ibm_kernel k;
-    k.kind = UB200_KERNEL_GAUSSIAN; // Gaussian::phi has no radial cut: every point of the support counts
-    k.support = support; k.h = h; k.prefactor = (double)prefactor; k.tau = (double)tau; k.rmax = 1e300;
+    int rc;
+    if ((rc = planQ.init(cells[0], cells[1], cells[2])) || (rc = planF.init(cells[0], cells[1], cells[2]))) return rc;
     const int periodic[3] = {1, 1, 1};
-    if ((rc = ibm.init(L, periodic, cells, k, plan.nxPad))) return rc;
-    if ((rc = A.reserve(plan.gridBytes())) || (rc = P.reserve(plan.gridBytes()))) return rc;
+    grid = makeGridT<T>(L, periodic, cells);
+    kern.kind = kKernelGaussian; // Poisson_ns::Gaussian::phi has no radial cut: every point of the support counts
+    kern.support = support;
+    kern.invh = (T)(1.0 / h);
+    kern.prefactor = prefactor; kern.tau = tau; kern.rmax = std::numeric_limits<T>::max();
+    if ((rc = Q.reserve(planQ.gridBytes())) || (rc = F.reserve(planF.gridBytes()))) return rc;
     if (split > 0) {
       nTable = std::max(4096, std::min(1 << 16, int((T)nearCut / ((T)gw * (T)tolerance * 1e3))));
       std::vector<T> tg(nTable), tf(nTable);
@@ -309,8 +369,8 @@ template <class T> struct PoissonState {
     return UB200_OK;
   }
   void release() {
-    plan.release(); ibm.release();
-    DevBuf *b[] = {&A, &P, &qv, &Eout, &Pout, &tableG, &tableF, &posF, &sortedPQ};
+    planQ.release(); planF.release();
+    DevBuf *b[] = {&Q, &F, &tableG, &tableF, &posF, &sortedPQ};
     for (auto *x : b) x->release();
     if (cl) ub200_celllist_destroy(cl);
     cl = nullptr;
@@ -325,38 +385,32 @@ template <class T> struct PoissonState {
     return tb;
   }
 
-  // Poisson::farField (SpectralEwaldPoisson.cu:337-366): leaves E (and phi) at the particles in Eout / Pout
-  int farField(const void *pos, const void *charge, int N, bool wantPhi, cudaStream_t st) {
+  // Poisson::farField (SpectralEwaldPoisson.cu:337-366): zero fill, spread, forward FFT, convolution, inverse FFT,
+  // interpolation into (force, energy) or into fieldPotential
+  int farField(const void *pos, const void *charge, int N, T4 *force, T *energy, T4 *fieldPotential, cudaStream_t st) {
     int rc;
-    if ((rc = qv.reserve(sizeof(T4) * (size_t)N)) || (rc = Eout.reserve(sizeof(T) * 3 * (size_t)N)) ||
-        (rc = Pout.reserve(sizeof(T) * 3 * (size_t)N)))
-      return rc;
-    const int nb = (N + 255) / 256;
-    poissonChargeValues<T4, T><<<nb, 256, 0, st>>>((const T *)charge, N, qv.as<T4>());
+    T *q = Q.as<T>(), *f = F.as<T>();
+    UB200_CUDA(cudaMemsetAsync(q, 0, planQ.gridBytes(), st));
+    const int nb = (N + 3) / 4;
+    poissonSpreadCharges<T4, T><<<nb, 128, 0, st>>>((const T4 *)pos, (const T *)charge, N, grid, kern, planQ.nxPad, q);
     UB200_LAUNCHED();
-    T *a = A.as<T>(), *p = P.as<T>();
-    if ((rc = ibm.spread(pos, qv.p, 4, N, a, false, st))) return rc;
-    if ((rc = launchPassX<T, true>(plan, a, st)) || (rc = launchPassY<T, -1>(plan, a, st)) || (rc = launchPassZ<T, -1>(plan, a, st)))
+    if ((rc = launchPassX<T, true>(planQ, q, st)) || (rc = launchPassY<T, -1>(planQ, q, st)) || (rc = launchPassZ<T, -1>(planQ, q, st)))
       return rc;
     PoissonSpectral<T> s;
-    s.nx = plan.nx; s.ny = plan.ny; s.nz = plan.nz; s.nkx = plan.nkx;
+    s.nx = planQ.nx; s.ny = planQ.ny; s.nz = planQ.nz; s.nkx = planQ.nkx;
     s.kfx = (T)(T(2.0) * T(M_PI) / (T)L[0]);
     s.kfy = (T)(T(2.0) * T(M_PI) / (T)L[1]);
     s.kfz = (T)(T(2.0) * T(M_PI) / (T)L[2]);
     s.epsilon = (T)epsilon;
-    s.ncells = (T)((double)plan.nx * plan.ny * plan.nz);
-    const size_t nk = (size_t)plan.nkx * plan.ny * plan.nz;
-    poissonFieldAndPotential<T><<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(reinterpret_cast<C *>(a),
-                                                                             wantPhi ? reinterpret_cast<C *>(p) : nullptr, s);
+    s.ncells = (T)((double)planQ.nx * planQ.ny * planQ.nz);
+    const size_t nk = (size_t)planQ.nkx * planQ.ny * planQ.nz;
+    poissonFieldAndPotential<T><<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(reinterpret_cast<const C *>(q), reinterpret_cast<C *>(f), s);
     UB200_LAUNCHED();
-    if ((rc = launchPassZ<T, +1>(plan, a, st)) || (rc = launchPassY<T, +1>(plan, a, st)) || (rc = launchPassX<T, false>(plan, a, st)))
+    if ((rc = launchPassZ<T, +1>(planF, f, st)) || (rc = launchPassY<T, +1>(planF, f, st)) || (rc = launchPassX<T, false>(planF, f, st)))
       return rc;
-    if ((rc = ibm.gather(pos, N, a, Eout.as<T>(), false, true, st))) return rc;
-    if (wantPhi) {
-      if ((rc = launchPassZ<T, +1>(plan, p, st)) || (rc = launchPassY<T, +1>(plan, p, st)) || (rc = launchPassX<T, false>(plan, p, st)))
-        return rc;
-      if ((rc = ibm.gather(pos, N, p, Pout.as<T>(), false, true, st))) return rc;
-    }
+    poissonGatherField<T4, T><<<nb, 128, 0, st>>>((const T4 *)pos, (const T *)charge, N, grid, kern, planF.nxPad,
+                                                    reinterpret_cast<const T4 *>(f), force, energy, fieldPotential);
+    UB200_LAUNCHED();
     return UB200_OK;
   }
 
@@ -404,10 +458,7 @@ template <class T> struct PoissonState {
   int sum(const void *pos, const void *charge, int N, void *force4, void *energy, bool nearForce, bool nearEnergy,
           cudaStream_t st) {
     int rc;
-    if ((rc = farField(pos, charge, N, energy != nullptr, st))) return rc;
-    poissonCombine<T4, T><<<(N + 255) / 256, 256, 0, st>>>(Eout.as<T>(), energy ? Pout.as<T>() : nullptr, (const T *)charge, N,
-                                                            (T4 *)force4, (T *)energy, (T4 *)nullptr);
-    UB200_LAUNCHED();
+    if ((rc = farField(pos, charge, N, (T4 *)force4, (T *)energy, nullptr, st))) return rc;
     nearForce = nearForce && force4;
     nearEnergy = nearEnergy && energy;
     if (split > 0 && (nearForce || nearEnergy)) {
@@ -420,10 +471,7 @@ template <class T> struct PoissonState {
   // Poisson::computeFieldPotentialAtParticles (SpectralEwaldPoisson.cuh:124-135): (Ex, Ey, Ez, phi) ADDED to out4
   int fieldPotential(const void *pos, const void *charge, int N, void *out4, cudaStream_t st) {
     int rc;
-    if ((rc = farField(pos, charge, N, true, st))) return rc;
-    poissonCombine<T4, T><<<(N + 255) / 256, 256, 0, st>>>(Eout.as<T>(), Pout.as<T>(), (const T *)charge, N, (T4 *)nullptr,
-                                                            (T *)nullptr, (T4 *)out4);
-    UB200_LAUNCHED();
+    if ((rc = farField(pos, charge, N, nullptr, nullptr, (T4 *)out4, st))) return rc;
     if (split > 0) {
       if ((rc = nearPrepare(pos, charge, N, st))) return rc;
       if ((rc = nearLaunch<2>((T4 *)out4, nullptr, st))) return rc;
