@@ -78,11 +78,13 @@ template <class T> __device__ __forceinline__ T tableValue(const ScalarTable<T> 
 template <class T4, class T>
 __global__ void __launch_bounds__(128)
 poissonSpreadCharges(const T4 *__restrict__ pos, const T *__restrict__ charge, int N, GridT<T> g, IbmKernel<T> k, int nxPad,
-                     T *__restrict__ gridQ) {
+                     T *__restrict__ gridQ, const int *__restrict__ order) {
+  // order: optional cell-sorted permutation (the near field's cell list): neighbouring warps then touch neighbouring nodes
   __shared__ T wsh[4][3 * kMaxSupport];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 4 + warp;
-  if (i >= N) return;
+  const int slot = blockIdx.x * 4 + warp;
+  if (slot >= N) return;
+  const int i = order ? order[slot] : slot;
   const T4 p = pos[i];
   const T pr[3] = {p.x, p.y, p.z};
   int o[3];
@@ -112,11 +114,13 @@ poissonSpreadCharges(const T4 *__restrict__ pos, const T *__restrict__ charge, i
 template <class T4, class T>
 __global__ void __launch_bounds__(128)
 poissonGatherField(const T4 *__restrict__ pos, const T *__restrict__ charge, int N, GridT<T> g, IbmKernel<T> k, int nxPad,
-                   const T4 *__restrict__ gridF, T4 *__restrict__ force, T *__restrict__ energy, T4 *__restrict__ fieldPotential) {
+                   const T4 *__restrict__ gridF, T4 *__restrict__ force, T *__restrict__ energy, T4 *__restrict__ fieldPotential,
+                   const int *__restrict__ order) {
   __shared__ T wsh[4][3 * kMaxSupport];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 4 + warp;
-  if (i >= N) return;
+  const int slot = blockIdx.x * 4 + warp;
+  if (slot >= N) return;
+  const int i = order ? order[slot] : slot;
   const T4 p = pos[i];
   const T pr[3] = {p.x, p.y, p.z};
   int o[3];
@@ -387,12 +391,13 @@ template <class T> struct PoissonState {
 
   // Poisson::farField (SpectralEwaldPoisson.cu:337-366): zero fill, spread, forward FFT, convolution, inverse FFT,
   // interpolation into (force, energy) or into fieldPotential
-  int farField(const void *pos, const void *charge, int N, T4 *force, T *energy, T4 *fieldPotential, cudaStream_t st) {
+  int farField(const void *pos, const void *charge, int N, T4 *force, T *energy, T4 *fieldPotential, const int *order,
+               cudaStream_t st) {
     int rc;
     T *q = Q.as<T>(), *f = F.as<T>();
     UB200_CUDA(cudaMemsetAsync(q, 0, planQ.gridBytes(), st));
     const int nb = (N + 3) / 4;
-    poissonSpreadCharges<T4, T><<<nb, 128, 0, st>>>((const T4 *)pos, (const T *)charge, N, grid, kern, planQ.nxPad, q);
+    poissonSpreadCharges<T4, T><<<nb, 128, 0, st>>>((const T4 *)pos, (const T *)charge, N, grid, kern, planQ.nxPad, q, order);
     UB200_LAUNCHED();
     if ((rc = launchPassX<T, true>(planQ, q, st)) || (rc = launchPassY<T, -1>(planQ, q, st)) || (rc = launchPassZ<T, -1>(planQ, q, st)))
       return rc;
@@ -409,7 +414,7 @@ template <class T> struct PoissonState {
     if ((rc = launchPassZ<T, +1>(planF, f, st)) || (rc = launchPassY<T, +1>(planF, f, st)) || (rc = launchPassX<T, false>(planF, f, st)))
       return rc;
     poissonGatherField<T4, T><<<nb, 128, 0, st>>>((const T4 *)pos, (const T *)charge, N, grid, kern, planF.nxPad,
-                                                    reinterpret_cast<const T4 *>(f), force, energy, fieldPotential);
+                                                    reinterpret_cast<const T4 *>(f), force, energy, fieldPotential, order);
     UB200_LAUNCHED();
     return UB200_OK;
   }
@@ -458,11 +463,13 @@ template <class T> struct PoissonState {
   int sum(const void *pos, const void *charge, int N, void *force4, void *energy, bool nearForce, bool nearEnergy,
           cudaStream_t st) {
     int rc;
-    if ((rc = farField(pos, charge, N, (T4 *)force4, (T *)energy, nullptr, st))) return rc;
     nearForce = nearForce && force4;
     nearEnergy = nearEnergy && energy;
-    if (split > 0 && (nearForce || nearEnergy)) {
-      if ((rc = nearPrepare(pos, charge, N, st))) return rc;
+    const bool near = split > 0 && (nearForce || nearEnergy);
+    // the near field's cell list first: its order also serves the spreading and the interpolation (grid locality)
+    if (near && (rc = nearPrepare(pos, charge, N, st))) return rc;
+    if ((rc = farField(pos, charge, N, (T4 *)force4, (T *)energy, nullptr, near ? cl->groupIndex.as<int>() : nullptr, st))) return rc;
+    if (near) {
       if (nearForce && (rc = nearLaunch<0>((T4 *)force4, nullptr, st))) return rc;
       if (nearEnergy && (rc = nearLaunch<1>(nullptr, (T *)energy, st))) return rc;
     }
@@ -471,9 +478,9 @@ template <class T> struct PoissonState {
   // Poisson::computeFieldPotentialAtParticles (SpectralEwaldPoisson.cuh:124-135): (Ex, Ey, Ez, phi) ADDED to out4
   int fieldPotential(const void *pos, const void *charge, int N, void *out4, cudaStream_t st) {
     int rc;
-    if ((rc = farField(pos, charge, N, nullptr, nullptr, (T4 *)out4, st))) return rc;
+    if (split > 0 && (rc = nearPrepare(pos, charge, N, st))) return rc;
+    if ((rc = farField(pos, charge, N, nullptr, nullptr, (T4 *)out4, split > 0 ? cl->groupIndex.as<int>() : nullptr, st))) return rc;
     if (split > 0) {
-      if ((rc = nearPrepare(pos, charge, N, st))) return rc;
       if ((rc = nearLaunch<2>((T4 *)out4, nullptr, st))) return rc;
     }
     return UB200_OK;
