@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest "tests/test_vlist_gpu.py::test_row_list_holds_the_pairs_of_the_reference_list" "tests/test_vlist_gpu.py::test_dense_cloud_grows_the_rows_and_takes_the_unstaged_fill" "tests/test_poisson_gpu.py::test_two_charges_field_known_answer" -q -x 2>&1 | grep -v "^\[W" | tail -15 > gpurun_out/r03g_racecheck.log; tail -8 gpurun_out/r03g_racecheck.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r03h_launches.csv python bench.py --steps 4 --warmup 3 --equil 3 --fcm-steps 4 --no-cpu-baseline > gpurun_out/r03h_ncu_bench.log 2>&1; tail -1 gpurun_out/r03h_ncu_bench.log | cut -c1-200
