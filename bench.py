@@ -455,7 +455,15 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
         import bench_fcm as fcm_bench
         peak, _ = measured_peaks()
         fcm_line = fcm_bench.run_distributed(dev, peak, steps=args.fcm_steps)
+    pse_line = None
+    if not args.no_extra:
+        try:
+            pse_line = extra_bench.pse_far_distributed(dev)
+        except Exception as e:  # a secondary leg must not take the headline down
+            pse_line = {"error": repr(e)[:300]}
     if rank == 0:
+        if pse_line is not None:
+            line_out["pse_far"] = pse_line
         if fcm_line is not None:
             line_out["fcm"] = fcm_line
         if dpd_line is not None:

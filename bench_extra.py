@@ -179,6 +179,54 @@ def pse(dev, steps=20, warmup=3):
             "gpu_launches": int(lib().ub200_launch_count() - l0)}
 
 
+def pse_far_distributed(dev, steps=20, warmup=3):
+    """BASELINE config 3's far field ("slab-decomposed FFT over 8 GPUs"): pse_ns::FarField over all ranks
+    (uammd_b200.multigpu.DistributedPSEFarField: z slabs, FFT transposes as NVLink peer stores), N = 1e6, 256^3 fp32, force and
+    noise. Device time per call, max over ranks; rank 0 also times the single-GPU far field of the same inputs. Returns None
+    except on rank 0."""
+    import math
+    import torch.distributed as dist
+    from uammd_b200 import bd
+    from uammd_b200 import pse as P
+    from uammd_b200.multigpu import DistributedPSEFarField
+    world, rank = dist.get_world_size(), dist.get_rank()
+    pos, force = _pse_inputs()
+    p, f = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)
+    par = P.Parameters(PSE_L, viscosity=1.0, hydrodynamicRadius=1.0, tolerance=PSE_TOL, psi=PSE_PSI, temperature=PSE_T, dt=PSE_DT)
+    far = DistributedPSEFarField(par, PSE_N, seedFar=777)
+    far_planes = far.cells[2]
+    MF = torch.zeros(PSE_N, 3, device=dev)
+    calls = [0]
+
+    def step():
+        calls[0] += 1
+        far.computeHydrodynamicDisplacements(p, f, MF, temperature=PSE_T, prefactor=1.0 / math.sqrt(PSE_DT), seed2=calls[0])
+
+    scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(); dist.barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        scrub.fill_(3)
+        a.record(); step(); b.record()
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in evs]))], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = far.fcm.errorFlag()
+    far.close()
+    single = None
+    if rank == 0:
+        m = P.PSE(p, par, sys=bd.System(1234), force=f)
+        single = _timed(dev, lambda: m.computeMFFarField(MF), 10, 3)
+    dist.barrier()
+    if rank != 0:
+        return None
+    return {"metric": "PSE far-field calls/s @1e6 particles, 256^3", "value": 1000.0 / float(t.item()), "unit": "calls/s",
+            "ms_per_step": float(t.item()), "n_gpus": world, "scaling": "strong", "single_gpu_ms": single, "barrier_error_flag": err,
+            "what": "pse_ns::FarField::computeHydrodynamicDisplacements (force + noise) over z slabs, %d planes per rank" % (far_planes // world)}
+
+
 def pse_reference(root, steps=20, warmup=3):
     exe = os.path.join(root, "oracle", "_ref", "ref_pse_f32")
     if not os.path.exists(exe):
