@@ -1,2 +1,11 @@
 cd /root/repo
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r03h_launches.csv python bench.py --steps 4 --warmup 3 --equil 3 --fcm-steps 4 --no-cpu-baseline > gpurun_out/r03h_ncu_bench.log 2>&1; tail -1 gpurun_out/r03h_ncu_bench.log | cut -c1-200
+for g in sorted warp; do
+UB200_IBM_GATHER=$g timeout 600 python - <<'PY'
+import os, json, torch, sys
+sys.path.insert(0, '/root/repo')
+import bench_extra as b
+r = b.pse(torch.device('cuda:0'), steps=10, warmup=3)
+print(os.environ.get('UB200_IBM_GATHER'), {k: r[k] for k in ('value', 'ms_per_step', 'far_field_T0_ms', 'near_field_T0_ms')})
+PY
+done
+timeout 900 python -m pytest tests/test_pse_gpu.py tests/test_fcm_gpu.py -q -x 2>&1 | grep -v "^\[W" | tail -3

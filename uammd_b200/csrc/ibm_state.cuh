@@ -1,6 +1,7 @@
 // Host-side state of the immersed-boundary operators (scratch buffers + launch logic), shared by the FCM and PSE
 // pipelines and by the stand-alone ub200_ibm_* entry points.
 #pragma once
+#include <cstdlib>
 #include "ibm.cuh"
 
 namespace ub200 {
@@ -44,7 +45,10 @@ template <class T> struct IbmState {
     // a brick plus a support (smaller grids take the generic path); origins are packed in 16 bits
     if (grid.n[0] < kRbX + k.support || grid.n[0] > 65000 || grid.n[1] > 65000 || grid.n[2] > 65000) nodeCentric = false;
     if ((grid.m[1] != T(0) && grid.n[1] < kRbY + k.support) || (grid.m[2] != T(0) && grid.n[2] < kRbZ + k.support)) nodeCentric = false;
-    sortedGather = nodeCentric && k.support <= 4;
+    // thread-per-particle interpolation over the cell-sorted records; UB200_IBM_GATHER=warp keeps the warp-per-particle kernel
+    // for the wide supports (5, 7) - A/B switch
+    const char *gsel = getenv("UB200_IBM_GATHER");
+    sortedGather = nodeCentric && (k.support <= 4 || !(gsel && gsel[0] == 'w'));
     if (grid.n[2] == 1) nodeCentric = false; // 2-D grids take the generic path
     return UB200_OK;
   }
@@ -133,8 +137,12 @@ template <class T> struct IbmState {
       const int nb = (N + 127) / 128;
 #define UB200_GATHER(SS, ACC)                                                                                 \
   ibmGatherSorted<T, SS, ACC><<<nb, 128, 0, st>>>(sortedRec.as<T>(), sortedIndex.as<int>(), N, grid, nxPad, grid3, out3)
-      if (kern.support == 3) { if (accumulate) UB200_GATHER(3, true); else UB200_GATHER(3, false); }
-      else { if (accumulate) UB200_GATHER(4, true); else UB200_GATHER(4, false); }
+      switch (kern.support) {
+      case 3: if (accumulate) UB200_GATHER(3, true); else UB200_GATHER(3, false); break;
+      case 4: if (accumulate) UB200_GATHER(4, true); else UB200_GATHER(4, false); break;
+      case 5: if (accumulate) UB200_GATHER(5, true); else UB200_GATHER(5, false); break;
+      default: if (accumulate) UB200_GATHER(7, true); else UB200_GATHER(7, false); break;
+      }
 #undef UB200_GATHER
       UB200_LAUNCHED();
       return UB200_OK;
