@@ -535,6 +535,12 @@ int ub200_pse_far_mdot(ub200_pse *pse, const void *d_pos, const void *d_force, i
 int ub200_pse_near_mdot(ub200_pse *pse, const void *d_pos, const void *d_v, int vStride, int N, void *d_Mv3, void *stream);
 /* NearField::computeStochasticDisplacements (NearField.cuh:254-282): d_BdW3 = prefactor sqrt(2T) Mr^1/2 dW (overwritten,
  * like the reference's gemv with beta = 0). Host-synchronous (Lanczos convergence checks) like the reference. */
+/* The same product through the near field's Verlet list, for a step that also draws noise: the Lanczos iteration needs the list
+ * anyway (it walks it 5 - 10 times), so it is built here and ub200_pse_near_noise_reuse skips its own build when it is given the
+ * SAME position array, unchanged since (the reference's BDHI::EulerMaruyama calls computeMF and computeBdW back to back). */
+int ub200_pse_near_mdot_list(ub200_pse *pse, const void *d_pos, const void *d_v, int vStride, int N, void *d_Mv3, void *stream);
+int ub200_pse_near_noise_reuse(ub200_pse *pse, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
+                               void *d_BdW3, int *iterations, void *stream);
 int ub200_pse_near_noise(ub200_pse *pse, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
                          void *d_BdW3, int *iterations, void *stream);
 /* same, ADDED to d_out3: what PSE::computeHydrodynamicDisplacements (BDHI_PSE.cuh:141-158) documents - "Mobility force +

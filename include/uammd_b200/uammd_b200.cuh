@@ -965,14 +965,18 @@ public:
     auto force = pd->getForce(access::gpu, access::read);
     const uint seed2 = temperature > real(0) ? pd->getSystem()->rng().next32() : 0u;
     check(ub200_pse_far_mdot(handle, pos.raw(), force.raw(), N, temperature, 1.0 / sqrt((double)dt), seed2, MF, (void *)st), "pse_far");
-    check(ub200_pse_near_mdot(handle, pos.raw(), force.raw(), 4, N, MF, (void *)st), "pse_near");
+    // with noise the Lanczos iteration of computeBdW needs the near field's Verlet list anyway: the product runs over it and
+    // leaves it for the computeBdW that BDHI::EulerMaruyama issues next on the same positions (BDHI_EulerMaruyama.cu:125-166)
+    if (temperature > real(0)) check(ub200_pse_near_mdot_list(handle, pos.raw(), force.raw(), 4, N, MF, (void *)st), "pse_near");
+    else check(ub200_pse_near_mdot(handle, pos.raw(), force.raw(), 4, N, MF, (void *)st), "pse_near");
   }
   void computeBdW(real3 *BdW, cudaStream_t st) {
     if (temperature == real(0)) return;
     auto pd = pg->getParticleData();
     auto pos = pd->getPos(access::gpu, access::read);
     const uint seed2 = pd->getSystem()->rng().next32();
-    check(ub200_pse_near_noise(handle, pos.raw(), pg->getNumberParticles(), temperature, 1.0, seed2, BdW, nullptr, (void *)st), "pse_noise");
+    check(ub200_pse_near_noise_reuse(handle, pos.raw(), pg->getNumberParticles(), temperature, 1.0, seed2, BdW, nullptr, (void *)st),
+          "pse_noise");
   }
   void computeDivM(real3 *divM, cudaStream_t st = 0) {}
   void setShearStrain(real s) { check(ub200_pse_set_shear_strain(handle, s), "pse_shear"); }

@@ -228,3 +228,29 @@ def test_displacements_with_force_and_noise_keep_every_term(cuda):
     total = (near + noise + far).cpu().numpy()
     assert _rel(MF.cpu().numpy(), total) < 1e-12
     assert np.linalg.norm(near.cpu().numpy()) > 1e-3 * np.linalg.norm(total)   # the term the reference drops is not small
+
+
+@pytest.mark.parametrize("shear", [0.0, 0.15])
+def test_near_product_over_the_verlet_list_and_list_reuse(cuda, shear):
+    """The step with noise runs the near-field M F over the Verlet list the Lanczos iteration needs anyway and hands the list
+    on: the product must equal the cell-list one (fp64: summation order only) and the noise drawn with the reused list must
+    equal the noise drawn with a list of its own (same Saru seeds)."""
+    N, L = 6000, 32.0
+    pos = np.zeros((N, 4)); pos[:, :3] = syn.uniform_cloud(N, L, seed=41)[:, :3].astype(np.float64)
+    force = np.zeros((N, 4)); force[:, :3] = syn.gaussian_forces(N, seed=42)
+    p, f = torch.from_numpy(pos).to(cuda), torch.from_numpy(force).to(cuda)
+    par = pse.Parameters(L, viscosity=1.0, hydrodynamicRadius=1.0, tolerance=1e-6, psi=0.6, temperature=0.9, dt=0.01, shearStrain=shear)
+    a, b = pse.PSE(p, par, sys=bd.System(7), force=f), pse.PSE(p, par, sys=bd.System(7), force=f)
+    ma, mb = torch.zeros(N, 3, dtype=p.dtype, device=cuda), torch.zeros(N, 3, dtype=p.dtype, device=cuda)
+    a.computeMFNearField(ma)
+    b.computeMFNearField(mb, listForNoise=True)
+    assert _rel(mb.cpu().numpy(), ma.cpu().numpy()) < 1e-13
+    na, nb = torch.zeros_like(ma), torch.zeros_like(mb)
+    a.computeBdW(na)
+    b.computeBdW(nb, reuseList=True)
+    assert _rel(nb.cpu().numpy(), na.cpu().numpy()) < 1e-12
+    # a reuse request without a preceding list product builds its own list
+    nc = torch.zeros_like(ma)
+    c = pse.PSE(p, par, sys=bd.System(7), force=f)
+    c.computeBdW(nc, reuseList=True)
+    assert _rel(nc.cpu().numpy(), na.cpu().numpy()) < 1e-12

@@ -441,6 +441,7 @@ template <class T> struct PseState {
   ub200_verletlist *vl = nullptr; // neighbours inside the cut-off, built once per Lanczos square root
   DevBuf sortedPV;
   int listN = -1;
+  const void *listPos = nullptr; // positions the list was built from; set when a caller may reuse it (near_mdot_list)
   // Lanczos
   GrowBuf V;
   DevBuf w, oldBz, z, partial, scalar, coeff;
@@ -766,13 +767,25 @@ template <class T> struct PseState {
     return UB200_ERR_UNSUPPORTED; // "[Lanczos] Could not converge"
   }
 
+  // NearField::Mdot over the Verlet list instead of the cell list: for callers that need the list anyway (a step with
+  // noise: the Lanczos iteration walks it 5 - 10 times) - the list is built here and may be reused by the nearNoise that follows
+  int nearMdotList(const void *pos, const T *v, int vStride, int N, T *Mv3, cudaStream_t st) {
+    int rc;
+    if ((rc = nearPrepareList(pos, N, st))) return rc;
+    listPos = pos;
+    return nearDotList(v, vStride, N, Mv3, true, st);
+  }
+
   // NearField::computeStochasticDisplacements (NearField.cuh:254-282): BdW = prefactor sqrt(2 T) M_near^1/2 dW
+  // reuseList: the caller states that the positions are the ones of the preceding nearMdotList (same array, unchanged)
   int nearNoise(const void *pos, int N, double temperature, double prefactor, uint32_t seed2, void *BdW3, int *iterations,
-                cudaStream_t st) {
+                cudaStream_t st, bool reuseList = false) {
     if (iterations) *iterations = 0;
     if (temperature == 0.0) return UB200_OK;
     int rc;
-    if ((rc = nearPrepareList(pos, N, st))) return rc;
+    const bool reuse = reuseList && listPos == pos && listN == N;
+    listPos = nullptr;
+    if (!reuse && (rc = nearPrepareList(pos, N, st))) return rc;
     if ((rc = z.reserve(sizeof(T) * 3 * (size_t)N))) return rc;
     const T noisePrefactor = (T)prefactor * (T)sqrt(2 * (T)temperature);
     pseNearNoise<T><<<(N + 255) / 256, 256, 0, st>>>(z.as<T>(), N, noisePrefactor, seedNear, seed2);
@@ -860,6 +873,18 @@ int ub200_pse_near_mdot(ub200_pse *h, const void *d_pos, const void *d_v, int vS
   }
   if ((rc = h->d.nearPrepare(d_pos, N, st))) return rc;
   return h->d.nearDot((const double *)d_v, vStride, N, (double *)d_Mv3, true, st);
+}
+int ub200_pse_near_mdot_list(ub200_pse *h, const void *d_pos, const void *d_v, int vStride, int N, void *d_Mv3, void *stream) {
+  if (!h || !d_pos || !d_Mv3 || N <= 0 || (vStride != 3 && vStride != 4)) return UB200_ERR_INVALID_ARGUMENT;
+  if (!d_v) return UB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->precision == 4) return h->f.nearMdotList(d_pos, (const float *)d_v, vStride, N, (float *)d_Mv3, st);
+  return h->d.nearMdotList(d_pos, (const double *)d_v, vStride, N, (double *)d_Mv3, st);
+}
+int ub200_pse_near_noise_reuse(ub200_pse *h, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
+                               void *d_BdW3, int *iterations, void *stream) {
+  if (!h || !d_pos || !d_BdW3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return PSE_DISPATCH(h, nearNoise(d_pos, N, temperature, prefactor, seed2, d_BdW3, iterations, (cudaStream_t)stream, true));
 }
 int ub200_pse_near_noise(ub200_pse *h, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
                          void *d_BdW3, int *iterations, void *stream) {

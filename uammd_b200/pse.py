@@ -44,6 +44,8 @@ def _declare():
         "ub200_pse_near_mdot": (i, [vp, vp, vp, i, i, vp, vp]),
         "ub200_pse_near_noise": (i, [vp, vp, i, d, d, u32, vp, C.POINTER(i), vp]),
         "ub200_pse_near_noise_add": (i, [vp, vp, i, d, d, u32, vp, C.POINTER(i), vp]),
+        "ub200_pse_near_mdot_list": (i, [vp, vp, vp, i, i, vp, vp]),
+        "ub200_pse_near_noise_reuse": (i, [vp, vp, i, d, d, u32, vp, C.POINTER(i), vp]),
         "ub200_bdhi_euler_update": (i, [i, vp, vp, vp, vp, vp, i, d, d, i, vp]),
     }
     for name, (res, args) in sig.items():
@@ -123,13 +125,16 @@ class PSE:
     def finish_step(self, stream=None):
         pass
 
-    def computeMF(self, MF, stream=None):
+    def computeMF(self, MF, stream=None, listForNoise=False):
+        """listForNoise: the near-field product runs over the Verlet list and leaves it for the computeBdW(reuseList=True)
+        that follows on the same, unchanged positions (EulerMaruyama.forwardTime with T > 0)."""
         MF.zero_()
         self.computeMFFarField(MF, stream)
-        self.computeMFNearField(MF, stream)
+        self.computeMFNearField(MF, stream, listForNoise)
 
-    def computeMFNearField(self, MF, stream=None):
-        check(self.lib.ub200_pse_near_mdot(self._h, _ptr(self.pos), _ptr(self.force) if self.force is not None else None,
+    def computeMFNearField(self, MF, stream=None, listForNoise=False):
+        fn = self.lib.ub200_pse_near_mdot_list if listForNoise else self.lib.ub200_pse_near_mdot
+        check(fn(self._h, _ptr(self.pos), _ptr(self.force) if self.force is not None else None,
                                            4, self.N, _ptr(MF), _stream_ptr(stream)))
 
     def computeMFFarField(self, MF, stream=None):
@@ -138,15 +143,15 @@ class PSE:
                                           self.N, float(self.temperature), 1.0 / math.sqrt(self.dt), seed2, _ptr(MF),
                                           _stream_ptr(stream)))
 
-    def computeBdW(self, BdW, stream=None):
-        self._nearNoise(BdW, self.temperature, 1.0, stream)
+    def computeBdW(self, BdW, stream=None, reuseList=False):
+        self._nearNoise(BdW, self.temperature, 1.0, stream, reuse=reuseList)
 
-    def _nearNoise(self, out, temperature, prefactor, stream, add=False):
+    def _nearNoise(self, out, temperature, prefactor, stream, add=False, reuse=False):
         if temperature == 0:
             return 0
         seed2 = self.sys.rng().next32()                                     # NearField.cuh:274
         it = C.c_int(0)
-        fn = self.lib.ub200_pse_near_noise_add if add else self.lib.ub200_pse_near_noise
+        fn = self.lib.ub200_pse_near_noise_add if add else (self.lib.ub200_pse_near_noise_reuse if reuse else self.lib.ub200_pse_near_noise)
         check(fn(self._h, _ptr(self.pos), self.N, float(temperature), float(prefactor), seed2, _ptr(out), C.byref(it),
                  _stream_ptr(stream)))
         return it.value
@@ -187,9 +192,10 @@ class EulerMaruyama:
     def forwardTime(self, stream=None):
         self.steps += 1
         m = self.method
-        m.computeMF(self.MF, stream)
+        noisy = self.temperature > 0 and m.force is not None
+        m.computeMF(self.MF, stream, listForNoise=noisy)
         if self.temperature > 0:
-            m.computeBdW(self.BdW, stream)
+            m.computeBdW(self.BdW, stream, reuseList=noisy)
         check(m.lib.ub200_bdhi_euler_update(8 if m.pos.dtype == torch.float64 else 4, _ptr(m.pos), None, _ptr(self.MF),
                                             _ptr(self.BdW) if self.temperature > 0 else None, None, m.N,
                                             math.sqrt(2 * self.dt * self.temperature), self.dt, 0, _stream_ptr(stream)))
