@@ -1,9 +1,6 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_pse_gpu.py "tests/test_dropin_gpu.py::test_verlet_bd_pse_dropin_matches_reference" -q -x 2>&1 | grep -v "^\[W" | tail -5
-timeout 600 python - <<'PY'
-import torch, sys
-sys.path.insert(0, '/root/repo')
-import bench_extra as b
-r = b.pse(torch.device('cuda:0'), steps=10, warmup=3)
-print({k: r[k] for k in ('value', 'ms_per_step', 'far_field_T0_ms', 'near_field_T0_ms', 'lanczos_iterations')})
-PY
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rpyNearList|rpyNearTraversal|ibmGatherSorted|ibmSpreadRows|verletFill|pseNear" -s 12 -c 8 -o gpurun_out/r03j_pse -f python scripts/extra_step.py pse > gpurun_out/r03j_pse.log 2>&1; tail -1 gpurun_out/r03j_pse.log | cut -c1-150
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dpdTileTraversal|brickAdvancePush|brickUnpack|brickKick" -s 8 -c 6 -o gpurun_out/r03j_dpd -f python -c "
+import json, sys; sys.path.insert(0, '.')
+import torch, bench_extra
+print(json.dumps(bench_extra.dpd(torch.device('cuda:0'), steps=3, warmup=2, equil=10)))" > gpurun_out/r03j_dpd.log 2>&1; tail -1 gpurun_out/r03j_dpd.log | cut -c1-150
