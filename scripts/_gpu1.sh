@@ -1,6 +1,15 @@
 cd /root/repo
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rpyNearList|rpyNearTraversal|ibmGatherSorted|ibmSpreadRows|verletFill|pseNear" -s 12 -c 8 -o gpurun_out/r03j_pse -f python scripts/extra_step.py pse > gpurun_out/r03j_pse.log 2>&1; tail -1 gpurun_out/r03j_pse.log | cut -c1-150
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dpdTileTraversal|brickAdvancePush|brickUnpack|brickKick" -s 8 -c 6 -o gpurun_out/r03j_dpd -f python -c "
-import json, sys; sys.path.insert(0, '.')
-import torch, bench_extra
-print(json.dumps(bench_extra.dpd(torch.device('cuda:0'), steps=3, warmup=2, equil=10)))" > gpurun_out/r03j_dpd.log 2>&1; tail -1 gpurun_out/r03j_dpd.log | cut -c1-150
+T=r03k
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | grep -v "^\[W" | tail -6 > gpurun_out/${T}_pytest_gpu.log; tail -3 gpurun_out/${T}_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -1 gpurun_out/${T}_smoke.log
+timeout 900 python bench.py --impl reference > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_ref.err; tail -1 gpurun_out/${T}_ref.err | cut -c1-200
+timeout 900 python bench.py > gpurun_out/${T}_bench_ours.json 2> gpurun_out/${T}_ours.err; tail -1 gpurun_out/${T}_ours.err | cut -c1-200
+python - <<'PY'
+import json
+T='r03k'
+o = json.load(open(f'/root/repo/gpurun_out/{T}_bench_ours.json')); r = json.load(open(f'/root/repo/gpurun_out/{T}_bench_reference.json'))
+print('LJ', o['value'], r['value'], o['value']/r['value'], 'e2e', o['e2e']['value'], 'resident', o['e2e_resident']['value'])
+for k in ('fcm','verlet','pse','bd','langevin','dpd','poisson'):
+    a, b = o.get(k, {}), r.get(k, {})
+    print(k, a.get('value'), b.get('value'), (a.get('value') or 0)/(b.get('value') or 1e30), a.get('error'), b.get('error'))
+PY
