@@ -235,6 +235,15 @@ int ub200_brick_profile(ub200_brick *b, double phases[5]);
  * 5 inbox overflow, 6 a peer's flag never arrived) */
 int ub200_brick_counts(ub200_brick *b, void *stream, int *nOwned, int *nLocal, int *errorFlag);
 
+/* ParticleData::sortParticles (ParticleData/ParticleData.cuh:492-522): d_order[k] = index of the particle that comes k-th in the
+ * stable sort by the Morton hash of its cell, cells of L / hashCutOff per dimension (truncated, like hints.hash_box.boxSize /
+ * hints.hash_cutOff) - the permutation ParticleSorter::updateOrderByCellHash computes (utils/ParticleSorter.cuh:157-164), bit for
+ * bit. scratch: any cell list handle (its contents are replaced). ub200_apply_order = ParticleSorter::applyCurrentOrder
+ * (:177-187): d_out[k] = d_in[d_order[k]] for rows of rowBytes bytes (a multiple of 4); in and out must not alias. */
+int ub200_particles_sort_order_f32(ub200_celllist *scratch, const void *d_pos, int N, const float L[3], const int periodic[3],
+                                   float hashCutOff, int *d_order, void *stream);
+int ub200_apply_order(const void *d_in, void *d_out, const int *d_order, int N, int rowBytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Path 3: spectral Ewald Poisson solver for Gaussian charges in a triply periodic box. Replaces
  * Poisson (Interactor/SpectralEwaldPoisson.cuh:84-184, SpectralEwaldPoisson.cu:74-580): same parameter resolution (grid

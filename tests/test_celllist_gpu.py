@@ -126,3 +126,32 @@ def test_full_size_1e6_properties(orc, cuda):
     bs = d["binStart"].long()
     assert int(bs[-1]) == N and bool(torch.all(bs[1:] >= bs[:-1]))               # checksum of bin counts
     assert tuple(d["cellDim"]) == (43, 43, 43)
+
+
+def test_sort_particles_is_the_reference_permutation(orc, cuda):
+    """ParticleData::sortParticles: the stable Morton-hash order (the oracle's ParticleSorter restatement, pinned by the golden
+    morton.bin and by the bit-exact cell lists), applied to every property; the forces of the reordered system are the
+    reordered forces."""
+    from uammd_b200.md import LJ, PairForces, sortParticles
+    N = 50000
+    Lb = syn.lj_box_length(N)
+    rng = np.random.default_rng(2)
+    pos = syn.uniform_cloud(N, Lb, seed=12)
+    pos = pos[rng.permutation(N)]
+    vel = rng.normal(size=(N, 3)).astype(np.float32)
+    ids = np.arange(N, dtype=np.int32)
+    box = Box(Lb)
+    hashCutOff = 1.25
+    cd = tuple(int(np.float32(Lb) / np.float32(hashCutOff)) for _ in range(3))
+    ref = orc.celllist_build(orc.make_grid_f(box.boxSize, cd, (1, 1, 1)), pos)
+    dpos, dvel, dids = (torch.from_numpy(a).to(cuda) for a in (pos, vel, ids))
+    order, spos, svel, sids = sortParticles(box, hashCutOff, dpos, dvel, dids)
+    assert np.array_equal(order.cpu().numpy(), ref["index"])
+    assert np.array_equal(spos.cpu().numpy().view(np.uint32), pos[ref["index"]].view(np.uint32))
+    assert np.array_equal(svel.cpu().numpy(), vel[ref["index"]]) and np.array_equal(sids.cpu().numpy(), ref["index"])
+    pot = LJ(); pot.setPotParameters(0, 0, cutOff=2.5)
+    f0, f1 = torch.zeros(N, 4, device=cuda), torch.zeros(N, 4, device=cuda)
+    PairForces(pot, box).sum(dpos, f0)
+    PairForces(pot, box).sum(spos, f1)
+    # same pairs; the order inside a half cell follows the particle indices, which the sort changes: fp32 summation order only
+    assert (f1 - f0[order.long()]).abs().max().item() < 1e-5 * f0.abs().max().item()

@@ -21,6 +21,15 @@ namespace ub200 {
 thread_local int g_lastCudaError = 0;
 unsigned long long g_launchCount = 0;
 
+// out[k] = in[order[k]] for rows of `words` 32-bit words (ParticleSorter::applyCurrentOrder)
+__global__ void __launch_bounds__(256)
+applyOrderRows(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, const int *__restrict__ order, int N, int words) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= (size_t)N * words) return;
+  const int k = (int)(t / words), w = (int)(t - (size_t)k * words);
+  out[t] = in[(size_t)order[k] * words + w];
+}
+
 __global__ void __launch_bounds__(256)
 binParticles(const float4 *__restrict__ pos, const int *__restrict__ groupIdx, int N, const int *__restrict__ nDev, GridF g,
              uint32_t *__restrict__ binCount, uint2 *__restrict__ codeSlot, int *__restrict__ errorFlag) {
@@ -259,6 +268,34 @@ int ub200_neighbour_celldim_f32(const float L[3], float rc, int cellDim[3]) {
     if (c <= 3) c = 1;        // CellList.cuh:117-122
     cellDim[d] = c;
   }
+  return UB200_OK;
+}
+
+// ParticleData::sortParticles (ParticleData/ParticleData.cuh:492-522): the order of the stable sort by the Morton hash of the
+// cell a particle lies in, cells of hash_box / hash_cutOff per dimension (truncated) - the sort the cell list performs
+int ub200_particles_sort_order_f32(ub200_celllist *scratch, const void *d_pos, int N, const float L[3], const int periodic[3],
+                                   float hashCutOff, int *d_order, void *stream) {
+  if (!scratch || !d_pos || !d_order || N <= 0 || !L || !periodic || !(hashCutOff > 0.f)) return UB200_ERR_INVALID_ARGUMENT;
+  int cd[3];
+  for (int d = 0; d < 3; d++) {
+    cd[d] = (int)(L[d] / hashCutOff); // make_int3(hints.hash_box.boxSize / hints.hash_cutOff)
+    if (cd[d] < 1) cd[d] = 1;
+    if (cd[d] > 1024) return UB200_ERR_GRID_TOO_LARGE;
+  }
+  const int rc = ub200_celllist_build_f32(scratch, d_pos, nullptr, N, L, periodic, cd, stream);
+  if (rc) return rc;
+  UB200_CUDA(cudaMemcpyAsync(d_order, scratch->groupIndex.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return UB200_OK;
+}
+
+// ParticleSorter::applyCurrentOrder (utils/ParticleSorter.cuh:177-187): out[k] = in[order[k]], rows of rowBytes (a multiple of 4)
+int ub200_apply_order(const void *d_in, void *d_out, const int *d_order, int N, int rowBytes, void *stream) {
+  if (!d_in || !d_out || !d_order || N <= 0 || rowBytes <= 0 || rowBytes % 4 || d_in == d_out) return UB200_ERR_INVALID_ARGUMENT;
+  const int words = rowBytes / 4;
+  const size_t total = (size_t)N * words;
+  ub200::applyOrderRows<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)d_in, (uint32_t *)d_out,
+                                                                                          d_order, N, words);
+  UB200_LAUNCHED();
   return UB200_OK;
 }
 

@@ -274,6 +274,32 @@ class VerletList:
         }
 
 
+def sortParticles(box, hashCutOff, pos, *properties, stream=None):
+    """ParticleData::sortParticles (ParticleData/ParticleData.cuh:492-522): reorders the particles by the Morton hash of their cell
+    (cells of box / hashCutOff) for memory locality. Returns (order, pos_sorted, *properties_sorted) where order[k] is the old
+    index of the particle now at k (apply it to `id`-like arrays to keep track, as the reference's originalOrderIndex does).
+    Properties: contiguous CUDA tensors with one row per particle and 4-byte elements."""
+    lib = _lib.lib()
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    lib.ub200_particles_sort_order_f32.argtypes = [vp, vp, i, C.c_float * 3, C.c_int * 3, f, vp, vp]
+    lib.ub200_apply_order.argtypes = [vp, vp, vp, i, i, vp]
+    if pos.dtype != torch.float32 or pos.dim() != 2 or pos.shape[1] != 4 or not pos.is_cuda or not pos.is_contiguous():
+        raise UB200Error("sortParticles: pos must be a contiguous CUDA float32 [N,4] tensor (real4)")
+    N = pos.shape[0]
+    scratch = CellList()
+    order = torch.empty(N, dtype=torch.int32, device=pos.device)
+    check(lib.ub200_particles_sort_order_f32(scratch._h, _ptr(pos), N, f3(box.boxSize), i3([int(p) for p in box.periodic]),
+                                             float(hashCutOff), _ptr(order), _stream_ptr(stream)))
+    out = []
+    for t in (pos,) + tuple(properties):
+        if not (t.is_cuda and t.is_contiguous() and t.shape[0] == N and t.element_size() == 4):
+            raise UB200Error("sortParticles: properties must be contiguous CUDA tensors of 4-byte elements with N rows")
+        o = torch.empty_like(t)
+        check(lib.ub200_apply_order(_ptr(t), _ptr(o), _ptr(order), N, t.element_size() * (t.numel() // N), _stream_ptr(stream)))
+        out.append(o)
+    return (order,) + tuple(out)
+
+
 class LJEngine:
     """ub200_ljengine: PairForces<Potential::LJ, CellList>::sum in one call (Interactor/PairForces.cu:43-78) over the
     engine's private half-cell list (column traversal, uammd_b200/csrc/lj_column.cu)."""
