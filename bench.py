@@ -384,6 +384,10 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
     launches0 = lib.ub200_launch_count()
     barrier()
     with ClockSampler(local) as clk:
+        # ranks leave the host-side barrier (and start their clock sampler) milliseconds apart; the steps themselves run in
+        # lockstep through the device-side flags, so two untimed steps put every rank on the same device timeline - without
+        # them the FIRST timed step of some rank measures that host skew (2 - 30 ms) instead of a step
+        md.run(2)
         for a, b in evs:
             scrub.fill_(1)
             a.record()
@@ -391,7 +395,12 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
             b.record()
         barrier()
     launches = lib.ub200_launch_count() - launches0
-    ms_per_step = float(np.sum([a.elapsed_time(b) for a, b in evs]) / args.steps)
+    per_step = [a.elapsed_time(b) for a, b in evs]
+    ms_per_step = float(np.sum(per_step) / args.steps)
+    if os.environ.get("UB200_BENCH_DUMP"):  # diagnostics: the distribution of the per-step times of this rank
+        ps = np.sort(per_step)
+        print(f"[rank {rank}] per-step ms: min {ps[0]:.3f} median {ps[len(ps) // 2]:.3f} p90 {ps[int(0.9 * len(ps))]:.3f} "
+              f"max {ps[-1]:.3f} first5 {[round(x, 3) for x in per_step[:5]]} argmax {int(np.argmax(per_step))}", file=sys.stderr)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

@@ -206,6 +206,7 @@ def pse_far_distributed(dev, steps=20, warmup=3):
     for _ in range(warmup):
         step()
     torch.cuda.synchronize(); dist.barrier()
+    step(); step()  # untimed: re-aligns the ranks on the device after the host-side barrier (see bench.py)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in evs:
         scrub.fill_(3)

@@ -110,6 +110,7 @@ def run_distributed(dev, hbm_peak, steps=100, warmup=10):
     for _ in range(warmup):
         step()
     torch.cuda.synchronize(); dist.barrier()
+    step(); step()  # untimed: re-aligns the ranks on the device after the host-side barrier (see bench.py)
     l0 = lib().ub200_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in evs:
