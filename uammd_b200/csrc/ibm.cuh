@@ -262,12 +262,13 @@ ibmOrderSorted(const int *__restrict__ unstable, const uint2 *__restrict__ codeS
 // (computeSupportShift lowers P by at most one).
 constexpr int kRbX = 4, kRbY = 16, kRbZ = 16, kRbThreads = kRbY * kRbZ / 2;
 
-template <class T, int S> struct RowBrickGeom {
+// KB: shared-memory budget of the staged records per pass (a brick with more records takes several passes)
+template <class T, int S, int KB = 52> struct RowBrickGeom {
   static constexpr int hi = S / 2, lo = -(S - 1) + S / 2 - ((S & 1) ? 0 : 1);
   static constexpr int W = hi - lo;
   static constexpr int RX = kRbX + W, RY = kRbY + W, RZ = kRbZ + W, nrows = RY * RZ;
   static constexpr int REC = RecGeom<T, S>::REC;
-  static constexpr int cap = (52 * 1024) / (REC * (int)sizeof(T)); // staged records per pass
+  static constexpr int cap = (KB * 1024) / (REC * (int)sizeof(T)); // staged records per pass
   static constexpr size_t headBytes = (((size_t)nrows * sizeof(int4) + (size_t)(nrows + 1) * sizeof(int) + (size_t)cap * sizeof(int) + (size_t)cap * sizeof(unsigned short)) + 15) / 16 * 16;
   static constexpr size_t smemBytes = headBytes + (size_t)cap * REC * sizeof(T);
 };
@@ -278,13 +279,13 @@ __device__ __forceinline__ int foldIndex(int d, int n, bool periodic) {
   return d;
 }
 
-template <class T, int S>
+template <class T, int S, int KB = 52>
 __global__ void __launch_bounds__(kRbThreads)
 ibmSpreadRows(const T *__restrict__ sortedRec, const uint32_t *__restrict__ binStart, GridT<T> g, int nxPad,
               T *__restrict__ grid3, int zPlane0, int nzLocal) {
   // zPlane0 / nzLocal: the z planes [zPlane0, zPlane0 + nzLocal) this launch writes; grid3 starts at plane zPlane0
   // (the whole grid on one GPU: 0, n[2])
-  using G = RowBrickGeom<T, S>;
+  using G = RowBrickGeom<T, S, KB>;
   constexpr int REC = G::REC;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   int4 *rowSeg = reinterpret_cast<int4 *>(smemRaw);                  // [nrows] {startA, countA, startB, countB}

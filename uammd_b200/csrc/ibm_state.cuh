@@ -100,19 +100,27 @@ template <class T> struct IbmState {
       int rc = prepare(pos, val, valStride, N, st);
       if (rc) return rc;
       dim3 grd((nxPad + kRbX - 1) / kRbX, (grid.n[1] + kRbY - 1) / kRbY, (grid.n[2] + kRbZ - 1) / kRbZ);
-#define UB200_SPREAD(SS)                                                                                                 \
+      // staging budget per CTA: 52 KB (a whole brick in one pass at FCM densities) for the narrow supports, 26 KB (twice
+      // the resident CTAs, bricks with more records take two passes) for supports 5 and 7, whose records are large -
+      // measured: FCM 128^3 / support 3: 0.504 ms (52) vs 0.525 (26); PSE far field 256^3 / support 7: 3.68 ms (52) vs
+      // 3.54 (26). UB200_IBM_SPREAD_KB=52|26 overrides (A/B switch).
+      static const int envKB = getenv("UB200_IBM_SPREAD_KB") ? atoi(getenv("UB200_IBM_SPREAD_KB")) : 0;
+      const bool smallStage = envKB ? envKB <= 26 : kern.support >= 5;
+#define UB200_SPREAD_KB(SS, KB)                                                                                         \
   {                                                                                                                      \
-    auto kfn = ibmSpreadRows<T, SS>;                                                                                     \
-    const size_t sm = RowBrickGeom<T, SS>::smemBytes;                                                                    \
+    auto kfn = ibmSpreadRows<T, SS, KB>;                                                                                 \
+    const size_t sm = RowBrickGeom<T, SS, KB>::smemBytes;                                                                \
     UB200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                         \
     kfn<<<grd, kRbThreads, sm, st>>>(sortedRec.as<T>(), binStart.as<uint32_t>(), grid, nxPad, grid3, 0, grid.n[2]);      \
   }
+#define UB200_SPREAD(SS) { if (smallStage) UB200_SPREAD_KB(SS, 26) else UB200_SPREAD_KB(SS, 52) }
       switch (kern.support) {
       case 3: UB200_SPREAD(3) break;
       case 4: UB200_SPREAD(4) break;
       case 5: UB200_SPREAD(5) break;
       default: UB200_SPREAD(7) break;
       }
+#undef UB200_SPREAD_KB
 #undef UB200_SPREAD
       UB200_LAUNCHED();
       return UB200_OK;
