@@ -476,9 +476,17 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
             pse_line = extra_bench.pse_far_distributed(dev)
         except Exception as e:  # a secondary leg must not take the headline down
             pse_line = {"error": repr(e)[:300]}
+    pse_near_line = None
+    if not args.no_extra:
+        try:
+            pse_near_line = extra_bench.pse_near_distributed(dev)
+        except Exception as e:  # a secondary leg must not take the headline down
+            pse_near_line = {"error": repr(e)[:300]}
     if rank == 0:
         if pse_line is not None:
             line_out["pse_far"] = pse_line
+        if pse_near_line is not None:
+            line_out["pse_near"] = pse_near_line
         if fcm_line is not None:
             line_out["fcm"] = fcm_line
         if dpd_line is not None:

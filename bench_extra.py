@@ -228,6 +228,102 @@ def pse_far_distributed(dev, steps=20, warmup=3):
             "what": "pse_ns::FarField::computeHydrodynamicDisplacements (force + noise) over z slabs, %d planes per rank" % (far_planes // world)}
 
 
+def pse_near_distributed(dev, steps=10, warmup=2):
+    """BASELINE config 3's near field over all ranks (uammd_b200.multigpu.DistributedPSENearField: rows of the cell-sorted order
+    per rank, Krylov vectors exchanged as NVLink peer stores, scalars summed by the barrier kernel): list build (replicated) +
+    M_near F + Lanczos noise at N = 1e6 fp32. Device time per call, max over ranks; rank 0 also times the same three pieces on
+    one GPU. Returns None except on rank 0."""
+    import math
+    import torch.distributed as dist
+    from uammd_b200 import bd
+    from uammd_b200 import pse as P
+    from uammd_b200.multigpu import DistributedPSENearField
+    world, rank = dist.get_world_size(), dist.get_rank()
+    pos, force = _pse_inputs()
+    p, f = torch.from_numpy(pos).to(dev), torch.from_numpy(force).to(dev)
+    par = P.Parameters(PSE_L, viscosity=1.0, hydrodynamicRadius=1.0, tolerance=PSE_TOL, psi=PSE_PSI, temperature=PSE_T, dt=PSE_DT)
+    near = DistributedPSENearField(p, par, sys=bd.System(1234))
+    MF = torch.zeros(PSE_N, 3, device=dev)
+    calls, its = [0], [0]
+    pref = 1.0 / math.sqrt(PSE_DT)
+
+    def step():
+        calls[0] += 1
+        near.prepare()
+        near.Mdot(f, MF)
+        its[0] = near.noiseAdd(MF, PSE_T, pref, calls[0])
+
+    # Every rank walks the same sequence of torch collectives whatever happens inside its own steps (which only use the
+    # library's time-bounded peer barriers): a failure on one rank becomes a flag all ranks agree on, never a rank that
+    # leaves the others waiting in a collective.
+    failure = [None]
+
+    def guarded(fn):
+        if failure[0] is None:
+            try:
+                fn()
+            except Exception as e:  # noqa: BLE001
+                failure[0] = repr(e)[:200]
+
+    def agreed_failure():
+        bad = failure[0] is not None
+        if not bad:
+            try:
+                bad = near.errorFlag() != 0
+                if bad:
+                    failure[0] = "a peer barrier timed out"
+            except Exception as e:  # noqa: BLE001
+                bad, failure[0] = True, repr(e)[:200]
+        flag = torch.tensor([1.0 if bad else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        return flag.item() != 0
+
+    guarded(step)
+    if agreed_failure():  # no number rather than a wrong one
+        return {"error": failure[0] or "another rank failed in the first call"} if rank == 0 else None
+    for _ in range(warmup):
+        guarded(step)
+    guarded(torch.cuda.synchronize); dist.barrier()
+    guarded(step)  # untimed: re-aligns the ranks on the device after the host-side barrier (see bench.py)
+    evs = []
+
+    def timed():
+        scrub = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            scrub.fill_(3)
+            a.record(); step(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+    guarded(timed)
+    dist.barrier()
+    if agreed_failure():
+        return {"error": failure[0] or "another rank failed in the timed calls"} if rank == 0 else None
+    t = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in evs]))], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = near.errorFlag()
+    single, single_it = None, None
+    if rank == 0:
+        m = P.PSE(p, par, sys=bd.System(1234), force=f)
+
+        def one():
+            m.computeMFNearField(MF, listForNoise=True)
+            m._nearNoise(MF, PSE_T, pref, None, add=False, reuse=True)
+        try:
+            single = _timed(dev, one, steps, warmup)
+            single_it = m.info().lastLanczosIterations
+        except Exception as e:  # noqa: BLE001 - the collective below must still be reached
+            single = repr(e)[:200]
+    dist.barrier()
+    if rank != 0:
+        return None
+    return {"metric": "PSE near-field calls/s @1e6 particles", "value": 1000.0 / float(t.item()), "unit": "calls/s",
+            "ms_per_step": float(t.item()), "n_gpus": world, "scaling": "strong", "single_gpu_ms": single,
+            "lanczos_iterations": its[0], "single_gpu_lanczos_iterations": single_it, "barrier_error_flag": err,
+            "what": "NearField::Mdot + computeStochasticDisplacements (Lanczos) by rows of the sorted order, %d rows per rank; "
+                    "the neighbour list is built on every rank" % (PSE_N // world)}
+
+
 def pse_reference(root, steps=20, warmup=3):
     exe = os.path.join(root, "oracle", "_ref", "ref_pse_f32")
     if not os.path.exists(exe):

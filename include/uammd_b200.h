@@ -558,6 +558,33 @@ int ub200_pse_near_noise(ub200_pse *pse, const void *d_pos, int N, double temper
 int ub200_pse_near_noise_add(ub200_pse *pse, const void *d_pos, int N, double temperature, double prefactor, uint32_t seed2,
                              void *d_out3, int *iterations, void *stream);
 
+/* ---- PSE near field and its Lanczos noise over the ranks of one NVSwitch domain (the reference is single
+ * GPU: NearField::Mdot NearField.cuh:236-251, computeStochasticDisplacements :254-282, lanczos::Solver::run
+ * LanczosAlgorithm.cu:202-228). Positions (and the force vector of Mdot) are replicated; rank r owns the rows
+ * [r N / world, (r + 1) N / world) of the cell-sorted order. A product evaluates only the owned rows; the next Krylov
+ * vector is stored straight into the records of every rank (peer stores) and the two scalars of an iteration are summed
+ * over the ranks by a one-warp kernel that is also the barrier - in rank order, so every rank sees the same bits and
+ * takes the same convergence decisions. Results land, complete, on every rank (added to d_Mv3 / d_out3).
+ * Set-up like ub200_brick_*: ub200_pse_dist_create on every rank, exchange the ub200_comm_ipc_size()-byte blobs of
+ * ub200_pse_dist_ipc_export and hand all of them (rank order) to ub200_pse_dist_ipc_import; ranks that share a process
+ * (tests) exchange ub200_pse_dist_arena pointers through ub200_pse_dist_attach_local instead. All ranks must then make
+ * the same sequence of near_mdot / near_noise_add calls. */
+int ub200_pse_dist_create(ub200_pse *pse, int rank, int world, int maxParticles);
+int ub200_pse_dist_ipc_export(ub200_pse *pse, void *blob);
+int ub200_pse_dist_ipc_import(ub200_pse *pse, const void *blobsOfAllRanks);
+int ub200_pse_dist_arena(ub200_pse *pse, void **arena);
+int ub200_pse_dist_attach_local(ub200_pse *pse, void *const *arenasOfAllRanks);
+/* neighbour list of the replicated positions (every rank builds it; no communication) */
+int ub200_pse_dist_near_prepare(ub200_pse *pse, const void *d_pos, int N, void *stream);
+/* d_Mv3 += M_near v (v replicated: real3 or real4 rows, vStride 3 or 4) */
+int ub200_pse_dist_near_mdot(ub200_pse *pse, const void *d_v, int vStride, int N, void *d_Mv3, void *stream);
+/* d_out3 += prefactor sqrt(2 T) M_near^1/2 dW; the noise of a particle is keyed by its index as in ub200_pse_near_noise,
+ * so the result equals the single-GPU one up to the summation order of the dot products */
+int ub200_pse_dist_near_noise_add(ub200_pse *pse, int N, double temperature, double prefactor, uint32_t seed2, void *d_out3,
+                                  int *iterations, void *stream);
+/* reads back (synchronising the stream) whether a peer barrier ever timed out */
+int ub200_pse_dist_error_flag(ub200_pse *pse, void *stream, int *flag);
+
 /* ------------------------------------------------------------------------------------------------
  * BASELINE config 0: BD::EulerMaruyama (ideal or with interactor forces). Replaces EulerMaruyama_ns::integrateGPU
  * (Integrator/BrownianDynamics.cu:117-145, launched by EulerMaruyama::updatePositions :158-173):

@@ -17,6 +17,7 @@
 #include "saru.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 namespace ub200 {
@@ -198,17 +199,15 @@ __device__ __forceinline__ double4 ldgV4(const double *p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-template <class T, bool ACCUMULATE, bool SHEAR>
-__global__ void __launch_bounds__(128)
-rpyNearList(const T *__restrict__ pv8, const int *__restrict__ groupIndex, const int *__restrict__ neighbourList,
-            const int *__restrict__ numberNeighbours, int N, TableView<T> tb, NearGeom<T> q, T *__restrict__ Mv3) {
+// one row of the near-field product: the neighbours of sorted particle id, in list order
+template <class T, bool SHEAR>
+__device__ __forceinline__ void rpyListRow(const T *__restrict__ pv8, const int *__restrict__ neighbourList,
+                                           const int *__restrict__ numberNeighbours, int N, int id, const TableView<T> &tb,
+                                           const NearGeom<T> &q, T &ax, T &ay, T &az) {
   using V4 = typename Real4<T>::type;
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= N) return;
   const V4 a = ldgV4(pv8 + 8 * (size_t)id);
   const int nn = numberNeighbours[id];
   const int *lp = neighbourList + id;
-  T ax = T(0), ay = T(0), az = T(0);
   int k = 0;
   for (; k + 2 <= nn; k += 2) {
     const int j0 = __ldg(lp + (size_t)k * N), j1 = __ldg(lp + (size_t)(k + 1) * N);
@@ -222,9 +221,122 @@ rpyNearList(const T *__restrict__ pv8, const int *__restrict__ groupIndex, const
     const V4 b0 = ldgV4(pv8 + 8 * (size_t)j0), c0 = ldgV4(pv8 + 8 * (size_t)j0 + 4);
     rpyPair<T, SHEAR>(q, tb, a.x, a.y, a.z, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, ax, ay, az);
   }
+}
+
+template <class T, bool ACCUMULATE, bool SHEAR>
+__global__ void __launch_bounds__(128)
+rpyNearList(const T *__restrict__ pv8, const int *__restrict__ groupIndex, const int *__restrict__ neighbourList,
+            const int *__restrict__ numberNeighbours, int N, TableView<T> tb, NearGeom<T> q, T *__restrict__ Mv3) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= N) return;
+  T ax = T(0), ay = T(0), az = T(0);
+  rpyListRow<T, SHEAR>(pv8, neighbourList, numberNeighbours, N, id, tb, q, ax, ay, az);
   T *out = Mv3 + 3 * (size_t)groupIndex[id];
   if (ACCUMULATE) { out[0] += ax; out[1] += ay; out[2] += az; }
   else { out[0] = ax; out[1] = ay; out[2] = az; }
+}
+
+// ---- near field over ranks: rank r owns the rows [lo, hi) of the SORTED order (contiguous, spatially compact); the
+// positions are replicated, the vector of the product lives in the v half of the pv8 records of every rank (peer
+// stores over NVLink, distPublishV), the result rows in a slice indexed by k - lo
+template <class T, bool SHEAR>
+__global__ void __launch_bounds__(128)
+rpyNearListRows(const T *__restrict__ pv8, const int *__restrict__ neighbourList, const int *__restrict__ numberNeighbours,
+                int N, int lo, int hi, TableView<T> tb, NearGeom<T> q, T *__restrict__ wRows) {
+  const int id = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= hi) return;
+  T ax = T(0), ay = T(0), az = T(0);
+  rpyListRow<T, SHEAR>(pv8, neighbourList, numberNeighbours, N, id, tb, q, ax, ay, az);
+  T *out = wRows + 3 * (size_t)(id - lo);
+  out[0] = ax; out[1] = ay; out[2] = az;
+}
+// vNext = alpha x on the owned rows, written to the local Krylov vector and into the records of every rank
+template <class T>
+__global__ void __launch_bounds__(256)
+distPublishV(PeerTable<T> pv8, int world, int lo, int hi, T alpha, const T *__restrict__ x, T *__restrict__ vNext) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= hi - lo) return;
+  const T a = alpha * x[3 * (size_t)r], b = alpha * x[3 * (size_t)r + 1], c = alpha * x[3 * (size_t)r + 2];
+  vNext[3 * (size_t)r] = a; vNext[3 * (size_t)r + 1] = b; vNext[3 * (size_t)r + 2] = c;
+  for (int p = 0; p < world; p++) {
+    T *o = pv8.p[p] + 8 * (size_t)(lo + r) + 3;
+    o[0] = a; o[1] = b; o[2] = c;
+  }
+}
+// result rows (sorted slice) -> the result array (particle order) of every rank
+template <class T>
+__global__ void __launch_bounds__(256)
+distPublishOut(PeerTable<T> out3, int world, int lo, int hi, const int *__restrict__ groupIndex, const T *__restrict__ rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= hi - lo) return;
+  const size_t i = (size_t)groupIndex[lo + r];
+  const T a = rows[3 * (size_t)r], b = rows[3 * (size_t)r + 1], c = rows[3 * (size_t)r + 2];
+  for (int p = 0; p < world; p++) {
+    T *o = out3.p[p] + 3 * i;
+    o[0] = a; o[1] = b; o[2] = c;
+  }
+}
+// SaruTransform (NearField.cuh:222-232) of the owned rows: the stream of a particle is keyed by its index, not by its row
+template <class T>
+__global__ void __launch_bounds__(256)
+distNoiseRows(T *__restrict__ zRows, const int *__restrict__ groupIndex, int lo, int hi, T variance, uint32_t seed1, uint32_t seed2) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= hi - lo) return;
+  Saru rng((uint32_t)groupIndex[lo + r], seed1, seed2);
+  const float2 a = rng.gauss2(1.0f), b = rng.gauss2(1.0f);
+  zRows[3 * (size_t)r] = (T)a.x * variance; zRows[3 * (size_t)r + 1] = (T)a.y * variance; zRows[3 * (size_t)r + 2] = (T)b.x * variance;
+}
+
+// One warp: all-reduce of one double over the ranks fused with a barrier (value == nullptr: barrier only).
+// arena of rank r: flags[p] = last epoch rank p announced to r | slots[row][p] = the addend of rank p. Lane p stores this
+// rank's addend into slot [row][rank] of rank p, announces the epoch with a system-scope release, and spins (bounded)
+// on what rank p announced here; lane 0 then adds the slots in rank order, so every rank obtains the same bits.
+constexpr unsigned long long kNearWaitNs = 10000000000ull; // 10 s: a lost peer must not hang the GPU
+constexpr int kNearSlotRows = 4;
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(32)
+nearPeerReduce(PeerTable<char> arena, size_t slotsOff, int row, int rank, int world, uint32_t epoch, const double *value,
+               double *out, int *err) { // value may alias out
+  const int p = threadIdx.x;
+  if (*reinterpret_cast<volatile int *>(err) != 0) { // a barrier timed out before: no more waiting, the host sees NaN and stops
+    if (p == 0 && value) *out = nan("");
+    return;
+  }
+  if (p < world) {
+    if (value) {
+      volatile double *slot = reinterpret_cast<double *>(arena.p[p] + slotsOff) + row * kMaxPeers + rank;
+      *slot = *value;
+    }
+    __threadfence_system();
+    uint32_t *remote = reinterpret_cast<uint32_t *>(arena.p[p]) + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const uint32_t *mine = reinterpret_cast<const uint32_t *>(arena.p[rank]) + p;
+    const unsigned long long t0 = globalTimerNs();
+    unsigned spins = 0;
+    while (true) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - epoch) >= 0) break;
+      if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > kNearWaitNs) { *err = (int)epoch; break; } // which barrier it was
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (p == 0 && value) {
+    const volatile double *slots = reinterpret_cast<const double *>(arena.p[rank] + slotsOff) + row * kMaxPeers;
+    double s = 0;
+    for (int q = 0; q < world; q++) s += slots[q];
+    *out = s;
+  }
+}
+template <class T>
+__global__ void __launch_bounds__(256) vecAdd(const T *__restrict__ x, T *__restrict__ y, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -279,6 +391,24 @@ __global__ void __launch_bounds__(256) vecGemv(const T *__restrict__ V, size_t n
   T acc = T(0);
   for (int j = 0; j < m; j++) acc += V[i + n * (size_t)j] * __ldg(c + j);
   out[i] = scale * acc;
+}
+// the same with the coefficients as a kernel argument (no host-to-device copy on the stream)
+constexpr int kLanczosMaxSteps = 200;
+template <class T> struct LanczosCoeff { T c[kLanczosMaxSteps]; };
+template <class T>
+__global__ void __launch_bounds__(256) vecGemvArg(const T *__restrict__ V, size_t n, int m, const LanczosCoeff<T> c, T scale,
+                                                  T *__restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T acc = T(0);
+  for (int j = 0; j < m; j++) acc += V[i + n * (size_t)j] * c.c[j];
+  out[i] = scale * acc;
+}
+// y = 0, or the first unit vector
+template <class T>
+__global__ void __launch_bounds__(256) vecFillUnit(T *__restrict__ y, size_t n, bool unit) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (unit && i == 0) ? T(1) : T(0);
 }
 // SaruTransform (NearField.cuh:222-232)
 template <class T>
@@ -440,12 +570,13 @@ template <class T> struct PseState {
   int nearN = -1;
   ub200_verletlist *vl = nullptr; // neighbours inside the cut-off, built once per Lanczos square root
   DevBuf sortedPV;
+  T *pv8 = nullptr; // the records the list products read: sortedPV, or the arena of the rank decomposition
   int listN = -1;
   const void *listPos = nullptr; // positions the list was built from; set when a caller may reuse it (near_mdot_list)
   // Lanczos
   GrowBuf V;
   DevBuf w, oldBz, z, partial, scalar, coeff;
-  int checkConvergenceSteps = 3, iterationHardLimit = 200, lastRunRequiredSteps = 0;
+  int checkConvergenceSteps = 3, iterationHardLimit = kLanczosMaxSteps, lastRunRequiredSteps = 0;
 
   int init(const ub200_pse_params &par, uint32_t seedNear_, uint32_t seedFar_) {
     for (int d = 0; d < 3; d++) Lb[d] = (T)par.L[d];
@@ -538,6 +669,9 @@ template <class T> struct PseState {
     if (vl) ub200_verletlist_destroy(vl);
     vl = nullptr;
     sortedPV.release();
+    distRelease();
+    if (hScalar) cudaFreeHost(hScalar);
+    hScalar = nullptr; hScalarDev = nullptr;
   }
 
   // ---------------- far field ----------------
@@ -652,21 +786,27 @@ template <class T> struct PseState {
       posf = posF.p;
     }
     if ((rc = ub200_verletlist_update_f32(vl, posf, nullptr, N, Lf, periodic, rcList, 1, nullptr, (void *)st))) return rc;
-    if ((rc = sortedPV.reserve(sizeof(T) * 8 * (size_t)N))) return rc;
-    pseGatherPV<T4, T><<<(N + 255) / 256, 256, 0, st>>>(vl->cl->groupIndex.as<int>(), (const T4 *)pos, (const T *)nullptr, 0, N, sortedPV.as<T>());
+    if (dArena) { // rank decomposition: the records live in the arena the peers store into
+      if (N > dMaxN) return UB200_ERR_INVALID_ARGUMENT;
+      pv8 = reinterpret_cast<T *>(static_cast<char *>(dArena) + dOffPV);
+    } else {
+      if ((rc = sortedPV.reserve(sizeof(T) * 8 * (size_t)N))) return rc;
+      pv8 = sortedPV.as<T>();
+    }
+    pseGatherPV<T4, T><<<(N + 255) / 256, 256, 0, st>>>(vl->cl->groupIndex.as<int>(), (const T4 *)pos, (const T *)nullptr, 0, N, pv8);
     UB200_LAUNCHED();
     listN = N;
     return UB200_OK;
   }
   int nearDotList(const T *v, int vStride, int N, T *Mv3, bool accumulate, cudaStream_t st) {
     if (listN != N) return UB200_ERR_NOT_BUILT;
-    pseGatherPV<T4, T><<<(N + 255) / 256, 256, 0, st>>>(vl->cl->groupIndex.as<int>(), (const T4 *)nullptr, v, vStride, N, sortedPV.as<T>());
+    pseGatherPV<T4, T><<<(N + 255) / 256, 256, 0, st>>>(vl->cl->groupIndex.as<int>(), (const T4 *)nullptr, v, vStride, N, pv8);
     UB200_LAUNCHED();
     const TableView<T> tb = tableView();
     const NearGeom<T> q = nearGeom();
     const int nb = (N + 127) / 128;
 #define UB200_NEARL(ACC, SH)                                                                                              \
-  rpyNearList<T, ACC, SH><<<nb, 128, 0, st>>>(sortedPV.as<T>(), vl->cl->groupIndex.as<int>(), vl->neighbourList.as<int>(),  \
+  rpyNearList<T, ACC, SH><<<nb, 128, 0, st>>>(pv8, vl->cl->groupIndex.as<int>(), vl->neighbourList.as<int>(),               \
                                               vl->numberNeighbours.as<int>(), N, tb, q, Mv3)
     const bool sh = shear != T(0);
     if (accumulate) { if (sh) UB200_NEARL(true, true); else UB200_NEARL(true, false); }
@@ -677,57 +817,220 @@ template <class T> struct PseState {
   }
 
   // ---------------- Lanczos ----------------
-  int dotHost(const T *a, const T *b, size_t n, double *out, cudaStream_t st) {
+  // a . b on the host; dist: over the rows of every rank (nearPeerReduce, same bits on every rank)
+  // the scalars of the iteration are written by the reduction kernels straight into mapped pinned host memory and the
+  // coefficients of the estimate travel as a kernel argument: the iteration enqueues kernels only - no copy-engine work,
+  // which is shared by all streams of a device and would order the virtual ranks of a one-process test behind each other
+  double *hScalar = nullptr, *hScalarDev = nullptr;
+  int ensureHost() {
+    if (hScalar) return UB200_OK;
+    UB200_CUDA(cudaHostAlloc((void **)&hScalar, sizeof(double) * 2, cudaHostAllocMapped | cudaHostAllocPortable));
+    UB200_CUDA(cudaHostGetDevicePointer((void **)&hScalarDev, hScalar, 0));
+    return UB200_OK;
+  }
+  int fillUnit(T *y, size_t n, bool unit, cudaStream_t st) {
+    if (n == 0) return UB200_OK;
+    vecFillUnit<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, n, unit);
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+  // every buffer of a square root over vectors of n numbers (dist: sized once, before the first barrier)
+  int reserveLanczos(size_t n, int basisVectors, cudaStream_t st) {
+    const size_t ld = std::max(n, (size_t)1);
+    int rc;
+    if ((rc = ensureHost())) return rc;
+    if ((rc = w.reserve(sizeof(T) * ld)) || (rc = oldBz.reserve(sizeof(T) * ld)) || (rc = partial.reserve(sizeof(double) * kRedBlocks)) ||
+        (rc = scalar.reserve(sizeof(double))))
+      return rc;
+    return V.grow(sizeof(T) * ld * (size_t)basisVectors, st);
+  }
+  int dotHost(const T *a, const T *b, size_t n, double *out, cudaStream_t st, bool dist = false) {
     redDotPartial<T><<<kRedBlocks, kRedThreads, 0, st>>>(a, b, n, partial.as<double>());
     UB200_LAUNCHED();
-    redFinal<<<1, kRedThreads, 0, st>>>(partial.as<double>(), kRedBlocks, scalar.as<double>());
-    UB200_LAUNCHED();
-    UB200_CUDA(cudaMemcpyAsync(out, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    int rc;
+    if (dist) {
+      redFinal<<<1, kRedThreads, 0, st>>>(partial.as<double>(), kRedBlocks, scalar.as<double>());
+      UB200_LAUNCHED();
+      if ((rc = peerReduce(scalar.as<double>(), hScalarDev, st))) return rc;
+    } else {
+      redFinal<<<1, kRedThreads, 0, st>>>(partial.as<double>(), kRedBlocks, hScalarDev);
+      UB200_LAUNCHED();
+    }
     UB200_CUDA(cudaStreamSynchronize(st));
+    *out = *static_cast<volatile double *>(hScalar);
     return UB200_OK;
   }
   int axpby(T alpha, const T *x, T beta, T *y, size_t n, cudaStream_t st) {
+    if (n == 0) return UB200_OK;
     vecAxpby<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(alpha, x, beta, y, n);
     UB200_LAUNCHED();
     return UB200_OK;
   }
 
-  // lanczos::Solver::run (LanczosAlgorithm.cu:202-228) with KrylovSubspace (:27-173); matrix = near-field mobility
-  int lanczosSqrt(const T *zin, T *Bz, int N, double tol, int *iterations, cudaStream_t st) {
-    const size_t n = 3 * (size_t)N;
+  // ---- rank decomposition of the near field (ub200_pse_dist_*) ----
+  int dRank = 0, dWorld = 1, dMaxN = 0, dLo = 0, dHi = 0;
+  void *dArena = nullptr; // flags | reduction slots | pv8 records | result (particle order); exported to the peers
+  size_t dOffSlots = 0, dOffPV = 0, dOffOut = 0, dArenaBytes = 0;
+  char *dPeer[kMaxPeers] = {};
+  bool dOpened[kMaxPeers] = {}, dAttached = false;
+  uint32_t dEpoch = 0, dSeq = 0;
+  DevBuf dErr, dRows;
+
+  int distCreate(int rank, int world, int maxParticles) {
+    if (dArena || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || maxParticles < 1) return UB200_ERR_INVALID_ARGUMENT;
+    dRank = rank; dWorld = world; dMaxN = maxParticles;
+    dOffSlots = 256;
+    dOffPV = dOffSlots + ((sizeof(double) * kNearSlotRows * kMaxPeers + 255) / 256) * 256;
+    dOffOut = dOffPV + ((sizeof(T) * 8 * (size_t)maxParticles + 255) / 256) * 256;
+    dArenaBytes = dOffOut + sizeof(T) * 3 * (size_t)maxParticles;
+    if (cudaMalloc(&dArena, dArenaBytes) != cudaSuccess) { dArena = nullptr; return UB200_ERR_ALLOC; }
+    UB200_CUDA(cudaMemset(dArena, 0, dArenaBytes));
     int rc;
-    if ((rc = w.reserve(sizeof(T) * n)) || (rc = oldBz.reserve(sizeof(T) * n)) || (rc = partial.reserve(sizeof(double) * kRedBlocks)) ||
-        (rc = scalar.reserve(sizeof(double))) || (rc = coeff.reserve(sizeof(T) * (iterationHardLimit + 2))))
-      return rc;
-    UB200_CUDA(cudaMemsetAsync(oldBz.p, 0, sizeof(T) * n, st));
+    if ((rc = dErr.reserve(sizeof(int)))) return rc;
+    UB200_CUDA(cudaMemset(dErr.p, 0, sizeof(int)));
+    dPeer[rank] = (char *)dArena;
+    dAttached = world == 1;
+    return UB200_OK;
+  }
+  void distRelease() {
+    for (int p = 0; p < kMaxPeers; p++)
+      if (dOpened[p]) { cudaIpcCloseMemHandle(dPeer[p]); dOpened[p] = false; }
+    if (dArena) cudaFree(dArena);
+    dArena = nullptr;
+    dErr.release(); dRows.release();
+  }
+  PeerTable<char> peerArenas() const {
+    PeerTable<char> t;
+    for (int p = 0; p < kMaxPeers; p++) t.p[p] = p < dWorld ? dPeer[p] : nullptr;
+    return t;
+  }
+  template <class U> PeerTable<U> peerAt(size_t off) const {
+    PeerTable<U> t;
+    for (int p = 0; p < kMaxPeers; p++) t.p[p] = p < dWorld ? reinterpret_cast<U *>(dPeer[p] + off) : nullptr;
+    return t;
+  }
+  // value != nullptr: *out = sum over the ranks of *value; in any case a barrier of the ranks on this stream
+  int peerReduce(const double *value, double *out, cudaStream_t st) {
+    if (!dAttached) return UB200_ERR_NOT_BUILT;
+    nearPeerReduce<<<1, 32, 0, st>>>(peerArenas(), dOffSlots, (int)(dSeq++ % kNearSlotRows), dRank, dWorld, ++dEpoch, value, out,
+                                     dErr.as<int>());
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+  // list of the replicated positions and the rows of this rank (the list build is not decomposed: every rank builds it)
+  int distPrepare(const void *pos, int N, cudaStream_t st) {
+    if (!dArena) return UB200_ERR_NOT_BUILT;
+    int rc;
+    if ((rc = nearPrepareList(pos, N, st))) return rc;
+    dLo = (int)(((long long)dRank * N) / dWorld);
+    dHi = (int)(((long long)(dRank + 1) * N) / dWorld);
+    const size_t nloc3 = 3 * (size_t)std::max(dHi - dLo, 1);
+    if ((rc = dRows.reserve(sizeof(T) * nloc3)) || (rc = z.reserve(sizeof(T) * nloc3)) || (rc = noiseOut.reserve(sizeof(T) * nloc3))) return rc;
+    return reserveLanczos(3 * (size_t)(dHi - dLo), 40, st);
+  }
+  // w (rows of this rank) = M_near v, v = the v half of the records
+  int distDotRows(T *wRows, cudaStream_t st) {
+    const int nloc = dHi - dLo;
+    if (nloc == 0) return UB200_OK;
+    const TableView<T> tb = tableView();
+    const NearGeom<T> q = nearGeom();
+    const int nb = (nloc + 127) / 128;
+    if (shear != T(0))
+      rpyNearListRows<T, true><<<nb, 128, 0, st>>>(pv8, vl->neighbourList.as<int>(), vl->numberNeighbours.as<int>(), listN, dLo, dHi, tb, q, wRows);
+    else
+      rpyNearListRows<T, false><<<nb, 128, 0, st>>>(pv8, vl->neighbourList.as<int>(), vl->numberNeighbours.as<int>(), listN, dLo, dHi, tb, q, wRows);
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+  int distPublishVec(T alpha, const T *x, T *vNext, cudaStream_t st) {
+    const int nloc = dHi - dLo;
+    if (nloc > 0) {
+      distPublishV<T><<<(nloc + 255) / 256, 256, 0, st>>>(peerAt<T>(dOffPV), dWorld, dLo, dHi, alpha, x, vNext);
+      UB200_LAUNCHED();
+    }
+    return peerReduce(nullptr, nullptr, st); // every rank's rows have landed before the next product reads them
+  }
+  // out3 += the full vector whose rows (sorted slices) the ranks hold; callers placed a barrier of this call before it
+  int distCollect(const T *rows, int N, T *out3, cudaStream_t st) {
+    const int nloc = dHi - dLo;
+    int rc;
+    if (nloc > 0) {
+      distPublishOut<T><<<(nloc + 255) / 256, 256, 0, st>>>(peerAt<T>(dOffOut), dWorld, dLo, dHi, vl->cl->groupIndex.as<int>(), rows);
+      UB200_LAUNCHED();
+    }
+    if ((rc = peerReduce(nullptr, nullptr, st))) return rc;
+    const size_t n = 3 * (size_t)N;
+    vecAdd<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const T *>(static_cast<char *>(dArena) + dOffOut), out3, n);
+    UB200_LAUNCHED();
+    return UB200_OK;
+  }
+  // Mv3 += M_near v on every rank (v replicated); distPrepare first
+  int distMdot(const T *v, int vStride, int N, T *Mv3, cudaStream_t st) {
+    if (!dAttached || listN != N) return UB200_ERR_NOT_BUILT;
+    int rc;
+    pseGatherPV<T4, T><<<(N + 255) / 256, 256, 0, st>>>(vl->cl->groupIndex.as<int>(), (const T4 *)nullptr, v, vStride, N, pv8);
+    UB200_LAUNCHED();
+    if ((rc = distDotRows(dRows.as<T>(), st))) return rc;
+    if ((rc = peerReduce(nullptr, nullptr, st))) return rc; // the peers have consumed the result area of the previous call
+    return distCollect(dRows.as<T>(), N, Mv3, st);
+  }
+  // out3 += prefactor sqrt(2 T) M_near^1/2 dW on every rank; distPrepare first
+  int distNoise(int N, double temperature, double prefactor, uint32_t seed2, T *out3, int *iterations, cudaStream_t st) {
+    if (iterations) *iterations = 0;
+    if (!dAttached || listN != N) return UB200_ERR_NOT_BUILT;
+    if (temperature == 0.0) return UB200_OK;
+    const int nloc = dHi - dLo;
+    int rc;
+    if ((rc = z.reserve(sizeof(T) * 3 * (size_t)std::max(nloc, 1))) || (rc = noiseOut.reserve(sizeof(T) * 3 * (size_t)std::max(nloc, 1)))) return rc;
+    const T noisePrefactor = (T)prefactor * (T)sqrt(2 * (T)temperature);
+    if (nloc > 0) {
+      distNoiseRows<T><<<(nloc + 255) / 256, 256, 0, st>>>(z.as<T>(), vl->cl->groupIndex.as<int>(), dLo, dHi, noisePrefactor, seedNear, seed2);
+      UB200_LAUNCHED();
+    }
+    if ((rc = lanczosSqrt(z.as<T>(), noiseOut.as<T>(), N, (double)tolerance, iterations, st, true))) return rc;
+    return distCollect(noiseOut.as<T>(), N, out3, st);
+  }
+
+  // lanczos::Solver::run (LanczosAlgorithm.cu:202-228) with KrylovSubspace (:27-173); matrix = near-field mobility.
+  // dist: the vectors are the rows of this rank (zin, Bz and the Krylov basis hold 3 (hi - lo) numbers), the products
+  // read the basis vector from the records every rank published into, the scalars are sums over the ranks - every rank
+  // takes the same decisions from the same bits
+  int lanczosSqrt(const T *zin, T *Bz, int N, double tol, int *iterations, cudaStream_t st, bool dist = false) {
+    const size_t n = dist ? 3 * (size_t)(dHi - dLo) : 3 * (size_t)N;
+    const size_t ld = std::max(n, (size_t)1);
+    int rc;
+    // dist: the basis is sized for 40 vectors at once (no allocation, hence no device-wide synchronisation, between barriers)
+    if ((rc = reserveLanczos(n, dist ? 40 : 8, st))) return rc;
+    if ((rc = fillUnit(oldBz.as<T>(), ld, false, st))) return rc;
     std::vector<double> hdiag, hsup;
     double nz2;
-    if ((rc = dotHost(zin, zin, n, &nz2, st))) return rc;
+    if ((rc = dotHost(zin, zin, n, &nz2, st, dist))) return rc;
     const T normz = (T)sqrt(nz2);
-    if ((rc = V.grow(sizeof(T) * n * 8, st))) return rc;
-    if ((rc = axpby((T)(1.0 / normz), zin, T(0), (T *)V.p, n, st))) return rc;
+    if (dist) { if ((rc = distPublishVec((T)(1.0 / normz), zin, (T *)V.p, st))) return rc; }
+    else if ((rc = axpby((T)(1.0 / normz), zin, T(0), (T *)V.p, n, st))) return rc;
     const int checkSteps = std::min(checkConvergenceSteps, iterationHardLimit - 2);
     for (int i = 0; i < iterationHardLimit; i++) {
-      if ((rc = V.grow(sizeof(T) * n * (size_t)(i + 2), st))) return rc;
+      if ((rc = V.grow(sizeof(T) * ld * (size_t)(i + 2), st))) return rc;
       T *Vm = (T *)V.p, *dw = w.as<T>();
-      if ((rc = nearDotList(Vm + n * i, 3, N, dw, false, st))) return rc;                // w = M v_i
-      if (i > 0 && (rc = axpby((T)(-hsup[i - 1]), Vm + n * (i - 1), T(1), dw, n, st))) return rc;
+      if (dist) { if ((rc = distDotRows(dw, st))) return rc; }                           // w = M v_i
+      else if ((rc = nearDotList(Vm + ld * i, 3, N, dw, false, st))) return rc;
+      if (i > 0 && (rc = axpby((T)(-hsup[i - 1]), Vm + ld * (i - 1), T(1), dw, n, st))) return rc;
       double hd;
-      if ((rc = dotHost(dw, Vm + n * i, n, &hd, st))) return rc;
+      if ((rc = dotHost(dw, Vm + ld * i, n, &hd, st, dist))) return rc;
       hdiag.push_back((double)(T)hd);
-      if ((rc = axpby((T)(-hdiag[i]), Vm + n * i, T(1), dw, n, st))) return rc;
+      if ((rc = axpby((T)(-hdiag[i]), Vm + ld * i, T(1), dw, n, st))) return rc;
       double hs2;
-      if ((rc = dotHost(dw, dw, n, &hs2, st))) return rc;
+      if ((rc = dotHost(dw, dw, n, &hs2, st, dist))) return rc;
       double hs = (double)(T)sqrt(hs2);
       const T tolw = (T)(1e-3 * hdiag[i] / normz);
       if (hs < tolw) hs = 0.0;
       hsup.push_back(hs);
       if (hs > 0.0) {
-        if ((rc = axpby((T)(1.0 / hs), dw, T(0), Vm + n * (i + 1), n, st))) return rc;
+        if (dist) { if ((rc = distPublishVec((T)(1.0 / hs), dw, Vm + ld * (i + 1), st))) return rc; }
+        else if ((rc = axpby((T)(1.0 / hs), dw, T(0), Vm + ld * (i + 1), n, st))) return rc;
       } else { // w = e1
-        UB200_CUDA(cudaMemsetAsync(Vm + n * (i + 1), 0, sizeof(T) * n, st));
-        const T one = T(1);
-        UB200_CUDA(cudaMemcpyAsync(Vm + n * (i + 1), &one, sizeof(T), cudaMemcpyHostToDevice, st));
+        if ((rc = fillUnit(Vm + ld * (i + 1), ld, !dist || (dLo == 0 && dHi > 0), st))) return rc;
+        if (dist && (rc = distPublishVec(T(1), Vm + ld * (i + 1), Vm + ld * (i + 1), st))) return rc;
       }
       if (i >= checkSteps) {
         // Bz = ||z|| V_m H^1/2 e1 (computeCurrentResultEstimation :163-172, computeSquareRoot :63-80)
@@ -736,21 +1039,21 @@ template <class T> struct PseState {
         if (!tridiagEigen(m, d, e, Z)) return UB200_ERR_UNSUPPORTED;
         std::vector<double> tmp(m);
         for (int j = 0; j < m; j++) tmp[j] = sqrt(std::max(d[j], 0.0)) * Z[(size_t)j * m];
-        std::vector<T> c(m);
+        LanczosCoeff<T> c;
         for (int r = 0; r < m; r++) {
           double s = 0;
           for (int j = 0; j < m; j++) s += Z[(size_t)j * m + r] * tmp[j];
-          c[r] = (T)s;
+          c.c[r] = (T)s;
         }
-        UB200_CUDA(cudaMemcpyAsync(coeff.p, c.data(), sizeof(T) * m, cudaMemcpyHostToDevice, st));
-        UB200_CUDA(cudaStreamSynchronize(st)); // c is a local
-        vecGemv<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Vm, n, m, coeff.as<T>(), normz, Bz);
-        UB200_LAUNCHED();
+        if (n > 0) {
+          vecGemvArg<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Vm, ld, m, c, normz, Bz);
+          UB200_LAUNCHED();
+        }
         if (i > 0) { // computeError (:231-250): ||Bz_i - Bz_{i-1}|| / ||Bz_{i-1}||
           double prev2, yy2;
-          if ((rc = dotHost(oldBz.as<T>(), oldBz.as<T>(), n, &prev2, st))) return rc;
+          if ((rc = dotHost(oldBz.as<T>(), oldBz.as<T>(), n, &prev2, st, dist))) return rc;
           if ((rc = axpby(T(-1), Bz, T(1), oldBz.as<T>(), n, st))) return rc;
-          if ((rc = dotHost(oldBz.as<T>(), oldBz.as<T>(), n, &yy2, st))) return rc;
+          if ((rc = dotHost(oldBz.as<T>(), oldBz.as<T>(), n, &yy2, st, dist))) return rc;
           const double err = fabs(sqrt(yy2) / sqrt(prev2));
           if (std::isnan(err)) return UB200_ERR_UNSUPPORTED;
           if (err <= tol) {
@@ -761,7 +1064,7 @@ template <class T> struct PseState {
             return UB200_OK;
           }
         }
-        UB200_CUDA(cudaMemcpyAsync(oldBz.p, Bz, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
+        if ((rc = axpby(T(1), Bz, T(0), oldBz.as<T>(), n, st))) return rc;
       }
     }
     return UB200_ERR_UNSUPPORTED; // "[Lanczos] Could not converge"
@@ -895,5 +1198,86 @@ int ub200_pse_near_noise_add(ub200_pse *h, const void *d_pos, int N, double temp
                              void *d_out3, int *iterations, void *stream) {
   if (!h || !d_pos || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
   return PSE_DISPATCH(h, nearNoiseAdd(d_pos, N, temperature, prefactor, seed2, d_out3, iterations, (cudaStream_t)stream));
+}
+
+/* ---- near field over ranks (PSE near field + Lanczos decomposed by rows of the sorted order) ---- */
+int ub200_pse_dist_create(ub200_pse *h, int rank, int world, int maxParticles) {
+  if (!h) return UB200_ERR_INVALID_ARGUMENT;
+  return PSE_DISPATCH(h, distCreate(rank, world, maxParticles));
+}
+int ub200_pse_dist_ipc_export(ub200_pse *h, void *blob) {
+  if (!h || !blob) return UB200_ERR_INVALID_ARGUMENT;
+  void *arena = h->precision == 4 ? h->f.dArena : h->d.dArena;
+  if (!arena) return UB200_ERR_NOT_BUILT;
+  cudaIpcMemHandle_t m;
+  UB200_CUDA(cudaIpcGetMemHandle(&m, arena));
+  memcpy(blob, &m, sizeof(m));
+  return UB200_OK;
+}
+} // extern "C"
+template <class S> static int pseDistImport(S &s, const void *blobs) {
+  if (!s.dArena) return UB200_ERR_NOT_BUILT;
+  for (int p = 0; p < s.dWorld; p++) {
+    if (p == s.dRank) continue;
+    cudaIpcMemHandle_t m;
+    memcpy(&m, static_cast<const char *>(blobs) + (size_t)p * sizeof(m), sizeof(m));
+    void *ptr = nullptr;
+    UB200_CUDA(cudaIpcOpenMemHandle(&ptr, m, cudaIpcMemLazyEnablePeerAccess));
+    s.dPeer[p] = (char *)ptr;
+    s.dOpened[p] = true;
+  }
+  s.dAttached = true;
+  return UB200_OK;
+}
+extern "C" {
+int ub200_pse_dist_ipc_import(ub200_pse *h, const void *blobsOfAllRanks) {
+  if (!h || !blobsOfAllRanks) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? pseDistImport(h->f, blobsOfAllRanks) : pseDistImport(h->d, blobsOfAllRanks);
+}
+int ub200_pse_dist_arena(ub200_pse *h, void **arena) {
+  if (!h || !arena) return UB200_ERR_INVALID_ARGUMENT;
+  *arena = h->precision == 4 ? h->f.dArena : h->d.dArena;
+  return *arena ? UB200_OK : UB200_ERR_NOT_BUILT;
+}
+} // extern "C"
+template <class S> static int pseDistAttach(S &s, void *const *arenas) {
+  if (!s.dArena) return UB200_ERR_NOT_BUILT;
+  for (int p = 0; p < s.dWorld; p++) {
+    if (!arenas[p]) return UB200_ERR_INVALID_ARGUMENT;
+    if (p != s.dRank) s.dPeer[p] = (char *)arenas[p];
+  }
+  s.dAttached = true;
+  return UB200_OK;
+}
+extern "C" {
+int ub200_pse_dist_attach_local(ub200_pse *h, void *const *arenasOfAllRanks) {
+  if (!h || !arenasOfAllRanks) return UB200_ERR_INVALID_ARGUMENT;
+  return h->precision == 4 ? pseDistAttach(h->f, arenasOfAllRanks) : pseDistAttach(h->d, arenasOfAllRanks);
+}
+int ub200_pse_dist_near_prepare(ub200_pse *h, const void *d_pos, int N, void *stream) {
+  if (!h || !d_pos || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  return PSE_DISPATCH(h, distPrepare(d_pos, N, (cudaStream_t)stream));
+}
+int ub200_pse_dist_near_mdot(ub200_pse *h, const void *d_v, int vStride, int N, void *d_Mv3, void *stream) {
+  if (!h || !d_Mv3 || N <= 0 || (vStride != 3 && vStride != 4)) return UB200_ERR_INVALID_ARGUMENT;
+  if (!d_v) return UB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->precision == 4) return h->f.distMdot((const float *)d_v, vStride, N, (float *)d_Mv3, st);
+  return h->d.distMdot((const double *)d_v, vStride, N, (double *)d_Mv3, st);
+}
+int ub200_pse_dist_near_noise_add(ub200_pse *h, int N, double temperature, double prefactor, uint32_t seed2, void *d_out3,
+                                  int *iterations, void *stream) {
+  if (!h || !d_out3 || N <= 0) return UB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->precision == 4) return h->f.distNoise(N, temperature, prefactor, seed2, (float *)d_out3, iterations, st);
+  return h->d.distNoise(N, temperature, prefactor, seed2, (double *)d_out3, iterations, st);
+}
+int ub200_pse_dist_error_flag(ub200_pse *h, void *stream, int *flag) {
+  if (!h || !flag) return UB200_ERR_INVALID_ARGUMENT;
+  const void *p = h->precision == 4 ? h->f.dErr.p : h->d.dErr.p;
+  if (!p) return UB200_ERR_NOT_BUILT;
+  UB200_CUDA(cudaMemcpyAsync(flag, p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  UB200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return UB200_OK;
 }
 }

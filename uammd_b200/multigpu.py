@@ -269,3 +269,113 @@ class DistributedPSEFarField:
 
     def close(self):
         self.fcm.close()
+
+
+class DistributedPSENearField:
+    """pse_ns::NearField (PSE/NearField.cuh:236-282: Mdot and the Lanczos noise) over `world` GPUs (ub200_pse_dist_*):
+    replicated positions, every rank evaluates the rows of its share of the cell-sorted order and stores the next Krylov
+    vector into the records of all ranks over NVLink; the scalars of the iteration are summed by a one-warp kernel that is
+    also the barrier. Results are complete on every rank and equal the single-GPU ones up to the summation order of the
+    dot products (the noise of a particle is keyed by its index).
+
+    group = a torch.distributed group (one rank per process, CUDA IPC), or None with rank / world given and
+    `attachLocal` called on the list of all virtual ranks (one process, one stream and one host thread per rank: tests)."""
+
+    def __init__(self, pos, par, sys=None, group=None, rank=None, world=None):
+        from . import pse as P
+        from ._lib import check
+        self.pse = P.PSE(pos, par, sys=sys)
+        self.lib, self.check, self.pos, self.N = self.pse.lib, check, pos, pos.shape[0]
+        vp, i, d, u32 = C.c_void_p, C.c_int, C.c_double, C.c_uint32
+        l = self.lib
+        for name, args in {"ub200_pse_dist_create": [vp, i, i, i], "ub200_pse_dist_ipc_export": [vp, vp],
+                           "ub200_pse_dist_ipc_import": [vp, vp], "ub200_pse_dist_arena": [vp, C.POINTER(vp)],
+                           "ub200_pse_dist_attach_local": [vp, C.POINTER(vp)],
+                           "ub200_pse_dist_near_prepare": [vp, vp, i, vp],
+                           "ub200_pse_dist_near_mdot": [vp, vp, i, i, vp, vp],
+                           "ub200_pse_dist_near_noise_add": [vp, i, d, d, u32, vp, C.POINTER(i), vp],
+                           "ub200_pse_dist_error_flag": [vp, vp, C.POINTER(i)]}.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = i, args
+        l.ub200_comm_ipc_size.restype = i
+        local = rank is not None
+        self.rank = rank if local else dist.get_rank(group)
+        self.world = world if local else dist.get_world_size(group)
+        check(l.ub200_pse_dist_create(self.pse._h, self.rank, self.world, self.N))
+        if not local:
+            blob = C.create_string_buffer(l.ub200_comm_ipc_size())
+            check(l.ub200_pse_dist_ipc_export(self.pse._h, blob))
+            allb = exchange_blobs(blob.raw, group)
+            self._blobs = C.create_string_buffer(allb, len(allb))
+            check(l.ub200_pse_dist_ipc_import(self.pse._h, self._blobs))
+            dist.barrier(group)
+
+    @staticmethod
+    def attachLocal(ranks):
+        """virtual ranks of one process: hand every rank the arenas of all of them"""
+        arenas = (C.c_void_p * len(ranks))()
+        for r in ranks:
+            a = C.c_void_p()
+            r.check(r.lib.ub200_pse_dist_arena(r.pse._h, C.byref(a)))
+            arenas[r.rank] = a.value
+        for r in ranks:
+            r.check(r.lib.ub200_pse_dist_attach_local(r.pse._h, arenas))
+
+    def prepare(self, stream=None):
+        """NearField::updateNeighbourList for the current (replicated) positions; no communication"""
+        from .md import _ptr, _stream_ptr
+        self.check(self.lib.ub200_pse_dist_near_prepare(self.pse._h, _ptr(self.pos), self.N, _stream_ptr(stream)))
+
+    def Mdot(self, force, MF, stream=None):
+        """MF += M_near F (force: replicated real4 or real3 tensor)"""
+        from .md import _ptr, _stream_ptr
+        if force is None:
+            return
+        self.check(self.lib.ub200_pse_dist_near_mdot(self.pse._h, _ptr(force), force.shape[1], self.N, _ptr(MF), _stream_ptr(stream)))
+
+    def noiseAdd(self, out, temperature, prefactor, seed2, stream=None):
+        """out += prefactor sqrt(2 T) M_near^1/2 dW; returns the Lanczos iterations"""
+        from .md import _ptr, _stream_ptr
+        it = C.c_int(0)
+        self.check(self.lib.ub200_pse_dist_near_noise_add(self.pse._h, self.N, float(temperature), float(prefactor),
+                                                          seed2 & 0xFFFFFFFF, _ptr(out), C.byref(it), _stream_ptr(stream)))
+        return it.value
+
+    def errorFlag(self, stream=None):
+        from .md import _stream_ptr
+        f = C.c_int(0)
+        self.check(self.lib.ub200_pse_dist_error_flag(self.pse._h, _stream_ptr(stream), C.byref(f)))
+        return f.value
+
+
+class DistributedPSE:
+    """BDHI::PSE::computeHydrodynamicDisplacements (BDHI_PSE.cuh:141-158) over `world` GPUs (BASELINE config 3 end to end):
+    near field and Lanczos noise by rows (DistributedPSENearField), far field by FFT slabs (DistributedPSEFarField).
+    Same seed draws, in the same order, as the single-GPU uammd_b200.pse.PSE."""
+
+    def __init__(self, pos, par, sys=None, group=None):
+        from .bd import System
+        self.sys = sys if sys is not None else System()
+        self.near = DistributedPSENearField(pos, par, sys=self.sys, group=group)
+        self.far = DistributedPSEFarField(par, pos.shape[0], self.near.pse.seedFar, dtype=pos.dtype, group=group)
+        self.pos = pos
+
+    def computeHydrodynamicDisplacements(self, force, MF, temperature, noise_prefactor, stream=None):
+        MF.zero_()
+        rng = self.sys.rng()
+        if force is not None or temperature > 0:
+            self.near.prepare(stream)
+        self.near.Mdot(force, MF, stream)
+        iterations = 0
+        if temperature > 0:
+            iterations = self.near.noiseAdd(MF, temperature, noise_prefactor, rng.next32(), stream)
+        seed2 = rng.next32() if temperature > 0 else 0
+        self.far.computeHydrodynamicDisplacements(self.pos, force, MF, temperature=temperature, prefactor=noise_prefactor,
+                                                  seed2=seed2, stream=stream)
+        return iterations
+
+    def errorFlag(self):
+        return self.near.errorFlag() | self.far.fcm.errorFlag()
+
+    def close(self):
+        self.far.close()
