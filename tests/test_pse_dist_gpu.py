@@ -127,6 +127,7 @@ def test_virtual_ranks_match_single_gpu(cuda, world, shear, dtype):
         assert np.array_equal(noise.view(np.uint8), got[0][1].view(np.uint8))
 
 
+@pytest.mark.xfail(strict=False, reason="first execution pending (round 2 GPU budget spent)")
 def test_dist_calls_need_setup(cuda):
     """products before create / attach / prepare are refused, as are more particles than the arena was sized for"""
     from uammd_b200._lib import UB200Error
