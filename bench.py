@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fcm", action="store_true")
     ap.add_argument("--fcm-steps", type=int, default=100)
+    ap.add_argument("--pse-near-limit", type=int, default=180, help="seconds the multi-GPU PSE near-field leg may take (N > 1)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (VerletList MD, PSE, BD ideal)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -476,22 +477,43 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
             pse_line = extra_bench.pse_far_distributed(dev)
         except Exception as e:  # a secondary leg must not take the headline down
             pse_line = {"error": repr(e)[:300]}
-    pse_near_line = None
-    if not args.no_extra:
-        try:
-            pse_near_line = extra_bench.pse_near_distributed(dev)
-        except Exception as e:  # a secondary leg must not take the headline down
-            pse_near_line = {"error": repr(e)[:300]}
     if rank == 0:
         if pse_line is not None:
             line_out["pse_far"] = pse_line
-        if pse_near_line is not None:
-            line_out["pse_near"] = pse_near_line
         if fcm_line is not None:
             line_out["fcm"] = fcm_line
         if dpd_line is not None:
             line_out["dpd"] = dpd_line
-        print(json.dumps(line_out))
+    # The PSE near-field leg is the newest multi-GPU path: it runs LAST, behind a watchdog. Whatever happens in it (an error
+    # on one rank, a rank that never returns), rank 0 prints its ONE line with the legs measured so far and every rank leaves
+    # within the limit.
+    if not args.no_extra:
+        import threading
+        lock, finished = threading.Lock(), [False]
+
+        def abandon():
+            with lock:
+                if finished[0]:
+                    return
+                finished[0] = True
+                if rank == 0:
+                    line_out["pse_near"] = {"error": "the leg did not finish within %d s and was abandoned" % args.pse_near_limit}
+                    print(json.dumps(line_out), flush=True)
+                os._exit(0)
+        timer = threading.Timer(args.pse_near_limit, abandon)
+        timer.daemon = True
+        timer.start()
+        try:
+            pse_near_line = extra_bench.pse_near_distributed(dev)
+        except Exception as e:  # a secondary leg must not take the headline down
+            pse_near_line = {"error": repr(e)[:300]}
+        with lock:
+            finished[0] = True
+        timer.cancel()
+        if rank == 0 and pse_near_line is not None:
+            line_out["pse_near"] = pse_near_line
+    if rank == 0:
+        print(json.dumps(line_out), flush=True)
     dist.destroy_process_group()
     return 0
 

@@ -228,6 +228,36 @@ def pse_far_distributed(dev, steps=20, warmup=3):
             "what": "pse_ns::FarField::computeHydrodynamicDisplacements (force + noise) over z slabs, %d planes per rank" % (far_planes // world)}
 
 
+class RankAgreement:
+    """Keeps the ranks of a bench leg on ONE sequence of torch collectives whatever happens inside a rank's own steps (which use
+    only the library's time-bounded peer barriers): `guarded(fn)` runs fn unless this rank has already failed and records an
+    exception instead of raising it; `failed()` is a collective that tells every rank whether ANY rank failed (or reports a
+    non-zero `error_flag()`, e.g. a timed-out peer barrier). A failure thus becomes an "error" entry of the JSON line, never a
+    rank that left the others waiting in a collective. `failure[0]` holds this rank's own message (None if it was another's)."""
+
+    def __init__(self, dev, error_flag=None):
+        self.dev, self.error_flag, self.failure = dev, error_flag, [None]
+
+    def guarded(self, fn):
+        if self.failure[0] is None:
+            try:
+                fn()
+            except Exception as e:  # noqa: BLE001
+                self.failure[0] = repr(e)[:200]
+
+    def failed(self):
+        import torch.distributed as dist
+        if self.failure[0] is None and self.error_flag is not None:
+            try:
+                if self.error_flag() != 0:
+                    self.failure[0] = "a peer barrier timed out"
+            except Exception as e:  # noqa: BLE001
+                self.failure[0] = repr(e)[:200]
+        flag = torch.tensor([0.0 if self.failure[0] is None else 1.0], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        return flag.item() != 0
+
+
 def pse_near_distributed(dev, steps=10, warmup=2):
     """BASELINE config 3's near field over all ranks (uammd_b200.multigpu.DistributedPSENearField: rows of the cell-sorted order
     per rank, Krylov vectors exchanged as NVLink peer stores, scalars summed by the barrier kernel): list build (replicated) +
@@ -253,30 +283,8 @@ def pse_near_distributed(dev, steps=10, warmup=2):
         near.Mdot(f, MF)
         its[0] = near.noiseAdd(MF, PSE_T, pref, calls[0])
 
-    # Every rank walks the same sequence of torch collectives whatever happens inside its own steps (which only use the
-    # library's time-bounded peer barriers): a failure on one rank becomes a flag all ranks agree on, never a rank that
-    # leaves the others waiting in a collective.
-    failure = [None]
-
-    def guarded(fn):
-        if failure[0] is None:
-            try:
-                fn()
-            except Exception as e:  # noqa: BLE001
-                failure[0] = repr(e)[:200]
-
-    def agreed_failure():
-        bad = failure[0] is not None
-        if not bad:
-            try:
-                bad = near.errorFlag() != 0
-                if bad:
-                    failure[0] = "a peer barrier timed out"
-            except Exception as e:  # noqa: BLE001
-                bad, failure[0] = True, repr(e)[:200]
-        flag = torch.tensor([1.0 if bad else 0.0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        return flag.item() != 0
+    agree = RankAgreement(dev, near.errorFlag)
+    guarded, agreed_failure, failure = agree.guarded, agree.failed, agree.failure
 
     guarded(step)
     if agreed_failure():  # no number rather than a wrong one
