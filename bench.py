@@ -488,28 +488,11 @@ def main_distributed(args, dev, world, rank, local, N, Lb, pos, vel, pot, box):
     # on one rank, a rank that never returns), rank 0 prints its ONE line with the legs measured so far and every rank leaves
     # within the limit.
     if not args.no_extra:
-        import threading
-        lock, finished = threading.Lock(), [False]
-
-        def abandon():
-            with lock:
-                if finished[0]:
-                    return
-                finished[0] = True
-                if rank == 0:
-                    line_out["pse_near"] = {"error": "the leg did not finish within %d s and was abandoned" % args.pse_near_limit}
-                    print(json.dumps(line_out), flush=True)
-                os._exit(0)
-        timer = threading.Timer(args.pse_near_limit, abandon)
-        timer.daemon = True
-        timer.start()
-        try:
-            pse_near_line = extra_bench.pse_near_distributed(dev)
-        except Exception as e:  # a secondary leg must not take the headline down
-            pse_near_line = {"error": repr(e)[:300]}
-        with lock:
-            finished[0] = True
-        timer.cancel()
+        def abandoned():
+            if rank == 0:
+                line_out["pse_near"] = {"error": "the leg did not finish within %d s and was abandoned" % args.pse_near_limit}
+                print(json.dumps(line_out), flush=True)
+        pse_near_line = extra_bench.run_bounded(args.pse_near_limit, lambda: extra_bench.pse_near_distributed(dev), abandoned)
         if rank == 0 and pse_near_line is not None:
             line_out["pse_near"] = pse_near_line
     if rank == 0:

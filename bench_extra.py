@@ -7,6 +7,7 @@ each next to the unmodified reference's own CUDA path (oracle/_ref binaries) in 
 import json
 import math
 import os
+import sys
 import subprocess
 import tempfile
 
@@ -226,6 +227,37 @@ def pse_far_distributed(dev, steps=20, warmup=3):
     return {"metric": "PSE far-field calls/s @1e6 particles, 256^3", "value": 1000.0 / float(t.item()), "unit": "calls/s",
             "ms_per_step": float(t.item()), "n_gpus": world, "scaling": "strong", "single_gpu_ms": single, "barrier_error_flag": err,
             "what": "pse_ns::FarField::computeHydrodynamicDisplacements (force + noise) over z slabs, %d planes per rank" % (far_planes // world)}
+
+
+def run_bounded(limit_s, fn, on_timeout):
+    """fn() under a watchdog: returns fn's result, or {"error": ...} if it raised. If fn has not returned after
+    limit_s seconds, on_timeout() runs on the timer thread (it prints what there is to print) and the PROCESS exits with code 0:
+    a leg that hangs on one rank (a lost peer, a collective nobody else reaches) must not take the lines measured before it
+    down with it. Exactly one of the two ways out is taken."""
+    import threading
+    lock, finished = threading.Lock(), [False]
+
+    def abandon():
+        with lock:
+            if finished[0]:
+                return
+            finished[0] = True
+            try:
+                on_timeout()
+            finally:
+                sys.stdout.flush()
+                os._exit(0)
+    timer = threading.Timer(limit_s, abandon)
+    timer.daemon = True
+    timer.start()
+    try:
+        result = fn()
+    except Exception as e:  # a secondary leg must not take the headline down
+        result = {"error": repr(e)[:300]}
+    with lock:
+        finished[0] = True
+    timer.cancel()
+    return result
 
 
 class RankAgreement:

@@ -60,3 +60,29 @@ def test_ranks_agree_on_a_failure_of_one_of_them(tmp_path):
     assert r0["msg"][2] == "a peer barrier timed out" and r1["msg"][2] is None
     assert r0["msg"][3] is None and "no context" in r1["msg"][3]
     assert r0["ran"] == 5 and r1["ran"] == 3   # rank 1 skipped the step after its failure in scenario 2
+
+
+def _bounded(code, timeout=60):
+    import subprocess
+    import time
+    t0 = time.time()
+    r = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r)\nimport time\nfrom bench_extra import run_bounded\n%s" % (ROOT, code)],
+                       capture_output=True, text=True, timeout=timeout)
+    return r, time.time() - t0
+
+
+def test_watchdog_lets_a_leg_that_returns_through():
+    r, _ = _bounded("print(run_bounded(30, lambda: {'value': 1}, lambda: print('TIMEOUT')))\nprint('after')")
+    assert r.returncode == 0 and r.stdout.splitlines()[-2:] == ["{'value': 1}", "after"] and "TIMEOUT" not in r.stdout
+
+
+def test_watchdog_turns_an_exception_into_an_error_entry():
+    r, _ = _bounded("def f():\n    raise RuntimeError('boom')\nprint(run_bounded(30, f, lambda: print('TIMEOUT')))")
+    assert r.returncode == 0 and "'error'" in r.stdout and "boom" in r.stdout and "TIMEOUT" not in r.stdout
+
+
+def test_watchdog_abandons_a_leg_that_hangs_and_exits_cleanly():
+    """the line is printed once, by the time-out handler, and the process leaves with code 0 well before the leg would end"""
+    r, dt = _bounded("print(run_bounded(1.0, lambda: time.sleep(40), lambda: print('LINE')))\nprint('never')")
+    assert r.returncode == 0 and r.stdout.count("LINE") == 1 and "never" not in r.stdout
+    assert dt < 30
