@@ -108,6 +108,23 @@ int ub200_lj_nbody_f32(const void *d_pos, const int *d_globalIdx, int N, const f
                        const float *params, int ntypes, void *d_force, float *d_energy, float *d_virial, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Path 1b in double precision: PairForces<Potential::LJ, CellList>::sum of a `real = double` build of the reference
+ * (-DDOUBLE_PRECISION, global/defines.h; Interactor/PairForces.cu:43-78 with Radial<LJFunctor>::Transverser,
+ * Potential/RadialPotential.cuh:107-127, LJFunctor::force / energy Potential/Potential.cuh:37-56, Box::apply_pbc
+ * utils/Box.cuh:50-57 - all evaluated in double on the double positions). d_pos: double4[N] (w = type); params: HOST array
+ * [ntypes*ntypes] of {cutOff2, sigma2, epsilonDivSigma2, shift} in double; cutOff: the largest cut-off (what
+ * Potential::getCutOff returns); d_force double4[N], d_energy / d_virial double[N] accumulate (+=) like Transverser::set,
+ * any may be NULL. The neighbour search runs on a single precision copy of the positions with the cut-off padded by the
+ * rounding of that copy; boxes <= 3 cut-offs collapse to one cell (CellList.cuh:117-122) and are summed all-pairs with the
+ * per-pair minimum image. Results equal the reference's up to the order of the sums.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ub200_lj64 ub200_lj64;
+int ub200_lj64_create(ub200_lj64 **out);
+int ub200_lj64_destroy(ub200_lj64 *lj);
+int ub200_lj_sum_f64(ub200_lj64 *lj, const void *d_pos, int N, const double L[3], const int periodic[3], double cutOff,
+                     const double *params, int ntypes, void *d_force, double *d_energy, double *d_virial, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Path 1b': PairForces<Potential::LJ, CellList>::sum in ONE call (Interactor/PairForces.cu:43-78: neighbour-list update +
  * traversal with Radial<LJFunctor>::Transverser, or NBody::transverse for boxes <= 3 cut-offs, :49-53). The forces,
  * energies and virials are the reference's (every pair within the cut-off once, minimum image, self excluded); the

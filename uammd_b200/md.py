@@ -300,6 +300,42 @@ def sortParticles(box, hashCutOff, pos, *properties, stream=None):
     return (order,) + tuple(out)
 
 
+class PairForcesLJ64:
+    """PairForces<Potential::LJ, CellList>::sum of a `real = double` build of the reference (ub200_lj_sum_f64): positions
+    float64 [N,4] (w = type), forces float64 [N,4] / energies / virials float64 [N] accumulated like Transverser::set.
+    `pot` is the same LJ object as for the single precision path; its table rows are widened to double (the reference's
+    processPairParameters would compute them in double from the same inputs: identical whenever cutOff, sigma and epsilon
+    are exact in single precision, as in every BASELINE configuration)."""
+
+    def __init__(self, box, pot):
+        self.box, self.pot = box, pot
+        self._h = C.c_void_p()
+        l = _lib.lib()
+        l.ub200_lj64_create.restype = C.c_int
+        l.ub200_lj64_create.argtypes = [C.POINTER(C.c_void_p)]
+        l.ub200_lj64_destroy.argtypes = [C.c_void_p]
+        l.ub200_lj_sum_f64.restype = C.c_int
+        l.ub200_lj_sum_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double * 3, C.c_int * 3, C.c_double,
+                                       C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        check(l.ub200_lj64_create(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().ub200_lj64_destroy(self._h)
+        except Exception:
+            pass
+
+    def sum(self, pos, force=None, energy=None, virial=None, stream=None):
+        if pos.dtype != torch.float64 or pos.dim() != 2 or pos.shape[1] != 4 or not pos.is_cuda or not pos.is_contiguous():
+            raise UB200Error("PairForcesLJ64.sum: pos must be a contiguous CUDA float64 [N,4] tensor (real4)")
+        table = np.ascontiguousarray(self.pot.table().astype(np.float64))
+        L = (C.c_double * 3)(*[float(x) for x in self.box.boxSize])
+        check(_lib.lib().ub200_lj_sum_f64(self._h, _ptr(pos), pos.shape[0], L, i3([int(p) for p in self.box.periodic]),
+                                          float(self.pot.getCutOff()), table.ctypes.data_as(C.POINTER(C.c_double)),
+                                          self.pot.ntypes, _ptr(force), _ptr(energy), _ptr(virial), _stream_ptr(stream)))
+
+
 class LJEngine:
     """ub200_ljengine: PairForces<Potential::LJ, CellList>::sum in one call (Interactor/PairForces.cu:43-78) over the
     engine's private half-cell list (column traversal, uammd_b200/csrc/lj_column.cu)."""
