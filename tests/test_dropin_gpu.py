@@ -38,6 +38,18 @@ def test_nbody_fallback_dropin_matches_reference():
     assert r["force_vs_ref"] < 1e-5 and r["energy_vs_ref"] < 1e-5 and r["virial_vs_ref"] < 1e-5
 
 
+@pytest.mark.xfail(strict=False, reason="first execution pending (round 2 GPU budget spent)")
+@pytest.mark.parametrize("N,shift", [(4000, 1), (50000, 0)])
+def test_double_precision_pairforces_dropin_matches_reference(N, shift):
+    """A -DDOUBLE_PRECISION UAMMD program: the stock PairForces<LJ> (cell list and transverser in double) next to an
+    Interactor over ub200_lj_sum_f64. Same pair terms in double, another summation order: flat 1e-12 of the largest value.
+    (The program is its own process: the newest kernel cannot disturb the CUDA context of this session.)"""
+    r = _run("dropin_lj64", N, shift)
+    print(r)
+    assert r["fmax"] > 1.0
+    assert r["force_vs_ref"] < 1e-12 and r["energy_vs_ref"] < 1e-12 and r["virial_vs_ref"] < 1e-12
+
+
 def test_langevin_verlet_dropin_matches_reference():
     """benchmark.cu's configuration: VerletNVT::GronbechJensen + PairForces<LJ, VerletList> with both modules swapped."""
     r = _run("dropin_nvt", 32768, 38.0, 20)
