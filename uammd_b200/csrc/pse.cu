@@ -382,17 +382,8 @@ __global__ void __launch_bounds__(256) vecAxpby(T alpha, const T *__restrict__ x
   if (i >= n) return;
   y[i] = beta == T(0) ? alpha * x[i] : alpha * x[i] + beta * y[i];
 }
-// out = scale * V[:, 0:m] c   (V column major, leading dimension n)
-template <class T>
-__global__ void __launch_bounds__(256) vecGemv(const T *__restrict__ V, size_t n, int m, const T *__restrict__ c, T scale,
-                                               T *__restrict__ out) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  T acc = T(0);
-  for (int j = 0; j < m; j++) acc += V[i + n * (size_t)j] * __ldg(c + j);
-  out[i] = scale * acc;
-}
-// the same with the coefficients as a kernel argument (no host-to-device copy on the stream)
+// out = scale * V[:, 0:m] c   (V column major, leading dimension n), the coefficients as a kernel argument (no host-to-device
+// copy on the stream)
 constexpr int kLanczosMaxSteps = 200;
 template <class T> struct LanczosCoeff { T c[kLanczosMaxSteps]; };
 template <class T>
@@ -575,7 +566,7 @@ template <class T> struct PseState {
   const void *listPos = nullptr; // positions the list was built from; set when a caller may reuse it (near_mdot_list)
   // Lanczos
   GrowBuf V;
-  DevBuf w, oldBz, z, partial, scalar, coeff;
+  DevBuf w, oldBz, z, partial, scalar;
   int checkConvergenceSteps = 3, iterationHardLimit = kLanczosMaxSteps, lastRunRequiredSteps = 0;
 
   int init(const ub200_pse_params &par, uint32_t seedNear_, uint32_t seedFar_) {
@@ -663,7 +654,7 @@ template <class T> struct PseState {
   }
   void release() {
     plan.release(); ibm.release(); grid.release(); table.release(); posF.release(); sortedPos.release(); sortedV.release();
-    V.release(); w.release(); oldBz.release(); z.release(); partial.release(); scalar.release(); coeff.release();
+    V.release(); w.release(); oldBz.release(); z.release(); partial.release(); scalar.release();
     if (cl) ub200_celllist_destroy(cl);
     cl = nullptr;
     if (vl) ub200_verletlist_destroy(vl);
